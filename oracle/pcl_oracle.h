@@ -1,0 +1,104 @@
+/*
+ * pcl_oracle.h — C API of the CPU parity oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the upstream PCL 1.8.x / FLANN
+ * semantics that the reference programs (/root/reference/SHOT.cpp, SHOT_demo.cpp, FPFH_demo.cpp,
+ * 6Dpose.cpp, CAD_desc.cpp ...) reach through their PCL calls.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product (libb200reg.so) never
+ * links, loads or calls anything in this directory.
+ *
+ * PARITY UNPINNED: the reference repo holds no tests, golden vectors or data files, and PCL itself is
+ * not vendored nor installed here.  The algorithm is restated from the published
+ * PCL 1.8 / FLANN 1.8 sources as recorded in SURVEY.md Appendix A; every function below cites the
+ * reference call site (file:line under /root/reference) whose behaviour it stands in for and the
+ * upstream PCL file it follows.
+ *
+ * Conventions: points are `float` rows with a caller-given stride (in floats, >= 3; x,y,z first).
+ * Normals are rows of 4 floats (nx, ny, nz, curvature).  All squared distances are float32 sums
+ * dx*dx + dy*dy + dz*dz evaluated left to right with no fused multiply-add (FLANN L2_Simple).
+ */
+#ifndef PCL_ORACLE_H_
+#define PCL_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int index_query;  /* model descriptor / keypoint index  (pcl::Correspondence::index_query) */
+  int index_match;  /* scene descriptor / keypoint index  (pcl::Correspondence::index_match) */
+  float distance;   /* squared L2 descriptor distance */
+} orc_corr;
+
+int orc_num_threads(void);
+void orc_set_num_threads(int n);
+
+/* KdTreeFLANN::radiusSearch (SHOT_VAR.cpp:356; implicit in every Feature::compute with
+ * setRadiusSearch).  Neighbours with d2 < (float)(radius*radius), sorted by (d2, index).
+ * CSR output: offsets[nq+1]; idx/d2 hold up to `cap` entries.  Returns the total number of
+ * neighbours (call once with cap = 0 to size the buffers; offsets is always filled). */
+int64_t orc_radius_search(const float *surf, int n, int sstride, const float *q, int nq, int qstride,
+                          double radius, int64_t *offsets, int *idx, float *d2, int64_t cap);
+
+/* KdTreeFLANN::nearestKSearch (SHOT.cpp:163, Edge_detection.cpp:120; implicit with setKSearch).
+ * k is clamped to the number of finite surface points; rows are sorted by (d2, index); unused
+ * slots are filled with -1 / +inf.  Returns the clamped k. */
+int orc_knn_search(const float *surf, int n, int sstride, const float *q, int nq, int qstride, int k,
+                   int *idx, float *d2);
+
+/* NormalEstimationOMP::compute with setKSearch(k) (SHOT.cpp:302-308, 6Dpose.cpp:275-278,
+ * SHOT_demo.cpp:405-411) or setRadiusSearch(r) (FPFH_demo.cpp:416-420).  Exactly one of k / radius
+ * must be non-zero.  Queries = input cloud, surf = search surface (pass the same array for both, as
+ * every reference call site does).  out: nq rows of 4 floats. */
+int orc_normals(const float *surf, int n, int sstride, const float *q, int nq, int qstride, int k,
+                double radius, const float *viewpoint3, float *out);
+
+/* SHOTLocalReferenceFrameEstimationOMP (built implicitly by SHOTEstimationOMP::initCompute,
+ * SHOT.cpp:360-366).  out: K rows of 9 floats (x axis, y axis, z axis); NaN rows when < 5 valid
+ * neighbours. */
+int orc_shot_lrf(const float *surf, int n, int sstride, const float *kp, int K, int kstride,
+                 double radius, float *out);
+
+/* SHOTEstimationOMP<.., SHOT352>::compute (SHOT.cpp:360-371, SHOT_demo.cpp:419-424, 497-502,
+ * CAD_desc.cpp:341-352).  normals: n rows of 4 floats for the search surface.
+ * desc: K x 352, rf: K x 9. */
+int orc_shot352(const float *surf, const float *normals, int n, int sstride, const float *kp, int K,
+                int kstride, double radius, float *desc, float *rf);
+
+/* FPFHEstimation / FPFHEstimationOMP ::compute (FPFH_demo.cpp:422-428, 505-510;
+ * FPFH_scenes_clustered.cpp:287-293).  q == NULL means input == surface (every reference call
+ * site).  out: nq (or n) rows of 33 floats. */
+int orc_fpfh33(const float *surf, const float *normals, int n, int sstride, const float *q, int nq,
+               int qstride, double radius, float *out);
+
+/* KdTreeFLANN<Descriptor>::setInputCloud + the user matching loop.
+ * mode 1: k = 1, accept iff d2 < thr            (SHOT.cpp:405-423, SHOT_scenes.cpp:359-365)
+ * mode 2: k = 2, accept iff d0/d1 <= 1 (float)   (SHOT_demo.cpp:508-530, FPFH_demo.cpp:516-538)
+ * Returns the number of correspondences written to out (capacity Ks). */
+int orc_match(const float *model, int Km, const float *scene, int Ks, int D, int mode, float thr,
+              orc_corr *out);
+/* OpenMP-parallel variant of the same loop (labelled baseline only; the reference loop is serial). */
+int orc_match_omp(const float *model, int Km, const float *scene, int Ks, int D, int mode, float thr,
+                  orc_corr *out);
+
+/* GeometricConsistencyGrouping::recognize (SHOT.cpp:473-482, 6Dpose.cpp:529-538).
+ * transforms: up to max_inst x 16 floats (row-major 4x4, model -> scene).
+ * inst_offsets: max_inst + 1; inst_corrs: capacity corr_cap.  Returns the number of instances
+ * (all are counted even if the buffers are too small; nothing is written past the capacities). */
+int orc_gc_recognize(const float *model_kp, int Km, int mstride, const float *scene_kp, int Ks,
+                     int sstride, const orc_corr *corrs, int C, double gc_size, int gc_threshold,
+                     float *transforms, int max_inst, int *inst_offsets, orc_corr *inst_corrs,
+                     int corr_cap);
+
+/* Building blocks exposed for unit tests. */
+void orc_eigen33_smallest(const float cov9[9], float *eigenvalue, float evec3[3]); /* pcl::eigen33 */
+void orc_eigh3_f64(const double a9[9], double evals3[3], double evecs9[9]);          /* ascending; columns */
+void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]);      /* rigid, no scale */
+uint32_t orc_mt19937_nth(uint32_t seed, int nth);                                    /* known-answer hook */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

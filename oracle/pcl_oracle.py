@@ -1,0 +1,209 @@
+"""ctypes loader for the CPU parity oracle (TEST INFRASTRUCTURE ONLY — see pcl_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+PARITY UNPINNED: the oracle restates PCL 1.8.x semantics; the reference repo
+holds no golden vectors for this path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Corr(C.Structure):
+    _fields_ = [("index_query", C.c_int), ("index_match", C.c_int), ("distance", C.c_float)]
+
+
+CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libpcl_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("pcl_oracle.cpp", "pcl_oracle.h", "Makefile")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        fp = C.POINTER(C.c_float)
+        ip = C.POINTER(C.c_int)
+        L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_radius_search.restype = C.c_int64
+        L.orc_radius_search.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double,
+                                        C.POINTER(C.c_int64), ip, fp, C.c_int64]
+        L.orc_knn_search.restype = C.c_int
+        L.orc_knn_search.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, ip, fp]
+        L.orc_normals.restype = C.c_int
+        L.orc_normals.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_double, fp, fp]
+        L.orc_shot_lrf.restype = C.c_int
+        L.orc_shot_lrf.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double, fp]
+        L.orc_shot352.restype = C.c_int
+        L.orc_shot352.argtypes = [fp, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double, fp, fp]
+        L.orc_fpfh33.restype = C.c_int
+        L.orc_fpfh33.argtypes = [fp, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double, fp]
+        for f in (L.orc_match, L.orc_match_omp):
+            f.restype = C.c_int
+            f.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(Corr)]
+        L.orc_gc_recognize.restype = C.c_int
+        L.orc_gc_recognize.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.POINTER(Corr), C.c_int,
+                                       C.c_double, C.c_int, fp, C.c_int, ip, C.POINTER(Corr), C.c_int]
+        L.orc_eigen33_smallest.argtypes = [fp, fp, fp]
+        L.orc_eigh3_f64.argtypes = [C.POINTER(C.c_double)] * 3
+        L.orc_umeyama3.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+        L.orc_mt19937_nth.restype = C.c_uint32
+        L.orc_mt19937_nth.argtypes = [C.c_uint32, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
+def radius_search(surf, q, radius):
+    surf, q = _pts(surf), _pts(q)
+    off = np.zeros(len(q) + 1, dtype=np.int64)
+    total = lib().orc_radius_search(_f(surf), len(surf), surf.shape[1], _f(q), len(q), q.shape[1], float(radius),
+                                    off.ctypes.data_as(C.POINTER(C.c_int64)), None, None, 0)
+    idx = np.zeros(max(total, 1), dtype=np.int32)
+    d2 = np.zeros(max(total, 1), dtype=np.float32)
+    lib().orc_radius_search(_f(surf), len(surf), surf.shape[1], _f(q), len(q), q.shape[1], float(radius),
+                            off.ctypes.data_as(C.POINTER(C.c_int64)), _i(idx), _f(d2), total)
+    return off, idx[:total], d2[:total]
+
+
+def knn_search(surf, q, k):
+    surf, q = _pts(surf), _pts(q)
+    idx = np.zeros((len(q), k), dtype=np.int32)
+    d2 = np.zeros((len(q), k), dtype=np.float32)
+    kk = lib().orc_knn_search(_f(surf), len(surf), surf.shape[1], _f(q), len(q), q.shape[1], int(k), _i(idx), _f(d2))
+    return idx, d2, kk
+
+
+def normals(surf, q=None, k=0, radius=0.0, viewpoint=(0.0, 0.0, 0.0)):
+    surf = _pts(surf)
+    q = surf if q is None else _pts(q)
+    out = np.zeros((len(q), 4), dtype=np.float32)
+    vp = np.asarray(viewpoint, dtype=np.float32)
+    rc = lib().orc_normals(_f(surf), len(surf), surf.shape[1], _f(q), len(q), q.shape[1], int(k), float(radius),
+                           _f(vp), _f(out))
+    if rc != 0:
+        raise ValueError("orc_normals: exactly one of k / radius must be non-zero")
+    return out
+
+
+def shot_lrf(surf, kp, radius):
+    surf, kp = _pts(surf), _pts(kp)
+    out = np.zeros((len(kp), 9), dtype=np.float32)
+    lib().orc_shot_lrf(_f(surf), len(surf), surf.shape[1], _f(kp), len(kp), kp.shape[1], float(radius), _f(out))
+    return out
+
+
+def shot352(surf, nrm, kp, radius):
+    surf, kp = _pts(surf), _pts(kp)
+    nrm = np.ascontiguousarray(nrm, dtype=np.float32)
+    assert nrm.shape == (len(surf), 4)
+    desc = np.zeros((len(kp), 352), dtype=np.float32)
+    rf = np.zeros((len(kp), 9), dtype=np.float32)
+    lib().orc_shot352(_f(surf), _f(nrm), len(surf), surf.shape[1], _f(kp), len(kp), kp.shape[1], float(radius),
+                      _f(desc), _f(rf))
+    return desc, rf
+
+
+def fpfh33(surf, nrm, radius, q=None):
+    surf = _pts(surf)
+    nrm = np.ascontiguousarray(nrm, dtype=np.float32)
+    assert nrm.shape == (len(surf), 4)
+    if q is None:
+        out = np.zeros((len(surf), 33), dtype=np.float32)
+        lib().orc_fpfh33(_f(surf), _f(nrm), len(surf), surf.shape[1], None, 0, 0, float(radius), _f(out))
+    else:
+        q = _pts(q)
+        out = np.zeros((len(q), 33), dtype=np.float32)
+        lib().orc_fpfh33(_f(surf), _f(nrm), len(surf), surf.shape[1], _f(q), len(q), q.shape[1], float(radius),
+                         _f(out))
+    return out
+
+
+def match(model, scene, mode=1, thr=0.25, omp=False):
+    model = np.ascontiguousarray(model, dtype=np.float32)
+    scene = np.ascontiguousarray(scene, dtype=np.float32)
+    assert model.shape[1] == scene.shape[1]
+    out = np.zeros(max(len(scene), 1), dtype=CORR_DTYPE)
+    fn = lib().orc_match_omp if omp else lib().orc_match
+    c = fn(_f(model), len(model), _f(scene), len(scene), model.shape[1], int(mode), float(thr),
+           out.ctypes.data_as(C.POINTER(Corr)))
+    return out[:c].copy()
+
+
+def gc_recognize(model_kp, scene_kp, corrs, gc_size, gc_threshold, max_inst=256):
+    model_kp, scene_kp = _pts(model_kp), _pts(scene_kp)
+    corrs = np.ascontiguousarray(corrs, dtype=CORR_DTYPE)
+    T = np.zeros((max_inst, 16), dtype=np.float32)
+    off = np.zeros(max_inst + 1, dtype=np.int32)
+    cap = max(len(corrs), 1) * 2
+    oc = np.zeros(cap, dtype=CORR_DTYPE)
+    n = lib().orc_gc_recognize(_f(model_kp), len(model_kp), model_kp.shape[1], _f(scene_kp), len(scene_kp),
+                               scene_kp.shape[1], corrs.ctypes.data_as(C.POINTER(Corr)), len(corrs),
+                               float(gc_size), int(gc_threshold), _f(T), max_inst, _i(off),
+                               oc.ctypes.data_as(C.POINTER(Corr)), cap)
+    n = min(n, max_inst)
+    return T[:n].reshape(n, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(n)]
+
+
+def eigen33_smallest(cov):
+    cov = np.ascontiguousarray(cov, dtype=np.float32).reshape(9)
+    ev = np.zeros(1, dtype=np.float32)
+    vec = np.zeros(3, dtype=np.float32)
+    lib().orc_eigen33_smallest(_f(cov), _f(ev), _f(vec))
+    return float(ev[0]), vec
+
+
+def eigh3(a):
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(9)
+    w = np.zeros(3)
+    v = np.zeros(9)
+    dp = C.POINTER(C.c_double)
+    lib().orc_eigh3_f64(a.ctypes.data_as(dp), w.ctypes.data_as(dp), v.ctypes.data_as(dp))
+    return w, v.reshape(3, 3)
+
+
+def umeyama3(src, dst):
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.ascontiguousarray(dst, dtype=np.float64)
+    T = np.zeros(16)
+    dp = C.POINTER(C.c_double)
+    lib().orc_umeyama3(src.ctypes.data_as(dp), dst.ctypes.data_as(dp), len(src), T.ctypes.data_as(dp))
+    return T.reshape(4, 4)
+
+
+def mt19937_nth(seed, nth):
+    return int(lib().orc_mt19937_nth(seed, nth))
