@@ -1,0 +1,362 @@
+"""ctypes mirror of include/b200reg.h (the C ABI of libb200reg.so).
+
+Tests and bench.py call the CUDA path through this module, i.e. through the same entry points the
+PCL-style C++ adapters (include/pcl_b200/) bind.  Nothing here computes anything: if the shared
+library is missing or no B200 is present the calls raise — there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200reg.so")
+_LIB = None
+
+CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_NODEVICE = 0, -1, -2, -3, -4, -5
+
+EXPORTS = [
+    "b200_ctx_create", "b200_ctx_destroy", "b200_ctx_sync", "b200_last_error", "b200_abi_version",
+    "b200_ctx_launch_count", "b200_cloud_create", "b200_dev_cloud_create", "b200_cloud_destroy", "b200_cloud_size",
+    "b200_radius_search", "b200_knn_search", "b200_normals", "b200_dev_normals", "b200_shot_lrf", "b200_shot352",
+    "b200_dev_shot352", "b200_fpfh33", "b200_dev_fpfh33", "b200_match", "b200_dev_match", "b200_gc_recognize",
+    "b200_model_create_shot", "b200_model_destroy", "b200_model_size", "b200_model_download",
+    "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
+]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libb200reg error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Corr(C.Structure):
+    _fields_ = [("index_query", C.c_int), ("index_match", C.c_int), ("distance", C.c_float)]
+
+
+class ShotParams(C.Structure):
+    _fields_ = [("normal_k", C.c_int), ("normal_radius", C.c_double), ("descr_radius", C.c_double),
+                ("match_mode", C.c_int), ("match_thr", C.c_float), ("gc_size", C.c_double),
+                ("gc_threshold", C.c_int), ("max_instances", C.c_int)]
+
+
+def shot_params(normal_k=10, normal_radius=0.0, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02,
+                gc_threshold=2, max_instances=256):
+    return ShotParams(int(normal_k), float(normal_radius), float(descr_radius), int(match_mode), float(match_thr),
+                      float(gc_size), int(gc_threshold), int(max_instances))
+
+
+def lib():
+    """Loads libb200reg.so; raises (loudly) if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libb200reg.so is missing (%s): build it with __graft_entry__.build(); "
+                               "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
+        i, d, f = C.c_int, C.c_double, C.c_float
+        sig = {
+            "b200_ctx_create": [C.POINTER(vp), i, vp],
+            "b200_ctx_destroy": [vp],
+            "b200_ctx_sync": [vp],
+            "b200_cloud_create": [vp, fp, i, i, C.POINTER(vp)],
+            "b200_dev_cloud_create": [vp, vp, i, i, C.POINTER(vp)],
+            "b200_cloud_destroy": [vp],
+            "b200_cloud_size": [vp],
+            "b200_radius_search": [vp, vp, fp, i, i, d, C.POINTER(C.c_int64), ip, fp, C.c_int64,
+                                   C.POINTER(C.c_int64)],
+            "b200_knn_search": [vp, vp, fp, i, i, i, ip, fp, ip],
+            "b200_normals": [vp, vp, fp, i, i, i, d, fp, fp],
+            "b200_dev_normals": [vp, vp, vp, i, i, i, d, fp, vp],
+            "b200_shot_lrf": [vp, vp, fp, i, i, d, fp],
+            "b200_shot352": [vp, vp, fp, fp, i, i, d, fp, fp],
+            "b200_dev_shot352": [vp, vp, vp, vp, i, i, d, vp, vp],
+            "b200_fpfh33": [vp, vp, fp, fp, i, i, d, fp],
+            "b200_dev_fpfh33": [vp, vp, vp, vp, i, i, d, vp],
+            "b200_match": [vp, fp, i, fp, i, i, i, f, C.POINTER(Corr), ip],
+            "b200_dev_match": [vp, vp, i, vp, i, i, i, f, vp, vp],
+            "b200_gc_recognize": [vp, fp, i, i, fp, i, i, C.POINTER(Corr), i, d, i, fp, i, ip, C.POINTER(Corr), i, ip],
+            "b200_model_create_shot": [vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), C.POINTER(vp)],
+            "b200_model_destroy": [vp],
+            "b200_model_size": [vp],
+            "b200_model_download": [vp, vp, fp, fp],
+            "b200_register_scene_shot": [vp, vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), fp, ip, C.POINTER(Corr), i,
+                                         ip, C.POINTER(Corr), ip],
+            "b200_dev_register_scene_shot": [vp, vp, vp, i, i, vp, i, i, C.POINTER(ShotParams), vp, vp, vp, vp, i, vp,
+                                             vp, vp, vp],
+            "b200_last_neighbor_stats": [vp, C.POINTER(d), ip],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        L.b200_last_error.argtypes = [vp]
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_abi_version.argtypes = []
+        L.b200_abi_version.restype = C.c_int
+        L.b200_ctx_launch_count.argtypes = [vp]
+        L.b200_ctx_launch_count.restype = C.c_int64
+        _LIB = L
+    return _LIB
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _c(a):
+    return a.ctypes.data_as(C.POINTER(Corr))
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("points must be (n, >=3) float32")
+    return a
+
+
+def _dptr(t):
+    """Device pointer of a torch CUDA tensor (or a raw int)."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+class Cloud:
+    def __init__(self, ctx, handle, n):
+        self.ctx, self.h, self.n = ctx, handle, n
+
+    def close(self):
+        if self.h:
+            lib().b200_cloud_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Model:
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def size(self):
+        return lib().b200_model_size(self.h)
+
+    def download(self):
+        K = self.size
+        desc = np.zeros((K, 352), dtype=np.float32)
+        kp = np.zeros((K, 3), dtype=np.float32)
+        self.ctx._chk(lib().b200_model_download(self.ctx.h, self.h, _f(desc), _f(kp)))
+        return desc, kp
+
+    def close(self):
+        if self.h:
+            lib().b200_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """b200_ctx: one per host thread.  stream: a raw cudaStream_t (int), e.g.
+    torch.cuda.current_stream().cuda_stream, or None for a private stream."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        rc = lib().b200_ctx_create(C.byref(h), int(device), C.c_void_p(stream) if stream else None)
+        if rc != OK:
+            raise B200Error(rc, lib().b200_last_error(None).decode())
+        self.h = h
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise B200Error(rc, lib().b200_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().b200_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self._chk(lib().b200_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(lib().b200_ctx_launch_count(self.h))
+
+    def neighbor_stats(self):
+        m, mx = C.c_double(), C.c_int()
+        lib().b200_last_neighbor_stats(self.h, C.byref(m), C.byref(mx))
+        return m.value, mx.value
+
+    # ---- surface ------------------------------------------------------------------------------
+    def cloud(self, xyz):
+        xyz = _pts(xyz)
+        h = C.c_void_p()
+        self._chk(lib().b200_cloud_create(self.h, _f(xyz), len(xyz), xyz.shape[1], C.byref(h)))
+        return Cloud(self, h, len(xyz))
+
+    def dev_cloud(self, t, n=None, stride=None):
+        n = t.shape[0] if n is None else n
+        stride = t.shape[1] if stride is None else stride
+        h = C.c_void_p()
+        self._chk(lib().b200_dev_cloud_create(self.h, _dptr(t), int(n), int(stride), C.byref(h)))
+        return Cloud(self, h, n)
+
+    def radius_search(self, cloud, q, radius):
+        q = _pts(q)
+        off = np.zeros(len(q) + 1, dtype=np.int64)
+        total = C.c_int64()
+        op = off.ctypes.data_as(C.POINTER(C.c_int64))
+        self._chk(lib().b200_radius_search(self.h, cloud.h, _f(q), len(q), q.shape[1], float(radius), op, None, None, 0,
+                                           C.byref(total)))
+        t = total.value
+        idx = np.zeros(max(t, 1), dtype=np.int32)
+        d2 = np.zeros(max(t, 1), dtype=np.float32)
+        if t:
+            self._chk(lib().b200_radius_search(self.h, cloud.h, _f(q), len(q), q.shape[1], float(radius), op, _i(idx),
+                                               _f(d2), t, C.byref(total)))
+        return off, idx[:t], d2[:t]
+
+    def knn_search(self, cloud, q, k):
+        q = _pts(q)
+        idx = np.zeros((len(q), k), dtype=np.int32)
+        d2 = np.zeros((len(q), k), dtype=np.float32)
+        kf = C.c_int()
+        self._chk(lib().b200_knn_search(self.h, cloud.h, _f(q), len(q), q.shape[1], int(k), _i(idx), _f(d2),
+                                        C.byref(kf)))
+        return idx, d2, kf.value
+
+    # ---- features -----------------------------------------------------------------------------
+    def normals(self, cloud, q=None, k=0, radius=0.0, viewpoint=None):
+        vp = None if viewpoint is None else _f(np.ascontiguousarray(viewpoint, dtype=np.float32))
+        if q is None:
+            out = np.zeros((cloud.n, 4), dtype=np.float32)
+            self._chk(lib().b200_normals(self.h, cloud.h, None, 0, 0, int(k), float(radius), vp, _f(out)))
+        else:
+            q = _pts(q)
+            out = np.zeros((len(q), 4), dtype=np.float32)
+            self._chk(lib().b200_normals(self.h, cloud.h, _f(q), len(q), q.shape[1], int(k), float(radius), vp,
+                                         _f(out)))
+        return out
+
+    def shot_lrf(self, cloud, kp, radius):
+        kp = _pts(kp)
+        out = np.zeros((len(kp), 9), dtype=np.float32)
+        self._chk(lib().b200_shot_lrf(self.h, cloud.h, _f(kp), len(kp), kp.shape[1], float(radius), _f(out)))
+        return out
+
+    def shot352(self, cloud, normals, kp, radius):
+        kp = _pts(kp)
+        normals = np.ascontiguousarray(normals, dtype=np.float32)
+        assert normals.shape == (cloud.n, 4)
+        desc = np.zeros((len(kp), 352), dtype=np.float32)
+        rf = np.zeros((len(kp), 9), dtype=np.float32)
+        self._chk(lib().b200_shot352(self.h, cloud.h, _f(normals), _f(kp), len(kp), kp.shape[1], float(radius),
+                                     _f(desc), _f(rf)))
+        return desc, rf
+
+    def fpfh33(self, cloud, normals, radius, q=None):
+        normals = np.ascontiguousarray(normals, dtype=np.float32)
+        assert normals.shape == (cloud.n, 4)
+        if q is None:
+            out = np.zeros((cloud.n, 33), dtype=np.float32)
+            self._chk(lib().b200_fpfh33(self.h, cloud.h, _f(normals), None, 0, 0, float(radius), _f(out)))
+        else:
+            q = _pts(q)
+            out = np.zeros((len(q), 33), dtype=np.float32)
+            self._chk(lib().b200_fpfh33(self.h, cloud.h, _f(normals), _f(q), len(q), q.shape[1], float(radius),
+                                        _f(out)))
+        return out
+
+    # ---- matching / grouping ------------------------------------------------------------------
+    def match(self, model, scene, mode=1, thr=0.25):
+        model = np.ascontiguousarray(model, dtype=np.float32)
+        scene = np.ascontiguousarray(scene, dtype=np.float32)
+        assert model.ndim == 2 and scene.ndim == 2 and model.shape[1] == scene.shape[1]
+        out = np.zeros(max(len(scene), 1), dtype=CORR_DTYPE)
+        cnt = C.c_int()
+        self._chk(lib().b200_match(self.h, _f(model), len(model), _f(scene), len(scene), model.shape[1], int(mode),
+                                   float(thr), _c(out), C.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    def gc_recognize(self, model_kp, scene_kp, corrs, gc_size, gc_threshold, max_inst=256):
+        model_kp, scene_kp = _pts(model_kp), _pts(scene_kp)
+        corrs = np.ascontiguousarray(corrs, dtype=CORR_DTYPE)
+        T = np.zeros((max_inst, 16), dtype=np.float32)
+        off = np.zeros(max_inst + 1, dtype=np.int32)
+        cap = max(len(corrs), 1)
+        oc = np.zeros(cap, dtype=CORR_DTYPE)
+        n = C.c_int()
+        rc = lib().b200_gc_recognize(self.h, _f(model_kp), len(model_kp), model_kp.shape[1], _f(scene_kp),
+                                     len(scene_kp), scene_kp.shape[1], _c(corrs), len(corrs), float(gc_size),
+                                     int(gc_threshold), _f(T), max_inst, _i(off), _c(oc), cap, C.byref(n))
+        if rc not in (OK, ERR_CAPACITY):
+            self._chk(rc)
+        m = min(n.value, max_inst)
+        return T[:m].reshape(m, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(m)], n.value
+
+    # ---- resident pipeline --------------------------------------------------------------------
+    def model_create_shot(self, xyz, kp, params):
+        xyz, kp = _pts(xyz), _pts(kp)
+        h = C.c_void_p()
+        self._chk(lib().b200_model_create_shot(self.h, _f(xyz), len(xyz), xyz.shape[1], _f(kp), len(kp), kp.shape[1],
+                                               C.byref(params), C.byref(h)))
+        return Model(self, h)
+
+    def register_scene_shot(self, model, scene_xyz, scene_kp, params):
+        """Host buffers in, host results out (b200_register_scene_shot)."""
+        scene_xyz, scene_kp = _pts(scene_xyz), _pts(scene_kp)
+        mi = params.max_instances
+        Ks = len(scene_kp)
+        T = np.zeros((mi, 16), dtype=np.float32)
+        off = np.zeros(mi + 1, dtype=np.int32)
+        ic = np.zeros(max(Ks, 1), dtype=CORR_DTYPE)
+        corrs = np.zeros(max(Ks, 1), dtype=CORR_DTYPE)
+        n_inst, n_corr = C.c_int(), C.c_int()
+        rc = lib().b200_register_scene_shot(self.h, model.h, _f(scene_xyz), len(scene_xyz), scene_xyz.shape[1],
+                                            _f(scene_kp), Ks, scene_kp.shape[1], C.byref(params), _f(T), _i(off),
+                                            _c(ic), max(Ks, 1), C.byref(n_inst), _c(corrs), C.byref(n_corr))
+        if rc not in (OK, ERR_CAPACITY):
+            self._chk(rc)
+        m = min(n_inst.value, mi)
+        return {"transforms": T[:m].reshape(m, 4, 4).copy(),
+                "instances": [ic[off[i]:off[i + 1]].copy() for i in range(m)],
+                "n_instances": n_inst.value, "corrs": corrs[:n_corr.value].copy()}
+
+    def dev_register_scene_shot(self, model, d_xyz, n, stride, d_kp, Ks, kstride, params, out):
+        """All buffers resident (torch CUDA tensors in `out`), asynchronous (b200_dev_register_scene_shot)."""
+        self._chk(lib().b200_dev_register_scene_shot(
+            self.h, model.h, _dptr(d_xyz), int(n), int(stride), _dptr(d_kp), int(Ks), int(kstride), C.byref(params),
+            _dptr(out["transforms"]), _dptr(out["inst_offsets"]), _dptr(out["inst_counts"]), _dptr(out["inst_corrs"]),
+            int(out["corr_cap"]), _dptr(out["n_inst"]), _dptr(out["corrs"]), _dptr(out["n_corrs"]),
+            _dptr(out.get("desc"))))
+
+    def dev_normals(self, cloud, d_out, k=0, radius=0.0):
+        self._chk(lib().b200_dev_normals(self.h, cloud.h, None, 0, 0, int(k), float(radius), None, _dptr(d_out)))
+
+    def dev_shot352(self, cloud, d_normals, d_kp, K, kstride, radius, d_desc, d_rf=None):
+        self._chk(lib().b200_dev_shot352(self.h, cloud.h, _dptr(d_normals), _dptr(d_kp), int(K), int(kstride),
+                                         float(radius), _dptr(d_desc), _dptr(d_rf)))
+
+    def dev_match(self, d_model, Km, d_scene, Ks, D, mode, thr, d_out, d_count):
+        self._chk(lib().b200_dev_match(self.h, _dptr(d_model), int(Km), _dptr(d_scene), int(Ks), int(D), int(mode),
+                                       float(thr), _dptr(d_out), _dptr(d_count)))

@@ -1,0 +1,589 @@
+// api.cu — the C ABI of libb200reg.so (include/b200reg.h): argument checking, host<->device staging
+// and the resident SHOT registration pipeline.  No torch types, no exceptions across the boundary.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+std::string g_error = "";
+
+int set_device(b200_ctx *ctx) {
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaSetDevice", __FILE__, __LINE__);
+  return B200_OK;
+}
+
+#define API_ENTER(ctx)                        \
+  if (!(ctx)) {                               \
+    g_error = "null context";                 \
+    return B200_ERR_INVALID;                  \
+  }                                           \
+  B200_TRY(set_device(ctx))
+
+template <class T>
+int upload(b200_ctx *ctx, DevBuf<T> &buf, const T *host, size_t count) {
+  B200_TRY(buf.alloc(ctx, count));
+  if (count)
+    B200_CUDA(ctx, cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return B200_OK;
+}
+
+template <class T>
+int download(b200_ctx *ctx, T *host, const T *dev, size_t count) {
+  if (count) B200_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  return B200_OK;
+}
+
+// host rows (stride floats) → device float4
+int upload_points(b200_ctx *ctx, const float *xyz, int n, int stride, DevBuf<float4> &out) {
+  if (n < 0 || stride < 3 || (n > 0 && !xyz)) return ctx->fail(B200_ERR_INVALID, "bad point array");
+  B200_TRY(out.alloc(ctx, (size_t)std::max(n, 1)));
+  if (n == 0) return B200_OK;
+  DevBuf<float> stage;
+  B200_TRY(upload(ctx, stage, xyz, (size_t)n * stride));
+  return pack_points(ctx, stage.p, n, stride, out.p);
+}
+
+int pack_device_points(b200_ctx *ctx, const float *d_xyz, int n, int stride, DevBuf<float4> &out) {
+  if (n < 0 || stride < 3 || (n > 0 && !d_xyz)) return ctx->fail(B200_ERR_INVALID, "bad point array");
+  B200_TRY(out.alloc(ctx, (size_t)std::max(n, 1)));
+  return pack_points(ctx, d_xyz, n, stride, out.p);
+}
+
+int check_params(b200_ctx *ctx, const b200_shot_params *p) {
+  if (!p) return ctx->fail(B200_ERR_INVALID, "null params");
+  if ((p->normal_k != 0) == (p->normal_radius != 0.0))
+    return ctx->fail(B200_ERR_INVALID, "params: exactly one of normal_k / normal_radius must be non-zero");
+  if (!(p->descr_radius > 0.0)) return ctx->fail(B200_ERR_INVALID, "params: descr_radius must be > 0");
+  if (p->match_mode != 1 && p->match_mode != 2) return ctx->fail(B200_ERR_INVALID, "params: match_mode must be 1 or 2");
+  if (p->max_instances < 1) return ctx->fail(B200_ERR_INVALID, "params: max_instances must be >= 1");
+  return B200_OK;
+}
+
+// scene side of the pipeline on resident buffers
+int scene_pipeline(b200_ctx *ctx, const b200_model *model, b200_cloud *scene, const float4 *d_kp, int Ks,
+                   const b200_shot_params *p, float *d_T, int *d_inst_offsets, int *d_inst_counts,
+                   b200_corr *d_inst_corrs, int corr_cap, int *d_n_inst, b200_corr *d_corrs, int *d_n_corrs,
+                   float *d_desc_out) {
+  DevBuf<float> normals, desc_tmp;
+  B200_TRY(normals.alloc(ctx, (size_t)std::max(scene->n, 1) * 4));
+  B200_TRY(dev_normals(ctx, scene, scene->raw.p, scene->n, true, p->normal_k, p->normal_radius, nullptr, normals.p));
+  float *d_desc = d_desc_out;
+  if (!d_desc) {
+    B200_TRY(desc_tmp.alloc(ctx, (size_t)std::max(Ks, 1) * 352));
+    d_desc = desc_tmp.p;
+  }
+  B200_TRY(dev_shot(ctx, scene, normals.p, d_kp, Ks, p->descr_radius, d_desc, nullptr, false));
+  B200_TRY(dev_match(ctx, model->desc.p, model->K, d_desc, Ks, 352, p->match_mode, p->match_thr, d_corrs, d_n_corrs));
+  B200_TRY(dev_gc(ctx, model->kp.p, d_kp, d_corrs, d_n_corrs, Ks, p->gc_size, p->gc_threshold, d_T, p->max_instances,
+                  d_inst_offsets, d_inst_counts, d_inst_corrs, corr_cap, d_n_inst));
+  return B200_OK;
+}
+
+__global__ void unpack_points_kernel(const float4 *__restrict__ in, int n, float *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = in[i];
+  out[(size_t)i * 3 + 0] = v.x;
+  out[(size_t)i * 3 + 1] = v.y;
+  out[(size_t)i * 3 + 2] = v.z;
+}
+
+
+int download_instances(b200_ctx *ctx, const float *d_T, const int *d_offsets, const int *d_counts,
+                              const b200_corr *d_inst_corrs, const int *d_n_inst, int max_inst, int C_cap,
+                              float *transforms, int *inst_offsets, b200_corr *inst_corrs, int corr_cap, int *n_inst) {
+  int found = 0;
+  B200_TRY(download(ctx, &found, d_n_inst, 1));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_inst = found;
+  const int m = std::min(found, max_inst);
+  if (inst_offsets) inst_offsets[0] = 0;
+  if (m > 0) {
+    std::vector<int> offs((size_t)m + 1), cnts((size_t)m);
+    B200_TRY(download(ctx, offs.data(), d_offsets, (size_t)m + 1));
+    B200_TRY(download(ctx, cnts.data(), d_counts, (size_t)m));
+    if (transforms) B200_TRY(download(ctx, transforms, d_T, (size_t)m * 16));
+    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int used = std::min(offs[m], C_cap);
+    std::vector<b200_corr> all((size_t)std::max(used, 1));
+    B200_TRY(download(ctx, all.data(), d_inst_corrs, (size_t)used));
+    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int w = 0;
+    bool overflow = false;
+    for (int i = 0; i < m; ++i) {
+      for (int j = 0; j < cnts[i]; ++j) {
+        if (inst_corrs && w < corr_cap)
+          inst_corrs[w] = all[(size_t)offs[i] + j];
+        else if (inst_corrs)
+          overflow = true;
+        ++w;
+      }
+      if (inst_offsets) inst_offsets[i + 1] = std::min(w, corr_cap);
+    }
+    if (overflow) return ctx->fail(B200_ERR_CAPACITY, "gc: inst_corrs capacity too small");
+  }
+  if (found > max_inst) return ctx->fail(B200_ERR_CAPACITY, "gc: more instances than max_inst");
+  return B200_OK;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+int b200_abi_version(void) { return B200REG_ABI_VERSION; }
+
+const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_error.c_str(); }
+
+int b200_ctx_create(b200_ctx **out, int device, void *stream) {
+  if (!out) {
+    g_error = "b200_ctx_create: null output";
+    return B200_ERR_INVALID;
+  }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libb200reg has no CPU fallback";
+    return B200_ERR_NODEVICE;
+  }
+  if (device < 0 || device >= count) {
+    g_error = "b200_ctx_create: device index out of range";
+    return B200_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_error = std::string("cudaSetDevice/cudaGetDeviceProperties failed: ") + cudaGetErrorString(e);
+    return B200_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_error = "libb200reg is built for sm_100a only; device is " + std::string(prop.name);
+    return B200_ERR_NODEVICE;
+  }
+  b200_ctx *ctx = new (std::nothrow) b200_ctx();
+  if (!ctx) return B200_ERR_NOMEM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      g_error = std::string("cudaStreamCreate failed: ") + cudaGetErrorString(e);
+      delete ctx;
+      return B200_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+  }
+  // keep freed scratch in the pool instead of returning it to the driver between calls
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return B200_OK;
+}
+
+int b200_ctx_destroy(b200_ctx *ctx) {
+  if (!ctx) return B200_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return B200_OK;
+}
+
+int b200_ctx_sync(b200_ctx *ctx) {
+  API_ENTER(ctx);
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs) {
+  if (!ctx) return B200_ERR_INVALID;
+  if (mean_nbrs) *mean_nbrs = ctx->last_mean_nbrs;
+  if (max_nbrs) *max_nbrs = ctx->last_max_nbrs;
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------------ surface */
+int b200_cloud_create(b200_ctx *ctx, const float *xyz, int n, int stride, b200_cloud **out) {
+  API_ENTER(ctx);
+  return cloud_upload(ctx, xyz, n, stride, false, out);
+}
+
+int b200_dev_cloud_create(b200_ctx *ctx, const float *d_xyz, int n, int stride, b200_cloud **out) {
+  API_ENTER(ctx);
+  return cloud_upload(ctx, d_xyz, n, stride, true, out);
+}
+
+int b200_cloud_destroy(b200_cloud *cloud) {
+  if (!cloud) return B200_OK;
+  cudaSetDevice(cloud->ctx->device);
+  delete cloud;
+  return B200_OK;
+}
+
+int b200_cloud_size(const b200_cloud *cloud) { return cloud ? cloud->n : 0; }
+
+int b200_radius_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qstride, double radius,
+                       int64_t *offsets, int *idx, float *d2, int64_t cap, int64_t *total) {
+  API_ENTER(ctx);
+  if (!surf || !offsets || !total || nq < 0 || !(radius > 0.0))
+    return ctx->fail(B200_ERR_INVALID, "radius_search: bad arguments");
+  DevBuf<float4> dq;
+  B200_TRY(upload_points(ctx, q, nq, qstride, dq));
+  const GridView *g;
+  B200_TRY(cloud_grid_for_radius(surf, radius, &g));
+  DevBuf<int> counts;
+  DevBuf<unsigned long long> stats;
+  DevBuf<long long> offs;
+  B200_TRY(counts.alloc(ctx, (size_t)std::max(nq, 1)));
+  B200_TRY(stats.alloc(ctx, 2));
+  B200_TRY(offs.alloc(ctx, (size_t)nq + 1));
+  B200_TRY(dev_radius_count(ctx, *g, dq.p, nq, radius, counts.p, stats.p));
+  if (nq > 0) {
+    B200_TRY(counts_to_offsets_i64(ctx, counts.p, nq, offs.p));
+  } else {
+    B200_CUDA(ctx, cudaMemsetAsync(offs.p, 0, sizeof(long long), ctx->stream));
+  }
+  unsigned long long hstats[2];
+  B200_TRY(download(ctx, hstats, stats.p, 2));
+  B200_TRY(download(ctx, reinterpret_cast<long long *>(offsets), offs.p, (size_t)nq + 1));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *total = offsets[nq];
+  if (cap < *total || !idx || !d2) {
+    if (cap == 0) return B200_OK; /* sizing call */
+    return ctx->fail(B200_ERR_CAPACITY, "radius_search: output capacity too small");
+  }
+  if (*total == 0) return B200_OK;
+  DevBuf<int> didx;
+  DevBuf<float> dd2;
+  B200_TRY(didx.alloc(ctx, (size_t)*total));
+  B200_TRY(dd2.alloc(ctx, (size_t)*total));
+  B200_TRY(dev_radius_fill_sized(ctx, *g, dq.p, nq, radius, (int)hstats[0], offs.p, didx.p, dd2.p));
+  B200_TRY(download(ctx, idx, didx.p, (size_t)*total));
+  B200_TRY(download(ctx, d2, dd2.p, (size_t)*total));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_knn_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qstride, int k, int *idx, float *d2,
+                    int *k_found) {
+  API_ENTER(ctx);
+  if (!surf || nq < 0 || (nq > 0 && (!idx || !d2))) return ctx->fail(B200_ERR_INVALID, "knn_search: bad arguments");
+  DevBuf<float4> dq;
+  B200_TRY(upload_points(ctx, q, nq, qstride, dq));
+  DevBuf<int> didx;
+  DevBuf<float> dd2;
+  B200_TRY(didx.alloc(ctx, (size_t)std::max(nq, 1) * std::max(k, 1)));
+  B200_TRY(dd2.alloc(ctx, (size_t)std::max(nq, 1) * std::max(k, 1)));
+  B200_TRY(dev_knn_search(ctx, surf, dq.p, nq, k, didx.p, dd2.p, k_found));
+  B200_TRY(download(ctx, idx, didx.p, (size_t)nq * k));
+  B200_TRY(download(ctx, d2, dd2.p, (size_t)nq * k));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------------ normals */
+int b200_dev_normals(b200_ctx *ctx, b200_cloud *surf, const float *d_q, int nq, int qstride, int k, double radius,
+                     const float *viewpoint, float *d_out) {
+  API_ENTER(ctx);
+  if (!surf || !d_out) return ctx->fail(B200_ERR_INVALID, "normals: bad arguments");
+  if (!d_q) return dev_normals(ctx, surf, surf->raw.p, surf->n, true, k, radius, viewpoint, d_out);
+  DevBuf<float4> dq;
+  B200_TRY(pack_device_points(ctx, d_q, nq, qstride, dq));
+  return dev_normals(ctx, surf, dq.p, nq, false, k, radius, viewpoint, d_out);
+}
+
+int b200_normals(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qstride, int k, double radius,
+                 const float *viewpoint, float *out) {
+  API_ENTER(ctx);
+  if (!surf || !out) return ctx->fail(B200_ERR_INVALID, "normals: bad arguments");
+  DevBuf<float> dout;
+  if (!q) {
+    nq = surf->n;
+    B200_TRY(dout.alloc(ctx, (size_t)std::max(nq, 1) * 4));
+    B200_TRY(dev_normals(ctx, surf, surf->raw.p, nq, true, k, radius, viewpoint, dout.p));
+  } else {
+    DevBuf<float4> dq;
+    B200_TRY(upload_points(ctx, q, nq, qstride, dq));
+    B200_TRY(dout.alloc(ctx, (size_t)std::max(nq, 1) * 4));
+    B200_TRY(dev_normals(ctx, surf, dq.p, nq, false, k, radius, viewpoint, dout.p));
+  }
+  B200_TRY(download(ctx, out, dout.p, (size_t)nq * 4));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------------ SHOT */
+int b200_shot_lrf(b200_ctx *ctx, b200_cloud *surf, const float *kp, int K, int kstride, double radius, float *out) {
+  API_ENTER(ctx);
+  if (!surf || (K > 0 && !out)) return ctx->fail(B200_ERR_INVALID, "shot_lrf: bad arguments");
+  DevBuf<float4> dkp;
+  B200_TRY(upload_points(ctx, kp, K, kstride, dkp));
+  DevBuf<float> drf;
+  B200_TRY(drf.alloc(ctx, (size_t)std::max(K, 1) * 9));
+  B200_TRY(dev_shot(ctx, surf, nullptr, dkp.p, K, radius, nullptr, drf.p, true));
+  B200_TRY(download(ctx, out, drf.p, (size_t)K * 9));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_dev_shot352(b200_ctx *ctx, b200_cloud *surf, const float *d_normals, const float *d_kp, int K, int kstride,
+                     double radius, float *d_desc, float *d_rf) {
+  API_ENTER(ctx);
+  if (!surf || !d_normals || (K > 0 && !d_desc)) return ctx->fail(B200_ERR_INVALID, "shot352: bad arguments");
+  DevBuf<float4> dkp;
+  B200_TRY(pack_device_points(ctx, d_kp, K, kstride, dkp));
+  return dev_shot(ctx, surf, d_normals, dkp.p, K, radius, d_desc, d_rf, false);
+}
+
+int b200_shot352(b200_ctx *ctx, b200_cloud *surf, const float *normals, const float *kp, int K, int kstride,
+                 double radius, float *desc, float *rf) {
+  API_ENTER(ctx);
+  if (!surf || !normals || (K > 0 && !desc)) return ctx->fail(B200_ERR_INVALID, "shot352: bad arguments");
+  DevBuf<float4> dkp;
+  B200_TRY(upload_points(ctx, kp, K, kstride, dkp));
+  DevBuf<float> dn, ddesc, drf;
+  B200_TRY(upload(ctx, dn, normals, (size_t)surf->n * 4));
+  B200_TRY(ddesc.alloc(ctx, (size_t)std::max(K, 1) * 352));
+  B200_TRY(drf.alloc(ctx, (size_t)std::max(K, 1) * 9));
+  B200_TRY(dev_shot(ctx, surf, dn.p, dkp.p, K, radius, ddesc.p, drf.p, false));
+  B200_TRY(download(ctx, desc, ddesc.p, (size_t)K * 352));
+  if (rf) B200_TRY(download(ctx, rf, drf.p, (size_t)K * 9));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------------ FPFH */
+int b200_dev_fpfh33(b200_ctx *ctx, b200_cloud *surf, const float *d_normals, const float *d_q, int nq, int qstride,
+                    double radius, float *d_out) {
+  API_ENTER(ctx);
+  if (!surf || !d_normals || !d_out) return ctx->fail(B200_ERR_INVALID, "fpfh33: bad arguments");
+  if (!d_q) return dev_fpfh(ctx, surf, d_normals, surf->raw.p, surf->n, true, radius, d_out);
+  DevBuf<float4> dq;
+  B200_TRY(pack_device_points(ctx, d_q, nq, qstride, dq));
+  return dev_fpfh(ctx, surf, d_normals, dq.p, nq, false, radius, d_out);
+}
+
+int b200_fpfh33(b200_ctx *ctx, b200_cloud *surf, const float *normals, const float *q, int nq, int qstride,
+                double radius, float *out) {
+  API_ENTER(ctx);
+  if (!surf || !normals || !out) return ctx->fail(B200_ERR_INVALID, "fpfh33: bad arguments");
+  DevBuf<float> dn, dout;
+  B200_TRY(upload(ctx, dn, normals, (size_t)surf->n * 4));
+  if (!q) {
+    nq = surf->n;
+    B200_TRY(dout.alloc(ctx, (size_t)std::max(nq, 1) * 33));
+    B200_TRY(dev_fpfh(ctx, surf, dn.p, surf->raw.p, nq, true, radius, dout.p));
+  } else {
+    DevBuf<float4> dq;
+    B200_TRY(upload_points(ctx, q, nq, qstride, dq));
+    B200_TRY(dout.alloc(ctx, (size_t)std::max(nq, 1) * 33));
+    B200_TRY(dev_fpfh(ctx, surf, dn.p, dq.p, nq, false, radius, dout.p));
+  }
+  B200_TRY(download(ctx, out, dout.p, (size_t)nq * 33));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------------ matching */
+int b200_dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode,
+                   float thr, b200_corr *d_out, int *d_count) {
+  API_ENTER(ctx);
+  if (!d_count || (Ks > 0 && !d_out)) return ctx->fail(B200_ERR_INVALID, "match: bad arguments");
+  return dev_match(ctx, d_model, Km, d_scene, Ks, D, mode, thr, d_out, d_count);
+}
+
+int b200_match(b200_ctx *ctx, const float *model, int Km, const float *scene, int Ks, int D, int mode, float thr,
+               b200_corr *out, int *count) {
+  API_ENTER(ctx);
+  if (!count || Km < 0 || Ks < 0 || D <= 0 || (Ks > 0 && (!out || !scene)) || (Km > 0 && !model))
+    return ctx->fail(B200_ERR_INVALID, "match: bad arguments");
+  DevBuf<float> dm, ds;
+  DevBuf<b200_corr> dout;
+  DevBuf<int> dcount;
+  B200_TRY(upload(ctx, dm, model, (size_t)Km * D));
+  B200_TRY(upload(ctx, ds, scene, (size_t)Ks * D));
+  B200_TRY(dout.alloc(ctx, (size_t)std::max(Ks, 1)));
+  B200_TRY(dcount.alloc(ctx, 1));
+  B200_TRY(dev_match(ctx, dm.p, Km, ds.p, Ks, D, mode, thr, dout.p, dcount.p));
+  B200_TRY(download(ctx, count, dcount.p, 1));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_TRY(download(ctx, out, dout.p, (size_t)*count));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------------ grouping */
+int b200_gc_recognize(b200_ctx *ctx, const float *model_kp, int Km, int mstride, const float *scene_kp, int Ks,
+                      int sstride, const b200_corr *corrs, int C, double gc_size, int gc_threshold, float *transforms,
+                      int max_inst, int *inst_offsets, b200_corr *inst_corrs, int corr_cap, int *n_inst) {
+  API_ENTER(ctx);
+  if (!n_inst || C < 0 || max_inst < 1 || (C > 0 && !corrs))
+    return ctx->fail(B200_ERR_INVALID, "gc_recognize: bad arguments");
+  *n_inst = 0;
+  if (inst_offsets) inst_offsets[0] = 0;
+  if (C == 0) {
+    // PCL: "no correspondences" → recognize() returns without instances
+    return B200_OK;
+  }
+  for (int i = 0; i < C; ++i)
+    if (corrs[i].index_query < 0 || corrs[i].index_query >= Km || corrs[i].index_match < 0 ||
+        corrs[i].index_match >= Ks)
+      return ctx->fail(B200_ERR_INVALID, "gc_recognize: correspondence index out of range");
+  DevBuf<float4> dm, ds;
+  B200_TRY(upload_points(ctx, model_kp, Km, mstride, dm));
+  B200_TRY(upload_points(ctx, scene_kp, Ks, sstride, ds));
+  DevBuf<b200_corr> dc, dic;
+  DevBuf<int> dC, doffs, dcnts, dn;
+  DevBuf<float> dT;
+  B200_TRY(upload(ctx, dc, corrs, (size_t)C));
+  B200_TRY(upload(ctx, dC, &C, 1));
+  B200_TRY(dic.alloc(ctx, (size_t)C));
+  B200_TRY(doffs.alloc(ctx, (size_t)max_inst + 1));
+  B200_TRY(dcnts.alloc(ctx, (size_t)max_inst));
+  B200_TRY(dn.alloc(ctx, 1));
+  B200_TRY(dT.alloc(ctx, (size_t)max_inst * 16));
+  B200_TRY(dev_gc(ctx, dm.p, ds.p, dc.p, dC.p, C, gc_size, gc_threshold, dT.p, max_inst, doffs.p, dcnts.p, dic.p, C,
+                  dn.p));
+  return download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, max_inst, C, transforms, inst_offsets,
+                            inst_corrs, corr_cap, n_inst);
+}
+
+/* ------------------------------------------------------------------ resident pipeline */
+int b200_model_create_shot(b200_ctx *ctx, const float *xyz, int n, int stride, const float *kp, int K, int kstride,
+                           const b200_shot_params *p, b200_model **out) {
+  API_ENTER(ctx);
+  if (!out) return ctx->fail(B200_ERR_INVALID, "model_create: null output");
+  B200_TRY(check_params(ctx, p));
+  b200_cloud *cloud = nullptr;
+  B200_TRY(cloud_upload(ctx, xyz, n, stride, false, &cloud));
+  b200_model *m = new b200_model();
+  m->ctx = ctx;
+  m->K = K;
+  int rc = B200_OK;
+  do {
+    DevBuf<float> normals;
+    if ((rc = normals.alloc(ctx, (size_t)std::max(n, 1) * 4)) != B200_OK) break;
+    if ((rc = dev_normals(ctx, cloud, cloud->raw.p, n, true, p->normal_k, p->normal_radius, nullptr, normals.p)) !=
+        B200_OK)
+      break;
+    if ((rc = upload_points(ctx, kp, K, kstride, m->kp)) != B200_OK) break;
+    if ((rc = m->desc.alloc(ctx, (size_t)std::max(K, 1) * 352)) != B200_OK) break;
+    if ((rc = dev_shot(ctx, cloud, normals.p, m->kp.p, K, p->descr_radius, m->desc.p, nullptr, false)) != B200_OK)
+      break;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = ctx->fail_cuda(e, "model_create sync", __FILE__, __LINE__);
+  } while (0);
+  delete cloud;
+  if (rc != B200_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return B200_OK;
+}
+
+int b200_model_destroy(b200_model *m) {
+  if (!m) return B200_OK;
+  cudaSetDevice(m->ctx->device);
+  delete m;
+  return B200_OK;
+}
+
+int b200_model_size(const b200_model *m) { return m ? m->K : 0; }
+
+int b200_model_download(b200_ctx *ctx, const b200_model *m, float *desc, float *kp) {
+  API_ENTER(ctx);
+  if (!m) return ctx->fail(B200_ERR_INVALID, "model_download: null model");
+  if (desc) B200_TRY(download(ctx, desc, m->desc.p, (size_t)m->K * 352));
+  DevBuf<float> tmp;
+  if (kp && m->K > 0) {
+    B200_TRY(tmp.alloc(ctx, (size_t)m->K * 3));
+    unpack_points_kernel<<<ceil_div(m->K, 256), 256, 0, ctx->stream>>>(m->kp.p, m->K, tmp.p);
+    B200_LAUNCHED(ctx);
+    B200_TRY(download(ctx, kp, tmp.p, (size_t)m->K * 3));
+  }
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_dev_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float *d_scene_xyz, int n, int stride,
+                                 const float *d_scene_kp, int Ks, int kstride, const b200_shot_params *p,
+                                 float *d_transforms, int *d_inst_offsets, int *d_inst_counts,
+                                 b200_corr *d_inst_corrs, int corr_cap, int *d_n_inst, b200_corr *d_corrs_out,
+                                 int *d_n_corrs, float *d_desc_out) {
+  API_ENTER(ctx);
+  if (!model || !d_transforms || !d_inst_offsets || !d_inst_counts || !d_inst_corrs || !d_n_inst || !d_corrs_out ||
+      !d_n_corrs || Ks < 0)
+    return ctx->fail(B200_ERR_INVALID, "register_scene: bad arguments");
+  B200_TRY(check_params(ctx, p));
+  b200_cloud *scene = nullptr;
+  B200_TRY(cloud_upload(ctx, d_scene_xyz, n, stride, true, &scene));
+  DevBuf<float4> dkp;
+  int rc = pack_device_points(ctx, d_scene_kp, Ks, kstride, dkp);
+  if (rc == B200_OK)
+    rc = scene_pipeline(ctx, model, scene, dkp.p, Ks, p, d_transforms, d_inst_offsets, d_inst_counts, d_inst_corrs,
+                        corr_cap, d_n_inst, d_corrs_out, d_n_corrs, d_desc_out);
+  delete scene;
+  return rc;
+}
+
+int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float *scene_xyz, int n, int stride,
+                             const float *scene_kp, int Ks, int kstride, const b200_shot_params *p, float *transforms,
+                             int *inst_offsets, b200_corr *inst_corrs, int corr_cap, int *n_inst, b200_corr *corrs_out,
+                             int *n_corrs) {
+  API_ENTER(ctx);
+  if (!model || !n_inst || Ks < 0) return ctx->fail(B200_ERR_INVALID, "register_scene: bad arguments");
+  B200_TRY(check_params(ctx, p));
+  *n_inst = 0;
+  if (n_corrs) *n_corrs = 0;
+  b200_cloud *scene = nullptr;
+  B200_TRY(cloud_upload(ctx, scene_xyz, n, stride, false, &scene));
+  int rc = B200_OK;
+  do {
+    DevBuf<float4> dkp;
+    if ((rc = upload_points(ctx, scene_kp, Ks, kstride, dkp)) != B200_OK) break;
+    const int cap = std::max(Ks, 1);
+    DevBuf<b200_corr> dcorrs, dic;
+    DevBuf<int> doffs, dcnts, dn, dnc;
+    DevBuf<float> dT;
+    if ((rc = dcorrs.alloc(ctx, (size_t)cap)) != B200_OK) break;
+    if ((rc = dic.alloc(ctx, (size_t)cap)) != B200_OK) break;
+    if ((rc = doffs.alloc(ctx, (size_t)p->max_instances + 1)) != B200_OK) break;
+    if ((rc = dcnts.alloc(ctx, (size_t)p->max_instances)) != B200_OK) break;
+    if ((rc = dn.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dnc.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dT.alloc(ctx, (size_t)p->max_instances * 16)) != B200_OK) break;
+    if ((rc = scene_pipeline(ctx, model, scene, dkp.p, Ks, p, dT.p, doffs.p, dcnts.p, dic.p, cap, dn.p, dcorrs.p,
+                             dnc.p, nullptr)) != B200_OK)
+      break;
+    int nc = 0;
+    if ((rc = download(ctx, &nc, dnc.p, 1)) != B200_OK) break;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      rc = ctx->fail_cuda(e, "register_scene sync", __FILE__, __LINE__);
+      break;
+    }
+    if (n_corrs) *n_corrs = nc;
+    if (corrs_out && nc > 0) {
+      if ((rc = download(ctx, corrs_out, dcorrs.p, (size_t)nc)) != B200_OK) break;
+    }
+    rc = download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, p->max_instances, cap, transforms, inst_offsets,
+                            inst_corrs, corr_cap, n_inst);
+  } while (0);
+  delete scene;
+  return rc;
+}
+
+} /* extern "C" */

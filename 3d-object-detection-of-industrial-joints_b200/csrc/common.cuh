@@ -1,0 +1,208 @@
+// common.cuh — context, stream-ordered scratch buffers, launch accounting and small device helpers
+// shared by every kernel file of libb200reg.so.  Compiled with --fmad=false: float32 sums that
+// PCL/FLANN evaluate as plain mul/add sequences must not be contracted into FMAs.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/b200reg.h"
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  double last_mean_nbrs = 0.0;
+  int last_max_nbrs = 0;
+  std::string err;
+  void *pinned = nullptr;  // small pinned staging block for tiny readbacks
+  int fail(int code, const char *msg) {
+    err = msg;
+    return code;
+  }
+  int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e),
+             file, line, what);
+    err = buf;
+    return B200_ERR_CUDA;
+  }
+};
+
+#define B200_CUDA(ctx, expr)                                                        \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define B200_TRY(expr)          \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != B200_OK) return rc__; \
+  } while (0)
+
+// After a kernel launch: count it and surface launch-configuration errors.
+#define B200_LAUNCHED(ctx)                                                           \
+  do {                                                                               \
+    (ctx)->launches++;                                                               \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync on the context's stream; the pool keeps memory).
+template <class T>
+struct DevBuf {
+  b200_ctx *ctx = nullptr;
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFreeAsync(p, ctx->stream);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(b200_ctx *c, size_t count) {
+    release();
+    ctx = c;
+    n = count;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), c->stream);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      c->fail_cuda(e, "cudaMallocAsync", __FILE__, __LINE__);
+      return e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA;
+    }
+    return B200_OK;
+  }
+  int zero() {
+    cudaError_t e = cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream);
+    if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaMemsetAsync", __FILE__, __LINE__);
+    return B200_OK;
+  }
+};
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// Uniform grid over a search surface (grid.cu builds it).
+// pts: points in cell-major order, w = original row index (bit pattern of an int).
+// ------------------------------------------------------------------------------------------
+struct GridView {
+  const float4 *pts;
+  const int *cell_start;  // ncell + 1 entries
+  float lox, loy, loz;
+  float h, inv_h;
+  int dx, dy, dz;
+  int n;              // number of indexed (finite) points
+  float coord_scale;  // max |coordinate| of the bounding box (for conservative float margins)
+};
+
+__host__ __device__ __forceinline__ int grid_coord(float v, float lo, float inv_h, int dim) {
+  float f = floorf((v - lo) * inv_h);
+  if (!(f >= 0.0f)) return 0;
+  if (f >= (float)dim) return dim - 1;
+  return (int)f;
+}
+
+// FLANN L2_Simple<float> over x, y, z: ((dx*dx + dy*dy) + dz*dz), no FMA (--fmad=false keeps it so).
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  float d0 = ax - bx;
+  float r = __fmul_rn(d0, d0);
+  float d1 = ay - by;
+  r = __fadd_rn(r, __fmul_rn(d1, d1));
+  float d2 = az - bz;
+  r = __fadd_rn(r, __fmul_rn(d2, d2));
+  return r;
+}
+
+__device__ __forceinline__ int orig_index(const float4 &p) { return __float_as_int(p.w); }
+
+__device__ __forceinline__ float nanf32() { return __int_as_float(0x7fc00000); }
+
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+  return isfinite(x) && isfinite(y) && isfinite(z);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// internal entry points implemented across the .cu files (all asynchronous on ctx->stream unless
+// noted; every pointer is a device pointer)
+// ------------------------------------------------------------------------------------------
+struct DeviceGrid {
+  DevBuf<float4> pts;
+  DevBuf<int> cell_start;
+  GridView view;
+  float cell = 0.f;
+  bool valid = false;
+};
+
+struct b200_cloud {
+  b200_ctx *ctx = nullptr;
+  int n = 0;
+  int n_valid = 0;
+  DevBuf<float4> raw;  // original order, w = 1 (pad)
+  float lo[3], hi[3];  // bounding box of the finite points (host copy)
+  DeviceGrid knn_grid;     // cell sized for k-nearest queries
+  int knn_grid_k = 0;
+  DeviceGrid radius_grid;  // cell sized for fixed-radius queries
+};
+
+struct b200_model {
+  b200_ctx *ctx = nullptr;
+  int K = 0;
+  int D = 352;
+  DevBuf<float> desc;  // K x D
+  DevBuf<float4> kp;   // K keypoints
+};
+
+// scan.cu
+int exclusive_scan_i32(b200_ctx *ctx, const int *d_in, int *d_out, int n, int *d_total /*nullable*/);
+// grid.cu
+int cloud_upload(b200_ctx *ctx, const float *xyz, int n, int stride, bool on_device, b200_cloud **out);
+int cloud_grid_for_knn(b200_cloud *c, int k, const GridView **out);
+int cloud_grid_for_radius(b200_cloud *c, double radius, const GridView **out);
+int pack_points(b200_ctx *ctx, const float *d_xyz, int n, int stride, float4 *d_out);
+// search.cu
+int dev_knn_search(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, int k, int *d_idx, float *d_d2,
+                   int *k_found);
+int dev_radius_count(b200_ctx *ctx, const GridView &g, const float4 *d_q, int nq, double radius, int *d_counts,
+                     unsigned long long *d_stats /* [0]=max, [1]=sum */);
+int dev_radius_fill_sized(b200_ctx *ctx, const GridView &g, const float4 *d_q, int nq, double radius, int max_count,
+                          const long long *d_offsets, int *d_idx, float *d_d2);
+int counts_to_offsets_i64(b200_ctx *ctx, const int *d_counts, int nq, long long *d_offsets);
+int knn_threads_for(int k, size_t *smem_bytes);
+// normals.cu
+int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_is_surface, int k, double radius,
+                const float *vp, float *d_out);
+// shot.cu
+int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 *d_kp, int K, double radius,
+             float *d_desc, float *d_rf, bool lrf_only);
+// fpfh.cu
+int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 *d_q, int nq, bool q_is_surface,
+             double radius, float *d_out);
+// match.cu
+int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
+              b200_corr *d_out, int *d_count);
+// gc.cu
+int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, const b200_corr *d_corrs,
+           const int *d_C, int C_cap, double gc_size, int gc_threshold, float *d_T, int max_inst,
+           int *d_inst_offsets, int *d_inst_counts, b200_corr *d_inst_corrs, int corr_cap, int *d_n_inst);

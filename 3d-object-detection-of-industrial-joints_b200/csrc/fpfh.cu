@@ -1,0 +1,316 @@
+// fpfh.cu — 33-bin Fast Point Feature Histograms.
+//
+// Replaces pcl::FPFHEstimation / FPFHEstimationOMP <PointXYZRGBA, Normal, FPFHSignature33>::compute
+// (FPFH_demo.cpp:422-428 and 505-510, FPFH_scenes_clustered.cpp:287-293 and 379-387).
+//
+// Pass 1 (computeSPFHSignatures): for every surface point that is a neighbour of some query (all
+// points when input == surface, as at every reference call site) the Darboux pair features
+// (pcl::computePairFeatures, float32) of its neighbourhood are binned into 3 x 11 bins.  Each hit adds
+// the same increment 100/(n-1), so the bins are counted as integers in shared memory (warp-level
+// atomics, order independent) and the float32 value PCL reaches by repeated addition is rebuilt
+// exactly from the count.
+// Pass 2 (weightPointSPFHSignature): FPFH(p) = sum over neighbours (d2 != 0) of SPFH(q)/d2, walked in
+// the (d2, index) order FLANN returns so each float32 bin sum keeps PCL's sequence (one lane per
+// bin), then every 11-bin block is rescaled to sum 100 with the float64 running sums kept in PCL's
+// order (one lane per block).
+//
+// Algorithmic HBM traffic per descriptor (surface == keypoints): 32 B point+normal read, 132 B SPFH
+// written and re-read, 132 B FPFH written: ~428 B.
+#include <algorithm>
+
+#include "search.cuh"
+
+namespace {
+
+constexpr int FPFH_THREADS = 128;
+
+__global__ void gather_normals_sorted_kernel(const float4 *__restrict__ sorted_pts, int n,
+                                             const float4 *__restrict__ normals, float4 *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = normals[orig_index(sorted_pts[i])];
+}
+
+__global__ void fill_int_kernel(int *p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// mark every surface point that lies in the neighbourhood of a query
+__global__ void __launch_bounds__(FPFH_THREADS)
+    fpfh_mark_kernel(GridView g, const float4 *__restrict__ q, int nq, float radius, float r2, int *__restrict__ need) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nq) return;
+  const float4 c = q[w];
+  int x0, x1, y0, y1, z0, z1;
+  if (!finite3(c.x, c.y, c.z) || g.n == 0 || !ball_cell_range(g, c.x, c.y, c.z, radius, x0, x1, y0, y1, z0, z1)) return;
+  for (int z = z0; z <= z1; ++z)
+    for (int y = y0; y <= y1; ++y) {
+      const int base = g.dx * (y + g.dy * z);
+      const int s = g.cell_start[base + x0], e = g.cell_start[base + x1 + 1];
+      for (int j = s + lane; j < e; j += 32) {
+        const float4 p = g.pts[j];
+        if (sqdist3(c.x, c.y, c.z, p.x, p.y, p.z) < r2) need[j] = 1;  // indexed by sorted position
+      }
+    }
+}
+
+// pcl::computePairFeatures (features/src/pfh.cpp), float32.  Degenerate pairs yield f1=f2=f3=0
+// (FPFHEstimation::computePairFeatures ignores the return value and still bins them).
+__device__ inline void pair_features(const float4 &p1, const float4 &n1, const float4 &p2, const float4 &n2,
+                                     float &f1, float &f2, float &f3) {
+  float dx = p2.x - p1.x, dy = p2.y - p1.y, dz = p2.z - p1.z;
+  float s = dx * dx;
+  s += dy * dy;
+  s += dz * dz;
+  const float f4 = sqrtf(s);
+  if (f4 == 0.0f) {
+    f1 = f2 = f3 = 0.0f;
+    return;
+  }
+  float ax = n1.x, ay = n1.y, az = n1.z;  // n1_copy
+  float bx = n2.x, by = n2.y, bz = n2.z;  // n2_copy
+  float t = ax * dx;
+  t += ay * dy;
+  t += az * dz;
+  const float angle1 = t / f4;
+  t = bx * dx;
+  t += by * dy;
+  t += bz * dz;
+  const float angle2 = t / f4;
+  if (acos((double)fabsf(angle1)) > acos((double)fabsf(angle2))) {
+    ax = n2.x, ay = n2.y, az = n2.z;
+    bx = n1.x, by = n1.y, bz = n1.z;
+    dx *= -1.0f;
+    dy *= -1.0f;
+    dz *= -1.0f;
+    f3 = -angle2;
+  } else {
+    f3 = angle1;
+  }
+  // v = dp x n1
+  float vx = dy * az - dz * ay;
+  float vy = dz * ax - dx * az;
+  float vz = dx * ay - dy * ax;
+  s = vx * vx;
+  s += vy * vy;
+  s += vz * vz;
+  const float v_norm = sqrtf(s);
+  if (v_norm == 0.0f) {
+    f1 = f2 = f3 = 0.0f;
+    return;
+  }
+  vx /= v_norm;
+  vy /= v_norm;
+  vz /= v_norm;
+  // w = n1 x v
+  const float wx = ay * vz - az * vy;
+  const float wy = az * vx - ax * vz;
+  const float wz = ax * vy - ay * vx;
+  t = vx * bx;
+  t += vy * by;
+  t += vz * bz;
+  f2 = t;
+  float wn = wx * bx;
+  wn += wy * by;
+  wn += wz * bz;
+  float nn = ax * bx;
+  nn += ay * by;
+  nn += az * bz;
+  f1 = (float)atan2((double)wn, (double)nn);  // correctly rounded stand-in for atan2f
+}
+
+__device__ __forceinline__ int clamp_bin(double x) {
+  const double f = floor(x);
+  int h;
+  if (!(f == f) || f >= 2147483648.0 || f < -2147483648.0)
+    h = -1;  // static_cast<int> of NaN / out of range gives INT_MIN on x86 → clamps to 0
+  else
+    h = (int)f;
+  if (h < 0) h = 0;
+  if (h >= 11) h = 10;
+  return h;
+}
+
+// Pass 1: one surface point (in cell order) per CTA.  spfh is indexed by ORIGINAL row.
+__global__ void __launch_bounds__(FPFH_THREADS)
+    spfh_kernel(GridView g, const float4 *__restrict__ nrm, const int *__restrict__ need, float radius, float r2,
+                int cap, unsigned long long *glob_key, int *glob_pos, float *__restrict__ spfh) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ int s_count;
+  __shared__ int s_bins[33];
+  unsigned long long *key;
+  int *pos;
+  if (glob_key) {
+    key = glob_key + (size_t)blockIdx.x * cap;
+    pos = glob_pos + (size_t)blockIdx.x * cap;
+  } else {
+    key = reinterpret_cast<unsigned long long *>(smem_raw);
+    pos = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(unsigned long long));
+  }
+  const int tid = threadIdx.x;
+  const double kPi = 3.14159265358979323846;
+  const float d_pi = 1.0f / (2.0f * (float)kPi);
+  for (int s = blockIdx.x; s < g.n; s += gridDim.x) {
+    if (!need[s]) continue;  // block-uniform
+    const float4 p = g.pts[s];
+    const float4 np = nrm[s];
+    int n = gather_radius(g, p.x, p.y, p.z, radius, r2, key, pos, cap, &s_count);
+    if (n > cap) n = cap;
+    if (tid < 33) s_bins[tid] = 0;
+    __syncthreads();
+    for (int j = tid; j < n; j += FPFH_THREADS) {
+      const int pj = pos[j];
+      if (pj == s) continue;  // p_idx == indices[idx]
+      float f1, f2, f3;
+      pair_features(p, np, g.pts[pj], nrm[pj], f1, f2, f3);
+      atomicAdd(&s_bins[clamp_bin(11 * (((double)f1 + kPi) * (double)d_pi))], 1);
+      atomicAdd(&s_bins[11 + clamp_bin(11 * (((double)f2 + 1.0) * 0.5))], 1);
+      atomicAdd(&s_bins[22 + clamp_bin(11 * (((double)f3 + 1.0) * 0.5))], 1);
+    }
+    __syncthreads();
+    if (tid < 33) {
+      // n == 0 cannot happen (the point finds itself); PCL would leave the row at zero
+      const float hist_incr = 100.0f / (float)(n - 1);
+      float v = 0.0f;
+      const int cnt = s_bins[tid];
+      for (int t = 0; t < cnt; ++t) v += hist_incr;
+      spfh[(size_t)orig_index(p) * 33 + tid] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Pass 2: one query per CTA.
+__global__ void __launch_bounds__(FPFH_THREADS)
+    fpfh_weight_kernel(GridView g, const float4 *__restrict__ q, int nq, float radius, float r2, int cap,
+                       unsigned long long *glob_key, int *glob_pos, const float *__restrict__ spfh,
+                       float *__restrict__ out) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ int s_count;
+  __shared__ double s_sum[3];
+  unsigned long long *key;
+  int *pos;
+  if (glob_key) {
+    key = glob_key + (size_t)blockIdx.x * cap;
+    pos = glob_pos + (size_t)blockIdx.x * cap;
+  } else {
+    key = reinterpret_cast<unsigned long long *>(smem_raw);
+    pos = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(unsigned long long));
+  }
+  const int tid = threadIdx.x;
+  for (int i = blockIdx.x; i < nq; i += gridDim.x) {
+    const float4 c = q[i];
+    int n = gather_radius(g, c.x, c.y, c.z, radius, r2, key, pos, cap, &s_count);
+    if (n > cap) n = cap;
+    bitonic_sort(key, pos, n);
+    float acc = 0.0f;
+    if (tid < 33) {
+      for (int j = 0; j < n; ++j) {
+        const float d2 = key_d2(key[j]);
+        if (d2 == 0.0f) continue;
+        const float weight = 1.0f / d2;
+        const float val = spfh[(size_t)key_orig(key[j]) * 33 + tid] * weight;
+        acc += val;
+      }
+    } else if (tid >= 64 && tid < 67) {
+      // float64 running sum of one 11-bin block in PCL's order (neighbour-major, bin-minor)
+      const int f = tid - 64;
+      double sum = 0.0;
+      for (int j = 0; j < n; ++j) {
+        const float d2 = key_d2(key[j]);
+        if (d2 == 0.0f) continue;
+        const float weight = 1.0f / d2;
+        const float *row = spfh + (size_t)key_orig(key[j]) * 33 + f * 11;
+        for (int b = 0; b < 11; ++b) sum += (double)(row[b] * weight);
+      }
+      if (sum != 0) sum = 100.0 / sum;
+      s_sum[f] = sum;
+    }
+    __syncthreads();
+    if (tid < 33) {
+      float v = acc * (float)s_sum[tid / 11];
+      if (n == 0) v = nanf32();  // searchForNeighbors == 0 → NaN row
+      out[(size_t)i * 33 + tid] = v;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 *d_q, int nq, bool q_is_surface,
+             double radius, float *d_out) {
+  if (!(radius > 0.0)) return ctx->fail(B200_ERR_INVALID, "fpfh: radius must be > 0");
+  if (nq <= 0) return B200_OK;
+  const GridView *g;
+  B200_TRY(cloud_grid_for_radius(c, radius, &g));
+  const int nv = c->n_valid;
+  const float r2 = (float)(radius * radius);
+  DevBuf<float4> nrm_sorted;
+  B200_TRY(nrm_sorted.alloc(ctx, (size_t)std::max(nv, 1)));
+  DevBuf<int> need, counts;
+  DevBuf<unsigned long long> stats;
+  DevBuf<float> spfh;
+  B200_TRY(need.alloc(ctx, (size_t)std::max(nv, 1)));
+  B200_TRY(counts.alloc(ctx, (size_t)std::max(std::max(nv, nq), 1)));
+  B200_TRY(stats.alloc(ctx, 2));
+  B200_TRY(spfh.alloc(ctx, (size_t)std::max(c->n, 1) * 33));
+  B200_TRY(spfh.zero());
+  if (nv > 0) {
+    gather_normals_sorted_kernel<<<ceil_div(nv, 256), 256, 0, ctx->stream>>>(
+        g->pts, nv, reinterpret_cast<const float4 *>(d_normals), nrm_sorted.p);
+    B200_LAUNCHED(ctx);
+    if (q_is_surface) {
+      fill_int_kernel<<<ceil_div(nv, 256), 256, 0, ctx->stream>>>(need.p, nv, 1);
+      B200_LAUNCHED(ctx);
+    } else {
+      B200_TRY(need.zero());
+      fpfh_mark_kernel<<<ceil_div((long long)nq * 32, FPFH_THREADS), FPFH_THREADS, 0, ctx->stream>>>(
+          *g, d_q, nq, (float)radius, r2, need.p);
+      B200_LAUNCHED(ctx);
+    }
+  }
+  // list capacity: the largest neighbourhood over the surface points (pass 1) and the queries (pass 2)
+  unsigned long long hs[2], hq[2];
+  B200_TRY(dev_radius_count(ctx, *g, g->pts, nv, radius, counts.p, stats.p));
+  B200_CUDA(ctx, cudaMemcpyAsync(hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (q_is_surface) {
+    hq[0] = hs[0];
+    hq[1] = hs[1];
+  } else {
+    B200_TRY(dev_radius_count(ctx, *g, d_q, nq, radius, counts.p, stats.p));
+    B200_CUDA(ctx, cudaMemcpyAsync(hq, stats.p, sizeof(hq), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->last_max_nbrs = (int)hq[0];
+  ctx->last_mean_nbrs = (double)hq[1] / nq;
+  const int max_count = (int)std::max(hs[0], hq[0]);
+  const int cap = next_pow2_host(std::max(max_count, 32));
+  const size_t smem = (size_t)cap * 12;
+  const bool in_smem = smem <= 96 * 1024;
+  DevBuf<unsigned long long> gk;
+  DevBuf<int> gp;
+  int grid1, grid2;
+  if (in_smem) {
+    B200_CUDA(ctx, cudaFuncSetAttribute(spfh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(ctx, cudaFuncSetAttribute(fpfh_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grid1 = std::min(std::max(nv, 1), ctx->sm_count * 8);
+    grid2 = std::min(nq, ctx->sm_count * 8);
+  } else {
+    grid1 = std::min(std::max(nv, 1), ctx->sm_count * 2);
+    grid2 = std::min(nq, ctx->sm_count * 2);
+    B200_TRY(gk.alloc(ctx, (size_t)std::max(grid1, grid2) * cap));
+    B200_TRY(gp.alloc(ctx, (size_t)std::max(grid1, grid2) * cap));
+  }
+  if (nv > 0) {
+    spfh_kernel<<<grid1, FPFH_THREADS, in_smem ? smem : 0, ctx->stream>>>(*g, nrm_sorted.p, need.p, (float)radius, r2,
+                                                                         cap, gk.p, gp.p, spfh.p);
+    B200_LAUNCHED(ctx);
+  }
+  fpfh_weight_kernel<<<grid2, FPFH_THREADS, in_smem ? smem : 0, ctx->stream>>>(*g, d_q, nq, (float)radius, r2, cap,
+                                                                              gk.p, gp.p, spfh.p, d_out);
+  B200_LAUNCHED(ctx);
+  return B200_OK;
+}

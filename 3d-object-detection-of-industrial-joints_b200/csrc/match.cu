@@ -1,0 +1,201 @@
+// match.cu — model↔scene descriptor correspondence search (exact float32 path).
+//
+// Replaces pcl::KdTreeFLANN<SHOT352 / FPFHSignature33>::setInputCloud + nearestKSearch and the user
+// threshold loop around them: SHOT.cpp:405-423 (k = 1, d2 < 0.20), SHOT_scenes.cpp:359-365 (0.25),
+// 6Dpose.cpp:464-482, SHOT_demo.cpp:508-530 and FPFH_demo.cpp:516-538 (k = 2, d0/d1 <= 1).
+//
+// A kd-tree over 352 dimensions prunes almost nothing, so the reference effectively evaluates all
+// Ks x Km distances; this kernel does exactly that, tiled through shared memory.  Every distance is
+// the FLANN L2_Simple float32 sum over d = 0..D-1 in order (separate multiply and add, no FMA), so
+// the winning distance and the arg-min (ties → lower model index) are bit-identical to the CPU.
+// The per-scene-row minimum across CTAs is taken with a 64-bit atomicMin on (d2 bits << 32 | index).
+//
+// This is the exact path; match_tc.cu adds a tcgen05 tensor-core pre-filter for large libraries and
+// falls back to this kernel's arithmetic for the final (exact) rescoring.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int MT = 64;      // tile rows (scene and model)
+constexpr int MKC = 32;     // descriptor chunk
+constexpr int MTHREADS = 256;
+
+__global__ void row_valid_kernel(const float *__restrict__ desc, int rows, int D, int all_dims,
+                                 unsigned char *__restrict__ valid, int *__restrict__ n_valid) {
+  // one warp per row
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  bool ok = true;
+  if (all_dims) {
+    for (int d = lane; d < D; d += 32) ok = ok && isfinite(desc[(size_t)w * D + d]);
+    ok = __all_sync(0xffffffffu, ok);
+  } else {
+    ok = isfinite(desc[(size_t)w * D]);
+  }
+  if (lane == 0) {
+    valid[w] = ok ? 1 : 0;
+    if (ok && n_valid) atomicAdd(n_valid, 1);
+  }
+}
+
+__global__ void init_best_kernel(unsigned long long *best, int *zero_cnt, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    best[i] = ~0ull;
+    zero_cnt[i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(MTHREADS)
+    match_tile_kernel(const float *__restrict__ model, int Km, const unsigned char *__restrict__ model_valid,
+                      const float *__restrict__ scene, int Ks, int D, unsigned long long *__restrict__ best,
+                      int *__restrict__ zero_cnt) {
+  __shared__ float As[MT][MKC + 1];
+  __shared__ float Bs[MT][MKC + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int s0 = blockIdx.x * MT;
+  unsigned long long rbest[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  int rzero[4] = {0, 0, 0, 0};
+  const int ntiles = (Km + MT - 1) / MT;
+  for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+    const int m0 = tile * MT;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int d0 = 0; d0 < D; d0 += MKC) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < MT * MKC; idx += MTHREADS) {
+        const int r = idx / MKC, c = idx % MKC;
+        const int d = d0 + c;
+        const int sr = s0 + r, mr = m0 + r;
+        As[r][c] = (sr < Ks && d < D) ? scene[(size_t)sr * D + d] : 0.0f;
+        Bs[r][c] = (mr < Km && d < D) ? model[(size_t)mr * D + d] : 0.0f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int c = 0; c < MKC; ++c) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[ty + 16 * i][c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[tx + 16 * j][c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float diff = a[i] - b[j];
+            acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(diff, diff));
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + tx + 16 * j;
+        if (m < Km && model_valid[m]) {
+          const unsigned long long k = ((unsigned long long)__float_as_uint(acc[i][j]) << 32) | (unsigned)m;
+          rbest[i] = (k < rbest[i]) ? k : rbest[i];
+          rzero[i] += (acc[i][j] == 0.0f) ? 1 : 0;
+        }
+      }
+  }
+  // reduce over the 16 threads (tx) that share a scene row: they are 16 consecutive lanes
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unsigned long long k = rbest[i];
+    int z = rzero[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, o);
+      k = (ok < k) ? ok : k;
+      z += __shfl_xor_sync(0xffffffffu, z, o);
+    }
+    const int sr = s0 + ty + 16 * i;
+    if (tx == 0 && sr < Ks) {
+      if (k != ~0ull) atomicMin(&best[sr], k);
+      if (z) atomicAdd(&zero_cnt[sr], z);
+    }
+  }
+}
+
+__global__ void match_flags_kernel(const unsigned long long *__restrict__ best, const int *__restrict__ zero_cnt,
+                                   const unsigned char *__restrict__ scene_valid, const int *__restrict__ n_model_valid,
+                                   int Ks, int mode, float thr, int *__restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ks) return;
+  int f = 0;
+  const unsigned long long k = best[i];
+  if (scene_valid[i] && k != ~0ull) {
+    const float d2 = __uint_as_float((unsigned)(k >> 32));
+    if (mode == 1) {
+      f = (d2 < thr) ? 1 : 0;
+    } else {
+      // tau = d0 / d1 <= 1: fails only when it is NaN (d0 == d1 == 0) or there is no second neighbour
+      f = (*n_model_valid >= 2 && zero_cnt[i] < 2) ? 1 : 0;
+    }
+  }
+  flags[i] = f;
+}
+
+__global__ void match_emit_kernel(const unsigned long long *__restrict__ best, const int *__restrict__ flags,
+                                  const int *__restrict__ slots, int Ks, b200_corr *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ks || !flags[i]) return;
+  const unsigned long long k = best[i];
+  b200_corr c;
+  c.index_query = (int)(unsigned)(k & 0xffffffffull);
+  c.index_match = i;
+  c.distance = __uint_as_float((unsigned)(k >> 32));
+  out[slots[i]] = c;
+}
+
+}  // namespace
+
+int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
+              b200_corr *d_out, int *d_count) {
+  if (mode != 1 && mode != 2) return ctx->fail(B200_ERR_INVALID, "match: mode must be 1 or 2");
+  if (D <= 0 || Km < 0 || Ks < 0) return ctx->fail(B200_ERR_INVALID, "match: bad sizes");
+  B200_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+  if (Ks == 0) return B200_OK;
+  DevBuf<unsigned char> mvalid, svalid;
+  DevBuf<int> nmv, zero_cnt, flags, slots;
+  DevBuf<unsigned long long> best;
+  B200_TRY(mvalid.alloc(ctx, (size_t)std::max(Km, 1)));
+  B200_TRY(svalid.alloc(ctx, (size_t)Ks));
+  B200_TRY(nmv.alloc(ctx, 1));
+  B200_TRY(nmv.zero());
+  B200_TRY(zero_cnt.alloc(ctx, (size_t)Ks));
+  B200_TRY(flags.alloc(ctx, (size_t)Ks));
+  B200_TRY(slots.alloc(ctx, (size_t)Ks));
+  B200_TRY(best.alloc(ctx, (size_t)Ks));
+  if (Km > 0) {
+    row_valid_kernel<<<ceil_div((long long)Km * 32, 256), 256, 0, ctx->stream>>>(d_model, Km, D, 1, mvalid.p, nmv.p);
+    B200_LAUNCHED(ctx);
+  }
+  row_valid_kernel<<<ceil_div((long long)Ks * 32, 256), 256, 0, ctx->stream>>>(d_scene, Ks, D, 0, svalid.p, nullptr);
+  B200_LAUNCHED(ctx);
+  init_best_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, Ks);
+  B200_LAUNCHED(ctx);
+  if (Km > 0) {
+    const int sx = ceil_div(Ks, MT);
+    const int mtiles = ceil_div(Km, MT);
+    // enough CTAs for >= 4 waves when the scene is small
+    int sy = std::max(1, std::min(mtiles, (ctx->sm_count * 8) / std::max(sx, 1)));
+    dim3 grid(sx, sy);
+    match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, best.p, zero_cnt.p);
+    B200_LAUNCHED(ctx);
+  }
+  match_flags_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, svalid.p, nmv.p, Ks, mode, thr,
+                                                                 flags.p);
+  B200_LAUNCHED(ctx);
+  B200_TRY(exclusive_scan_i32(ctx, flags.p, slots.p, Ks, d_count));
+  match_emit_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, flags.p, slots.p, Ks, d_out);
+  B200_LAUNCHED(ctx);
+  return B200_OK;
+}

@@ -1,0 +1,223 @@
+// search.cuh — device-side exact neighbour search on the uniform grid.
+//
+//  knn_query       one query per thread, candidate list in shared memory; replaces
+//                  KdTreeFLANN::nearestKSearch as used by NormalEstimationOMP with setKSearch
+//                  (SHOT.cpp:302-308) and by the explicit calls (SHOT.cpp:163, Edge_detection.cpp:120).
+//  gather_radius   one query per CTA, neighbours appended to a list with warp-aggregated atomics;
+//                  replaces KdTreeFLANN::radiusSearch (SHOT_VAR.cpp:356; implicit in SHOT / FPFH /
+//                  radius normals).  Acceptance is d2 < (float)(r*r), strict, on the float32
+//                  L2_Simple distance — bit-identical to FLANN's test.
+//  bitonic_sort    orders a CTA's list by (d2, original index), the order FLANN returns
+//                  (RadiusResultSet is sorted with DistanceIndex::operator<).
+#pragma once
+
+#include "common.cuh"
+
+__device__ __forceinline__ bool cand_before(float d, int o, float d2, int o2) {
+  return (d < d2) || (d == d2 && o < o2);
+}
+
+// Exact k nearest neighbours of (qx,qy,qz).  sd/sp: this thread's column of two [k][T] shared
+// arrays (element j at [j*T]).  Returns the number found (min(k, g.n)); entries are sorted by
+// (d2, original index); sp holds positions in g.pts.
+__device__ inline int knn_query(const GridView &g, float qx, float qy, float qz, int k, float *sd, int *sp, int T) {
+  const float4 *__restrict__ pts = g.pts;
+  const int *__restrict__ cs = g.cell_start;
+  if (k > g.n) k = g.n;
+  if (k <= 0) return 0;
+  const int cx = grid_coord(qx, g.lox, g.inv_h, g.dx);
+  const int cy = grid_coord(qy, g.loy, g.inv_h, g.dy);
+  const int cz = grid_coord(qz, g.loz, g.inv_h, g.dz);
+  int cnt = 0;
+  const int maxR = max(g.dx, max(g.dy, g.dz));
+  const float margin = 4e-6f * (g.coord_scale + fabsf(qx) + fabsf(qy) + fabsf(qz)) + 1e-5f * g.h;
+
+  auto scan_run = [&](int c0, int c1) {
+    const int s = cs[c0], e = cs[c1 + 1];
+    for (int j = s; j < e; ++j) {
+      const float4 p = pts[j];
+      const float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
+      if (cnt == k) {
+        const float wd = sd[(k - 1) * T];
+        if (d > wd) continue;
+        if (d == wd && orig_index(p) >= orig_index(pts[sp[(k - 1) * T]])) continue;
+      }
+      int pos = (cnt < k) ? cnt : k - 1;
+      const int o = orig_index(p);
+      while (pos > 0) {
+        const float pd = sd[(pos - 1) * T];
+        const int pp = sp[(pos - 1) * T];
+        if (pd < d || (pd == d && orig_index(pts[pp]) < o)) break;
+        sd[pos * T] = pd;
+        sp[pos * T] = pp;
+        --pos;
+      }
+      sd[pos * T] = d;
+      sp[pos * T] = j;
+      if (cnt < k) ++cnt;
+    }
+  };
+
+  for (int R = 0; R <= maxR; ++R) {
+    const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
+    const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
+    const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dx - 1);
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const bool face = (abs(z - cz) == R) || (abs(y - cy) == R);
+        const int row = g.dx * (y + g.dy * z);
+        if (face) {
+          scan_run(row + x0, row + x1);
+        } else {
+          if (cx - R >= 0) scan_run(row + cx - R, row + cx - R);
+          if (cx + R <= g.dx - 1) scan_run(row + cx + R, row + cx + R);  // R > 0 here (R == 0 is a face row)
+        }
+      }
+    const bool whole = (z0 == 0 && z1 == g.dz - 1 && y0 == 0 && y1 == g.dy - 1 && x0 == 0 && x1 == g.dx - 1);
+    if (whole) break;
+    if (cnt == k) {
+      // everything outside the scanned block is at least `cert` away from the query
+      float cert = 3.0e38f;
+      if (cx - R > 0) cert = fminf(cert, qx - (g.lox + (float)(cx - R) * g.h));
+      if (cx + R < g.dx - 1) cert = fminf(cert, (g.lox + (float)(cx + R + 1) * g.h) - qx);
+      if (cy - R > 0) cert = fminf(cert, qy - (g.loy + (float)(cy - R) * g.h));
+      if (cy + R < g.dy - 1) cert = fminf(cert, (g.loy + (float)(cy + R + 1) * g.h) - qy);
+      if (cz - R > 0) cert = fminf(cert, qz - (g.loz + (float)(cz - R) * g.h));
+      if (cz + R < g.dz - 1) cert = fminf(cert, (g.loz + (float)(cz + R + 1) * g.h) - qz);
+      cert -= margin;
+      if (cert > 0.f && sd[(k - 1) * T] < cert * cert * 0.99999f) break;
+    }
+  }
+  return cnt;
+}
+
+// Cell range of the ball around q, padded so that float rounding can never exclude a point the
+// distance test would accept.  Returns false if the ball misses the grid entirely.
+__device__ __forceinline__ bool ball_cell_range(const GridView &g, float qx, float qy, float qz, float radius,
+                                                int &x0, int &x1, int &y0, int &y1, int &z0, int &z1) {
+  const float rp = radius * 1.00001f;
+  const float ex = rp + 2e-6f * (fabsf(qx) + g.coord_scale);
+  const float ey = rp + 2e-6f * (fabsf(qy) + g.coord_scale);
+  const float ez = rp + 2e-6f * (fabsf(qz) + g.coord_scale);
+  const float hix = g.lox + (float)g.dx * g.h, hiy = g.loy + (float)g.dy * g.h, hiz = g.loz + (float)g.dz * g.h;
+  if (qx + ex < g.lox || qx - ex > hix + g.h || qy + ey < g.loy || qy - ey > hiy + g.h || qz + ez < g.loz ||
+      qz - ez > hiz + g.h)
+    return false;
+  x0 = grid_coord(qx - ex, g.lox, g.inv_h, g.dx);
+  x1 = grid_coord(qx + ex, g.lox, g.inv_h, g.dx);
+  y0 = grid_coord(qy - ey, g.loy, g.inv_h, g.dy);
+  y1 = grid_coord(qy + ey, g.loy, g.inv_h, g.dy);
+  z0 = grid_coord(qz - ez, g.loz, g.inv_h, g.dz);
+  z1 = grid_coord(qz + ez, g.loz, g.inv_h, g.dz);
+  return true;
+}
+
+__device__ __forceinline__ unsigned long long nbr_key(float d2, int orig) {
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)orig;
+}
+__device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ int key_orig(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull); }
+
+// CTA-cooperative radius gather.  Every thread of the block must call it.  key/pos: list storage
+// with room for `cap` entries (shared or global).  Returns the total number of neighbours; only the
+// first `cap` (in arrival order) are stored.  s_count: one int of shared memory.
+__device__ inline int gather_radius(const GridView &g, float qx, float qy, float qz, float radius, float r2,
+                                    unsigned long long *key, int *pos, int cap, int *s_count) {
+  if (threadIdx.x == 0) *s_count = 0;
+  __syncthreads();
+  int x0, x1, y0, y1, z0, z1;
+  if (finite3(qx, qy, qz) && g.n > 0 && ball_cell_range(g, qx, qy, qz, radius, x0, x1, y0, y1, z0, z1)) {
+    const float4 *__restrict__ pts = g.pts;
+    const int *__restrict__ cs = g.cell_start;
+    const int ny = y1 - y0 + 1;
+    const int nrows = ny * (z1 - z0 + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int row = warp; row < nrows; row += nw) {
+      const int y = y0 + row % ny, z = z0 + row / ny;
+      const int base = g.dx * (y + g.dy * z);
+      const int s = cs[base + x0], e = cs[base + x1 + 1];
+      for (int j0 = s; j0 < e; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        float d2 = 0.f;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < e) {
+          p = pts[j];
+          d2 = sqdist3(qx, qy, qz, p.x, p.y, p.z);
+          hit = d2 < r2;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          int slot0 = 0;
+          if (lane == 0) slot0 = atomicAdd(s_count, __popc(m));
+          slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+          if (hit) {
+            const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
+            if (slot < cap) {
+              key[slot] = nbr_key(d2, orig_index(p));
+              pos[slot] = j;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  return *s_count;
+}
+
+// Count-only variant for one warp (used to size lists / CSR outputs).
+__device__ inline int count_radius_warp(const GridView &g, float qx, float qy, float qz, float radius, float r2) {
+  int x0, x1, y0, y1, z0, z1;
+  int c = 0;
+  if (finite3(qx, qy, qz) && g.n > 0 && ball_cell_range(g, qx, qy, qz, radius, x0, x1, y0, y1, z0, z1)) {
+    const float4 *__restrict__ pts = g.pts;
+    const int *__restrict__ cs = g.cell_start;
+    const int lane = threadIdx.x & 31;
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const int base = g.dx * (y + g.dy * z);
+        const int s = cs[base + x0], e = cs[base + x1 + 1];
+        for (int j = s + lane; j < e; j += 32) {
+          const float4 p = pts[j];
+          c += (sqdist3(qx, qy, qz, p.x, p.y, p.z) < r2) ? 1 : 0;
+        }
+      }
+  }
+  return warp_sum(c);
+}
+
+// CTA-cooperative bitonic sort of n (key, pos) pairs, ascending key.  The arrays must have room for
+// the next power of two >= n.  Every thread of the block must call it.
+__device__ inline void bitonic_sort(unsigned long long *key, int *pos, int n) {
+  int np = 1;
+  while (np < n) np <<= 1;
+  for (int i = n + threadIdx.x; i < np; i += blockDim.x) {
+    key[i] = ~0ull;
+    pos[i] = -1;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (np >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool up = ((i & k) == 0);
+        const unsigned long long a = key[i], b = key[l];
+        if ((a > b) == up) {
+          key[i] = b;
+          key[l] = a;
+          const int pa = pos[i];
+          pos[i] = pos[l];
+          pos[l] = pa;
+        }
+      }
+      __syncthreads();
+    }
+}
+
+static inline int next_pow2_host(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}

@@ -1,0 +1,187 @@
+/*
+ * b200reg.h — C ABI of libb200reg.so, the B200 (sm_100a) implementation of the SHOT/FPFH
+ * recognition hot path of Merium88/3D-Object-Detection-of-Industrial-Joints.
+ *
+ * The reference reaches this path through PCL classes; each entry point below
+ * names the reference call site (file:line under /root/reference) whose PCL call it replaces.
+ * The PCL-style C++ adapters in include/pcl_b200/ flatten clouds and call these functions;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 (B200_OK) or a negative b200_status;
+ *    no exceptions cross the boundary; b200_last_error() gives the text of the last failure.
+ *  - points are float rows with a caller-given stride in floats (>= 3; x, y, z first), so
+ *    pcl::PointXYZRGBA (stride 8), float4 (4) and packed xyz (3) are all accepted without a copy
+ *    on the caller's side.  Normals are rows of 4 floats (nx, ny, nz, curvature) — the first 16
+ *    bytes of pcl::Normal are nx, ny, nz, pad; the shim copies curvature into slot 3.
+ *  - `b200_*`      : HOST pointers; the call uploads, computes on the GPU, downloads and
+ *                    synchronises (this is the drop-in form the PCL-style adapters use).
+ *  - `b200_dev_*`  : DEVICE pointers; asynchronous on the context's stream, no host sync unless
+ *                    stated.  Used for resident pipelines and by the torch-based harness.
+ *  - there is no CPU fallback: every function fails with B200_ERR_NODEVICE / B200_ERR_CUDA when
+ *    no sm_100 device is usable.
+ *  - NaN semantics follow PCL: degenerate points yield NaN rows, not errors.
+ */
+#ifndef B200REG_H_
+#define B200REG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,   /* bad argument (e.g. both k and radius set, like Feature::initCompute) */
+  B200_ERR_CUDA = -2,      /* CUDA runtime error; see b200_last_error */
+  B200_ERR_NOMEM = -3,
+  B200_ERR_CAPACITY = -4,  /* caller-provided output capacity too small; required size reported */
+  B200_ERR_NODEVICE = -5
+} b200_status;
+
+typedef struct b200_ctx b200_ctx;     /* device, stream, scratch pool; one per host thread */
+typedef struct b200_cloud b200_cloud; /* device-resident search surface (+ uniform grids) */
+typedef struct b200_model b200_model; /* device-resident model descriptor library + keypoints */
+
+/* pcl::Correspondence (SHOT.cpp:420): index_query = model index, index_match = scene index,
+ * distance = squared L2 descriptor distance. */
+typedef struct {
+  int index_query;
+  int index_match;
+  float distance;
+} b200_corr;
+
+/* ---------------------------------------------------------------- context ---------------- */
+/* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+B200_API int b200_ctx_create(b200_ctx **out, int device, void *stream);
+B200_API int b200_ctx_destroy(b200_ctx *ctx);
+B200_API int b200_ctx_sync(b200_ctx *ctx);
+B200_API const char *b200_last_error(const b200_ctx *ctx); /* never NULL; ctx may be NULL (global error) */
+B200_API int b200_abi_version(void);
+/* Number of this library's kernel launches on the context since creation (bench gpu_launches). */
+B200_API int64_t b200_ctx_launch_count(const b200_ctx *ctx);
+
+/* ---------------------------------------------------------------- search surface --------- */
+/* Replaces pcl::search::KdTree / KdTreeFLANN<PointXYZRGBA>::setInputCloud (built implicitly by
+ * Feature::initCompute for every compute(); explicit at SHOT_VAR.cpp:350, Edge_detection.cpp:117).
+ * Rows with a non-finite coordinate are dropped from the index but keep their position. */
+B200_API int b200_cloud_create(b200_ctx *ctx, const float *xyz, int n, int stride, b200_cloud **out);     /* host rows */
+B200_API int b200_dev_cloud_create(b200_ctx *ctx, const float *d_xyz, int n, int stride, b200_cloud **out); /* device rows */
+B200_API int b200_cloud_destroy(b200_cloud *cloud);
+B200_API int b200_cloud_size(const b200_cloud *cloud);
+
+/* KdTreeFLANN::radiusSearch (SHOT_VAR.cpp:356, 434).  CSR result: offsets[nq+1]; neighbours with
+ * d2 < (float)(radius*radius), each list sorted by (d2, index).  Two-call sizing: pass cap = 0 (idx,
+ * d2 may be NULL) to obtain *total, then call again with buffers of that capacity. */
+B200_API int b200_radius_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qstride, double radius,
+                       int64_t *offsets, int *idx, float *d2, int64_t cap, int64_t *total);
+/* KdTreeFLANN::nearestKSearch (SHOT.cpp:163, Edge_detection.cpp:120).  idx/d2: nq x k, sorted by
+ * (d2, index); k is clamped to the number of indexed points (*k_found), unused slots are -1/+inf. */
+B200_API int b200_knn_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qstride, int k, int *idx,
+                    float *d2, int *k_found);
+
+/* ---------------------------------------------------------------- normals ---------------- */
+/* pcl::NormalEstimationOMP::compute — setKSearch(k) (SHOT.cpp:302-308, 6Dpose.cpp:275-278,
+ * SHOT_demo.cpp:405-411, CAD_desc.cpp:283-289) or setRadiusSearch(r) (FPFH_demo.cpp:416-420,
+ * FPFH_scenes_clustered.cpp:273-277).  Exactly one of k / radius non-zero.  q == NULL: the input
+ * cloud is the surface itself.  viewpoint: 3 floats or NULL for (0,0,0).  out: nq x 4. */
+B200_API int b200_normals(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qstride, int k, double radius,
+                 const float *viewpoint, float *out);
+B200_API int b200_dev_normals(b200_ctx *ctx, b200_cloud *surf, const float *d_q, int nq, int qstride, int k,
+                     double radius, const float *viewpoint, float *d_out);
+
+/* ---------------------------------------------------------------- SHOT ------------------- */
+/* pcl::SHOTLocalReferenceFrameEstimationOMP (implicit in SHOTEstimationOMP::initCompute,
+ * SHOT.cpp:360-366).  out: K x 9 (x, y, z axes). */
+B200_API int b200_shot_lrf(b200_ctx *ctx, b200_cloud *surf, const float *kp, int K, int kstride, double radius, float *out);
+/* pcl::SHOTEstimationOMP<PointXYZRGBA, Normal, SHOT352>::compute (SHOT.cpp:360-371,
+ * SHOT_demo.cpp:419-424, 497-502, 6Dpose.cpp:450-461, CAD_desc.cpp:341-352).
+ * normals: n x 4 for the search surface (setInputNormals); desc: K x 352; rf: K x 9 (may be NULL). */
+B200_API int b200_shot352(b200_ctx *ctx, b200_cloud *surf, const float *normals, const float *kp, int K, int kstride,
+                 double radius, float *desc, float *rf);
+B200_API int b200_dev_shot352(b200_ctx *ctx, b200_cloud *surf, const float *d_normals, const float *d_kp, int K,
+                     int kstride, double radius, float *d_desc, float *d_rf);
+
+/* ---------------------------------------------------------------- FPFH ------------------- */
+/* pcl::FPFHEstimation / FPFHEstimationOMP ::compute (FPFH_demo.cpp:422-428, 505-510;
+ * FPFH_scenes_clustered.cpp:287-293, 379-387).  q == NULL: input == surface.  out: nq x 33. */
+B200_API int b200_fpfh33(b200_ctx *ctx, b200_cloud *surf, const float *normals, const float *q, int nq, int qstride,
+                double radius, float *out);
+B200_API int b200_dev_fpfh33(b200_ctx *ctx, b200_cloud *surf, const float *d_normals, const float *d_q, int nq,
+                    int qstride, double radius, float *d_out);
+
+/* ---------------------------------------------------------------- matching --------------- */
+/* pcl::KdTreeFLANN<SHOT352 / FPFHSignature33>::setInputCloud + nearestKSearch + the user
+ * threshold loop.  mode 1: k = 1, accept d2 < thr (SHOT.cpp:405-423, SHOT_scenes.cpp:359-365,
+ * 6Dpose.cpp:464-482).  mode 2: k = 2, accept d0/d1 <= 1 (SHOT_demo.cpp:508-530,
+ * FPFH_demo.cpp:516-538).  D = 352 or 33 (any D accepted).  out: capacity Ks; ascending scene index. */
+B200_API int b200_match(b200_ctx *ctx, const float *model, int Km, const float *scene, int Ks, int D, int mode, float thr,
+               b200_corr *out, int *count);
+B200_API int b200_dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode,
+                   float thr, b200_corr *d_out, int *d_count);
+
+/* ---------------------------------------------------------------- grouping --------------- */
+/* pcl::GeometricConsistencyGrouping::recognize (SHOT.cpp:473-482, 6Dpose.cpp:529-538,
+ * SHOT_scenes.cpp:413-425).  transforms: max_inst x 16 (row-major 4x4, model -> scene);
+ * inst_offsets: max_inst + 1; inst_corrs: capacity corr_cap (>= C is always enough).
+ * *n_inst is the number found (B200_ERR_CAPACITY if it exceeds max_inst; the first max_inst are valid). */
+B200_API int b200_gc_recognize(b200_ctx *ctx, const float *model_kp, int Km, int mstride, const float *scene_kp, int Ks,
+                      int sstride, const b200_corr *corrs, int C, double gc_size, int gc_threshold,
+                      float *transforms, int max_inst, int *inst_offsets, b200_corr *inst_corrs, int corr_cap,
+                      int *n_inst);
+
+/* ---------------------------------------------------------------- resident pipeline ------ */
+typedef struct {
+  int normal_k;          /* NormalEstimationOMP::setKSearch; 0 if radius is used */
+  double normal_radius;  /* NormalEstimationOMP::setRadiusSearch; 0 if k is used */
+  double descr_radius;   /* SHOTEstimationOMP::setRadiusSearch (descr_rad_, SHOT.cpp:52) */
+  int match_mode;        /* 1 or 2, see b200_match */
+  float match_thr;       /* 0.25f SHOT_scenes.cpp:360 / 0.20f SHOT.cpp:418 */
+  double gc_size;        /* cg_size_   (SHOT.cpp:53) */
+  int gc_threshold;      /* cg_thresh_ (SHOT.cpp:54; passed as float, truncated) */
+  int max_instances;
+} b200_shot_params;
+
+/* Model side of SHOT.cpp:302-371 / CAD_desc.cpp:283-352: normals + SHOT352 of the model keypoints,
+ * kept on the device as the (replicated) descriptor library. */
+B200_API int b200_model_create_shot(b200_ctx *ctx, const float *xyz, int n, int stride, const float *kp, int K,
+                           int kstride, const b200_shot_params *p, b200_model **out);
+B200_API int b200_model_destroy(b200_model *m);
+B200_API int b200_model_size(const b200_model *m);
+/* copy the library out (host): desc K x 352, kp K x 3 (either may be NULL) */
+B200_API int b200_model_download(b200_ctx *ctx, const b200_model *m, float *desc, float *kp);
+
+/* Scene side of SHOT.cpp:305-483 in one call (host buffers in, host results out): normals →
+ * SHOT352 at the keypoints → correspondence search against the resident model → GC grouping.
+ * corrs_out (capacity Ks) / n_corrs receive the model-scene correspondences; may be NULL. */
+B200_API int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float *scene_xyz, int n, int stride,
+                             const float *scene_kp, int Ks, int kstride, const b200_shot_params *p,
+                             float *transforms, int *inst_offsets, b200_corr *inst_corrs, int corr_cap,
+                             int *n_inst, b200_corr *corrs_out, int *n_corrs);
+
+/* Same pipeline with every buffer already resident (device pointers), asynchronous, no host
+ * synchronisation; d_n_inst / d_n_corrs are device ints.  d_desc_out (Ks x 352) may be NULL. */
+B200_API int b200_dev_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float *d_scene_xyz, int n,
+                                 int stride, const float *d_scene_kp, int Ks, int kstride,
+                                 const b200_shot_params *p, float *d_transforms, int *d_inst_offsets,
+                                 int *d_inst_counts, b200_corr *d_inst_corrs, int corr_cap, int *d_n_inst,
+                                 b200_corr *d_corrs_out, int *d_n_corrs, float *d_desc_out);
+
+/* Statistics of the last descriptor call on this context (for bench records): mean / max number of
+ * radius neighbours per keypoint. */
+B200_API int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REG_H_ */

@@ -1,0 +1,351 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): neighbour index sets and correspondence lists
+bit-exact; descriptors within 1e-4 L2 per descriptor; poses within 1e-4 m and 0.01 degrees.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rng(seed):
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+@pytest.fixture(scope="module")
+def ctx(b200):
+    c = b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def small(synth):
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 40000, scene_id=1)
+    return model, scene
+
+
+def _rot_angle_deg(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+
+
+# ------------------------------------------------------------------------------------------ search
+def test_radius_search_bit_exact(ctx, orc, small):
+    model, scene = small
+    q = scene[::17]
+    for cloud_np, r in ((scene, 0.02), (model, 0.015)):
+        qq = q if cloud_np is scene else model[::5]
+        cl = ctx.cloud(cloud_np)
+        off, idx, d2 = ctx.radius_search(cl, qq, r)
+        ooff, oidx, od2 = orc.radius_search(cloud_np, qq, r)
+        assert np.array_equal(off, ooff)
+        assert np.array_equal(idx, oidx)
+        assert np.array_equal(d2, od2)
+        cl.close()
+
+
+def test_radius_search_degenerate(ctx, orc, synth):
+    # radius 50 on a small model: the support is the whole cloud (SHOT_demo.cpp:498)
+    model = synth.make_model("diagonal", 3000)
+    cl = ctx.cloud(model)
+    q = model[::300]
+    off, idx, d2 = ctx.radius_search(cl, q, 50.0)
+    ooff, oidx, od2 = orc.radius_search(model, q, 50.0)
+    assert off[-1] == len(q) * 3000
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(d2, od2)
+    # NaN rows in the surface are skipped but keep their index; NaN / far queries return nothing
+    s = model.copy()
+    s[10] = np.nan
+    s[500, 1] = np.inf
+    cl2 = ctx.cloud(s)
+    q2 = np.concatenate([s[:50], [[np.nan, 0, 0]], [[9, 9, 9]]]).astype(np.float32)
+    off, idx, d2 = ctx.radius_search(cl2, q2, 0.03)
+    ooff, oidx, od2 = orc.radius_search(s, q2, 0.03)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(d2, od2)
+    assert off[-1] == off[-3]
+    # empty query set
+    off, idx, d2 = ctx.radius_search(cl2, np.zeros((0, 3), np.float32), 0.03)
+    assert off.tolist() == [0] and len(idx) == 0
+
+
+@pytest.mark.parametrize("k", [1, 10, 50])
+def test_knn_search_parity(ctx, orc, small, k):
+    _, scene = small
+    cl = ctx.cloud(scene)
+    q = scene[::23]
+    idx, d2, kf = ctx.knn_search(cl, q, k)
+    oidx, od2, okf = orc.knn_search(scene, q, k)
+    assert kf == okf == k
+    assert np.array_equal(d2, od2)
+    assert np.array_equal(idx, oidx)
+    # queries that are not surface points, including one far outside the bounding box
+    q2 = (q[:200] + np.float32(0.003)).astype(np.float32)
+    q2[0] = [5, -4, 3]
+    idx, d2, _ = ctx.knn_search(cl, q2, k)
+    oidx, od2, _ = orc.knn_search(scene, q2, k)
+    assert np.array_equal(d2, od2) and np.array_equal(idx, oidx)
+
+
+def test_knn_clamps(ctx, orc):
+    s = _rng(1).normal(size=(7, 3)).astype(np.float32)
+    cl = ctx.cloud(s)
+    idx, d2, kf = ctx.knn_search(cl, s, 10)
+    oidx, od2, okf = orc.knn_search(s, s, 10)
+    assert kf == okf == 7
+    assert np.array_equal(idx, oidx) and np.array_equal(d2, od2)
+
+
+# ------------------------------------------------------------------------------------------ normals
+@pytest.mark.parametrize("k", [10, 20, 50])
+def test_normals_knn_parity(ctx, orc, small, k):
+    model, scene = small
+    for cloud_np in (model, scene):
+        cl = ctx.cloud(cloud_np)
+        got = ctx.normals(cl, k=k)
+        ref = orc.normals(cloud_np, k=k)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        err = np.abs(got - ref)
+        # float32 covariance sums are bit-identical; only the libm calls in eigen33 differ by an ulp
+        assert np.nanmax(err[:, :3]) < 2e-4, np.nanmax(err[:, :3])
+        assert np.nanmedian(err[:, :3]) < 1e-6
+        assert np.nanmax(err[:, 3]) < 2e-4
+        assert np.mean(np.all(err[:, :3] < 1e-5, axis=1)) > 0.995
+
+
+def test_normals_radius_and_nan(ctx, orc, synth):
+    scene = synth.make_scene(("horizontal",), 20000, scene_id=2)
+    kp = synth.voxel_grid(scene, 0.03)
+    cl = ctx.cloud(kp)
+    got = ctx.normals(cl, radius=0.15)          # FPFH_demo.cpp:416-420: normals on the keypoints
+    ref = orc.normals(kp, radius=0.15)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.nanmax(np.abs(got - ref)) < 2e-4
+    s = scene[:5000].copy()
+    s[7] = np.nan
+    cl2 = ctx.cloud(s)
+    got = ctx.normals(cl2, k=10)
+    ref = orc.normals(s, k=10)
+    assert np.all(np.isnan(got[7])) and np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.nanmax(np.abs(got - ref)) < 2e-4
+    # explicit query cloud (input != surface) and a non-default viewpoint
+    q = s[100:400]
+    got = ctx.normals(cl2, q=q, k=15, viewpoint=(0.5, 0.5, 3.0))
+    ref = orc.normals(s, q=q, k=15, viewpoint=(0.5, 0.5, 3.0))
+    assert np.nanmax(np.abs(got - ref)) < 2e-4
+    # Feature::initCompute: k and radius are exclusive
+    with pytest.raises(Exception):
+        ctx.normals(cl2, k=10, radius=0.1)
+    with pytest.raises(Exception):
+        ctx.normals(cl2, k=0, radius=0.0)
+
+
+# ------------------------------------------------------------------------------------------ SHOT
+def _desc_check(got, ref, tol=1e-4):
+    assert np.array_equal(np.isnan(got[:, 0]), np.isnan(ref[:, 0]))
+    ok = ~np.isnan(ref[:, 0])
+    err = np.linalg.norm(got[ok].astype(np.float64) - ref[ok].astype(np.float64), axis=1)
+    return err
+
+
+def test_shot_parity(ctx, orc, synth, small):
+    model, scene = small
+    for cloud_np, kp, r in ((model, synth.voxel_grid(model, 0.02), 0.02),
+                            (scene, synth.voxel_grid(scene, 0.03), 0.02),
+                            (scene, synth.uniform_sampling(scene, 0.04), 0.035)):
+        nrm = orc.normals(cloud_np, k=10)
+        cl = ctx.cloud(cloud_np)
+        lrf = ctx.shot_lrf(cl, kp, r)
+        olrf = orc.shot_lrf(cloud_np, kp, r)
+        assert np.array_equal(np.isnan(lrf), np.isnan(olrf))
+        assert np.nanmax(np.abs(lrf - olrf)) < 1e-5
+        desc, rf = ctx.shot352(cl, nrm, kp, r)
+        odesc, orf = orc.shot352(cloud_np, nrm, kp, r)
+        err = _desc_check(desc, odesc)
+        assert err.max() < 1e-4, err.max()
+        assert np.array_equal(np.isnan(rf), np.isnan(orf))
+        assert np.nanmax(np.abs(rf - orf)) < 1e-5
+        ok = ~np.isnan(desc[:, 0])
+        np.testing.assert_allclose(np.linalg.norm(desc[ok], axis=1), 1.0, atol=1e-5)
+
+
+def test_shot_whole_model_support(ctx, orc, synth):
+    # SHOT_demo.cpp:497-502: model descriptors with radius 50 (every point is a neighbour)
+    model = synth.make_model("y", 6000)
+    kp = synth.voxel_grid(model, 0.04)
+    nrm = orc.normals(model, k=20)
+    cl = ctx.cloud(model)
+    desc, rf = ctx.shot352(cl, nrm, kp, 50.0)
+    odesc, orf = orc.shot352(model, nrm, kp, 50.0)
+    err = _desc_check(desc, odesc)
+    assert err.max() < 1e-4, err.max()
+
+
+def test_shot_nan_rows(ctx, orc):
+    s = _rng(9).uniform(-1, 1, (300, 3)).astype(np.float32)
+    nrm = orc.normals(s, k=5)
+    nrm[5] = np.nan                                  # a NaN normal is skipped, not fatal
+    kp = np.concatenate([s[:20], [[10, 10, 10]], [[np.nan, 0, 0]]]).astype(np.float32)
+    cl = ctx.cloud(s)
+    desc, rf = ctx.shot352(cl, nrm, kp, 0.4)
+    odesc, orf = orc.shot352(s, nrm, kp, 0.4)
+    assert np.array_equal(np.isnan(desc), np.isnan(odesc))
+    assert np.all(np.isnan(desc[-2:])) and np.all(np.isnan(rf[-2:]))
+    ok = ~np.isnan(odesc[:, 0])
+    assert np.linalg.norm(desc[ok] - odesc[ok], axis=1).max() < 1e-4
+    d0, _ = ctx.shot352(cl, nrm, np.zeros((0, 3), np.float32), 0.4)
+    assert d0.shape == (0, 352)
+
+
+# ------------------------------------------------------------------------------------------ FPFH
+def test_fpfh_parity(ctx, orc, synth, small):
+    model, scene = small
+    for cloud_np, leaf, r in ((model, 0.01, 0.05), (scene, 0.03, 0.15)):
+        kp = synth.voxel_grid(cloud_np, leaf)
+        nrm = orc.normals(kp, radius=r)
+        cl = ctx.cloud(kp)
+        got = ctx.fpfh33(cl, nrm, r)
+        ref = orc.fpfh33(kp, nrm, r)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref[:, 0])
+        nrm_ref = np.linalg.norm(ref[ok], axis=1)
+        rel = np.linalg.norm(got[ok].astype(np.float64) - ref[ok], axis=1) / nrm_ref
+        # 1e-4 L2 relative to the descriptor norm (FPFH blocks sum to 100, |d| ~ 60..170)
+        assert rel.max() < 1e-4, rel.max()
+        np.testing.assert_allclose(got[ok].reshape(-1, 3, 11).sum(2), 100.0, atol=2e-3)
+        # explicit query set (input != surface)
+        got_q = ctx.fpfh33(cl, nrm, r, q=kp[::9])
+        ref_q = orc.fpfh33(kp, nrm, r, q=kp[::9])
+        okq = ~np.isnan(ref_q[:, 0])
+        relq = np.linalg.norm(got_q[okq] - ref_q[okq], axis=1) / np.linalg.norm(ref_q[okq], axis=1)
+        assert relq.max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ matching
+def test_match_bit_exact(ctx, orc):
+    rng = _rng(11)
+    for D, Km, Ks in ((352, 700, 1500), (33, 257, 999), (352, 1, 10)):
+        a = rng.uniform(0, 1, (Km, D)).astype(np.float32)
+        a /= np.linalg.norm(a, axis=1, keepdims=True)
+        b = a[rng.integers(0, Km, Ks)] + rng.normal(0, 0.03, (Ks, D)).astype(np.float32)
+        b[3, 0] = np.nan
+        if Km > 5:
+            a[4, D - 1] = np.inf
+            b[5] = a[2]                   # exact duplicate → distance 0
+        for mode, thr in ((1, 0.25), (1, 0.05), (2, 0.0)):
+            got = ctx.match(a, b, mode, thr)
+            ref = orc.match(a, b, mode, thr)
+            assert np.array_equal(got["index_query"], ref["index_query"])
+            assert np.array_equal(got["index_match"], ref["index_match"])
+            assert np.array_equal(got["distance"], ref["distance"])
+    assert len(ctx.match(np.zeros((0, 352), np.float32), np.ones((5, 352), np.float32))) == 0
+    assert len(ctx.match(np.ones((5, 352), np.float32), np.zeros((0, 352), np.float32))) == 0
+
+
+def test_match_real_descriptors(ctx, orc, synth, small):
+    model, scene = small
+    kpm, kps = synth.voxel_grid(model, 0.02), synth.voxel_grid(scene, 0.03)
+    dm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, 0.02)
+    ds, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, 0.02)
+    for mode in (1, 2):
+        got = ctx.match(dm, ds, mode, 0.25)
+        ref = orc.match(dm, ds, mode, 0.25)
+        assert len(ref) > 0
+        assert got.tobytes() == ref.tobytes()
+
+
+# ------------------------------------------------------------------------------------------ grouping
+def _gc_case(seed, n_model=80, n_in=60, n_out=50):
+    from scipy.spatial.transform import Rotation
+    rng = _rng(seed)
+    R = Rotation.random(random_state=seed).as_matrix()
+    t = rng.uniform(-1, 1, 3)
+    model = rng.uniform(-0.3, 0.3, (n_model, 3)).astype(np.float32)
+    scene_in = (model.astype(np.float64) @ R.T + t + rng.normal(0, 0.0005, (n_model, 3))).astype(np.float32)
+    clutter = rng.uniform(-2, 2, (100, 3)).astype(np.float32)
+    scene = np.concatenate([scene_in, clutter])
+    return rng, R, t, model, scene
+
+
+def test_gc_parity(ctx, orc, b200):
+    for seed in (21, 22, 23):
+        rng, R, t, model, scene = _gc_case(seed)
+        C = 110
+        corrs = np.zeros(C, dtype=b200.CORR_DTYPE)
+        corrs["index_query"][:60] = rng.permutation(80)[:60]
+        corrs["index_match"][:60] = corrs["index_query"][:60]
+        corrs["index_query"][60:] = rng.integers(0, 80, C - 60)      # outliers, duplicate model indices
+        corrs["index_match"][60:] = rng.integers(80, 180, C - 60)
+        corrs["distance"] = rng.uniform(0, 0.2, C).astype(np.float32)
+        corrs["distance"][5] = corrs["distance"][6]                    # a distance tie
+        corrs = corrs[rng.permutation(C)]
+        for thr in (2, 5):
+            T, inst, n = ctx.gc_recognize(model, scene, corrs, 0.01, thr)
+            oT, oinst = orc.gc_recognize(model, scene, corrs, 0.01, thr)
+            assert n == len(oT)
+            assert [len(i) for i in inst] == [len(i) for i in oinst]
+            for a, b in zip(inst, oinst):
+                assert a.tobytes() == b.tobytes()
+            for A, B in zip(T, oT):
+                assert np.abs(A[:3, 3] - B[:3, 3]).max() < 1e-4
+                assert _rot_angle_deg(A[:3, :3].astype(np.float64), B[:3, :3].astype(np.float64)) < 0.01
+            b = int(np.argmax([len(i) for i in inst]))
+            assert np.abs(T[b][:3, 3] - t).max() < 5e-3
+    # empty / tiny inputs
+    T, inst, n = ctx.gc_recognize(model, scene, corrs[:0], 0.01, 2)
+    assert n == 0
+    T, inst, n = ctx.gc_recognize(model, scene, corrs[:2], 0.01, 2)
+    assert n == 0
+
+
+def test_gc_many_small_instances(ctx, orc, synth, small, b200):
+    # gc_threshold = 2 on noisy descriptor matches yields hundreds of 3-4 element instances
+    model, scene = small
+    kpm, kps = synth.voxel_grid(model, 0.02), synth.voxel_grid(scene, 0.03)
+    dm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, 0.02)
+    ds, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, 0.02)
+    corrs = orc.match(dm, ds, 1, 0.25)
+    assert len(corrs) > 100
+    T, inst, n = ctx.gc_recognize(kpm, kps, corrs, 0.02, 2, max_inst=2048)
+    oT, oinst = orc.gc_recognize(kpm, kps, corrs, 0.02, 2, max_inst=2048)
+    assert n == len(oT) and n > 0
+    for a, b in zip(inst, oinst):
+        assert a.tobytes() == b.tobytes()
+    dT = max(np.abs(A - B).max() for A, B in zip(T, oT))
+    assert dT < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ pipeline
+def test_register_scene_pipeline(ctx, orc, synth, b200):
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 60000, scene_id=0)
+    kpm, kps = synth.voxel_grid(model, 0.02), synth.voxel_grid(scene, 0.03)
+    p = b200.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=2048)
+    m = ctx.model_create_shot(model, kpm, p)
+    dm, kk = m.download()
+    odm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, 0.02)
+    assert np.array_equal(kk, kpm)
+    assert _desc_check(dm, odm).max() < 1e-4
+    res = ctx.register_scene_shot(m, scene, kps, p)
+    ods, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, 0.02)
+    # oracle chain on the oracle's own descriptors; correspondence lists must agree except where a
+    # descriptor distance sits within 1e-5 of the threshold / of the runner-up
+    oc = orc.match(odm, ods, 1, 0.25)
+    gc_ = res["corrs"]
+    same = set(map(tuple, gc_[["index_query", "index_match"]].tolist()))
+    osame = set(map(tuple, oc[["index_query", "index_match"]].tolist()))
+    assert len(same ^ osame) <= max(2, 0.002 * len(osame))
+    # grouping parity on identical correspondences
+    T, inst, n = ctx.gc_recognize(kpm, kps, gc_, 0.02, 2, max_inst=2048)
+    assert n == res["n_instances"]
+    for a, b in zip(inst, res["instances"]):
+        assert a.tobytes() == b.tobytes()
+    oT, oinst = orc.gc_recognize(kpm, kps, gc_, 0.02, 2, max_inst=2048)
+    assert n == len(oT)
+    for a, b in zip(inst, oinst):
+        assert a.tobytes() == b.tobytes()
+    assert max(np.abs(A - B).max() for A, B in zip(res["transforms"], oT)) < 1e-4
+    assert ctx.launches > 0
+    m.close()
