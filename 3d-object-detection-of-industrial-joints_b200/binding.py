@@ -24,6 +24,8 @@ EXPORTS = [
     "b200_dev_shot352", "b200_fpfh33", "b200_dev_fpfh33", "b200_match", "b200_dev_match", "b200_gc_recognize",
     "b200_model_create_shot", "b200_model_destroy", "b200_model_size", "b200_model_download",
     "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
+    "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
+    "b200_ctx_stage_time",
 ]
 
 
@@ -89,6 +91,10 @@ def lib():
             "b200_dev_register_scene_shot": [vp, vp, vp, i, i, vp, i, i, C.POINTER(ShotParams), vp, vp, vp, vp, i, vp,
                                              vp, vp, vp],
             "b200_last_neighbor_stats": [vp, C.POINTER(d), ip],
+            "b200_ctx_set_profiling": [vp, i],
+            "b200_ctx_reset_profiling": [vp],
+            "b200_ctx_stage_count": [],
+            "b200_ctx_stage_time": [vp, i, C.POINTER(d), ip],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -96,6 +102,8 @@ def lib():
             fn.restype = C.c_int
         L.b200_last_error.argtypes = [vp]
         L.b200_last_error.restype = C.c_char_p
+        L.b200_ctx_stage_name.argtypes = [i]
+        L.b200_ctx_stage_name.restype = C.c_char_p
         L.b200_abi_version.argtypes = []
         L.b200_abi_version.restype = C.c_int
         L.b200_ctx_launch_count.argtypes = [vp]
@@ -201,6 +209,21 @@ class Context:
     @property
     def launches(self):
         return int(lib().b200_ctx_launch_count(self.h))
+
+    def set_profiling(self, on=True):
+        self._chk(lib().b200_ctx_set_profiling(self.h, 1 if on else 0))
+
+    def reset_profiling(self):
+        self._chk(lib().b200_ctx_reset_profiling(self.h))
+
+    def stage_times(self):
+        """{stage name: (total ms, calls)} since the last reset (synchronises the stream)."""
+        out = {}
+        for s in range(lib().b200_ctx_stage_count()):
+            ms, n = C.c_double(), C.c_int()
+            self._chk(lib().b200_ctx_stage_time(self.h, s, C.byref(ms), C.byref(n)))
+            out[lib().b200_ctx_stage_name(s).decode()] = (ms.value, n.value)
+        return out
 
     def neighbor_stats(self):
         m, mx = C.c_double(), C.c_int()

@@ -194,6 +194,11 @@ int b200_ctx_destroy(b200_ctx *ctx) {
   if (!ctx) return B200_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto &ev : ctx->stage_events) {
+    cudaEventDestroy(ev.a);
+    cudaEventDestroy(ev.b);
+  }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200_OK;
@@ -206,6 +211,54 @@ int b200_ctx_sync(b200_ctx *ctx) {
 }
 
 int64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int resolve_stage_events(b200_ctx *ctx) {
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto &ev : ctx->stage_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {
+      ctx->stage_ms[ev.stage] += ms;
+      ctx->stage_n[ev.stage] += 1;
+    }
+    ctx->event_pool.push_back(ev.a);
+    ctx->event_pool.push_back(ev.b);
+  }
+  ctx->stage_events.clear();
+  return B200_OK;
+}
+
+int b200_ctx_set_profiling(b200_ctx *ctx, int enable) {
+  API_ENTER(ctx);
+  ctx->profiling = enable != 0;
+  return B200_OK;
+}
+
+int b200_ctx_reset_profiling(b200_ctx *ctx) {
+  API_ENTER(ctx);
+  B200_TRY(resolve_stage_events(ctx));
+  for (int i = 0; i < ST_COUNT; ++i) {
+    ctx->stage_ms[i] = 0.0;
+    ctx->stage_n[i] = 0;
+  }
+  return B200_OK;
+}
+
+int b200_ctx_stage_count(void) { return ST_COUNT; }
+
+const char *b200_ctx_stage_name(int stage) {
+  static const char *names[ST_COUNT] = {"grid_build", "normals", "neighbor_count", "shot", "fpfh",
+                                        "match",      "gc_sort", "gc_group",       "gc_ransac"};
+  return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
+}
+
+int b200_ctx_stage_time(b200_ctx *ctx, int stage, double *total_ms, int *calls) {
+  API_ENTER(ctx);
+  if (stage < 0 || stage >= ST_COUNT) return ctx->fail(B200_ERR_INVALID, "stage out of range");
+  B200_TRY(resolve_stage_events(ctx));
+  if (total_ms) *total_ms = ctx->stage_ms[stage];
+  if (calls) *calls = ctx->stage_n[stage];
+  return B200_OK;
+}
 
 int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs) {
   if (!ctx) return B200_ERR_INVALID;

@@ -8,10 +8,35 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/b200reg.h"
 
+// pipeline stages timed with CUDA events on the context's stream when profiling is enabled
+enum b200_stage {
+  ST_GRID = 0,
+  ST_NORMALS,
+  ST_NBR_COUNT,
+  ST_SHOT,
+  ST_FPFH,
+  ST_MATCH,
+  ST_GC_SORT,
+  ST_GC_GROUP,
+  ST_GC_RANSAC,
+  ST_COUNT
+};
+
+struct StageEvent {
+  cudaEvent_t a, b;
+  int stage;
+};
+
 struct b200_ctx {
+  bool profiling = false;
+  std::vector<StageEvent> stage_events;
+  std::vector<cudaEvent_t> event_pool;
+  double stage_ms[ST_COUNT] = {0};
+  int stage_n[ST_COUNT] = {0};
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -87,6 +112,35 @@ struct DevBuf {
     cudaError_t e = cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream);
     if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaMemsetAsync", __FILE__, __LINE__);
     return B200_OK;
+  }
+};
+
+// Records a CUDA-event pair around a stage (only when profiling is on; otherwise free).
+struct StageScope {
+  b200_ctx *ctx;
+  StageEvent ev;
+  bool on;
+  StageScope(b200_ctx *c, int stage) : ctx(c), on(c->profiling) {
+    if (!on) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!ctx->event_pool.empty()) {
+        e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    ev.a = get();
+    ev.b = get();
+    ev.stage = stage;
+    cudaEventRecord(ev.a, ctx->stream);
+  }
+  ~StageScope() {
+    if (!on) return;
+    cudaEventRecord(ev.b, ctx->stream);
+    ctx->stage_events.push_back(ev);
   }
 };
 

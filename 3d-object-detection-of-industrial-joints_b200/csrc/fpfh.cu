@@ -304,6 +304,7 @@ int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
     B200_TRY(gk.alloc(ctx, (size_t)std::max(grid1, grid2) * cap));
     B200_TRY(gp.alloc(ctx, (size_t)std::max(grid1, grid2) * cap));
   }
+  StageScope st_(ctx, ST_FPFH);
   if (nv > 0) {
     spfh_kernel<<<grid1, FPFH_THREADS, in_smem ? smem : 0, ctx->stream>>>(*g, nrm_sorted.p, need.p, (float)radius, r2,
                                                                          cap, gk.p, gp.p, spfh.p);

@@ -495,9 +495,12 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   B200_TRY(sp.alloc(ctx, (size_t)C_cap));
   B200_TRY(taken.alloc(ctx, (size_t)C_cap));
   B200_TRY(taken.zero());
-  gc_rank_kernel<<<ceil_div(C_cap, 256), 256, 0, ctx->stream>>>(d_corrs, d_C, C_cap, d_model_kp, d_scene_kp, sorted.p,
-                                                               mp.p, sp.p);
-  B200_LAUNCHED(ctx);
+  {
+    StageScope st_(ctx, ST_GC_SORT);
+    gc_rank_kernel<<<ceil_div(C_cap, 256), 256, 0, ctx->stream>>>(d_corrs, d_C, C_cap, d_model_kp, d_scene_kp,
+                                                                 sorted.p, mp.p, sp.p);
+    B200_LAUNCHED(ctx);
+  }
 
   int per_sm = 0;
   B200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_group_kernel, GC_THREADS, 0));
@@ -519,8 +522,12 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   st.inst_offsets = d_inst_offsets;
   st.n_inst_out = d_n_inst;
   void *args[] = {&st, (void *)&d_C, &C_cap, &gc_size, &gc_threshold, &max_inst};
-  B200_CUDA(ctx, cudaLaunchCooperativeKernel((void *)gc_group_kernel, dim3(G), dim3(GC_THREADS), args, 0, ctx->stream));
-  ctx->launches++;
+  {
+    StageScope st_(ctx, ST_GC_GROUP);
+    B200_CUDA(ctx,
+              cudaLaunchCooperativeKernel((void *)gc_group_kernel, dim3(G), dim3(GC_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+  }
 
   B200_TRY(shuffled.alloc(ctx, (size_t)C_cap));
   B200_TRY(last_pos.alloc(ctx, (size_t)C_cap));
@@ -538,6 +545,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   rb.T_out = d_T;
   rb.inst_counts = d_inst_counts;
   rb.inst_corrs = d_inst_corrs;
+  StageScope st_(ctx, ST_GC_RANSAC);
   gc_ransac_kernel<<<max_inst, GC_THREADS, 0, ctx->stream>>>(rb, max_inst, corr_cap, gc_size, 10000);
   B200_LAUNCHED(ctx);
   return B200_OK;

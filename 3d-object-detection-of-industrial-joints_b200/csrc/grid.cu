@@ -112,6 +112,7 @@ __global__ void cell_scatter_kernel(const float4 *__restrict__ pts, int n, const
 
 int build_grid(b200_cloud *c, float cell, DeviceGrid &g) {
   b200_ctx *ctx = c->ctx;
+  StageScope st_(ctx, ST_GRID);
   g.valid = false;
   const float requested = cell;
   // bound the dense cell array: <= 2^25 cells

@@ -163,6 +163,7 @@ int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene,
   if (D <= 0 || Km < 0 || Ks < 0) return ctx->fail(B200_ERR_INVALID, "match: bad sizes");
   B200_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
   if (Ks == 0) return B200_OK;
+  StageScope st_(ctx, ST_MATCH);
   DevBuf<unsigned char> mvalid, svalid;
   DevBuf<int> nmv, zero_cnt, flags, slots;
   DevBuf<unsigned long long> best;

@@ -213,6 +213,7 @@ int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_
     const int T = knn_threads_for(k, &smem);
     if (smem > ctx->smem_optin) return ctx->fail(B200_ERR_INVALID, "normals: k too large for shared memory");
     B200_CUDA(ctx, cudaFuncSetAttribute(normals_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageScope st_(ctx, ST_NORMALS);
     if (q_is_surface) {
       // rows with non-finite coordinates are not in the grid: they keep NaN normals (PCL: is_dense=false)
       if (c->n_valid < c->n) {
@@ -247,6 +248,7 @@ int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_
   const float r2 = (float)(radius * radius);
   const int cap = next_pow2_host(std::max(max_count, 32));
   const size_t smem = (size_t)cap * 12;
+  StageScope st_(ctx, ST_NORMALS);
   if (smem <= 96 * 1024) {
     B200_CUDA(ctx,
               cudaFuncSetAttribute(normals_radius_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -108,6 +108,7 @@ int dev_knn_search(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, int 
 
 int dev_radius_count(b200_ctx *ctx, const GridView &g, const float4 *d_q, int nq, double radius, int *d_counts,
                      unsigned long long *d_stats) {
+  StageScope st_(ctx, ST_NBR_COUNT);
   if (d_stats) B200_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if (nq <= 0) return B200_OK;
   const float r2 = (float)(radius * radius);

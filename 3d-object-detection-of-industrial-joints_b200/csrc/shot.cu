@@ -351,6 +351,7 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
   ctx->last_max_nbrs = max_count;
   ctx->last_mean_nbrs = (double)hstats[1] / K;
 
+  StageScope st_(ctx, ST_SHOT);
   DevBuf<float4> nrm_sorted;
   if (!lrf_only) {
     B200_TRY(nrm_sorted.alloc(ctx, (size_t)std::max(c->n_valid, 1)));

@@ -1,0 +1,39 @@
+"""Multi-GPU layer: scenes (or views) are independent units, sharded round-robin across ranks with
+the model descriptor library replicated.  The only data-path exchange is the gather
+of the per-scene correspondence lists, which have a data-dependent length: one all_gather of the
+counts, then one padded all_gather of the 12-byte records (NCCL over NVLink on the GPU box; the same
+code runs on gloo/CPU tensors in the tests).  torch.distributed is plumbing only.
+"""
+import numpy as np
+
+CORR_WORDS = 3  # b200_corr = {int index_query, int index_match, float distance} = 3 x 4 bytes
+
+
+def scenes_for_rank(n_scenes, rank, world):
+    """scene s → rank s mod world."""
+    return list(range(rank, n_scenes, world))
+
+
+def gather_correspondences(corr_words, count, group=None):
+    """corr_words: (cap, 3) int32 tensor viewing this rank's b200_corr buffer; count: (1,) int32 tensor
+    with the number of valid rows.  Returns (all_counts (world,), all_corrs (world, cap, 3)) on every
+    rank.  Rows past a rank's count are padding."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    counts = torch.empty(world, dtype=count.dtype, device=count.device)
+    dist.all_gather_into_tensor(counts, count.reshape(1), group=group)
+    out = torch.empty((world,) + tuple(corr_words.shape), dtype=corr_words.dtype, device=corr_words.device)
+    dist.all_gather_into_tensor(out, corr_words.contiguous(), group=group)
+    return counts, out
+
+
+def unpack_gathered(counts, words):
+    """→ list (one per rank) of structured numpy correspondence arrays."""
+    dt = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
+    res = []
+    c = counts.cpu().numpy()
+    w = words.cpu().numpy()
+    for r in range(len(c)):
+        res.append(np.ascontiguousarray(w[r, :int(c[r])]).view(dt).reshape(-1))
+    return res

@@ -71,6 +71,15 @@ B200_API int b200_abi_version(void);
 /* Number of this library's kernel launches on the context since creation (bench gpu_launches). */
 B200_API int64_t b200_ctx_launch_count(const b200_ctx *ctx);
 
+/* Per-stage device timing (CUDA events on the context's stream) for bench.py's roofline line.
+ * Stages: 0 grid build, 1 normals, 2 neighbour count, 3 SHOT (LRF + descriptor), 4 FPFH, 5 matching,
+ * 6 GC sort, 7 GC grouping, 8 GC RANSAC.  b200_ctx_stage_time synchronises the stream. */
+B200_API int b200_ctx_set_profiling(b200_ctx *ctx, int enable);
+B200_API int b200_ctx_reset_profiling(b200_ctx *ctx);
+B200_API int b200_ctx_stage_count(void);
+B200_API const char *b200_ctx_stage_name(int stage);
+B200_API int b200_ctx_stage_time(b200_ctx *ctx, int stage, double *total_ms, int *calls);
+
 /* ---------------------------------------------------------------- search surface --------- */
 /* Replaces pcl::search::KdTree / KdTreeFLANN<PointXYZRGBA>::setInputCloud (built implicitly by
  * Feature::initCompute for every compute(); explicit at SHOT_VAR.cpp:350, Edge_detection.cpp:117).
