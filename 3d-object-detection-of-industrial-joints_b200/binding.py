@@ -6,6 +6,7 @@ library is missing or no B200 is present the calls raise — there is no CPU fal
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -143,11 +144,12 @@ def _dptr(t):
 class Cloud:
     def __init__(self, ctx, handle, n):
         self.ctx, self.h, self.n = ctx, handle, n
+        ctx._children.add(self)
 
     def close(self):
-        if self.h:
+        if self.h and self.ctx.h:      # clouds / models must be destroyed before their context
             lib().b200_cloud_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -159,6 +161,7 @@ class Cloud:
 class Model:
     def __init__(self, ctx, handle):
         self.ctx, self.h = ctx, handle
+        ctx._children.add(self)
 
     @property
     def size(self):
@@ -172,9 +175,9 @@ class Model:
         return desc, kp
 
     def close(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().b200_model_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -193,6 +196,7 @@ class Context:
         if rc != OK:
             raise B200Error(rc, lib().b200_last_error(None).decode())
         self.h = h
+        self._children = weakref.WeakSet()
 
     def _chk(self, rc):
         if rc != OK:
@@ -200,6 +204,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for ch in list(self._children):
+                ch.close()
             lib().b200_ctx_destroy(self.h)
             self.h = None
 

@@ -180,12 +180,6 @@ int b200_ctx_create(b200_ctx **out, int device, void *stream) {
     }
     ctx->own_stream = true;
   }
-  // keep freed scratch in the pool instead of returning it to the driver between calls
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   *out = ctx;
   return B200_OK;
 }
@@ -199,6 +193,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     cudaEventDestroy(ev.b);
   }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  ctx->arena_destroy();
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200_OK;

@@ -6,12 +6,18 @@
 // threshold are taken) followed per set by CorrespondenceRejectorSampleConsensus (RANSAC on
 // SampleConsensusModelRegistration, Umeyama on 3-samples, mt19937 seeded 12345).
 //
-// The greedy order is kept exactly.  Failing seeds do not change any state, so a window of the next
-// G seeds (one per CTA of a persistent cooperative grid) is evaluated speculatively against the
-// current `taken` flags; the first seed of the window whose set is large enough is committed and the
-// window restarts behind it.  Inside a seed, 256 candidates are tested per step against the set so
-// far; candidates that survive are admitted in index order, each admission re-testing the later
-// survivors, which is the sequential rule.  RANSAC runs afterwards, one CTA per instance.
+// The greedy order is kept exactly.  A seed's consensus set depends on earlier seeds only through
+// the `taken` flags, and only successful seeds change those.  A persistent cooperative grid therefore
+// evaluates a window of the next G seeds (one per CTA) speculatively against the current flags; the
+// successful seeds of the window mark their members (atomicMin of the window position), every seed
+// then checks whether one of its own members was claimed by an EARLIER successful position — if not,
+// its result is what the sequential algorithm would have computed.  All successes before the first
+// conflicting position commit at once and the window restarts at the conflict.  Inside a seed, 1024
+// candidates are tested per step against the set so far; survivors are admitted in index order, each
+// admission re-testing the later survivors, which is the sequential rule.
+// RANSAC runs afterwards, one CTA per instance: thread 0 draws the sample sequence (the RNG stream
+// is inherently serial), 16 warps fit and score 16 samples at a time, thread 0 then replays the
+// adaptive-termination logic in order and discards the samples past the stopping point.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -24,7 +30,10 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int GC_THREADS = 256;
+constexpr int GC_PER_THREAD = 4;
+constexpr int GC_STEP = GC_THREADS * GC_PER_THREAD;
 constexpr int GC_MEMBER_CACHE = 512;  // member points kept in shared memory
+constexpr int GC_INF = 0x7f7f7f7f;    // memset(0x7f) pattern
 
 // ---- sort by (distance, original position): rank by counting -----------------------------------
 __global__ void __launch_bounds__(256)
@@ -53,10 +62,8 @@ __global__ void __launch_bounds__(256)
   }
   if (i < C) {
     sorted[rank] = mine;
-    float4 m = model_kp[mine.index_query];
-    float4 s = scene_kp[mine.index_match];
-    mp[rank] = m;
-    sp[rank] = s;
+    mp[rank] = model_kp[mine.index_query];
+    sp[rank] = scene_kp[mine.index_match];
   }
 }
 
@@ -79,11 +86,13 @@ struct GcState {
   const b200_corr *sorted;
   const float4 *mp;
   const float4 *sp;
-  unsigned char *taken;
-  int *res_size;       // [G]
-  int *scratch;        // [G][C_cap] member lists of the seeds under evaluation
-  int *members;        // [C_cap] committed member lists, concatenated
-  int *inst_offsets;   // [max_inst + 1]
+  unsigned char *taken;  // [C_cap + 4]
+  int *mark;             // [C_cap], GC_INF when unclaimed
+  int *res_size;         // [G]
+  int *conf;             // [G]
+  int *scratch;          // [G][C_cap] member lists of the seeds under evaluation
+  int *members;          // [C_cap] committed member lists, concatenated
+  int *inst_offsets;     // [max_inst + 1]
   int *n_inst_out;
 };
 
@@ -94,17 +103,17 @@ __global__ void __launch_bounds__(GC_THREADS)
   __shared__ float4 s_mp[GC_MEMBER_CACHE];
   __shared__ float4 s_sp[GC_MEMBER_CACHE];
   __shared__ unsigned s_mask[GC_THREADS / 32];
-  __shared__ int s_first;
+  __shared__ int s_red[5];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int G = gridDim.x;
+  const int G = gridDim.x, bid = blockIdx.x;
   const int C = min(*d_C, C_cap);
-  int *my_members = st.scratch + (size_t)blockIdx.x * C_cap;
+  int *my_members = st.scratch + (size_t)bid * C_cap;
   int cur = 0, n_inst = 0, total_members = 0;
-  if (blockIdx.x == 0 && tid == 0) st.inst_offsets[0] = 0;
+  if (bid == 0 && tid == 0) st.inst_offsets[0] = 0;
 
   while (cur < C) {
     // ---- evaluate the seed of this CTA against the current `taken` flags ----
-    const int seed = cur + blockIdx.x;
+    const int seed = cur + bid;
     int size = 0;
     if (seed < C && !__ldcg(&st.taken[seed])) {
       if (tid == 0) {
@@ -114,32 +123,41 @@ __global__ void __launch_bounds__(GC_THREADS)
       }
       size = 1;
       __syncthreads();
-      for (int base = 0; base < C; base += GC_THREADS) {
-        const int j = base + tid;
-        bool alive = (j < C) && (j != seed) && !__ldcg(&st.taken[j]);
-        float4 mj, sj;
-        if (alive) {
-          mj = st.mp[j];
-          sj = st.sp[j];
-          for (int k = 0; k < size; ++k) {
-            float4 mk, sk;
-            if (k < GC_MEMBER_CACHE) {
-              mk = s_mp[k];
-              sk = s_sp[k];
-            } else {
-              const int mi = my_members[k];
-              mk = st.mp[mi];
-              sk = st.sp[mi];
-            }
-            if (gc_rejects(mk, sk, mj, sj, gc_size)) {
-              alive = false;
-              break;
-            }
+      for (int base = 0; base < C; base += GC_STEP) {
+        const int j0 = base + tid * GC_PER_THREAD;
+        unsigned alive = 0;
+        float4 mj[GC_PER_THREAD], sj[GC_PER_THREAD];
+        if (j0 < C) {
+          const unsigned tk = __ldcg(reinterpret_cast<const unsigned *>(st.taken + j0));  // 4 flags
+#pragma unroll
+          for (int u = 0; u < GC_PER_THREAD; ++u) {
+            const int j = j0 + u;
+            if (j < C && j != seed && ((tk >> (8 * u)) & 0xffu) == 0) alive |= 1u << u;
           }
         }
+#pragma unroll
+        for (int u = 0; u < GC_PER_THREAD; ++u)
+          if ((alive >> u) & 1u) {
+            mj[u] = st.mp[j0 + u];
+            sj[u] = st.sp[j0 + u];
+          }
+        for (int k = 0; k < size && alive; ++k) {
+          float4 mk, sk;
+          if (k < GC_MEMBER_CACHE) {
+            mk = s_mp[k];
+            sk = s_sp[k];
+          } else {
+            const int mi = my_members[k];
+            mk = st.mp[mi];
+            sk = st.sp[mi];
+          }
+#pragma unroll
+          for (int u = 0; u < GC_PER_THREAD; ++u)
+            if (((alive >> u) & 1u) && gc_rejects(mk, sk, mj[u], sj[u], gc_size)) alive &= ~(1u << u);
+        }
         // admit survivors in index order; each admission re-tests the later survivors
-        while (true) {
-          const unsigned m = __ballot_sync(0xffffffffu, alive);
+        while (__syncthreads_or(alive != 0)) {
+          const unsigned m = __ballot_sync(0xffffffffu, alive != 0);
           if (lane == 0) s_mask[warp] = m;
           __syncthreads();
           int first = -1;
@@ -148,62 +166,106 @@ __global__ void __launch_bounds__(GC_THREADS)
             const unsigned mw = s_mask[w];
             if (first < 0 && mw) first = w * 32 + __ffs(mw) - 1;
           }
-          if (first < 0) {
-            __syncthreads();
-            break;
-          }
           if (tid == first) {
-            my_members[size] = j;
+            const int u = __ffs(alive) - 1;
+            my_members[size] = j0 + u;
             if (size < GC_MEMBER_CACHE) {
-              s_mp[size] = mj;
-              s_sp[size] = sj;
+              // dynamic register-array index avoided: select by u
+              float4 a = mj[0], b = sj[0];
+#pragma unroll
+              for (int v = 1; v < GC_PER_THREAD; ++v)
+                if (u == v) {
+                  a = mj[v];
+                  b = sj[v];
+                }
+              s_mp[size] = a;
+              s_sp[size] = b;
             }
-            alive = false;
+            alive &= ~(1u << u);
           }
           __syncthreads();
-          // new member = candidate `first` of this chunk
           float4 mk, sk;
           if (size < GC_MEMBER_CACHE) {
             mk = s_mp[size];
             sk = s_sp[size];
           } else {
-            const int mi = base + first;
+            const int mi = my_members[size];
             mk = st.mp[mi];
             sk = st.sp[mi];
           }
           ++size;
-          if (alive && gc_rejects(mk, sk, mj, sj, gc_size)) alive = false;
+#pragma unroll
+          for (int u = 0; u < GC_PER_THREAD; ++u)
+            if (((alive >> u) & 1u) && gc_rejects(mk, sk, mj[u], sj[u], gc_size)) alive &= ~(1u << u);
         }
       }
     }
-    if (tid == 0) st.res_size[blockIdx.x] = size;
+    // ---- publish: size, and successful seeds claim their members with their window position ----
+    const bool succ = size > gc_threshold;
+    if (tid == 0) st.res_size[bid] = size;
+    if (succ)
+      for (int k = tid; k < size; k += GC_THREADS) atomicMin(&st.mark[my_members[k]], bid);
     grid.sync();
-    // ---- every CTA finds the first successful seed of the window (identical result everywhere) ----
-    if (tid == 0) s_first = 0x7fffffff;
+    // ---- conflict: one of my members (or my seed) belongs to an earlier successful seed ----
+    int conflict = 0;
+    for (int k = tid; k < size; k += GC_THREADS)
+      if (__ldcg(&st.mark[my_members[k]]) < bid) conflict = 1;
+    conflict = __syncthreads_or(conflict);
+    if (tid == 0) st.conf[bid] = conflict;
+    grid.sync();
+    // ---- everything before the first conflicting position is exact: commit its successes ----
+    if (tid < 5) s_red[tid] = (tid == 0) ? G : 0;
     __syncthreads();
     for (int b = tid; b < G; b += GC_THREADS)
-      if (__ldcg(&st.res_size[b]) > gc_threshold) atomicMin(&s_first, b);
+      if (__ldcg(&st.conf[b])) atomicMin(&s_red[0], b);
     __syncthreads();
-    const int first = s_first;
-    if (first < G) {
-      const int wsize = __ldcg(&st.res_size[first]);
-      if (first == (int)blockIdx.x) {
-        for (int k = tid; k < wsize; k += GC_THREADS) {
-          const int mi = my_members[k];
-          st.members[total_members + k] = mi;
-          st.taken[mi] = 1;
+    const int pstar = s_red[0];
+    {
+      int tot = 0, cnt = 0, off = 0, idx = 0;
+      for (int b = tid; b < pstar; b += GC_THREADS) {
+        const int sz = __ldcg(&st.res_size[b]);
+        if (sz > gc_threshold) {
+          tot += sz;
+          ++cnt;
+          if (b < bid) {
+            off += sz;
+            ++idx;
+          }
         }
-        if (tid == 0 && n_inst < max_inst) st.inst_offsets[n_inst + 1] = total_members + wsize;
       }
-      total_members += wsize;
-      ++n_inst;
-      cur += first + 1;
-    } else {
-      cur += G;
+      tot = warp_sum(tot);
+      cnt = warp_sum(cnt);
+      off = warp_sum(off);
+      idx = warp_sum(idx);
+      if (lane == 0) {
+        atomicAdd(&s_red[1], tot);
+        atomicAdd(&s_red[2], cnt);
+        atomicAdd(&s_red[3], off);
+        atomicAdd(&s_red[4], idx);
+      }
     }
+    __syncthreads();
+    if (succ) {
+      if (bid < pstar) {
+        const int o = total_members + s_red[3];
+        for (int k = tid; k < size; k += GC_THREADS) {
+          const int mi = my_members[k];
+          st.members[o + k] = mi;
+          st.taken[mi] = 1;
+          st.mark[mi] = GC_INF;
+        }
+        const int inst = n_inst + s_red[4];
+        if (tid == 0 && inst < max_inst) st.inst_offsets[inst + 1] = o + size;
+      } else {
+        for (int k = tid; k < size; k += GC_THREADS) st.mark[my_members[k]] = GC_INF;
+      }
+    }
+    total_members += s_red[1];
+    n_inst += s_red[2];
+    cur += pstar;
     grid.sync();
   }
-  if (blockIdx.x == 0 && tid == 0) *st.n_inst_out = n_inst;
+  if (bid == 0 && tid == 0) *st.n_inst_out = n_inst;
 }
 
 // ---- RANSAC pose per instance -------------------------------------------------------------------
@@ -247,14 +309,36 @@ struct RansacBuffers {
   b200_corr *inst_corrs;
 };
 
-__global__ void __launch_bounds__(GC_THREADS)
+constexpr int RS_THREADS = 512;
+constexpr int RS_BATCH = RS_THREADS / 32;
+
+// squared residual of correspondence (s → g) under the row-major 4x4 float transform T
+__device__ __forceinline__ float residual2(const float *T, const float4 &s, const float4 &g) {
+  float e[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float v = T[r * 4 + 0] * s.x;
+    v += T[r * 4 + 1] * s.y;
+    v += T[r * 4 + 2] * s.z;
+    v += T[r * 4 + 3];
+    e[r] = v - (r == 0 ? g.x : (r == 1 ? g.y : g.z));
+  }
+  float d = e[0] * e[0];
+  d += e[1] * e[1];
+  d += e[2] * e[2];
+  return d;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
     gc_ransac_kernel(RansacBuffers rb, int max_inst, int corr_cap, double threshold, int max_iterations) {
   __shared__ unsigned s_mt[624];
-  __shared__ float s_T[16];
+  __shared__ float s_Tb[RS_BATCH][16];
+  __shared__ int s_sel[RS_BATCH][3];
+  __shared__ int s_cnt[RS_BATCH];
   __shared__ float s_bestT[16];
-  __shared__ int s_ctrl[4];    // 0: continue flag, 1: count accumulator
+  __shared__ int s_ctrl[4];  // 0: samples in this batch, 2: have_best
   __shared__ float s_acc[9];
-  __shared__ int s_warp_cnt[GC_THREADS / 32];
+  __shared__ int s_warp_cnt[RS_BATCH];
   const int b = blockIdx.x;
   const int n_inst = min(*rb.n_inst, max_inst);
   if (b >= n_inst) return;
@@ -268,7 +352,7 @@ __global__ void __launch_bounds__(GC_THREADS)
 
   // index maps keyed by the model index: the last correspondence with a given index_query wins
   // (std::map in computeOriginalIndexMapping, unordered_map index_to_correspondence)
-  for (int t = tid; t < n; t += GC_THREADS) {
+  for (int t = tid; t < n; t += RS_THREADS) {
     const int q = rb.sorted[mem[t]].index_query;
     int last = t;
     for (int u = t + 1; u < n; ++u)
@@ -307,12 +391,12 @@ __global__ void __launch_bounds__(GC_THREADS)
   rng.idx = 624;
   int iterations = 0, n_best = -2147483647;
   double k = 1.0;
-  unsigned skipped = 0;
+  const unsigned skipped = 0;  // computeModelCoefficients cannot fail for a 3-sample
   const unsigned max_skip = (unsigned)max_iterations * 10u;
   const double log_probability = log(1.0 - 0.99);
   const double one_over_indices = 1.0 / (double)n;
   const double thresh2 = threshold * threshold;
-  bool have_best = false;
+  bool have_best = false, stop = false;
   if (tid == 0) {
     const float *a = s_acc;
     float cov[9];
@@ -333,92 +417,100 @@ __global__ void __launch_bounds__(GC_THREADS)
   }
 
   while (true) {
-    // ---- thread 0: loop condition, sample selection, model from the 3-sample ----
+    // ---- thread 0: draw the next RS_BATCH samples of the (serial) sample sequence ----
     if (tid == 0) {
-      int go = ((double)iterations < k && skipped < max_skip) ? 1 : 0;
-      if (go && n < 3) go = 0;
-      if (go) {
-        bool good = false;
-        int sel[3] = {0, 0, 0};
-        for (int iter = 0; iter < 1000 && !good; ++iter) {
-          for (int i = 0; i < 3; ++i) {
-            const int r = (int)(rng.next() >> 1);
-            const int jx = i + (r % (n - i));
-            const int tmp = shuffled[i];
-            shuffled[i] = shuffled[jx];
-            shuffled[jx] = tmp;
+      int nb = 0;
+      bool draw_failed = false;
+      if (!stop && (double)iterations < k && skipped < max_skip && n >= 3) {
+        for (; nb < RS_BATCH; ++nb) {
+          bool good = false;
+          int sel[3] = {0, 0, 0};
+          for (int iter = 0; iter < 1000 && !good; ++iter) {  // SampleConsensusModel::getSamples
+            for (int i = 0; i < 3; ++i) {                     // drawIndexSample
+              const int r = (int)(rng.next() >> 1);
+              const int jx = i + (r % (n - i));
+              const int tmp = shuffled[i];
+              shuffled[i] = shuffled[jx];
+              shuffled[jx] = tmp;
+            }
+            sel[0] = shuffled[0];
+            sel[1] = shuffled[1];
+            sel[2] = shuffled[2];
+            const float4 p0 = rb.mp[mem[sel[0]]], p1 = rb.mp[mem[sel[1]]], p2 = rb.mp[mem[sel[2]]];
+            auto sq = [](const float4 &u, const float4 &v) {
+              const float dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z;
+              return dx * dx + dy * dy + dz * dz;
+            };
+            good = (double)sq(p1, p0) > sample_dist_thresh && (double)sq(p2, p0) > sample_dist_thresh &&
+                   (double)sq(p2, p1) > sample_dist_thresh;  // isSampleGood
           }
-          sel[0] = shuffled[0];
-          sel[1] = shuffled[1];
-          sel[2] = shuffled[2];
-          const float4 p0 = rb.mp[mem[sel[0]]], p1 = rb.mp[mem[sel[1]]], p2 = rb.mp[mem[sel[2]]];
-          auto sq = [](const float4 &u, const float4 &v) {
-            const float dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z;
-            return dx * dx + dy * dy + dz * dz;
-          };
-          good = (double)sq(p1, p0) > sample_dist_thresh && (double)sq(p2, p0) > sample_dist_thresh &&
-                 (double)sq(p2, p1) > sample_dist_thresh;
-        }
-        if (!good) {
-          go = 0;  // "No samples could be selected"
-        } else {
-          double src[9], dst[9];
-          for (int i = 0; i < 3; ++i) {
-            const float4 s = rb.mp[mem[sel[i]]];
-            const float4 t = rb.sp[mem[last_pos[sel[i]]]];
-            src[i * 3 + 0] = s.x;
-            src[i * 3 + 1] = s.y;
-            src[i * 3 + 2] = s.z;
-            dst[i * 3 + 0] = t.x;
-            dst[i * 3 + 1] = t.y;
-            dst[i * 3 + 2] = t.z;
+          if (!good) {
+            draw_failed = true;  // "No samples could be selected": the loop ends when it gets here
+            break;
           }
-          double Td[16];
-          umeyama3(src, dst, 3, Td);
-          for (int i = 0; i < 16; ++i) s_T[i] = (float)Td[i];
+          s_sel[nb][0] = sel[0];
+          s_sel[nb][1] = sel[1];
+          s_sel[nb][2] = sel[2];
         }
       }
-      s_ctrl[0] = go;
-      s_ctrl[1] = 0;
+      s_ctrl[0] = nb;
+      s_ctrl[1] = draw_failed ? 1 : 0;
     }
     __syncthreads();
-    if (!s_ctrl[0]) break;
-    // ---- all threads: countWithinDistance ----
-    int cnt = 0;
-    for (int t = tid; t < n; t += GC_THREADS) {
-      const float4 s = rb.mp[mem[t]];
-      const float4 g = rb.sp[mem[t]];
-      float e[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        float v = s_T[r * 4 + 0] * s.x;
-        v += s_T[r * 4 + 1] * s.y;
-        v += s_T[r * 4 + 2] * s.z;
-        v += s_T[r * 4 + 3];
-        e[r] = v - (r == 0 ? g.x : (r == 1 ? g.y : g.z));
+    const int nb = s_ctrl[0];
+    if (nb == 0) break;
+    // ---- warp w: model from sample w (computeModelCoefficients), then countWithinDistance ----
+    if (warp < nb) {
+      if (lane == 0) {
+        double src[9], dst[9];
+        for (int i = 0; i < 3; ++i) {
+          const int t = s_sel[warp][i];
+          const float4 s = rb.mp[mem[t]];
+          const float4 g = rb.sp[mem[last_pos[t]]];
+          src[i * 3 + 0] = s.x;
+          src[i * 3 + 1] = s.y;
+          src[i * 3 + 2] = s.z;
+          dst[i * 3 + 0] = g.x;
+          dst[i * 3 + 1] = g.y;
+          dst[i * 3 + 2] = g.z;
+        }
+        double Td[16];
+        umeyama3(src, dst, 3, Td);
+        for (int i = 0; i < 16; ++i) s_Tb[warp][i] = (float)Td[i];
       }
-      float d = e[0] * e[0];
-      d += e[1] * e[1];
-      d += e[2] * e[2];
-      cnt += ((double)d < thresh2) ? 1 : 0;
+      __syncwarp();
+      int cnt = 0;
+      for (int t = lane; t < n; t += 32)
+        cnt += ((double)residual2(s_Tb[warp], rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
+      cnt = warp_sum(cnt);
+      if (lane == 0) s_cnt[warp] = cnt;
     }
-    cnt = warp_sum(cnt);
-    if (lane == 0 && cnt) atomicAdd(&s_ctrl[1], cnt);
     __syncthreads();
+    // ---- thread 0: replay the sequential loop over the batch ----
     if (tid == 0) {
-      const int c = s_ctrl[1];
-      if (c > n_best) {
-        n_best = c;
-        have_best = true;
-        for (int i = 0; i < 16; ++i) s_bestT[i] = s_T[i];
-        const double w = (double)n_best * one_over_indices;
-        double p_no_outliers = 1.0 - pow(w, 3.0);
-        p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
-        p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
-        k = log_probability / log(p_no_outliers);
+      for (int i = 0; i < nb; ++i) {
+        if (i > 0 && !((double)iterations < k && skipped < max_skip)) {
+          stop = true;
+          break;
+        }
+        const int c = s_cnt[i];
+        if (c > n_best) {
+          n_best = c;
+          have_best = true;
+          for (int e = 0; e < 16; ++e) s_bestT[e] = s_Tb[i][e];
+          const double w = (double)n_best * one_over_indices;
+          double p_no_outliers = 1.0 - pow(w, 3.0);
+          p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
+          p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
+          k = log_probability / log(p_no_outliers);
+        }
+        ++iterations;
+        if (iterations > max_iterations) {
+          stop = true;  // "RANSAC reached the maximum number of trials"
+          break;
+        }
       }
-      ++iterations;
-      if (iterations > max_iterations) k = -1.0;  // "reached the maximum number of trials" → leave the loop
+      if (s_ctrl[1]) stop = true;
     }
     __syncthreads();
   }
@@ -428,37 +520,21 @@ __global__ void __launch_bounds__(GC_THREADS)
   const bool ok = s_ctrl[2] != 0;
   int n_inl = 0;
   if (ok) {
-    // flags + ordered compaction (block-wide, chunked)
+    // ordered compaction of the inlier positions (block-wide, chunked); flags[] receives the list
     int base_total = 0;
-    for (int base = 0; base < n; base += GC_THREADS) {
+    for (int base = 0; base < n; base += RS_THREADS) {
       const int t = base + tid;
       int f = 0;
-      if (t < n) {
-        const float4 s = rb.mp[mem[t]];
-        const float4 g = rb.sp[mem[t]];
-        float e[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          float v = s_bestT[r * 4 + 0] * s.x;
-          v += s_bestT[r * 4 + 1] * s.y;
-          v += s_bestT[r * 4 + 2] * s.z;
-          v += s_bestT[r * 4 + 3];
-          e[r] = v - (r == 0 ? g.x : (r == 1 ? g.y : g.z));
-        }
-        float d = e[0] * e[0];
-        d += e[1] * e[1];
-        d += e[2] * e[2];
-        f = ((double)d < thresh2) ? 1 : 0;
-      }
+      if (t < n) f = ((double)residual2(s_bestT, rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
       const unsigned m = __ballot_sync(0xffffffffu, f);
       if (lane == 0) s_warp_cnt[warp] = __popc(m);
       __syncthreads();
       int before = base_total, chunk_total = 0;
-      for (int w = 0; w < GC_THREADS / 32; ++w) {
+      for (int w = 0; w < RS_BATCH; ++w) {
         if (w < warp) before += s_warp_cnt[w];
         chunk_total += s_warp_cnt[w];
       }
-      if (f) flags[before + __popc(m & ((1u << lane) - 1u))] = t;  // flags[] reused as the ordered inlier list
+      if (f) flags[before + __popc(m & ((1u << lane) - 1u))] = t;
       base_total += chunk_total;
       __syncthreads();
     }
@@ -469,7 +545,7 @@ __global__ void __launch_bounds__(GC_THREADS)
   float *T = rb.T_out + (size_t)b * 16;
   if (tid < 16) T[tid] = use_model ? s_bestT[tid] : ((tid % 5 == 0) ? 1.0f : 0.0f);
   const int out_n = use_model ? n_inl : n;
-  for (int i = tid; i < out_n; i += GC_THREADS) {
+  for (int i = tid; i < out_n; i += RS_THREADS) {
     const int t = use_model ? last_pos[flags[i]] : i;
     if (off + i < corr_cap) rb.inst_corrs[off + i] = rb.sorted[mem[t]];
   }
@@ -489,12 +565,14 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   DevBuf<b200_corr> sorted;
   DevBuf<float4> mp, sp;
   DevBuf<unsigned char> taken;
-  DevBuf<int> res_size, scratch, members, shuffled, last_pos, flags;
+  DevBuf<int> mark, res_size, conf, scratch, members, shuffled, last_pos, flags;
   B200_TRY(sorted.alloc(ctx, (size_t)C_cap));
   B200_TRY(mp.alloc(ctx, (size_t)C_cap));
   B200_TRY(sp.alloc(ctx, (size_t)C_cap));
-  B200_TRY(taken.alloc(ctx, (size_t)C_cap));
+  B200_TRY(taken.alloc(ctx, (size_t)C_cap + 4));
   B200_TRY(taken.zero());
+  B200_TRY(mark.alloc(ctx, (size_t)C_cap));
+  B200_CUDA(ctx, cudaMemsetAsync(mark.p, 0x7f, sizeof(int) * (size_t)C_cap, ctx->stream));
   {
     StageScope st_(ctx, ST_GC_SORT);
     gc_rank_kernel<<<ceil_div(C_cap, 256), 256, 0, ctx->stream>>>(d_corrs, d_C, C_cap, d_model_kp, d_scene_kp,
@@ -509,6 +587,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   int G = ctx->sm_count * per_sm;
   G = std::max(1, std::min(G, C_cap));
   B200_TRY(res_size.alloc(ctx, (size_t)G));
+  B200_TRY(conf.alloc(ctx, (size_t)G));
   B200_TRY(scratch.alloc(ctx, (size_t)G * C_cap));
   B200_TRY(members.alloc(ctx, (size_t)C_cap));
   GcState st;
@@ -516,14 +595,16 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   st.mp = mp.p;
   st.sp = sp.p;
   st.taken = taken.p;
+  st.mark = mark.p;
   st.res_size = res_size.p;
+  st.conf = conf.p;
   st.scratch = scratch.p;
   st.members = members.p;
   st.inst_offsets = d_inst_offsets;
   st.n_inst_out = d_n_inst;
-  void *args[] = {&st, (void *)&d_C, &C_cap, &gc_size, &gc_threshold, &max_inst};
   {
     StageScope st_(ctx, ST_GC_GROUP);
+    void *args[] = {&st, (void *)&d_C, &C_cap, &gc_size, &gc_threshold, &max_inst};
     B200_CUDA(ctx,
               cudaLaunchCooperativeKernel((void *)gc_group_kernel, dim3(G), dim3(GC_THREADS), args, 0, ctx->stream));
     ctx->launches++;
@@ -546,7 +627,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   rb.inst_counts = d_inst_counts;
   rb.inst_corrs = d_inst_corrs;
   StageScope st_(ctx, ST_GC_RANSAC);
-  gc_ransac_kernel<<<max_inst, GC_THREADS, 0, ctx->stream>>>(rb, max_inst, corr_cap, gc_size, 10000);
+  gc_ransac_kernel<<<max_inst, RS_THREADS, 0, ctx->stream>>>(rb, max_inst, corr_cap, gc_size, 10000);
   B200_LAUNCHED(ctx);
   return B200_OK;
 }

@@ -12,6 +12,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -110,7 +112,22 @@ __global__ void cell_scatter_kernel(const float4 *__restrict__ pts, int n, const
   sorted[slot] = p;
 }
 
+// B200_TRACE=1: host-side wall time of each step of a grid build (debugging aid)
+struct HostTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  HostTrace() : on(getenv("B200_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void tick(const char *what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    double ms = std::chrono::duration<double, std::milli>(n - t).count();
+    if (ms > 1.0) fprintf(stderr, "[b200 trace] %s: %.3f ms host\n", what, ms);
+    t = n;
+  }
+};
+
 int build_grid(b200_cloud *c, float cell, DeviceGrid &g) {
+  HostTrace tr;
   b200_ctx *ctx = c->ctx;
   StageScope st_(ctx, ST_GRID);
   g.valid = false;
@@ -149,12 +166,16 @@ int build_grid(b200_cloud *c, float cell, DeviceGrid &g) {
   for (int a = 0; a < 3; ++a) sc = std::max(sc, std::max(fabsf(c->lo[a]), fabsf(c->hi[a])));
   v.coord_scale = sc;
   const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
+  tr.tick("grid setup");
   B200_TRY(g.cell_start.alloc(ctx, ncell + 1));
+  tr.tick("alloc cell_start");
   B200_TRY(g.pts.alloc(ctx, (size_t)std::max(c->n_valid, 1)));
   DevBuf<int> counts, cell_of;
   B200_TRY(counts.alloc(ctx, ncell + 1));
+  tr.tick("alloc counts");
   B200_TRY(counts.zero());
   B200_TRY(cell_of.alloc(ctx, (size_t)std::max(c->n, 1)));
+  tr.tick("memset + alloc cell_of");
   v.pts = g.pts.p;
   v.cell_start = g.cell_start.p;
   if (c->n > 0) {
@@ -167,6 +188,8 @@ int build_grid(b200_cloud *c, float cell, DeviceGrid &g) {
                                                                      counts.p, g.pts.p);
     B200_LAUNCHED(ctx);
   }
+  tr.tick("grid kernels enqueue");
+  if (tr.on) fprintf(stderr, "[b200 trace] grid %d x %d x %d cells, h=%g\n", dim[0], dim[1], dim[2], (double)cell);
   g.view = v;
   g.cell = requested;
   g.valid = true;
