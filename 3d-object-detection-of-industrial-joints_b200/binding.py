@@ -26,7 +26,7 @@ EXPORTS = [
     "b200_model_create_shot", "b200_model_destroy", "b200_model_size", "b200_model_download",
     "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
     "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
-    "b200_ctx_stage_time",
+    "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio",
 ]
 
 
@@ -96,6 +96,8 @@ def lib():
             "b200_ctx_reset_profiling": [vp],
             "b200_ctx_stage_count": [],
             "b200_ctx_stage_time": [vp, i, C.POINTER(d), ip],
+            "b200_last_match_fallback": [vp, ip],
+            "b200_last_match_error_ratio": [vp, fp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -230,6 +232,16 @@ class Context:
             self._chk(lib().b200_ctx_stage_time(self.h, s, C.byref(ms), C.byref(n)))
             out[lib().b200_ctx_stage_name(s).decode()] = (ms.value, n.value)
         return out
+
+    def match_fallback_rows(self):
+        n = C.c_int()
+        self._chk(lib().b200_last_match_fallback(self.h, C.byref(n)))
+        return n.value
+
+    def match_error_ratio(self):
+        r = C.c_float()
+        self._chk(lib().b200_last_match_error_ratio(self.h, C.byref(r)))
+        return r.value
 
     def neighbor_stats(self):
         m, mx = C.c_double(), C.c_int()

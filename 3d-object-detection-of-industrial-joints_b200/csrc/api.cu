@@ -255,6 +255,20 @@ int b200_ctx_stage_time(b200_ctx *ctx, int stage, double *total_ms, int *calls) 
   return B200_OK;
 }
 
+int b200_last_match_fallback(b200_ctx *ctx, int *rows) {
+  API_ENTER(ctx);
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (rows) *rows = ctx->last_match_fallback;
+  return B200_OK;
+}
+
+int b200_last_match_error_ratio(b200_ctx *ctx, float *ratio) {
+  API_ENTER(ctx);
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ratio) *ratio = ctx->last_match_err_ratio;
+  return B200_OK;
+}
+
 int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs) {
   if (!ctx) return B200_ERR_INVALID;
   if (mean_nbrs) *mean_nbrs = ctx->last_mean_nbrs;

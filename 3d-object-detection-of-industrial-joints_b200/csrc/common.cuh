@@ -87,6 +87,8 @@ struct b200_ctx {
   int64_t launches = 0;
   double last_mean_nbrs = 0.0;
   int last_max_nbrs = 0;
+  float last_match_err_ratio = 0.f;  // max observed approximation error / assumed bound (profiling only)
+  int last_match_fallback = -1;  // rows the tensor-core filter could not certify (valid after a sync)
   std::string err;
   void *pinned = nullptr;  // small pinned staging block for tiny readbacks
   int fail(int code, const char *msg) {

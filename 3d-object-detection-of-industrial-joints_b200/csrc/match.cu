@@ -13,6 +13,8 @@
 // This is the exact path; match_tc.cu adds a tcgen05 tensor-core pre-filter for large libraries and
 // falls back to this kernel's arithmetic for the final (exact) rescoring.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -51,12 +53,22 @@ __global__ void init_best_kernel(unsigned long long *best, int *zero_cnt, int n)
 
 __global__ void __launch_bounds__(MTHREADS)
     match_tile_kernel(const float *__restrict__ model, int Km, const unsigned char *__restrict__ model_valid,
-                      const float *__restrict__ scene, int Ks, int D, unsigned long long *__restrict__ best,
+                      const float *__restrict__ scene, int Ks, int D, const int *__restrict__ row_map,
+                      const int *__restrict__ n_rows_dev, unsigned long long *__restrict__ best,
                       int *__restrict__ zero_cnt) {
   __shared__ float As[MT][MKC + 1];
   __shared__ float Bs[MT][MKC + 1];
+  __shared__ int s_row[MT];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int s0 = blockIdx.x * MT;
+  // optional indirection: only the rows listed in row_map (the tensor-core filter's uncertified rows)
+  const int n_rows = row_map ? *n_rows_dev : Ks;
+  if (s0 >= n_rows) return;
+  if (threadIdx.x < MT) {
+    const int r = s0 + threadIdx.x;
+    s_row[threadIdx.x] = (r < n_rows) ? (row_map ? row_map[r] : r) : -1;
+  }
+  __syncthreads();
   unsigned long long rbest[4] = {~0ull, ~0ull, ~0ull, ~0ull};
   int rzero[4] = {0, 0, 0, 0};
   const int ntiles = (Km + MT - 1) / MT;
@@ -72,8 +84,8 @@ __global__ void __launch_bounds__(MTHREADS)
       for (int idx = threadIdx.x; idx < MT * MKC; idx += MTHREADS) {
         const int r = idx / MKC, c = idx % MKC;
         const int d = d0 + c;
-        const int sr = s0 + r, mr = m0 + r;
-        As[r][c] = (sr < Ks && d < D) ? scene[(size_t)sr * D + d] : 0.0f;
+        const int sr = s_row[r], mr = m0 + r;
+        As[r][c] = (sr >= 0 && d < D) ? scene[(size_t)sr * D + d] : 0.0f;
         Bs[r][c] = (mr < Km && d < D) ? model[(size_t)mr * D + d] : 0.0f;
       }
       __syncthreads();
@@ -116,8 +128,8 @@ __global__ void __launch_bounds__(MTHREADS)
       k = (ok < k) ? ok : k;
       z += __shfl_xor_sync(0xffffffffu, z, o);
     }
-    const int sr = s0 + ty + 16 * i;
-    if (tx == 0 && sr < Ks) {
+    const int sr = s_row[ty + 16 * i];
+    if (tx == 0 && sr >= 0) {
       if (k != ~0ull) atomicMin(&best[sr], k);
       if (z) atomicAdd(&zero_cnt[sr], z);
     }
@@ -157,6 +169,24 @@ __global__ void match_emit_kernel(const unsigned long long *__restrict__ best, c
 
 }  // namespace
 
+int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid, const float *d_scene,
+                    int Ks, const unsigned char *svalid, int D, int terms, unsigned long long *best, int *zero_cnt,
+                    int *fb_rows, int *fb_count);
+
+// 0: exact float32 kernel only; 1 / 3: tcgen05 pre-filter with 1 / 3 fp16 terms + exact rescoring.
+// B200_MATCH=exact|tc1|tc3 overrides the size heuristic (testing aid).
+static int match_mode_for(int Km, int Ks, int D) {
+  const char *e = getenv("B200_MATCH");
+  if (e) {
+    if (!strcmp(e, "exact")) return 0;
+    if (!strcmp(e, "tc1")) return 1;
+    if (!strcmp(e, "tc3")) return 3;
+  }
+  if (D > 2048 || D < 16) return 0;
+  // the filter pays off once the all-pairs work is large
+  return ((double)Km * (double)Ks * D >= 2.0e10 && Km >= 1024) ? 3 : 0;
+}
+
 int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
               b200_corr *d_out, int *d_count) {
   if (mode != 1 && mode != 2) return ctx->fail(B200_ERR_INVALID, "match: mode must be 1 or 2");
@@ -189,8 +219,27 @@ int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene,
     // enough CTAs for >= 4 waves when the scene is small
     int sy = std::max(1, std::min(mtiles, (ctx->sm_count * 8) / std::max(sx, 1)));
     dim3 grid(sx, sy);
-    match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, best.p, zero_cnt.p);
-    B200_LAUNCHED(ctx);
+    const int tc_terms = match_mode_for(Km, Ks, D);
+    ctx->last_match_fallback = -1;
+    if (tc_terms) {
+      DevBuf<int> fb_rows, fb_count;
+      B200_TRY(fb_rows.alloc(ctx, (size_t)Ks));
+      B200_TRY(fb_count.alloc(ctx, 1));
+      B200_TRY(match_tc_filter(ctx, d_model, Km, mvalid.p, d_scene, Ks, svalid.p, D, tc_terms, best.p, zero_cnt.p,
+                               fb_rows.p, fb_count.p));
+      if (ctx->profiling) {  // bench statistic: how many rows needed the exact kernel
+        B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_fallback, fb_count.p, sizeof(int), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+      }
+      // uncertified rows: exact evaluation (grid sized for the worst case, surplus CTAs exit at once)
+      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, fb_rows.p,
+                                                            fb_count.p, best.p, zero_cnt.p);
+      B200_LAUNCHED(ctx);
+    } else {
+      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, nullptr, nullptr,
+                                                            best.p, zero_cnt.p);
+      B200_LAUNCHED(ctx);
+    }
   }
   match_flags_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, svalid.p, nmv.p, Ks, mode, thr,
                                                                  flags.p);

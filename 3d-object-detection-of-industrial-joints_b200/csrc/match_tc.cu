@@ -1,0 +1,564 @@
+// match_tc.cu — tensor-core pre-filter for the descriptor correspondence search.
+//
+// Same contract as match.cu (KdTreeFLANN<SHOT352>::nearestKSearch + the user threshold loop,
+// SHOT.cpp:405-423, SHOT_demo.cpp:508-530): the answer is the exact float32 L2_Simple arg-min.  For a
+// large model library the all-pairs float32 evaluation is FP32-pipe bound, so the bulk of it moves to
+// the 5th-generation tensor cores:
+//
+//   d2(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j ; for a fixed scene row i only s_ij = |b_j|^2 - 2 a_i.b_j
+//   matters.  a.b is evaluated as a dense contraction on tcgen05 (fp16 operands, fp32 accumulation in
+//   TMEM).  Each fp32 value is split into fp16 terms x = x1 + x2 (x1 = rn16(x), x2 = rn16(x - x1)) and
+//   the contraction runs over the concatenated K' = [a1|a1|a2] . [b1|b2|b1] (3 terms, ~2^-22 relative
+//   operand error) or just a1.b1 (1 term, 2^-11), after an exact power-of-two rescale into fp16 range.
+//   The epilogue (4 warps, one TMEM lane = one scene row per thread) keeps the 8 smallest s_ij of the
+//   row in registers across all model tiles.
+//   A second kernel rescoring those candidates with the exact sequential float32 distance then
+//   CERTIFIES the arg-min: every non-candidate has approximate s >= the 8th smallest, so if the best
+//   exact distance is below |a_i|^2 + s_8 - eps (eps = proven error bound of the approximation) no
+//   other row can win or tie.  Rows that cannot be certified are re-evaluated exactly by
+//   match_tile_kernel.  The result is therefore bit-identical to the exact path.
+//
+// Kernel structure (one CTA per SM, persistent over (scene tile, model split) work items):
+//   warp 0   TMA producer: 4-stage ring of {A 128x64, B 256x64} fp16 tiles, SWIZZLE_128B
+//   warp 1   TMEM allocator (512 columns = two 128x256 fp32 accumulators) + single-thread MMA issuer:
+//            tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, smem descriptors, commit → mbarrier
+//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 → s = nb_j - 2*acc → top-8 insert; overlaps the next
+//            tile's MMAs through the second accumulator
+// Roofline: tensor pipe; 2*Ks*Km*K' flop per call.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_BK = 64;  // fp16 elements per k-block = 128 bytes = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_CAND = 8;
+constexpr int TC_MAX_SPLIT = 4;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;
+constexpr uint32_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni LAB_DONE;\n"
+      "bra.uni LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B: 8-row groups are 1024 bytes apart (SBO).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
+  d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+
+// 32 lanes x 32 columns of fp32 accumulators → 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------- operand preparation
+__global__ void absmax_kernel(const float *__restrict__ x, size_t n, unsigned *__restrict__ out_bits) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[i]);
+    if (isfinite(v)) m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
+}
+
+// scale[0] = 2^-e such that absmax * scale <= 1; scale[1] = absmax
+__global__ void make_scale_kernel(const unsigned *__restrict__ absmax_bits, float *__restrict__ scale) {
+  const float m = __uint_as_float(*absmax_bits);
+  int e = 0;
+  if (m > 0.f) frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+  scale[0] = ldexpf(1.0f, -e);
+  scale[1] = m;
+}
+
+// One warp per row.  is_b = 0: row = [x1 | x1 | x2], is_b = 1: row = [x1 | x2 | x1] (terms == 3);
+// terms == 1: row = [x1].  Rows are zero padded to Kp halves.  norm2[row] = float32 sum of squares of
+// the ORIGINAL values (+inf for rows that are not valid).
+__global__ void tc_prep_kernel(const float *__restrict__ X, int rows, int rows_padded, int D, int Kp, int terms,
+                               int is_b, const float *__restrict__ scale, const unsigned char *__restrict__ valid,
+                               __half *__restrict__ out, float *__restrict__ norm2, unsigned *__restrict__ normmax_bits) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows_padded) return;
+  __half *o = out + (size_t)w * Kp;
+  const bool ok = (w < rows) && (valid == nullptr || valid[w]);
+  if (!ok) {
+    for (int d = lane; d < Kp; d += 32) o[d] = __float2half_rn(0.f);
+    if (lane == 0) norm2[w] = __int_as_float(0x7f800000);
+    return;
+  }
+  const float sc = scale[0];
+  float n2 = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float x = X[(size_t)w * D + d];
+    n2 += x * x;
+    const float xs = x * sc;
+    const __half h1 = __float2half_rn(xs);
+    if (terms == 3) {
+      const __half h2 = __float2half_rn(xs - __half2float(h1));
+      o[d] = h1;
+      o[D + d] = is_b ? h2 : h1;
+      o[2 * D + d] = is_b ? h1 : h2;
+    } else {
+      o[d] = h1;
+    }
+  }
+  for (int d = terms * D + lane; d < Kp; d += 32) o[d] = __float2half_rn(0.f);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+  if (lane == 0) {
+    norm2[w] = n2;
+    if (normmax_bits && isfinite(n2)) atomicMax(normmax_bits, __float_as_uint(n2));
+  }
+}
+
+// ---------------------------------------------------------------- the tensor-core filter
+struct TcParams {
+  int Ks, Km;
+  int m_tiles, n_tiles, n_split;
+  int k_blocks;
+  const float *nb;     // |b_j|^2, padded to n_tiles * TC_BN (+inf padding)
+  const float *scaleA;
+  const float *scaleB;
+  float *cand_s;       // [Ks][n_split * TC_CAND]
+  int *cand_j;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_filter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char *sA = smem;
+  unsigned char *sB = smem + TC_STAGES * TC_A_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES));
+  uint64_t *full = bars;                 // [TC_STAGES]
+  uint64_t *empty = bars + TC_STAGES;    // [TC_STAGES]
+  uint64_t *tfull = bars + 2 * TC_STAGES;       // [2]
+  uint64_t *tempty = bars + 2 * TC_STAGES + 2;  // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = p.m_tiles * p.n_split;
+  const int tiles_per_split = (p.n_tiles + p.n_split - 1) / p.n_split;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int mt = item / p.n_split, sp = item % p.n_split;
+        const int nt0 = sp * tiles_per_split, nt1 = min(p.n_tiles, nt0 + tiles_per_split);
+        for (int nt = nt0; nt < nt1; ++nt)
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_expect_tx(&full[stage], TC_A_BYTES + TC_B_BYTES);
+            tma_load_2d(sA + stage * TC_A_BYTES, &mapA, &full[stage], kb * TC_BK, mt * TC_BM);
+            tma_load_2d(sB + stage * TC_B_BYTES, &mapB, &full[stage], kb * TC_BK, nt * TC_BN);
+            if (++stage == TC_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D = f32, A = B = f16, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int sp = item % p.n_split;
+        const int nt0 = sp * tiles_per_split, nt1 = min(p.n_tiles, nt0 + tiles_per_split);
+        for (int nt = nt0; nt < nt1; ++nt) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_sdesc(smem_u32(sA + stage * TC_A_BYTES));
+            const uint64_t bdesc = make_sdesc(smem_u32(sB + stage * TC_B_BYTES));
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(&empty[stage]);  // smem slot free when these MMAs retire
+            if (++stage == TC_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(&tfull[acc]);  // accumulator complete
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    const float inv = 1.0f / (p.scaleA[0] * p.scaleB[0]);
+    const float m2inv = -2.0f * inv;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int mt = item / p.n_split, sp = item % p.n_split;
+      const int nt0 = sp * tiles_per_split, nt1 = min(p.n_tiles, nt0 + tiles_per_split);
+      float cs[TC_CAND];
+      int cj[TC_CAND];
+#pragma unroll
+      for (int t = 0; t < TC_CAND; ++t) {
+        cs[t] = __int_as_float(0x7f800000);
+        cj[t] = -1;
+      }
+      for (int nt = nt0; nt < nt1; ++nt) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN);
+        const int n0 = nt * TC_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(t_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int j = n0 + c0 + e;
+            const float s = fmaf(m2inv, v[e], __ldg(&p.nb[j]));
+            if (s < cs[TC_CAND - 1]) {
+              cs[TC_CAND - 1] = s;
+              cj[TC_CAND - 1] = j;
+#pragma unroll
+              for (int t = TC_CAND - 1; t > 0; --t)
+                if (cs[t] < cs[t - 1]) {
+                  const float ts = cs[t];
+                  cs[t] = cs[t - 1];
+                  cs[t - 1] = ts;
+                  const int tj = cj[t];
+                  cj[t] = cj[t - 1];
+                  cj[t - 1] = tj;
+                }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      const int row = mt * TC_BM + row_in_tile;
+      if (row < p.Ks) {
+        float *os = p.cand_s + ((size_t)row * p.n_split + sp) * TC_CAND;
+        int *oj = p.cand_j + ((size_t)row * p.n_split + sp) * TC_CAND;
+#pragma unroll
+        for (int t = 0; t < TC_CAND; ++t) {
+          os[t] = cs[t];
+          oj[t] = cj[t];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- exact rescoring + certificate
+// One warp per scene row; lane l rescores candidate l with the exact sequential float32 distance.
+__global__ void tc_rescore_kernel(const float *__restrict__ model, int Km, const float *__restrict__ scene, int Ks, int D,
+                                  const unsigned char *__restrict__ svalid, int n_split,
+                                  const float *__restrict__ cand_s, const int *__restrict__ cand_j,
+                                  const float *__restrict__ na, const float *__restrict__ normmaxB,
+                                  const float *__restrict__ scaleA, const float *__restrict__ scaleB, float eta,
+                                  unsigned long long *__restrict__ best, int *__restrict__ zero_cnt,
+                                  int *__restrict__ fb_rows, int *__restrict__ fb_count,
+                                  unsigned *__restrict__ err_ratio_bits) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= Ks) return;
+  if (!svalid[i]) return;  // row is skipped by the caller's flags (pcl_isfinite(descriptor[0]))
+  const int nc = n_split * TC_CAND;
+  int j = -1;
+  float s = __int_as_float(0x7f800000);
+  if (lane < nc) {
+    j = cand_j[(size_t)i * nc + lane];
+    s = cand_s[(size_t)i * nc + lane];
+  }
+  // s_cut: every model row that is not a candidate has approximate s >= the worst kept value of its split
+  float s_cut = __int_as_float(0x7f800000);
+  if (lane < nc && (lane % TC_CAND) == TC_CAND - 1) s_cut = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s_cut = fminf(s_cut, __shfl_xor_sync(0xffffffffu, s_cut, o));
+  unsigned long long key = ~0ull;
+  int zeros = 0;
+  if (j >= 0 && j < Km) {
+    const float *a = scene + (size_t)i * D;
+    const float *b = model + (size_t)j * D;
+    float acc = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      const float diff = a[d] - b[d];
+      acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+    }
+    key = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j;
+    zeros = (acc == 0.0f) ? 1 : 0;
+    if (err_ratio_bits) {
+      // observed |approximate - exact| distance of this candidate, relative to the bound the certificate
+      // assumes (statistic for the tests: must stay well below 1)
+      const float nai = na[i], nbm = normmaxB[0];
+      const float eps = 2.0f * eta * sqrtf(nai * nbm) + 4e-5f * (nai + nbm + acc) +
+                        4e-6f * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+      const float ratio = fabsf((nai + s) - acc) / eps;
+      if (ratio == ratio) atomicMax(err_ratio_bits, __float_as_uint(ratio));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+    key = (ok < key) ? ok : key;
+    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+  }
+  if (lane == 0) {
+    bool certified = false;
+    if (key != ~0ull) {
+      const float best_d2 = __uint_as_float((unsigned)(key >> 32));
+      if (!(s_cut < __int_as_float(0x7f800000))) {
+        certified = true;  // every valid model row was a candidate
+      } else {
+        const float nai = na[i];
+        const float nbm = normmaxB[0];
+        // |s_approx - s_real| <= 2*eta*|a||b| ; float32 sequential sums and norms: 4e-5 relative
+        // fp16 subnormal flush of the split terms: absolute 2^-24 per element in scaled units
+        const float eps = 2.0f * eta * sqrtf(nai * nbm) + 4e-5f * (nai + nbm + best_d2) +
+                          4e-6f * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+        certified = best_d2 < (nai + s_cut) - eps;
+      }
+    }
+    if (certified) {
+      best[i] = key;
+      zero_cnt[i] = zeros;
+    } else {
+      fb_rows[atomicAdd(fb_count, 1)] = i;
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_map(b200_ctx *ctx, CUtensorMap *map, const __half *base, int rows, int Kp, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return ctx->fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ctx->fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return B200_OK;
+}
+
+}  // namespace
+
+// terms: 1 or 3.  On return best[] / zero_cnt[] hold the certified rows; fb_rows[0..*fb_count) lists the
+// rows that need the exact kernel.
+int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid, const float *d_scene,
+                    int Ks, const unsigned char *svalid, int D, int terms, unsigned long long *best, int *zero_cnt,
+                    int *fb_rows, int *fb_count) {
+  const int Kp = ((terms * D + TC_BK - 1) / TC_BK) * TC_BK;
+  const int m_tiles = ceil_div(Ks, TC_BM), n_tiles = ceil_div(Km, TC_BN);
+  const int rowsA = m_tiles * TC_BM, rowsB = n_tiles * TC_BN;
+  int n_split = 1;
+  while (n_split < TC_MAX_SPLIT && m_tiles * n_split < ctx->sm_count && n_split * 2 <= n_tiles) n_split *= 2;
+  DevBuf<__half> A16, B16;
+  DevBuf<float> na, nb, scA, scB, cand_s, nbmax;
+  DevBuf<unsigned> bits;
+  DevBuf<int> cand_j;
+  B200_TRY(A16.alloc(ctx, (size_t)rowsA * Kp));
+  B200_TRY(B16.alloc(ctx, (size_t)rowsB * Kp));
+  B200_TRY(na.alloc(ctx, (size_t)rowsA));
+  B200_TRY(nb.alloc(ctx, (size_t)rowsB));
+  B200_TRY(scA.alloc(ctx, 2));
+  B200_TRY(scB.alloc(ctx, 2));
+  B200_TRY(nbmax.alloc(ctx, 1));
+  B200_TRY(bits.alloc(ctx, 4));
+  B200_TRY(bits.zero());
+  B200_TRY(cand_s.alloc(ctx, (size_t)Ks * n_split * TC_CAND));
+  B200_TRY(cand_j.alloc(ctx, (size_t)Ks * n_split * TC_CAND));
+  B200_CUDA(ctx, cudaMemsetAsync(fb_count, 0, sizeof(int), ctx->stream));
+
+  const int rb = std::min(ctx->sm_count * 8, 4096);
+  absmax_kernel<<<rb, 256, 0, ctx->stream>>>(d_scene, (size_t)Ks * D, bits.p + 0);
+  B200_LAUNCHED(ctx);
+  absmax_kernel<<<rb, 256, 0, ctx->stream>>>(d_model, (size_t)Km * D, bits.p + 1);
+  B200_LAUNCHED(ctx);
+  make_scale_kernel<<<1, 1, 0, ctx->stream>>>(bits.p + 0, scA.p);
+  B200_LAUNCHED(ctx);
+  make_scale_kernel<<<1, 1, 0, ctx->stream>>>(bits.p + 1, scB.p);
+  B200_LAUNCHED(ctx);
+  tc_prep_kernel<<<ceil_div((long long)rowsA * 32, 256), 256, 0, ctx->stream>>>(d_scene, Ks, rowsA, D, Kp, terms, 0,
+                                                                                scA.p, nullptr, A16.p, na.p, nullptr);
+  B200_LAUNCHED(ctx);
+  tc_prep_kernel<<<ceil_div((long long)rowsB * 32, 256), 256, 0, ctx->stream>>>(d_model, Km, rowsB, D, Kp, terms, 1,
+                                                                                scB.p, mvalid, B16.p, nb.p, bits.p + 2);
+  B200_LAUNCHED(ctx);
+
+  CUtensorMap mapA, mapB;
+  B200_TRY(make_map(ctx, &mapA, A16.p, rowsA, Kp, TC_BM));
+  B200_TRY(make_map(ctx, &mapB, B16.p, rowsB, Kp, TC_BN));
+  TcParams p;
+  p.Ks = Ks;
+  p.Km = Km;
+  p.m_tiles = m_tiles;
+  p.n_tiles = n_tiles;
+  p.n_split = n_split;
+  p.k_blocks = Kp / TC_BK;
+  p.nb = nb.p;
+  p.scaleA = scA.p;
+  p.scaleB = scB.p;
+  p.cand_s = cand_s.p;
+  p.cand_j = cand_j.p;
+  B200_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  const int grid = std::min(ctx->sm_count, m_tiles * n_split);
+  tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(mapA, mapB, p);
+  B200_LAUNCHED(ctx);
+  // error bound of the approximate inner product relative to |a||b|: fp16 operand rounding (2^-11 per
+  // operand for one term, ~2^-21 for the three-term split) plus fp32 tensor-core accumulation
+  const float eta = (terms == 3) ? 1.0e-4f : 1.2e-3f;
+  tc_rescore_kernel<<<ceil_div((long long)Ks * 32, 256), 256, 0, ctx->stream>>>(
+      d_model, Km, d_scene, Ks, D, svalid, n_split, cand_s.p, cand_j.p, na.p,
+      reinterpret_cast<const float *>(bits.p + 2), scA.p, scB.p, eta, best, zero_cnt, fb_rows, fb_count,
+      ctx->profiling ? bits.p + 3 : nullptr);
+  B200_LAUNCHED(ctx);
+  if (ctx->profiling)
+    B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_err_ratio, bits.p + 3, sizeof(float), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+  return B200_OK;
+}

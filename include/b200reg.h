@@ -190,6 +190,14 @@ B200_API int b200_dev_register_scene_shot(b200_ctx *ctx, const b200_model *model
  * radius neighbours per keypoint. */
 B200_API int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs);
 
+/* Rows of the last b200_match / pipeline call that the tensor-core pre-filter could not certify and
+ * that were re-evaluated by the exact float32 kernel (-1: the filter was not used).  Recorded only while
+ * profiling is enabled; synchronises the stream. */
+B200_API int b200_last_match_fallback(b200_ctx *ctx, int *rows);
+/* Largest observed |approximate - exact| candidate distance of the last filtered match, divided by the
+ * error bound the certificate assumes (must stay well below 1).  Profiling only; synchronises. */
+B200_API int b200_last_match_error_ratio(b200_ctx *ctx, float *ratio);
+
 #ifdef __cplusplus
 }
 #endif
