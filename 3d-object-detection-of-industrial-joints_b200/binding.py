@@ -27,6 +27,7 @@ EXPORTS = [
     "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
     "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
     "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio",
+    "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
 ]
 
 
@@ -98,6 +99,10 @@ def lib():
             "b200_ctx_stage_time": [vp, i, C.POINTER(d), ip],
             "b200_last_match_fallback": [vp, ip],
             "b200_last_match_error_ratio": [vp, fp],
+            "b200_desc_index_create": [vp, fp, i, i, C.POINTER(vp)],
+            "b200_desc_index_destroy": [vp],
+            "b200_desc_index_size": [vp],
+            "b200_desc_index_knn": [vp, vp, fp, i, i, ip, fp, ip],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -179,6 +184,36 @@ class Model:
     def close(self):
         if self.h and self.ctx.h:
             lib().b200_model_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DescIndex:
+    def __init__(self, ctx, handle, D):
+        self.ctx, self.h, self.D = ctx, handle, D
+        ctx._children.add(self)
+
+    @property
+    def size(self):
+        return lib().b200_desc_index_size(self.h)
+
+    def knn(self, queries, k):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.D)
+        idx = np.zeros((len(q), k), dtype=np.int32)
+        d2 = np.zeros((len(q), k), dtype=np.float32)
+        kf = C.c_int()
+        self.ctx._chk(lib().b200_desc_index_knn(self.ctx.h, self.h, _f(q), len(q), int(k), _i(idx), _f(d2),
+                                                C.byref(kf)))
+        return idx, d2, kf.value
+
+    def close(self):
+        if self.h and self.ctx.h:
+            lib().b200_desc_index_destroy(self.h)
         self.h = None
 
     def __del__(self):
@@ -327,6 +362,13 @@ class Context:
             self._chk(lib().b200_fpfh33(self.h, cloud.h, _f(normals), _f(q), len(q), q.shape[1], float(radius),
                                         _f(out)))
         return out
+
+    # ---- per-query descriptor index (KdTreeFLANN<Descriptor> drop-in) -------------------------------
+    def desc_index(self, desc):
+        desc = np.ascontiguousarray(desc, dtype=np.float32)
+        h = C.c_void_p()
+        self._chk(lib().b200_desc_index_create(self.h, _f(desc), desc.shape[0], desc.shape[1], C.byref(h)))
+        return DescIndex(self, h, desc.shape[1])
 
     # ---- matching / grouping ------------------------------------------------------------------
     def match(self, model, scene, mode=1, thr=0.25):

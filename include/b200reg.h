@@ -139,6 +139,18 @@ B200_API int b200_match(b200_ctx *ctx, const float *model, int Km, const float *
 B200_API int b200_dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode,
                    float thr, b200_corr *d_out, int *d_count);
 
+/* Resident descriptor index for the reference's per-query loop: KdTreeFLANN<Descriptor>::setInputCloud
+ * (SHOT.cpp:405-406, SHOT_demo.cpp:508-509, FPFH_demo.cpp:516-517) followed by nearestKSearch per scene
+ * descriptor (SHOT.cpp:417 k=1, SHOT_demo.cpp:521 k=2).  Rows with a non-finite value are dropped from
+ * the index (their positions are kept).  idx/d2: nq x k in (distance, index) order; 1 <= k <= 16;
+ * *k_found = min(k, indexed rows); unused slots are -1 / +inf. */
+typedef struct b200_desc_index b200_desc_index;
+B200_API int b200_desc_index_create(b200_ctx *ctx, const float *desc, int K, int D, b200_desc_index **out);
+B200_API int b200_desc_index_destroy(b200_desc_index *index);
+B200_API int b200_desc_index_size(const b200_desc_index *index);
+B200_API int b200_desc_index_knn(b200_ctx *ctx, const b200_desc_index *index, const float *queries, int nq, int k,
+                                 int *idx, float *d2, int *k_found);
+
 /* ---------------------------------------------------------------- grouping --------------- */
 /* pcl::GeometricConsistencyGrouping::recognize (SHOT.cpp:473-482, 6Dpose.cpp:529-538,
  * SHOT_scenes.cpp:413-425).  transforms: max_inst x 16 (row-major 4x4, model -> scene);

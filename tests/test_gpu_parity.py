@@ -349,3 +349,37 @@ def test_register_scene_pipeline(ctx, orc, synth, b200):
     assert max(np.abs(A - B).max() for A, B in zip(res["transforms"], oT)) < 1e-4
     assert ctx.launches > 0
     m.close()
+
+
+# ------------------------------------------------------------------------------------------ descriptor index
+def test_desc_index_knn_bit_exact(ctx, orc):
+    """KdTreeFLANN<SHOT352>::setInputCloud + nearestKSearch per query (SHOT.cpp:405-417, SHOT_demo.cpp:508-521):
+    distances are FLANN's sequential float32 L2_Simple sums, order (distance, index)."""
+    rng = _rng(41)
+    for D, Km, nq in ((352, 300, 40), (33, 500, 64)):
+        a = rng.uniform(0, 1, (Km, D)).astype(np.float32)
+        q = (a[rng.integers(0, Km, nq)] + rng.normal(0, 0.05, (nq, D))).astype(np.float32)
+        a[7, 3] = np.nan                     # dropped from the index, position kept
+        a[11] = a[10]                        # duplicate rows: tie broken by index
+        q[0] = a[10]
+        ix = ctx.desc_index(a)
+        assert ix.size == Km - 1
+        valid = np.isfinite(a).all(1)
+        diff = (q[:, None, :] - a[None, :, :]).astype(np.float32)
+        d2_all = np.cumsum(diff * diff, axis=2, dtype=np.float32)[:, :, -1]     # sequential float32 sum
+        d2_all[:, ~valid] = np.inf
+        for k in (1, 2, 5, 16):
+            idx, d2, kf = ix.knn(q, k)
+            assert kf == k
+            order = np.lexsort((np.broadcast_to(np.arange(Km), d2_all.shape), d2_all), axis=1)[:, :k]
+            assert np.array_equal(idx, order.astype(np.int32))
+            assert np.array_equal(d2, np.take_along_axis(d2_all, order, 1))
+        # k = 1 / 2 agree with the correspondence oracle (same arg-min, same distance)
+        ref = orc.match(a, q, 1, 1e30)
+        idx, d2, _ = ix.knn(q, 1)
+        assert np.array_equal(ref["index_query"], idx[:, 0]) and np.array_equal(ref["distance"], d2[:, 0])
+        ix.close()
+    small = ctx.desc_index(rng.uniform(0, 1, (3, 33)).astype(np.float32))
+    idx, d2, kf = small.knn(rng.uniform(0, 1, (2, 33)).astype(np.float32), 5)
+    assert kf == 3 and np.all(idx[:, 3:] == -1) and np.all(np.isinf(d2[:, 3:]))
+    small.close()
