@@ -194,6 +194,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
   }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   ctx->arena_destroy();
+  if (ctx->mt_state) cudaFree(ctx->mt_state);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200_OK;
@@ -242,7 +243,7 @@ int b200_ctx_stage_count(void) { return ST_COUNT; }
 
 const char *b200_ctx_stage_name(int stage) {
   static const char *names[ST_COUNT] = {"grid_build", "normals", "neighbor_count", "shot", "fpfh",
-                                        "match",      "gc_sort", "gc_group",       "gc_ransac"};
+                                        "match",      "gc_sort", "gc_adjacency",   "gc_group", "gc_ransac"};
   return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
 }
 

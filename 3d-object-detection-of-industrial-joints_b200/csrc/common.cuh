@@ -21,6 +21,7 @@ enum b200_stage {
   ST_FPFH,
   ST_MATCH,
   ST_GC_SORT,
+  ST_GC_ADJ,
   ST_GC_GROUP,
   ST_GC_RANSAC,
   ST_COUNT
@@ -91,6 +92,7 @@ struct b200_ctx {
   int last_match_fallback = -1;  // rows the tensor-core filter could not certify (valid after a sync)
   std::string err;
   void *pinned = nullptr;  // small pinned staging block for tiny readbacks
+  unsigned *mt_state = nullptr;  // mt19937 state after seeding with 12345 and the first twist (gc.cu)
   int fail(int code, const char *msg) {
     err = msg;
     return code;

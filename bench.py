@@ -305,6 +305,7 @@ def run_b200(args, rank, world, local_rank):
             "neighbor_count": ("hbm", 16.0 * N + 4.0 * Ks, "GB/s"),
             "grid_build": ("hbm", 40.0 * N, "GB/s"),
             "match": ("tensor", 2.0 * Ks * Km * 352, "TFLOP/s"),
+            "gc_adjacency": ("hbm", 32.0 * n_corrs + n_corrs * (n_corrs / 8.0), "GB/s"),
             "gc_group": ("hbm", 12.0 * n_corrs + 16.0 * (Ks + Km), "GB/s"),
             "gc_sort": ("hbm", 12.0 * n_corrs * 2, "GB/s"),
             "gc_ransac": ("hbm", 12.0 * n_corrs, "GB/s"),

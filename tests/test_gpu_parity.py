@@ -27,8 +27,9 @@ def small(synth):
 
 
 def _rot_angle_deg(Ra, Rb):
-    c = (np.trace(Ra.T @ Rb) - 1) / 2
-    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+    # chord form ||Ra - Rb||_F = 2 sqrt(2) sin(angle / 2): unlike arccos((trace - 1) / 2) it is well
+    # conditioned near zero (float32 matrices are orthonormal only to ~1e-7)
+    return np.degrees(2 * np.arcsin(min(1.0, np.linalg.norm(Ra - Rb) / (2 * np.sqrt(2)))))
 
 
 # ------------------------------------------------------------------------------------------ search
@@ -314,6 +315,44 @@ def test_gc_many_small_instances(ctx, orc, synth, small, b200):
         assert a.tobytes() == b.tobytes()
     dT = max(np.abs(A - B).max() for A, B in zip(T, oT))
     assert dT < 1e-4
+
+
+def test_gc_large_instances(ctx, orc, b200):
+    """Sets far larger than the grouping kernel's shared-memory member cache (64) and candidate lists longer than
+    its per-seed list (1024): two rigid instances with 1500 / 700 inliers plus outliers."""
+    from scipy.spatial.transform import Rotation
+    rng = _rng(77)
+    model = rng.uniform(-0.3, 0.3, (2500, 3)).astype(np.float32)
+    parts, corr_parts = [], []
+    base = 0
+    for seed, n_in in ((1, 1500), (2, 700)):
+        R = Rotation.random(random_state=seed).as_matrix()
+        t = rng.uniform(-1, 1, 3) + 3 * seed
+        sel = rng.permutation(2500)[:n_in]
+        pts = (model[sel].astype(np.float64) @ R.T + t + rng.normal(0, 0.0005, (n_in, 3))).astype(np.float32)
+        parts.append(pts)
+        c = np.zeros(n_in, dtype=b200.CORR_DTYPE)
+        c["index_query"], c["index_match"] = sel, base + np.arange(n_in)
+        corr_parts.append(c)
+        base += n_in
+    clutter = rng.uniform(-2, 8, (600, 3)).astype(np.float32)
+    parts.append(clutter)
+    c = np.zeros(600, dtype=b200.CORR_DTYPE)
+    c["index_query"], c["index_match"] = rng.integers(0, 2500, 600), base + np.arange(600)
+    corr_parts.append(c)
+    scene = np.concatenate(parts)
+    corrs = np.concatenate(corr_parts)
+    corrs["distance"] = rng.uniform(0, 0.25, len(corrs)).astype(np.float32)
+    corrs = corrs[rng.permutation(len(corrs))]
+    T, inst, n = ctx.gc_recognize(model, scene, corrs, 0.01, 3, max_inst=256)
+    oT, oinst = orc.gc_recognize(model, scene, corrs, 0.01, 3, max_inst=256)
+    assert n == len(oT) and n >= 2
+    assert max(len(i) for i in inst) > 1024
+    for a, b in zip(inst, oinst):
+        assert a.tobytes() == b.tobytes()
+    for A, B in zip(T, oT):
+        assert np.abs(A[:3, 3] - B[:3, 3]).max() < 1e-4
+        assert _rot_angle_deg(A[:3, :3].astype(np.float64), B[:3, :3].astype(np.float64)) < 0.01
 
 
 # ------------------------------------------------------------------------------------------ pipeline
