@@ -15,7 +15,7 @@ OUT = os.path.join(HERE, "libb200reg.so")
 OBJ = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
-    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false"] + (["-DB200_GC_TIMING"] if os.environ.get("B200_GC_TIMING") else []) + [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-ccbin", "/usr/bin/g++",
 ]
 

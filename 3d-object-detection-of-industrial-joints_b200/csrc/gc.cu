@@ -22,6 +22,8 @@
 // RANSAC runs afterwards, one warp per instance: lane 0 draws the sample sequence (the RNG stream is
 // inherently serial), the lanes fit and score one sample each, lane 0 then replays the adaptive
 // termination logic in order and discards the samples past the stopping point.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "linalg3.cuh"
@@ -99,7 +101,7 @@ __device__ __forceinline__ bool gc_fits(const float4 &mk, const float4 &sk, cons
   return !((double)fabsf(sqrtf(a) - sqrtf(c)) > gc_size);
 }
 
-__device__ __forceinline__ int gc_row_words(int C) { return (((C + 31) >> 5) + 7) & ~7; }
+__device__ __forceinline__ int gc_row_words(int C) { return (((C + 31) >> 5) + 127) & ~127; }
 
 __global__ void __launch_bounds__(ADJ_THREADS)
     gc_adjacency_kernel(const float4 *__restrict__ mp, const float4 *__restrict__ sp, const int *__restrict__ d_C,
@@ -147,12 +149,11 @@ __global__ void __launch_bounds__(ADJ_THREADS)
   }
 }
 
-// ---- greedy grouping: one CTA, GW seeds evaluated speculatively per round ------------------------
+// ---- greedy grouping: one CTA, up to GW seeds evaluated speculatively per round -------------------
 constexpr int GW = 16;                 // seeds (one per warp) per round
 constexpr int GG_THREADS = GW * 32;
-constexpr int G_MC = 64;               // members kept in shared memory per seed (index + points)
-constexpr int G_CL = 1024;             // candidate list capacity per seed
-constexpr int G_CPL = 4;               // candidates per lane per chunk
+constexpr int G_MC = 64;               // member indices kept in shared memory per seed
+constexpr int G_HS = 4096;             // commit hash table slots (>= 4 x GW x G_MC)
 
 struct GroupArgs {
   const unsigned *adj;
@@ -162,6 +163,7 @@ struct GroupArgs {
   int *members;       // [C_cap] committed member lists, concatenated
   int *inst_offsets;  // [max_inst + 1]
   int *n_inst_out;
+  long long *dbg;     // nullable (B200_GC_TIMING builds): per warp [rounds, window, eval, commit] cycles
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -173,328 +175,376 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
+__device__ __forceinline__ unsigned gc_hash(int m) { return ((unsigned)m * 2654435761u) >> 20; }  // 12 bits
+
+// lowest set position of a 128-bit group that starts at position base, or INT_MAX
+__device__ __forceinline__ int first_bit128(const uint4 &w, int base) {
+  if (w.x) return base + __ffs(w.x) - 1;
+  if (w.y) return base + 32 + __ffs(w.y) - 1;
+  if (w.z) return base + 64 + __ffs(w.z) - 1;
+  if (w.w) return base + 96 + __ffs(w.w) - 1;
+  return 0x7fffffff;
+}
+
+// The whole greedy growth of a seed runs on bitmaps: candidates = row(seed) & ~taken; the lowest
+// candidate j is admitted (it fits every member so far by construction) and candidates &= row(j);
+// repeat until no candidate is left.  A warp owns one seed; lane l handles the 16-byte groups
+// l, l + 32, ... of the row (coalesced), the candidate bitmap lives in shared memory, the next
+// admission is a warp-wide integer min.  Rows are padded to a multiple of 128 words (32 groups).
 __global__ void __launch_bounds__(GG_THREADS, 1)
-    gc_group_kernel(GroupArgs ga, const int *__restrict__ d_C, int C_cap, double gc_size, float g_lo, float g_hi,
-                    int gc_threshold, int max_inst) {
+    gc_group_kernel(GroupArgs ga, const int *__restrict__ d_C, int C_cap, int dyn_smem_bytes, double gc_size, float g_lo,
+                    float g_hi, int gc_threshold, int max_inst) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ int s_seed[GW], s_size[GW], s_commit_off[GW], s_commit_inst[GW];
-  __shared__ int s_nwin, s_cur, s_ninst, s_total;
+  __shared__ int s_seed[GW], s_size[GW], s_conf[GW];
+  __shared__ int s_nwin, s_big;
+  __shared__ int s_hkey[G_HS], s_hval[G_HS];
+  __shared__ int s_mem[GW][G_MC];
+  __shared__ int s_list[GW][64];
   __shared__ float4 s_newm[GW], s_news[GW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = min(*d_C, C_cap);
   const int row_words = gc_row_words(C);
-  // dynamic shared memory: member points | taken bitmap | candidate lists | member indices
-  float4 *s_mp = reinterpret_cast<float4 *>(s_raw);                  // [GW][G_MC]
-  float4 *s_sp = s_mp + GW * G_MC;                                   // [GW][G_MC]
-  unsigned *s_taken = reinterpret_cast<unsigned *>(s_sp + GW * G_MC);  // [row_words]
-  int *s_cand = reinterpret_cast<int *>(s_taken + row_words);        // [GW][G_CL]
-  int *s_mem = s_cand + GW * G_CL;                                   // [GW][G_MC]
+  const int nq = row_words >> 7;  // 16-byte groups per lane
+  // seeds per round: as many candidate bitmaps as fit beside the taken bitmap (the launch sized the
+  // dynamic shared memory for the capacity; the actual count is usually much smaller)
+  const int gw = min(GW, dyn_smem_bytes / (row_words * 4) - 1);
+  // dynamic shared memory: taken bitmap | one candidate bitmap per evaluating warp
+  uint4 *s_taken4 = reinterpret_cast<uint4 *>(s_raw);                            // [row_words / 4]
+  unsigned *s_taken = reinterpret_cast<unsigned *>(s_raw);
+  uint4 *my_cb4 = s_taken4 + (size_t)(row_words >> 2) * (1 + warp);              // [row_words / 4], warp < gw
 
   for (int w = tid; w < row_words; w += GG_THREADS) {
     const int j0 = w * 32;
     s_taken[w] = (j0 + 32 <= C) ? 0u : ((j0 >= C) ? ~0u : ~((1u << (C - j0)) - 1u));  // padding counts as taken
   }
-  if (tid == 0) {
-    s_cur = 0;
-    s_ninst = 0;
-    s_total = 0;
-    ga.inst_offsets[0] = 0;
+  for (int h = tid; h < G_HS; h += GG_THREADS) {
+    s_hkey[h] = -1;
+    s_hval[h] = 0x7fffffff;
   }
+  if (tid == 0) ga.inst_offsets[0] = 0;
+  // replicated in every thread (all threads derive the same values from shared memory each round)
+  int cur = 0, n_inst = 0, total = 0;
   __syncthreads();
 
-  float4 *my_mp = s_mp + warp * G_MC, *my_sp = s_sp + warp * G_MC;
-  int *my_cand = s_cand + warp * G_CL, *my_mem = s_mem + warp * G_MC;
+  int *my_mem = s_mem[warp];
   int *my_over = ga.overflow + (size_t)warp * C_cap;
 
+#ifdef B200_GC_TIMING
+  long long t_win = 0, t_eval = 0, t_commit = 0, n_rounds = 0, t_wait = 0;
+#define GC_CLOCK(v) const long long v = clock64()
+#define GC_ACC(acc, expr) acc += (expr)
+#else
+#define GC_CLOCK(v)
+#define GC_ACC(acc, expr)
+#endif
   while (true) {
-    // ---- window: the next GW untaken positions at or after s_cur (warp 0) ----
+    GC_CLOCK(c0);
+    // ---- window: the next gw untaken positions at or after cur (warp 0) ----
     if (warp == 0) {
-      const int cur = s_cur;
       int n = 0;
-      for (int wb = cur >> 5; wb < row_words && n < GW; wb += 32) {
+      for (int wb = cur >> 5; wb < row_words && n < gw; wb += 32) {
         const int wi = wb + lane;
         unsigned bits = (wi < row_words) ? ~s_taken[wi] : 0u;
         if (wi == (cur >> 5)) bits &= ~((1u << (cur & 31)) - 1u);
         const int cnt = __popc(bits);
         const int incl = warp_incl_scan(cnt, lane);
         int o = n + incl - cnt;
-        while (bits && o < GW) {
+        while (bits && o < gw) {
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
           s_seed[o++] = wi * 32 + b;
         }
         n += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (lane == 0) s_nwin = min(n, GW);
+      if (lane == 0) {
+        s_nwin = min(n, gw);
+        s_big = 0;
+      }
     }
     __syncthreads();
     const int nwin = s_nwin;
     if (nwin == 0) break;
+    GC_CLOCK(c1);
+    GC_ACC(t_win, c1 - c0);
+    GC_ACC(n_rounds, 1);
 
     // ---- evaluate: warp w grows the consensus set of seed w against the current flags ----
     if (warp < nwin) {
       const int seed = s_seed[warp];
       int size = 1;
+      if (lane == 0) my_mem[0] = seed;
+      int first = 0x7fffffff, my_cnt = 0;
+      {
+        const uint4 *row4 = reinterpret_cast<const uint4 *>(ga.adj + (size_t)seed * row_words);
+        for (int q0 = 0; q0 < nq; q0 += 8) {  // all loads of a block are issued before the first use
+          uint4 x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (q0 + i < nq) x[i] = __ldg(row4 + (q0 + i) * 32 + lane);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (q0 + i < nq) {
+              const int g = (q0 + i) * 32 + lane;
+              const uint4 t = s_taken4[g];
+              const uint4 w = make_uint4(x[i].x & ~t.x, x[i].y & ~t.y, x[i].z & ~t.z, x[i].w & ~t.w);
+              my_cb4[g] = w;
+              my_cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+              if (first == 0x7fffffff) first = first_bit128(w, g * 128);
+            }
+        }
+      }
+      first = __reduce_min_sync(0xffffffffu, first);
+      int n_cand = __reduce_add_sync(0xffffffffu, my_cnt);
+      // bitmap admissions while many candidates remain (each costs one row read)
+      while (n_cand > 64) {
+        const int j = first;
+        if (lane == 0) {
+          if (size < G_MC)
+            my_mem[size] = j;
+          else
+            my_over[size] = j;
+        }
+        ++size;
+        const uint4 *rowj4 = reinterpret_cast<const uint4 *>(ga.adj + (size_t)j * row_words);
+        first = 0x7fffffff;
+        my_cnt = 0;
+        for (int q0 = j >> 12; q0 < nq; q0 += 8) {  // groups before j's hold no candidates any more
+          uint4 y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (q0 + i < nq) y[i] = __ldg(rowj4 + (q0 + i) * 32 + lane);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (q0 + i < nq) {
+              const int g = (q0 + i) * 32 + lane;
+              uint4 w = my_cb4[g];
+              w.x &= y[i].x, w.y &= y[i].y, w.z &= y[i].z, w.w &= y[i].w;
+              my_cb4[g] = w;
+              my_cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+              if (first == 0x7fffffff) first = first_bit128(w, g * 128);
+            }
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        n_cand = __reduce_add_sync(0xffffffffu, my_cnt);
+      }
+      if (n_cand > 0) {
+        // at most 64 candidates left: list them in ascending position (each lane expands a contiguous
+        // slice of the shared-memory bitmap), fetch their points once and finish the greedy growth in
+        // registers — no further memory round trips
+        __syncwarp();
+        const unsigned *cb = reinterpret_cast<const unsigned *>(my_cb4);
+        const int wpl = row_words >> 5, w_lo = lane * wpl;
+        const int w_min = first >> 5;  // nothing before the first candidate
+        int cnt = 0;
+        for (int w = max(w_lo, w_min); w < w_lo + wpl; ++w) cnt += __popc(cb[w]);
+        const int incl = warp_incl_scan(cnt, lane);
+        if (cnt) {
+          int o = incl - cnt;
+          for (int w = max(w_lo, w_min); w < w_lo + wpl; ++w) {
+            unsigned bits = cb[w];
+            while (bits) {
+              s_list[warp][o++] = w * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+            }
+          }
+        }
+        __syncwarp();
+        int j[2];
+        float4 mj[2], sj[2];
+        unsigned alive = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int idx = u * 32 + lane;
+          if (idx < n_cand) {
+            j[u] = s_list[warp][idx];
+            mj[u] = ga.mp[j[u]];
+            sj[u] = ga.sp[j[u]];
+            alive |= 1u << u;
+          }
+        }
+        while (true) {
+          unsigned bal = __ballot_sync(0xffffffffu, alive & 1u);
+          int usel = 0;
+          if (!bal) {
+            bal = __ballot_sync(0xffffffffu, alive & 2u);
+            usel = 1;
+            if (!bal) break;
+          }
+          const int owner = __ffs(bal) - 1;
+          if (lane == owner) {
+            const int jj = usel ? j[1] : j[0];
+            s_newm[warp] = usel ? mj[1] : mj[0];
+            s_news[warp] = usel ? sj[1] : sj[0];
+            if (size < G_MC)
+              my_mem[size] = jj;
+            else
+              my_over[size] = jj;
+            alive &= ~(1u << usel);
+          }
+          __syncwarp();
+          const float4 mk = s_newm[warp], sk = s_news[warp];
+          ++size;
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (((alive >> u) & 1u) && !gc_fits(mk, sk, mj[u], sj[u], g_lo, g_hi, gc_size)) alive &= ~(1u << u);
+          __syncwarp();
+        }
+      }
       if (lane == 0) {
-        my_mem[0] = seed;
-        my_mp[0] = ga.mp[seed];
-        my_sp[0] = ga.sp[seed];
+        s_size[warp] = size;
+        if (size > G_MC) s_big = 1;
       }
       __syncwarp();
-      const uint4 *row4 = reinterpret_cast<const uint4 *>(ga.adj + (size_t)seed * row_words);
-      // pass A: how many candidates (row & ~taken) and which is the first.  The first candidate is
-      // always admitted (it only has to fit the seed); when many candidates remain, its bitmap row
-      // is intersected as well, so the list below holds only candidates that fit both.
-      int n_cand = 0, first = 0x7fffffff;
-      for (int wb = lane * 8; wb < row_words; wb += 256) {
-        const uint4 x = __ldg(row4 + wb / 4), y = __ldg(row4 + wb / 4 + 1);
-        const unsigned w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-          const unsigned v = w[k] & ~s_taken[wb + k];
-          n_cand += __popc(v);
-          if (v && first > (wb + k) * 32) first = (wb + k) * 32 + __ffs(v) - 1;
-        }
-      }
-      n_cand = warp_sum(n_cand);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-      const bool pre = n_cand > 32 * G_CPL;
-      const uint4 *rowj4 = row4;
-      if (pre) {
-        rowj4 = reinterpret_cast<const uint4 *>(ga.adj + (size_t)first * row_words);
-        if (lane == 0) {
-          my_mem[1] = first;
-          my_mp[1] = ga.mp[first];
-          my_sp[1] = ga.sp[first];
-        }
-        size = 2;
-        __syncwarp();
-      }
-      const int k_start = size;  // members whose rows are already folded into the candidate list
-      int ord_base = 0, n_total = 0;
-      if (n_cand > 0) do {
-        // candidates in ascending position; ordinals [ord_base, ord_base + G_CL)
-        int seen = 0;
-        for (int seg = 0; seg * 256 < row_words; ++seg) {
-          const int wb = seg * 256 + lane * 8;
-          unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          int cnt = 0;
-          if (wb < row_words) {
-            const uint4 x = __ldg(row4 + wb / 4), y = __ldg(row4 + wb / 4 + 1);
-            w[0] = x.x, w[1] = x.y, w[2] = x.z, w[3] = x.w, w[4] = y.x, w[5] = y.y, w[6] = y.z, w[7] = y.w;
-            if (pre) {
-              const uint4 p = __ldg(rowj4 + wb / 4), q = __ldg(rowj4 + wb / 4 + 1);
-              w[0] &= p.x, w[1] &= p.y, w[2] &= p.z, w[3] &= p.w, w[4] &= q.x, w[5] &= q.y, w[6] &= q.z, w[7] &= q.w;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              w[k] &= ~s_taken[wb + k];
-              cnt += __popc(w[k]);
-            }
-          }
-          const int incl = warp_incl_scan(cnt, lane);
-          const int tot = __shfl_sync(0xffffffffu, incl, 31);
-          if (tot) {
-            int o = seen + incl - cnt - ord_base;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              unsigned bits = w[k];
-              while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (o >= 0 && o < G_CL) my_cand[o] = (wb + k) * 32 + b;
-                ++o;
-              }
-            }
-          }
-          seen += tot;
-        }
-        n_total = seen;
-        const int n_list = min(G_CL, n_total - ord_base);
-        __syncwarp();
-        // ---- chunks of 128 candidates: test against the members so far, admit survivors in order ----
-        int nj[G_CPL];
-        float4 nm[G_CPL], ns[G_CPL];
-        unsigned nalive = 0;
-#pragma unroll
-        for (int u = 0; u < G_CPL; ++u) {
-          const int idx = u * 32 + lane;
-          if (idx < n_list) {
-            nj[u] = my_cand[idx];
-            nm[u] = ga.mp[nj[u]];
-            ns[u] = ga.sp[nj[u]];
-            nalive |= 1u << u;
-          }
-        }
-        for (int cb = 0; cb < n_list; cb += 32 * G_CPL) {
-          int j[G_CPL];
-          float4 mj[G_CPL], sj[G_CPL];
-          unsigned alive = nalive;
-#pragma unroll
-          for (int u = 0; u < G_CPL; ++u) {
-            j[u] = nj[u];
-            mj[u] = nm[u];
-            sj[u] = ns[u];
-          }
-          nalive = 0;
-#pragma unroll
-          for (int u = 0; u < G_CPL; ++u) {  // prefetch the next chunk
-            const int idx = cb + 32 * G_CPL + u * 32 + lane;
-            if (idx < n_list) {
-              nj[u] = my_cand[idx];
-              nm[u] = ga.mp[nj[u]];
-              ns[u] = ga.sp[nj[u]];
-              nalive |= 1u << u;
-            }
-          }
-          for (int k = k_start; k < size; ++k) {
-            if (!__any_sync(0xffffffffu, alive != 0)) break;
-            float4 mk, sk;
-            if (k < G_MC) {
-              mk = my_mp[k];
-              sk = my_sp[k];
-            } else {
-              const int mi = *reinterpret_cast<volatile int *>(my_over + k);
-              mk = ga.mp[mi];
-              sk = ga.sp[mi];
-            }
-#pragma unroll
-            for (int u = 0; u < G_CPL; ++u)
-              if (((alive >> u) & 1u) && !gc_fits(mk, sk, mj[u], sj[u], g_lo, g_hi, gc_size)) alive &= ~(1u << u);
-          }
+      // successful seeds publish their members: hash slot value = lowest window position holding it
+      if (size > gc_threshold && size <= G_MC) {
+        for (int kk = lane; kk < size; kk += 32) {
+          const int m = my_mem[kk];
+          unsigned h = gc_hash(m);
           while (true) {
-            unsigned bal = 0;
-            int usel = -1;
-#pragma unroll
-            for (int u = 0; u < G_CPL; ++u) {
-              if (usel < 0) {
-                bal = __ballot_sync(0xffffffffu, (alive >> u) & 1u);
-                if (bal) usel = u;
-              }
+            const int old = atomicCAS(&s_hkey[h], -1, m);
+            if (old == -1 || old == m) {
+              atomicMin(&s_hval[h], warp);
+              break;
             }
-            if (usel < 0) break;
-            const int owner = __ffs(bal) - 1;
-            if (lane == owner) {
-              int jj = j[0];
-              float4 a = mj[0], b = sj[0];
-#pragma unroll
-              for (int v = 1; v < G_CPL; ++v)
-                if (usel == v) {
-                  jj = j[v];
-                  a = mj[v];
-                  b = sj[v];
-                }
-              s_newm[warp] = a;
-              s_news[warp] = b;
-              if (size < G_MC) {
-                my_mem[size] = jj;
-                my_mp[size] = a;
-                my_sp[size] = b;
-              } else {
-                *reinterpret_cast<volatile int *>(my_over + size) = jj;
-              }
-              alive &= ~(1u << usel);
-            }
-            __syncwarp();
-            const float4 mk = s_newm[warp], sk = s_news[warp];
-            ++size;
-#pragma unroll
-            for (int u = 0; u < G_CPL; ++u)
-              if (((alive >> u) & 1u) && !gc_fits(mk, sk, mj[u], sj[u], g_lo, g_hi, gc_size)) alive &= ~(1u << u);
-            __syncwarp();
+            h = (h + 1) & (G_HS - 1);
           }
         }
-        ord_base += G_CL;
-      } while (ord_base < n_total);
-      if (lane == 0) s_size[warp] = size;
+      }
     }
+    GC_CLOCK(c2);
+    GC_ACC(t_eval, c2 - c1);
     __threadfence_block();
     __syncthreads();
+    GC_CLOCK(c3);
+    GC_ACC(t_wait, c3 - c2);
 
-    // ---- commit (warp 0): walk the window in order; a seed whose set touches an element taken
-    // earlier in this walk is the first inexact one: everything before it is what the sequential
-    // algorithm computes, the next window restarts there ----
-    if (warp == 0) {
-      int n_inst = s_ninst, total = s_total;
-      int pstar = nwin;
-      for (int r = 0; r < nwin; ++r) {
-        const int sz = s_size[r];
-        bool conflict = false;
-        for (int k0 = 0; k0 < sz; k0 += 32) {
-          const int k = k0 + lane;
-          int m = -1;
-          if (k < sz) m = (k < G_MC) ? s_mem[r * G_MC + k] : __ldcg(ga.overflow + (size_t)r * C_cap + k);
-          const bool hit = m >= 0 && ((s_taken[m >> 5] >> (m & 31)) & 1u);
-          if (__any_sync(0xffffffffu, hit)) conflict = true;
+    // ---- commit: walk the window in order; a seed whose set touches an element claimed by an earlier
+    // successful seed of this window is the first inexact one: everything before it is what the
+    // sequential algorithm computes, the next window restarts there ----
+    const bool slow = s_big != 0;
+    int pstar = nwin;
+    int my_off = -1, my_inst = 0;
+    if (!slow) {
+      if (warp < nwin) {
+        const int size = s_size[warp];
+        bool hit = false;
+        for (int kk = lane; kk < size; kk += 32) {
+          const int m = my_mem[kk];
+          unsigned h = gc_hash(m);
+          while (true) {
+            const int key = s_hkey[h];
+            if (key == -1) break;
+            if (key == m) {
+              hit = s_hval[h] < warp;
+              break;
+            }
+            h = (h + 1) & (G_HS - 1);
+          }
+          if (hit) break;
         }
-        if (conflict) {
+        const bool conflict = __any_sync(0xffffffffu, hit);
+        if (lane == 0) s_conf[warp] = conflict ? 1 : 0;
+      }
+      __syncthreads();
+      // every thread resolves the window identically
+      int run_total = total, run_inst = n_inst;
+      for (int r = 0; r < nwin; ++r) {
+        if (s_conf[r]) {
           pstar = r;
           break;
         }
+        const int sz = s_size[r];
         if (sz > gc_threshold) {
-          for (int k0 = 0; k0 < sz; k0 += 32) {
-            const int k = k0 + lane;
-            if (k < sz) {
-              const int m = (k < G_MC) ? s_mem[r * G_MC + k] : __ldcg(ga.overflow + (size_t)r * C_cap + k);
-              atomicOr(&s_taken[m >> 5], 1u << (m & 31));
-            }
+          if (r == warp) {
+            my_off = run_total;
+            my_inst = run_inst;
           }
-          if (lane == 0) {
-            s_commit_off[r] = total;
-            s_commit_inst[r] = n_inst;
-          }
-          total += sz;
-          ++n_inst;
-        } else if (lane == 0) {
-          s_commit_off[r] = -1;
+          run_total += sz;
+          ++run_inst;
         }
-        __syncwarp();
       }
-      for (int r = pstar + lane; r < nwin; r += 32) s_commit_off[r] = -1;
-      if (lane == 0) {
-        s_cur = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
-        s_ninst = n_inst;
-        s_total = total;
+      total = run_total;
+      n_inst = run_inst;
+      cur = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
+      if (warp < nwin && my_off >= 0) {
+        const int sz = s_size[warp];
+        for (int kk = lane; kk < sz; kk += 32) {
+          const int m = my_mem[kk];
+          atomicOr(&s_taken[m >> 5], 1u << (m & 31));
+          ga.members[my_off + kk] = m;
+        }
+        if (lane == 0 && my_inst < max_inst) ga.inst_offsets[my_inst + 1] = my_off + sz;
+      }
+      __syncthreads();  // all probes done before the table is cleared
+      for (int h = tid; h < G_HS; h += GG_THREADS) {
+        s_hkey[h] = -1;
+        s_hval[h] = 0x7fffffff;
+      }
+    } else {
+      // a set larger than the shared-memory member list: sequential walk by warp 0
+      __shared__ int s_res[4];
+      if (warp == 0) {
+        int run_total = total, run_inst = n_inst;
+        for (int r = 0; r < nwin; ++r) {
+          const int sz = s_size[r];
+          bool conflict = false;
+          for (int k0 = 0; k0 < sz; k0 += 32) {
+            const int kk = k0 + lane;
+            int m = -1;
+            if (kk < sz) m = (kk < G_MC) ? s_mem[r][kk] : __ldcg(ga.overflow + (size_t)r * C_cap + kk);
+            const bool hit = m >= 0 && ((s_taken[m >> 5] >> (m & 31)) & 1u);
+            if (__any_sync(0xffffffffu, hit)) conflict = true;
+          }
+          if (conflict) {
+            pstar = r;
+            break;
+          }
+          if (sz > gc_threshold) {
+            for (int k0 = 0; k0 < sz; k0 += 32) {
+              const int kk = k0 + lane;
+              if (kk < sz) {
+                const int m = (kk < G_MC) ? s_mem[r][kk] : __ldcg(ga.overflow + (size_t)r * C_cap + kk);
+                atomicOr(&s_taken[m >> 5], 1u << (m & 31));
+                ga.members[run_total + kk] = m;
+              }
+            }
+            if (lane == 0 && run_inst < max_inst) ga.inst_offsets[run_inst + 1] = run_total + sz;
+            run_total += sz;
+            ++run_inst;
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
+          s_res[0] = run_total;
+          s_res[1] = run_inst;
+          s_res[2] = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
+        }
+      }
+      __syncthreads();
+      total = s_res[0];
+      n_inst = s_res[1];
+      cur = s_res[2];
+      for (int h = tid; h < G_HS; h += GG_THREADS) {
+        s_hkey[h] = -1;
+        s_hval[h] = 0x7fffffff;
       }
     }
     __syncthreads();
-    // ---- committed seeds write their member lists ----
-    if (warp < nwin && s_commit_off[warp] >= 0) {
-      const int off = s_commit_off[warp], sz = s_size[warp], inst = s_commit_inst[warp];
-      for (int k = lane; k < sz; k += 32)
-        ga.members[off + k] = (k < G_MC) ? my_mem[k] : *reinterpret_cast<volatile int *>(my_over + k);
-      if (lane == 0 && inst < max_inst) ga.inst_offsets[inst + 1] = off + sz;
-    }
-    // the next round's window selection (warp 0) only reads s_taken / s_cur, written before the barrier
+    GC_ACC(t_commit, clock64() - c3);
   }
-  if (tid == 0) *ga.n_inst_out = s_ninst;
+  if (tid == 0) *ga.n_inst_out = n_inst;
+#ifdef B200_GC_TIMING
+  if (ga.dbg && lane == 0) {
+    long long *d = ga.dbg + warp * 8;
+    d[0] = n_rounds, d[1] = t_win, d[2] = t_eval, d[3] = t_commit, d[4] = t_wait;
+  }
+#endif
 }
 
 // ---- RANSAC pose per instance -------------------------------------------------------------------
 // boost::mt19937 seeded 12345 (RandomSampleConsensus, non-random mode).  Every instance restarts the
 // same stream, so the generator state after seeding and the first twist is computed once on the host
-// and copied into shared memory per warp.
-struct Mt19937 {
-  unsigned *s;  // 624 words
-  int idx;
-  __device__ unsigned next() {
-    if (idx >= 624) {
-      for (int i = 0; i < 624; ++i) {
-        const unsigned y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
-        s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      idx = 0;
-    }
-    unsigned y = s[idx++];
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= y >> 18;
-    return y;
-  }
-};
-
+// and copied into shared memory per warp; later twists are done by the whole warp.
 void mt19937_twisted_state(unsigned seed, unsigned out[624]) {
   out[0] = seed;
   for (int i = 1; i < 624; ++i) out[i] = 1812433253u * (out[i - 1] ^ (out[i - 1] >> 30)) + (unsigned)i;
@@ -502,6 +552,47 @@ void mt19937_twisted_state(unsigned seed, unsigned out[624]) {
     const unsigned y = (out[i] & 0x80000000u) | (out[(i + 1) % 624] & 0x7fffffffu);
     out[i] = out[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
   }
+}
+
+__device__ __forceinline__ unsigned mt_twist_word(unsigned a, unsigned b, unsigned c) {
+  const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+// In-place regeneration of the 624-word state by one warp.  Word i needs s[i], s[i+1] (old) and
+// s[(i+397) % 624]: old for i < 227, already regenerated for i >= 227 — so ranges of at most 227
+// words are independent.
+__device__ void mt_twist_warp(unsigned *s, int lane) {
+  // every lane runs the same trip counts, so the __syncwarp calls are convergent; a step reads its
+  // inputs before the barrier and writes after it (s[i + 1] belongs to the neighbouring lane)
+  for (int base = 0; base < 227; base += 32) {
+    const int i = base + lane;
+    const bool on = i < 227;
+    unsigned v = 0;
+    if (on) v = mt_twist_word(s[i], s[i + 1], s[i + 397]);
+    __syncwarp();
+    if (on) s[i] = v;
+    __syncwarp();
+  }
+  for (int base = 227; base < 623; base += 32) {  // s[i - 227] was regenerated at least 195 words earlier
+    const int i = base + lane;
+    const bool on = i < 623;
+    unsigned v = 0;
+    if (on) v = mt_twist_word(s[i], s[i + 1], s[i - 227]);
+    __syncwarp();
+    if (on) s[i] = v;
+    __syncwarp();
+  }
+  if (lane == 0) s[623] = mt_twist_word(s[623], s[0], s[396]);
+  __syncwarp();
+}
+
+__device__ __forceinline__ unsigned mt_temper(unsigned y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
 }
 
 struct RansacBuffers {
@@ -520,11 +611,9 @@ struct RansacBuffers {
   b200_corr *inst_corrs;
 };
 
-constexpr int RS_WARPS = 4;            // instances per CTA (one warp each)
-constexpr int RS_THREADS = RS_WARPS * 32;
-constexpr int RS_BATCH = 32;           // samples fitted per batch (one per lane)
-constexpr int RS_FIRST_BATCH = 8;
-constexpr int RS_SMALL = 128;          // instances up to this size keep their shuffle array in shared memory
+constexpr int RS_THREADS = 128;        // one CTA per instance
+constexpr int RS_BATCH = RS_THREADS;   // samples fitted per batch (one per thread)
+constexpr int RS_SMALL = 128;          // instances up to this size keep shuffle array / pair matrix in shared memory
 
 // squared residual of correspondence (s → g) under the row-major 4x4 float transform T
 __device__ __forceinline__ float residual2(const float *T, const float4 &s, const float4 &g) {
@@ -543,32 +632,53 @@ __device__ __forceinline__ float residual2(const float *T, const float4 &s, cons
   return d;
 }
 
+__device__ __forceinline__ float sqdiff3(const float4 &u, const float4 &v) {
+  const float dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// r % d for 32-bit operands through a precomputed 64-bit reciprocal (Lemire's fastmod): exact.
+__device__ __forceinline__ unsigned fastmod_u32(unsigned r, unsigned long long magic, unsigned d) {
+  return (unsigned)__umul64hi(magic * r, d);
+}
+
+// One CTA per instance.  The sample sequence is inherently serial (one mt19937 stream, a partial
+// Fisher-Yates shuffle whose state carries over between draws), so thread 0 draws; everything that
+// does not depend on the shuffle state is taken out of that loop: the swap partners of a whole
+// 624-word generator block are computed by all threads at once, isSampleGood is a table lookup,
+// positions 0..2 of the shuffle array live in registers.  Models (double-precision Umeyama) are
+// fitted and scored one sample per thread, in batches of 1, 4, 32, 128, 128, ...; thread 0 then
+// replays the adaptive termination rule in order and discards the samples past the stopping point.
 __global__ void __launch_bounds__(RS_THREADS)
     gc_ransac_kernel(RansacBuffers rb, int max_inst, int corr_cap, double threshold, int max_iterations) {
-  __shared__ unsigned s_mt[RS_WARPS][624];
-  __shared__ float s_Tb[RS_WARPS][RS_BATCH][17];  // padded rows: one sample per lane
-  __shared__ int s_sel[RS_WARPS][RS_BATCH][3];
-  __shared__ int s_cnt[RS_WARPS][RS_BATCH];
-  __shared__ float s_bestT[RS_WARPS][16];
-  __shared__ float s_acc[RS_WARPS][9];
-  __shared__ int s_shuf[RS_WARPS][RS_SMALL];
+  __shared__ unsigned s_mt[624];
+  __shared__ unsigned short s_jx[624];  // swap partner of draw t (valid when n <= 65536)
+  __shared__ float s_Tb[RS_BATCH][17];  // padded rows: one sample per thread
+  __shared__ int s_sel[RS_BATCH][3];
+  __shared__ int s_cnt[RS_BATCH];
+  __shared__ float s_bestT[16];
+  __shared__ float s_acc[9];
+  __shared__ int s_shuf[RS_SMALL];
+  __shared__ unsigned s_pg[RS_SMALL][RS_SMALL / 32];  // pair (p, q) far enough apart for isSampleGood
+  __shared__ int s_ctrl[8];  // 0 nb, 1 draw_failed, 2 need_twist, 3 stop, 4 any_good, 5 have_best
+  __shared__ int s_warp_cnt[RS_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_inst = min(*rb.n_inst, max_inst);
-  const int b = blockIdx.x * RS_WARPS + warp;
+  const int b = blockIdx.x;
   if (b >= n_inst) return;
   const int off = rb.inst_offsets[b];
   const int n = rb.inst_offsets[b + 1] - off;
   const int *mem = rb.members + off;
-  int *shuffled = (n <= RS_SMALL) ? s_shuf[warp] : rb.shuffled + off;  // drawn from by lane 0 only
+  const bool small = n <= RS_SMALL;
+  int *shuffled = small ? s_shuf : rb.shuffled + off;  // drawn from by thread 0 only
   int *last_pos = rb.last_pos + off;
   int *flags = rb.flags + off;
-  unsigned *mt = s_mt[warp];
-  float(*Tb)[17] = s_Tb[warp];
 
-  for (int i = lane; i < 624; i += 32) mt[i] = rb.mt_init[i];
+  for (int i = tid; i < 624; i += RS_THREADS) s_mt[i] = rb.mt_init[i];
+  if (tid < 8) s_ctrl[tid] = 0;
   // index maps keyed by the model index: the last correspondence with a given index_query wins
   // (std::map in computeOriginalIndexMapping, unordered_map index_to_correspondence)
-  for (int t = lane; t < n; t += 32) {
+  for (int t = tid; t < n; t += RS_THREADS) {
     const int q = rb.sorted[mem[t]].index_query;
     int last = t;
     for (int u = t + 1; u < n; ++u)
@@ -577,13 +687,13 @@ __global__ void __launch_bounds__(RS_THREADS)
     shuffled[t] = t;
   }
   // computeSampleDistanceThreshold: float32 single-pass covariance of the source (model) points in
-  // list order, one lane per accumulator
-  if (lane < 9) {
+  // list order, one thread per accumulator
+  if (tid < 9) {
     float acc = 0.0f;
     for (int t = 0; t < n; ++t) {
       const float4 v = rb.mp[mem[t]];
       float a, c;
-      switch (lane) {
+      switch (tid) {
         case 0: a = v.x, c = v.x; break;
         case 1: a = v.x, c = v.y; break;
         case 2: a = v.x, c = v.z; break;
@@ -594,27 +704,15 @@ __global__ void __launch_bounds__(RS_THREADS)
         case 7: a = v.y, c = 1.0f; break;
         default: a = v.z, c = 1.0f; break;
       }
-      acc += (lane < 6) ? a * c : a;
+      acc += (tid < 6) ? a * c : a;
     }
-    s_acc[warp][lane] = acc / (float)n;
+    s_acc[tid] = acc / (float)n;
   }
-  __syncwarp();
+  __syncthreads();
 
-  // lane-0 state
-  double sample_dist_thresh = 0.0;
-  Mt19937 rng;
-  rng.s = mt;
-  rng.idx = 0;
-  int iterations = 0, n_best = -2147483647;
-  double k = 1.0;
-  const unsigned skipped = 0;  // computeModelCoefficients cannot fail for a 3-sample
-  const unsigned max_skip = (unsigned)max_iterations * 10u;
-  const double log_probability = log(1.0 - 0.99);
-  const double one_over_indices = 1.0 / (double)n;
-  const double thresh2 = threshold * threshold;
-  bool have_best = false, stop = false;
-  if (lane == 0) {
-    const float *a = s_acc[warp];
+  double sample_dist_thresh;
+  {
+    const float *a = s_acc;  // every thread evaluates the same scalar expression
     float cov[9];
     cov[0] = a[0] - a[6] * a[6];
     cov[1] = a[1] - a[6] * a[7];
@@ -630,81 +728,134 @@ __global__ void __launch_bounds__(RS_THREADS)
     sample_dist_thresh = ((double)(sqrtf(ev[0]) + sqrtf(ev[1]) + sqrtf(ev[2]))) / 3.0;
     sample_dist_thresh *= sample_dist_thresh;
   }
-  // isSampleGood needs three members whose pairwise squared (model) distances all exceed the
-  // threshold.  When no such triple exists (typical: several scene points matched to one model
-  // point) every one of getSamples' 1000 redraws fails and RANSAC ends without a model, whatever
-  // the random stream is: detect that up front instead of replaying 3000 draws on one lane.
-  if (n <= RS_SMALL && n >= 3) {
-    sample_dist_thresh = __shfl_sync(0xffffffffu, sample_dist_thresh, 0);
-    int any_good = 0;
-    for (int pq = lane; pq < n * n && !any_good; pq += 32) {
-      const int p = pq / n, q = pq % n;
-      if (q <= p) continue;
-      const float4 a = rb.mp[mem[p]], c = rb.mp[mem[q]];
-      auto sq = [](const float4 &u, const float4 &v) {
-        const float dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z;
-        return dx * dx + dy * dy + dz * dz;
-      };
-      // squared distances are symmetric bit for bit (the differences only change sign)
-      if (!((double)sq(c, a) > sample_dist_thresh)) continue;
-      for (int r = q + 1; r < n; ++r) {
-        const float4 e = rb.mp[mem[r]];
-        if ((double)sq(e, a) > sample_dist_thresh && (double)sq(e, c) > sample_dist_thresh) {
-          any_good = 1;
-          break;
-        }
-      }
-    }
-    if (!__any_sync(0xffffffffu, any_good)) stop = true;  // lane 0 then draws nothing: "no samples could be selected"
-  }
 
-  int batch_cap = RS_FIRST_BATCH;
+  const double thresh2 = threshold * threshold;
+  // isSampleGood needs three members whose pairwise squared (model) distances all exceed the
+  // threshold.  For small instances the pair predicate is tabulated once; when no good triple
+  // exists at all (typical: several scene points matched to one model point) every one of
+  // getSamples' 1000 redraws fails and RANSAC ends without a model whatever the random stream is —
+  // detected here instead of replaying 3000 draws on one thread.
+  if (small && n >= 3) {
+    const int nw = (n + 31) >> 5;
+    for (int e = tid; e < n * nw; e += RS_THREADS) {
+      const int p = e / nw, w = e % nw;
+      const float4 a = rb.mp[mem[p]];
+      unsigned bits = 0;
+      for (int q = w * 32; q < min(n, w * 32 + 32); ++q)
+        if (q != p && (double)sqdiff3(rb.mp[mem[q]], a) > sample_dist_thresh) bits |= 1u << (q & 31);
+      s_pg[p][w] = bits;  // symmetric bit for bit: the coordinate differences only change sign
+    }
+    __syncthreads();
+    int any_good = 0;
+    for (int pq = tid; pq < n * n && !any_good; pq += RS_THREADS) {
+      const int p = pq / n, q = pq % n;
+      if (q <= p || !((s_pg[p][q >> 5] >> (q & 31)) & 1u)) continue;
+      for (int w = 0; w < nw; ++w)
+        if (s_pg[p][w] & s_pg[q][w]) any_good = 1;
+    }
+    if (any_good) s_ctrl[4] = 1;
+    __syncthreads();
+    if (tid == 0 && !s_ctrl[4]) s_ctrl[3] = 1;  // "no samples could be selected"
+  }
+  unsigned long long magic[3] = {0, 0, 0};
+  if (n >= 3)
+    for (int i = 0; i < 3; ++i) magic[i] = 0xFFFFFFFFFFFFFFFFull / (unsigned)(n - i) + 1ull;
+  const bool use_jx = n >= 3 && n <= 65536;
+  auto fill_jx = [&]() {  // swap partners for the 208 redraws of the current generator block
+    if (use_jx)
+      for (int t = tid; t < 624; t += RS_THREADS) {
+        const int i = t % 3;
+        s_jx[t] = (unsigned short)(i + (int)fastmod_u32(mt_temper(s_mt[t]) >> 1, magic[i], (unsigned)(n - i)));
+      }
+  };
+  fill_jx();
+  __syncthreads();
+
+  // thread-0 state
+  int mt_idx = 0;
+  int iterations = 0, n_best = -2147483647;
+  double k = 1.0;
+  const unsigned skipped = 0;  // computeModelCoefficients cannot fail for a 3-sample
+  const unsigned max_skip = (unsigned)max_iterations * 10u;
+  const double log_probability = log(1.0 - 0.99);
+  const double one_over_indices = 1.0 / (double)n;
+  int sh0 = 0, sh1 = 1, sh2 = 2;  // shuffled[0..2]
+  int attempts = 0;               // redraws of the sample under construction (survives a twist)
+  int nb_local = 0;
+
+  int batch_cap = 1;
   while (true) {
-    // ---- lane 0: draw the next samples of the (serial) sample sequence ----
-    int nb = 0, draw_failed = 0;
-    if (lane == 0) {
-      if (!stop && (double)iterations < k && skipped < max_skip && n >= 3) {
-        for (; nb < batch_cap; ++nb) {
+    // ---- draw phase ----
+    if (tid == 0) {
+      nb_local = 0;
+      s_ctrl[1] = 0;
+      attempts = 0;
+    }
+    while (true) {
+      if (tid == 0) {
+        s_ctrl[2] = 0;
+        const bool active = !s_ctrl[3] && (double)iterations < k && skipped < max_skip && n >= 3;
+        while (active && nb_local < batch_cap && !s_ctrl[1]) {
           bool good = false;
-          int sel[3] = {0, 0, 0};
-          for (int iter = 0; iter < 1000 && !good; ++iter) {  // SampleConsensusModel::getSamples
-            for (int i = 0; i < 3; ++i) {                     // drawIndexSample
-              const int r = (int)(rng.next() >> 1);
-              const int jx = i + (r % (n - i));
-              const int tmp = shuffled[i];
-              shuffled[i] = shuffled[jx];
-              shuffled[jx] = tmp;
+          while (!good && attempts < 1000 && mt_idx < 624) {  // SampleConsensusModel::getSamples
+            int j0, j1, j2;
+            if (use_jx) {
+              j0 = s_jx[mt_idx], j1 = s_jx[mt_idx + 1], j2 = s_jx[mt_idx + 2];
+            } else {
+              j0 = (int)((mt_temper(s_mt[mt_idx]) >> 1) % (unsigned)n);
+              j1 = 1 + (int)((mt_temper(s_mt[mt_idx + 1]) >> 1) % (unsigned)(n - 1));
+              j2 = 2 + (int)((mt_temper(s_mt[mt_idx + 2]) >> 1) % (unsigned)(n - 2));
             }
-            sel[0] = shuffled[0];
-            sel[1] = shuffled[1];
-            sel[2] = shuffled[2];
-            const float4 p0 = rb.mp[mem[sel[0]]], p1 = rb.mp[mem[sel[1]]], p2 = rb.mp[mem[sel[2]]];
-            auto sq = [](const float4 &u, const float4 &v) {
-              const float dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z;
-              return dx * dx + dy * dy + dz * dz;
-            };
-            good = (double)sq(p1, p0) > sample_dist_thresh && (double)sq(p2, p0) > sample_dist_thresh &&
-                   (double)sq(p2, p1) > sample_dist_thresh;  // isSampleGood
+            mt_idx += 3;
+            // drawIndexSample: swap(shuffled[i], shuffled[i + r % (n - i)]) for i = 0, 1, 2
+            int t;
+            if (j0 == 1) { t = sh0, sh0 = sh1, sh1 = t; }
+            else if (j0 == 2) { t = sh0, sh0 = sh2, sh2 = t; }
+            else if (j0 > 2) { t = shuffled[j0], shuffled[j0] = sh0, sh0 = t; }
+            if (j1 == 2) { t = sh1, sh1 = sh2, sh2 = t; }
+            else if (j1 > 2) { t = shuffled[j1], shuffled[j1] = sh1, sh1 = t; }
+            if (j2 > 2) { t = shuffled[j2], shuffled[j2] = sh2, sh2 = t; }
+            if (small) {
+              good = ((s_pg[sh0][sh1 >> 5] >> (sh1 & 31)) & (s_pg[sh0][sh2 >> 5] >> (sh2 & 31)) &
+                      (s_pg[sh1][sh2 >> 5] >> (sh2 & 31)) & 1u) != 0;
+            } else {
+              const float4 p0 = rb.mp[mem[sh0]], p1 = rb.mp[mem[sh1]], p2 = rb.mp[mem[sh2]];
+              good = (double)sqdiff3(p1, p0) > sample_dist_thresh && (double)sqdiff3(p2, p0) > sample_dist_thresh &&
+                     (double)sqdiff3(p2, p1) > sample_dist_thresh;  // isSampleGood
+            }
+            ++attempts;
           }
-          if (!good) {
-            draw_failed = 1;  // "No samples could be selected": the loop ends when it gets here
+          if (good) {
+            s_sel[nb_local][0] = sh0;
+            s_sel[nb_local][1] = sh1;
+            s_sel[nb_local][2] = sh2;
+            ++nb_local;
+            attempts = 0;
+          } else if (attempts >= 1000) {
+            s_ctrl[1] = 1;  // "No samples could be selected": the loop ends when it gets here
+          } else {
+            s_ctrl[2] = 1;  // generator block used up (624 = 3 x 208: falls between redraws)
             break;
           }
-          s_sel[warp][nb][0] = sel[0];
-          s_sel[warp][nb][1] = sel[1];
-          s_sel[warp][nb][2] = sel[2];
         }
+        s_ctrl[0] = nb_local;
       }
+      __syncthreads();
+      if (!s_ctrl[2]) break;
+      if (warp == 0) mt_twist_warp(s_mt, lane);
+      __syncthreads();
+      fill_jx();
+      if (tid == 0) mt_idx = 0;
+      __syncthreads();
     }
-    nb = __shfl_sync(0xffffffffu, nb, 0);
-    draw_failed = __shfl_sync(0xffffffffu, draw_failed, 0);
+    const int nb = s_ctrl[0];
     if (nb == 0) break;
-    // ---- lane l: model from sample l (computeModelCoefficients) ----
-    if (lane < nb) {
+    // ---- thread t: model from sample t (computeModelCoefficients), then countWithinDistance ----
+    if (tid < nb) {
       double src[9], dst[9];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int t = s_sel[warp][lane][i];
+        const int t = s_sel[tid][i];
         const float4 s = rb.mp[mem[t]];
         const float4 g = rb.sp[mem[last_pos[t]]];
         src[i * 3 + 0] = s.x;
@@ -717,39 +868,39 @@ __global__ void __launch_bounds__(RS_THREADS)
       double Td[16];
       umeyama3(src, dst, 3, Td);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) Tb[lane][i] = (float)Td[i];
+      for (int i = 0; i < 16; ++i) s_Tb[tid][i] = (float)Td[i];
     }
-    __syncwarp();
-    // ---- countWithinDistance ----
-    if (n <= 64) {
-      if (lane < nb) {
+    __syncthreads();
+    if (nb >= 32 && n <= 256) {
+      if (tid < nb) {
         int cnt = 0;
         for (int t = 0; t < n; ++t)
-          cnt += ((double)residual2(Tb[lane], rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
-        s_cnt[warp][lane] = cnt;
+          cnt += ((double)residual2(s_Tb[tid], rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
+        s_cnt[tid] = cnt;
       }
     } else {
-      for (int sidx = 0; sidx < nb; ++sidx) {
+      for (int sidx = warp; sidx < nb; sidx += RS_THREADS / 32) {
         int cnt = 0;
         for (int t = lane; t < n; t += 32)
-          cnt += ((double)residual2(Tb[sidx], rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
+          cnt += ((double)residual2(s_Tb[sidx], rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
         cnt = warp_sum(cnt);
-        if (lane == 0) s_cnt[warp][sidx] = cnt;
+        if (lane == 0) s_cnt[sidx] = cnt;
       }
     }
-    __syncwarp();
-    // ---- lane 0: replay the sequential loop over the batch ----
-    if (lane == 0) {
+    __syncthreads();
+    // ---- thread 0: replay the sequential loop over the batch ----
+    if (tid == 0) {
+      bool stop = false;
       for (int i = 0; i < nb; ++i) {
         if (i > 0 && !((double)iterations < k && skipped < max_skip)) {
           stop = true;
           break;
         }
-        const int c = s_cnt[warp][i];
+        const int c = s_cnt[i];
         if (c > n_best) {
           n_best = c;
-          have_best = true;
-          for (int e = 0; e < 16; ++e) s_bestT[warp][e] = Tb[i][e];
+          s_ctrl[5] = 1;
+          for (int e = 0; e < 16; ++e) s_bestT[e] = s_Tb[i][e];
           const double w = (double)n_best * one_over_indices;
           double p_no_outliers = 1.0 - pow(w, 3.0);
           p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
@@ -762,36 +913,44 @@ __global__ void __launch_bounds__(RS_THREADS)
           break;
         }
       }
-      if (draw_failed) stop = true;
+      if (s_ctrl[1] || stop) s_ctrl[3] = 1;
     }
-    __syncwarp();
-    batch_cap = RS_BATCH;
+    __syncthreads();
+    batch_cap = (batch_cap == 1) ? 4 : (batch_cap == 4 ? 32 : RS_BATCH);
   }
   // ---- result: inliers of the best model, filtered correspondences ----
-  const bool ok = __shfl_sync(0xffffffffu, have_best ? 1 : 0, 0) != 0;
-  __syncwarp();
+  __syncthreads();
+  const bool ok = s_ctrl[5] != 0;
   int n_inl = 0;
   if (ok) {
-    // ordered compaction of the inlier positions; flags[] receives the list
-    for (int base = 0; base < n; base += 32) {
-      const int t = base + lane;
+    // ordered compaction of the inlier positions (block-wide, chunked); flags[] receives the list
+    for (int base = 0; base < n; base += RS_THREADS) {
+      const int t = base + tid;
       int f = 0;
-      if (t < n) f = ((double)residual2(s_bestT[warp], rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
+      if (t < n) f = ((double)residual2(s_bestT, rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
       const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) flags[n_inl + __popc(m & ((1u << lane) - 1u))] = t;
-      n_inl += __popc(m);
+      if (lane == 0) s_warp_cnt[warp] = __popc(m);
+      __syncthreads();
+      int before = n_inl, chunk_total = 0;
+      for (int w = 0; w < RS_THREADS / 32; ++w) {
+        if (w < warp) before += s_warp_cnt[w];
+        chunk_total += s_warp_cnt[w];
+      }
+      if (f) flags[before + __popc(m & ((1u << lane) - 1u))] = t;
+      n_inl += chunk_total;
+      __syncthreads();
     }
   }
-  __syncwarp();
+  __syncthreads();
   const bool use_model = ok && n_inl >= 3;
   float *T = rb.T_out + (size_t)b * 16;
-  if (lane < 16) T[lane] = use_model ? s_bestT[warp][lane] : ((lane % 5 == 0) ? 1.0f : 0.0f);
+  if (tid < 16) T[tid] = use_model ? s_bestT[tid] : ((tid % 5 == 0) ? 1.0f : 0.0f);
   const int out_n = use_model ? n_inl : n;
-  for (int i = lane; i < out_n; i += 32) {
+  for (int i = tid; i < out_n; i += RS_THREADS) {
     const int t = use_model ? last_pos[flags[i]] : i;
     if (off + i < corr_cap) rb.inst_corrs[off + i] = rb.sorted[mem[t]];
   }
-  if (lane == 0) rb.inst_counts[b] = out_n;
+  if (tid == 0) rb.inst_counts[b] = out_n;
 }
 
 }  // namespace
@@ -816,7 +975,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
     C_eff = std::max(1, std::min(C_now, C_cap));
     if (C_eff > GC_MAX_C) return ctx->fail(B200_ERR_CAPACITY, "gc: more than 524288 correspondences");
   }
-  const int row_words_cap = ((((C_eff + 31) >> 5) + 7) & ~7);
+  const int row_words_cap = ((((C_eff + 31) >> 5) + 127) & ~127);
   const float g_lo = nextafterf((float)gc_size, -INFINITY), g_hi = nextafterf((float)gc_size, INFINITY);
   DevBuf<b200_corr> sorted;
   DevBuf<float4> mp, sp;
@@ -848,16 +1007,33 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   ga.members = members.p;
   ga.inst_offsets = d_inst_offsets;
   ga.n_inst_out = d_n_inst;
+  DevBuf<long long> dbg;
+  const bool debug = getenv("B200_GC_DEBUG") != nullptr;
+  ga.dbg = nullptr;
+  if (debug) {
+    B200_TRY(dbg.alloc(ctx, GW * 8));
+    B200_TRY(dbg.zero());
+    ga.dbg = dbg.p;
+  }
   {
     StageScope st_(ctx, ST_GC_GROUP);
-    const size_t smem = (size_t)GW * G_MC * 2 * sizeof(float4) + (size_t)row_words_cap * sizeof(unsigned) +
-                        (size_t)GW * G_CL * sizeof(int) + (size_t)GW * G_MC * sizeof(int);
-    static_assert(GW * G_MC * 2 * sizeof(float4) + (GC_MAX_C / 32 + 8) * 4 + GW * G_CL * 4 + GW * G_MC * 4 <= 200 * 1024,
-                  "grouping kernel shared memory");
+    // shared memory: the taken bitmap plus one candidate bitmap per concurrently evaluated seed
+    const size_t row_bytes = (size_t)row_words_cap * sizeof(unsigned);
+    const size_t budget = 160 * 1024;
+    if (2 * row_bytes > budget) return ctx->fail(B200_ERR_CAPACITY, "gc: too many correspondences for the grouping kernel");
+    const size_t smem = std::min(budget, row_bytes * (size_t)(1 + GW));
     B200_CUDA(ctx, cudaFuncSetAttribute(gc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gc_group_kernel<<<1, GG_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, gc_size, g_lo, g_hi, gc_threshold,
+    gc_group_kernel<<<1, GG_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, (int)smem, gc_size, g_lo, g_hi, gc_threshold,
                                                           max_inst);
     B200_LAUNCHED(ctx);
+  }
+  if (debug) {
+    long long h[GW * 8];
+    B200_CUDA(ctx, cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int w = 0; w < GW; ++w)
+      fprintf(stderr, "gc_group warp %2d: rounds %lld cycles window %lld eval %lld wait %lld commit %lld\n", w, h[w * 8], h[w * 8 + 1],
+              h[w * 8 + 2], h[w * 8 + 4], h[w * 8 + 3]);
   }
 
   if (!ctx->mt_state) {
@@ -885,7 +1061,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   rb.inst_counts = d_inst_counts;
   rb.inst_corrs = d_inst_corrs;
   StageScope st_(ctx, ST_GC_RANSAC);
-  gc_ransac_kernel<<<ceil_div(max_inst, RS_WARPS), RS_THREADS, 0, ctx->stream>>>(rb, max_inst, corr_cap, gc_size, 10000);
+  gc_ransac_kernel<<<max_inst, RS_THREADS, 0, ctx->stream>>>(rb, max_inst, corr_cap, gc_size, 10000);
   B200_LAUNCHED(ctx);
   return B200_OK;
 }

@@ -355,6 +355,41 @@ def test_gc_large_instances(ctx, orc, b200):
         assert _rot_angle_deg(A[:3, :3].astype(np.float64), B[:3, :3].astype(np.float64)) < 0.01
 
 
+def test_gc_ransac_rare_good_samples(ctx, orc, b200):
+    """Instances in which almost every 3-sample is rejected by isSampleGood (many scene points matched to one model
+    point): RANSAC redraws hundreds of times, past the first 624 outputs of the mt19937 stream.  One instance
+    has no good sample at all (identity transform, unfiltered correspondences)."""
+    from scipy.spatial.transform import Rotation
+    rng = _rng(91)
+    model = np.array([[0, 0, 0], [0.3, 0, 0], [0, 0.25, 0.1], [2, 2, 2], [2.2, 2, 2]], np.float32)
+    R = Rotation.random(random_state=3).as_matrix()
+    base = (model.astype(np.float64) @ R.T + [0.5, -0.2, 1.0]).astype(np.float32)
+    scene, corr = [], []
+
+    def add(mi, pt, d):
+        corr.append((mi, len(scene), d))
+        scene.append(pt)
+    add(0, base[0], 0.01)
+    add(1, base[1], 0.02)
+    for i in range(38):                                  # 38 scene points matched to model point 2
+        add(2, base[2] + rng.uniform(-0.002, 0.002, 3).astype(np.float32), 0.03 + 0.001 * i)
+    for i in range(5):                                   # second instance: every member shares model point 3
+        add(3, base[3] + np.float32([1, 0, 0]) + rng.uniform(-0.002, 0.002, 3).astype(np.float32), 0.1 + 0.001 * i)
+    scene = np.array(scene, np.float32)
+    corrs = np.zeros(len(corr), dtype=b200.CORR_DTYPE)
+    corrs["index_query"] = [c[0] for c in corr]
+    corrs["index_match"] = [c[1] for c in corr]
+    corrs["distance"] = np.array([c[2] for c in corr], np.float32)
+    T, inst, n = ctx.gc_recognize(model, scene, corrs, 0.01, 2, max_inst=16)
+    oT, oinst = orc.gc_recognize(model, scene, corrs, 0.01, 2, max_inst=16)
+    assert n == len(oT) == 2
+    for a, b in zip(inst, oinst):
+        assert a.tobytes() == b.tobytes()
+    assert max(np.abs(A - B).max() for A, B in zip(T, oT)) < 1e-4
+    assert np.array_equal(T[1], np.eye(4, dtype=np.float32)) and len(inst[1]) == 5
+    assert np.abs(T[0][:3, :3] - R).max() < 0.05
+
+
 # ------------------------------------------------------------------------------------------ pipeline
 def test_register_scene_pipeline(ctx, orc, synth, b200):
     model = synth.make_model("y", 5000)
