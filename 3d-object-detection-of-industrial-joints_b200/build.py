@@ -69,5 +69,34 @@ def build(force=False, verbose=False):
     return OUT
 
 
+ROOT = os.path.dirname(HERE)
+APPS = os.path.join(ROOT, "apps")
+APP_BIN = os.path.join(APPS, "bin")
+
+
+def build_apps(force=False):
+    """C++ host side above the C ABI: the harness programs in apps/ (PCL-style adapters from
+    include/pcl_b200/), linked against libb200reg.so with an rpath relative to the binary."""
+    so = build()
+    os.makedirs(APP_BIN, exist_ok=True)
+    hdr = os.path.join(ROOT, "include", "pcl_b200", "pcl_b200.h")
+    outs = []
+    for f in sorted(os.listdir(APPS)):
+        if not f.endswith(".cpp"):
+            continue
+        src, out = os.path.join(APPS, f), os.path.join(APP_BIN, f[:-4])
+        deps = [src, hdr, os.path.join(ROOT, "include", "b200reg.h"), so]
+        if force or not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+            cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-o", out,
+                   "-L" + HERE, "-lb200reg", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("g++ failed on %s" % src)
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_apps(force="--force" in sys.argv))

@@ -23,9 +23,11 @@ def gather_correspondences(corr_words, count, group=None):
     world = dist.get_world_size(group)
     counts = torch.empty(world, dtype=count.dtype, device=count.device)
     dist.all_gather_into_tensor(counts, count.reshape(1), group=group)
-    out = torch.empty((world,) + tuple(corr_words.shape), dtype=corr_words.dtype, device=corr_words.device)
+    cap = corr_words.shape[0]
+    # concatenated layout (world * cap, 3): the form both the NCCL and the gloo backend accept
+    out = torch.empty((world * cap,) + tuple(corr_words.shape[1:]), dtype=corr_words.dtype, device=corr_words.device)
     dist.all_gather_into_tensor(out, corr_words.contiguous(), group=group)
-    return counts, out
+    return counts, out.view((world, cap) + tuple(corr_words.shape[1:]))
 
 
 def unpack_gathered(counts, words):

@@ -1,0 +1,151 @@
+// shot_recognition.cpp — the recognition callback of the reference, driven through the PCL-style
+// adapters (include/pcl_b200/pcl_b200.h) instead of libpcl.
+//
+// Same call sequence and parameters as the reference's cloud_cb in SHOT.cpp:298-482 with the
+// GeometricConsistency branch (SHOT.cpp:471-483): normals (k) on model and scene → SHOT352 at the
+// keypoints (search surface = full cloud) → KdTreeFLANN<SHOT352> nearest-neighbour loop with a
+// squared-distance threshold → GeometricConsistencyGrouping::recognize.  ROS, the viewer and ICP are
+// outside the hot path and are not part of this harness; clouds come from raw float32 files
+// (n x 3, written by the tests) instead of PCD files, keypoints are given (the reference's
+// UniformSampling runs on the CPU before the hot path).
+//
+// usage: shot_recognition <model.f32> <model_kp.f32> <scene.f32> <scene_kp.f32> <out_prefix>
+//                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch]
+// writes <out_prefix>.corr (b200_corr records), <out_prefix>.T (instances x 16 float),
+//        <out_prefix>.inst (int32 count per instance followed by the records)
+#include <pcl_b200/pcl_b200.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+namespace pcl = pcl_b200;
+
+typedef pcl::PointXYZRGBA PointType;
+typedef pcl::Normal NormalType;
+typedef pcl::SHOT352 DescriptorType;
+
+static bool load_cloud(const char *path, pcl::PointCloud<PointType> &cloud) {
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    std::cerr << "cannot open " << path << std::endl;
+    return false;
+  }
+  float xyz[3];
+  while (fread(xyz, sizeof(float), 3, f) == 3) {
+    PointType p;
+    p.x = xyz[0], p.y = xyz[1], p.z = xyz[2];
+    cloud.push_back(p);
+  }
+  fclose(f);
+  return true;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 6) {
+    std::cerr << "usage: " << argv[0] << " model.f32 model_kp.f32 scene.f32 scene_kp.f32 out_prefix [normal_k descr_rad "
+              << "match_thr cg_size cg_thresh loop|batch]" << std::endl;
+    return 2;
+  }
+  const int normal_k = argc > 6 ? atoi(argv[6]) : 10;
+  const float descr_rad_ = argc > 7 ? (float)atof(argv[7]) : 0.02f;
+  const float match_thr = argc > 8 ? (float)atof(argv[8]) : 0.25f;
+  const float cg_size_ = argc > 9 ? (float)atof(argv[9]) : 0.02f;
+  const float cg_thresh_ = argc > 10 ? (float)atof(argv[10]) : 2.0f;
+  const bool batch = argc > 11 && std::string(argv[11]) == "batch";
+
+  pcl::PointCloud<PointType>::Ptr model(new pcl::PointCloud<PointType>()), scene(new pcl::PointCloud<PointType>());
+  pcl::PointCloud<PointType>::Ptr model_keypoints(new pcl::PointCloud<PointType>()),
+      scene_keypoints(new pcl::PointCloud<PointType>());
+  pcl::PointCloud<NormalType>::Ptr model_normals(new pcl::PointCloud<NormalType>()),
+      scene_normals(new pcl::PointCloud<NormalType>());
+  pcl::PointCloud<DescriptorType>::Ptr model_descriptors(new pcl::PointCloud<DescriptorType>()),
+      scene_descriptors(new pcl::PointCloud<DescriptorType>());
+  if (!load_cloud(argv[1], *model) || !load_cloud(argv[2], *model_keypoints) || !load_cloud(argv[3], *scene) ||
+      !load_cloud(argv[4], *scene_keypoints))
+    return 1;
+  std::cout << "Model total points: " << model->size() << "; Selected Keypoints: " << model_keypoints->size() << std::endl;
+  std::cout << "Scene total points: " << scene->size() << "; Selected Keypoints: " << scene_keypoints->size() << std::endl;
+
+  //  Compute Normals (one estimator reused for both clouds, as the reference does)
+  pcl::NormalEstimationOMP<PointType, NormalType> norm_est;
+  norm_est.setKSearch(normal_k);
+  norm_est.setInputCloud(model);
+  norm_est.compute(*model_normals);
+  norm_est.setInputCloud(scene);
+  norm_est.compute(*scene_normals);
+
+  //  Compute Descriptor for keypoints
+  pcl::SHOTEstimationOMP<PointType, NormalType, DescriptorType> descr_est;
+  descr_est.setRadiusSearch(descr_rad_);
+  descr_est.setInputCloud(model_keypoints);
+  descr_est.setInputNormals(model_normals);
+  descr_est.setSearchSurface(model);
+  descr_est.compute(*model_descriptors);
+  descr_est.setInputCloud(scene_keypoints);
+  descr_est.setInputNormals(scene_normals);
+  descr_est.setSearchSurface(scene);
+  descr_est.compute(*scene_descriptors);
+  if (model_descriptors->size() != model_keypoints->size() || scene_descriptors->size() != scene_keypoints->size()) {
+    std::cerr << "descriptor computation failed" << std::endl;
+    return 1;
+  }
+
+  //  Find Model-Scene Correspondences
+  pcl::CorrespondencesPtr model_scene_corrs(new pcl::Correspondences());
+  if (batch) {
+    // one call for the whole scene (b200_match): same list as the loop below
+    pcl::determineCorrespondences(*model_descriptors, *scene_descriptors, 1, match_thr, *model_scene_corrs);
+  } else {
+    pcl::KdTreeFLANN<DescriptorType> match_search;
+    match_search.setInputCloud(model_descriptors);
+    for (size_t i = 0; i < scene_descriptors->size(); ++i) {
+      std::vector<int> neigh_indices(1);
+      std::vector<float> neigh_sqr_dists(1);
+      if (!std::isfinite(scene_descriptors->at(i).descriptor[0])) continue;  // skipping NaNs
+      const int found_neighs = match_search.nearestKSearch(scene_descriptors->at(i), 1, neigh_indices, neigh_sqr_dists);
+      if (found_neighs == 1 && neigh_sqr_dists[0] < match_thr)
+        model_scene_corrs->push_back(pcl::Correspondence(neigh_indices[0], static_cast<int>(i), neigh_sqr_dists[0]));
+    }
+  }
+  std::cout << "Correspondences found: " << model_scene_corrs->size() << std::endl;
+
+  //  Actual Clustering (GeometricConsistency branch)
+  std::vector<pcl::Matrix4f> rototranslations;
+  std::vector<pcl::Correspondences> clustered_corrs;
+  pcl::GeometricConsistencyGrouping<PointType, PointType> gc_clusterer;
+  gc_clusterer.setGCSize(cg_size_);
+  gc_clusterer.setGCThreshold(cg_thresh_);  // float → int, as in the reference
+  gc_clusterer.setInputCloud(model_keypoints);
+  gc_clusterer.setSceneCloud(scene_keypoints);
+  gc_clusterer.setModelSceneCorrespondences(model_scene_corrs);
+  gc_clusterer.recognize(rototranslations, clustered_corrs);
+
+  std::cout << "Model instances found: " << rototranslations.size() << std::endl;
+  for (size_t i = 0; i < rototranslations.size() && i < 3; ++i) {
+    std::cout << "\n    Instance " << i + 1 << ":" << std::endl;
+    std::cout << "        Correspondences belonging to this instance: " << clustered_corrs[i].size() << std::endl;
+    const pcl::Matrix4f &T = rototranslations[i];
+    printf("            | %6.3f %6.3f %6.3f | \n", T(0, 0), T(0, 1), T(0, 2));
+    printf("        R = | %6.3f %6.3f %6.3f | \n", T(1, 0), T(1, 1), T(1, 2));
+    printf("            | %6.3f %6.3f %6.3f | \n", T(2, 0), T(2, 1), T(2, 2));
+    printf("        t = < %0.3f, %0.3f, %0.3f >\n", T(0, 3), T(1, 3), T(2, 3));
+  }
+
+  const std::string prefix = argv[5];
+  FILE *f = fopen((prefix + ".corr").c_str(), "wb");
+  if (!model_scene_corrs->empty()) fwrite(model_scene_corrs->data(), sizeof(pcl::Correspondence), model_scene_corrs->size(), f);
+  fclose(f);
+  f = fopen((prefix + ".T").c_str(), "wb");
+  for (size_t i = 0; i < rototranslations.size(); ++i) fwrite(rototranslations[i].m, sizeof(float), 16, f);
+  fclose(f);
+  f = fopen((prefix + ".inst").c_str(), "wb");
+  for (size_t i = 0; i < clustered_corrs.size(); ++i) {
+    const int32_t n = (int32_t)clustered_corrs[i].size();
+    fwrite(&n, sizeof(n), 1, f);
+    if (n) fwrite(clustered_corrs[i].data(), sizeof(pcl::Correspondence), (size_t)n, f);
+  }
+  fclose(f);
+  return 0;
+}

@@ -1,0 +1,105 @@
+"""The C++ host side above the C ABI: apps/*.cpp drive the pipeline through the PCL-style adapters
+(include/pcl_b200/pcl_b200.h) in the reference's call order (SHOT.cpp:298-482, FPFH_demo.cpp:405-538).
+CPU: they build and fail loudly without a GPU.  GPU: their output equals the oracle chain."""
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG_NAME
+
+CORR = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
+
+
+@pytest.fixture(scope="module")
+def apps():
+    builder = importlib.import_module(PKG_NAME + ".build")
+    return {os.path.basename(p): p for p in builder.build_apps()}
+
+
+def _write(path, a):
+    np.ascontiguousarray(a[:, :3], dtype=np.float32).tofile(path)
+
+
+def test_apps_build_and_need_a_gpu(apps, synth, tmp_path):
+    import torch
+    assert set(apps) >= {"shot_recognition", "fpfh_recognition"}
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = synth.make_model("y", 500)
+    for n in ("m", "mk", "s", "sk"):
+        _write(tmp_path / (n + ".f32"), m)
+    r = subprocess.run([apps["shot_recognition"], str(tmp_path / "m.f32"), str(tmp_path / "mk.f32"),
+                        str(tmp_path / "s.f32"), str(tmp_path / "sk.f32"), str(tmp_path / "out")],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+
+
+def _read_instances(prefix):
+    T = np.fromfile(prefix + ".T", dtype=np.float32).reshape(-1, 4, 4)
+    raw = np.fromfile(prefix + ".inst", dtype=np.int32)
+    inst, p = [], 0
+    while p < len(raw):
+        n = int(raw[p])
+        inst.append(raw[p + 1:p + 1 + 3 * n].view(CORR).copy())
+        p += 1 + 3 * n
+    return T, inst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["loop", "batch"])
+def test_shot_recognition_app_matches_oracle(apps, orc, synth, tmp_path, mode):
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 30000, scene_id=3)
+    kpm, kps = synth.uniform_sampling(model, 0.02), synth.uniform_sampling(scene, 0.03)
+    for name, a in (("m", model), ("mk", kpm), ("s", scene), ("sk", kps)):
+        _write(tmp_path / (name + ".f32"), a)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([apps["shot_recognition"]] + [str(tmp_path / (n + ".f32")) for n in ("m", "mk", "s", "sk")] +
+                       [prefix, "10", "0.02", "0.25", "0.02", "2", mode], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "Model instances found" in r.stdout
+    corr = np.fromfile(prefix + ".corr", dtype=CORR)
+    T, inst = _read_instances(prefix)
+    # oracle chain with the same parameters (descr_rad is a float in the reference: 0.02f)
+    rad = float(np.float32(0.02))
+    dm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, rad)
+    ds, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, rad)
+    oc = orc.match(dm, ds, 1, 0.25)
+    a = set(map(tuple, corr[["index_query", "index_match"]].tolist()))
+    b = set(map(tuple, oc[["index_query", "index_match"]].tolist()))
+    assert len(b) > 20 and len(a ^ b) <= max(2, 0.002 * len(b))
+    # grouping on the app's own correspondences is bit-exact against the oracle
+    oT, oinst = orc.gc_recognize(kpm, kps, corr, float(np.float32(0.02)), 2, max_inst=len(corr))
+    assert len(oT) == len(T) == len(inst)
+    for x, y in zip(inst, oinst):
+        assert x.tobytes() == y.tobytes()
+    if len(T):
+        assert max(np.abs(A - B).max() for A, B in zip(T, oT)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_fpfh_recognition_app_matches_oracle(apps, orc, synth, tmp_path):
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 30000, scene_id=4)
+    kpm, kps = synth.voxel_grid(model, 0.01), synth.voxel_grid(scene, 0.02)
+    _write(tmp_path / "mk.f32", kpm)
+    _write(tmp_path / "sk.f32", kps)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([apps["fpfh_recognition"], str(tmp_path / "mk.f32"), str(tmp_path / "sk.f32"), prefix, "0.05",
+                        "0.02", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    desc = np.fromfile(prefix + ".desc", dtype=np.float32).reshape(-1, 33)
+    ref = orc.fpfh33(kps, orc.normals(kps, radius=0.05), 0.05)
+    assert np.array_equal(np.isnan(desc[:, 0]), np.isnan(ref[:, 0]))
+    ok = ~np.isnan(ref[:, 0])
+    rel = np.linalg.norm(desc[ok].astype(np.float64) - ref[ok], axis=1) / np.linalg.norm(ref[ok], axis=1)
+    assert rel.max() < 1e-4
+    corr = np.fromfile(prefix + ".corr", dtype=CORR)
+    dm = orc.fpfh33(kpm, orc.normals(kpm, radius=0.05), 0.05)
+    oc = orc.match(dm, desc, 2, 0.0)            # k = 2 ratio test on the app's own scene descriptors
+    same = (corr["index_match"] == oc["index_match"]).all() and (corr["index_query"] == oc["index_query"]).mean() > 0.99
+    assert len(corr) == len(oc) and same

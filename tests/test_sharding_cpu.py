@@ -1,0 +1,76 @@
+"""Multi-GPU layer on CPU: world_size-2 gloo run of the one exchange on the path (gather of the
+variable-length correspondence lists) and of the scene → rank partition."""
+import importlib
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG_NAME, ROOT
+
+CORR = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_corrs(rank, cap):
+    rng = np.random.Generator(np.random.PCG64(100 + rank))
+    n = 5 + 7 * rank
+    c = np.zeros(cap, dtype=CORR)
+    c["index_query"][:n] = rng.integers(0, 1000, n)
+    c["index_match"][:n] = np.sort(rng.integers(0, 5000, n))
+    c["distance"][:n] = rng.uniform(0, 0.25, n).astype(np.float32)
+    return c, n
+
+
+def _worker(rank, world, port, root, pkg, out_dir):
+    import sys
+    sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharding = importlib.import_module(pkg + ".sharding")
+    cap = 64
+    c, n = _make_corrs(rank, cap)
+    words = torch.from_numpy(c.view(np.int32).reshape(cap, 3).copy())
+    counts, allw = sharding.gather_correspondences(words, torch.tensor([n], dtype=torch.int32))
+    lists = sharding.unpack_gathered(counts, allw)
+    ok = len(lists) == world
+    for r in range(world):
+        cr, nr = _make_corrs(r, cap)
+        ok = ok and lists[r].tobytes() == cr[:nr].tobytes()
+    # every scene is owned by exactly one rank
+    mine = sharding.scenes_for_rank(11, rank, world)
+    owned = torch.zeros(11, dtype=torch.int32)
+    owned[mine] = 1
+    dist.all_reduce(owned)
+    ok = ok and bool((owned == 1).all()) and mine == list(range(rank, 11, world))
+    np.save(os.path.join(out_dir, "ok%d.npy" % rank), np.array([int(ok)]))
+    dist.destroy_process_group()
+
+
+def test_gather_correspondences_gloo_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), ROOT, PKG_NAME, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert int(np.load(tmp_path / ("ok%d.npy" % r))[0]) == 1
+
+
+def test_bench_reference_arm_only_rank0(tmp_path):
+    """bench.py --impl reference under a 2-rank launch: rank 1 exits without work (no output)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
