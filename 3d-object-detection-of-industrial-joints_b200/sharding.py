@@ -14,9 +14,19 @@ def scenes_for_rank(n_scenes, rank, world):
     return list(range(rank, n_scenes, world))
 
 
+def common_capacity(local_cap, device=None, group=None):
+    """Largest per-rank correspondence capacity: the padded all_gather needs equally sized buffers on every
+    rank (scenes differ in their keypoint count).  Call once at set-up."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(local_cap)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
 def gather_correspondences(corr_words, count, group=None):
     """corr_words: (cap, 3) int32 tensor viewing this rank's b200_corr buffer; count: (1,) int32 tensor
-    with the number of valid rows.  Returns (all_counts (world,), all_corrs (world, cap, 3)) on every
+    with the number of valid rows; cap must be the same on every rank (common_capacity).  Returns (all_counts (world,), all_corrs (world, cap, 3)) on every
     rank.  Rows past a rank's count are padding."""
     import torch
     import torch.distributed as dist

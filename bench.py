@@ -34,6 +34,15 @@ PARAMS = dict(normal_k=20, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_s
 MODEL_SS, SCENE_SS = 0.005, 0.01
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload(scene_id, scene_points, model_points):
     synth = importlib.import_module(PKG).synth
     model = synth.make_model("y", model_points)
@@ -180,7 +189,7 @@ def run_reference(args, rank, world):
         "note": "PCL-semantics restatement (oracle/), not libpcl: PCL is neither vendored in the reference nor "
                 "installed here",
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -214,12 +223,14 @@ def run_b200(args, rank, world, local_rank):
         d_scene = torch.from_numpy(wl["scene"]).to(dev)
         d_kp = torch.from_numpy(wl["scene_kp"]).to(dev)
         mi = PARAMS["max_instances"]
+        # the gather needs equally sized correspondence buffers on every rank (scenes differ in K_s)
+        corr_cap_all = sharding.common_capacity(Ks, device=dev) if world > 1 else Ks
         out = {"transforms": torch.zeros(mi * 16, dtype=torch.float32, device=dev),
                "inst_offsets": torch.zeros(mi + 1, dtype=torch.int32, device=dev),
                "inst_counts": torch.zeros(mi, dtype=torch.int32, device=dev),
                "inst_corrs": torch.zeros((Ks, 3), dtype=torch.int32, device=dev), "corr_cap": Ks,
                "n_inst": torch.zeros(1, dtype=torch.int32, device=dev),
-               "corrs": torch.zeros((Ks, 3), dtype=torch.int32, device=dev),
+               "corrs": torch.zeros((corr_cap_all, 3), dtype=torch.int32, device=dev),
                "n_corrs": torch.zeros(1, dtype=torch.int32, device=dev)}
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -353,7 +364,7 @@ def run_b200(args, rank, world, local_rank):
             "measured": {"N": N, "K_scene": Ks, "K_model": Km, "mean_neighbors": mean_nbrs, "max_neighbors": max_nbrs,
                          "correspondences": n_corrs, "instances": n_inst, "step_ms": [round(x, 3) for x in step_ms]},
         }
-        print(json.dumps(line))
+        _emit(line)
     model.close()
     ctx.close()
     if world > 1:
@@ -372,6 +383,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner)
+    # goes to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -40,7 +40,7 @@ def _worker(rank, world, port, root, pkg, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sharding = importlib.import_module(pkg + ".sharding")
-    cap = 64
+    cap = sharding.common_capacity(40 + 24 * rank)      # ranks hold scenes of different size
     c, n = _make_corrs(rank, cap)
     words = torch.from_numpy(c.view(np.int32).reshape(cap, 3).copy())
     counts, allw = sharding.gather_correspondences(words, torch.tensor([n], dtype=torch.int32))
@@ -48,6 +48,7 @@ def _worker(rank, world, port, root, pkg, out_dir):
     ok = len(lists) == world
     for r in range(world):
         cr, nr = _make_corrs(r, cap)
+        ok = ok and cap == 64
         ok = ok and lists[r].tobytes() == cr[:nr].tobytes()
     # every scene is owned by exactly one rank
     mine = sharding.scenes_for_rank(11, rank, world)
