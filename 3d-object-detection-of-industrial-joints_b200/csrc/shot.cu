@@ -1,4 +1,17 @@
-// shot.cu — SHOT local reference frame + SHOT352 descriptor, fused, one keypoint per CTA.
+// shot.cu — SHOT local reference frame + SHOT352 descriptor, fused.
+//
+// Two kernels share the arithmetic:
+//   shot_warp_kernel  one keypoint per WARP (neighbourhoods up to 1024 points — every keypoint of the
+//                     reference's parameter sets): the warp gathers its neighbour list into shared
+//                     memory, accumulates the float64 covariance with shuffles, one lane solves the
+//                     3x3 eigen-problem while the SM's other warps keep working, and the 352-bin
+//                     histogram is a per-warp shared-memory array.  No sort: the distance order is
+//                     only needed by PCL's tie rule, which selects five rows by rank on demand.
+//                     Per-neighbour interpolation runs in float32 with explicit error bands around
+//                     every discrete decision; a neighbour inside a band is re-evaluated with PCL's
+//                     float64 expressions (shot_neighbor_exact), so the bins chosen are identical.
+//   shot_kernel       one keypoint per CTA, sorted list in shared or global memory: neighbourhoods
+//                     larger than that (SHOT_demo.cpp:498's radius 50 puts the whole model in one).
 //
 // Replaces pcl::SHOTEstimationOMP<PointXYZRGBA, Normal, SHOT352>::compute (SHOT.cpp:360-371,
 // SHOT_demo.cpp:419-424 and 497-502, 6Dpose.cpp:450-461, CAD_desc.cpp:341-352), including the
@@ -31,10 +44,133 @@ __global__ void gather_normals_kernel(const float4 *__restrict__ sorted_pts, int
   if (i < n) out[i] = normals[orig_index(sorted_pts[i])];
 }
 
+// One neighbour of computePointSHOT (createBinDistanceShape + interpolateSingleChannel), evaluated
+// with PCL's float64 expressions.  hist: 352 floats in shared memory; fr: frame rows x, y, z.
+__device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, const float4 p, const float4 c,
+                                                 const float d2, const float *fr, const double radius) {
+  float *s_hist = hist;
+  const float fxx = fr[0], fxy = fr[1], fxz = fr[2];
+  const float fyx = fr[3], fyy = fr[4], fyz = fr[5];
+  const float fzx = fr[6], fzy = fr[7], fzz = fr[8];
+  const double radius3_4 = (radius * 3) / 4, radius1_4 = radius / 4, radius1_2 = radius / 2;
+  const double RAD_45 = 0.78539816339744830961566084581988;
+  const double RAD_90 = 1.5707963267948966192313216916398;
+  const double RAD_135 = 2.3561944901923449288469825374596;
+  const double RAD_PI_7_8 = 2.7488935718910690836548129603691;
+  {
+        // createBinDistanceShape
+        float dotf = nv.x * fzx;
+        dotf += nv.y * fzy;
+        dotf += nv.z * fzz;
+        double cosineDesc = (double)dotf;
+        if (cosineDesc > 1.0) cosineDesc = 1.0;
+        if (cosineDesc < -1.0) cosineDesc = -1.0;
+        double binDistance = ((1.0 + cosineDesc) * 10) / 2;
+        // interpolateSingleChannel
+        const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+        const double distance = sqrt((double)d2);
+        if (fabs(distance) < 1E-15) return;
+        float t;
+        t = dx * fxx;
+        t += dy * fxy;
+        t += dz * fxz;
+        double xInFeatRef = (double)t;
+        t = dx * fyx;
+        t += dy * fyy;
+        t += dz * fyz;
+        double yInFeatRef = (double)t;
+        t = dx * fzx;
+        t += dy * fzy;
+        t += dz * fzz;
+        double zInFeatRef = (double)t;
+        if (fabs(yInFeatRef) < 1E-30) yInFeatRef = 0;
+        if (fabs(xInFeatRef) < 1E-30) xInFeatRef = 0;
+        if (fabs(zInFeatRef) < 1E-30) zInFeatRef = 0;
+
+        const int bit4 = ((yInFeatRef > 0) || ((yInFeatRef == 0.0) && (xInFeatRef < 0))) ? 1 : 0;
+        const int bit3 = (((xInFeatRef > 0) || ((xInFeatRef == 0.0) && (yInFeatRef > 0))) ? !bit4 : bit4) ? 1 : 0;
+        int desc_index = (bit4 << 3) + (bit3 << 2);
+        desc_index = desc_index << 1;
+        if ((xInFeatRef * yInFeatRef > 0) || (xInFeatRef == 0.0))
+          desc_index += (fabs(xInFeatRef) >= fabs(yInFeatRef)) ? 0 : 4;
+        else
+          desc_index += (fabs(xInFeatRef) > fabs(yInFeatRef)) ? 4 : 0;
+        desc_index += zInFeatRef > 0 ? 1 : 0;
+        desc_index += (distance > radius1_2) ? 2 : 0;
+
+        const int step_index = (int)floor(binDistance + 0.5);
+        const int volume_index = desc_index * 11;
+        binDistance -= step_index;
+        double intWeight = (1 - fabs(binDistance));
+        if (binDistance > 0)
+          atomicAdd(&s_hist[volume_index + ((step_index + 1) % 10)], (float)binDistance);
+        else
+          atomicAdd(&s_hist[volume_index + ((step_index - 1 + 10) % 10)], -(float)binDistance);
+
+        if (distance > radius1_2) {
+          const double radiusDistance = (distance - radius3_4) / radius1_2;
+          if (distance > radius3_4)
+            intWeight += 1 - radiusDistance;
+          else {
+            intWeight += 1 + radiusDistance;
+            atomicAdd(&s_hist[(desc_index - 2) * 11 + step_index], -(float)radiusDistance);
+          }
+        } else {
+          const double radiusDistance = (distance - radius1_4) / radius1_2;
+          if (distance < radius1_4)
+            intWeight += 1 + radiusDistance;
+          else {
+            intWeight += 1 - radiusDistance;
+            atomicAdd(&s_hist[(desc_index + 2) * 11 + step_index], (float)radiusDistance);
+          }
+        }
+
+        double inclinationCos = zInFeatRef / distance;
+        if (inclinationCos < -1.0) inclinationCos = -1.0;
+        if (inclinationCos > 1.0) inclinationCos = 1.0;
+        const double inclination = acos(inclinationCos);
+        if (inclination > RAD_90 || (fabs(inclination - RAD_90) < 1e-30 && zInFeatRef <= 0)) {
+          const double inclinationDistance = (inclination - RAD_135) / RAD_90;
+          if (inclination > RAD_135)
+            intWeight += 1 - inclinationDistance;
+          else {
+            intWeight += 1 + inclinationDistance;
+            atomicAdd(&s_hist[(desc_index + 1) * 11 + step_index], -(float)inclinationDistance);
+          }
+        } else {
+          const double inclinationDistance = (inclination - RAD_45) / RAD_90;
+          if (inclination < RAD_45)
+            intWeight += 1 + inclinationDistance;
+          else {
+            intWeight += 1 - inclinationDistance;
+            atomicAdd(&s_hist[(desc_index - 1) * 11 + step_index], (float)inclinationDistance);
+          }
+        }
+
+        if (yInFeatRef != 0.0 || xInFeatRef != 0.0) {
+          const double azimuth = atan2(yInFeatRef, xInFeatRef);
+          const int sel = desc_index >> 2;
+          double azimuthDistance = (azimuth - (-RAD_PI_7_8 + RAD_45 * sel)) / RAD_45;
+          azimuthDistance = fmax(-0.5, fmin(azimuthDistance, 0.5));
+          if (azimuthDistance > 0) {
+            intWeight += 1 - azimuthDistance;
+            const int interp_index = (desc_index + 4) % 32;
+            atomicAdd(&s_hist[interp_index * 11 + step_index], (float)azimuthDistance);
+          } else {
+            const int interp_index = (desc_index - 4 + 32) % 32;
+            intWeight += 1 + azimuthDistance;
+            atomicAdd(&s_hist[interp_index * 11 + step_index], -(float)azimuthDistance);
+          }
+        }
+        atomicAdd(&s_hist[volume_index + step_index], (float)intWeight);
+  }
+}
+
 __global__ void __launch_bounds__(SHOT_THREADS)
     shot_kernel(GridView g, const float4 *__restrict__ nrm, const float4 *__restrict__ kp, int K, float radius_f,
                 double radius, float r2, int cap, unsigned long long *glob_key, int *glob_pos,
-                float *__restrict__ desc, float *__restrict__ rf_out, int lrf_only) {
+                float *__restrict__ desc, float *__restrict__ rf_out, int lrf_only,
+                const int *__restrict__ counts, int min_count) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_count;
   __shared__ int s_votes[3];       // skipped, plusX, plusZ
@@ -58,6 +194,7 @@ __global__ void __launch_bounds__(SHOT_THREADS)
   const float4 *__restrict__ pts = g.pts;
 
   for (int i = blockIdx.x; i < K; i += gridDim.x) {
+    if (counts[i] < min_count) continue;  // handled by shot_warp_kernel
     const float4 c = kp[i];
     int n = gather_radius(g, c.x, c.y, c.z, radius_f, r2, key, pos, cap, &s_count);
     if (n > cap) n = cap;
@@ -187,124 +324,14 @@ __global__ void __launch_bounds__(SHOT_THREADS)
     // computePointSHOT: fewer than 5 neighbours → NaN descriptor.
     const bool desc_ok = ok && n >= 5;
     if (desc_ok) {
-      const float fxx = s_frame[0], fxy = s_frame[1], fxz = s_frame[2];
-      const float fyx = s_frame[3], fyy = s_frame[4], fyz = s_frame[5];
-      const float fzx = s_frame[6], fzy = s_frame[7], fzz = s_frame[8];
-      const double radius3_4 = (radius * 3) / 4, radius1_4 = radius / 4, radius1_2 = radius / 2;
-      const double RAD_45 = 0.78539816339744830961566084581988;
-      const double RAD_90 = 1.5707963267948966192313216916398;
-      const double RAD_135 = 2.3561944901923449288469825374596;
-      const double RAD_PI_7_8 = 2.7488935718910690836548129603691;
+      float fr[9];
+#pragma unroll
+      for (int a = 0; a < 9; ++a) fr[a] = s_frame[a];
       for (int j = tid; j < n; j += SHOT_THREADS) {
         const int pj = pos[j];
         const float4 nv = nrm[pj];
         if (!finite3(nv.x, nv.y, nv.z)) continue;
-        // createBinDistanceShape
-        float dotf = nv.x * fzx;
-        dotf += nv.y * fzy;
-        dotf += nv.z * fzz;
-        double cosineDesc = (double)dotf;
-        if (cosineDesc > 1.0) cosineDesc = 1.0;
-        if (cosineDesc < -1.0) cosineDesc = -1.0;
-        double binDistance = ((1.0 + cosineDesc) * 10) / 2;
-        // interpolateSingleChannel
-        const float4 p = pts[pj];
-        const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
-        const double distance = sqrt((double)key_d2(key[j]));
-        if (fabs(distance) < 1E-15) continue;
-        float t;
-        t = dx * fxx;
-        t += dy * fxy;
-        t += dz * fxz;
-        double xInFeatRef = (double)t;
-        t = dx * fyx;
-        t += dy * fyy;
-        t += dz * fyz;
-        double yInFeatRef = (double)t;
-        t = dx * fzx;
-        t += dy * fzy;
-        t += dz * fzz;
-        double zInFeatRef = (double)t;
-        if (fabs(yInFeatRef) < 1E-30) yInFeatRef = 0;
-        if (fabs(xInFeatRef) < 1E-30) xInFeatRef = 0;
-        if (fabs(zInFeatRef) < 1E-30) zInFeatRef = 0;
-
-        const int bit4 = ((yInFeatRef > 0) || ((yInFeatRef == 0.0) && (xInFeatRef < 0))) ? 1 : 0;
-        const int bit3 = (((xInFeatRef > 0) || ((xInFeatRef == 0.0) && (yInFeatRef > 0))) ? !bit4 : bit4) ? 1 : 0;
-        int desc_index = (bit4 << 3) + (bit3 << 2);
-        desc_index = desc_index << 1;
-        if ((xInFeatRef * yInFeatRef > 0) || (xInFeatRef == 0.0))
-          desc_index += (fabs(xInFeatRef) >= fabs(yInFeatRef)) ? 0 : 4;
-        else
-          desc_index += (fabs(xInFeatRef) > fabs(yInFeatRef)) ? 4 : 0;
-        desc_index += zInFeatRef > 0 ? 1 : 0;
-        desc_index += (distance > radius1_2) ? 2 : 0;
-
-        const int step_index = (int)floor(binDistance + 0.5);
-        const int volume_index = desc_index * 11;
-        binDistance -= step_index;
-        double intWeight = (1 - fabs(binDistance));
-        if (binDistance > 0)
-          atomicAdd(&s_hist[volume_index + ((step_index + 1) % 10)], (float)binDistance);
-        else
-          atomicAdd(&s_hist[volume_index + ((step_index - 1 + 10) % 10)], -(float)binDistance);
-
-        if (distance > radius1_2) {
-          const double radiusDistance = (distance - radius3_4) / radius1_2;
-          if (distance > radius3_4)
-            intWeight += 1 - radiusDistance;
-          else {
-            intWeight += 1 + radiusDistance;
-            atomicAdd(&s_hist[(desc_index - 2) * 11 + step_index], -(float)radiusDistance);
-          }
-        } else {
-          const double radiusDistance = (distance - radius1_4) / radius1_2;
-          if (distance < radius1_4)
-            intWeight += 1 + radiusDistance;
-          else {
-            intWeight += 1 - radiusDistance;
-            atomicAdd(&s_hist[(desc_index + 2) * 11 + step_index], (float)radiusDistance);
-          }
-        }
-
-        double inclinationCos = zInFeatRef / distance;
-        if (inclinationCos < -1.0) inclinationCos = -1.0;
-        if (inclinationCos > 1.0) inclinationCos = 1.0;
-        const double inclination = acos(inclinationCos);
-        if (inclination > RAD_90 || (fabs(inclination - RAD_90) < 1e-30 && zInFeatRef <= 0)) {
-          const double inclinationDistance = (inclination - RAD_135) / RAD_90;
-          if (inclination > RAD_135)
-            intWeight += 1 - inclinationDistance;
-          else {
-            intWeight += 1 + inclinationDistance;
-            atomicAdd(&s_hist[(desc_index + 1) * 11 + step_index], -(float)inclinationDistance);
-          }
-        } else {
-          const double inclinationDistance = (inclination - RAD_45) / RAD_90;
-          if (inclination < RAD_45)
-            intWeight += 1 + inclinationDistance;
-          else {
-            intWeight += 1 - inclinationDistance;
-            atomicAdd(&s_hist[(desc_index - 1) * 11 + step_index], (float)inclinationDistance);
-          }
-        }
-
-        if (yInFeatRef != 0.0 || xInFeatRef != 0.0) {
-          const double azimuth = atan2(yInFeatRef, xInFeatRef);
-          const int sel = desc_index >> 2;
-          double azimuthDistance = (azimuth - (-RAD_PI_7_8 + RAD_45 * sel)) / RAD_45;
-          azimuthDistance = fmax(-0.5, fmin(azimuthDistance, 0.5));
-          if (azimuthDistance > 0) {
-            intWeight += 1 - azimuthDistance;
-            const int interp_index = (desc_index + 4) % 32;
-            atomicAdd(&s_hist[interp_index * 11 + step_index], (float)azimuthDistance);
-          } else {
-            const int interp_index = (desc_index - 4 + 32) % 32;
-            intWeight += 1 + azimuthDistance;
-            atomicAdd(&s_hist[interp_index * 11 + step_index], -(float)azimuthDistance);
-          }
-        }
-        atomicAdd(&s_hist[volume_index + step_index], (float)intWeight);
+        shot_neighbor_exact(s_hist, nv, pts[pj], c, key_d2(key[j]), fr, radius);
       }
       __syncthreads();
       // normalizeHistogram: acc_norm (double) += shot[j] * shot[j] (float product)
@@ -327,6 +354,348 @@ __global__ void __launch_bounds__(SHOT_THREADS)
       if (rf_out && tid < 9) rf_out[(size_t)i * 9 + tid] = nanf32();
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp-per-keypoint kernel
+// ------------------------------------------------------------------------------------------
+constexpr int SW_WARPS = 8;
+constexpr int SW_THREADS = SW_WARPS * 32;
+constexpr int SW_CAP = 1024;  // neighbours per keypoint held in shared memory
+
+struct ShotWarpSmem {
+  int pos[SW_CAP];     // position of the neighbour in the cell-ordered point array
+  float d2[SW_CAP];    // its float32 squared distance (FLANN's L2_Simple value)
+  float hist[SHOT_LEN];
+  int sel[8];          // rows picked by the tie rule
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 2)
+    shot_warp_kernel(GridView g, const float4 *__restrict__ nrm, const float4 *__restrict__ kp,
+                     const int *__restrict__ counts, int K, float radius_f, double radius, float r2,
+                     int *__restrict__ work_counter, float *__restrict__ desc, float *__restrict__ rf_out,
+                     int lrf_only) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ShotWarpSmem &sm = reinterpret_cast<ShotWarpSmem *>(smem_raw)[warp];
+  const float4 *__restrict__ pts = g.pts;
+  const int *__restrict__ cs = g.cell_start;
+
+  const double radius3_4 = (radius * 3) / 4, radius1_4 = radius / 4, radius1_2 = radius / 2;
+  const float r12f = (float)radius1_2, r34f = (float)radius3_4, r14f = (float)radius1_4;
+  const float inv_r12f = 1.0f / r12f;
+  const float m_r = 1e-6f * radius_f;  // band around the radial thresholds: covers sqrtf vs sqrt((double)d2)
+  const float RAD_45f = 0.78539816339744830961566084581988f, RAD_90f = 1.5707963267948966192313216916398f;
+  const float RAD_135f = 2.3561944901923449288469825374596f, RAD_PI_7_8f = 2.7488935718910690836548129603691f;
+  const float INV_RAD_90f = 1.0f / RAD_90f, INV_RAD_45f = 1.0f / RAD_45f;
+  const float COS_45f = 0.70710678118654752440f;
+
+  while (true) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(work_counter, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= K) break;
+    if (counts[i] > SW_CAP) continue;  // left to shot_kernel
+    const float4 c = kp[i];
+
+    // ---- gather: neighbours with d2 < r2, appended in scan order ----
+    int n = 0;
+    {
+      int x0, x1, y0, y1, z0, z1;
+      if (finite3(c.x, c.y, c.z) && g.n > 0 && ball_cell_range(g, c.x, c.y, c.z, radius_f, x0, x1, y0, y1, z0, z1)) {
+        for (int z = z0; z <= z1; ++z)
+          for (int y = y0; y <= y1; ++y) {
+            const int base = g.dx * (y + g.dy * z);
+            const int s0 = cs[base + x0], e = cs[base + x1 + 1];
+            for (int j0 = s0; j0 < e; j0 += 32) {
+              const int j = j0 + lane;
+              bool hit = false;
+              float d2 = 0.f;
+              if (j < e) {
+                const float4 p = pts[j];
+                d2 = sqdist3(c.x, c.y, c.z, p.x, p.y, p.z);
+                hit = d2 < r2;
+              }
+              const unsigned m = __ballot_sync(0xffffffffu, hit);
+              if (hit) {
+                const int slot = n + __popc(m & ((1u << lane) - 1u));
+                if (slot < SW_CAP) {
+                  sm.pos[slot] = j;
+                  sm.d2[slot] = d2;
+                }
+              }
+              n += __popc(m);
+            }
+          }
+      }
+    }
+    if (n > SW_CAP) n = SW_CAP;  // cannot happen: counts[i] is the same count
+    for (int b = lane; b < SHOT_LEN; b += 32) sm.hist[b] = 0.0f;
+    __syncwarp();
+
+    // ---- local reference frame: weighted covariance (shot_lrf.hpp getLocalRF), float64 ----
+    double part[7] = {0, 0, 0, 0, 0, 0, 0};
+    int skipped = 0;
+    for (int j = lane; j < n; j += 32) {
+      const float4 p = pts[sm.pos[j]];
+      if (p.x == c.x && p.y == c.y && p.z == c.z) {
+        ++skipped;
+        continue;
+      }
+      const double vx = (double)(p.x - c.x), vy = (double)(p.y - c.y), vz = (double)(p.z - c.z);
+      const double w = radius - sqrt((double)sm.d2[j]);
+      part[0] += w * (vx * vx);
+      part[1] += w * (vx * vy);
+      part[2] += w * (vx * vz);
+      part[3] += w * (vy * vy);
+      part[4] += w * (vy * vz);
+      part[5] += w * (vz * vz);
+      part[6] += w;
+    }
+#pragma unroll
+    for (int a = 0; a < 7; ++a) part[a] = warp_sum(part[a]);
+    const int n_skip = warp_sum(skipped);
+    const int valid = n - n_skip;
+    int ok = (valid >= 5) ? 1 : 0;
+    double ax[6] = {0, 0, 0, 0, 0, 0};  // x axis (largest eigenvalue), z axis (smallest), before disambiguation
+    if (ok) {
+      if (lane == 0) {
+        const double *sacc = part;
+        double cov[9] = {sacc[0] / sacc[6], sacc[1] / sacc[6], sacc[2] / sacc[6], sacc[1] / sacc[6], sacc[3] / sacc[6],
+                         sacc[4] / sacc[6], sacc[2] / sacc[6], sacc[4] / sacc[6], sacc[5] / sacc[6]};
+        double w[3], V[9];
+        eigh3_f64(cov, w, V);
+        if (!isfinite(w[0]) || !isfinite(w[1]) || !isfinite(w[2])) ok = 0;
+        ax[0] = V[0 * 3 + 2], ax[1] = V[1 * 3 + 2], ax[2] = V[2 * 3 + 2];
+        ax[3] = V[0 * 3 + 0], ax[4] = V[1 * 3 + 0], ax[5] = V[2 * 3 + 0];
+      }
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) ax[a] = __shfl_sync(0xffffffffu, ax[a], 0);
+    }
+    float fr[9];
+    if (ok) {
+      // sign votes: v . axis >= 0 in float64; a float32 estimate settles the clear cases
+      const float a0 = (float)ax[0], a1 = (float)ax[1], a2 = (float)ax[2];
+      const float b0 = (float)ax[3], b1 = (float)ax[4], b2 = (float)ax[5];
+      int px = 0, pz = 0;
+      for (int j = lane; j < n; j += 32) {
+        const float4 p = pts[sm.pos[j]];
+        if (p.x == c.x && p.y == c.y && p.z == c.z) continue;
+        const float fx = p.x - c.x, fy = p.y - c.y, fz = p.z - c.z;
+        const float band = 4e-6f * (fabsf(fx) + fabsf(fy) + fabsf(fz));
+        const float ex = fx * a0 + fy * a1 + fz * a2, ez = fx * b0 + fy * b1 + fz * b2;
+        if (fabsf(ex) > band)
+          px += ex > 0.f;
+        else
+          px += ((double)fx * ax[0] + (double)fy * ax[1] + (double)fz * ax[2] >= 0) ? 1 : 0;
+        if (fabsf(ez) > band)
+          pz += ez > 0.f;
+        else
+          pz += ((double)fx * ax[3] + (double)fy * ax[4] + (double)fz * ax[5] >= 0) ? 1 : 0;
+      }
+      px = warp_sum(px);
+      pz = warp_sum(pz);
+      const int plus_x = 2 * px - valid, plus_z = 2 * pz - valid;
+      if (plus_x == 0 || plus_z == 0) {
+        // tie: PCL looks at the 5 valid rows around the median distance of the (d2, index)-sorted
+        // list (the skipped rows are its d2 == 0 prefix): select them by rank
+        const int r0 = n_skip + valid / 2 - 2;
+        for (int a = lane; a < n; a += 32) {
+          const float da = sm.d2[a];
+          int oa = -1, rank = 0;
+          for (int b = 0; b < n; ++b) {
+            const float db = sm.d2[b];
+            if (db < da) {
+              ++rank;
+            } else if (db == da && b != a) {
+              if (oa < 0) oa = orig_index(pts[sm.pos[a]]);
+              rank += orig_index(pts[sm.pos[b]]) < oa;
+            }
+          }
+          if (rank >= r0 && rank < r0 + 5) sm.sel[rank - r0] = sm.pos[a];
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        for (int which = 0; which < 2; ++which) {
+          int plus = which ? plus_z : plus_x;
+          double *a = ax + 3 * which;
+          if (plus == 0) {
+            for (int t = 0; t < 5; ++t) {
+              const float4 p = pts[sm.sel[t]];
+              const double vx = (double)(p.x - c.x), vy = (double)(p.y - c.y), vz = (double)(p.z - c.z);
+              if (vx * a[0] + vy * a[1] + vz * a[2] > 0) ++plus;
+            }
+            if (plus < 3) a[0] = -a[0], a[1] = -a[1], a[2] = -a[2];
+          } else if (plus < 0) {
+            a[0] = -a[0], a[1] = -a[1], a[2] = -a[2];
+          }
+        }
+        const float x0 = (float)ax[0], x1 = (float)ax[1], x2 = (float)ax[2];
+        const float z0 = (float)ax[3], z1 = (float)ax[4], z2 = (float)ax[5];
+        fr[0] = x0, fr[1] = x1, fr[2] = x2;
+        fr[3] = z1 * x2 - z2 * x1;  // y = z cross x (float)
+        fr[4] = z2 * x0 - z0 * x2;
+        fr[5] = z0 * x1 - z1 * x0;
+        fr[6] = z0, fr[7] = z1, fr[8] = z2;
+      }
+#pragma unroll
+      for (int a = 0; a < 9; ++a) fr[a] = __shfl_sync(0xffffffffu, fr[a], 0);
+    }
+
+    if (lrf_only) {
+      if (lane < 9) {
+        float v = nanf32();
+#pragma unroll
+        for (int a = 0; a < 9; ++a)
+          if (lane == a && ok) v = fr[a];
+        rf_out[(size_t)i * 9 + lane] = v;
+      }
+      continue;
+    }
+
+    // SHOTEstimation::computeFeature: non-finite keypoint, NaN frame or empty search → NaN row;
+    // computePointSHOT: fewer than 5 neighbours → NaN descriptor.
+    const bool desc_ok = ok && n >= 5;
+    if (desc_ok) {
+      const float fxx = fr[0], fxy = fr[1], fxz = fr[2];
+      const float fyx = fr[3], fyy = fr[4], fyz = fr[5];
+      const float fzx = fr[6], fzy = fr[7], fzz = fr[8];
+      float *hist = sm.hist;
+      for (int j = lane; j < n; j += 32) {
+        const int pj = sm.pos[j];
+        const float4 nv = nrm[pj];
+        if (!finite3(nv.x, nv.y, nv.z)) continue;
+        const float4 p = pts[pj];
+        const float d2 = sm.d2[j];
+        // ---- float32 evaluation with error bands; `slow` → PCL's float64 expressions decide ----
+        const float df = sqrtf(d2);
+        bool slow = d2 < 1e-29f || fabsf(df - r12f) < m_r || fabsf(df - r34f) < m_r || fabsf(df - r14f) < m_r;
+        const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+        float xf = dx * fxx;
+        xf += dy * fxy;
+        xf += dz * fxz;
+        float yf = dx * fyx;
+        yf += dy * fyy;
+        yf += dz * fyz;
+        float zf = dx * fzx;
+        zf += dy * fzy;
+        zf += dz * fzz;
+        // PCL zeroes |.| < 1e-30 (in float64): magnitudes this small go to the exact path
+        slow = slow || fabsf(xf) < 1e-29f || fabsf(yf) < 1e-29f || fabsf(zf) < 1e-29f;
+        const float cosv = zf / df;
+        const float acv = fabsf(cosv);
+        slow = slow || fabsf(acv - COS_45f) < 2e-6f;
+        const float az = atan2f(yf, xf);
+        // sector bits: sign and magnitude comparisons of float values are exact in float32
+        const int bit4 = (yf > 0.f) ? 1 : 0;
+        const int bit3 = ((xf > 0.f) ? !bit4 : bit4) ? 1 : 0;
+        int desc_index = ((bit4 << 3) + (bit3 << 2)) << 1;
+        if ((xf > 0.f) == (yf > 0.f))
+          desc_index += (fabsf(xf) >= fabsf(yf)) ? 0 : 4;
+        else
+          desc_index += (fabsf(xf) > fabsf(yf)) ? 4 : 0;
+        const int sel = desc_index >> 2;
+        const float az0 = -RAD_PI_7_8f + RAD_45f * (float)sel;
+        slow = slow || fabsf(az - az0) < 6e-6f;
+        if (slow) {
+          shot_neighbor_exact(hist, nv, p, c, d2, fr, radius);
+          continue;
+        }
+        desc_index += zf > 0.f ? 1 : 0;
+        desc_index += (df > r12f) ? 2 : 0;
+        // createBinDistanceShape: the cosine bin is cheap in float64, exactly as PCL
+        float dotf = nv.x * fzx;
+        dotf += nv.y * fzy;
+        dotf += nv.z * fzz;
+        double cosineDesc = (double)dotf;
+        if (cosineDesc > 1.0) cosineDesc = 1.0;
+        if (cosineDesc < -1.0) cosineDesc = -1.0;
+        double binDistance = ((1.0 + cosineDesc) * 10) / 2;
+        const int step_index = (int)floor(binDistance + 0.5);
+        const int volume_index = desc_index * 11;
+        binDistance -= step_index;
+        const float bd = (float)binDistance;
+        float intWeight = (float)(1 - fabs(binDistance));
+        if (binDistance > 0)
+          atomicAdd(&hist[volume_index + ((step_index + 1) % 10)], bd);
+        else
+          atomicAdd(&hist[volume_index + ((step_index - 1 + 10) % 10)], -bd);
+        // radial
+        if (df > r12f) {
+          const float rd = (df - r34f) * inv_r12f;
+          if (df > r34f)
+            intWeight += 1 - rd;
+          else {
+            intWeight += 1 + rd;
+            atomicAdd(&hist[(desc_index - 2) * 11 + step_index], -rd);
+          }
+        } else {
+          const float rd = (df - r14f) * inv_r12f;
+          if (df < r14f)
+            intWeight += 1 + rd;
+          else {
+            intWeight += 1 - rd;
+            atomicAdd(&hist[(desc_index + 2) * 11 + step_index], rd);
+          }
+        }
+        // elevation: acos(z/d) > 90 degrees <=> z <= 0 (PCL's tie clause covers z == 0)
+        const float inc = acosf(fminf(1.0f, fmaxf(-1.0f, cosv)));
+        if (zf < 0.f) {
+          const float id = (inc - RAD_135f) * INV_RAD_90f;
+          if (cosv < -COS_45f)
+            intWeight += 1 - id;
+          else {
+            intWeight += 1 + id;
+            atomicAdd(&hist[(desc_index + 1) * 11 + step_index], -id);
+          }
+        } else {
+          const float id = (inc - RAD_45f) * INV_RAD_90f;
+          if (cosv > COS_45f)
+            intWeight += 1 + id;
+          else {
+            intWeight += 1 - id;
+            atomicAdd(&hist[(desc_index - 1) * 11 + step_index], id);
+          }
+        }
+        // azimuth (x and y are non-zero here)
+        {
+          float ad = (az - az0) * INV_RAD_45f;
+          ad = fmaxf(-0.5f, fminf(ad, 0.5f));
+          if (ad > 0) {
+            intWeight += 1 - ad;
+            atomicAdd(&hist[((desc_index + 4) % 32) * 11 + step_index], ad);
+          } else {
+            intWeight += 1 + ad;
+            atomicAdd(&hist[((desc_index - 4 + 32) % 32) * 11 + step_index], -ad);
+          }
+        }
+        atomicAdd(&hist[volume_index + step_index], intWeight);
+      }
+      __syncwarp();
+      // normalizeHistogram: acc_norm (double) += shot[j] * shot[j] (float product)
+      double acc = 0.0;
+      for (int b = lane; b < SHOT_LEN; b += 32) {
+        const float h = hist[b];
+        acc += (double)(h * h);
+      }
+      acc = warp_sum(acc);
+      const float fnorm = (float)sqrt(acc);
+      for (int b = lane; b < SHOT_LEN; b += 32) desc[(size_t)i * SHOT_LEN + b] = hist[b] / fnorm;
+      if (rf_out && lane < 9) {
+        float v = 0.f;
+#pragma unroll
+        for (int a = 0; a < 9; ++a)
+          if (lane == a) v = fr[a];
+        rf_out[(size_t)i * 9 + lane] = v;
+      }
+    } else {
+      for (int b = lane; b < SHOT_LEN; b += 32) desc[(size_t)i * SHOT_LEN + b] = nanf32();
+      if (rf_out && lane < 9) rf_out[(size_t)i * 9 + lane] = nanf32();
+    }
+    __syncwarp();
   }
 }
 
@@ -362,6 +731,21 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
     }
   }
   const float r2 = (float)(radius * radius);
+  // neighbourhoods up to SW_CAP points: one keypoint per warp, dynamic work distribution
+  {
+    DevBuf<int> work;
+    B200_TRY(work.alloc(ctx, 1));
+    B200_TRY(work.zero());
+    const size_t smem_w = sizeof(ShotWarpSmem) * SW_WARPS;
+    B200_CUDA(ctx, cudaFuncSetAttribute(shot_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    const int grid_w = std::min(ceil_div(K, SW_WARPS), ctx->sm_count * 2);
+    shot_warp_kernel<<<grid_w, SW_THREADS, smem_w, ctx->stream>>>(*g, nrm_sorted.p, d_kp, counts.p, K, (float)radius,
+                                                                 radius, r2, work.p, d_desc, d_rf, lrf_only ? 1 : 0);
+    B200_LAUNCHED(ctx);
+  }
+  if (max_count <= SW_CAP) return B200_OK;
+  // larger neighbourhoods (e.g. SHOT_demo.cpp:498's radius 50): one keypoint per CTA, sorted list
+  const int min_count = SW_CAP + 1;
   const int cap = next_pow2_host(std::max(max_count, 32));
   const size_t smem = (size_t)cap * 12;
   if (smem <= 96 * 1024) {
@@ -369,7 +753,7 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 4096)));
     const int grid = std::min(K, ctx->sm_count * per_sm);
     shot_kernel<<<grid, SHOT_THREADS, smem, ctx->stream>>>(*g, nrm_sorted.p, d_kp, K, (float)radius, radius, r2, cap,
-                                                          nullptr, nullptr, d_desc, d_rf, lrf_only ? 1 : 0);
+                                                          nullptr, nullptr, d_desc, d_rf, lrf_only ? 1 : 0, counts.p, min_count);
     B200_LAUNCHED(ctx);
   } else {
     const int grid = std::min(K, ctx->sm_count * 2);
@@ -378,7 +762,7 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
     B200_TRY(gk.alloc(ctx, (size_t)grid * cap));
     B200_TRY(gp.alloc(ctx, (size_t)grid * cap));
     shot_kernel<<<grid, SHOT_THREADS, 0, ctx->stream>>>(*g, nrm_sorted.p, d_kp, K, (float)radius, radius, r2, cap,
-                                                       gk.p, gp.p, d_desc, d_rf, lrf_only ? 1 : 0);
+                                                       gk.p, gp.p, d_desc, d_rf, lrf_only ? 1 : 0, counts.p, min_count);
     B200_LAUNCHED(ctx);
   }
   return B200_OK;
