@@ -46,9 +46,23 @@ __global__ void gather_normals_kernel(const float4 *__restrict__ sorted_pts, int
 
 // One neighbour of computePointSHOT (createBinDistanceShape + interpolateSingleChannel), evaluated
 // with PCL's float64 expressions.  hist: 352 floats in shared memory; fr: frame rows x, y, z.
-__device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, const float4 p, const float4 c,
+// Histogram accumulators.  FloatBins: float32 atomics (CTA kernel, several warps share the bins).
+// FixedBins: 2^-20 fixed point in int32 — shared-memory integer adds are native while float adds are
+// compare-and-swap loops; every contribution is >= 0 and <= 4, a bin receives at most SW_CAP of them,
+// and the quantisation (4.8e-7 per contribution) is ~5e-7 of the histogram norm, far inside the
+// 1e-4 parity bound.
+struct FloatBins {
+  float *h;
+  __device__ __forceinline__ void add(int bin, float v) const { atomicAdd(&h[bin], v); }
+};
+struct FixedBins {
+  int *h;
+  __device__ __forceinline__ void add(int bin, float v) const { atomicAdd(&h[bin], __float2int_rn(v * 1048576.0f)); }
+};
+
+template <class Bins>
+__device__ __noinline__ void shot_neighbor_exact(Bins s_hist, const float4 nv, const float4 p, const float4 c,
                                                  const float d2, const float *fr, const double radius) {
-  float *s_hist = hist;
   const float fxx = fr[0], fxy = fr[1], fxz = fr[2];
   const float fyx = fr[3], fyy = fr[4], fyz = fr[5];
   const float fzx = fr[6], fzy = fr[7], fzz = fr[8];
@@ -103,9 +117,9 @@ __device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, c
         binDistance -= step_index;
         double intWeight = (1 - fabs(binDistance));
         if (binDistance > 0)
-          atomicAdd(&s_hist[volume_index + ((step_index + 1) % 10)], (float)binDistance);
+          s_hist.add(volume_index + ((step_index + 1) % 10), (float)binDistance);
         else
-          atomicAdd(&s_hist[volume_index + ((step_index - 1 + 10) % 10)], -(float)binDistance);
+          s_hist.add(volume_index + ((step_index - 1 + 10) % 10), -(float)binDistance);
 
         if (distance > radius1_2) {
           const double radiusDistance = (distance - radius3_4) / radius1_2;
@@ -113,7 +127,7 @@ __device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, c
             intWeight += 1 - radiusDistance;
           else {
             intWeight += 1 + radiusDistance;
-            atomicAdd(&s_hist[(desc_index - 2) * 11 + step_index], -(float)radiusDistance);
+            s_hist.add((desc_index - 2) * 11 + step_index, -(float)radiusDistance);
           }
         } else {
           const double radiusDistance = (distance - radius1_4) / radius1_2;
@@ -121,7 +135,7 @@ __device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, c
             intWeight += 1 + radiusDistance;
           else {
             intWeight += 1 - radiusDistance;
-            atomicAdd(&s_hist[(desc_index + 2) * 11 + step_index], (float)radiusDistance);
+            s_hist.add((desc_index + 2) * 11 + step_index, (float)radiusDistance);
           }
         }
 
@@ -135,7 +149,7 @@ __device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, c
             intWeight += 1 - inclinationDistance;
           else {
             intWeight += 1 + inclinationDistance;
-            atomicAdd(&s_hist[(desc_index + 1) * 11 + step_index], -(float)inclinationDistance);
+            s_hist.add((desc_index + 1) * 11 + step_index, -(float)inclinationDistance);
           }
         } else {
           const double inclinationDistance = (inclination - RAD_45) / RAD_90;
@@ -143,7 +157,7 @@ __device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, c
             intWeight += 1 + inclinationDistance;
           else {
             intWeight += 1 - inclinationDistance;
-            atomicAdd(&s_hist[(desc_index - 1) * 11 + step_index], (float)inclinationDistance);
+            s_hist.add((desc_index - 1) * 11 + step_index, (float)inclinationDistance);
           }
         }
 
@@ -155,14 +169,14 @@ __device__ __noinline__ void shot_neighbor_exact(float *hist, const float4 nv, c
           if (azimuthDistance > 0) {
             intWeight += 1 - azimuthDistance;
             const int interp_index = (desc_index + 4) % 32;
-            atomicAdd(&s_hist[interp_index * 11 + step_index], (float)azimuthDistance);
+            s_hist.add(interp_index * 11 + step_index, (float)azimuthDistance);
           } else {
             const int interp_index = (desc_index - 4 + 32) % 32;
             intWeight += 1 + azimuthDistance;
-            atomicAdd(&s_hist[interp_index * 11 + step_index], -(float)azimuthDistance);
+            s_hist.add(interp_index * 11 + step_index, -(float)azimuthDistance);
           }
         }
-        atomicAdd(&s_hist[volume_index + step_index], (float)intWeight);
+        s_hist.add(volume_index + step_index, (float)intWeight);
   }
 }
 
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(SHOT_THREADS)
         const int pj = pos[j];
         const float4 nv = nrm[pj];
         if (!finite3(nv.x, nv.y, nv.z)) continue;
-        shot_neighbor_exact(s_hist, nv, pts[pj], c, key_d2(key[j]), fr, radius);
+        shot_neighbor_exact(FloatBins{s_hist}, nv, pts[pj], c, key_d2(key[j]), fr, radius);
       }
       __syncthreads();
       // normalizeHistogram: acc_norm (double) += shot[j] * shot[j] (float product)
@@ -367,7 +381,7 @@ constexpr int SW_CAP = 1024;  // neighbours per keypoint held in shared memory
 struct ShotWarpSmem {
   int pos[SW_CAP];     // position of the neighbour in the cell-ordered point array
   float d2[SW_CAP];    // its float32 squared distance (FLANN's L2_Simple value)
-  float hist[SHOT_LEN];
+  int hist[SHOT_LEN];  // 2^-20 fixed point (FixedBins)
   int sel[8];          // rows picked by the tie rule
 };
 
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
       }
     }
     if (n > SW_CAP) n = SW_CAP;  // cannot happen: counts[i] is the same count
-    for (int b = lane; b < SHOT_LEN; b += 32) sm.hist[b] = 0.0f;
+    for (int b = lane; b < SHOT_LEN; b += 32) sm.hist[b] = 0;
     __syncwarp();
 
     // ---- local reference frame: weighted covariance (shot_lrf.hpp getLocalRF), float64 ----
@@ -502,19 +516,50 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
         // tie: PCL looks at the 5 valid rows around the median distance of the (d2, index)-sorted
         // list (the skipped rows are its d2 == 0 prefix): select them by rank
         const int r0 = n_skip + valid / 2 - 2;
-        for (int a = lane; a < n; a += 32) {
-          const float da = sm.d2[a];
-          int oa = -1, rank = 0;
-          for (int b = 0; b < n; ++b) {
-            const float db = sm.d2[b];
-            if (db < da) {
-              ++rank;
-            } else if (db == da && b != a) {
-              if (oa < 0) oa = orig_index(pts[sm.pos[a]]);
-              rank += orig_index(pts[sm.pos[b]]) < oa;
-            }
+        // d2 values (as ordered bit patterns) of ranks r0 and r0 + 4 by bisection on the bits ...
+        unsigned u_lo = 0, u_hi = 0;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const int target = r0 + 4 * which + 1;  // smallest u with #{d2 <= u} >= target
+          unsigned lo = 0, hi = 0x7f800000u;
+          while (lo < hi) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            int cnt = 0;
+            for (int a = lane; a < n; a += 32) cnt += __float_as_uint(sm.d2[a]) <= mid;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt >= target)
+              hi = mid;
+            else
+              lo = mid + 1;
           }
-          if (rank >= r0 && rank < r0 + 5) sm.sel[rank - r0] = sm.pos[a];
+          if (which)
+            u_hi = lo;
+          else
+            u_lo = lo;
+        }
+        // ... then exact (d2, index) ranks only for the few rows in that value range
+        for (int a0 = 0; a0 < n; a0 += 32) {
+          const int a = a0 + lane;
+          const unsigned ua = (a < n) ? __float_as_uint(sm.d2[a]) : 0xffffffffu;
+          unsigned todo = __ballot_sync(0xffffffffu, a < n && ua >= u_lo && ua <= u_hi);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int e = a0 + src;
+            const float de = sm.d2[e];
+            const int pe = sm.pos[e];
+            const int oe = orig_index(pts[pe]);
+            int rank = 0;
+            for (int b = lane; b < n; b += 32) {
+              const float db = sm.d2[b];
+              if (db < de)
+                ++rank;
+              else if (db == de && b != e)
+                rank += orig_index(pts[sm.pos[b]]) < oe;
+            }
+            rank = __reduce_add_sync(0xffffffffu, rank);
+            if (lane == 0 && rank >= r0 && rank < r0 + 5) sm.sel[rank - r0] = pe;
+          }
         }
         __syncwarp();
       }
@@ -563,7 +608,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
       const float fxx = fr[0], fxy = fr[1], fxz = fr[2];
       const float fyx = fr[3], fyy = fr[4], fyz = fr[5];
       const float fzx = fr[6], fzy = fr[7], fzz = fr[8];
-      float *hist = sm.hist;
+      const FixedBins hist{sm.hist};
       for (int j = lane; j < n; j += 32) {
         const int pj = sm.pos[j];
         const float4 nv = nrm[pj];
@@ -620,9 +665,9 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
         const float bd = (float)binDistance;
         float intWeight = (float)(1 - fabs(binDistance));
         if (binDistance > 0)
-          atomicAdd(&hist[volume_index + ((step_index + 1) % 10)], bd);
+          hist.add(volume_index + ((step_index + 1) % 10), bd);
         else
-          atomicAdd(&hist[volume_index + ((step_index - 1 + 10) % 10)], -bd);
+          hist.add(volume_index + ((step_index - 1 + 10) % 10), -bd);
         // radial
         if (df > r12f) {
           const float rd = (df - r34f) * inv_r12f;
@@ -630,7 +675,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
             intWeight += 1 - rd;
           else {
             intWeight += 1 + rd;
-            atomicAdd(&hist[(desc_index - 2) * 11 + step_index], -rd);
+            hist.add((desc_index - 2) * 11 + step_index, -rd);
           }
         } else {
           const float rd = (df - r14f) * inv_r12f;
@@ -638,7 +683,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
             intWeight += 1 + rd;
           else {
             intWeight += 1 - rd;
-            atomicAdd(&hist[(desc_index + 2) * 11 + step_index], rd);
+            hist.add((desc_index + 2) * 11 + step_index, rd);
           }
         }
         // elevation: acos(z/d) > 90 degrees <=> z <= 0 (PCL's tie clause covers z == 0)
@@ -649,7 +694,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
             intWeight += 1 - id;
           else {
             intWeight += 1 + id;
-            atomicAdd(&hist[(desc_index + 1) * 11 + step_index], -id);
+            hist.add((desc_index + 1) * 11 + step_index, -id);
           }
         } else {
           const float id = (inc - RAD_45f) * INV_RAD_90f;
@@ -657,7 +702,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
             intWeight += 1 + id;
           else {
             intWeight += 1 - id;
-            atomicAdd(&hist[(desc_index - 1) * 11 + step_index], id);
+            hist.add((desc_index - 1) * 11 + step_index, id);
           }
         }
         // azimuth (x and y are non-zero here)
@@ -666,24 +711,25 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
           ad = fmaxf(-0.5f, fminf(ad, 0.5f));
           if (ad > 0) {
             intWeight += 1 - ad;
-            atomicAdd(&hist[((desc_index + 4) % 32) * 11 + step_index], ad);
+            hist.add(((desc_index + 4) % 32) * 11 + step_index, ad);
           } else {
             intWeight += 1 + ad;
-            atomicAdd(&hist[((desc_index - 4 + 32) % 32) * 11 + step_index], -ad);
+            hist.add(((desc_index - 4 + 32) % 32) * 11 + step_index, -ad);
           }
         }
-        atomicAdd(&hist[volume_index + step_index], intWeight);
+        hist.add(volume_index + step_index, intWeight);
       }
       __syncwarp();
       // normalizeHistogram: acc_norm (double) += shot[j] * shot[j] (float product)
       double acc = 0.0;
       for (int b = lane; b < SHOT_LEN; b += 32) {
-        const float h = hist[b];
+        const float h = (float)sm.hist[b] * (1.0f / 1048576.0f);
         acc += (double)(h * h);
       }
       acc = warp_sum(acc);
       const float fnorm = (float)sqrt(acc);
-      for (int b = lane; b < SHOT_LEN; b += 32) desc[(size_t)i * SHOT_LEN + b] = hist[b] / fnorm;
+      for (int b = lane; b < SHOT_LEN; b += 32)
+        desc[(size_t)i * SHOT_LEN + b] = ((float)sm.hist[b] * (1.0f / 1048576.0f)) / fnorm;
       if (rf_out && lane < 9) {
         float v = 0.f;
 #pragma unroll
