@@ -44,7 +44,8 @@ constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;
-constexpr uint32_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ +
+                             2 * TC_BN * 4 /*|b|^2 of the two accumulators' model tiles*/;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t *tfull = bars + 2 * TC_STAGES;       // [2]
   uint64_t *tempty = bars + 2 * TC_STAGES + 2;  // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+  float *s_nb = reinterpret_cast<float *>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256);  // [2][TC_BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -325,27 +327,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN);
         const int n0 = nt * TC_BN;
+        // |b_j|^2 of this model tile → shared memory (every epilogue thread needs all 256 values)
+        float *snb = s_nb + acc * TC_BN;
+        {
+          const int t = threadIdx.x - 64;  // 0..127
+          snb[t] = __ldg(&p.nb[n0 + t]);
+          snb[t + 128] = __ldg(&p.nb[n0 + t + 128]);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
           float v[32];
           tmem_ld32(t_addr + (uint32_t)c0, v);
+          // s = |b|^2 - 2 a.b for 32 model rows; a row rarely has anything below its current cut
+          float gmin = __int_as_float(0x7f800000);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int j = n0 + c0 + e;
-            const float s = fmaf(m2inv, v[e], __ldg(&p.nb[j]));
-            if (s < cs[TC_CAND - 1]) {
-              cs[TC_CAND - 1] = s;
-              cj[TC_CAND - 1] = j;
+          for (int e = 0; e < 32; e += 4) {
+            const float4 nb4 = *reinterpret_cast<const float4 *>(snb + c0 + e);
+            v[e] = fmaf(m2inv, v[e], nb4.x);
+            v[e + 1] = fmaf(m2inv, v[e + 1], nb4.y);
+            v[e + 2] = fmaf(m2inv, v[e + 2], nb4.z);
+            v[e + 3] = fmaf(m2inv, v[e + 3], nb4.w);
+            gmin = fminf(gmin, fminf(fminf(v[e], v[e + 1]), fminf(v[e + 2], v[e + 3])));
+          }
+          if (gmin < cs[TC_CAND - 1]) {
 #pragma unroll
-              for (int t = TC_CAND - 1; t > 0; --t)
-                if (cs[t] < cs[t - 1]) {
-                  const float ts = cs[t];
-                  cs[t] = cs[t - 1];
-                  cs[t - 1] = ts;
-                  const int tj = cj[t];
-                  cj[t] = cj[t - 1];
-                  cj[t - 1] = tj;
-                }
+            for (int e = 0; e < 32; ++e) {
+              const float s = v[e];
+              if (s < cs[TC_CAND - 1]) {
+                cs[TC_CAND - 1] = s;
+                cj[TC_CAND - 1] = n0 + c0 + e;
+#pragma unroll
+                for (int t = TC_CAND - 1; t > 0; --t)
+                  if (cs[t] < cs[t - 1]) {
+                    const float ts = cs[t];
+                    cs[t] = cs[t - 1];
+                    cs[t - 1] = ts;
+                    const int tj = cj[t];
+                    cj[t] = cj[t - 1];
+                    cj[t - 1] = tj;
+                  }
+              }
             }
           }
         }
