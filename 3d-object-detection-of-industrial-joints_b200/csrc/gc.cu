@@ -23,6 +23,7 @@
 // inherently serial), the lanes fit and score one sample each, lane 0 then replays the adaptive
 // termination logic in order and discards the samples past the stopping point.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -154,6 +155,7 @@ constexpr int GW = 16;                 // seeds (one per warp) per round
 constexpr int GG_THREADS = GW * 32;
 constexpr int G_MC = 64;               // member indices kept in shared memory per seed
 constexpr int G_HS = 4096;             // commit hash table slots (>= 4 x GW x G_MC)
+constexpr int G_LIST = 64;             // candidates finished in registers
 
 struct GroupArgs {
   const unsigned *adj;
@@ -539,6 +541,441 @@ __global__ void __launch_bounds__(GG_THREADS, 1)
     d[0] = n_rounds, d[1] = t_win, d[2] = t_eval, d[3] = t_commit, d[4] = t_wait;
   }
 #endif
+}
+
+// ---- greedy grouping on a thread-block cluster ----------------------------------------------------
+// Same algorithm as gc_group_kernel, spread over the SMs of one cluster: CTA r of the cluster
+// evaluates window seed r with all of its 128 threads (thread t handles the 16-byte pieces t,
+// t + 128, ... of a bitmap row), so a round's evaluations no longer share one SM's issue slots.
+// Every CTA keeps its own copy of the `taken` bitmap and of the running totals; after the
+// evaluation each CTA writes its result (size + members) into every CTA's shared memory through
+// DSMEM, one cluster barrier later all CTAs walk the window identically, so the copies never
+// diverge and one barrier per round suffices (results are double-buffered by round parity).
+constexpr int GCL = 8;            // cluster size = seeds per round
+constexpr int GCL_THREADS = 128;
+constexpr int GCT_BITS = 11;
+constexpr int GCT = 1 << GCT_BITS;  // commit table slots (>= 4 x GCL x G_MC)
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned dsmem_addr(const void *p, unsigned rank) {
+  unsigned local = (unsigned)__cvta_generic_to_shared(p), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void dsmem_store(unsigned addr, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
+    gc_group_cluster_kernel(GroupArgs ga, const int *__restrict__ d_C, int C_cap, double gc_size, float g_lo, float g_hi,
+                            int gc_threshold, int max_inst) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_res[2][GCL][1 + G_MC];  // published results by round parity: [0] size, then members
+  __shared__ int s_seed[GCL];
+  __shared__ int s_nwin;
+  __shared__ int s_list[64];
+  __shared__ int s_redf[4], s_redc[4];
+  __shared__ int s_mine[G_MC];
+  __shared__ int s_state[4];  // cur, n_inst, total after a sequential commit walk
+  __shared__ int s_tkey[GCT], s_tmask[GCT];  // commit table: member → mask of successful seeds holding it
+  __shared__ int s_flags[2];
+  __shared__ float4 s_newm, s_news;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_cta_rank();
+  const int C = min(*d_C, C_cap);
+  const int row_words = gc_row_words(C);
+  const int n4 = row_words >> 2;
+  const int wpt = row_words / GCL_THREADS;
+  uint4 *s_taken4 = reinterpret_cast<uint4 *>(s_raw);
+  unsigned *s_taken = reinterpret_cast<unsigned *>(s_raw);
+  uint4 *my_cb4 = s_taken4 + n4;
+  const unsigned *my_cb = reinterpret_cast<const unsigned *>(my_cb4);
+  int *my_over = ga.overflow + (size_t)rank * C_cap;
+
+  for (int w = tid; w < row_words; w += GCL_THREADS) {
+    const int j0 = w * 32;
+    s_taken[w] = (j0 + 32 <= C) ? 0u : ((j0 >= C) ? ~0u : ~((1u << (C - j0)) - 1u));  // padding counts as taken
+  }
+  for (int h = tid; h < GCT; h += GCL_THREADS) {
+    s_tkey[h] = -1;
+    s_tmask[h] = 0;
+  }
+  if (rank == 0 && tid == 0) ga.inst_offsets[0] = 0;
+  int cur = 0, n_inst = 0, total = 0;  // identical in every thread of every CTA
+  __syncthreads();
+  cluster_sync_all();  // every CTA's shared memory exists before the first remote store
+
+#ifdef B200_GC_TIMING
+  long long tc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define CT(v) const long long v = clock64()
+#define CA(i, e) tc_[i] += (e)
+#else
+#define CT(v)
+#define CA(i, e)
+#endif
+  for (int round = 0;; ++round) {
+    const int par = round & 1;
+    CT(q0);
+    // ---- window: the next GCL untaken positions at or after cur (warp 0 of every CTA, same result) ----
+    if (warp == 0) {
+      int n = 0;
+      for (int wb = cur >> 5; wb < row_words && n < GCL; wb += 32) {
+        const int wi = wb + lane;
+        unsigned bits = (wi < row_words) ? ~s_taken[wi] : 0u;
+        if (wi == (cur >> 5)) bits &= ~((1u << (cur & 31)) - 1u);
+        const int cnt = __popc(bits);
+        const int incl = warp_incl_scan(cnt, lane);
+        int o = n + incl - cnt;
+        while (bits && o < GCL) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          s_seed[o++] = wi * 32 + b;
+        }
+        n += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) s_nwin = min(n, GCL);
+    }
+    __syncthreads();
+    const int nwin = s_nwin;
+    if (nwin == 0) break;
+    CT(q1);
+    CA(0, q1 - q0);
+
+    // ---- evaluate seed `rank` ----
+    int size = 0;
+    if (rank < nwin) {
+      const int seed = s_seed[rank];
+      size = 1;
+      if (tid == 0) s_mine[0] = seed;
+      int first = 0x7fffffff, cnt = 0;
+      {
+        const uint4 *row4 = reinterpret_cast<const uint4 *>(ga.adj + (size_t)seed * row_words);
+        for (int u0 = tid; u0 < n4; u0 += 4 * GCL_THREADS) {  // loads of a block are issued before the first use
+          uint4 x[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (u0 + i * GCL_THREADS < n4) x[i] = __ldg(row4 + u0 + i * GCL_THREADS);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int u = u0 + i * GCL_THREADS;
+            if (u < n4) {
+              const uint4 t = s_taken4[u];
+              const uint4 w = make_uint4(x[i].x & ~t.x, x[i].y & ~t.y, x[i].z & ~t.z, x[i].w & ~t.w);
+              my_cb4[u] = w;
+              if (w.x | w.y | w.z | w.w) {
+                cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+                if (first == 0x7fffffff) first = first_bit128(w, u * 128);
+              }
+            }
+          }
+        }
+      }
+      first = __reduce_min_sync(0xffffffffu, first);
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) {
+        s_redf[warp] = first;
+        s_redc[warp] = cnt;
+      }
+      __syncthreads();
+      first = min(min(s_redf[0], s_redf[1]), min(s_redf[2], s_redf[3]));
+      int n_cand = s_redc[0] + s_redc[1] + s_redc[2] + s_redc[3];
+      CT(q2);
+      CA(1, q2 - q1);
+      // bitmap admissions while many candidates remain (each costs one row read)
+      while (n_cand > G_LIST) {
+        __syncthreads();  // everybody has read s_red* of the previous pass
+        const int j = first;
+        if (tid == 0) {
+          if (size < G_MC)
+            s_mine[size] = j;
+          else
+            my_over[size] = j;
+        }
+        ++size;
+        const uint4 *rowj4 = reinterpret_cast<const uint4 *>(ga.adj + (size_t)j * row_words);
+        first = 0x7fffffff;
+        cnt = 0;
+        const int ufirst = j >> 7;  // pieces before j's hold no candidates any more
+        for (int u0 = (ufirst & ~(GCL_THREADS - 1)) + tid; u0 < n4; u0 += 4 * GCL_THREADS) {
+          uint4 y[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (u0 + i * GCL_THREADS < n4) y[i] = __ldg(rowj4 + u0 + i * GCL_THREADS);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int u = u0 + i * GCL_THREADS;
+            if (u < n4) {
+              uint4 w = my_cb4[u];
+              if (w.x | w.y | w.z | w.w) {
+                w.x &= y[i].x, w.y &= y[i].y, w.z &= y[i].z, w.w &= y[i].w;
+                my_cb4[u] = w;
+                cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+                if (first == 0x7fffffff) first = first_bit128(w, u * 128);
+              }
+            }
+          }
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) {
+          s_redf[warp] = first;
+          s_redc[warp] = cnt;
+        }
+        __syncthreads();
+        first = min(min(s_redf[0], s_redf[1]), min(s_redf[2], s_redf[3]));
+        n_cand = s_redc[0] + s_redc[1] + s_redc[2] + s_redc[3];
+      }
+      CT(q3);
+      CA(2, q3 - q2);
+      if (n_cand > 0) {
+        // at most 64 candidates left: list them in ascending position (thread t expands words
+        // [t * wpt, (t + 1) * wpt) of the bitmap), fetch their points once and let warp 0 finish the
+        // greedy growth in registers
+        __syncthreads();
+        int c = 0;
+        const int w_lo = tid * wpt, w_min = first >> 5;
+        for (int w = max(w_lo, w_min); w < w_lo + wpt; ++w) c += __popc(my_cb[w]);
+        const int incl = warp_incl_scan(c, lane);
+        if (lane == 31) s_redc[warp] = incl;
+        __syncthreads();
+        if (c) {
+          int o = incl - c;
+          for (int k = 0; k < warp; ++k) o += s_redc[k];
+          for (int w = max(w_lo, w_min); w < w_lo + wpt; ++w) {
+            unsigned bits = my_cb[w];
+            while (bits) {
+              s_list[o++] = w * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+            }
+          }
+        }
+        __syncthreads();
+        CT(q4);
+        CA(3, q4 - q3);
+        if (warp == 0) {
+          int j[2];
+          float4 mj[2], sj[2];
+          unsigned alive = 0;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int idx = u * 32 + lane;
+            if (idx < n_cand) {
+              j[u] = s_list[idx];
+              mj[u] = ga.mp[j[u]];
+              sj[u] = ga.sp[j[u]];
+              alive |= 1u << u;
+            }
+          }
+          while (true) {
+            unsigned bal = __ballot_sync(0xffffffffu, alive & 1u);
+            int usel = 0;
+            if (!bal) {
+              bal = __ballot_sync(0xffffffffu, alive & 2u);
+              usel = 1;
+              if (!bal) break;
+            }
+            const int owner = __ffs(bal) - 1;
+            // the admitted candidate's index and points go to every lane by shuffle
+            const float4 am = usel ? mj[1] : mj[0], as = usel ? sj[1] : sj[0];
+            const int jj = __shfl_sync(0xffffffffu, usel ? j[1] : j[0], owner);
+            float4 mk, sk;
+            mk.x = __shfl_sync(0xffffffffu, am.x, owner);
+            mk.y = __shfl_sync(0xffffffffu, am.y, owner);
+            mk.z = __shfl_sync(0xffffffffu, am.z, owner);
+            sk.x = __shfl_sync(0xffffffffu, as.x, owner);
+            sk.y = __shfl_sync(0xffffffffu, as.y, owner);
+            sk.z = __shfl_sync(0xffffffffu, as.z, owner);
+            mk.w = sk.w = 0.f;
+            if (lane == owner) alive &= ~(1u << usel);
+            if (lane == 0) {
+              if (size < G_MC)
+                s_mine[size] = jj;
+              else
+                my_over[size] = jj;
+            }
+            ++size;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (((alive >> u) & 1u) && !gc_fits(mk, sk, mj[u], sj[u], g_lo, g_hi, gc_size)) alive &= ~(1u << u);
+          }
+          if (lane == 0) s_redc[0] = size;
+        }
+        __syncthreads();
+        size = s_redc[0];
+      }
+      CT(q5);
+      CA(4, q5 - q3);
+      // ---- publish (size, members) into every CTA of the cluster ----
+      const int msz = min(size, G_MC);
+      for (int idx = tid; idx < GCL * (1 + msz); idx += GCL_THREADS) {
+        const int t = idx / (1 + msz), k = idx % (1 + msz);
+        dsmem_store(dsmem_addr(&s_res[par][rank][k], (unsigned)t), k == 0 ? size : s_mine[k - 1]);
+      }
+    }
+    CT(q6);
+    cluster_sync_all();
+    CT(q7);
+    CA(5, q7 - q6);
+
+    // ---- commit (every CTA, identically).  A seed is inexact when its set holds an element that an
+    // earlier successful seed of this window also holds; everything before the first inexact seed is
+    // what the sequential algorithm computes.  The (seed, member) pairs are spread over the threads: a
+    // small direct-mapped table keyed by the member collects the mask of successful seeds holding it.
+    // Two different members landing in one slot (or a set beyond the shared-memory list) fall back to
+    // the sequential walk. ----
+    {
+      if (tid == 0) {
+        s_flags[0] = 0;
+        s_flags[1] = 0;  // conflict mask
+      }
+      int succ = 0, big = 0;
+      for (int r = 0; r < nwin; ++r) {
+        const int sz = s_res[par][r][0];
+        if (sz > gc_threshold) succ |= 1 << r;
+        if (sz > G_MC) big = 1;
+      }
+      __syncthreads();
+      // phase 1: successful seeds enter their members (open addressing, linear probing); a thread owns
+      // the pairs idx = tid + i * 128 in every phase and remembers their slots
+      constexpr int PAIRS = GCL * G_MC / GCL_THREADS;
+      int slot[PAIRS], mem[PAIRS];
+#pragma unroll
+      for (int i = 0; i < PAIRS; ++i) {
+        const int idx = tid + i * GCL_THREADS;
+        const int r = idx / G_MC, k = idx % G_MC;
+        slot[i] = -1;
+        mem[i] = -1;
+        if (r < nwin && k < s_res[par][r][0]) {
+          const int m = s_res[par][r][1 + k];
+          mem[i] = m;
+          if ((succ >> r) & 1) {
+            int h = (int)(((unsigned)m * 2654435761u) >> (32 - GCT_BITS));
+            while (true) {
+              const int old = atomicCAS(&s_tkey[h], -1, m);
+              if (old == -1 || old == m) break;
+              h = (h + 1) & (GCT - 1);
+            }
+            atomicOr(&s_tmask[h], 1 << r);
+            slot[i] = h;
+          }
+        }
+      }
+      __syncthreads();
+      // phase 2: every seed (successful or not) looks its members up
+      if (!big) {
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) {
+          const int idx = tid + i * GCL_THREADS;
+          const int r = idx / G_MC;
+          const int m = mem[i];
+          if (m >= 0) {
+            int h = (int)(((unsigned)m * 2654435761u) >> (32 - GCT_BITS));
+            while (true) {
+              const int key = s_tkey[h];
+              if (key == -1) break;
+              if (key == m) {
+                if (s_tmask[h] & ((1 << r) - 1)) atomicOr(&s_flags[1], 1 << r);
+                break;
+              }
+              h = (h + 1) & (GCT - 1);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const bool slow_walk = big != 0;
+      if (!slow_walk) {
+        const int conf = s_flags[1];
+        const int pstar = conf ? (__ffs(conf) - 1) : nwin;
+        const int commit = succ & ((1 << pstar) - 1);
+        // phase 3: committed seeds mark their members taken; the owner writes its instance out
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) {
+          const int r = (tid + i * GCL_THREADS) / G_MC;
+          if (mem[i] >= 0 && ((commit >> r) & 1)) atomicOr(&s_taken[mem[i] >> 5], 1u << (mem[i] & 31));
+        }
+        for (int r = 0; r < nwin; ++r)
+          if ((commit >> r) & 1) {
+            const int sz = s_res[par][r][0];
+            if (r == rank) {
+              for (int k = tid; k < sz; k += GCL_THREADS) ga.members[total + k] = s_res[par][r][1 + k];
+              if (tid == 0 && n_inst < max_inst) ga.inst_offsets[n_inst + 1] = total + sz;
+            }
+            total += sz;
+            ++n_inst;
+          }
+        cur = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
+      }
+      // clear the table slots this thread filled
+#pragma unroll
+      for (int i = 0; i < PAIRS; ++i)
+        if (slot[i] >= 0) {
+          s_tkey[slot[i]] = -1;
+          s_tmask[slot[i]] = 0;
+        }
+      if (slow_walk) {
+        __syncthreads();
+        if (warp == 0) {
+          int pstar = nwin;
+          for (int r = 0; r < nwin; ++r) {
+            const int sz = s_res[par][r][0];
+            bool conflict = false;
+            for (int k0 = 0; k0 < sz; k0 += 32) {
+              const int kk = k0 + lane;
+              int m = -1;
+              if (kk < sz) m = (kk < G_MC) ? s_res[par][r][1 + kk] : __ldcg(ga.overflow + (size_t)r * C_cap + kk);
+              const bool hit = m >= 0 && ((s_taken[m >> 5] >> (m & 31)) & 1u);
+              if (__any_sync(0xffffffffu, hit)) conflict = true;
+            }
+            if (conflict) {
+              pstar = r;
+              break;
+            }
+            if (sz > gc_threshold) {
+              for (int k0 = 0; k0 < sz; k0 += 32) {
+                const int kk = k0 + lane;
+                if (kk < sz) {
+                  const int m = (kk < G_MC) ? s_res[par][r][1 + kk] : __ldcg(ga.overflow + (size_t)r * C_cap + kk);
+                  atomicOr(&s_taken[m >> 5], 1u << (m & 31));
+                  if (r == rank) ga.members[total + kk] = m;  // the owner writes the instance out
+                }
+              }
+              if (r == rank && lane == 0 && n_inst < max_inst) ga.inst_offsets[n_inst + 1] = total + sz;
+              total += sz;
+              ++n_inst;
+            }
+            __syncwarp();
+          }
+          if (lane == 0) {
+            s_state[0] = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
+            s_state[1] = n_inst;
+            s_state[2] = total;
+          }
+        }
+        __syncthreads();
+        cur = s_state[0];
+        n_inst = s_state[1];
+        total = s_state[2];
+      }
+    }
+    __syncthreads();
+
+    CA(6, clock64() - q7);
+    CA(7, 1);
+  }
+#ifdef B200_GC_TIMING
+  if (ga.dbg && tid == 0)
+    for (int i = 0; i < 8; ++i) ga.dbg[rank * 8 + i] = tc_[i];
+#endif
+  if (rank == 0 && tid == 0) *ga.n_inst_out = n_inst;
 }
 
 // ---- RANSAC pose per instance -------------------------------------------------------------------
@@ -997,7 +1434,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
     gc_adjacency_kernel<<<grid, ADJ_THREADS, 0, ctx->stream>>>(mp.p, sp.p, d_C, C_eff, gc_size, g_lo, g_hi, adj.p);
     B200_LAUNCHED(ctx);
   }
-  B200_TRY(overflow.alloc(ctx, (size_t)GW * C_eff));
+  B200_TRY(overflow.alloc(ctx, (size_t)std::max(GW, GCL) * C_eff));
   B200_TRY(members.alloc(ctx, (size_t)C_eff));
   GroupArgs ga;
   ga.adj = adj.p;
@@ -1017,23 +1454,34 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   }
   {
     StageScope st_(ctx, ST_GC_GROUP);
-    // shared memory: the taken bitmap plus one candidate bitmap per concurrently evaluated seed
     const size_t row_bytes = (size_t)row_words_cap * sizeof(unsigned);
-    const size_t budget = 160 * 1024;
-    if (2 * row_bytes > budget) return ctx->fail(B200_ERR_CAPACITY, "gc: too many correspondences for the grouping kernel");
-    const size_t smem = std::min(budget, row_bytes * (size_t)(1 + GW));
-    B200_CUDA(ctx, cudaFuncSetAttribute(gc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gc_group_kernel<<<1, GG_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, (int)smem, gc_size, g_lo, g_hi, gc_threshold,
-                                                          max_inst);
-    B200_LAUNCHED(ctx);
+    const char *sel = getenv("B200_GC_GROUP");
+    const bool use_cluster = !(sel && !strcmp(sel, "cta")) && 2 * row_bytes <= 200 * 1024;
+    if (use_cluster) {
+      // one 8-CTA cluster: a seed per CTA; shared memory = taken bitmap + candidate bitmap
+      const size_t smem = 2 * row_bytes;
+      B200_CUDA(ctx, cudaFuncSetAttribute(gc_group_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_group_cluster_kernel<<<GCL, GCL_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, gc_size, g_lo, g_hi, gc_threshold,
+                                                                      max_inst);
+      B200_LAUNCHED(ctx);
+    } else {
+      // single CTA: the taken bitmap plus one candidate bitmap per concurrently evaluated seed
+      const size_t budget = 160 * 1024;
+      if (2 * row_bytes > budget) return ctx->fail(B200_ERR_CAPACITY, "gc: too many correspondences for the grouping kernel");
+      const size_t smem = std::min(budget, row_bytes * (size_t)(1 + GW));
+      B200_CUDA(ctx, cudaFuncSetAttribute(gc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_group_kernel<<<1, GG_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, (int)smem, gc_size, g_lo, g_hi, gc_threshold,
+                                                            max_inst);
+      B200_LAUNCHED(ctx);
+    }
   }
   if (debug) {
     long long h[GW * 8];
     B200_CUDA(ctx, cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int w = 0; w < GW; ++w)
-      fprintf(stderr, "gc_group warp %2d: rounds %lld cycles window %lld eval %lld wait %lld commit %lld\n", w, h[w * 8], h[w * 8 + 1],
-              h[w * 8 + 2], h[w * 8 + 4], h[w * 8 + 3]);
+    for (int w = 0; w < GCL; ++w)
+      fprintf(stderr, "gc_group cta %d: window %lld init %lld and %lld list %lld list+greedy %lld cluster-sync %lld commit %lld rounds %lld\n",
+              w, h[w * 8], h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6], h[w * 8 + 7]);
   }
 
   if (!ctx->mt_state) {

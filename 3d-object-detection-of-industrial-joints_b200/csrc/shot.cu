@@ -47,17 +47,19 @@ __global__ void gather_normals_kernel(const float4 *__restrict__ sorted_pts, int
 // One neighbour of computePointSHOT (createBinDistanceShape + interpolateSingleChannel), evaluated
 // with PCL's float64 expressions.  hist: 352 floats in shared memory; fr: frame rows x, y, z.
 // Histogram accumulators.  FloatBins: float32 atomics (CTA kernel, several warps share the bins).
-// FixedBins: 2^-20 fixed point in int32 — shared-memory integer adds are native while float adds are
-// compare-and-swap loops; every contribution is >= 0 and <= 4, a bin receives at most SW_CAP of them,
-// and the quantisation (4.8e-7 per contribution) is ~5e-7 of the histogram norm, far inside the
-// 1e-4 parity bound.
+// FixedBins: fixed point in 32 bits — shared-memory integer adds are native while float (and 64-bit)
+// adds are compare-and-swap loops.  Every contribution is >= 0 and <= 4, so with n neighbours a bin sum
+// is at most 4 n: the scale is 2^20 for n <= 1024 and 2^19 up to SW_CAP = 2048 (the unsigned sum cannot
+// wrap).  The quantisation (<= 4.8e-7 per contribution of order 1, same size as float32 rounding of the
+// bin sums) is ~1e-7 of the histogram norm, far inside the 1e-4 parity bound.
 struct FloatBins {
   float *h;
   __device__ __forceinline__ void add(int bin, float v) const { atomicAdd(&h[bin], v); }
 };
 struct FixedBins {
   int *h;
-  __device__ __forceinline__ void add(int bin, float v) const { atomicAdd(&h[bin], __float2int_rn(v * 1048576.0f)); }
+  float scale;
+  __device__ __forceinline__ void add(int bin, float v) const { atomicAdd(&h[bin], __float2int_rn(v * scale)); }
 };
 
 template <class Bins>
@@ -376,12 +378,12 @@ __global__ void __launch_bounds__(SHOT_THREADS)
 // ------------------------------------------------------------------------------------------
 constexpr int SW_WARPS = 8;
 constexpr int SW_THREADS = SW_WARPS * 32;
-constexpr int SW_CAP = 1024;  // neighbours per keypoint held in shared memory
+constexpr int SW_CAP = 2048;  // neighbours per keypoint held in shared memory
 
 struct ShotWarpSmem {
-  int pos[SW_CAP];     // position of the neighbour in the cell-ordered point array
-  float d2[SW_CAP];    // its float32 squared distance (FLANN's L2_Simple value)
-  int hist[SHOT_LEN];  // 2^-20 fixed point (FixedBins)
+  int pos[SW_CAP];     // position of the neighbour in the cell-ordered point array; its float32 squared
+                       // distance (FLANN's L2_Simple value) is recomputed from the point when needed
+  int hist[SHOT_LEN];  // fixed point (FixedBins), read back as unsigned
   int sel[8];          // rows picked by the tie rule
 };
 
@@ -434,10 +436,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
               const unsigned m = __ballot_sync(0xffffffffu, hit);
               if (hit) {
                 const int slot = n + __popc(m & ((1u << lane) - 1u));
-                if (slot < SW_CAP) {
-                  sm.pos[slot] = j;
-                  sm.d2[slot] = d2;
-                }
+                if (slot < SW_CAP) sm.pos[slot] = j;
               }
               n += __popc(m);
             }
@@ -458,7 +457,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
         continue;
       }
       const double vx = (double)(p.x - c.x), vy = (double)(p.y - c.y), vz = (double)(p.z - c.z);
-      const double w = radius - sqrt((double)sm.d2[j]);
+      const double w = radius - sqrt((double)sqdist3(c.x, c.y, c.z, p.x, p.y, p.z));
       part[0] += w * (vx * vx);
       part[1] += w * (vx * vy);
       part[2] += w * (vx * vz);
@@ -516,6 +515,21 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
         // tie: PCL looks at the 5 valid rows around the median distance of the (d2, index)-sorted
         // list (the skipped rows are its d2 == 0 prefix): select them by rank
         const int r0 = n_skip + valid / 2 - 2;
+        // squared distances: staged in the unused half of the list when it fits, else recomputed
+        const bool staged = n <= SW_CAP / 2;
+        float *d2s = reinterpret_cast<float *>(sm.pos + SW_CAP / 2);
+        auto d2_at = [&](int a) -> float {
+          if (staged) return d2s[a];
+          const float4 q = pts[sm.pos[a]];
+          return sqdist3(c.x, c.y, c.z, q.x, q.y, q.z);
+        };
+        if (staged) {
+          for (int a = lane; a < n; a += 32) {
+            const float4 q = pts[sm.pos[a]];
+            d2s[a] = sqdist3(c.x, c.y, c.z, q.x, q.y, q.z);
+          }
+          __syncwarp();
+        }
         // d2 values (as ordered bit patterns) of ranks r0 and r0 + 4 by bisection on the bits ...
         unsigned u_lo = 0, u_hi = 0;
 #pragma unroll 1
@@ -525,7 +539,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
           while (lo < hi) {
             const unsigned mid = lo + ((hi - lo) >> 1);
             int cnt = 0;
-            for (int a = lane; a < n; a += 32) cnt += __float_as_uint(sm.d2[a]) <= mid;
+            for (int a = lane; a < n; a += 32) cnt += __float_as_uint(d2_at(a)) <= mid;
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (cnt >= target)
               hi = mid;
@@ -540,18 +554,18 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
         // ... then exact (d2, index) ranks only for the few rows in that value range
         for (int a0 = 0; a0 < n; a0 += 32) {
           const int a = a0 + lane;
-          const unsigned ua = (a < n) ? __float_as_uint(sm.d2[a]) : 0xffffffffu;
+          const unsigned ua = (a < n) ? __float_as_uint(d2_at(a)) : 0xffffffffu;
           unsigned todo = __ballot_sync(0xffffffffu, a < n && ua >= u_lo && ua <= u_hi);
           while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             const int e = a0 + src;
-            const float de = sm.d2[e];
+            const float de = d2_at(e);
             const int pe = sm.pos[e];
             const int oe = orig_index(pts[pe]);
             int rank = 0;
             for (int b = lane; b < n; b += 32) {
-              const float db = sm.d2[b];
+              const float db = d2_at(b);
               if (db < de)
                 ++rank;
               else if (db == de && b != e)
@@ -608,13 +622,14 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
       const float fxx = fr[0], fxy = fr[1], fxz = fr[2];
       const float fyx = fr[3], fyy = fr[4], fyz = fr[5];
       const float fzx = fr[6], fzy = fr[7], fzz = fr[8];
-      const FixedBins hist{sm.hist};
+      const float fx_scale = (n <= 1024) ? 1048576.0f : 524288.0f, fx_inv = 1.0f / fx_scale;
+      const FixedBins hist{sm.hist, fx_scale};
       for (int j = lane; j < n; j += 32) {
         const int pj = sm.pos[j];
         const float4 nv = nrm[pj];
         if (!finite3(nv.x, nv.y, nv.z)) continue;
         const float4 p = pts[pj];
-        const float d2 = sm.d2[j];
+        const float d2 = sqdist3(c.x, c.y, c.z, p.x, p.y, p.z);
         // ---- float32 evaluation with error bands; `slow` → PCL's float64 expressions decide ----
         const float df = sqrtf(d2);
         bool slow = d2 < 1e-29f || fabsf(df - r12f) < m_r || fabsf(df - r34f) < m_r || fabsf(df - r14f) < m_r;
@@ -723,13 +738,13 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
       // normalizeHistogram: acc_norm (double) += shot[j] * shot[j] (float product)
       double acc = 0.0;
       for (int b = lane; b < SHOT_LEN; b += 32) {
-        const float h = (float)sm.hist[b] * (1.0f / 1048576.0f);
+        const float h = (float)(unsigned)sm.hist[b] * fx_inv;
         acc += (double)(h * h);
       }
       acc = warp_sum(acc);
       const float fnorm = (float)sqrt(acc);
       for (int b = lane; b < SHOT_LEN; b += 32)
-        desc[(size_t)i * SHOT_LEN + b] = ((float)sm.hist[b] * (1.0f / 1048576.0f)) / fnorm;
+        desc[(size_t)i * SHOT_LEN + b] = ((float)(unsigned)sm.hist[b] * fx_inv) / fnorm;
       if (rf_out && lane < 9) {
         float v = 0.f;
 #pragma unroll
