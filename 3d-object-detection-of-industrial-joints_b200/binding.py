@@ -421,9 +421,11 @@ class Context:
         if rc not in (OK, ERR_CAPACITY):
             self._chk(rc)
         m = min(n_inst.value, mi)
-        return {"transforms": T[:m].reshape(m, 4, 4).copy(),
-                "instances": [ic[off[i]:off[i + 1]].copy() for i in range(m)],
-                "n_instances": n_inst.value, "corrs": corrs[:n_corr.value].copy()}
+        # instances are views into one buffer (np.split): no per-instance copy on the caller's clock
+        used = ic[:off[m]] if m else ic[:0]
+        return {"transforms": T[:m].reshape(m, 4, 4),
+                "instances": np.split(used, off[1:m]) if m else [],
+                "n_instances": n_inst.value, "corrs": corrs[:n_corr.value]}
 
     def dev_register_scene_shot(self, model, d_xyz, n, stride, d_kp, Ks, kstride, params, out):
         """All buffers resident (torch CUDA tensors in `out`), asynchronous (b200_dev_register_scene_shot)."""

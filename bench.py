@@ -331,8 +331,13 @@ def run_b200(args, rank, world, local_rank):
         else:
             achieved = units / dur_s / 1e12
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        # DRAM read + write per launch of the stage's main kernel, from the committed `ncu --set full`
+        # capture of this workload (profiles/summary_r01.md); None for stages not captured
+        traffic_ncu = {"gc_group": 25.6e6, "gc_ransac": 1.5e6, "match": 371.5e6 + 155.5e6, "normals": 23.7e6,
+                       "shot": 123.1e6, "gc_adjacency": 37.3e6}
         roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic_ncu.get(dom),
+                    "traffic_source": "ncu --set full, profiles/summary_r01.md (default workload only)",
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                     "algorithmic_units": units, "avg_stage_ms": stage_ms[dom][0]}
         cpu_baseline = None
