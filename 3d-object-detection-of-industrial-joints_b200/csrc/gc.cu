@@ -1050,6 +1050,8 @@ struct RansacBuffers {
 
 constexpr int RS_THREADS = 128;        // one CTA per instance
 constexpr int RS_BATCH = RS_THREADS;   // samples fitted per batch (one per thread)
+constexpr int RS_EXHAUST_AFTER = 165;   // samples (1 + 4 + 32 + 128) before the exhaustive bound is computed
+constexpr int RS_EXHAUST_MAX_N = 18;    // ... for instances of at most this size (<= 4896 ordered samples)
 constexpr int RS_SMALL = 128;          // instances up to this size keep shuffle array / pair matrix in shared memory
 
 // squared residual of correspondence (s → g) under the row-major 4x4 float transform T
@@ -1097,7 +1099,7 @@ __global__ void __launch_bounds__(RS_THREADS)
   __shared__ float s_acc[9];
   __shared__ int s_shuf[RS_SMALL];
   __shared__ unsigned s_pg[RS_SMALL][RS_SMALL / 32];  // pair (p, q) far enough apart for isSampleGood
-  __shared__ int s_ctrl[8];  // 0 nb, 1 draw_failed, 2 need_twist, 3 stop, 4 any_good, 5 have_best
+  __shared__ int s_ctrl[8];  // 0 nb, 1 draw_failed, 2 need_twist, 3 stop, 4 any_good, 5 have_best, 6 cmax, 7 iterations
   __shared__ int s_warp_cnt[RS_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_inst = min(*rb.n_inst, max_inst);
@@ -1112,7 +1114,7 @@ __global__ void __launch_bounds__(RS_THREADS)
   int *flags = rb.flags + off;
 
   for (int i = tid; i < 624; i += RS_THREADS) s_mt[i] = rb.mt_init[i];
-  if (tid < 8) s_ctrl[tid] = 0;
+  if (tid < 8) s_ctrl[tid] = (tid == 6) ? -1 : 0;  // [6]: best count over ALL admissible ordered samples, once known
   // index maps keyed by the model index: the last correspondence with a given index_query wins
   // (std::map in computeOriginalIndexMapping, unordered_map index_to_correspondence)
   for (int t = tid; t < n; t += RS_THREADS) {
@@ -1349,10 +1351,60 @@ __global__ void __launch_bounds__(RS_THREADS)
           stop = true;  // "RANSAC reached the maximum number of trials"
           break;
         }
+        if (s_ctrl[6] >= 0 && n_best >= s_ctrl[6]) {
+          stop = true;  // no later sample can replace the best model (see below): the remaining iterations are idle
+          break;
+        }
       }
       if (s_ctrl[1] || stop) s_ctrl[3] = 1;
+      s_ctrl[7] = iterations;
     }
     __syncthreads();
+    // A small instance that is still iterating after RS_EXHAUST_AFTER samples (typically one whose
+    // models fit few of its members, so the adaptive bound stays near the 10 000-iteration limit):
+    // evaluate every admissible ORDERED sample once, with the same arithmetic, to learn the largest
+    // inlier count any sample can reach.  A later sample replaces the best model only with a strictly
+    // larger count, so once n_best equals that maximum the outcome is final and the (serial) drawing of
+    // the remaining samples is skipped.  Exact: the best model is the one the full loop would keep.
+    if (s_ctrl[6] < 0 && !s_ctrl[3] && small && n <= RS_EXHAUST_MAX_N && s_ctrl[7] >= RS_EXHAUST_AFTER) {
+      __syncthreads();
+      if (tid == 0) s_ctrl[6] = 0;
+      __syncthreads();
+      const int n_ord = n * (n - 1) * (n - 2);
+      for (int e = tid; e < n_ord; e += RS_THREADS) {
+        const int t0 = e / ((n - 1) * (n - 2));
+        const int rem = e % ((n - 1) * (n - 2));
+        int t1 = rem / (n - 2), t2 = rem % (n - 2);
+        t1 += (t1 >= t0) ? 1 : 0;                       // skip t0
+        const int lo = min(t0, t1), hi = max(t0, t1);  // skip both
+        t2 += (t2 >= lo) ? 1 : 0;
+        t2 += (t2 >= hi) ? 1 : 0;
+        const bool good = ((s_pg[t0][t1 >> 5] >> (t1 & 31)) & (s_pg[t0][t2 >> 5] >> (t2 & 31)) &
+                           (s_pg[t1][t2 >> 5] >> (t2 & 31)) & 1u) != 0;
+        if (!good) continue;
+        const int sel[3] = {t0, t1, t2};
+        double src[9], dst[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int t = sel[i];
+          const float4 sv = rb.mp[mem[t]];
+          const float4 gv = rb.sp[mem[last_pos[t]]];
+          src[i * 3 + 0] = sv.x, src[i * 3 + 1] = sv.y, src[i * 3 + 2] = sv.z;
+          dst[i * 3 + 0] = gv.x, dst[i * 3 + 1] = gv.y, dst[i * 3 + 2] = gv.z;
+        }
+        double Td[16];
+        umeyama3(src, dst, 3, Td);
+        float Tf[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Tf[i] = (float)Td[i];
+        int cnt = 0;
+        for (int t = 0; t < n; ++t) cnt += ((double)residual2(Tf, rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
+        atomicMax(&s_ctrl[6], cnt);
+      }
+      __syncthreads();
+      if (tid == 0 && n_best >= s_ctrl[6]) s_ctrl[3] = 1;
+      __syncthreads();
+    }
     batch_cap = (batch_cap == 1) ? 4 : (batch_cap == 4 ? 32 : RS_BATCH);
   }
   // ---- result: inliers of the best model, filtered correspondences ----
