@@ -22,7 +22,7 @@
 //   warp 0   TMA producer: 4-stage ring of {A 128x64, B 256x64} fp16 tiles, SWIZZLE_128B
 //   warp 1   TMEM allocator (512 columns = two 128x256 fp32 accumulators) + single-thread MMA issuer:
 //            tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, smem descriptors, commit → mbarrier
-//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 → s = nb_j - 2*acc → top-8 insert; overlaps the next
+//   warps 2-9 epilogue (two per TMEM lane quarter, half of the columns each): tcgen05.ld 32x32b.x32 → s = nb_j - 2*acc → top-8 insert; overlaps the next
 //            tile's MMAs through the second accumulator
 // Roofline: tensor pipe; 2*Ks*Km*K' flop per call.
 #include <cuda.h>
@@ -41,11 +41,15 @@ constexpr int TC_BK = 64;  // fp16 elements per k-block = 128 bytes = one swizzl
 constexpr int TC_STAGES = 4;
 constexpr int TC_CAND = 8;
 constexpr int TC_MAX_SPLIT = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 16;  // TC_PARTS warps per TMEM lane quarter, each handles 1/TC_PARTS of the tile's columns
+constexpr int TC_PARTS = TC_EPI_WARPS / 4;
+constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;
 constexpr uint32_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ +
-                             2 * TC_BN * 4 /*|b|^2 of the two accumulators' model tiles*/;
+                             2 * TC_BN * 4 /*|b|^2 of the two accumulators' model tiles*/ +
+                             (TC_PARTS - 1) * TC_BM * TC_CAND * 8 /*candidate hand-over between the column parts*/;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -214,6 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t *tempty = bars + 2 * TC_STAGES + 2;  // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
   float *s_nb = reinterpret_cast<float *>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256);  // [2][TC_BN]
+  float *s_hs = s_nb + 2 * TC_BN;  // [TC_PARTS - 1][TC_BM][TC_CAND] candidates of the column parts 1..
+  int *s_hj = reinterpret_cast<int *>(s_hs + (TC_PARTS - 1) * TC_BM * TC_CAND);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 32 * TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -305,8 +311,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..) =====================
+    // warps 2-5 take the first TC_BN / TC_PARTS columns of every accumulator tile, warps 6-9 the next, ...;
+    // a row's candidate lists are merged once per work item
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // column part
+    const int col_lo = half * (TC_BN / TC_PARTS);
     const int row_in_tile = quarter * 32 + lane;
     const float inv = 1.0f / (p.scaleA[0] * p.scaleB[0]);
     const float m2inv = -2.0f * inv;
@@ -330,13 +340,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // |b_j|^2 of this model tile → shared memory (every epilogue thread needs all 256 values)
         float *snb = s_nb + acc * TC_BN;
         {
-          const int t = threadIdx.x - 64;  // 0..127
-          snb[t] = __ldg(&p.nb[n0 + t]);
-          snb[t + 128] = __ldg(&p.nb[n0 + t + 128]);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int t = threadIdx.x - 64;
+          if (t < TC_BN) snb[t] = __ldg(&p.nb[n0 + t]);
+          asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        for (int c0 = col_lo; c0 < col_lo + TC_BN / TC_PARTS; c0 += 32) {
           float v[32];
           tmem_ld32(t_addr + (uint32_t)c0, v);
           // s = |b|^2 - 2 a.b for 32 model rows; a row rarely has anything below its current cut
@@ -378,8 +387,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           acc_phase ^= 1u;
         }
       }
+      // hand the other parts' candidates to part 0 and merge (ascending lists)
+      if (half > 0) {
+#pragma unroll
+        for (int t = 0; t < TC_CAND; ++t) {
+          s_hs[((half - 1) * TC_BM + row_in_tile) * TC_CAND + t] = cs[t];
+          s_hj[((half - 1) * TC_BM + row_in_tile) * TC_CAND + t] = cj[t];
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      if (half == 0) {
+#pragma unroll 1
+        for (int u = 0; u < (TC_PARTS - 1) * TC_CAND; ++u) {
+          const int o = ((u / TC_CAND) * TC_BM + row_in_tile) * TC_CAND + (u % TC_CAND);
+          const float s = s_hs[o];
+          if (s < cs[TC_CAND - 1]) {
+            cs[TC_CAND - 1] = s;
+            cj[TC_CAND - 1] = s_hj[o];
+#pragma unroll
+            for (int t = TC_CAND - 1; t > 0; --t)
+              if (cs[t] < cs[t - 1]) {
+                const float ts = cs[t];
+                cs[t] = cs[t - 1];
+                cs[t - 1] = ts;
+                const int tj = cj[t];
+                cj[t] = cj[t - 1];
+                cj[t - 1] = tj;
+              }
+          }
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory");  // the hand-over buffer is free again
       const int row = mt * TC_BM + row_in_tile;
-      if (row < p.Ks) {
+      if (half == 0 && row < p.Ks) {
         float *os = p.cand_s + ((size_t)row * p.n_split + sp) * TC_CAND;
         int *oj = p.cand_j + ((size_t)row * p.n_split + sp) * TC_CAND;
 #pragma unroll
@@ -399,41 +439,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 // ---------------------------------------------------------------- exact rescoring + certificate
-// One warp per scene row; lane l rescores candidate l with the exact sequential float32 distance.
-__global__ void tc_rescore_kernel(const float *__restrict__ model, int Km, const float *__restrict__ scene, int Ks, int D,
-                                  const unsigned char *__restrict__ svalid, int n_split,
-                                  const float *__restrict__ cand_s, const int *__restrict__ cand_j,
-                                  const float *__restrict__ na, const float *__restrict__ normmaxB,
-                                  const float *__restrict__ scaleA, const float *__restrict__ scaleB, float eta,
-                                  unsigned long long *__restrict__ best, int *__restrict__ zero_cnt,
-                                  int *__restrict__ fb_rows, int *__restrict__ fb_count,
-                                  unsigned *__restrict__ err_ratio_bits) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (i >= Ks) return;
-  if (!svalid[i]) return;  // row is skipped by the caller's flags (pcl_isfinite(descriptor[0]))
-  const int nc = n_split * TC_CAND;
+// A warp handles 32 / nc scene rows at a time (nc = n_split * TC_CAND candidates per row: 8, 16 or 32),
+// one (row, candidate) pair per lane.  The descriptor rows are staged through shared memory in
+// 64-column chunks with coalesced loads (the candidate rows are scattered over the library); each lane
+// then adds its 64 squared differences in column order, so the distance is the exact sequential
+// float32 L2_Simple value.
+constexpr int RS_CHUNK = 64;
+constexpr int RS_WARPS_PER_CTA = 8;
+
+struct RescoreSmem {
+  float a[4][RS_CHUNK];        // scene rows of the warp (at most 4)
+  float b[32][RS_CHUNK + 1];   // candidate rows, padded: lane l reads b[l][d], conflict free
+};
+
+__global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
+    tc_rescore_kernel(const float *__restrict__ model, int Km, const float *__restrict__ scene, int Ks, int D,
+                      const unsigned char *__restrict__ svalid, int n_split, const float *__restrict__ cand_s,
+                      const int *__restrict__ cand_j, const float *__restrict__ na,
+                      const float *__restrict__ normmaxB, const float *__restrict__ scaleA,
+                      const float *__restrict__ scaleB, float eta, unsigned long long *__restrict__ best,
+                      int *__restrict__ zero_cnt, int *__restrict__ fb_rows, int *__restrict__ fb_count,
+                      unsigned *__restrict__ err_ratio_bits) {
+  extern __shared__ __align__(16) unsigned char rs_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RescoreSmem &sm = reinterpret_cast<RescoreSmem *>(rs_raw)[warp];
+  const int nc = n_split * TC_CAND;  // 8, 16 or 32
+  const int rpw = 32 / nc;           // rows per warp
+  const int gw = blockIdx.x * RS_WARPS_PER_CTA + warp;
+  const int r = lane / nc, c = lane % nc;  // this lane's (row, candidate)
+  const int i = gw * rpw + r;
+  const bool row_ok = i < Ks && svalid[i];  // rows skipped by the caller's flags (pcl_isfinite(descriptor[0]))
   int j = -1;
   float s = __int_as_float(0x7f800000);
-  if (lane < nc) {
-    j = cand_j[(size_t)i * nc + lane];
-    s = cand_s[(size_t)i * nc + lane];
+  if (row_ok) {
+    j = cand_j[(size_t)i * nc + c];
+    s = cand_s[(size_t)i * nc + c];
   }
+  const bool pair_ok = row_ok && j >= 0 && j < Km;
   // s_cut: every model row that is not a candidate has approximate s >= the worst kept value of its split
   float s_cut = __int_as_float(0x7f800000);
-  if (lane < nc && (lane % TC_CAND) == TC_CAND - 1) s_cut = s;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s_cut = fminf(s_cut, __shfl_xor_sync(0xffffffffu, s_cut, o));
+  if (row_ok && (c % TC_CAND) == TC_CAND - 1) s_cut = s;
+  for (int o = nc >> 1; o > 0; o >>= 1) s_cut = fminf(s_cut, __shfl_xor_sync(0xffffffffu, s_cut, o));
+
+  float acc = 0.0f;
+  for (int d0 = 0; d0 < D; d0 += RS_CHUNK) {
+    const int w = min(RS_CHUNK, D - d0);
+    // stage: scene rows, then the 32 candidate rows (two coalesced 128-byte loads per row)
+    for (int rr = 0; rr < rpw; ++rr) {
+      const int ii = gw * rpw + rr;
+      for (int dd = lane; dd < w; dd += 32) sm.a[rr][dd] = (ii < Ks) ? scene[(size_t)ii * D + d0 + dd] : 0.0f;
+    }
+    for (int l = 0; l < 32; ++l) {
+      const int jl = __shfl_sync(0xffffffffu, pair_ok ? j : -1, l);
+      if (jl >= 0)
+        for (int dd = lane; dd < w; dd += 32) sm.b[l][dd] = model[(size_t)jl * D + d0 + dd];
+    }
+    __syncwarp();
+    if (pair_ok) {
+#pragma unroll 8
+      for (int dd = 0; dd < w; ++dd) {
+        const float diff = sm.a[r][dd] - sm.b[lane][dd];
+        acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+      }
+    }
+    __syncwarp();
+  }
   unsigned long long key = ~0ull;
   int zeros = 0;
-  if (j >= 0 && j < Km) {
-    const float *a = scene + (size_t)i * D;
-    const float *b = model + (size_t)j * D;
-    float acc = 0.0f;
-    for (int d = 0; d < D; ++d) {
-      const float diff = a[d] - b[d];
-      acc = __fadd_rn(acc, __fmul_rn(diff, diff));
-    }
+  if (pair_ok) {
     key = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j;
     zeros = (acc == 0.0f) ? 1 : 0;
     if (err_ratio_bits) {
@@ -446,13 +519,12 @@ __global__ void tc_rescore_kernel(const float *__restrict__ model, int Km, const
       if (ratio == ratio) atomicMax(err_ratio_bits, __float_as_uint(ratio));
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = nc >> 1; o > 0; o >>= 1) {
     const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
     key = (ok < key) ? ok : key;
     zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
   }
-  if (lane == 0) {
+  if (c == 0 && row_ok) {
     bool certified = false;
     if (key != ~0ull) {
       const float best_d2 = __uint_as_float((unsigned)(key >> 32));
@@ -574,7 +646,10 @@ int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned 
   // error bound of the approximate inner product relative to |a||b|: fp16 operand rounding (2^-11 per
   // operand for one term, ~2^-21 for the three-term split) plus fp32 tensor-core accumulation
   const float eta = (terms == 3) ? 1.0e-4f : 1.2e-3f;
-  tc_rescore_kernel<<<ceil_div((long long)Ks * 32, 256), 256, 0, ctx->stream>>>(
+  const int rows_per_cta = RS_WARPS_PER_CTA * (32 / (n_split * TC_CAND));
+  const size_t rs_smem = sizeof(RescoreSmem) * RS_WARPS_PER_CTA;
+  B200_CUDA(ctx, cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+  tc_rescore_kernel<<<ceil_div(Ks, rows_per_cta), RS_WARPS_PER_CTA * 32, rs_smem, ctx->stream>>>(
       d_model, Km, d_scene, Ks, D, svalid, n_split, cand_s.p, cand_j.p, na.p,
       reinterpret_cast<const float *>(bits.p + 2), scA.p, scB.p, eta, best, zero_cnt, fb_rows, fb_count,
       ctx->profiling ? bits.p + 3 : nullptr);
