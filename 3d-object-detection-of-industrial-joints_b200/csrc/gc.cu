@@ -553,8 +553,6 @@ __global__ void __launch_bounds__(GG_THREADS, 1)
 // diverge and one barrier per round suffices (results are double-buffered by round parity).
 constexpr int GCL = 8;            // cluster size = seeds per round
 constexpr int GCL_THREADS = 128;
-constexpr int GCT_BITS = 11;
-constexpr int GCT = 1 << GCT_BITS;  // commit table slots (>= 4 x GCL x G_MC)
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -585,8 +583,6 @@ __global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
   __shared__ int s_redf[4], s_redc[4];
   __shared__ int s_mine[G_MC];
   __shared__ int s_state[4];  // cur, n_inst, total after a sequential commit walk
-  __shared__ int s_tkey[GCT], s_tmask[GCT];  // commit table: member → mask of successful seeds holding it
-  __shared__ int s_flags[2];
   __shared__ float4 s_newm, s_news;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_cta_rank();
@@ -603,10 +599,6 @@ __global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
   for (int w = tid; w < row_words; w += GCL_THREADS) {
     const int j0 = w * 32;
     s_taken[w] = (j0 + 32 <= C) ? 0u : ((j0 >= C) ? ~0u : ~((1u << (C - j0)) - 1u));  // padding counts as taken
-  }
-  for (int h = tid; h < GCT; h += GCL_THREADS) {
-    s_tkey[h] = -1;
-    s_tmask[h] = 0;
   }
   if (rank == 0 && tid == 0) ga.inst_offsets[0] = 0;
   int cur = 0, n_inst = 0, total = 0;  // identical in every thread of every CTA
@@ -825,149 +817,61 @@ __global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
     CT(q7);
     CA(5, q7 - q6);
 
-    // ---- commit (every CTA, identically).  A seed is inexact when its set holds an element that an
-    // earlier successful seed of this window also holds; everything before the first inexact seed is
-    // what the sequential algorithm computes.  The (seed, member) pairs are spread over the threads: a
-    // small direct-mapped table keyed by the member collects the mask of successful seeds holding it.
-    // Two different members landing in one slot (or a set beyond the shared-memory list) fall back to
-    // the sequential walk. ----
-    {
-      if (tid == 0) {
-        s_flags[0] = 0;
-        s_flags[1] = 0;  // conflict mask
-      }
-      int succ = 0, big = 0;
-      for (int r = 0; r < nwin; ++r) {
-        const int sz = s_res[par][r][0];
-        if (sz > gc_threshold) succ |= 1 << r;
-        if (sz > G_MC) big = 1;
-      }
-      __syncthreads();
-      // phase 1: successful seeds enter their members (open addressing, linear probing); a thread owns
-      // the pairs idx = tid + i * 128 in every phase and remembers their slots
-      constexpr int PAIRS = GCL * G_MC / GCL_THREADS;
-      int slot[PAIRS], mem[PAIRS];
+    // ---- commit (warp 0 of every CTA, identically): walk the window in order with the members held in
+    // registers (lane l holds members l and l + 32 of every seed); a seed whose set touches an element
+    // taken earlier in the walk is the first inexact one, everything before it commits.  Sets beyond the
+    // shared-memory list are read from the owners' overflow arrays. ----
+    if (warp == 0) {
+      int szs = (lane < nwin) ? s_res[par][lane][0] : 0;
+      int m0[GCL], m1[GCL];
 #pragma unroll
-      for (int i = 0; i < PAIRS; ++i) {
-        const int idx = tid + i * GCL_THREADS;
-        const int r = idx / G_MC, k = idx % G_MC;
-        slot[i] = -1;
-        mem[i] = -1;
-        if (r < nwin && k < s_res[par][r][0]) {
-          const int m = s_res[par][r][1 + k];
-          mem[i] = m;
-          if ((succ >> r) & 1) {
-            int h = (int)(((unsigned)m * 2654435761u) >> (32 - GCT_BITS));
-            while (true) {
-              const int old = atomicCAS(&s_tkey[h], -1, m);
-              if (old == -1 || old == m) break;
-              h = (h + 1) & (GCT - 1);
-            }
-            atomicOr(&s_tmask[h], 1 << r);
-            slot[i] = h;
+      for (int r = 0; r < GCL; ++r) {
+        const int sz = __shfl_sync(0xffffffffu, szs, r);
+        m0[r] = (r < nwin && lane < sz) ? s_res[par][r][1 + lane] : -1;
+        m1[r] = (r < nwin && lane + 32 < sz && lane + 32 < G_MC) ? s_res[par][r][1 + lane + 32] : -1;
+      }
+      int pstar = nwin;
+#pragma unroll
+      for (int r = 0; r < GCL; ++r) {
+        if (r < nwin && pstar == nwin) {
+          const int sz = __shfl_sync(0xffffffffu, szs, r);
+          bool hit = (m0[r] >= 0 && ((s_taken[m0[r] >> 5] >> (m0[r] & 31)) & 1u)) ||
+                     (m1[r] >= 0 && ((s_taken[m1[r] >> 5] >> (m1[r] & 31)) & 1u));
+          for (int kk = G_MC + lane; kk < sz; kk += 32) {  // oversize set: the rest from global memory
+            const int m = __ldcg(ga.overflow + (size_t)r * C_cap + kk);
+            hit = hit || ((s_taken[m >> 5] >> (m & 31)) & 1u);
           }
-        }
-      }
-      __syncthreads();
-      // phase 2: every seed (successful or not) looks its members up
-      if (!big) {
-#pragma unroll
-        for (int i = 0; i < PAIRS; ++i) {
-          const int idx = tid + i * GCL_THREADS;
-          const int r = idx / G_MC;
-          const int m = mem[i];
-          if (m >= 0) {
-            int h = (int)(((unsigned)m * 2654435761u) >> (32 - GCT_BITS));
-            while (true) {
-              const int key = s_tkey[h];
-              if (key == -1) break;
-              if (key == m) {
-                if (s_tmask[h] & ((1 << r) - 1)) atomicOr(&s_flags[1], 1 << r);
-                break;
-              }
-              h = (h + 1) & (GCT - 1);
+          if (__any_sync(0xffffffffu, hit)) {
+            pstar = r;
+          } else if (sz > gc_threshold) {
+            if (m0[r] >= 0) atomicOr(&s_taken[m0[r] >> 5], 1u << (m0[r] & 31));
+            if (m1[r] >= 0) atomicOr(&s_taken[m1[r] >> 5], 1u << (m1[r] & 31));
+            if (r == rank) {  // the owner writes the instance out
+              if (m0[r] >= 0) ga.members[total + lane] = m0[r];
+              if (m1[r] >= 0) ga.members[total + lane + 32] = m1[r];
+              if (lane == 0 && n_inst < max_inst) ga.inst_offsets[n_inst + 1] = total + sz;
             }
-          }
-        }
-      }
-      __syncthreads();
-      const bool slow_walk = big != 0;
-      if (!slow_walk) {
-        const int conf = s_flags[1];
-        const int pstar = conf ? (__ffs(conf) - 1) : nwin;
-        const int commit = succ & ((1 << pstar) - 1);
-        // phase 3: committed seeds mark their members taken; the owner writes its instance out
-#pragma unroll
-        for (int i = 0; i < PAIRS; ++i) {
-          const int r = (tid + i * GCL_THREADS) / G_MC;
-          if (mem[i] >= 0 && ((commit >> r) & 1)) atomicOr(&s_taken[mem[i] >> 5], 1u << (mem[i] & 31));
-        }
-        for (int r = 0; r < nwin; ++r)
-          if ((commit >> r) & 1) {
-            const int sz = s_res[par][r][0];
-            if (r == rank) {
-              for (int k = tid; k < sz; k += GCL_THREADS) ga.members[total + k] = s_res[par][r][1 + k];
-              if (tid == 0 && n_inst < max_inst) ga.inst_offsets[n_inst + 1] = total + sz;
+            for (int kk = G_MC + lane; kk < sz; kk += 32) {
+              const int m = __ldcg(ga.overflow + (size_t)r * C_cap + kk);
+              atomicOr(&s_taken[m >> 5], 1u << (m & 31));
+              if (r == rank) ga.members[total + kk] = m;
             }
             total += sz;
             ++n_inst;
-          }
-        cur = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
-      }
-      // clear the table slots this thread filled
-#pragma unroll
-      for (int i = 0; i < PAIRS; ++i)
-        if (slot[i] >= 0) {
-          s_tkey[slot[i]] = -1;
-          s_tmask[slot[i]] = 0;
-        }
-      if (slow_walk) {
-        __syncthreads();
-        if (warp == 0) {
-          int pstar = nwin;
-          for (int r = 0; r < nwin; ++r) {
-            const int sz = s_res[par][r][0];
-            bool conflict = false;
-            for (int k0 = 0; k0 < sz; k0 += 32) {
-              const int kk = k0 + lane;
-              int m = -1;
-              if (kk < sz) m = (kk < G_MC) ? s_res[par][r][1 + kk] : __ldcg(ga.overflow + (size_t)r * C_cap + kk);
-              const bool hit = m >= 0 && ((s_taken[m >> 5] >> (m & 31)) & 1u);
-              if (__any_sync(0xffffffffu, hit)) conflict = true;
-            }
-            if (conflict) {
-              pstar = r;
-              break;
-            }
-            if (sz > gc_threshold) {
-              for (int k0 = 0; k0 < sz; k0 += 32) {
-                const int kk = k0 + lane;
-                if (kk < sz) {
-                  const int m = (kk < G_MC) ? s_res[par][r][1 + kk] : __ldcg(ga.overflow + (size_t)r * C_cap + kk);
-                  atomicOr(&s_taken[m >> 5], 1u << (m & 31));
-                  if (r == rank) ga.members[total + kk] = m;  // the owner writes the instance out
-                }
-              }
-              if (r == rank && lane == 0 && n_inst < max_inst) ga.inst_offsets[n_inst + 1] = total + sz;
-              total += sz;
-              ++n_inst;
-            }
             __syncwarp();
           }
-          if (lane == 0) {
-            s_state[0] = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
-            s_state[1] = n_inst;
-            s_state[2] = total;
-          }
         }
-        __syncthreads();
-        cur = s_state[0];
-        n_inst = s_state[1];
-        total = s_state[2];
+      }
+      if (lane == 0) {
+        s_state[0] = (pstar < nwin) ? s_seed[pstar] : s_seed[nwin - 1] + 1;
+        s_state[1] = n_inst;
+        s_state[2] = total;
       }
     }
     __syncthreads();
-
+    cur = s_state[0];
+    n_inst = s_state[1];
+    total = s_state[2];
     CA(6, clock64() - q7);
     CA(7, 1);
   }
