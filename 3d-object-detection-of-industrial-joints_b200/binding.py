@@ -148,6 +148,29 @@ def _dptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+class InstanceList:
+    """Per-instance correspondence lists as views into the flat output buffer (pcl's
+    std::vector<pcl::Correspondences>): nothing is copied or sliced until an item is asked for."""
+
+    def __init__(self, flat, offsets, n):
+        self.flat, self.offsets, self.n = flat, offsets, int(n)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(self.n))]
+        if i < 0:
+            i += self.n
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        return self.flat[self.offsets[i]:self.offsets[i + 1]]
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
+
+
 class Cloud:
     def __init__(self, ctx, handle, n):
         self.ctx, self.h, self.n = ctx, handle, n
@@ -410,10 +433,10 @@ class Context:
         scene_xyz, scene_kp = _pts(scene_xyz), _pts(scene_kp)
         mi = params.max_instances
         Ks = len(scene_kp)
-        T = np.zeros((mi, 16), dtype=np.float32)
-        off = np.zeros(mi + 1, dtype=np.int32)
-        ic = np.zeros(max(Ks, 1), dtype=CORR_DTYPE)
-        corrs = np.zeros(max(Ks, 1), dtype=CORR_DTYPE)
+        T = np.empty((mi, 16), dtype=np.float32)       # filled by the library (no zero-fill on the caller's clock)
+        off = np.empty(mi + 1, dtype=np.int32)
+        ic = np.empty(max(Ks, 1), dtype=CORR_DTYPE)
+        corrs = np.empty(max(Ks, 1), dtype=CORR_DTYPE)
         n_inst, n_corr = C.c_int(), C.c_int()
         rc = lib().b200_register_scene_shot(self.h, model.h, _f(scene_xyz), len(scene_xyz), scene_xyz.shape[1],
                                             _f(scene_kp), Ks, scene_kp.shape[1], C.byref(params), _f(T), _i(off),
@@ -421,10 +444,7 @@ class Context:
         if rc not in (OK, ERR_CAPACITY):
             self._chk(rc)
         m = min(n_inst.value, mi)
-        # instances are views into one buffer (np.split): no per-instance copy on the caller's clock
-        used = ic[:off[m]] if m else ic[:0]
-        return {"transforms": T[:m].reshape(m, 4, 4),
-                "instances": np.split(used, off[1:m]) if m else [],
+        return {"transforms": T[:m].reshape(m, 4, 4), "instances": InstanceList(ic, off, m),
                 "n_instances": n_inst.value, "corrs": corrs[:n_corr.value]}
 
     def dev_register_scene_shot(self, model, d_xyz, n, stride, d_kp, Ks, kstride, params, out):
