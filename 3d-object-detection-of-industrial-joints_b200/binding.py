@@ -28,6 +28,7 @@ EXPORTS = [
     "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
     "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio",
     "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
+    "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
 ]
 
 
@@ -103,6 +104,10 @@ def lib():
             "b200_desc_index_destroy": [vp],
             "b200_desc_index_size": [vp],
             "b200_desc_index_knn": [vp, vp, fp, i, i, ip, fp, ip],
+            "b200_uniform_sampling": [vp, fp, i, i, d, fp, ip, ip],
+            "b200_dev_uniform_sampling": [vp, vp, i, i, d, vp, vp, vp],
+            "b200_voxel_grid": [vp, fp, i, i, f, f, f, fp, ip],
+            "b200_dev_voxel_grid": [vp, vp, i, i, f, f, f, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -392,6 +397,25 @@ class Context:
         h = C.c_void_p()
         self._chk(lib().b200_desc_index_create(self.h, _f(desc), desc.shape[0], desc.shape[1], C.byref(h)))
         return DescIndex(self, h, desc.shape[1])
+
+    # ---- keypoints ------------------------------------------------------------------------------
+    def uniform_sampling(self, xyz, leaf, return_index=False):
+        xyz = _pts(xyz)
+        out = np.empty((max(len(xyz), 1), 3), dtype=np.float32)
+        idx = np.empty(max(len(xyz), 1), dtype=np.int32)
+        n = C.c_int()
+        self._chk(lib().b200_uniform_sampling(self.h, _f(xyz), len(xyz), xyz.shape[1], float(leaf), _f(out), _i(idx),
+                                              C.byref(n)))
+        return (out[:n.value].copy(), idx[:n.value].copy()) if return_index else out[:n.value].copy()
+
+    def voxel_grid(self, xyz, leaf):
+        xyz = _pts(xyz)
+        lx, ly, lz = (leaf, leaf, leaf) if np.isscalar(leaf) else leaf
+        out = np.empty((max(len(xyz), 1), 3), dtype=np.float32)
+        n = C.c_int()
+        self._chk(lib().b200_voxel_grid(self.h, _f(xyz), len(xyz), xyz.shape[1], float(lx), float(ly), float(lz),
+                                        _f(out), C.byref(n)))
+        return out[:n.value].copy()
 
     # ---- matching / grouping ------------------------------------------------------------------
     def match(self, model, scene, mode=1, thr=0.25):

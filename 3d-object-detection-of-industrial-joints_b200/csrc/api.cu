@@ -487,6 +487,65 @@ int b200_match(b200_ctx *ctx, const float *model, int Km, const float *scene, in
   return B200_OK;
 }
 
+/* ------------------------------------------------------------------ keypoints */
+int b200_dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, double leaf, float *d_out_xyz,
+                              int *d_out_index, int *d_count) {
+  API_ENTER(ctx);
+  if (n < 0 || stride < 3 || !d_count || (n > 0 && (!d_xyz || !d_out_xyz)))
+    return ctx->fail(B200_ERR_INVALID, "uniform_sampling: bad arguments");
+  return dev_uniform_sampling(ctx, d_xyz, n, stride, (float)leaf, d_out_xyz, d_out_index, d_count);
+}
+
+int b200_uniform_sampling(b200_ctx *ctx, const float *xyz, int n, int stride, double leaf, float *out_xyz,
+                          int *out_index, int *count) {
+  API_ENTER(ctx);
+  if (n < 0 || stride < 3 || !count || (n > 0 && (!xyz || !out_xyz)))
+    return ctx->fail(B200_ERR_INVALID, "uniform_sampling: bad arguments");
+  *count = 0;
+  if (n == 0) return B200_OK;
+  DevBuf<float> din, dout;
+  DevBuf<int> didx, dcount;
+  B200_TRY(upload(ctx, din, xyz, (size_t)n * stride));
+  B200_TRY(dout.alloc(ctx, (size_t)n * 3));
+  B200_TRY(didx.alloc(ctx, (size_t)n));
+  B200_TRY(dcount.alloc(ctx, 1));
+  B200_TRY(dev_uniform_sampling(ctx, din.p, n, stride, (float)leaf, dout.p, didx.p, dcount.p));
+  B200_TRY(download(ctx, count, dcount.p, 1));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_TRY(download(ctx, out_xyz, dout.p, (size_t)*count * 3));
+  if (out_index) B200_TRY(download(ctx, out_index, didx.p, (size_t)*count));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_dev_voxel_grid(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx, float ly, float lz,
+                        float *d_out_xyz, int *d_count) {
+  API_ENTER(ctx);
+  if (n < 0 || stride < 3 || !d_count || (n > 0 && (!d_xyz || !d_out_xyz)))
+    return ctx->fail(B200_ERR_INVALID, "voxel_grid: bad arguments");
+  return dev_voxel_grid(ctx, d_xyz, n, stride, lx, ly, lz, d_out_xyz, d_count);
+}
+
+int b200_voxel_grid(b200_ctx *ctx, const float *xyz, int n, int stride, float lx, float ly, float lz, float *out_xyz,
+                    int *count) {
+  API_ENTER(ctx);
+  if (n < 0 || stride < 3 || !count || (n > 0 && (!xyz || !out_xyz)))
+    return ctx->fail(B200_ERR_INVALID, "voxel_grid: bad arguments");
+  *count = 0;
+  if (n == 0) return B200_OK;
+  DevBuf<float> din, dout;
+  DevBuf<int> dcount;
+  B200_TRY(upload(ctx, din, xyz, (size_t)n * stride));
+  B200_TRY(dout.alloc(ctx, (size_t)n * 3));
+  B200_TRY(dcount.alloc(ctx, 1));
+  B200_TRY(dev_voxel_grid(ctx, din.p, n, stride, lx, ly, lz, dout.p, dcount.p));
+  B200_TRY(download(ctx, count, dcount.p, 1));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_TRY(download(ctx, out_xyz, dout.p, (size_t)*count * 3));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 /* ------------------------------------------------------------------ grouping */
 int b200_gc_recognize(b200_ctx *ctx, const float *model_kp, int Km, int mstride, const float *scene_kp, int Ks,
                       int sstride, const b200_corr *corrs, int C, double gc_size, int gc_threshold, float *transforms,

@@ -303,6 +303,11 @@ int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
 // match.cu
 int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
               b200_corr *d_out, int *d_count);
+// keypoints.cu
+int dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, float leaf, float *d_out_xyz,
+                         int *d_out_index, int *d_count);
+int dev_voxel_grid(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx, float ly, float lz,
+                   float *d_out_xyz, int *d_count);
 // gc.cu
 int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, const b200_corr *d_corrs,
            const int *d_C, int C_cap, double gc_size, int gc_threshold, float *d_T, int max_inst,

@@ -9,7 +9,7 @@
 // (n x 3, written by the tests) instead of PCD files, keypoints are given (the reference's
 // UniformSampling runs on the CPU before the hot path).
 //
-// usage: shot_recognition <model.f32> <model_kp.f32> <scene.f32> <scene_kp.f32> <out_prefix>
+// usage: shot_recognition <model.f32> <model_kp.f32 | us:leaf> <scene.f32> <scene_kp.f32 | us:leaf> <out_prefix>
 //                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch]
 // writes <out_prefix>.corr (b200_corr records), <out_prefix>.T (instances x 16 float),
 //        <out_prefix>.inst (int32 count per instance followed by the records)
@@ -62,9 +62,20 @@ int main(int argc, char **argv) {
       scene_normals(new pcl::PointCloud<NormalType>());
   pcl::PointCloud<DescriptorType>::Ptr model_descriptors(new pcl::PointCloud<DescriptorType>()),
       scene_descriptors(new pcl::PointCloud<DescriptorType>());
-  if (!load_cloud(argv[1], *model) || !load_cloud(argv[2], *model_keypoints) || !load_cloud(argv[3], *scene) ||
-      !load_cloud(argv[4], *scene_keypoints))
-    return 1;
+  if (!load_cloud(argv[1], *model) || !load_cloud(argv[3], *scene)) return 1;
+  // keypoints: a file, or "us:<leaf>" to extract them like the reference does (SHOT.cpp:314-323)
+  for (int side = 0; side < 2; ++side) {
+    const std::string spec = argv[side ? 4 : 2];
+    pcl::PointCloud<PointType>::Ptr &kp = side ? scene_keypoints : model_keypoints;
+    if (spec.rfind("us:", 0) == 0) {
+      pcl::UniformSampling<PointType> uniform_sampling;
+      uniform_sampling.setInputCloud(side ? scene : model);
+      uniform_sampling.setRadiusSearch(atof(spec.c_str() + 3));
+      uniform_sampling.filter(*kp);
+    } else if (!load_cloud(spec.c_str(), *kp)) {
+      return 1;
+    }
+  }
   std::cout << "Model total points: " << model->size() << "; Selected Keypoints: " << model_keypoints->size() << std::endl;
   std::cout << "Scene total points: " << scene->size() << "; Selected Keypoints: " << scene_keypoints->size() << std::endl;
 

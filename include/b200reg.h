@@ -99,6 +99,25 @@ B200_API int b200_radius_search(b200_ctx *ctx, b200_cloud *surf, const float *q,
 B200_API int b200_knn_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qstride, int k, int *idx,
                     float *d2, int *k_found);
 
+/* ---------------------------------------------------------------- keypoints -------------- */
+/* pcl::UniformSampling<PointT>::filter (SHOT.cpp:314-323, SHOT_demo.cpp:246-249, 6Dpose.cpp:281-284,
+ * CAD_desc.cpp:295-304; setRadiusSearch(leaf)): per occupied leaf of the lattice ijk = floor(p / leaf) the
+ * input point closest to the leaf's integer index vector (PCL's own test), first point on ties.  Output
+ * order: ascending leaf index (PCL's is hash-map order).  out_xyz: capacity n x 3 floats; out_index
+ * (nullable): original row of every kept point; *count = number kept.  Non-finite rows are skipped.
+ * B200_ERR_CAPACITY when the lattice has more than 2^26 leaves (PCL: "leaf size is too small"). */
+B200_API int b200_uniform_sampling(b200_ctx *ctx, const float *xyz, int n, int stride, double leaf, float *out_xyz,
+                                   int *out_index, int *count);
+B200_API int b200_dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, double leaf,
+                                       float *d_out_xyz, int *d_out_index, int *d_count);
+/* pcl::VoxelGrid<PointT>::filter (SHOT_demo.cpp:413-417, 489-491; FPFH_demo.cpp:412-415, 494;
+ * setLeafSize(lx, ly, lz)): centroid of the points of every occupied voxel, ascending voxel index.  Only
+ * x, y, z are averaged (the hot path never reads colour).  out_xyz: capacity n x 3 floats. */
+B200_API int b200_voxel_grid(b200_ctx *ctx, const float *xyz, int n, int stride, float lx, float ly, float lz,
+                             float *out_xyz, int *count);
+B200_API int b200_dev_voxel_grid(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx, float ly, float lz,
+                                 float *d_out_xyz, int *d_count);
+
 /* ---------------------------------------------------------------- normals ---------------- */
 /* pcl::NormalEstimationOMP::compute — setKSearch(k) (SHOT.cpp:302-308, 6Dpose.cpp:275-278,
  * SHOT_demo.cpp:405-411, CAD_desc.cpp:283-289) or setRadiusSearch(r) (FPFH_demo.cpp:416-420,

@@ -332,6 +332,71 @@ inline bool determineCorrespondences(const PointCloud<DescT> &model, const Point
   return good;
 }
 
+/* ---------------------------------------------------------------- keypoints */
+/* pcl::UniformSampling<PointT> (SHOT.cpp:314-323): setInputCloud, setRadiusSearch(leaf), filter(output).
+ * Keeps input points (all fields are copied); output order is ascending leaf index. */
+template <class PointT>
+class UniformSampling {
+ public:
+  typedef std::shared_ptr<const PointCloud<PointT>> PointCloudConstPtr;
+  void setInputCloud(const PointCloudConstPtr &cloud) { input_ = cloud; }
+  void setRadiusSearch(double radius) { leaf_ = radius; }
+  void filter(PointCloud<PointT> &output) {
+    output.clear();
+    if (!input_ || input_->empty() || !detail::ctx()) return;
+    const int n = (int)input_->size();
+    std::vector<float> xyz((size_t)n * 3);
+    std::vector<int> idx((size_t)n);
+    int count = 0;
+    if (!detail::ok(b200_uniform_sampling(detail::ctx(), detail::xyz(input_->points), n, detail::stride<PointT>(), leaf_,
+                                          xyz.data(), idx.data(), &count),
+                    "UniformSampling::filter"))
+      return;
+    output.points.resize((size_t)count);
+    for (int i = 0; i < count; ++i) output.points[i] = input_->points[idx[i]];
+    output.width = (uint32_t)count;
+    output.height = 1;
+    output.is_dense = true;
+  }
+
+ private:
+  PointCloudConstPtr input_;
+  double leaf_ = 0.0;
+};
+
+/* pcl::VoxelGrid<PointT> (SHOT_demo.cpp:413-417, 489-491): setInputCloud, setLeafSize, filter(output).
+ * x, y, z are the voxel centroids; the other fields (colour) are left at their defaults. */
+template <class PointT>
+class VoxelGrid {
+ public:
+  typedef std::shared_ptr<const PointCloud<PointT>> PointCloudConstPtr;
+  void setInputCloud(const PointCloudConstPtr &cloud) { input_ = cloud; }
+  void setLeafSize(float lx, float ly, float lz) { l_[0] = lx, l_[1] = ly, l_[2] = lz; }
+  void filter(PointCloud<PointT> &output) {
+    output.clear();
+    if (!input_ || input_->empty() || !detail::ctx()) return;
+    const int n = (int)input_->size();
+    std::vector<float> xyz((size_t)n * 3);
+    int count = 0;
+    if (!detail::ok(b200_voxel_grid(detail::ctx(), detail::xyz(input_->points), n, detail::stride<PointT>(), l_[0], l_[1],
+                                    l_[2], xyz.data(), &count),
+                    "VoxelGrid::filter"))
+      return;
+    output.points.resize((size_t)count);
+    for (int i = 0; i < count; ++i) {
+      output.points[i].x = xyz[(size_t)i * 3], output.points[i].y = xyz[(size_t)i * 3 + 1];
+      output.points[i].z = xyz[(size_t)i * 3 + 2];
+    }
+    output.width = (uint32_t)count;
+    output.height = 1;
+    output.is_dense = true;
+  }
+
+ private:
+  PointCloudConstPtr input_;
+  float l_[3] = {0.f, 0.f, 0.f};
+};
+
 /* ---------------------------------------------------------------- Feature base */
 template <class PointInT>
 class FeatureBase {

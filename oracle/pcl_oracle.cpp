@@ -1370,6 +1370,108 @@ void orc_eigen33_smallest(const float cov9[9], float *eigenvalue, float evec3[3]
   eigen33_smallest(cov9, *eigenvalue, evec3);
 }
 void orc_eigh3_f64(const double a9[9], double evals3[3], double evecs9[9]) { eigh3_f64(a9, evals3, evecs9); }
+/* ------------------------------------------------------------------------------------------------
+ * Keypoint extraction.
+ * pcl::UniformSampling<PointT>::applyFilter (pcl 1.8 filters/impl/uniform_sampling.hpp; SHOT.cpp:314-323):
+ *   inverse_leaf = 1 / leaf (float); ijk = floor(p * inverse_leaf); leaf index = (ijk - min_b) . divb_mul;
+ *   per leaf keep the point with the smaller (p - (float)ijk).squaredNorm() on the homogeneous 4-vectors
+ *   (w: 1 - 0), strict <, i.e. the first point wins ties.  Output order: hash-map order in PCL, defined
+ *   here as ascending leaf index.
+ * pcl::VoxelGrid<PointT>::applyFilter (filters/impl/voxel_grid.hpp; SHOT_demo.cpp:413-417): same lattice;
+ *   centroid of every occupied voxel, ascending voxel index.  PCL sums in float32 in the order of an
+ *   unstable sort; the centroid is evaluated in float64 here (order independent) and rounded once.
+ * Non-finite points are skipped.  Returns the number of keypoints, or -1 when the lattice would need
+ * more than 2^26 leaves ("Leaf size is too small for the input dataset").
+ * ---------------------------------------------------------------------------------------------- */
+namespace {
+struct LatticeO {
+  float inv[3];
+  long long mn[3], dim[3];
+};
+bool make_lattice_o(const float *xyz, int n, int stride, const float leaf[3], LatticeO &L) {
+  for (int a = 0; a < 3; ++a) L.inv[a] = 1.0f / leaf[a];
+  long long mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  for (int a = 0; a < 3; ++a) L.mn[a] = LLONG_MAX;
+  bool any = false;
+  for (int i = 0; i < n; ++i) {
+    const float *p = xyz + (size_t)i * stride;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    any = true;
+    for (int a = 0; a < 3; ++a) {
+      const long long c = (long long)std::floor(p[a] * L.inv[a]);
+      L.mn[a] = std::min(L.mn[a], c);
+      mx[a] = std::max(mx[a], c);
+    }
+  }
+  if (!any) {
+    for (int a = 0; a < 3; ++a) L.dim[a] = 0;
+    return true;
+  }
+  for (int a = 0; a < 3; ++a) L.dim[a] = mx[a] - L.mn[a] + 1;
+  return L.dim[0] * L.dim[1] * L.dim[2] <= (1ll << 26);
+}
+}  // namespace
+
+int orc_uniform_sampling(const float *xyz, int n, int stride, double leaf, float *out_xyz, int *out_index) {
+  LatticeO L;
+  const float lf[3] = {(float)leaf, (float)leaf, (float)leaf};
+  if (!make_lattice_o(xyz, n, stride, lf, L)) return -1;
+  const long long nleaf = L.dim[0] * L.dim[1] * L.dim[2];
+  std::vector<int> keep((size_t)nleaf, -1);
+  std::vector<float> best((size_t)nleaf, 0.f);
+  for (int i = 0; i < n; ++i) {
+    const float *p = xyz + (size_t)i * stride;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    long long c[3];
+    for (int a = 0; a < 3; ++a) c[a] = (long long)std::floor(p[a] * L.inv[a]);
+    const long long idx = (c[0] - L.mn[0]) + L.dim[0] * ((c[1] - L.mn[1]) + L.dim[1] * (c[2] - L.mn[2]));
+    const float d0 = p[0] - (float)c[0], d1 = p[1] - (float)c[1], d2 = p[2] - (float)c[2];
+    float diff = d0 * d0;
+    diff += d1 * d1;
+    diff += d2 * d2;
+    diff += 1.0f;
+    if (keep[(size_t)idx] < 0 || diff < best[(size_t)idx]) {
+      keep[(size_t)idx] = i;
+      best[(size_t)idx] = diff;
+    }
+  }
+  int m = 0;
+  for (long long l = 0; l < nleaf; ++l)
+    if (keep[(size_t)l] >= 0) {
+      const float *p = xyz + (size_t)keep[(size_t)l] * stride;
+      out_xyz[(size_t)m * 3 + 0] = p[0], out_xyz[(size_t)m * 3 + 1] = p[1], out_xyz[(size_t)m * 3 + 2] = p[2];
+      if (out_index) out_index[m] = keep[(size_t)l];
+      ++m;
+    }
+  return m;
+}
+
+int orc_voxel_grid(const float *xyz, int n, int stride, float lx, float ly, float lz, float *out_xyz) {
+  LatticeO L;
+  const float lf[3] = {lx, ly, lz};
+  if (!make_lattice_o(xyz, n, stride, lf, L)) return -1;
+  const long long nleaf = L.dim[0] * L.dim[1] * L.dim[2];
+  std::vector<double> sums((size_t)nleaf * 3, 0.0);
+  std::vector<int> cnt((size_t)nleaf, 0);
+  for (int i = 0; i < n; ++i) {
+    const float *p = xyz + (size_t)i * stride;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    long long c[3];
+    for (int a = 0; a < 3; ++a) c[a] = (long long)std::floor(p[a] * L.inv[a]);
+    const long long idx = (c[0] - L.mn[0]) + L.dim[0] * ((c[1] - L.mn[1]) + L.dim[1] * (c[2] - L.mn[2]));
+    for (int a = 0; a < 3; ++a) sums[(size_t)idx * 3 + a] += (double)p[a];
+    ++cnt[(size_t)idx];
+  }
+  int m = 0;
+  for (long long l = 0; l < nleaf; ++l)
+    if (cnt[(size_t)l] > 0) {
+      const double inv = 1.0 / (double)cnt[(size_t)l];
+      for (int a = 0; a < 3; ++a) out_xyz[(size_t)m * 3 + a] = (float)(sums[(size_t)l * 3 + a] * inv);
+      ++m;
+    }
+  return m;
+}
+
 void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]) { umeyama3(src, dst, n, T16); }
 uint32_t orc_mt19937_nth(uint32_t seed, int nth) {
   std::mt19937 rng(seed);

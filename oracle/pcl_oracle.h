@@ -98,6 +98,12 @@ void orc_eigh3_f64(const double a9[9], double evals3[3], double evecs9[9]);     
 void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]);      /* rigid, no scale */
 uint32_t orc_mt19937_nth(uint32_t seed, int nth);                                    /* known-answer hook */
 
+/* pcl::UniformSampling::filter (SHOT.cpp:314-323) / pcl::VoxelGrid::filter (SHOT_demo.cpp:413-417); output
+ * in ascending leaf index; out_xyz has room for n x 3 floats.  Return the number of keypoints, -1 when the
+ * lattice is too fine (PCL: "leaf size is too small").  See the implementation for the PCL semantics. */
+int orc_uniform_sampling(const float *xyz, int n, int stride, double leaf, float *out_xyz, int *out_index);
+int orc_voxel_grid(const float *xyz, int n, int stride, float lx, float ly, float lz, float *out_xyz);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,10 @@ def lib():
         L.orc_gc_recognize.restype = C.c_int
         L.orc_gc_recognize.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.POINTER(Corr), C.c_int,
                                        C.c_double, C.c_int, fp, C.c_int, ip, C.POINTER(Corr), C.c_int]
+        L.orc_uniform_sampling.restype = C.c_int
+        L.orc_uniform_sampling.argtypes = [fp, C.c_int, C.c_int, C.c_double, fp, ip]
+        L.orc_voxel_grid.restype = C.c_int
+        L.orc_voxel_grid.argtypes = [fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, fp]
         L.orc_eigen33_smallest.argtypes = [fp, fp, fp]
         L.orc_eigh3_f64.argtypes = [C.POINTER(C.c_double)] * 3
         L.orc_umeyama3.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
@@ -177,6 +181,26 @@ def gc_recognize(model_kp, scene_kp, corrs, gc_size, gc_threshold, max_inst=256)
                                oc.ctypes.data_as(C.POINTER(Corr)), cap)
     n = min(n, max_inst)
     return T[:n].reshape(n, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(n)]
+
+
+def uniform_sampling(xyz, leaf, return_index=False):
+    xyz = _pts(xyz)
+    out = np.zeros((max(len(xyz), 1), 3), dtype=np.float32)
+    idx = np.zeros(max(len(xyz), 1), dtype=np.int32)
+    n = lib().orc_uniform_sampling(_f(xyz), len(xyz), xyz.shape[1], float(leaf), _f(out), _i(idx))
+    if n < 0:
+        raise ValueError("leaf size is too small for the input dataset")
+    return (out[:n].copy(), idx[:n].copy()) if return_index else out[:n].copy()
+
+
+def voxel_grid(xyz, leaf):
+    xyz = _pts(xyz)
+    lx, ly, lz = (leaf, leaf, leaf) if np.isscalar(leaf) else leaf
+    out = np.zeros((max(len(xyz), 1), 3), dtype=np.float32)
+    n = lib().orc_voxel_grid(_f(xyz), len(xyz), xyz.shape[1], float(lx), float(ly), float(lz), _f(out))
+    if n < 0:
+        raise ValueError("leaf size is too small for the input dataset")
+    return out[:n].copy()
 
 
 def eigen33_smallest(cov):

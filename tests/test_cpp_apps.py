@@ -103,3 +103,26 @@ def test_fpfh_recognition_app_matches_oracle(apps, orc, synth, tmp_path):
     oc = orc.match(dm, desc, 2, 0.0)            # k = 2 ratio test on the app's own scene descriptors
     same = (corr["index_match"] == oc["index_match"]).all() and (corr["index_query"] == oc["index_query"]).mean() > 0.99
     assert len(corr) == len(oc) and same
+
+
+@pytest.mark.gpu
+def test_shot_recognition_app_extracts_keypoints(apps, orc, synth, tmp_path):
+    """`us:<leaf>` keypoints: pcl::UniformSampling through the adapter, as SHOT.cpp:314-323 does."""
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 30000, scene_id=3)
+    _write(tmp_path / "m.f32", model)
+    _write(tmp_path / "s.f32", scene)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([apps["shot_recognition"], str(tmp_path / "m.f32"), "us:0.02", str(tmp_path / "s.f32"), "us:0.03",
+                        prefix, "10", "0.02", "0.25", "0.02", "2", "batch"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    kpm, kps = orc.uniform_sampling(model, 0.02), orc.uniform_sampling(scene, 0.03)
+    assert "Selected Keypoints: %d" % len(kpm) in r.stdout and "Selected Keypoints: %d" % len(kps) in r.stdout
+    corr = np.fromfile(prefix + ".corr", dtype=CORR)
+    rad = float(np.float32(0.02))
+    dm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, rad)
+    ds, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, rad)
+    oc = orc.match(dm, ds, 1, 0.25)
+    a = set(map(tuple, corr[["index_query", "index_match"]].tolist()))
+    b = set(map(tuple, oc[["index_query", "index_match"]].tolist()))
+    assert len(b) > 20 and len(a ^ b) <= max(2, 0.002 * len(b))

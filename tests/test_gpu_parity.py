@@ -457,3 +457,25 @@ def test_desc_index_knn_bit_exact(ctx, orc):
     idx, d2, kf = small.knn(rng.uniform(0, 1, (2, 33)).astype(np.float32), 5)
     assert kf == 3 and np.all(idx[:, 3:] == -1) and np.all(np.isinf(d2[:, 3:]))
     small.close()
+
+
+# ------------------------------------------------------------------------------------------ keypoints
+def test_keypoint_extraction_parity(ctx, orc, synth, b200):
+    """UniformSampling (SHOT.cpp:314-323): same points and rows, bit for bit.  VoxelGrid (SHOT_demo.cpp:413-417):
+    same voxels in the same order, centroids to 1 ulp (float64 sums whose order is not fixed on the device)."""
+    for cloud, leaf in ((synth.make_model("y", 20000), 0.005), (synth.make_scene(("y",), 80000, scene_id=9), 0.01),
+                        (synth.make_scene(("horizontal",), 30000, scene_id=2), 0.03)):
+        cloud = cloud.copy()
+        cloud[5] = np.nan
+        us, idx = ctx.uniform_sampling(cloud, leaf, return_index=True)
+        ous, oidx = orc.uniform_sampling(cloud, leaf, return_index=True)
+        assert np.array_equal(idx, oidx) and np.array_equal(us, ous)
+        vg = ctx.voxel_grid(cloud, leaf)
+        ovg = orc.voxel_grid(cloud, leaf)
+        assert vg.shape == ovg.shape
+        assert np.abs(vg - ovg).max() <= 2.4e-7 * max(1.0, np.abs(ovg).max())
+    vg = ctx.voxel_grid(cloud, (0.03, 0.05, 0.02))
+    assert vg.shape == orc.voxel_grid(cloud, (0.03, 0.05, 0.02)).shape
+    assert len(ctx.uniform_sampling(np.zeros((0, 3), np.float32), 0.01)) == 0
+    with pytest.raises(b200.B200Error):
+        ctx.uniform_sampling(cloud, 1e-5)

@@ -269,3 +269,24 @@ def test_gc_recovers_known_transform(orc):
     # too few correspondences → no instance
     T2, _ = orc.gc_recognize(model, scene, corrs[:3], 0.01, 5)
     assert len(T2) == 0
+
+
+def test_keypoint_extractors_match_harness(orc, synth):
+    """oracle UniformSampling / VoxelGrid (Appendix A.9 semantics) against the numpy harness versions that feed
+    the benchmark, plus their defining properties."""
+    cloud = synth.make_scene(("diagonal",), 30000, scene_id=6)
+    cloud[17] = np.nan
+    us, idx = orc.uniform_sampling(cloud, 0.02, return_index=True)
+    ok = np.isfinite(cloud).all(1)
+    assert np.array_equal(us, synth.uniform_sampling(cloud[ok], 0.02))
+    assert np.array_equal(cloud[idx], us)                       # input points are kept, not averaged
+    cells = np.floor(us / np.float32(0.02)).astype(np.int64)
+    assert len(np.unique(cells, axis=0)) == len(us)             # one per leaf
+    vg = orc.voxel_grid(cloud, 0.03)
+    assert np.array_equal(vg, synth.voxel_grid(cloud[ok], 0.03))
+    assert len(vg) == len(np.unique(np.floor(cloud[ok] / np.float32(0.03)).astype(np.int64), axis=0))
+    vg3 = orc.voxel_grid(cloud, (0.03, 0.05, 0.02))
+    assert 0 < len(vg3) < len(cloud)
+    with pytest.raises(ValueError):
+        orc.uniform_sampling(cloud, 1e-5)                       # lattice too fine (PCL: leaf size too small)
+    assert len(orc.uniform_sampling(np.zeros((0, 3), np.float32), 0.01)) == 0
