@@ -62,6 +62,25 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
     const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
     const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
     const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dx - 1);
+    if (R == 1) {
+      // the first shell, nearest rows first (|dz| + |dy| = 0, 1, 2): the list fills with close points
+      // early, so that most later candidates fail the cheap "farther than the current k-th" test
+      // instead of being inserted and displaced again (the result does not depend on the order)
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t) {
+        const int dz = (t == 3) ? -1 : (t == 4) ? 1 : (t >= 5) ? ((t & 1) ? -1 : 1) : 0;
+        const int dy = (t == 1) ? -1 : (t == 2) ? 1 : (t >= 5) ? ((t < 7) ? -1 : 1) : 0;
+        const int z = cz + dz, y = cy + dy;
+        if (z < 0 || z >= g.dz || y < 0 || y >= g.dy) continue;
+        const int row = g.dx * (y + g.dy * z);
+        if (t == 0) {
+          if (cx - 1 >= 0) scan_run(row + cx - 1, row + cx - 1);
+          if (cx + 1 <= g.dx - 1) scan_run(row + cx + 1, row + cx + 1);
+        } else {
+          scan_run(row + x0, row + x1);
+        }
+      }
+    } else
     for (int z = z0; z <= z1; ++z)
       for (int y = y0; y <= y1; ++y) {
         const bool face = (abs(z - cz) == R) || (abs(y - cy) == R);
