@@ -29,6 +29,8 @@ EXPORTS = [
     "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio",
     "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
+    "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
+    "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
 ]
 
 
@@ -108,6 +110,14 @@ def lib():
             "b200_dev_uniform_sampling": [vp, vp, i, i, d, vp, vp, vp],
             "b200_voxel_grid": [vp, fp, i, i, f, f, f, fp, ip],
             "b200_dev_voxel_grid": [vp, vp, i, i, f, f, f, vp, vp],
+            "b200_library_create": [vp, C.POINTER(vp)],
+            "b200_library_destroy": [vp],
+            "b200_library_add_view": [vp, vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), ip],
+            "b200_library_views": [vp],
+            "b200_library_view_size": [vp, i],
+            "b200_library_download_view": [vp, vp, i, fp, fp],
+            "b200_register_scene_library": [vp, vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), fp, ip, ip,
+                                            C.POINTER(Corr), i, i, ip, ip],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -242,6 +252,68 @@ class DescIndex:
     def close(self):
         if self.h and self.ctx.h:
             lib().b200_desc_index_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Library:
+    """b200_library: descriptor library over the views of the CAD models (CAD_desc.cpp:231-370)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._chk(lib().b200_library_create(ctx.h, C.byref(h)))
+        self.h = h
+        ctx._children.add(self)
+
+    def add_view(self, xyz, kp, params):
+        xyz, kp = _pts(xyz), _pts(kp)
+        v = C.c_int()
+        self.ctx._chk(lib().b200_library_add_view(self.ctx.h, self.h, _f(xyz), len(xyz), xyz.shape[1], _f(kp), len(kp),
+                                                  kp.shape[1], C.byref(params), C.byref(v)))
+        return v.value
+
+    @property
+    def views(self):
+        return lib().b200_library_views(self.h)
+
+    def view_size(self, v):
+        return lib().b200_library_view_size(self.h, int(v))
+
+    def download_view(self, v):
+        K = self.view_size(v)
+        desc = np.zeros((K, 352), dtype=np.float32)
+        kp = np.zeros((K, 3), dtype=np.float32)
+        self.ctx._chk(lib().b200_library_download_view(self.ctx.h, self.h, int(v), _f(desc), _f(kp)))
+        return desc, kp
+
+    def register_scene(self, scene_xyz, scene_kp, params, max_inst=4096):
+        scene_xyz, scene_kp = _pts(scene_xyz), _pts(scene_kp)
+        Ks, nv = len(scene_kp), self.views
+        cap = max(Ks, 1) * max(nv, 1)
+        T = np.empty((max_inst, 16), dtype=np.float32)
+        view = np.empty(max_inst, dtype=np.int32)
+        off = np.empty(max_inst + 1, dtype=np.int32)
+        ic = np.empty(cap, dtype=CORR_DTYPE)
+        ncorr = np.zeros(max(nv, 1), dtype=np.int32)
+        n = C.c_int()
+        rc = lib().b200_register_scene_library(self.ctx.h, self.h, _f(scene_xyz), len(scene_xyz), scene_xyz.shape[1],
+                                               _f(scene_kp), Ks, scene_kp.shape[1], C.byref(params), _f(T), _i(view),
+                                               _i(off), _c(ic), cap, max_inst, C.byref(n), _i(ncorr))
+        if rc not in (OK, ERR_CAPACITY):
+            self.ctx._chk(rc)
+        m = n.value
+        return {"transforms": T[:m].reshape(m, 4, 4), "view": view[:m], "instances": InstanceList(ic, off, m),
+                "n_instances": m, "view_n_corrs": ncorr[:nv]}
+
+    def close(self):
+        if self.h and self.ctx.h:
+            lib().b200_library_destroy(self.h)
         self.h = None
 
     def __del__(self):

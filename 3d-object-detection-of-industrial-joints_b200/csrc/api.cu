@@ -708,4 +708,123 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
   return rc;
 }
 
+/* ------------------------------------------------------------------ multi-view library */
+int b200_library_create(b200_ctx *ctx, b200_library **out) {
+  API_ENTER(ctx);
+  if (!out) return ctx->fail(B200_ERR_INVALID, "library_create: null output");
+  b200_library *lib = new b200_library();
+  lib->ctx = ctx;
+  *out = lib;
+  return B200_OK;
+}
+
+int b200_library_destroy(b200_library *lib) {
+  if (!lib) return B200_OK;
+  for (b200_model *m : lib->views) b200_model_destroy(m);
+  delete lib;
+  return B200_OK;
+}
+
+int b200_library_add_view(b200_ctx *ctx, b200_library *lib, const float *xyz, int n, int stride, const float *kp, int K,
+                          int kstride, const b200_shot_params *p, int *view_id) {
+  API_ENTER(ctx);
+  if (!lib) return ctx->fail(B200_ERR_INVALID, "library_add_view: null library");
+  b200_model *m = nullptr;
+  B200_TRY(b200_model_create_shot(ctx, xyz, n, stride, kp, K, kstride, p, &m));
+  lib->views.push_back(m);
+  if (view_id) *view_id = (int)lib->views.size() - 1;
+  return B200_OK;
+}
+
+int b200_library_views(const b200_library *lib) { return lib ? (int)lib->views.size() : 0; }
+
+int b200_library_view_size(const b200_library *lib, int view) {
+  return (lib && view >= 0 && view < (int)lib->views.size()) ? lib->views[view]->K : 0;
+}
+
+int b200_library_download_view(b200_ctx *ctx, const b200_library *lib, int view, float *desc, float *kp) {
+  API_ENTER(ctx);
+  if (!lib || view < 0 || view >= (int)lib->views.size()) return ctx->fail(B200_ERR_INVALID, "library: bad view index");
+  return b200_model_download(ctx, lib->views[view], desc, kp);
+}
+
+int b200_register_scene_library(b200_ctx *ctx, const b200_library *lib, const float *scene_xyz, int n, int stride,
+                                const float *scene_kp, int Ks, int kstride, const b200_shot_params *p, float *transforms,
+                                int *inst_view, int *inst_offsets, b200_corr *inst_corrs, int corr_cap, int max_inst,
+                                int *n_inst, int *view_n_corrs) {
+  API_ENTER(ctx);
+  if (!lib || !n_inst || Ks < 0 || max_inst < 1) return ctx->fail(B200_ERR_INVALID, "register_scene_library: bad arguments");
+  B200_TRY(check_params(ctx, p));
+  *n_inst = 0;
+  if (inst_offsets) inst_offsets[0] = 0;
+  b200_cloud *scene = nullptr;
+  B200_TRY(cloud_upload(ctx, scene_xyz, n, stride, false, &scene));
+  int rc = B200_OK;
+  do {
+    // scene side once: normals + SHOT352 at the keypoints (the reference recomputes both per view)
+    DevBuf<float4> dkp;
+    DevBuf<float> normals, desc;
+    if ((rc = upload_points(ctx, scene_kp, Ks, kstride, dkp)) != B200_OK) break;
+    if ((rc = normals.alloc(ctx, (size_t)std::max(scene->n, 1) * 4)) != B200_OK) break;
+    if ((rc = dev_normals(ctx, scene, scene->raw.p, scene->n, true, p->normal_k, p->normal_radius, nullptr, normals.p)) !=
+        B200_OK)
+      break;
+    if ((rc = desc.alloc(ctx, (size_t)std::max(Ks, 1) * 352)) != B200_OK) break;
+    if ((rc = dev_shot(ctx, scene, normals.p, dkp.p, Ks, p->descr_radius, desc.p, nullptr, false)) != B200_OK) break;
+    const int cap = std::max(Ks, 1), mi = p->max_instances;
+    DevBuf<b200_corr> dcorrs, dic;
+    DevBuf<int> doffs, dcnts, dn, dnc;
+    DevBuf<float> dT;
+    if ((rc = dcorrs.alloc(ctx, (size_t)cap)) != B200_OK) break;
+    if ((rc = dic.alloc(ctx, (size_t)cap)) != B200_OK) break;
+    if ((rc = doffs.alloc(ctx, (size_t)mi + 1)) != B200_OK) break;
+    if ((rc = dcnts.alloc(ctx, (size_t)mi)) != B200_OK) break;
+    if ((rc = dn.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dnc.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dT.alloc(ctx, (size_t)mi * 16)) != B200_OK) break;
+    std::vector<float> hT((size_t)mi * 16);
+    std::vector<int> hoff((size_t)mi + 1);
+    std::vector<b200_corr> hic((size_t)cap);
+    int total_inst = 0, total_corr = 0;
+    bool overflow = false;
+    for (int v = 0; v < (int)lib->views.size() && rc == B200_OK; ++v) {
+      const b200_model *m = lib->views[v];
+      if ((rc = dev_match(ctx, m->desc.p, m->K, desc.p, Ks, 352, p->match_mode, p->match_thr, dcorrs.p, dnc.p)) != B200_OK) break;
+      if ((rc = dev_gc(ctx, m->kp.p, dkp.p, dcorrs.p, dnc.p, Ks, p->gc_size, p->gc_threshold, dT.p, mi, doffs.p, dcnts.p,
+                       dic.p, cap, dn.p)) != B200_OK)
+        break;
+      if (view_n_corrs) {
+        if ((rc = download(ctx, &view_n_corrs[v], dnc.p, 1)) != B200_OK) break;
+      }
+      int found = 0;
+      rc = download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, mi, cap, hT.data(), hoff.data(), hic.data(), cap,
+                              &found);
+      if (rc == B200_ERR_CAPACITY) {  // more than max_instances in this view: the first ones are kept
+        overflow = true;
+        rc = B200_OK;
+      }
+      if (rc != B200_OK) break;
+      const int kept = std::min(found, mi);
+      for (int i = 0; i < kept; ++i) {
+        const int cnt = hoff[i + 1] - hoff[i];
+        if (total_inst >= max_inst || total_corr + cnt > corr_cap) {
+          overflow = true;
+          break;
+        }
+        if (transforms) memcpy(transforms + (size_t)total_inst * 16, hT.data() + (size_t)i * 16, sizeof(float) * 16);
+        if (inst_view) inst_view[total_inst] = v;
+        if (inst_corrs) memcpy(inst_corrs + total_corr, hic.data() + hoff[i], sizeof(b200_corr) * (size_t)cnt);
+        total_corr += cnt;
+        ++total_inst;
+        if (inst_offsets) inst_offsets[total_inst] = total_corr;
+      }
+    }
+    if (rc != B200_OK) break;
+    *n_inst = total_inst;
+    if (overflow) rc = ctx->fail(B200_ERR_CAPACITY, "register_scene_library: output capacity too small");
+  } while (0);
+  delete scene;
+  return rc;
+}
+
 } /* extern "C" */

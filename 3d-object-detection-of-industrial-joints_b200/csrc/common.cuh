@@ -275,6 +275,11 @@ struct b200_model {
   DevBuf<float4> kp;   // K keypoints
 };
 
+struct b200_library {
+  b200_ctx *ctx = nullptr;
+  std::vector<b200_model *> views;
+};
+
 // scan.cu
 int exclusive_scan_i32(b200_ctx *ctx, const int *d_in, int *d_out, int n, int *d_total /*nullable*/);
 // grid.cu

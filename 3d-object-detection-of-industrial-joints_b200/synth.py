@@ -77,6 +77,23 @@ def make_model(joint="y", n=5000, seed=None):
     return p.astype(np.float32)
 
 
+def view_directions(n_views=64):
+    """Camera directions of the rendered partial views: a Fibonacci sphere (render.cpp:30-35 uses the 42
+    vertices of a tessellated icosphere; BASELINE.json config 4 asks for 64)."""
+    i = np.arange(n_views) + 0.5
+    phi = np.arccos(1 - 2 * i / n_views)
+    th = np.pi * (1 + 5 ** 0.5) * i
+    return np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
+
+
+def make_partial_view(joint="y", view=0, n=4000, n_views=64):
+    """Partial view of a CAD joint as seen from view direction `view`: the surface points whose outward
+    normal faces the camera (self-occlusion between chord and stub is ignored).  float32 (m, 3), m ~ n / 2."""
+    p, q = joint_surface(joint, n, _rng(3000 + 97 * JOINT_IDS[joint] + view))
+    d = view_directions(n_views)[view]
+    return p[q @ d > 0.1].astype(np.float32)
+
+
 def random_pose(rng, max_deg=60.0, trans=0.3, z=1.0):
     """Rigid pose: rotation within +-max_deg about each axis, translation U[-trans, trans]^3 + (0,0,z)."""
     ax, ay, az = np.deg2rad(rng.uniform(-max_deg, max_deg, 3))

@@ -217,6 +217,30 @@ B200_API int b200_dev_register_scene_shot(b200_ctx *ctx, const b200_model *model
                                  int *d_inst_counts, b200_corr *d_inst_corrs, int corr_cap, int *d_n_inst,
                                  b200_corr *d_corrs_out, int *d_n_corrs, float *d_desc_out);
 
+/* ---------------------------------------------------------------- multi-view library ----- */
+/* The reference recognises against a set of rendered partial views of the CAD models: CAD_desc.cpp:231-370
+ * builds one SHOT descriptor set per view, and SHOT.cpp:243-483 / 6Dpose.cpp / SHOT_demo.cpp:430-663 loop over
+ * the views, recomputing the SCENE normals and descriptors inside the loop (6Dpose.cpp:458-461).  A library
+ * keeps every view's descriptors + keypoints resident; b200_register_scene_library computes the scene side
+ * once and then runs correspondence search + geometric-consistency grouping per view. */
+typedef struct b200_library b200_library;
+B200_API int b200_library_create(b200_ctx *ctx, b200_library **out);
+B200_API int b200_library_destroy(b200_library *lib);
+/* one view = body of the CAD_desc.cpp loop (normals, SHOT352 at the keypoints); *view_id = its index */
+B200_API int b200_library_add_view(b200_ctx *ctx, b200_library *lib, const float *xyz, int n, int stride, const float *kp,
+                                   int K, int kstride, const b200_shot_params *p, int *view_id);
+B200_API int b200_library_views(const b200_library *lib);
+B200_API int b200_library_view_size(const b200_library *lib, int view);
+B200_API int b200_library_download_view(b200_ctx *ctx, const b200_library *lib, int view, float *desc, float *kp);
+/* Instances of all views, concatenated in view order: inst_view[i] = view of instance i; transforms, inst_offsets
+ * (max_inst + 1) and inst_corrs (index_query = keypoint index WITHIN the view) as in b200_gc_recognize;
+ * view_n_corrs (nullable, one per view) = correspondences found for that view.  p->max_instances bounds the
+ * instances kept per view, max_inst the total. */
+B200_API int b200_register_scene_library(b200_ctx *ctx, const b200_library *lib, const float *scene_xyz, int n, int stride,
+                                         const float *scene_kp, int Ks, int kstride, const b200_shot_params *p,
+                                         float *transforms, int *inst_view, int *inst_offsets, b200_corr *inst_corrs,
+                                         int corr_cap, int max_inst, int *n_inst, int *view_n_corrs);
+
 /* Statistics of the last descriptor call on this context (for bench records): mean / max number of
  * radius neighbours per keypoint. */
 B200_API int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs);

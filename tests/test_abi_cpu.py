@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     so = builder.build()
     lib = ctypes.CDLL(so)
     names = _declared()
-    assert len(names) >= 44
+    assert len(names) >= 51
     for n in names:
         assert hasattr(lib, n), n
     binding = importlib.import_module(PKG_NAME + ".binding")

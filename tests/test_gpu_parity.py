@@ -479,3 +479,50 @@ def test_keypoint_extraction_parity(ctx, orc, synth, b200):
     assert len(ctx.uniform_sampling(np.zeros((0, 3), np.float32), 0.01)) == 0
     with pytest.raises(b200.B200Error):
         ctx.uniform_sampling(cloud, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------ multi-view library
+def test_multiview_library_registration(ctx, orc, synth, b200):
+    """BASELINE.json config 4 (scaled down): a descriptor library over partial views of the three CAD joints
+    (CAD_desc.cpp:231-370) and one scene matched against every view (the per-view loop of SHOT.cpp:243-483), the
+    scene's normals and descriptors computed once.  Per view the result must equal the single-model pipeline
+    and, on the same correspondences, the oracle's grouping."""
+    p = b200.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=512)
+    scene = synth.make_scene(("y", "horizontal"), 50000, scene_id=4)
+    kps = synth.uniform_sampling(scene, 0.03)
+    lib = b200.Library(ctx)
+    views = []
+    for joint in ("y", "diagonal", "horizontal"):
+        for v in (3, 20, 41):
+            cloud = synth.make_partial_view(joint, v, 6000)
+            kp = synth.uniform_sampling(cloud, 0.02)
+            assert lib.add_view(cloud, kp, p) == len(views)
+            views.append((cloud, kp))
+    assert lib.views == 9 and lib.view_size(4) == len(views[4][1])
+    res = lib.register_scene(scene, kps, p, max_inst=4096)
+    assert res["n_instances"] == len(res["view"]) == len(res["instances"])
+    assert np.all(np.diff(res["view"]) >= 0)
+    total = 0
+    for v, (cloud, kp) in enumerate(views):
+        m = ctx.model_create_shot(cloud, kp, p)
+        single = ctx.register_scene_shot(m, scene, kps, p)
+        mine = [i for i in range(res["n_instances"]) if res["view"][i] == v]
+        assert len(mine) == single["n_instances"] and res["view_n_corrs"][v] == len(single["corrs"])
+        for i, ins in zip(mine, single["instances"]):
+            assert res["instances"][i].tobytes() == ins.tobytes()
+        if mine:
+            assert np.array_equal(res["transforms"][mine], single["transforms"])
+        # oracle grouping on the view's correspondences
+        oT, oinst = orc.gc_recognize(kp, kps, single["corrs"], 0.02, 2, max_inst=512)
+        assert len(oT) == len(mine)
+        for i, oi in zip(mine, oinst):
+            assert res["instances"][i].tobytes() == oi.tobytes()
+        # the library's descriptors are the single-model ones
+        dl, kl = lib.download_view(v)
+        dm, km = m.download()
+        assert np.array_equal(dl, dm, equal_nan=True) and np.array_equal(kl, km)
+        total += len(mine)
+        m.close()
+    assert total == res["n_instances"] and total > 0
+    lib.close()
