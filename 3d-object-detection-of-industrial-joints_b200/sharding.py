@@ -49,3 +49,40 @@ def unpack_gathered(counts, words):
     for r in range(len(c)):
         res.append(np.ascontiguousarray(w[r, :int(c[r])]).view(dt).reshape(-1))
     return res
+
+
+def register_scene_batch(ctx, model, scenes, keypoints, params, rank=0, world=1, group=None, device=None):
+    """BASELINE.json config 5: a batch of scenes sharded round-robin over the ranks (scene s -> rank s mod world),
+    every rank registering its scenes against the replicated model library through the host-buffer C-ABI call,
+    then ONE gather of the per-scene correspondence lists.  Returns (local, gathered): `local` maps scene id ->
+    result dict of this rank's scenes (poses and instances stay on the rank that found them); `gathered` maps
+    every scene id of the batch -> its correspondence list (structured numpy array), on every rank.
+    world == 1 needs no process group."""
+    import torch
+    mine = scenes_for_rank(len(scenes), rank, world)
+    local = {s: ctx.register_scene_shot(model, scenes[s], keypoints[s], params) for s in mine}
+    if world == 1:
+        return local, {s: local[s]["corrs"] for s in mine}
+    import torch.distributed as dist
+    per_rank = (len(scenes) + world - 1) // world                      # slots per rank (padded)
+    cap = common_capacity(max([len(keypoints[s]) for s in mine] + [1]), device=device, group=group)
+    words = torch.zeros((per_rank * cap, CORR_WORDS), dtype=torch.int32, device=device)
+    counts = torch.zeros(per_rank, dtype=torch.int32, device=device)
+    for slot, s in enumerate(mine):
+        c = local[s]["corrs"]
+        if len(c):
+            words[slot * cap:slot * cap + len(c)] = torch.from_numpy(
+                np.ascontiguousarray(c).view(np.int32).reshape(-1, CORR_WORDS)).to(words.device)
+        counts[slot] = len(c)
+    all_counts = torch.empty(world * per_rank, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_words = torch.empty((world * per_rank * cap, CORR_WORDS), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(all_words, words, group=group)
+    dt = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
+    ac = all_counts.cpu().numpy().reshape(world, per_rank)
+    aw = all_words.cpu().numpy().reshape(world, per_rank, cap, CORR_WORDS)
+    gathered = {}
+    for r in range(world):
+        for slot, s in enumerate(scenes_for_rank(len(scenes), r, world)):
+            gathered[s] = np.ascontiguousarray(aw[r, slot, :int(ac[r, slot])]).view(dt).reshape(-1)
+    return local, gathered

@@ -526,3 +526,23 @@ def test_multiview_library_registration(ctx, orc, synth, b200):
         m.close()
     assert total == res["n_instances"] and total > 0
     lib.close()
+
+
+def test_scene_batch_sharding(ctx, orc, synth, b200, pkg):
+    """BASELINE.json config 5 (scaled down): a batch of scenes registered against one model; on one rank the
+    sharded driver must return every scene's correspondences, identical to direct calls."""
+    import importlib
+    sharding = importlib.import_module(pkg.__name__ + ".sharding")
+    p = b200.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=512)
+    model = synth.make_model("y", 5000)
+    m = ctx.model_create_shot(model, synth.uniform_sampling(model, 0.02), p)
+    scenes = [synth.make_scene(("y",), 20000 + 3000 * s, scene_id=20 + s) for s in range(3)]
+    kps = [synth.uniform_sampling(s, 0.03) for s in scenes]
+    local, gathered = sharding.register_scene_batch(ctx, m, scenes, kps, p)
+    assert sorted(local) == sorted(gathered) == [0, 1, 2]
+    for s in range(3):
+        direct = ctx.register_scene_shot(m, scenes[s], kps[s], p)
+        assert gathered[s].tobytes() == direct["corrs"].tobytes()
+        assert local[s]["n_instances"] == direct["n_instances"]
+    m.close()

@@ -60,6 +60,44 @@ def _worker(rank, world, port, root, pkg, out_dir):
     dist.destroy_process_group()
 
 
+class _FakeCtx:
+    """Stands in for binding.Context on CPU: returns a deterministic correspondence list per scene."""
+
+    def register_scene_shot(self, model, scene, kp, params):
+        n = int(scene[0, 0])
+        c = np.zeros(n, dtype=CORR)
+        c["index_query"] = np.arange(n) * 3
+        c["index_match"] = np.arange(n)
+        c["distance"] = np.float32(0.01) * np.arange(n, dtype=np.float32)
+        return {"corrs": c, "n_instances": 0}
+
+
+def _batch_worker(rank, world, port, root, pkg, out_dir):
+    import sys
+    sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharding = importlib.import_module(pkg + ".sharding")
+    sizes = [5, 0, 17, 9, 30]                                  # scene s yields sizes[s] correspondences
+    scenes = [np.full((4, 3), n, dtype=np.float32) for n in sizes]
+    kps = [np.zeros((max(n, 1) + 2 * i, 3), np.float32) for i, n in enumerate(sizes)]
+    local, gathered = sharding.register_scene_batch(_FakeCtx(), None, scenes, kps, None, rank=rank, world=world)
+    ok = sorted(local) == list(range(rank, len(sizes), world)) and sorted(gathered) == list(range(len(sizes)))
+    for s, n in enumerate(sizes):
+        ref = _FakeCtx().register_scene_shot(None, scenes[s], None, None)["corrs"]
+        ok = ok and gathered[s].tobytes() == ref.tobytes()
+    np.save(os.path.join(out_dir, "bok%d.npy" % rank), np.array([int(ok)]))
+    dist.destroy_process_group()
+
+
+def test_scene_batch_gloo_world2(tmp_path):
+    world = 2
+    mp.spawn(_batch_worker, args=(world, _free_port(), ROOT, PKG_NAME, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert int(np.load(tmp_path / ("bok%d.npy" % r))[0]) == 1
+
+
 def test_gather_correspondences_gloo_world2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), ROOT, PKG_NAME, str(tmp_path)), nprocs=world, join=True)
