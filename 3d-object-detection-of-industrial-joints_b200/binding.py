@@ -31,6 +31,7 @@ EXPORTS = [
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
     "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
+    "b200_hough3d_recognize",
 ]
 
 
@@ -110,6 +111,8 @@ def lib():
             "b200_dev_uniform_sampling": [vp, vp, i, i, d, vp, vp, vp],
             "b200_voxel_grid": [vp, fp, i, i, f, f, f, fp, ip],
             "b200_dev_voxel_grid": [vp, vp, i, i, f, f, f, vp, vp],
+            "b200_hough3d_recognize": [vp, fp, fp, i, i, fp, fp, i, i, C.POINTER(Corr), i, d, d, fp, i, ip, C.POINTER(Corr),
+                                       i, ip],
             "b200_library_create": [vp, C.POINTER(vp)],
             "b200_library_destroy": [vp],
             "b200_library_add_view": [vp, vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), ip],
@@ -511,6 +514,25 @@ class Context:
         rc = lib().b200_gc_recognize(self.h, _f(model_kp), len(model_kp), model_kp.shape[1], _f(scene_kp),
                                      len(scene_kp), scene_kp.shape[1], _c(corrs), len(corrs), float(gc_size),
                                      int(gc_threshold), _f(T), max_inst, _i(off), _c(oc), cap, C.byref(n))
+        if rc not in (OK, ERR_CAPACITY):
+            self._chk(rc)
+        m = min(n.value, max_inst)
+        return T[:m].reshape(m, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(m)], n.value
+
+    def hough3d_recognize(self, model_kp, model_rf, scene_kp, scene_rf, corrs, bin_size, threshold, max_inst=256):
+        model_kp, scene_kp = _pts(model_kp), _pts(scene_kp)
+        model_rf = np.ascontiguousarray(model_rf, dtype=np.float32).reshape(len(model_kp), 9)
+        scene_rf = np.ascontiguousarray(scene_rf, dtype=np.float32).reshape(len(scene_kp), 9)
+        corrs = np.ascontiguousarray(corrs, dtype=CORR_DTYPE)
+        T = np.zeros((max_inst, 16), dtype=np.float32)
+        off = np.zeros(max_inst + 1, dtype=np.int32)
+        cap = max(len(corrs), 1)
+        oc = np.zeros(cap, dtype=CORR_DTYPE)
+        n = C.c_int()
+        rc = lib().b200_hough3d_recognize(self.h, _f(model_kp), _f(model_rf), len(model_kp), model_kp.shape[1],
+                                          _f(scene_kp), _f(scene_rf), len(scene_kp), scene_kp.shape[1], _c(corrs),
+                                          len(corrs), float(bin_size), float(threshold), _f(T), max_inst, _i(off), _c(oc),
+                                          cap, C.byref(n))
         if rc not in (OK, ERR_CAPACITY):
             self._chk(rc)
         m = min(n.value, max_inst)

@@ -582,6 +582,40 @@ int b200_gc_recognize(b200_ctx *ctx, const float *model_kp, int Km, int mstride,
                             inst_corrs, corr_cap, n_inst);
 }
 
+int b200_hough3d_recognize(b200_ctx *ctx, const float *model_kp, const float *model_rf, int Km, int mstride,
+                           const float *scene_kp, const float *scene_rf, int Ks, int sstride, const b200_corr *corrs, int C,
+                           double bin_size, double threshold, float *transforms, int max_inst, int *inst_offsets,
+                           b200_corr *inst_corrs, int corr_cap, int *n_inst) {
+  API_ENTER(ctx);
+  if (!n_inst || C < 0 || max_inst < 1 || (C > 0 && (!corrs || !model_rf || !scene_rf)))
+    return ctx->fail(B200_ERR_INVALID, "hough3d_recognize: bad arguments");
+  *n_inst = 0;
+  if (inst_offsets) inst_offsets[0] = 0;
+  if (C == 0) return B200_OK;
+  for (int i = 0; i < C; ++i)
+    if (corrs[i].index_query < 0 || corrs[i].index_query >= Km || corrs[i].index_match < 0 ||
+        corrs[i].index_match >= Ks)
+      return ctx->fail(B200_ERR_INVALID, "hough3d_recognize: correspondence index out of range");
+  DevBuf<float4> dm, ds;
+  DevBuf<float> dmrf, dsrf, dT;
+  B200_TRY(upload_points(ctx, model_kp, Km, mstride, dm));
+  B200_TRY(upload_points(ctx, scene_kp, Ks, sstride, ds));
+  B200_TRY(upload(ctx, dmrf, model_rf, (size_t)Km * 9));
+  B200_TRY(upload(ctx, dsrf, scene_rf, (size_t)Ks * 9));
+  DevBuf<b200_corr> dc, dic;
+  DevBuf<int> doffs, dcnts, dn;
+  B200_TRY(upload(ctx, dc, corrs, (size_t)C));
+  B200_TRY(dic.alloc(ctx, (size_t)C));
+  B200_TRY(doffs.alloc(ctx, (size_t)max_inst + 1));
+  B200_TRY(dcnts.alloc(ctx, (size_t)max_inst));
+  B200_TRY(dn.alloc(ctx, 1));
+  B200_TRY(dT.alloc(ctx, (size_t)max_inst * 16));
+  B200_TRY(dev_hough3d(ctx, dm.p, dmrf.p, Km, ds.p, dsrf.p, dc.p, C, bin_size, threshold, dT.p, max_inst, doffs.p, dcnts.p,
+                       dic.p, C, dn.p));
+  return download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, max_inst, C, transforms, inst_offsets,
+                            inst_corrs, corr_cap, n_inst);
+}
+
 /* ------------------------------------------------------------------ resident pipeline */
 int b200_model_create_shot(b200_ctx *ctx, const float *xyz, int n, int stride, const float *kp, int K, int kstride,
                            const b200_shot_params *p, b200_model **out) {

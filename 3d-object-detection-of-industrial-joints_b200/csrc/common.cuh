@@ -308,6 +308,15 @@ int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
 // match.cu
 int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
               b200_corr *d_out, int *d_count);
+int dev_ransac_instances(b200_ctx *ctx, const b200_corr *d_corrs, const float4 *d_mp, const float4 *d_sp,
+                         const int *d_members, const int *d_inst_offsets, const int *d_n_inst, int C_cap,
+                         double threshold, float *d_T, int max_inst, int *d_inst_counts, b200_corr *d_inst_corrs,
+                         int corr_cap);
+// hough.cu
+int dev_hough3d(b200_ctx *ctx, const float4 *d_model_kp, const float *d_model_rf, int Km, const float4 *d_scene_kp,
+                const float *d_scene_rf, const b200_corr *d_corrs, int C, double bin_size, double threshold, float *d_T,
+                int max_inst, int *d_inst_offsets, int *d_inst_counts, b200_corr *d_inst_corrs, int corr_cap,
+                int *d_n_inst);
 // keypoints.cu
 int dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, float leaf, float *d_out_xyz,
                          int *d_out_index, int *d_count);

@@ -1373,7 +1373,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   DevBuf<b200_corr> sorted;
   DevBuf<float4> mp, sp;
   DevBuf<unsigned> adj;
-  DevBuf<int> overflow, members, shuffled, last_pos, flags;
+  DevBuf<int> overflow, members;
   B200_TRY(sorted.alloc(ctx, (size_t)C_eff));
   B200_TRY(mp.alloc(ctx, (size_t)C_eff));
   B200_TRY(sp.alloc(ctx, (size_t)C_eff));
@@ -1440,6 +1440,18 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
               w, h[w * 8], h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6], h[w * 8 + 7]);
   }
 
+  return dev_ransac_instances(ctx, sorted.p, mp.p, sp.p, members.p, d_inst_offsets, d_n_inst, C_eff, gc_size, d_T, max_inst,
+                              d_inst_counts, d_inst_corrs, corr_cap);
+}
+
+// RANSAC pose + correspondence filtering for a set of instances (shared by geometric-consistency and
+// Hough grouping).  corrs: the correspondence records the member indices refer to; mp / sp: model and
+// scene keypoint of every correspondence; members: concatenated member lists, inst_offsets[i]..[i+1].
+int dev_ransac_instances(b200_ctx *ctx, const b200_corr *d_corrs, const float4 *d_mp, const float4 *d_sp,
+                         const int *d_members, const int *d_inst_offsets, const int *d_n_inst, int C_cap,
+                         double threshold, float *d_T, int max_inst, int *d_inst_counts, b200_corr *d_inst_corrs,
+                         int corr_cap) {
+  DevBuf<int> shuffled, last_pos, flags;
   if (!ctx->mt_state) {
     unsigned host_state[624];
     mt19937_twisted_state(12345u, host_state);
@@ -1447,14 +1459,14 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
     B200_CUDA(ctx, cudaMemcpyAsync(ctx->mt_state, host_state, sizeof(host_state), cudaMemcpyHostToDevice, ctx->stream));
     B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  B200_TRY(shuffled.alloc(ctx, (size_t)C_eff));
-  B200_TRY(last_pos.alloc(ctx, (size_t)C_eff));
-  B200_TRY(flags.alloc(ctx, (size_t)C_eff));
+  B200_TRY(shuffled.alloc(ctx, (size_t)C_cap));
+  B200_TRY(last_pos.alloc(ctx, (size_t)C_cap));
+  B200_TRY(flags.alloc(ctx, (size_t)C_cap));
   RansacBuffers rb;
-  rb.sorted = sorted.p;
-  rb.mp = mp.p;
-  rb.sp = sp.p;
-  rb.members = members.p;
+  rb.sorted = d_corrs;
+  rb.mp = d_mp;
+  rb.sp = d_sp;
+  rb.members = d_members;
   rb.inst_offsets = d_inst_offsets;
   rb.n_inst = d_n_inst;
   rb.mt_init = ctx->mt_state;
@@ -1465,7 +1477,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   rb.inst_counts = d_inst_counts;
   rb.inst_corrs = d_inst_corrs;
   StageScope st_(ctx, ST_GC_RANSAC);
-  gc_ransac_kernel<<<max_inst, RS_THREADS, 0, ctx->stream>>>(rb, max_inst, corr_cap, gc_size, 10000);
+  gc_ransac_kernel<<<max_inst, RS_THREADS, 0, ctx->stream>>>(rb, max_inst, corr_cap, threshold, 10000);
   B200_LAUNCHED(ctx);
   return B200_OK;
 }

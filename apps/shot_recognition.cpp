@@ -10,7 +10,7 @@
 // UniformSampling runs on the CPU before the hot path).
 //
 // usage: shot_recognition <model.f32> <model_kp.f32 | us:leaf> <scene.f32> <scene_kp.f32 | us:leaf> <out_prefix>
-//                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch]
+//                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch] [gc|hough]
 // writes <out_prefix>.corr (b200_corr records), <out_prefix>.T (instances x 16 float),
 //        <out_prefix>.inst (int32 count per instance followed by the records)
 #include <pcl_b200/pcl_b200.h>
@@ -54,6 +54,7 @@ int main(int argc, char **argv) {
   const float cg_size_ = argc > 9 ? (float)atof(argv[9]) : 0.02f;
   const float cg_thresh_ = argc > 10 ? (float)atof(argv[10]) : 2.0f;
   const bool batch = argc > 11 && std::string(argv[11]) == "batch";
+  const bool use_hough = argc > 12 && std::string(argv[12]) == "hough";  // the reference's --algorithm Hough|GC
 
   pcl::PointCloud<PointType>::Ptr model(new pcl::PointCloud<PointType>()), scene(new pcl::PointCloud<PointType>());
   pcl::PointCloud<PointType>::Ptr model_keypoints(new pcl::PointCloud<PointType>()),
@@ -125,13 +126,41 @@ int main(int argc, char **argv) {
   //  Actual Clustering (GeometricConsistency branch)
   std::vector<pcl::Matrix4f> rototranslations;
   std::vector<pcl::Correspondences> clustered_corrs;
-  pcl::GeometricConsistencyGrouping<PointType, PointType> gc_clusterer;
-  gc_clusterer.setGCSize(cg_size_);
-  gc_clusterer.setGCThreshold(cg_thresh_);  // float → int, as in the reference
-  gc_clusterer.setInputCloud(model_keypoints);
-  gc_clusterer.setSceneCloud(scene_keypoints);
-  gc_clusterer.setModelSceneCorrespondences(model_scene_corrs);
-  gc_clusterer.recognize(rototranslations, clustered_corrs);
+  if (use_hough) {
+    // Hough branch (SHOT.cpp:433-470).  The reference computes BOARD frames for it; this harness passes the
+    // SHOT frames the descriptor stage produced (pcl::SHOT352::rf) — Hough3DGrouping takes any frame cloud.
+    pcl::PointCloud<pcl::ReferenceFrame>::Ptr model_rf(new pcl::PointCloud<pcl::ReferenceFrame>()),
+        scene_rf(new pcl::PointCloud<pcl::ReferenceFrame>());
+    for (int side = 0; side < 2; ++side) {
+      const pcl::PointCloud<DescriptorType> &d = side ? *scene_descriptors : *model_descriptors;
+      pcl::PointCloud<pcl::ReferenceFrame> &rf = side ? *scene_rf : *model_rf;
+      rf.resize(d.size());
+      for (size_t i = 0; i < d.size(); ++i) {
+        memcpy(rf[i].x_axis, d[i].rf + 0, 12);
+        memcpy(rf[i].y_axis, d[i].rf + 3, 12);
+        memcpy(rf[i].z_axis, d[i].rf + 6, 12);
+      }
+    }
+    pcl::Hough3DGrouping<PointType, PointType, pcl::ReferenceFrame, pcl::ReferenceFrame> clusterer;
+    clusterer.setHoughBinSize(cg_size_);
+    clusterer.setHoughThreshold(cg_thresh_);
+    clusterer.setUseInterpolation(false);
+    clusterer.setUseDistanceWeight(true);
+    clusterer.setInputCloud(model_keypoints);
+    clusterer.setInputRf(model_rf);
+    clusterer.setSceneCloud(scene_keypoints);
+    clusterer.setSceneRf(scene_rf);
+    clusterer.setModelSceneCorrespondences(model_scene_corrs);
+    clusterer.recognize(rototranslations, clustered_corrs);
+  } else {
+    pcl::GeometricConsistencyGrouping<PointType, PointType> gc_clusterer;
+    gc_clusterer.setGCSize(cg_size_);
+    gc_clusterer.setGCThreshold(cg_thresh_);  // float → int, as in the reference
+    gc_clusterer.setInputCloud(model_keypoints);
+    gc_clusterer.setSceneCloud(scene_keypoints);
+    gc_clusterer.setModelSceneCorrespondences(model_scene_corrs);
+    gc_clusterer.recognize(rototranslations, clustered_corrs);
+  }
 
   std::cout << "Model instances found: " << rototranslations.size() << std::endl;
   for (size_t i = 0; i < rototranslations.size() && i < 3; ++i) {

@@ -180,6 +180,17 @@ B200_API int b200_gc_recognize(b200_ctx *ctx, const float *model_kp, int Km, int
                       float *transforms, int max_inst, int *inst_offsets, b200_corr *inst_corrs, int corr_cap,
                       int *n_inst);
 
+/* pcl::Hough3DGrouping::recognize (the reference's default grouping: SHOT.cpp:433-470, SHOT_demo.cpp:540-577,
+ * FPFH_demo.cpp:548-585) with the reference's settings — setUseInterpolation(false), setUseDistanceWeight(true)
+ * — and the reference frames given by the caller (setInputRf / setSceneRf; K x 9 floats: x, y, z axes, e.g.
+ * from b200_shot_lrf).  bin_size = setHoughBinSize, threshold = setHoughThreshold (negative: fraction of the
+ * largest bin).  Every Hough bin reaching the threshold is an instance (ascending bin index); its voters go
+ * through the same RANSAC as in b200_gc_recognize (inlier threshold = bin size).  Outputs as b200_gc_recognize. */
+B200_API int b200_hough3d_recognize(b200_ctx *ctx, const float *model_kp, const float *model_rf, int Km, int mstride,
+                                    const float *scene_kp, const float *scene_rf, int Ks, int sstride,
+                                    const b200_corr *corrs, int C, double bin_size, double threshold, float *transforms,
+                                    int max_inst, int *inst_offsets, b200_corr *inst_corrs, int corr_cap, int *n_inst);
+
 /* ---------------------------------------------------------------- resident pipeline ------ */
 typedef struct {
   int normal_k;          /* NormalEstimationOMP::setKSearch; 0 if radius is used */

@@ -641,6 +641,89 @@ class GeometricConsistencyGrouping {
   int gc_threshold_ = 3;
 };
 
+/* pcl::Hough3DGrouping<PointModelT, PointSceneT, ReferenceFrame, ReferenceFrame> (SHOT.cpp:433-470,
+ * SHOT_demo.cpp:540-577): the reference passes the frames with setInputRf / setSceneRf and uses
+ * setUseInterpolation(false), setUseDistanceWeight(true).  Interpolated voting is not provided. */
+template <class PointModelT, class PointSceneT, class PointModelRfT = ReferenceFrame, class PointSceneRfT = ReferenceFrame>
+class Hough3DGrouping {
+ public:
+  typedef std::shared_ptr<const PointCloud<PointModelT>> PointCloudConstPtr;
+  typedef std::shared_ptr<const PointCloud<PointSceneT>> SceneCloudConstPtr;
+  typedef std::shared_ptr<const PointCloud<PointModelRfT>> ModelRfCloudConstPtr;
+  typedef std::shared_ptr<const PointCloud<PointSceneRfT>> SceneRfCloudConstPtr;
+  void setHoughBinSize(double bin_size) { bin_size_ = bin_size; }
+  void setHoughThreshold(double threshold) { threshold_ = threshold; }
+  void setUseInterpolation(bool use) { use_interpolation_ = use; }
+  void setUseDistanceWeight(bool) {} /* without interpolation PCL's weight is 1 either way (see hough.cu) */
+  void setInputCloud(const PointCloudConstPtr &cloud) { input_ = cloud; }
+  void setInputRf(const ModelRfCloudConstPtr &rf) { input_rf_ = rf; }
+  void setSceneCloud(const SceneCloudConstPtr &scene) { scene_ = scene; }
+  void setSceneRf(const SceneRfCloudConstPtr &rf) { scene_rf_ = rf; }
+  void setModelSceneCorrespondences(const CorrespondencesConstPtr &corrs) { model_scene_corrs_ = corrs; }
+  bool recognize(std::vector<Matrix4f> &transformations) {
+    std::vector<Correspondences> clustered;
+    return recognize(transformations, clustered);
+  }
+  bool recognize(std::vector<Matrix4f> &transformations, std::vector<Correspondences> &clustered_corrs) {
+    transformations.clear();
+    clustered_corrs.clear();
+    if (!input_ || !scene_ || input_->empty() || scene_->empty() || !input_rf_ || !scene_rf_ ||
+        input_rf_->size() != input_->size() || scene_rf_->size() != scene_->size()) {
+      fprintf(stderr, "[pcl_b200::Hough3DGrouping::recognize] clouds and reference frames must be set and of equal size\n");
+      return false;
+    }
+    if (use_interpolation_) {
+      fprintf(stderr, "[pcl_b200::Hough3DGrouping::recognize] interpolated voting is not provided\n");
+      return false;
+    }
+    if (!model_scene_corrs_ || model_scene_corrs_->empty()) {
+      fprintf(stderr, "[pcl_b200::Hough3DGrouping::recognize] Error! Correspondences not set\n");
+      return false;
+    }
+    if (!detail::ctx()) return false;
+    auto flatten = [](const auto &rf_cloud) {
+      std::vector<float> f(rf_cloud.size() * 9);
+      for (size_t i = 0; i < rf_cloud.size(); ++i) {
+        memcpy(&f[i * 9 + 0], rf_cloud.points[i].x_axis, 12);
+        memcpy(&f[i * 9 + 3], rf_cloud.points[i].y_axis, 12);
+        memcpy(&f[i * 9 + 6], rf_cloud.points[i].z_axis, 12);
+      }
+      return f;
+    };
+    const std::vector<float> mrf = flatten(*input_rf_), srf = flatten(*scene_rf_);
+    const int C = (int)model_scene_corrs_->size();
+    const int max_inst = C;
+    std::vector<float> T((size_t)max_inst * 16);
+    std::vector<int> off((size_t)max_inst + 1);
+    std::vector<b200_corr> out((size_t)C);
+    int n = 0;
+    const int rc = b200_hough3d_recognize(
+        detail::ctx(), detail::xyz(input_->points), mrf.data(), (int)input_->size(), detail::stride<PointModelT>(),
+        detail::xyz(scene_->points), srf.data(), (int)scene_->size(), detail::stride<PointSceneT>(),
+        reinterpret_cast<const b200_corr *>(model_scene_corrs_->data()), C, bin_size_, threshold_, T.data(), max_inst,
+        off.data(), out.data(), C, &n);
+    if (!detail::ok(rc, "Hough3DGrouping::recognize")) return false;
+    transformations.resize((size_t)n);
+    clustered_corrs.resize((size_t)n);
+    for (int i = 0; i < n; ++i) {
+      memcpy(transformations[i].m, &T[(size_t)i * 16], sizeof(float) * 16);
+      clustered_corrs[i].resize((size_t)(off[i + 1] - off[i]));
+      if (off[i + 1] > off[i])
+        memcpy(static_cast<void *>(clustered_corrs[i].data()), &out[off[i]], sizeof(b200_corr) * (size_t)(off[i + 1] - off[i]));
+    }
+    return true;
+  }
+
+ private:
+  PointCloudConstPtr input_;
+  SceneCloudConstPtr scene_;
+  ModelRfCloudConstPtr input_rf_;
+  SceneRfCloudConstPtr scene_rf_;
+  CorrespondencesConstPtr model_scene_corrs_;
+  double bin_size_ = 1.0, threshold_ = 1.0;
+  bool use_interpolation_ = false;
+};
+
 }  // namespace pcl_b200
 
 #ifdef PCL_B200_AS_PCL

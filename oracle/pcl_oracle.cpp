@@ -1049,6 +1049,34 @@ RansacResult ransac_registration(const float *model_kp, int mstride, const float
   return res;
 }
 
+
+/* RANSAC on one consensus / voter set and the filtered correspondences, appended to the outputs the way
+ * GeometricConsistencyGrouping::recognize and Hough3DGrouping::recognize do. */
+void emit_instance(const float *model_kp, int mstride, const float *scene_kp, int sstride,
+                   const std::vector<orc_corr> &temp, double threshold, float *transforms, int max_inst,
+                   int *inst_offsets, orc_corr *inst_corrs, int corr_cap, int &n_inst, int &written) {
+  RansacResult rr = ransac_registration(model_kp, mstride, scene_kp, sstride, temp, threshold, 10000);
+  std::vector<orc_corr> filtered;
+  float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  if (!rr.ok || rr.inliers.size() < 3) {
+    filtered = temp; /* identity + unfiltered set */
+  } else {
+    /* index_to_correspondence keyed by index_query: last one wins */
+    std::unordered_map<int, int> index_to_corr;
+    for (int t = 0; t < (int)temp.size(); ++t) index_to_corr[temp[t].index_query] = t;
+    for (int inl : rr.inliers) filtered.push_back(temp[index_to_corr[inl]]);
+    std::memcpy(T, rr.T, sizeof(T));
+  }
+  if (n_inst < max_inst) {
+    if (transforms) std::memcpy(transforms + (size_t)n_inst * 16, T, sizeof(T));
+    if (inst_corrs && written + (int)filtered.size() <= corr_cap) {
+      std::memcpy(inst_corrs + written, filtered.data(), filtered.size() * sizeof(orc_corr));
+      written += (int)filtered.size();
+    }
+    if (inst_offsets) inst_offsets[n_inst + 1] = written;
+  }
+  ++n_inst;
+}
 }  // namespace
 
 /* ================================================================================================
@@ -1340,27 +1368,8 @@ int orc_gc_recognize(const float *model_kp, int Km, int mstride, const float *sc
         temp.push_back(corrs[c]);
         taken[c] = 1;
       }
-      RansacResult rr = ransac_registration(model_kp, mstride, scene_kp, sstride, temp, gc_size, 10000);
-      std::vector<orc_corr> filtered;
-      float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-      if (!rr.ok || rr.inliers.size() < 3) {
-        filtered = temp; /* identity + unfiltered set */
-      } else {
-        /* index_to_correspondence keyed by index_query: last one wins */
-        std::unordered_map<int, int> index_to_corr;
-        for (int t = 0; t < (int)temp.size(); ++t) index_to_corr[temp[t].index_query] = t;
-        for (int inl : rr.inliers) filtered.push_back(temp[index_to_corr[inl]]);
-        std::memcpy(T, rr.T, sizeof(T));
-      }
-      if (n_inst < max_inst) {
-        if (transforms) std::memcpy(transforms + (size_t)n_inst * 16, T, sizeof(T));
-        if (inst_corrs && written + (int)filtered.size() <= corr_cap) {
-          std::memcpy(inst_corrs + written, filtered.data(), filtered.size() * sizeof(orc_corr));
-          written += (int)filtered.size();
-        }
-        if (inst_offsets) inst_offsets[n_inst + 1] = written;
-      }
-      ++n_inst;
+      emit_instance(model_kp, mstride, scene_kp, sstride, temp, gc_size, transforms, max_inst, inst_offsets, inst_corrs,
+                    corr_cap, n_inst, written);
     }
   }
   return n_inst;
@@ -1470,6 +1479,108 @@ int orc_voxel_grid(const float *xyz, int n, int stride, float lx, float ly, floa
       ++m;
     }
   return m;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * pcl::Hough3DGrouping::recognize (pcl 1.8 recognition/impl/cg/hough_3d.hpp + recognition/hough_3d.cpp
+ * HoughSpace3D), as the reference configures it (SHOT.cpp:433-470): reference frames given (setInputRf /
+ * setSceneRf), setUseInterpolation(false), setUseDistanceWeight(true).
+ *   train: centroid = float running sum of the model keypoints / n; model_vote_i = (x.d, y.d, z.d) with
+ *          d = centroid - keypoint_i and x, y, z the axes of keypoint i's frame.
+ *   houghVoting: scene_vote = (float) rf_x[a] * mv.x + rf_y[a] * mv.y + rf_z[a] * mv.z + scene_point[a],
+ *          widened to double; space = [min, max] per axis, bin_count = ceil((max - min) / bin); weight =
+ *          1 - distance / max_distance where max_distance is tracked only with interpolation (it stays
+ *          -FLT_MAX), i.e. 1.0; HoughSpace3D::vote drops a vote whose bin coordinate is out of range.
+ *   findMaxima: bins with value >= threshold (negative threshold: that fraction of the largest bin), in
+ *          ascending bin index, voters in voting order; then RANSAC with inlier threshold = bin size.
+ * Correspondences whose frames are not finite are skipped (PCL would index out of range with them).
+ * rf: K x 9 floats (x, y, z axes).
+ * ---------------------------------------------------------------------------------------------- */
+int orc_hough3d_recognize(const float *model_kp, const float *model_rf, int Km, int mstride, const float *scene_kp,
+                          const float *scene_rf, int Ks, int sstride, const orc_corr *corrs, int C, double bin_size,
+                          double threshold, float *transforms, int max_inst, int *inst_offsets, orc_corr *inst_corrs,
+                          int corr_cap) {
+  (void)Ks;
+  if (inst_offsets) inst_offsets[0] = 0;
+  if (C <= 0 || Km <= 0) return 0;
+  float centroid[3] = {0.f, 0.f, 0.f};
+  for (int i = 0; i < Km; ++i)
+    for (int a = 0; a < 3; ++a) centroid[a] += model_kp[(size_t)i * mstride + a];
+  for (int a = 0; a < 3; ++a) centroid[a] /= (float)Km;
+  std::vector<float> mv((size_t)Km * 3);
+  for (int i = 0; i < Km; ++i) {
+    const float *p = model_kp + (size_t)i * mstride, *r = model_rf + (size_t)i * 9;
+    const float d[3] = {centroid[0] - p[0], centroid[1] - p[1], centroid[2] - p[2]};
+    for (int a = 0; a < 3; ++a) {
+      float v = r[a * 3 + 0] * d[0];
+      v += r[a * 3 + 1] * d[1];
+      v += r[a * 3 + 2] * d[2];
+      mv[(size_t)i * 3 + a] = v;
+    }
+  }
+  std::vector<double> votes((size_t)C * 3);
+  std::vector<char> valid(C, 0);
+  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int i = 0; i < C; ++i) {
+    const float *m = &mv[(size_t)corrs[i].index_query * 3];
+    const float *r = scene_rf + (size_t)corrs[i].index_match * 9;
+    const float *sp = scene_kp + (size_t)corrs[i].index_match * sstride;
+    bool fin = true;
+    for (int a = 0; a < 3; ++a) {
+      float t = r[0 * 3 + a] * m[0];
+      t += r[1 * 3 + a] * m[1];
+      t += r[2 * 3 + a] * m[2];
+      t += sp[a];
+      votes[(size_t)i * 3 + a] = (double)t;
+      fin = fin && std::isfinite(t);
+    }
+    valid[i] = fin;
+    if (fin)
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = std::min(mn[a], votes[(size_t)i * 3 + a]);
+        mx[a] = std::max(mx[a], votes[(size_t)i * 3 + a]);
+      }
+  }
+  if (mn[0] > mx[0]) return 0;
+  long long cnt[3], total = 1;
+  for (int a = 0; a < 3; ++a) {
+    cnt[a] = (long long)std::ceil((mx[a] - mn[a]) / bin_size);
+    total *= std::max(cnt[a], 0ll);
+  }
+  if (total == 0 || total > (1ll << 27)) return total == 0 ? 0 : -1;
+  std::vector<int> space((size_t)total, 0);
+  std::vector<std::vector<int>> voters((size_t)total);
+  for (int i = 0; i < C; ++i) {
+    if (!valid[i]) continue;
+    long long index = 0, mul = 1;
+    bool in = true;
+    for (int a = 0; a < 3; ++a) {
+      const int ci = (int)std::floor((votes[(size_t)i * 3 + a] - mn[a]) / bin_size);
+      if (ci < 0 || ci >= cnt[a]) {
+        in = false;
+        break;
+      }
+      index += mul * ci;
+      mul *= cnt[a];
+    }
+    if (!in) continue;
+    space[(size_t)index] += 1; /* weight 1.0 */
+    voters[(size_t)index].push_back(i);
+  }
+  double thr = threshold;
+  if (thr < 0) {
+    const double hmax = (double)*std::max_element(space.begin(), space.end());
+    thr = (thr >= -1.0) ? -thr * hmax : hmax;
+  }
+  int n_inst = 0, written = 0;
+  for (long long b = 0; b < total; ++b) {
+    if (space[(size_t)b] <= 0 || (double)space[(size_t)b] < thr) continue;
+    std::vector<orc_corr> temp;
+    for (int v : voters[(size_t)b]) temp.push_back(corrs[v]);
+    emit_instance(model_kp, mstride, scene_kp, sstride, temp, bin_size, transforms, max_inst, inst_offsets, inst_corrs,
+                  corr_cap, n_inst, written);
+  }
+  return n_inst;
 }
 
 void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]) { umeyama3(src, dst, n, T16); }

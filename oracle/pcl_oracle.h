@@ -98,6 +98,13 @@ void orc_eigh3_f64(const double a9[9], double evals3[3], double evecs9[9]);     
 void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]);      /* rigid, no scale */
 uint32_t orc_mt19937_nth(uint32_t seed, int nth);                                    /* known-answer hook */
 
+/* pcl::Hough3DGrouping::recognize with given reference frames, no interpolation, distance weight on (the
+ * reference's default grouping, SHOT.cpp:433-470).  rf: K x 9 floats.  Outputs as orc_gc_recognize. */
+int orc_hough3d_recognize(const float *model_kp, const float *model_rf, int Km, int mstride, const float *scene_kp,
+                          const float *scene_rf, int Ks, int sstride, const orc_corr *corrs, int C, double bin_size,
+                          double threshold, float *transforms, int max_inst, int *inst_offsets, orc_corr *inst_corrs,
+                          int corr_cap);
+
 /* pcl::UniformSampling::filter (SHOT.cpp:314-323) / pcl::VoxelGrid::filter (SHOT_demo.cpp:413-417); output
  * in ascending leaf index; out_xyz has room for n x 3 floats.  Return the number of keypoints, -1 when the
  * lattice is too fine (PCL: "leaf size is too small").  See the implementation for the PCL semantics. */

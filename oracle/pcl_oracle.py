@@ -57,6 +57,9 @@ def lib():
         L.orc_gc_recognize.restype = C.c_int
         L.orc_gc_recognize.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.POINTER(Corr), C.c_int,
                                        C.c_double, C.c_int, fp, C.c_int, ip, C.POINTER(Corr), C.c_int]
+        L.orc_hough3d_recognize.restype = C.c_int
+        L.orc_hough3d_recognize.argtypes = [fp, fp, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.POINTER(Corr), C.c_int,
+                                            C.c_double, C.c_double, fp, C.c_int, ip, C.POINTER(Corr), C.c_int]
         L.orc_uniform_sampling.restype = C.c_int
         L.orc_uniform_sampling.argtypes = [fp, C.c_int, C.c_int, C.c_double, fp, ip]
         L.orc_voxel_grid.restype = C.c_int
@@ -180,6 +183,23 @@ def gc_recognize(model_kp, scene_kp, corrs, gc_size, gc_threshold, max_inst=256)
                                float(gc_size), int(gc_threshold), _f(T), max_inst, _i(off),
                                oc.ctypes.data_as(C.POINTER(Corr)), cap)
     n = min(n, max_inst)
+    return T[:n].reshape(n, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(n)]
+
+
+def hough3d_recognize(model_kp, model_rf, scene_kp, scene_rf, corrs, bin_size, threshold, max_inst=256):
+    model_kp, scene_kp = _pts(model_kp), _pts(scene_kp)
+    model_rf = np.ascontiguousarray(model_rf, dtype=np.float32).reshape(len(model_kp), 9)
+    scene_rf = np.ascontiguousarray(scene_rf, dtype=np.float32).reshape(len(scene_kp), 9)
+    corrs = np.ascontiguousarray(corrs, dtype=CORR_DTYPE)
+    T = np.zeros((max_inst, 16), dtype=np.float32)
+    off = np.zeros(max_inst + 1, dtype=np.int32)
+    cap = max(len(corrs), 1) * 2
+    oc = np.zeros(cap, dtype=CORR_DTYPE)
+    n = lib().orc_hough3d_recognize(_f(model_kp), _f(model_rf), len(model_kp), model_kp.shape[1], _f(scene_kp),
+                                    _f(scene_rf), len(scene_kp), scene_kp.shape[1],
+                                    corrs.ctypes.data_as(C.POINTER(Corr)), len(corrs), float(bin_size), float(threshold),
+                                    _f(T), max_inst, _i(off), oc.ctypes.data_as(C.POINTER(Corr)), cap)
+    n = min(max(n, 0), max_inst)
     return T[:n].reshape(n, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(n)]
 
 

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     so = builder.build()
     lib = ctypes.CDLL(so)
     names = _declared()
-    assert len(names) >= 51
+    assert len(names) >= 52
     for n in names:
         assert hasattr(lib, n), n
     binding = importlib.import_module(PKG_NAME + ".binding")

@@ -126,3 +126,29 @@ def test_shot_recognition_app_extracts_keypoints(apps, orc, synth, tmp_path):
     a = set(map(tuple, corr[["index_query", "index_match"]].tolist()))
     b = set(map(tuple, oc[["index_query", "index_match"]].tolist()))
     assert len(b) > 20 and len(a ^ b) <= max(2, 0.002 * len(b))
+
+
+@pytest.mark.gpu
+def test_shot_recognition_app_hough_branch(apps, orc, synth, tmp_path):
+    """The reference's default grouping (SHOT.cpp:433-470) through the Hough3DGrouping adapter, frames = the SHOT
+    frames of the descriptor stage; grouping on the app's own correspondences equals the restatement."""
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 30000, scene_id=3)
+    kpm, kps = synth.uniform_sampling(model, 0.02), synth.uniform_sampling(scene, 0.03)
+    for name, a in (("m", model), ("mk", kpm), ("s", scene), ("sk", kps)):
+        _write(tmp_path / (name + ".f32"), a)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([apps["shot_recognition"]] + [str(tmp_path / (n + ".f32")) for n in ("m", "mk", "s", "sk")] +
+                       [prefix, "10", "0.02", "0.25", "0.03", "3", "batch", "hough"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    corr = np.fromfile(prefix + ".corr", dtype=CORR)
+    T, inst = _read_instances(prefix)
+    rad = float(np.float32(0.02))
+    _, mrf = orc.shot352(model, orc.normals(model, k=10), kpm, rad)
+    _, srf = orc.shot352(scene, orc.normals(scene, k=10), kps, rad)
+    oT, oinst = orc.hough3d_recognize(kpm, mrf, kps, srf, corr, float(np.float32(0.03)), 3.0, max_inst=len(corr))
+    # frames agree to ~1e-6, so a vote can change bin only on a bin boundary: allow a small mismatch
+    assert abs(len(T) - len(oT)) <= max(1, len(oT) // 20)
+    same = sum(1 for x, y in zip(inst, oinst) if x.tobytes() == y.tobytes())
+    assert len(oT) == 0 or same >= 0.8 * min(len(inst), len(oinst))

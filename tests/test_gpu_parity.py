@@ -546,3 +546,32 @@ def test_scene_batch_sharding(ctx, orc, synth, b200, pkg):
         assert gathered[s].tobytes() == direct["corrs"].tobytes()
         assert local[s]["n_instances"] == direct["n_instances"]
     m.close()
+
+
+# ------------------------------------------------------------------------------------------ Hough grouping
+def test_hough3d_parity(ctx, orc, synth, small):
+    """Hough3DGrouping (the reference's default grouping, SHOT.cpp:433-470) with SHOT reference frames: same
+    instances in the same order, voters bit-exact, poses within 1e-4, against the restatement."""
+    model, scene = small
+    kpm, kps = synth.uniform_sampling(model, 0.02), synth.uniform_sampling(scene, 0.03)
+    dm, mrf = orc.shot352(model, orc.normals(model, k=10), kpm, 0.02)
+    ds, srf = orc.shot352(scene, orc.normals(scene, k=10), kps, 0.02)
+    corrs = orc.match(dm, ds, 1, 0.25)
+    assert len(corrs) > 100
+    for bin_size, thr in ((0.02, 2.0), (0.03, 3.0), (0.05, -0.5)):
+        T, inst, n = ctx.hough3d_recognize(kpm, mrf, kps, srf, corrs, bin_size, thr, max_inst=4096)
+        oT, oinst = orc.hough3d_recognize(kpm, mrf, kps, srf, corrs, bin_size, thr, max_inst=4096)
+        assert n == len(oT) and (n > 0 or thr > 2)
+        for a, b in zip(inst, oinst):
+            assert a.tobytes() == b.tobytes()
+        if n:
+            assert max(np.abs(A - B).max() for A, B in zip(T, oT)) < 1e-4
+    # NaN frames are skipped, empty input gives nothing
+    srf2 = srf.copy()
+    srf2[corrs["index_match"][:5]] = np.nan
+    T, inst, n = ctx.hough3d_recognize(kpm, mrf, kps, srf2, corrs, 0.03, 2.0, max_inst=4096)
+    oT, oinst = orc.hough3d_recognize(kpm, mrf, kps, srf2, corrs, 0.03, 2.0, max_inst=4096)
+    assert n == len(oT)
+    for a, b in zip(inst, oinst):
+        assert a.tobytes() == b.tobytes()
+    assert ctx.hough3d_recognize(kpm, mrf, kps, srf, corrs[:0], 0.03, 2.0)[2] == 0

@@ -290,3 +290,34 @@ def test_keypoint_extractors_match_harness(orc, synth):
     with pytest.raises(ValueError):
         orc.uniform_sampling(cloud, 1e-5)                       # lattice too fine (PCL: leaf size too small)
     assert len(orc.uniform_sampling(np.zeros((0, 3), np.float32), 0.01)) == 0
+
+
+def test_hough3d_recovers_known_transform(orc):
+    """Hough3DGrouping (restated): correspondences of a rigidly moved model, with consistent reference frames,
+    all vote for the moved centroid — one bin holds them, RANSAC returns the transform; outliers do not."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.Generator(np.random.PCG64(3))
+    model = rng.uniform(-0.3, 0.3, (60, 3)).astype(np.float32)
+    R = Rotation.random(random_state=5).as_matrix()
+    t = np.array([0.4, -0.2, 1.1])
+    scene_in = (model.astype(np.float64) @ R.T + t).astype(np.float32)
+    clutter = rng.uniform(-2, 2, (40, 3)).astype(np.float32)
+    scene = np.concatenate([scene_in, clutter])
+    mrf = np.stack([Rotation.random(random_state=100 + i).as_matrix() for i in range(60)]).astype(np.float32)
+    srf_in = np.einsum("nij,kj->nik", mrf.astype(np.float64), R).astype(np.float32)     # rows (axes) rotated by R
+    srf = np.concatenate([srf_in, np.stack([Rotation.random(random_state=900 + i).as_matrix() for i in range(40)])
+                          .astype(np.float32)])
+    corrs = np.zeros(80, dtype=orc.CORR_DTYPE)
+    corrs["index_query"][:60] = np.arange(60)
+    corrs["index_match"][:60] = np.arange(60)
+    corrs["index_query"][60:] = rng.integers(0, 60, 20)
+    corrs["index_match"][60:] = rng.integers(60, 100, 20)
+    corrs["distance"] = rng.uniform(0, 0.2, 80).astype(np.float32)
+    T, inst = orc.hough3d_recognize(model, mrf.reshape(-1, 9), scene, srf.reshape(-1, 9), corrs, 0.05, 5.0)
+    assert len(T) >= 1
+    b = int(np.argmax([len(i) for i in inst]))
+    assert len(inst[b]) >= 50
+    assert np.abs(T[b][:3, :3] - R).max() < 1e-3 and np.abs(T[b][:3, 3] - t).max() < 1e-3
+    # a threshold above every bin yields nothing; a relative threshold keeps only the largest bin
+    assert len(orc.hough3d_recognize(model, mrf.reshape(-1, 9), scene, srf.reshape(-1, 9), corrs, 0.05, 1000.0)[0]) == 0
+    assert len(orc.hough3d_recognize(model, mrf.reshape(-1, 9), scene, srf.reshape(-1, 9), corrs, 0.05, -1.0)[0]) == 1
