@@ -32,6 +32,7 @@ EXPORTS = [
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
     "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
     "b200_hough3d_recognize",
+    "b200_icp_align",
 ]
 
 
@@ -113,6 +114,7 @@ def lib():
             "b200_dev_voxel_grid": [vp, vp, i, i, f, f, f, vp, vp],
             "b200_hough3d_recognize": [vp, fp, fp, i, i, fp, fp, i, i, C.POINTER(Corr), i, d, d, fp, i, ip, C.POINTER(Corr),
                                        i, ip],
+            "b200_icp_align": [vp, fp, i, i, vp, i, d, d, d, fp, fp, fp, C.POINTER(d), ip, ip],
             "b200_library_create": [vp, C.POINTER(vp)],
             "b200_library_destroy": [vp],
             "b200_library_add_view": [vp, vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), ip],
@@ -537,6 +539,22 @@ class Context:
             self._chk(rc)
         m = min(n.value, max_inst)
         return T[:m].reshape(m, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(m)], n.value
+
+    def icp_align(self, source, target, max_iterations=10, max_corr_dist=0.0, transformation_epsilon=0.0,
+                  euclidean_fitness_epsilon=-1.7976931348623157e308, guess=None):
+        """pcl::IterativeClosestPoint::align (b200_icp_align).  target: a Cloud.  Returns a dict with
+        final_transform (4x4), aligned (ns x 3), fitness, converged, iterations."""
+        source = _pts(source)
+        T = np.zeros(16, dtype=np.float32)
+        al = np.zeros((max(len(source), 1), 3), dtype=np.float32)
+        g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+        fit, conv, it = C.c_double(), C.c_int(), C.c_int()
+        self._chk(lib().b200_icp_align(self.h, _f(source), len(source), source.shape[1], target.h, int(max_iterations),
+                                       float(max_corr_dist), float(transformation_epsilon),
+                                       float(euclidean_fitness_epsilon), None if g is None else _f(g), _f(T), _f(al),
+                                       C.byref(fit), C.byref(conv), C.byref(it)))
+        return {"final_transform": T.reshape(4, 4), "aligned": al[:len(source)], "fitness": fit.value,
+                "converged": bool(conv.value), "iterations": it.value}
 
     # ---- resident pipeline --------------------------------------------------------------------
     def model_create_shot(self, xyz, kp, params):

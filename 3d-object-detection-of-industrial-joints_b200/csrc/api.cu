@@ -616,6 +616,33 @@ int b200_hough3d_recognize(b200_ctx *ctx, const float *model_kp, const float *mo
                             inst_corrs, corr_cap, n_inst);
 }
 
+/* ------------------------------------------------------------------ pose refinement */
+int b200_icp_align(b200_ctx *ctx, const float *source, int ns, int sstride, b200_cloud *target, int max_iterations,
+                   double max_corr_dist, double transformation_epsilon, double euclidean_fitness_epsilon,
+                   const float *guess, float *final_transform, float *aligned, double *fitness, int *converged,
+                   int *iterations) {
+  API_ENTER(ctx);
+  if (!target || !final_transform || ns < 0 || max_iterations < 0)
+    return ctx->fail(B200_ERR_INVALID, "icp_align: bad arguments");
+  DevBuf<float4> dsrc, dal;
+  B200_TRY(upload_points(ctx, source, ns, sstride, dsrc));
+  if (aligned) B200_TRY(dal.alloc(ctx, (size_t)std::max(ns, 1)));
+  B200_TRY(dev_icp_align(ctx, dsrc.p, ns, target, max_iterations, max_corr_dist, transformation_epsilon,
+                         euclidean_fitness_epsilon, guess, final_transform, aligned ? dal.p : nullptr, fitness, converged,
+                         iterations));
+  if (aligned && ns > 0) {
+    std::vector<float4> h((size_t)ns);
+    B200_TRY(download(ctx, h.data(), dal.p, (size_t)ns));
+    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ns; ++i) {
+      aligned[3 * i + 0] = h[i].x;
+      aligned[3 * i + 1] = h[i].y;
+      aligned[3 * i + 2] = h[i].z;
+    }
+  }
+  return B200_OK;
+}
+
 /* ------------------------------------------------------------------ resident pipeline */
 int b200_model_create_shot(b200_ctx *ctx, const float *xyz, int n, int stride, const float *kp, int K, int kstride,
                            const b200_shot_params *p, b200_model **out) {

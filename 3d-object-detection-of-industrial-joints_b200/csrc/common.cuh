@@ -317,6 +317,10 @@ int dev_hough3d(b200_ctx *ctx, const float4 *d_model_kp, const float *d_model_rf
                 const float *d_scene_rf, const b200_corr *d_corrs, int C, double bin_size, double threshold, float *d_T,
                 int max_inst, int *d_inst_offsets, int *d_inst_counts, b200_corr *d_inst_corrs, int corr_cap,
                 int *d_n_inst);
+// icp.cu
+int dev_icp_align(b200_ctx *ctx, const float4 *d_src, int ns, b200_cloud *target, int max_iterations, double max_corr_dist,
+                  double transformation_epsilon, double euclidean_fitness_epsilon, const float *guess, float *final_T,
+                  float4 *d_aligned, double *fitness, int *converged, int *iterations);
 // keypoints.cu
 int dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, float leaf, float *d_out_xyz,
                          int *d_out_index, int *d_count);

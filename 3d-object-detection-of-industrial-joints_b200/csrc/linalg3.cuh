@@ -8,7 +8,7 @@
 
 // Cyclic Jacobi.  A: row-major symmetric.  w: ascending eigenvalues, V: eigenvectors in columns
 // (row-major 3x3).
-__device__ inline void eigh3_f64(const double A_in[9], double w[3], double V[9]) {
+__host__ __device__ inline void eigh3_f64(const double A_in[9], double w[3], double V[9]) {
   double a[3][3] = {{A_in[0], A_in[1], A_in[2]}, {A_in[3], A_in[4], A_in[5]}, {A_in[6], A_in[7], A_in[8]}};
   double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   for (int sweep = 0; sweep < 64; ++sweep) {
@@ -59,7 +59,7 @@ __device__ inline void eigh3_f64(const double A_in[9], double w[3], double V[9])
   }
 }
 
-__device__ __forceinline__ void cross3d(const double *a, const double *b, double *o) {
+__host__ __device__ __forceinline__ void cross3d(const double *a, const double *b, double *o) {
   o[0] = a[1] * b[2] - a[2] * b[1];
   o[1] = a[2] * b[0] - a[0] * b[2];
   o[2] = a[0] * b[1] - a[1] * b[0];
@@ -68,7 +68,10 @@ __device__ __forceinline__ void cross3d(const double *a, const double *b, double
 // Rigid (no scale) least-squares transform dst ~ R src + t of n 3-D points (row-major n x 3).
 // T: row-major 4x4.  R = U diag(1, 1, det(U) det(V)) V^T from the SVD of the cross-covariance,
 // obtained through the eigen-decomposition of S^T S.
-__device__ inline void umeyama3(const double *src, const double *dst, int n, double T[16]) {
+__host__ __device__ inline void umeyama_from_moments(const double S[9], const double ms[3], const double md[3],
+                                                     double T[16]);
+
+__host__ __device__ inline void umeyama3(const double *src, const double *dst, int n, double T[16]) {
   double ms[3] = {0, 0, 0}, md[3] = {0, 0, 0};
   for (int i = 0; i < n; ++i)
     for (int a = 0; a < 3; ++a) {
@@ -84,6 +87,14 @@ __device__ inline void umeyama3(const double *src, const double *dst, int n, dou
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) S[r * 3 + c] += (dst[i * 3 + r] - md[r]) * (src[i * 3 + c] - ms[c]);
   for (int i = 0; i < 9; ++i) S[i] /= n;
+  umeyama_from_moments(S, ms, md, T);
+}
+
+// Rigid transform from the moments of two corresponding point sets: S = cross-covariance
+// (dst - md)(src - ms)^T / n (row-major 3x3), ms / md = means.  Shared by the 3-point RANSAC models and
+// by ICP's TransformationEstimationSVD.
+__host__ __device__ inline void umeyama_from_moments(const double S[9], const double ms[3], const double md[3],
+                                                     double T[16]) {
   double StS[9];
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) {

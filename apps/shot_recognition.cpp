@@ -11,8 +11,11 @@
 //
 // usage: shot_recognition <model.f32> <model_kp.f32 | us:leaf> <scene.f32> <scene_kp.f32 | us:leaf> <out_prefix>
 //                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch] [gc|hough]
+//                         [icp:N]
 // writes <out_prefix>.corr (b200_corr records), <out_prefix>.T (instances x 16 float),
 //        <out_prefix>.inst (int32 count per instance followed by the records)
+//        with icp:N, <out_prefix>.icp (per instance, first 8: 16 float refined pose, fitness, converged) — the
+//        reference's icp_align (SHOT.cpp:177-192) on the model placed by the grouped pose
 #include <pcl_b200/pcl_b200.h>
 
 #include <cmath>
@@ -55,6 +58,7 @@ int main(int argc, char **argv) {
   const float cg_thresh_ = argc > 10 ? (float)atof(argv[10]) : 2.0f;
   const bool batch = argc > 11 && std::string(argv[11]) == "batch";
   const bool use_hough = argc > 12 && std::string(argv[12]) == "hough";  // the reference's --algorithm Hough|GC
+  const int icp_iters = (argc > 13 && std::string(argv[13]).compare(0, 4, "icp:") == 0) ? atoi(argv[13] + 4) : 0;
 
   pcl::PointCloud<PointType>::Ptr model(new pcl::PointCloud<PointType>()), scene(new pcl::PointCloud<PointType>());
   pcl::PointCloud<PointType>::Ptr model_keypoints(new pcl::PointCloud<PointType>()),
@@ -187,5 +191,24 @@ int main(int argc, char **argv) {
     if (n) fwrite(clustered_corrs[i].data(), sizeof(pcl::Correspondence), (size_t)n, f);
   }
   fclose(f);
+  if (icp_iters > 0) {
+    f = fopen((prefix + ".icp").c_str(), "wb");
+    for (size_t i = 0; i < rototranslations.size() && i < 8; ++i) {
+      pcl::IterativeClosestPoint<PointType, PointType> icp;
+      icp.setMaximumIterations(icp_iters);
+      icp.setInputSource(model);
+      icp.setInputTarget(scene);
+      pcl::PointCloud<PointType> cloud_icp;
+      icp.align(cloud_icp, rototranslations[i]);  // the reference transforms the model first; the guess does the same
+      const double score = icp.getFitnessScore();
+      if (i < 3) printf("\nICP has converged, score is %+.0e\n", score);
+      float rec[18];
+      memcpy(rec, icp.getFinalTransformation().m, sizeof(float) * 16);
+      rec[16] = (float)score;
+      rec[17] = icp.hasConverged() ? 1.f : 0.f;
+      fwrite(rec, sizeof(float), 18, f);
+    }
+    fclose(f);
+  }
   return 0;
 }

@@ -191,6 +191,23 @@ B200_API int b200_hough3d_recognize(b200_ctx *ctx, const float *model_kp, const 
                                     const b200_corr *corrs, int C, double bin_size, double threshold, float *transforms,
                                     int max_inst, int *inst_offsets, b200_corr *inst_corrs, int corr_cap, int *n_inst);
 
+/* ---------------------------------------------------------------- pose refinement -------- */
+/* pcl::IterativeClosestPoint::align + getFitnessScore with the settings the reference uses: setMaximumIterations
+ * only (SHOT.cpp:177-192: 100; SHOT_demo.cpp:604-663, FPFH_demo.cpp:611-668: 1; 6Dpose.cpp:572-609), everything
+ * else PCL's default — pass max_corr_dist <= 0 for "unlimited", transformation_epsilon = 0,
+ * euclidean_fitness_epsilon = -DBL_MAX.  source: the cloud that is moved (setInputSource: the rotated model);
+ * target: a b200_cloud (setInputTarget: the scene).  guess (nullable): row-major 4x4 initial transform.
+ * final_transform: row-major 4x4 (getFinalTransformation); aligned (nullable): ns x 3 = the source under it
+ * (the cloud align() fills); *fitness = getFitnessScore() (mean squared distance to the nearest target point);
+ * *converged = hasConverged(); *iterations = iterations run.  Per iteration: exact nearest target point of
+ * every source point (kept when d2 <= max_corr_dist^2), Umeyama (no scale) on the pairs, stop on: iteration
+ * cap, null motion within transformation_epsilon, |mse - previous mse| < 1e-12, relative mse change below
+ * euclidean_fitness_epsilon; fewer than 3 pairs ends the loop unconverged. */
+B200_API int b200_icp_align(b200_ctx *ctx, const float *source, int ns, int sstride, b200_cloud *target,
+                            int max_iterations, double max_corr_dist, double transformation_epsilon,
+                            double euclidean_fitness_epsilon, const float *guess, float *final_transform, float *aligned,
+                            double *fitness, int *converged, int *iterations);
+
 /* ---------------------------------------------------------------- resident pipeline ------ */
 typedef struct {
   int normal_k;          /* NormalEstimationOMP::setKSearch; 0 if radius is used */

@@ -724,6 +724,68 @@ class Hough3DGrouping {
   bool use_interpolation_ = false;
 };
 
+/* pcl::IterativeClosestPoint<PointSource, PointTarget> (SHOT.cpp:177-192, SHOT_demo.cpp:604-663,
+ * FPFH_demo.cpp:611-668, 6Dpose.cpp:572-609): setMaximumIterations / setInputSource / setInputTarget / align /
+ * hasConverged / getFitnessScore / getFinalTransformation, plus the setters the reference leaves at their defaults. */
+template <class PointSource, class PointTarget>
+class IterativeClosestPoint {
+ public:
+  typedef std::shared_ptr<const PointCloud<PointSource>> PointCloudSourceConstPtr;
+  typedef std::shared_ptr<const PointCloud<PointTarget>> PointCloudTargetConstPtr;
+  void setMaximumIterations(int n) { max_iterations_ = n; }
+  int getMaximumIterations() const { return max_iterations_; }
+  void setMaxCorrespondenceDistance(double d) { corr_dist_threshold_ = d; }
+  void setTransformationEpsilon(double e) { transformation_epsilon_ = e; }
+  void setEuclideanFitnessEpsilon(double e) { euclidean_fitness_epsilon_ = e; }
+  void setInputSource(const PointCloudSourceConstPtr &cloud) { source_ = cloud; }
+  void setInputTarget(const PointCloudTargetConstPtr &cloud) {
+    target_ = cloud;
+    surf_.bind(cloud, "IterativeClosestPoint::setInputTarget");
+  }
+  void align(PointCloud<PointSource> &output) { align(output, Matrix4f()); }
+  void align(PointCloud<PointSource> &output, const Matrix4f &guess) {
+    converged_ = false;
+    final_transformation_ = guess;
+    fitness_ = 1.7976931348623157e308;
+    if (!source_ || source_->empty() || !surf_.c) {
+      fprintf(stderr, "[pcl_b200::IterativeClosestPoint::align] source or target cloud not set\n");
+      return;
+    }
+    if (!detail::ctx()) return;
+    const int ns = (int)source_->size();
+    std::vector<float> al((size_t)ns * 3);
+    int conv = 0, it = 0;
+    if (!detail::ok(b200_icp_align(detail::ctx(), detail::xyz(source_->points), ns, detail::stride<PointSource>(), surf_.c,
+                                   max_iterations_, corr_dist_threshold_, transformation_epsilon_,
+                                   euclidean_fitness_epsilon_, guess.m, final_transformation_.m, al.data(), &fitness_,
+                                   &conv, &it),
+                    "IterativeClosestPoint::align"))
+      return;
+    converged_ = conv != 0;
+    output = *source_; /* PCL copies the source's fields and overwrites x, y, z */
+    for (int i = 0; i < ns; ++i) {
+      output.points[(size_t)i].x = al[3 * (size_t)i + 0];
+      output.points[(size_t)i].y = al[3 * (size_t)i + 1];
+      output.points[(size_t)i].z = al[3 * (size_t)i + 2];
+    }
+  }
+  bool hasConverged() const { return converged_; }
+  double getFitnessScore() const { return fitness_; }
+  Matrix4f getFinalTransformation() const { return final_transformation_; }
+
+ private:
+  PointCloudSourceConstPtr source_;
+  PointCloudTargetConstPtr target_;
+  detail::Surface surf_;
+  int max_iterations_ = 10;
+  double corr_dist_threshold_ = 0.0; /* <= 0: PCL's default sqrt(DBL_MAX), i.e. unlimited */
+  double transformation_epsilon_ = 0.0;
+  double euclidean_fitness_epsilon_ = -1.7976931348623157e308;
+  bool converged_ = false;
+  double fitness_ = 1.7976931348623157e308;
+  Matrix4f final_transformation_;
+};
+
 }  // namespace pcl_b200
 
 #ifdef PCL_B200_AS_PCL

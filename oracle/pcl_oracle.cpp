@@ -1583,6 +1583,147 @@ int orc_hough3d_recognize(const float *model_kp, const float *model_rf, int Km, 
   return n_inst;
 }
 
+/* pcl::IterativeClosestPoint<PointT, PointT, float>::align + getFitnessScore (pcl 1.8 registration/impl/icp.hpp
+ * computeTransformation, default_convergence_criteria.hpp hasConverged, registration.hpp getFitnessScore) as
+ * the reference configures it: setMaximumIterations only (SHOT.cpp:177-192, SHOT_demo.cpp:604-663).
+ * Correspondences: nearest target point of every source point (brute force, L2_Simple float, lowest index on
+ * ties), kept when d2 <= max_dist^2.  The rigid fit is pcl::umeyama without scaling; PCL evaluates it in
+ * float32 through Eigen's JacobiSVD, here it is the float64 umeyama3 cast to float (agreement to float32
+ * rounding, not bit for bit — tests use a tolerance). */
+int orc_icp_align(const float *source, int ns, int sstride, const float *target, int nt, int tstride, int max_iterations,
+                  double max_corr_dist, double transformation_epsilon, double euclidean_fitness_epsilon,
+                  const float *guess, float *final_T, float *aligned, double *fitness, int *converged, int *iterations) {
+  float fin[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  if (guess) memcpy(fin, guess, sizeof(fin));
+  memcpy(final_T, fin, sizeof(fin));
+  if (converged) *converged = 0;
+  if (iterations) *iterations = 0;
+  if (fitness) *fitness = DBL_MAX;
+  std::vector<float> src, cur, tgt;
+  for (int i = 0; i < ns; ++i) {
+    const float *p = source + (size_t)i * sstride;
+    if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) src.insert(src.end(), p, p + 3);
+  }
+  for (int i = 0; i < nt; ++i) {
+    const float *p = target + (size_t)i * tstride;
+    if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) tgt.insert(tgt.end(), p, p + 3);
+  }
+  const int n = (int)src.size() / 3, m = (int)tgt.size() / 3;
+  if (n == 0 || m == 0) return 0;
+  auto apply = [](const float *T, std::vector<float> &pts) {
+    for (size_t i = 0; i < pts.size() / 3; ++i) {
+      const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+      for (int r = 0; r < 3; ++r) {
+        float v = T[r * 4 + 0] * x;
+        v += T[r * 4 + 1] * y;
+        v += T[r * 4 + 2] * z;
+        v += T[r * 4 + 3];
+        pts[3 * i + r] = v;
+      }
+    }
+  };
+  std::vector<int> nn((size_t)n);
+  std::vector<float> nd((size_t)n);
+  auto nearest = [&](const std::vector<float> &pts) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int best = -1;
+      float bd = 0.f;
+      for (int j = 0; j < m; ++j) {
+        const float d = sqdist3(&pts[3 * (size_t)i], &tgt[3 * (size_t)j]);
+        if (best < 0 || d < bd) {
+          best = j;
+          bd = d;
+        }
+      }
+      nn[i] = best;
+      nd[i] = bd;
+    }
+  };
+  cur = src;
+  apply(fin, cur);
+  const double md = (max_corr_dist > 0.0) ? max_corr_dist : std::sqrt(DBL_MAX);
+  const double max_d2 = md * md;
+  const double rotation_threshold = 1.0 - transformation_epsilon, translation_threshold = transformation_epsilon;
+  double prev_mse = DBL_MAX;
+  int it = 0;
+  bool conv = false;
+  std::vector<double> a, b;
+  for (;;) {
+    nearest(cur);
+    a.clear();
+    b.clear();
+    double sum_d = 0.0;
+    for (int i = 0; i < n; ++i) {
+      if ((double)nd[i] > max_d2) continue;
+      for (int k = 0; k < 3; ++k) {
+        a.push_back(cur[3 * (size_t)i + k]);
+        b.push_back(tgt[3 * (size_t)nn[i] + k]);
+      }
+      sum_d += (double)nd[i];
+    }
+    const int cnt = (int)a.size() / 3;
+    if (cnt < 3) break; /* NO_CORRESPONDENCES: converged_ stays false */
+    double Td[16];
+    umeyama3(a.data(), b.data(), cnt, Td);
+    float T[16];
+    for (int k = 0; k < 16; ++k) T[k] = (float)Td[k];
+    apply(T, cur);
+    float nf[16];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        float v = T[r * 4 + 0] * fin[0 * 4 + c];
+        v += T[r * 4 + 1] * fin[1 * 4 + c];
+        v += T[r * 4 + 2] * fin[2 * 4 + c];
+        v += T[r * 4 + 3] * fin[3 * 4 + c];
+        nf[r * 4 + c] = v;
+      }
+    memcpy(fin, nf, sizeof(fin));
+    ++it;
+    if (it >= max_iterations) {
+      conv = true;
+      break;
+    }
+    const double cos_angle = 0.5 * ((double)T[0] + (double)T[5] + (double)T[10] - 1.0);
+    const double tr2 = (double)T[3] * T[3] + (double)T[7] * T[7] + (double)T[11] * T[11];
+    if (cos_angle >= rotation_threshold && tr2 <= translation_threshold) {
+      conv = true;
+      break;
+    }
+    const double mse = sum_d / cnt;
+    if (std::fabs(mse - prev_mse) < 1e-12) {
+      conv = true;
+      break;
+    }
+    if (std::fabs(mse - prev_mse) / prev_mse < euclidean_fitness_epsilon) {
+      conv = true;
+      break;
+    }
+    prev_mse = mse;
+  }
+  memcpy(final_T, fin, sizeof(fin));
+  if (converged) *converged = conv ? 1 : 0;
+  if (iterations) *iterations = it;
+  cur = src;
+  apply(fin, cur);
+  if (aligned) { /* rows of non-finite source points stay NaN */
+    int k = 0;
+    for (int i = 0; i < ns; ++i) {
+      const float *p = source + (size_t)i * sstride;
+      const bool ok = std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]);
+      for (int c = 0; c < 3; ++c) aligned[3 * (size_t)i + c] = ok ? cur[3 * (size_t)k + c] : NAN;
+      if (ok) ++k;
+    }
+  }
+  if (fitness) {
+    nearest(cur);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += (double)nd[i];
+    *fitness = s / n;
+  }
+  return 0;
+}
+
 void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]) { umeyama3(src, dst, n, T16); }
 uint32_t orc_mt19937_nth(uint32_t seed, int nth) {
   std::mt19937 rng(seed);

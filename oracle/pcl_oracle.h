@@ -105,6 +105,13 @@ int orc_hough3d_recognize(const float *model_kp, const float *model_rf, int Km, 
                           double threshold, float *transforms, int max_inst, int *inst_offsets, orc_corr *inst_corrs,
                           int corr_cap);
 
+/* pcl::IterativeClosestPoint::align + getFitnessScore (SHOT.cpp:177-192, SHOT_demo.cpp:604-663).  PCL defaults:
+ * max_corr_dist <= 0 = unlimited, transformation_epsilon 0, euclidean_fitness_epsilon -DBL_MAX.  final_T: row-major
+ * 4x4; aligned (nullable): ns x 3. */
+int orc_icp_align(const float *source, int ns, int sstride, const float *target, int nt, int tstride, int max_iterations,
+                  double max_corr_dist, double transformation_epsilon, double euclidean_fitness_epsilon,
+                  const float *guess, float *final_T, float *aligned, double *fitness, int *converged, int *iterations);
+
 /* pcl::UniformSampling::filter (SHOT.cpp:314-323) / pcl::VoxelGrid::filter (SHOT_demo.cpp:413-417); output
  * in ascending leaf index; out_xyz has room for n x 3 floats.  Return the number of keypoints, -1 when the
  * lattice is too fine (PCL: "leaf size is too small").  See the implementation for the PCL semantics. */

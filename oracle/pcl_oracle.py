@@ -57,6 +57,9 @@ def lib():
         L.orc_gc_recognize.restype = C.c_int
         L.orc_gc_recognize.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.POINTER(Corr), C.c_int,
                                        C.c_double, C.c_int, fp, C.c_int, ip, C.POINTER(Corr), C.c_int]
+        L.orc_icp_align.restype = C.c_int
+        L.orc_icp_align.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                    C.c_double, fp, fp, fp, C.POINTER(C.c_double), ip, ip]
         L.orc_hough3d_recognize.restype = C.c_int
         L.orc_hough3d_recognize.argtypes = [fp, fp, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.POINTER(Corr), C.c_int,
                                             C.c_double, C.c_double, fp, C.c_int, ip, C.POINTER(Corr), C.c_int]
@@ -201,6 +204,21 @@ def hough3d_recognize(model_kp, model_rf, scene_kp, scene_rf, corrs, bin_size, t
                                     _f(T), max_inst, _i(off), oc.ctypes.data_as(C.POINTER(Corr)), cap)
     n = min(max(n, 0), max_inst)
     return T[:n].reshape(n, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(n)]
+
+
+def icp_align(source, target, max_iterations=10, max_corr_dist=0.0, transformation_epsilon=0.0,
+              euclidean_fitness_epsilon=-1.7976931348623157e308, guess=None):
+    source, target = _pts(source), _pts(target)
+    T = np.zeros(16, dtype=np.float32)
+    al = np.zeros((max(len(source), 1), 3), dtype=np.float32)
+    g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+    fit, conv, it = C.c_double(), C.c_int(), C.c_int()
+    lib().orc_icp_align(_f(source), len(source), source.shape[1], _f(target), len(target), target.shape[1],
+                        int(max_iterations), float(max_corr_dist), float(transformation_epsilon),
+                        float(euclidean_fitness_epsilon), None if g is None else _f(g), _f(T), _f(al), C.byref(fit),
+                        C.byref(conv), C.byref(it))
+    return {"final_transform": T.reshape(4, 4), "aligned": al[:len(source)], "fitness": fit.value,
+            "converged": bool(conv.value), "iterations": it.value}
 
 
 def uniform_sampling(xyz, leaf, return_index=False):

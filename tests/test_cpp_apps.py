@@ -152,3 +152,27 @@ def test_shot_recognition_app_hough_branch(apps, orc, synth, tmp_path):
     assert abs(len(T) - len(oT)) <= max(1, len(oT) // 20)
     same = sum(1 for x, y in zip(inst, oinst) if x.tobytes() == y.tobytes())
     assert len(oT) == 0 or same >= 0.8 * min(len(inst), len(oinst))
+
+
+@pytest.mark.gpu
+def test_shot_recognition_app_icp_refinement(apps, orc, synth, tmp_path):
+    """`icp:N`: the reference's icp_align (SHOT.cpp:177-192) through the IterativeClosestPoint adapter, on the model
+    placed by each grouped pose; equals the restatement started from the app's own poses."""
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 30000, scene_id=3)
+    kpm, kps = synth.uniform_sampling(model, 0.02), synth.uniform_sampling(scene, 0.03)
+    for name, a in (("m", model), ("mk", kpm), ("s", scene), ("sk", kps)):
+        _write(tmp_path / (name + ".f32"), a)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([apps["shot_recognition"]] + [str(tmp_path / (n + ".f32")) for n in ("m", "mk", "s", "sk")] +
+                       [prefix, "10", "0.02", "0.25", "0.02", "2", "batch", "gc", "icp:4"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    T, _ = _read_instances(prefix)
+    rec = np.fromfile(prefix + ".icp", dtype=np.float32).reshape(-1, 18)
+    assert len(rec) == min(len(T), 8) and len(rec) >= 1
+    assert "ICP has converged, score is" in r.stdout
+    for i in range(min(len(rec), 3)):
+        o = orc.icp_align(model, scene, max_iterations=4, guess=T[i])
+        assert np.abs(rec[i, :16].reshape(4, 4) - o["final_transform"]).max() < 1e-4
+        assert abs(rec[i, 16] - o["fitness"]) <= 1e-3 * o["fitness"] and rec[i, 17] == float(o["converged"])

@@ -575,3 +575,55 @@ def test_hough3d_parity(ctx, orc, synth, small):
     for a, b in zip(inst, oinst):
         assert a.tobytes() == b.tobytes()
     assert ctx.hough3d_recognize(kpm, mrf, kps, srf, corrs[:0], 0.03, 2.0)[2] == 0
+
+
+# ------------------------------------------------------------------------------------------ ICP
+def test_icp_parity(ctx, orc, synth, small):
+    """IterativeClosestPoint::align / getFitnessScore (SHOT.cpp:177-192: the model placed by a grouped pose is
+    refined against the scene).  Same iteration counts and convergence flags as the restatement, final transforms
+    within 1e-4 m / 0.01 degrees, fitness within 1e-4 relative (the rigid fit is float64 on both sides; the
+    nearest-neighbour sets are exact, so the iterates agree to float32 rounding)."""
+    from scipy.spatial.transform import Rotation
+    model, scene = small
+    _, poses = synth.make_scene(("y",), 40000, scene_id=1, return_poses=True)
+    Tgt = np.asarray(poses[0], dtype=np.float64)
+    # perturb the true pose the way a grouped pose is off: ~1 degree, a few millimetres
+    dR = Rotation.from_rotvec([0.012, -0.015, 0.01]).as_matrix()
+    G = Tgt.copy()
+    G[:3, :3] = dR @ Tgt[:3, :3]
+    G[:3, 3] = dR @ Tgt[:3, 3] + [0.003, -0.002, 0.002]
+    placed = (model.astype(np.float64) @ G[:3, :3].T + G[:3, 3]).astype(np.float32)
+    tgt = ctx.cloud(scene)
+    for iters in (1, 5, 30):
+        a = ctx.icp_align(placed, tgt, max_iterations=iters)
+        b = orc.icp_align(placed, scene, max_iterations=iters)
+        assert a["iterations"] == b["iterations"] and a["converged"] == b["converged"]
+        assert np.abs(a["final_transform"][:3, 3] - b["final_transform"][:3, 3]).max() < 1e-4
+        assert _rot_angle_deg(a["final_transform"][:3, :3], b["final_transform"][:3, :3]) < 0.01
+        assert abs(a["fitness"] - b["fitness"]) <= 1e-4 * b["fitness"]
+        assert np.abs(a["aligned"] - b["aligned"]).max() < 2e-4
+    # refinement reduces the error of the perturbed pose
+    err0 = np.abs(placed - (model.astype(np.float64) @ Tgt[:3, :3].T + Tgt[:3, 3])).max()
+    err1 = np.abs(a["aligned"] - (model.astype(np.float64) @ Tgt[:3, :3].T + Tgt[:3, 3])).max()
+    assert err1 < err0
+    # guess = the pose itself, source = the untransformed model (what the adapters' align(output, guess) does)
+    a = ctx.icp_align(model, tgt, max_iterations=5, guess=G.astype(np.float32))
+    b = orc.icp_align(model, scene, max_iterations=5, guess=G.astype(np.float32))
+    assert a["iterations"] == b["iterations"] == 5
+    assert np.abs(a["final_transform"] - b["final_transform"]).max() < 1e-4
+    # distance gate: only pairs within 5 mm are used; a gate nothing passes ends unconverged with the guess
+    a = ctx.icp_align(placed, tgt, max_iterations=5, max_corr_dist=0.005)
+    b = orc.icp_align(placed, scene, max_iterations=5, max_corr_dist=0.005)
+    assert a["iterations"] == b["iterations"]
+    assert np.abs(a["final_transform"] - b["final_transform"]).max() < 1e-4
+    far = ctx.icp_align(placed + 10.0, tgt, max_iterations=5, max_corr_dist=0.01)
+    assert not far["converged"] and far["iterations"] == 0 and np.array_equal(far["final_transform"], np.eye(4))
+    # NaN source rows are ignored and stay NaN in the aligned cloud; an empty source is a no-op
+    p2 = placed.copy()
+    p2[7] = np.nan
+    a = ctx.icp_align(p2, tgt, max_iterations=3)
+    b = orc.icp_align(p2, scene, max_iterations=3)
+    assert np.isnan(a["aligned"][7]).all() and np.abs(a["final_transform"] - b["final_transform"]).max() < 1e-4
+    e = ctx.icp_align(np.zeros((0, 3), np.float32), tgt, max_iterations=3)
+    assert e["iterations"] == 0 and np.array_equal(e["final_transform"], np.eye(4))
+    tgt.close()

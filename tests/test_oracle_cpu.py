@@ -321,3 +321,35 @@ def test_hough3d_recovers_known_transform(orc):
     # a threshold above every bin yields nothing; a relative threshold keeps only the largest bin
     assert len(orc.hough3d_recognize(model, mrf.reshape(-1, 9), scene, srf.reshape(-1, 9), corrs, 0.05, 1000.0)[0]) == 0
     assert len(orc.hough3d_recognize(model, mrf.reshape(-1, 9), scene, srf.reshape(-1, 9), corrs, 0.05, -1.0)[0]) == 1
+
+
+def test_icp_recovers_small_motion(orc):
+    """IterativeClosestPoint (restated): a dense surface moved by a small rigid motion is pulled back; the
+    convergence rules follow pcl::registration::DefaultConvergenceCriteria as ICP configures it."""
+    from scipy.spatial.transform import Rotation
+    from importlib import import_module
+    synth = import_module("3d-object-detection-of-industrial-joints_b200.synth")
+    model = synth.make_model("y", n=3000, seed=2)[:, :3]
+    R = Rotation.from_rotvec([0.02, -0.03, 0.025]).as_matrix()
+    t = np.array([0.004, -0.003, 0.002])
+    moved = (model.astype(np.float64) @ R.T + t).astype(np.float32)
+    # iteration cap: exactly max_iterations, "converged" (PCL reports ITERATIONS as convergence)
+    r1 = orc.icp_align(moved[::3], model, max_iterations=1)
+    assert r1["iterations"] == 1 and r1["converged"]
+    r = orc.icp_align(moved[::3], model, max_iterations=100)
+    assert r["converged"] and 1 < r["iterations"] <= 100
+    assert r["fitness"] < r1["fitness"]
+    Tinv = np.eye(4)
+    Tinv[:3, :3], Tinv[:3, 3] = R.T, -R.T @ t
+    assert np.abs(r["final_transform"] - Tinv).max() < 2e-3
+    # aligned = source under the final transform
+    ref = moved[::3].astype(np.float64) @ r["final_transform"][:3, :3].astype(np.float64).T + r["final_transform"][:3, 3]
+    assert np.abs(r["aligned"] - ref).max() < 1e-5
+    # a distance gate nothing passes: fewer than 3 correspondences, not converged, identity
+    far = orc.icp_align(moved[::3] + 10.0, model, max_iterations=5, max_corr_dist=0.01)
+    assert not far["converged"] and far["iterations"] == 0 and np.array_equal(far["final_transform"], np.eye(4))
+    # the guess is applied first and is part of the final transformation
+    g = np.eye(4, dtype=np.float32)
+    g[:3, 3] = [-0.004, 0.003, -0.002]
+    rg = orc.icp_align(moved[::3], model, max_iterations=100, guess=g)
+    assert np.abs(rg["final_transform"] - Tinv).max() < 2e-3
