@@ -86,3 +86,66 @@ def register_scene_batch(ctx, model, scenes, keypoints, params, rank=0, world=1,
         for slot, s in enumerate(scenes_for_rank(len(scenes), r, world)):
             gathered[s] = np.ascontiguousarray(aw[r, slot, :int(ac[r, slot])]).view(dt).reshape(-1)
     return local, gathered
+
+
+class Turnstile:
+    """Runs callables in global step order no matter which host thread reaches its step first.  The ranks of a
+    job must issue their collectives in the same order; with several lanes per rank the host threads race, so
+    each lane takes its turn here before it enqueues the gather of step s."""
+
+    def __init__(self):
+        import threading
+        self._cv = threading.Condition()
+        self._next = 0
+        self._failed = False
+
+    def reset(self, first=0):
+        with self._cv:
+            self._next, self._failed = first, False
+
+    def abort(self):
+        with self._cv:
+            self._failed = True
+            self._cv.notify_all()
+
+    def run(self, step, fn):
+        with self._cv:
+            while self._next != step and not self._failed:
+                self._cv.wait()
+            if self._failed:
+                raise RuntimeError("turnstile aborted: another lane failed")
+            try:
+                return fn()
+            finally:
+                self._next = step + 1
+                self._cv.notify_all()
+
+
+def run_lanes(n_lanes, n_steps, step_fn, first_step=0):
+    """Scenes within one rank are independent too: lane l (one host thread driving its own b200 context and
+    CUDA stream) runs steps l, l + n_lanes, ... of `n_steps`, so that the latency-bound grouping stage of one
+    scene (8 SMs) overlaps the wide stages of the next ones on the rest of the GPU.  step_fn(lane, step) is
+    called on the lane's thread; exceptions are re-raised on the caller's thread.  Returns after every lane has
+    issued (not necessarily completed) its steps."""
+    import threading
+    errors = []
+
+    def work(lane):
+        try:
+            for s in range(first_step + lane, first_step + n_steps, n_lanes):
+                if errors:
+                    break
+                step_fn(lane, s)
+        except BaseException as e:  # noqa: BLE001 - re-raised below
+            errors.append(e)
+
+    if n_lanes == 1:
+        work(0)
+    else:
+        threads = [threading.Thread(target=work, args=(l,), name="b200-lane-%d" % l) for l in range(n_lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]

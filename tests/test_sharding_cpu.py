@@ -113,3 +113,52 @@ def test_bench_reference_arm_only_rank0(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _lanes_worker(rank, world, port, root, pkg, out_dir):
+    import random
+    import sys
+    import time
+    sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharding = importlib.import_module(pkg + ".sharding")
+    n_lanes, n_steps, cap = 3, 10, 16
+    gate = sharding.Turnstile()
+    results = {}
+    rnd = random.Random(17 * rank + 1)
+    delays = [rnd.uniform(0.0, 0.02) for _ in range(n_steps)]   # lanes reach their steps in a different order per rank
+
+    def step(lane, s):
+        time.sleep(delays[s])
+        n = (s * 5 + rank * 3) % cap
+        words = torch.full((cap, 3), -1, dtype=torch.int32)
+        words[:n] = 1000 * s + rank
+        count = torch.tensor([n], dtype=torch.int32)
+        results[s] = gate.run(s, lambda: sharding.gather_correspondences(words, count))
+
+    sharding.run_lanes(n_lanes, n_steps, step)
+    ok = sorted(results) == list(range(n_steps))
+    for s in range(n_steps):
+        counts, words = results[s]
+        for r in range(world):
+            n = (s * 5 + r * 3) % cap
+            ok = ok and int(counts[r]) == n and bool((words[r, :n] == 1000 * s + r).all())
+    # an exception on one lane is re-raised on the caller's thread
+    try:
+        sharding.run_lanes(2, 4, lambda lane, s: (_ for _ in ()).throw(ValueError("boom")) if s == 1 else None)
+        ok = False
+    except ValueError:
+        pass
+    np.save(os.path.join(out_dir, "lok%d.npy" % rank), np.array([int(ok)]))
+    dist.destroy_process_group()
+
+
+def test_lanes_keep_collective_order_gloo_world2(tmp_path):
+    """Several lanes (host threads) per rank: the per-step gather is issued in global step order on every rank
+    (Turnstile), whatever order the lanes reach it in."""
+    world = 2
+    mp.spawn(_lanes_worker, args=(world, _free_port(), ROOT, PKG_NAME, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert int(np.load(tmp_path / ("lok%d.npy" % r))[0]) == 1
