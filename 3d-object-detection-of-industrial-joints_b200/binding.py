@@ -33,6 +33,9 @@ EXPORTS = [
     "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
     "b200_hough3d_recognize",
     "b200_icp_align",
+    "b200_board_params_default",
+    "b200_ctx_srand",
+    "b200_board_lrf",
 ]
 
 
@@ -56,6 +59,18 @@ def shot_params(normal_k=10, normal_radius=0.0, descr_radius=0.02, match_mode=1,
                 gc_threshold=2, max_instances=256):
     return ShotParams(int(normal_k), float(normal_radius), float(descr_radius), int(match_mode), float(match_thr),
                       float(gc_size), int(gc_threshold), int(max_instances))
+
+
+class BoardParams(C.Structure):
+    _fields_ = [("find_holes", C.c_int), ("tangent_radius", C.c_float), ("margin_thresh", C.c_float),
+                ("check_margin_array_size", C.c_int), ("hole_size_prob_thresh", C.c_float), ("steep_thresh", C.c_float)]
+
+
+def board_params(find_holes=True, tangent_radius=0.0, margin_thresh=0.85, check_margin_array_size=24,
+                 hole_size_prob_thresh=0.2, steep_thresh=0.1):
+    """PCL's constructor defaults, with find_holes as the reference sets it (SHOT.cpp:442)."""
+    return BoardParams(int(find_holes), float(tangent_radius), float(margin_thresh), int(check_margin_array_size),
+                       float(hole_size_prob_thresh), float(steep_thresh))
 
 
 def lib():
@@ -114,6 +129,9 @@ def lib():
             "b200_dev_voxel_grid": [vp, vp, i, i, f, f, f, vp, vp],
             "b200_hough3d_recognize": [vp, fp, fp, i, i, fp, fp, i, i, C.POINTER(Corr), i, d, d, fp, i, ip, C.POINTER(Corr),
                                        i, ip],
+            "b200_board_params_default": [C.POINTER(BoardParams)],
+            "b200_ctx_srand": [vp, C.c_uint],
+            "b200_board_lrf": [vp, vp, fp, fp, i, i, d, C.POINTER(BoardParams), fp],
             "b200_icp_align": [vp, fp, i, i, vp, i, d, d, d, fp, fp, fp, C.POINTER(d), ip, ip],
             "b200_library_create": [vp, C.POINTER(vp)],
             "b200_library_destroy": [vp],
@@ -128,6 +146,7 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        L.b200_board_params_default.restype = None
         L.b200_last_error.argtypes = [vp]
         L.b200_last_error.restype = C.c_char_p
         L.b200_ctx_stage_name.argtypes = [i]
@@ -539,6 +558,20 @@ class Context:
             self._chk(rc)
         m = min(n.value, max_inst)
         return T[:m].reshape(m, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(m)], n.value
+
+    def srand(self, seed):
+        """Reseeds the context's rand() stream (BOARD's random axis), like srand(seed) for PCL."""
+        self._chk(lib().b200_ctx_srand(self.h, int(seed)))
+
+    def board_lrf(self, cloud, normals, kp, radius, params=None):
+        """pcl::BOARDLocalReferenceFrameEstimation::compute (b200_board_lrf).  Returns K x 9 frames."""
+        kp = _pts(kp)
+        normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(cloud.n, 4)
+        params = params or board_params()
+        out = np.zeros((max(len(kp), 1), 9), dtype=np.float32)
+        self._chk(lib().b200_board_lrf(self.h, cloud.h, _f(normals), _f(kp), len(kp), kp.shape[1], float(radius),
+                                       C.byref(params), _f(out)))
+        return out[:len(kp)]
 
     def icp_align(self, source, target, max_iterations=10, max_corr_dist=0.0, transformation_epsilon=0.0,
                   euclidean_fitness_epsilon=-1.7976931348623157e308, guess=None):

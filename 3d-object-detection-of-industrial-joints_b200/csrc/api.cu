@@ -616,6 +616,38 @@ int b200_hough3d_recognize(b200_ctx *ctx, const float *model_kp, const float *mo
                             inst_corrs, corr_cap, n_inst);
 }
 
+/* ------------------------------------------------------------------ BOARD frames */
+void b200_board_params_default(b200_board_params *p) {
+  if (!p) return;
+  p->find_holes = 0;
+  p->tangent_radius = 0.0f;
+  p->margin_thresh = 0.85f;
+  p->check_margin_array_size = 24;
+  p->hole_size_prob_thresh = 0.2f;
+  p->steep_thresh = 0.1f;
+}
+
+int b200_ctx_srand(b200_ctx *ctx, unsigned seed) {
+  API_ENTER(ctx);
+  board_rand_seed(ctx, seed);
+  return B200_OK;
+}
+
+int b200_board_lrf(b200_ctx *ctx, b200_cloud *surface, const float *normals, const float *kp, int K, int kstride,
+                   double radius, const b200_board_params *p, float *rf) {
+  API_ENTER(ctx);
+  if (!surface || !normals || !p || K < 0 || (K > 0 && !rf)) return ctx->fail(B200_ERR_INVALID, "board_lrf: bad arguments");
+  DevBuf<float4> dkp;
+  B200_TRY(upload_points(ctx, kp, K, kstride, dkp));
+  DevBuf<float> dn, drf;
+  B200_TRY(upload(ctx, dn, normals, (size_t)surface->n * 4));
+  B200_TRY(drf.alloc(ctx, (size_t)std::max(K, 1) * 9));
+  B200_TRY(dev_board_lrf(ctx, surface, dn.p, dkp.p, K, radius, p, drf.p));
+  B200_TRY(download(ctx, rf, drf.p, (size_t)K * 9));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 /* ------------------------------------------------------------------ pose refinement */
 int b200_icp_align(b200_ctx *ctx, const float *source, int ns, int sstride, b200_cloud *target, int max_iterations,
                    double max_corr_dist, double transformation_epsilon, double euclidean_fitness_epsilon,

@@ -86,6 +86,8 @@ struct b200_ctx {
   int sm_count = 148;
   size_t smem_optin = 0;
   int64_t launches = 0;
+  uint32_t rand_state[31] = {0};  // glibc rand() stream for BOARD's random axis (board.cu)
+  bool rand_seeded = false;
   double last_mean_nbrs = 0.0;
   int last_max_nbrs = 0;
   float last_match_err_ratio = 0.f;  // max observed approximation error / assumed bound (profiling only)
@@ -317,6 +319,10 @@ int dev_hough3d(b200_ctx *ctx, const float4 *d_model_kp, const float *d_model_rf
                 const float *d_scene_rf, const b200_corr *d_corrs, int C, double bin_size, double threshold, float *d_T,
                 int max_inst, int *d_inst_offsets, int *d_inst_counts, b200_corr *d_inst_corrs, int corr_cap,
                 int *d_n_inst);
+// board.cu
+void board_rand_seed(b200_ctx *ctx, unsigned seed);
+int dev_board_lrf(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 *d_kp, int K, double radius,
+                  const b200_board_params *p, float *d_rf);
 // icp.cu
 int dev_icp_align(b200_ctx *ctx, const float4 *d_src, int ns, b200_cloud *target, int max_iterations, double max_corr_dist,
                   double transformation_epsilon, double euclidean_fitness_epsilon, const float *guess, float *final_T,

@@ -10,10 +10,11 @@
 // UniformSampling runs on the CPU before the hot path).
 //
 // usage: shot_recognition <model.f32> <model_kp.f32 | us:leaf> <scene.f32> <scene_kp.f32 | us:leaf> <out_prefix>
-//                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch] [gc|hough]
+//                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch] [gc|hough|hough-shot]
 //                         [icp:N]
 // writes <out_prefix>.corr (b200_corr records), <out_prefix>.T (instances x 16 float),
 //        <out_prefix>.inst (int32 count per instance followed by the records)
+//        with hough, <out_prefix>.rf (model then scene BOARD frames, 9 float each)
 //        with icp:N, <out_prefix>.icp (per instance, first 8: 16 float refined pose, fitness, converged) — the
 //        reference's icp_align (SHOT.cpp:177-192) on the model placed by the grouped pose
 #include <pcl_b200/pcl_b200.h>
@@ -57,7 +58,10 @@ int main(int argc, char **argv) {
   const float cg_size_ = argc > 9 ? (float)atof(argv[9]) : 0.02f;
   const float cg_thresh_ = argc > 10 ? (float)atof(argv[10]) : 2.0f;
   const bool batch = argc > 11 && std::string(argv[11]) == "batch";
-  const bool use_hough = argc > 12 && std::string(argv[12]) == "hough";  // the reference's --algorithm Hough|GC
+  const std::string algo = argc > 12 ? argv[12] : "gc";  // the reference's --algorithm Hough|GC
+  const bool use_hough = algo == "hough" || algo == "hough-shot";
+  const bool board_frames = algo == "hough";
+  const float rf_rad_ = 0.02f;  // SHOT.cpp:51
   const int icp_iters = (argc > 13 && std::string(argv[13]).compare(0, 4, "icp:") == 0) ? atoi(argv[13] + 4) : 0;
 
   pcl::PointCloud<PointType>::Ptr model(new pcl::PointCloud<PointType>()), scene(new pcl::PointCloud<PointType>());
@@ -131,18 +135,42 @@ int main(int argc, char **argv) {
   std::vector<pcl::Matrix4f> rototranslations;
   std::vector<pcl::Correspondences> clustered_corrs;
   if (use_hough) {
-    // Hough branch (SHOT.cpp:433-470).  The reference computes BOARD frames for it; this harness passes the
-    // SHOT frames the descriptor stage produced (pcl::SHOT352::rf) — Hough3DGrouping takes any frame cloud.
+    // Hough branch (SHOT.cpp:433-470): BOARD frames at the keypoints (SHOT.cpp:441-453), or with
+    // "hough-shot" the SHOT frames the descriptor stage produced (pcl::SHOT352::rf).
     pcl::PointCloud<pcl::ReferenceFrame>::Ptr model_rf(new pcl::PointCloud<pcl::ReferenceFrame>()),
         scene_rf(new pcl::PointCloud<pcl::ReferenceFrame>());
-    for (int side = 0; side < 2; ++side) {
-      const pcl::PointCloud<DescriptorType> &d = side ? *scene_descriptors : *model_descriptors;
-      pcl::PointCloud<pcl::ReferenceFrame> &rf = side ? *scene_rf : *model_rf;
-      rf.resize(d.size());
-      for (size_t i = 0; i < d.size(); ++i) {
-        memcpy(rf[i].x_axis, d[i].rf + 0, 12);
-        memcpy(rf[i].y_axis, d[i].rf + 3, 12);
-        memcpy(rf[i].z_axis, d[i].rf + 6, 12);
+    if (board_frames) {
+      pcl::BOARDLocalReferenceFrameEstimation<PointType, NormalType, pcl::ReferenceFrame> rf_est;
+      rf_est.setFindHoles(true);
+      rf_est.setRadiusSearch(rf_rad_);
+
+      rf_est.setInputCloud(model_keypoints);
+      rf_est.setInputNormals(model_normals);
+      rf_est.setSearchSurface(model);
+      rf_est.compute(*model_rf);
+
+      rf_est.setInputCloud(scene_keypoints);
+      rf_est.setInputNormals(scene_normals);
+      rf_est.setSearchSurface(scene);
+      rf_est.compute(*scene_rf);
+      FILE *frf = fopen((std::string(argv[5]) + ".rf").c_str(), "wb");
+      for (int side = 0; side < 2; ++side)
+        for (const pcl::ReferenceFrame &r : (side ? *scene_rf : *model_rf).points) {
+          fwrite(r.x_axis, sizeof(float), 3, frf);
+          fwrite(r.y_axis, sizeof(float), 3, frf);
+          fwrite(r.z_axis, sizeof(float), 3, frf);
+        }
+      fclose(frf);
+    } else {
+      for (int side = 0; side < 2; ++side) {
+        const pcl::PointCloud<DescriptorType> &d = side ? *scene_descriptors : *model_descriptors;
+        pcl::PointCloud<pcl::ReferenceFrame> &rf = side ? *scene_rf : *model_rf;
+        rf.resize(d.size());
+        for (size_t i = 0; i < d.size(); ++i) {
+          memcpy(rf[i].x_axis, d[i].rf + 0, 12);
+          memcpy(rf[i].y_axis, d[i].rf + 3, 12);
+          memcpy(rf[i].z_axis, d[i].rf + 6, 12);
+        }
       }
     }
     pcl::Hough3DGrouping<PointType, PointType, pcl::ReferenceFrame, pcl::ReferenceFrame> clusterer;

@@ -170,6 +170,29 @@ B200_API int b200_desc_index_size(const b200_desc_index *index);
 B200_API int b200_desc_index_knn(b200_ctx *ctx, const b200_desc_index *index, const float *queries, int nq, int k,
                                  int *idx, float *d2, int *k_found);
 
+/* ---------------------------------------------------------------- BOARD frames ----------- */
+/* pcl::BOARDLocalReferenceFrameEstimation::compute — the reference frames of the Hough branch (SHOT.cpp:441-453,
+ * 6Dpose.cpp:497-509, FPFH_demo.cpp:556-568: setFindHoles(true), setRadiusSearch(rf_rad_), setInputCloud(keypoints),
+ * setInputNormals(cloud normals), setSearchSurface(cloud)).  Parameters = the PCL setters; b200_board_params_default
+ * fills PCL's constructor defaults (tangent_radius 0, find_holes 0, margin_thresh 0.85, check_margin_array_size 24,
+ * hole_size_prob_thresh 0.2, steep_thresh 0.1).  normals: one row of 4 floats per surface point.  rf: K x 9
+ * (x, y, z axes); NaN rows for keypoints with fewer than 6 support points.  With find_holes PCL draws two rand()
+ * values per keypoint with a full support, in keypoint order, from the process-wide stream; here the stream
+ * (glibc's generator) belongs to the context: a new context is srand(1), b200_ctx_srand reseeds it, and successive
+ * calls continue it (model frames, then scene frames, like the reference's two compute() calls). */
+typedef struct b200_board_params {
+  int find_holes;
+  float tangent_radius; /* 0: PCL's code path when setTangentRadius is never called */
+  float margin_thresh;
+  int check_margin_array_size; /* 1..64 */
+  float hole_size_prob_thresh;
+  float steep_thresh;
+} b200_board_params;
+B200_API void b200_board_params_default(b200_board_params *p);
+B200_API int b200_ctx_srand(b200_ctx *ctx, unsigned seed);
+B200_API int b200_board_lrf(b200_ctx *ctx, b200_cloud *surface, const float *normals, const float *kp, int K, int kstride,
+                            double radius, const b200_board_params *p, float *rf);
+
 /* ---------------------------------------------------------------- grouping --------------- */
 /* pcl::GeometricConsistencyGrouping::recognize (SHOT.cpp:473-482, 6Dpose.cpp:529-538,
  * SHOT_scenes.cpp:413-425).  transforms: max_inst x 16 (row-major 4x4, model -> scene);

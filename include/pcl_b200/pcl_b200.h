@@ -536,6 +536,63 @@ class SHOTEstimationOMP : public FeatureBase<PointInT> {
 template <class PointInT, class PointNT = Normal, class PointOutT = SHOT352>
 using SHOTEstimation = SHOTEstimationOMP<PointInT, PointNT, PointOutT>;
 
+/* ---------------------------------------------------------------- BOARD frames */
+/* pcl::BOARDLocalReferenceFrameEstimation<PointInT, PointNT, ReferenceFrame> (SHOT.cpp:441-453, 6Dpose.cpp:497-509,
+ * FPFH_demo.cpp:556-568).  PCL draws the random reference axis from rand(); the device library keeps its own
+ * glibc-compatible stream per context (b200_ctx_srand; a fresh context is srand(1)). */
+template <class PointInT, class PointNT = Normal, class PointOutT = ReferenceFrame>
+class BOARDLocalReferenceFrameEstimation : public FeatureBase<PointInT> {
+ public:
+  typedef std::shared_ptr<const PointCloud<PointNT>> PointCloudNConstPtr;
+  BOARDLocalReferenceFrameEstimation() { b200_board_params_default(&params_); }
+  void setInputNormals(const PointCloudNConstPtr &normals) { normals_ = normals; }
+  void setFindHoles(bool find_holes) { params_.find_holes = find_holes ? 1 : 0; }
+  bool getFindHoles() const { return params_.find_holes != 0; }
+  void setTangentRadius(float radius) { params_.tangent_radius = radius; }
+  void setMarginThresh(float margin_thresh) { params_.margin_thresh = margin_thresh; }
+  void setCheckMarginArraySize(int size) { params_.check_margin_array_size = size; }
+  void setHoleSizeProbThresh(float prob_thresh) { params_.hole_size_prob_thresh = prob_thresh; }
+  void setSteepThresh(float steep_thresh) { params_.steep_thresh = steep_thresh; }
+  void compute(PointCloud<PointOutT> &output) {
+    output.clear();
+    if (this->k_ != 0) {
+      fprintf(stderr,
+              "[pcl_b200::BOARDLocalReferenceFrameEstimation::computeFeature] Error! Search method set to k-neighborhood. "
+              "Call setKSearch(0) and setRadiusSearch( radius ) to use this class.\n");
+      return;
+    }
+    if (!this->initCompute("BOARDLocalReferenceFrameEstimation", true)) return;
+    const size_t n_surf = (this->fake_surface_ ? this->input_ : this->surface_)->size();
+    if (!normals_ || normals_->size() != n_surf) {
+      fprintf(stderr,
+              "[pcl_b200::BOARDLocalReferenceFrameEstimation::initCompute] The number of points in the surface differs "
+              "from the number of normals!\n");
+      this->deinitCompute();
+      return;
+    }
+    const size_t K = this->input_->size();
+    std::vector<float> nrm = detail::flatten_normals(*normals_), rf(K * 9);
+    const int rc = b200_board_lrf(detail::ctx(), this->surf_.c, nrm.data(), detail::xyz(this->input_->points), (int)K,
+                                  detail::stride<PointInT>(), this->search_radius_, &params_, rf.data());
+    this->deinitCompute();
+    if (!detail::ok(rc, "BOARDLocalReferenceFrameEstimation::compute")) return;
+    output.points.resize(K);
+    output.width = (uint32_t)K;
+    output.height = 1;
+    output.is_dense = true;
+    for (size_t i = 0; i < K; ++i) {
+      memcpy(output.points[i].x_axis, &rf[i * 9 + 0], 12);
+      memcpy(output.points[i].y_axis, &rf[i * 9 + 3], 12);
+      memcpy(output.points[i].z_axis, &rf[i * 9 + 6], 12);
+      if (rf[i * 9] != rf[i * 9]) output.is_dense = false;
+    }
+  }
+
+ private:
+  PointCloudNConstPtr normals_;
+  b200_board_params params_;
+};
+
 /* ---------------------------------------------------------------- FPFH (a13) */
 /* pcl::FPFHEstimation / FPFHEstimationOMP (FPFH_demo.cpp:422-428, 505-510;
  * FPFH_scenes_clustered.cpp:287-293, 379-387) */

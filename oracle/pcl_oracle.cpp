@@ -18,6 +18,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -1722,6 +1723,352 @@ int orc_icp_align(const float *source, int ns, int sstride, const float *target,
     *fitness = s / n;
   }
   return 0;
+}
+
+/* glibc rand() (TYPE_3 additive feedback generator, random_r.c): r[i] = r[i-3] + r[i-31], seeded with the
+ * Lehmer sequence 16807 * r mod (2^31 - 1), the first 310 outputs discarded, output = r >> 1.  BOARD draws its
+ * "random orthogonal axis" from the process-global rand(); the restatement carries the stream explicitly. */
+struct GlibcRand {
+  uint32_t r[34];
+  int k;
+  std::vector<uint32_t> hist; /* sliding window of the last 31 values */
+  explicit GlibcRand(unsigned seed) { reseed(seed); }
+  void reseed(unsigned seed) {
+    if (seed == 0) seed = 1;
+    int32_t v[34];
+    v[0] = (int32_t)seed;
+    for (int i = 1; i < 31; ++i) {
+      int64_t hi = v[i - 1] / 127773, lo = v[i - 1] % 127773;
+      int64_t word = 16807 * lo - 2836 * hi;
+      if (word < 0) word += 2147483647;
+      v[i] = (int32_t)word;
+    }
+    hist.assign(v, v + 31);
+    for (int i = 31; i < 34; ++i) hist.push_back(hist[i - 31]);
+    for (int i = 34; i < 344; ++i) hist.push_back(hist[i - 31] + hist[i - 3]);
+    hist.erase(hist.begin(), hist.end() - 31);
+  }
+  int next() {
+    const uint32_t o = hist[0] + hist[28]; /* r[i-31] + r[i-3] */
+    hist.erase(hist.begin());
+    hist.push_back(o);
+    return (int)(o >> 1);
+  }
+};
+
+namespace {
+inline float dot3f(const float *a, const float *b) { /* Eigen 3-vector dot: ((a0 b0 + a1 b1) + a2 b2) */
+  float s = a[0] * b[0];
+  s += a[1] * b[1];
+  s += a[2] * b[2];
+  return s;
+}
+inline void normalize3f(float *v) { /* Eigen normalize(): v /= sqrt(squaredNorm) */
+  const float n = std::sqrt(dot3f(v, v));
+  v[0] /= n;
+  v[1] /= n;
+  v[2] /= n;
+}
+/* board.hpp directedOrthogonalAxis + projectPointOnPlane */
+inline void directed_orthogonal_axis(const float *axis, const float *origin, const float *point, float *out) {
+  float xo[3] = {point[0] - origin[0], point[1] - origin[1], point[2] - origin[2]};
+  const float t = dot3f(axis, xo);
+  float proj[3] = {point[0] - t * axis[0], point[1] - t * axis[1], point[2] - t * axis[2]};
+  out[0] = proj[0] - origin[0];
+  out[1] = proj[1] - origin[1];
+  out[2] = proj[2] - origin[2];
+  normalize3f(out);
+}
+/* board.hpp getAngleBetweenUnitVectors */
+inline float angle_between_unit(const float *v1, const float *v2, const float *axis) {
+  float o[3];
+  cross3f(v1, v2, o);
+  float a = std::acos(std::max(-1.0f, std::min(1.0f, dot3f(v1, v2))));
+  return dot3f(o, axis) < 0.f ? (2 * (float)M_PI - a) : a;
+}
+constexpr int BOARD_MAX_SECTORS = 64;
+
+/* board.hpp computePointLRF.  nb: the keypoint's support in (d2, index) order.  rnd: the two rand() values
+ * drawn for this keypoint (find_holes only).  out: x, y, z axes.  Returns false when the frame is NaN. */
+bool board_point_lrf(const float *surf, int sstride, const float *normals, const float *c, const std::vector<DistIdx> &nb,
+                     const std::vector<DistIdx> &nbt, const orc_board_params &bp, const int rnd[2], float *out) {
+  const int n = (int)nb.size();
+  auto set_nan = [&]() {
+    for (int k = 0; k < 9; ++k) out[k] = kNaNf;
+    return false;
+  };
+  if (n < 6) return set_nan();
+  /* planeFitting: centroid, centred points, right singular vector of the smallest singular value.  PCL runs
+   * Eigen's float JacobiSVD; here: float64 centroid and scatter, eigenvector of the smallest eigenvalue. */
+  double mean[3] = {0, 0, 0};
+  for (const DistIdx &e : nb)
+    for (int a = 0; a < 3; ++a) mean[a] += surf[(size_t)e.idx * sstride + a];
+  for (int a = 0; a < 3; ++a) mean[a] /= n;
+  double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (const DistIdx &e : nb) {
+    const double d[3] = {surf[(size_t)e.idx * sstride] - mean[0], surf[(size_t)e.idx * sstride + 1] - mean[1],
+                         surf[(size_t)e.idx * sstride + 2] - mean[2]};
+    cov[0] += d[0] * d[0];
+    cov[1] += d[0] * d[1];
+    cov[2] += d[0] * d[2];
+    cov[4] += d[1] * d[1];
+    cov[5] += d[1] * d[2];
+    cov[8] += d[2] * d[2];
+  }
+  cov[3] = cov[1];
+  cov[6] = cov[2];
+  cov[7] = cov[5];
+  double w[3], V[9];
+  eigh3_f64(cov, w, V);
+  float z[3] = {(float)V[0], (float)V[3], (float)V[6]}; /* column 0: smallest eigenvalue */
+  /* normalDisambiguation: sign by the mean of the finite support normals */
+  double nm[3] = {0, 0, 0};
+  for (const DistIdx &e : nb) {
+    const float *q = normals + (size_t)e.idx * 4;
+    if (std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]))
+      for (int a = 0; a < 3; ++a) nm[a] += q[a];
+  }
+  if (nm[0] != 0.0 || nm[1] != 0.0 || nm[2] != 0.0) {
+    if ((double)z[0] * nm[0] + (double)z[1] * nm[1] + (double)z[2] * nm[2] < 0.0) {
+      z[0] = -z[0];
+      z[1] = -z[1];
+      z[2] = -z[2];
+    }
+  }
+  for (int a = 0; a < 3; ++a) out[6 + a] = z[a];
+  const float tangent_radius = bp.tangent_radius;
+  const std::vector<DistIdx> *sup = &nbt; /* support of the x axis: the tangent-radius search when it differs */
+  const float radius2 = tangent_radius * tangent_radius;
+  const float margin_distance2 = bp.margin_thresh * bp.margin_thresh * radius2;
+  const int S = bp.check_margin_array_size;
+  float min_normal_cos = FLT_MAX;
+  int min_normal_index = -1;
+  bool margin_point_found = false;
+  bool check[BOARD_MAX_SECTORS];
+  float min_angle[BOARD_MAX_SECTORS], max_angle[BOARD_MAX_SECTORS], min_angle_normal[BOARD_MAX_SECTORS],
+      max_angle_normal[BOARD_MAX_SECTORS];
+  float x_axis[3] = {0, 0, 0}, y_axis[3];
+  float max_boundary_angle = 0.f;
+  if (bp.find_holes) {
+    /* randomOrthogonalAxis */
+    const float r0 = ((float)rnd[0] / (float)RAND_MAX) * 2.0f - 1.0f;
+    const float r1 = ((float)rnd[1] / (float)RAND_MAX) * 2.0f - 1.0f;
+    auto near0 = [](float v) { return std::fabs(v - 0.0f) < 1e-8f; };
+    if (!near0(z[2])) {
+      x_axis[0] = r0;
+      x_axis[1] = r1;
+      x_axis[2] = -(z[0] * x_axis[0] + z[1] * x_axis[1]) / z[2];
+    } else if (!near0(z[1])) {
+      x_axis[0] = r0;
+      x_axis[2] = r1;
+      x_axis[1] = -(z[0] * x_axis[0] + z[2] * x_axis[2]) / z[1];
+    } else if (!near0(z[0])) {
+      x_axis[1] = r0;
+      x_axis[2] = r1;
+      x_axis[0] = -(z[1] * x_axis[1] + z[2] * x_axis[2]) / z[0];
+    }
+    normalize3f(x_axis);
+    for (int i = 0; i < S; ++i) {
+      check[i] = false;
+      min_angle[i] = FLT_MAX;
+      max_angle[i] = -FLT_MAX;
+      min_angle_normal[i] = -1.0f;
+      max_angle_normal[i] = -1.0f;
+    }
+    max_boundary_angle = (2 * (float)M_PI) / (float)S;
+  }
+  for (const DistIdx &e : *sup) {
+    if (e.d2 <= margin_distance2) continue;
+    margin_point_found = true;
+    const float *nrm = normals + (size_t)e.idx * 4;
+    const float normal_cos = dot3f(z, nrm);
+    if (normal_cos < min_normal_cos) {
+      min_normal_index = e.idx;
+      min_normal_cos = normal_cos;
+    }
+    if (bp.find_holes) {
+      float ind[3];
+      directed_orthogonal_axis(z, c, surf + (size_t)e.idx * sstride, ind);
+      const float angle = angle_between_unit(x_axis, ind, z);
+      const int b = std::min((int)std::floor(angle / max_boundary_angle), S - 1);
+      if (b >= 0) { /* a NaN angle (neighbour on the axis) indexes out of range in PCL; skipped here */
+        check[b] = true;
+        if (angle < min_angle[b]) {
+          min_angle[b] = angle;
+          min_angle_normal[b] = normal_cos;
+        }
+        if (angle > max_angle[b]) {
+          max_angle[b] = angle;
+          max_angle_normal[b] = normal_cos;
+        }
+      }
+    }
+  }
+  auto finish = [&](void) {
+    cross3f(z, x_axis, y_axis);
+    for (int a = 0; a < 3; ++a) {
+      out[a] = x_axis[a];
+      out[3 + a] = y_axis[a];
+    }
+    return true;
+  };
+  auto toward_min_normal = [&]() {
+    if (min_normal_index == -1) return false;
+    directed_orthogonal_axis(z, c, surf + (size_t)min_normal_index * sstride, x_axis);
+    return true;
+  };
+  if (!margin_point_found) {
+    for (const DistIdx &e : *sup) {
+      if (e.d2 > margin_distance2) continue;
+      const float normal_cos = dot3f(z, normals + (size_t)e.idx * 4);
+      if (normal_cos < min_normal_cos) {
+        min_normal_index = e.idx;
+        min_normal_cos = normal_cos;
+      }
+    }
+    if (!toward_min_normal()) return set_nan();
+    return finish();
+  }
+  bool hole_present = false;
+  if (bp.find_holes)
+    for (int i = 0; i < S; ++i)
+      if (!check[i]) {
+        hole_present = true;
+        break;
+      }
+  if (!bp.find_holes || !hole_present) {
+    if (!toward_min_normal()) return set_nan();
+    return finish();
+  }
+  /* at least one empty sector: the widest plausible hole gives the x direction */
+  float angle = 0.f;
+  int first_no_border = -1;
+  if (check[S - 1]) {
+    first_no_border = 0;
+  } else {
+    for (int i = 0; i < S; ++i)
+      if (check[i]) {
+        first_no_border = i;
+        break;
+      }
+  }
+  float max_hole_prob = -FLT_MAX;
+  if (first_no_border >= 0) /* all sectors empty cannot happen here (margin_point_found), PCL would loop forever */
+    for (int ch = first_no_border; ch < S; ++ch) {
+      if (check[ch]) continue;
+      const int hole_first = ch;
+      int hole_end = hole_first + 1;
+      while (!check[hole_end % S]) ++hole_end;
+      if (hole_end - hole_first > 0) {
+        const int previous_hole = (((hole_first - 1) < 0) ? (hole_first - 1) + S : (hole_first - 1)) % S;
+        const int following_hole = hole_end % S;
+        float normal_begin = max_angle_normal[previous_hole];
+        float normal_end = min_angle_normal[following_hole];
+        normal_begin -= min_normal_cos;
+        normal_end -= min_normal_cos;
+        normal_begin = normal_begin / (1.0f - min_normal_cos);
+        normal_end = normal_end / (1.0f - min_normal_cos);
+        normal_begin = 1.0f - normal_begin;
+        normal_end = 1.0f - normal_end;
+        float hole_width;
+        if (following_hole < previous_hole)
+          hole_width = min_angle[following_hole] + 2 * (float)M_PI - max_angle[previous_hole];
+        else
+          hole_width = min_angle[following_hole] - max_angle[previous_hole];
+        const float hole_prob = hole_width / (2 * (float)M_PI);
+        const float steep_prob = (normal_end + normal_begin) / 2.0f;
+        if (hole_prob > bp.hole_size_prob_thresh && steep_prob > bp.steep_thresh && hole_prob > max_hole_prob) {
+          max_hole_prob = hole_prob;
+          const float angle_weight = ((normal_end - normal_begin) + 1.0f) / 2.0f;
+          if (following_hole < previous_hole)
+            angle = max_angle[previous_hole] +
+                    (min_angle[following_hole] + 2 * (float)M_PI - max_angle[previous_hole]) * angle_weight;
+          else
+            angle = max_angle[previous_hole] + (min_angle[following_hole] - max_angle[previous_hole]) * angle_weight;
+        }
+      }
+      if (hole_end >= S) break;
+      ch = hole_end - 1;
+    }
+  if (max_hole_prob > -FLT_MAX) {
+    /* x_axis = Eigen::AngleAxisf(angle, z) * x_axis  (AngleAxis::toRotationMatrix, then matrix * vector) */
+    const float sn = std::sin(angle), cs = std::cos(angle);
+    const float sa[3] = {sn * z[0], sn * z[1], sn * z[2]};
+    const float ca[3] = {(1.f - cs) * z[0], (1.f - cs) * z[1], (1.f - cs) * z[2]};
+    float R[9];
+    float tmp = ca[0] * z[1];
+    R[1] = tmp - sa[2];
+    R[3] = tmp + sa[2];
+    tmp = ca[0] * z[2];
+    R[2] = tmp + sa[1];
+    R[6] = tmp - sa[1];
+    tmp = ca[1] * z[2];
+    R[5] = tmp - sa[0];
+    R[7] = tmp + sa[0];
+    R[0] = ca[0] * z[0] + cs;
+    R[4] = ca[1] * z[1] + cs;
+    R[8] = ca[2] * z[2] + cs;
+    float nx[3];
+    for (int r = 0; r < 3; ++r) {
+      float v = R[r * 3 + 0] * x_axis[0];
+      v += R[r * 3 + 1] * x_axis[1];
+      v += R[r * 3 + 2] * x_axis[2];
+      nx[r] = v;
+    }
+    for (int a = 0; a < 3; ++a) x_axis[a] = nx[a];
+  } else {
+    if (!toward_min_normal()) return set_nan();
+  }
+  return finish();
+}
+}  // namespace
+
+/* pcl::BOARDLocalReferenceFrameEstimation::compute (SHOT.cpp:441-453: setFindHoles(true), setRadiusSearch(rf_rad_),
+ * keypoints as input, full cloud as search surface, the cloud's normals).  The keypoints are processed serially in
+ * PCL, each one with at least 6 support points drawing two rand() values: the stream here is glibc's generator
+ * seeded with *rand_seed_state == srand(seed); rand_skip values already consumed are skipped first.  Returns the
+ * number of rand() values consumed (so that a second call can continue the stream like PCL's second compute()). */
+int orc_board_lrf(const float *surf, const float *normals, int n, int sstride, const float *kp, int K, int kstride,
+                  double radius, const orc_board_params *bp, unsigned rand_seed, int rand_skip, float *out) {
+  CpuGrid g;
+  g.build(surf, n, sstride, cell_for_radius(radius));
+  std::vector<std::vector<DistIdx>> nbs((size_t)K);
+#pragma omp parallel for schedule(dynamic, 32)
+  for (int i = 0; i < K; ++i) g.radius(kp + (size_t)i * kstride, radius, nbs[(size_t)i]);
+  GlibcRand rng(rand_seed);
+  for (int i = 0; i < rand_skip; ++i) rng.next();
+  /* "if (tangent_radius_ != 0.0f && search_parameter_ != tangent_radius_)": second search for the x axis */
+  const bool second = bp->tangent_radius != 0.0f && radius != (double)bp->tangent_radius;
+  std::vector<std::vector<DistIdx>> nbt(second ? (size_t)K : 0);
+  CpuGrid gt;
+  if (second) {
+    gt.build(surf, n, sstride, cell_for_radius(bp->tangent_radius));
+#pragma omp parallel for schedule(dynamic, 32)
+    for (int i = 0; i < K; ++i) gt.radius(kp + (size_t)i * kstride, (double)bp->tangent_radius, nbt[(size_t)i]);
+  }
+  std::vector<int> rnd((size_t)K * 2, 0);
+  int consumed = 0;
+  for (int i = 0; i < K; ++i)
+    if (bp->find_holes && nbs[(size_t)i].size() >= 6) {
+      rnd[2 * (size_t)i] = rng.next();
+      rnd[2 * (size_t)i + 1] = rng.next();
+      consumed += 2;
+    }
+  orc_board_params p = *bp;
+  if (p.check_margin_array_size < 1) p.check_margin_array_size = 1;
+  if (p.check_margin_array_size > BOARD_MAX_SECTORS) p.check_margin_array_size = BOARD_MAX_SECTORS;
+#pragma omp parallel for schedule(dynamic, 32)
+  for (int i = 0; i < K; ++i)
+    board_point_lrf(surf, sstride, normals, kp + (size_t)i * kstride, nbs[(size_t)i],
+                    second ? nbt[(size_t)i] : nbs[(size_t)i], p, &rnd[2 * (size_t)i], out + (size_t)i * 9);
+  return consumed;
+}
+
+int orc_glibc_rand_nth(unsigned seed, int nth) {
+  GlibcRand rng(seed);
+  int v = 0;
+  for (int i = 0; i < nth; ++i) v = rng.next();
+  return v;
 }
 
 void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]) { umeyama3(src, dst, n, T16); }

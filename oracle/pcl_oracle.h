@@ -105,6 +105,22 @@ int orc_hough3d_recognize(const float *model_kp, const float *model_rf, int Km, 
                           double threshold, float *transforms, int max_inst, int *inst_offsets, orc_corr *inst_corrs,
                           int corr_cap);
 
+/* pcl::BOARDLocalReferenceFrameEstimation (SHOT.cpp:441-453, 6Dpose.cpp:497-509, FPFH_demo.cpp:556-568).  Defaults of
+ * the PCL constructor: tangent_radius 0, find_holes false (the reference sets true), margin_thresh 0.85,
+ * check_margin_array_size 24, hole_size_prob_thresh 0.2, steep_thresh 0.1.  out: K x 9 (x, y, z axes); returns the
+ * number of rand() values drawn (glibc generator seeded rand_seed, rand_skip values skipped first). */
+typedef struct {
+  int find_holes;
+  float tangent_radius;
+  float margin_thresh;
+  int check_margin_array_size;
+  float hole_size_prob_thresh;
+  float steep_thresh;
+} orc_board_params;
+int orc_board_lrf(const float *surf, const float *normals, int n, int sstride, const float *kp, int K, int kstride,
+                  double radius, const orc_board_params *bp, unsigned rand_seed, int rand_skip, float *out);
+int orc_glibc_rand_nth(unsigned seed, int nth); /* nth value of rand() after srand(seed), nth >= 1 */
+
 /* pcl::IterativeClosestPoint::align + getFitnessScore (SHOT.cpp:177-192, SHOT_demo.cpp:604-663).  PCL defaults:
  * max_corr_dist <= 0 = unlimited, transformation_epsilon 0, euclidean_fitness_epsilon -DBL_MAX.  final_T: row-major
  * 4x4; aligned (nullable): ns x 3. */

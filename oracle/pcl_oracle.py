@@ -18,6 +18,11 @@ class Corr(C.Structure):
     _fields_ = [("index_query", C.c_int), ("index_match", C.c_int), ("distance", C.c_float)]
 
 
+class BoardParams(C.Structure):
+    _fields_ = [("find_holes", C.c_int), ("tangent_radius", C.c_float), ("margin_thresh", C.c_float),
+                ("check_margin_array_size", C.c_int), ("hole_size_prob_thresh", C.c_float), ("steep_thresh", C.c_float)]
+
+
 CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
 
 
@@ -57,6 +62,11 @@ def lib():
         L.orc_gc_recognize.restype = C.c_int
         L.orc_gc_recognize.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.POINTER(Corr), C.c_int,
                                        C.c_double, C.c_int, fp, C.c_int, ip, C.POINTER(Corr), C.c_int]
+        L.orc_board_lrf.restype = C.c_int
+        L.orc_board_lrf.argtypes = [fp, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double, C.POINTER(BoardParams),
+                                    C.c_uint, C.c_int, fp]
+        L.orc_glibc_rand_nth.restype = C.c_int
+        L.orc_glibc_rand_nth.argtypes = [C.c_uint, C.c_int]
         L.orc_icp_align.restype = C.c_int
         L.orc_icp_align.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_double, fp, fp, fp, C.POINTER(C.c_double), ip, ip]
@@ -204,6 +214,28 @@ def hough3d_recognize(model_kp, model_rf, scene_kp, scene_rf, corrs, bin_size, t
                                     _f(T), max_inst, _i(off), oc.ctypes.data_as(C.POINTER(Corr)), cap)
     n = min(max(n, 0), max_inst)
     return T[:n].reshape(n, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(n)]
+
+
+def board_params(find_holes=True, tangent_radius=0.0, margin_thresh=0.85, check_margin_array_size=24,
+                 hole_size_prob_thresh=0.2, steep_thresh=0.1):
+    """PCL's constructor defaults, with find_holes as the reference sets it (SHOT.cpp:442)."""
+    return BoardParams(int(find_holes), tangent_radius, margin_thresh, check_margin_array_size, hole_size_prob_thresh,
+                       steep_thresh)
+
+
+def board_lrf(surf, normals, kp, radius, params=None, rand_seed=1, rand_skip=0):
+    """BOARDLocalReferenceFrameEstimation::compute.  Returns (frames K x 9, rand() values consumed)."""
+    surf, kp = _pts(surf), _pts(kp)
+    normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(len(surf), 4)
+    params = params or board_params()
+    out = np.zeros((max(len(kp), 1), 9), dtype=np.float32)
+    used = lib().orc_board_lrf(_f(surf), _f(normals), len(surf), surf.shape[1], _f(kp), len(kp), kp.shape[1],
+                               float(radius), C.byref(params), int(rand_seed), int(rand_skip), _f(out))
+    return out[:len(kp)], used
+
+
+def glibc_rand_nth(seed, nth):
+    return lib().orc_glibc_rand_nth(int(seed), int(nth))
 
 
 def icp_align(source, target, max_iterations=10, max_corr_dist=0.0, transformation_epsilon=0.0,

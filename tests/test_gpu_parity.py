@@ -627,3 +627,53 @@ def test_icp_parity(ctx, orc, synth, small):
     e = ctx.icp_align(np.zeros((0, 3), np.float32), tgt, max_iterations=3)
     assert e["iterations"] == 0 and np.array_equal(e["final_transform"], np.eye(4))
     tgt.close()
+
+
+# ------------------------------------------------------------------------------------------ BOARD
+def test_board_lrf_parity(ctx, orc, synth, small, b200):
+    """BOARDLocalReferenceFrameEstimation (SHOT.cpp:441-453: find_holes, keypoints on the full cloud).  Same NaN rows;
+    frames within 1e-5 of the restatement except where a support direction sits within an ulp of a sector border
+    (acosf differs in the last bit between the device and glibc) — at most 0.5 % of the keypoints.  The rand()
+    stream continues across calls (model, then scene) like PCL's two compute() calls."""
+    model, scene = small
+    kpm, kps = synth.uniform_sampling(model, 0.02), synth.uniform_sampling(scene, 0.03)
+    nm, ns = orc.normals(model, k=10), orc.normals(scene, k=10)
+    cm, cs = ctx.cloud(model), ctx.cloud(scene)
+
+    def compare(a, b, allowed):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        ok = ~np.isnan(b[:, 0])
+        bad = np.abs(a[ok] - b[ok]).max(axis=1) > 1e-5
+        assert bad.mean() <= allowed, bad.mean()
+        f = a[ok].reshape(-1, 3, 3)
+        assert np.abs(np.einsum("nij,nkj->nik", f, f) - np.eye(3)).max() < 1e-4
+
+    ctx.srand(1)
+    a_m = ctx.board_lrf(cm, nm, kpm, 0.015)
+    a_s = ctx.board_lrf(cs, ns, kps, 0.015)
+    o_m, used = orc.board_lrf(model, nm, kpm, 0.015)
+    o_s, used2 = orc.board_lrf(scene, ns, kps, 0.015, rand_skip=used)
+    assert used > 0 and used2 > 0
+    compare(a_m, o_m, 0.005)
+    compare(a_s, o_s, 0.005)
+    # reseeding reproduces the first call
+    ctx.srand(1)
+    assert np.array_equal(ctx.board_lrf(cm, nm, kpm, 0.015), a_m, equal_nan=True)
+    # parameter variants: no hole search; ring between 0.85 r and r (tangent radius = support radius); 12 sectors
+    for kw in (dict(find_holes=False), dict(tangent_radius=0.02), dict(check_margin_array_size=12, steep_thresh=0.0)):
+        r = 0.02
+        ctx.srand(7)
+        a = ctx.board_lrf(cs, ns, kps, r, b200.board_params(**kw))
+        o, _ = orc.board_lrf(scene, ns, kps, r, orc.board_params(**kw), rand_seed=7)
+        compare(a, o, 0.005)
+    # NaN normals and a far keypoint
+    ns2 = ns.copy()
+    ns2[::7] = np.nan
+    kp2 = np.concatenate([kps[:200], [[9.0, 9.0, 9.0]]]).astype(np.float32)
+    ctx.srand(3)
+    a = ctx.board_lrf(cs, ns2, kp2, 0.02)
+    o, _ = orc.board_lrf(scene, ns2, kp2, 0.02, rand_seed=3)
+    assert np.isnan(a[-1]).all()
+    compare(a, o, 0.01)
+    cm.close()
+    cs.close()

@@ -353,3 +353,56 @@ def test_icp_recovers_small_motion(orc):
     g[:3, 3] = [-0.004, 0.003, -0.002]
     rg = orc.icp_align(moved[::3], model, max_iterations=100, guess=g)
     assert np.abs(rg["final_transform"] - Tinv).max() < 2e-3
+
+
+def test_glibc_rand_known_answers(orc):
+    """BOARD draws from rand(): the restated generator reproduces glibc's sequence (srand(1): 1804289383, ...)."""
+    import ctypes
+    assert [orc.glibc_rand_nth(1, i) for i in (1, 2, 3, 4, 5)] == [1804289383, 846930886, 1681692777, 1714636915,
+                                                                  1957747793]
+    libc = ctypes.CDLL(None)
+    for seed in (1, 42, 12345):
+        libc.srand(seed)
+        ref = [libc.rand() for _ in range(400)]
+        assert ref[0] == orc.glibc_rand_nth(seed, 1) and ref[99] == orc.glibc_rand_nth(seed, 100)
+        assert ref[399] == orc.glibc_rand_nth(seed, 400)
+
+
+def test_board_lrf_properties(orc):
+    """BOARD frames (restated): orthonormal, z along the surface normal; on a plane with a straight border the x axis
+    points into the hole (the empty side); fewer than 6 support points give NaN and draw no random numbers."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    # half plane y <= 0.03 (border at y = 0.03), normals +z
+    g = np.stack(np.meshgrid(np.arange(-0.1, 0.1001, 0.004), np.arange(-0.1, 0.0301, 0.004)), -1).reshape(-1, 2)
+    surf = np.concatenate([g + rng.normal(0, 2e-4, g.shape), rng.normal(0, 1e-4, (len(g), 1))], 1).astype(np.float32)
+    normals = np.zeros((len(surf), 4), np.float32)
+    normals[:, :3] = [0.0, 0.0, 1.0] + rng.normal(0, 0.05, (len(surf), 3))     # (identical normals make PCL's
+    normals[:, :3] /= np.linalg.norm(normals[:, :3], axis=1, keepdims=True)    # steepness ratio 0/0)
+    kp = np.array([[0.0, 0.0, 0.0], [0.02, 0.005, 0.0], [5.0, 5.0, 5.0]], np.float32)
+    # PCL's code leaves tangent_radius_ at 0 unless setTangentRadius is called (the reference does not call it): the
+    # margin ring then degenerates to "every neighbour", and interior points fill all sectors.  With the tangent
+    # radius set to the support radius the ring (0.85 r .. r) is cut by the border and the hole is found.
+    rf0, used0 = orc.board_lrf(surf, normals, kp, 0.05)
+    assert used0 == 4 and np.isnan(rf0[2]).all()
+    for f in rf0[:2].reshape(2, 3, 3):
+        assert np.abs(f @ f.T - np.eye(3)).max() < 1e-5 and f[2, 2] > 0.999
+    tp = orc.board_params(tangent_radius=0.05)
+    rf, used = orc.board_lrf(surf, normals, kp, 0.05, tp)
+    assert used == 4 and np.isnan(rf[2]).all()
+    for f in rf[:2].reshape(2, 3, 3):
+        assert np.abs(f @ f.T - np.eye(3)).max() < 1e-5 and f[2, 2] > 0.999
+        assert f[0, 1] > 0.55                      # x axis inside the empty sector (towards +y, where the surface ends)
+        assert np.abs(np.cross(f[2], f[0]) - f[1]).max() < 1e-6
+    # the frames do not depend on the random reference axis beyond the sector quantisation
+    rf2, _ = orc.board_lrf(surf, normals, kp, 0.05, tp, rand_seed=99)
+    assert np.abs(rf2[:2] - rf[:2]).max() < 0.3
+    # without a hole (interior point, small radius) and without find_holes the x axis points to the most tilted normal
+    normals2 = normals.copy()
+    j = int(np.argmin(np.linalg.norm(surf[:, :2] - [0.01, -0.05], axis=1)))
+    normals2[j, :3] = [0.6, 0.0, 0.8]
+    kp2 = np.array([[0.0, -0.05, 0.0]], np.float32)
+    for fh in (True, False):
+        f = orc.board_lrf(surf, normals2, kp2, 0.03, orc.board_params(find_holes=fh))[0][0].reshape(3, 3)
+        d = surf[j] - kp2[0]
+        d[2] = 0
+        assert np.dot(f[0], d / np.linalg.norm(d)) > 0.99
