@@ -30,6 +30,8 @@ EXPORTS = [
     "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
+    "b200_library_add_view_descriptors", "b200_library_set_view_pose", "b200_library_get_view_pose",
+    "b200_library_save", "b200_library_load",
     "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
     "b200_hough3d_recognize",
     "b200_icp_align",
@@ -136,6 +138,11 @@ def lib():
             "b200_library_create": [vp, C.POINTER(vp)],
             "b200_library_destroy": [vp],
             "b200_library_add_view": [vp, vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), ip],
+            "b200_library_add_view_descriptors": [vp, vp, fp, fp, i, i, ip],
+            "b200_library_set_view_pose": [vp, i, fp],
+            "b200_library_get_view_pose": [vp, i, fp],
+            "b200_library_save": [vp, vp, C.c_char_p],
+            "b200_library_load": [vp, C.c_char_p, C.POINTER(vp)],
             "b200_library_views": [vp],
             "b200_library_view_size": [vp, i],
             "b200_library_download_view": [vp, vp, i, fp, fp],
@@ -288,12 +295,45 @@ class DescIndex:
 class Library:
     """b200_library: descriptor library over the views of the CAD models (CAD_desc.cpp:231-370)."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, handle=None):
         self.ctx = ctx
-        h = C.c_void_p()
-        ctx._chk(lib().b200_library_create(ctx.h, C.byref(h)))
+        h = handle
+        if h is None:
+            h = C.c_void_p()
+            ctx._chk(lib().b200_library_create(ctx.h, C.byref(h)))
         self.h = h
         ctx._children.add(self)
+
+    @classmethod
+    def load(cls, ctx, path):
+        """Reads a B200LIB1 file written by save() (b200_library_load)."""
+        h = C.c_void_p()
+        ctx._chk(lib().b200_library_load(ctx.h, os.fsencode(path), C.byref(h)))
+        return cls(ctx, h)
+
+    def save(self, path):
+        self.ctx._chk(lib().b200_library_save(self.ctx.h, self.h, os.fsencode(path)))
+
+    def add_view_descriptors(self, desc, kp):
+        """A view from precomputed descriptors (K x 352) and keypoints, e.g. the reference's text dumps."""
+        desc = np.ascontiguousarray(desc, dtype=np.float32).reshape(-1, 352)
+        kp = _pts(kp)
+        assert len(desc) == len(kp)
+        v = C.c_int()
+        self.ctx._chk(lib().b200_library_add_view_descriptors(self.ctx.h, self.h, _f(desc), _f(kp), len(kp), kp.shape[1],
+                                                              C.byref(v)))
+        return v.value
+
+    def set_view_pose(self, v, pose):
+        pose = np.ascontiguousarray(pose, dtype=np.float32).reshape(16)
+        if lib().b200_library_set_view_pose(self.h, int(v), _f(pose)) != OK:
+            raise B200Error(ERR_INVALID, "library: bad view index")
+
+    def view_pose(self, v):
+        pose = np.zeros(16, dtype=np.float32)
+        if lib().b200_library_get_view_pose(self.h, int(v), _f(pose)) != OK:
+            raise B200Error(ERR_INVALID, "library: bad view index")
+        return pose.reshape(4, 4)
 
     def add_view(self, xyz, kp, params):
         xyz, kp = _pts(xyz), _pts(kp)
@@ -634,3 +674,21 @@ class Context:
     def dev_match(self, d_model, Km, d_scene, Ks, D, mode, thr, d_out, d_count):
         self._chk(lib().b200_dev_match(self.h, _dptr(d_model), int(Km), _dptr(d_scene), int(Ks), int(D), int(mode),
                                        float(thr), _dptr(d_out), _dptr(d_count)))
+
+
+# ---- the reference's text dump of a view's descriptors (CAD_desc.cpp:354-370) ----------------------------------
+def read_partial_view_text(path):
+    """Partial_View<l>.txt: one float per line (std::ostream default formatting, 6 significant digits), 352 per
+    keypoint.  Returns (K, 352) float32.  Feed it to Library.add_view_descriptors with the view's keypoints."""
+    vals = np.loadtxt(path, dtype=np.float64, ndmin=1)
+    if len(vals) % 352:
+        raise ValueError("%s: %d values is not a multiple of 352" % (path, len(vals)))
+    return vals.astype(np.float32).reshape(-1, 352)
+
+
+def write_partial_view_text(path, desc):
+    """Writes descriptors the way CAD_desc.cpp does (`myfile << value << std::endl`, i.e. %g)."""
+    desc = np.asarray(desc, dtype=np.float32).reshape(-1, 352)
+    with open(path, "w") as f:
+        for v in desc.reshape(-1):
+            f.write("%g\n" % v)

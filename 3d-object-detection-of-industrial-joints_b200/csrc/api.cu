@@ -1,6 +1,9 @@
 // api.cu — the C ABI of libb200reg.so (include/b200reg.h): argument checking, host<->device staging
 // and the resident SHOT registration pipeline.  No torch types, no exceptions across the boundary.
 #include <algorithm>
+#include <array>
+#include <string>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -802,6 +805,7 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
 }
 
 /* ------------------------------------------------------------------ multi-view library */
+static const std::array<float, 16> kIdentityPose = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
 int b200_library_create(b200_ctx *ctx, b200_library **out) {
   API_ENTER(ctx);
   if (!out) return ctx->fail(B200_ERR_INVALID, "library_create: null output");
@@ -825,7 +829,132 @@ int b200_library_add_view(b200_ctx *ctx, b200_library *lib, const float *xyz, in
   b200_model *m = nullptr;
   B200_TRY(b200_model_create_shot(ctx, xyz, n, stride, kp, K, kstride, p, &m));
   lib->views.push_back(m);
+  lib->poses.push_back(kIdentityPose);
   if (view_id) *view_id = (int)lib->views.size() - 1;
+  return B200_OK;
+}
+
+int b200_library_add_view_descriptors(b200_ctx *ctx, b200_library *lib, const float *desc, const float *kp, int K,
+                                      int kstride, int *view_id) {
+  API_ENTER(ctx);
+  if (!lib || K < 0 || (K > 0 && (!desc || !kp))) return ctx->fail(B200_ERR_INVALID, "library_add_view_descriptors: bad arguments");
+  b200_model *m = new b200_model();
+  m->ctx = ctx;
+  m->K = K;
+  int rc = upload(ctx, m->desc, desc, (size_t)K * 352);
+  if (rc == B200_OK) rc = upload_points(ctx, kp, K, kstride, m->kp);
+  if (rc == B200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = B200_ERR_CUDA;
+  if (rc != B200_OK) {
+    delete m;
+    return rc;
+  }
+  lib->views.push_back(m);
+  lib->poses.push_back(kIdentityPose);
+  if (view_id) *view_id = (int)lib->views.size() - 1;
+  return B200_OK;
+}
+
+int b200_library_set_view_pose(b200_library *lib, int view, const float *pose16) {
+  if (!lib || !pose16 || view < 0 || view >= (int)lib->views.size()) return B200_ERR_INVALID;
+  memcpy(lib->poses[(size_t)view].data(), pose16, sizeof(float) * 16);
+  return B200_OK;
+}
+
+int b200_library_get_view_pose(const b200_library *lib, int view, float *pose16) {
+  if (!lib || !pose16 || view < 0 || view >= (int)lib->views.size()) return B200_ERR_INVALID;
+  memcpy(pose16, lib->poses[(size_t)view].data(), sizeof(float) * 16);
+  return B200_OK;
+}
+
+/* On-disk form (little endian): "B200LIB1", uint32 n_views, uint32 D (352), then per view: uint32 K, 16 float pose,
+ * K x 3 float keypoints, K x D float descriptors; the file ends with a uint64 FNV-1a hash of everything before it. */
+namespace {
+const char kLibMagic[8] = {'B', '2', '0', '0', 'L', 'I', 'B', '1'};
+struct Fnv {
+  uint64_t h = 1469598103934665603ull;
+  void add(const void *p, size_t n) {
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; ++i) {
+      h ^= b[i];
+      h *= 1099511628211ull;
+    }
+  }
+};
+bool put(FILE *f, Fnv &h, const void *p, size_t n) {
+  h.add(p, n);
+  return n == 0 || fwrite(p, 1, n, f) == n;
+}
+bool get(FILE *f, Fnv &h, void *p, size_t n) {
+  if (n && fread(p, 1, n, f) != n) return false;
+  h.add(p, n);
+  return true;
+}
+}  // namespace
+
+int b200_library_save(b200_ctx *ctx, const b200_library *lib, const char *path) {
+  API_ENTER(ctx);
+  if (!lib || !path) return ctx->fail(B200_ERR_INVALID, "library_save: bad arguments");
+  FILE *f = fopen(path, "wb");
+  if (!f) return ctx->fail(B200_ERR_INVALID, (std::string("library_save: cannot open ") + path).c_str());
+  Fnv h;
+  const uint32_t nv = (uint32_t)lib->views.size(), D = 352;
+  bool ok = put(f, h, kLibMagic, 8) && put(f, h, &nv, 4) && put(f, h, &D, 4);
+  int rc = B200_OK;
+  for (uint32_t v = 0; ok && v < nv; ++v) {
+    const b200_model *m = lib->views[v];
+    const uint32_t K = (uint32_t)m->K;
+    std::vector<float> desc((size_t)K * D), kp((size_t)K * 3);
+    if ((rc = b200_model_download(ctx, m, desc.data(), kp.data())) != B200_OK) break;
+    ok = put(f, h, &K, 4) && put(f, h, lib->poses[v].data(), 64) && put(f, h, kp.data(), kp.size() * 4) &&
+         put(f, h, desc.data(), desc.size() * 4);
+  }
+  const uint64_t sum = h.h;
+  ok = ok && fwrite(&sum, 8, 1, f) == 1;
+  ok = (fclose(f) == 0) && ok;
+  if (rc != B200_OK) return rc;
+  if (!ok) return ctx->fail(B200_ERR_INVALID, (std::string("library_save: write error on ") + path).c_str());
+  return B200_OK;
+}
+
+int b200_library_load(b200_ctx *ctx, const char *path, b200_library **out) {
+  API_ENTER(ctx);
+  if (!path || !out) return ctx->fail(B200_ERR_INVALID, "library_load: bad arguments");
+  *out = nullptr;
+  FILE *f = fopen(path, "rb");
+  if (!f) return ctx->fail(B200_ERR_INVALID, (std::string("library_load: cannot open ") + path).c_str());
+  Fnv h;
+  char magic[8];
+  uint32_t nv = 0, D = 0;
+  b200_library *lib = new b200_library();
+  lib->ctx = ctx;
+  int rc = B200_OK;
+  const char *why = nullptr;
+  if (!get(f, h, magic, 8) || memcmp(magic, kLibMagic, 8) != 0) why = "not a B200LIB1 file";
+  if (!why && (!get(f, h, &nv, 4) || !get(f, h, &D, 4) || D != 352 || nv > (1u << 20))) why = "bad header";
+  for (uint32_t v = 0; !why && rc == B200_OK && v < nv; ++v) {
+    uint32_t K = 0;
+    std::array<float, 16> pose;
+    if (!get(f, h, &K, 4) || K > (1u << 26) || !get(f, h, pose.data(), 64)) {
+      why = "truncated view header";
+      break;
+    }
+    std::vector<float> kp((size_t)K * 3), desc((size_t)K * D);
+    if (!get(f, h, kp.data(), kp.size() * 4) || !get(f, h, desc.data(), desc.size() * 4)) {
+      why = "truncated view data";
+      break;
+    }
+    int id = -1;
+    rc = b200_library_add_view_descriptors(ctx, lib, desc.data(), kp.data(), (int)K, 3, &id);
+    if (rc == B200_OK) lib->poses[(size_t)id] = pose;
+  }
+  uint64_t sum = 0;
+  if (!why && rc == B200_OK && (fread(&sum, 8, 1, f) != 1 || sum != h.h)) why = "checksum mismatch";
+  fclose(f);
+  if (why || rc != B200_OK) {
+    b200_library_destroy(lib);
+    return why ? ctx->fail(B200_ERR_INVALID, (std::string("library_load: ") + why).c_str()) : rc;
+  }
+  *out = lib;
   return B200_OK;
 }
 

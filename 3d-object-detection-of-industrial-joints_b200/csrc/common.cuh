@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../../include/b200reg.h"
@@ -280,6 +281,7 @@ struct b200_model {
 struct b200_library {
   b200_ctx *ctx = nullptr;
   std::vector<b200_model *> views;
+  std::vector<std::array<float, 16>> poses;  // per view: row-major 4x4 (view -> CAD pose table), identity by default
 };
 
 // scan.cu

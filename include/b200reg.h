@@ -283,6 +283,19 @@ B200_API int b200_library_add_view(b200_ctx *ctx, b200_library *lib, const float
 B200_API int b200_library_views(const b200_library *lib);
 B200_API int b200_library_view_size(const b200_library *lib, int view);
 B200_API int b200_library_download_view(b200_ctx *ctx, const b200_library *lib, int view, float *desc, float *kp);
+/* A view from descriptors computed elsewhere (K x 352) and their keypoints — e.g. the reference's own
+ * Partial_View<l>.txt dumps (CAD_desc.cpp:354-370: one float per line, 352 per keypoint). */
+B200_API int b200_library_add_view_descriptors(b200_ctx *ctx, b200_library *lib, const float *desc, const float *kp, int K,
+                                               int kstride, int *view_id);
+/* view -> CAD pose table (the reference keeps it in pose.txt, SHOT_demo.cpp:206-239): row-major 4x4 per view,
+ * identity until set; carried by the library file. */
+B200_API int b200_library_set_view_pose(b200_library *lib, int view, const float *pose16);
+B200_API int b200_library_get_view_pose(const b200_library *lib, int view, float *pose16);
+/* Binary library file replacing the text dumps: "B200LIB1", uint32 views, uint32 D, per view {uint32 K, 16 float pose,
+ * K x 3 float keypoints, K x D float descriptors}, uint64 FNV-1a of the preceding bytes; little endian.
+ * b200_library_load rejects a wrong magic, a truncated file or a checksum mismatch (B200_ERR_INVALID). */
+B200_API int b200_library_save(b200_ctx *ctx, const b200_library *lib, const char *path);
+B200_API int b200_library_load(b200_ctx *ctx, const char *path, b200_library **out);
 /* Instances of all views, concatenated in view order: inst_view[i] = view of instance i; transforms, inst_offsets
  * (max_inst + 1) and inst_corrs (index_query = keypoint index WITHIN the view) as in b200_gc_recognize;
  * view_n_corrs (nullable, one per view) = correspondences found for that view.  p->max_instances bounds the

@@ -60,3 +60,25 @@ def test_keypoint_extractors(synth):
     # uniform sampling returns input points; voxel grid returns centroids inside the voxel
     assert all((m == u).all(1).any() for u in us[:20])
     assert np.all(np.floor(vg / np.float32(0.02)) == np.floor(us / np.float32(0.02)))
+
+
+def test_partial_view_text_format(tmp_path):
+    """The reference dumps a view's descriptors as text, one float per line (CAD_desc.cpp:354-370); the reader and
+    writer of that format need no GPU."""
+    import importlib
+    import numpy as np
+    from conftest import PKG_NAME
+    binding = importlib.import_module(PKG_NAME + ".binding")
+    rng = np.random.Generator(np.random.PCG64(1))
+    d = rng.uniform(0, 0.3, (7, 352)).astype(np.float32)
+    d[2, 5] = 0.0
+    p = str(tmp_path / "Partial_View3.txt")
+    binding.write_partial_view_text(p, d)
+    lines = open(p).read().split("\n")
+    assert len(lines) == 7 * 352 + 1 and lines[2 * 352 + 5] == "0"
+    back = binding.read_partial_view_text(p)
+    assert back.shape == (7, 352) and np.abs(back - d).max() <= 5e-7 * 3 + 1e-6 * np.abs(d).max()
+    open(p, "a").write("0.5\n")
+    import pytest
+    with pytest.raises(ValueError):
+        binding.read_partial_view_text(p)

@@ -677,3 +677,63 @@ def test_board_lrf_parity(ctx, orc, synth, small, b200):
     compare(a, o, 0.01)
     cm.close()
     cs.close()
+
+
+# ------------------------------------------------------------------------------------------ library file
+def test_library_file_roundtrip(ctx, orc, synth, b200, tmp_path):
+    """The binary descriptor library (replaces the reference's Partial_View<l>.txt dumps, CAD_desc.cpp:354-370): save →
+    load in a second context → identical descriptors, keypoints, pose table and registration results; a view built
+    from the reference's text format equals the original to the 6 digits the text keeps; damaged files are refused."""
+    p = b200.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=512)
+    scene = synth.make_scene(("y",), 40000, scene_id=1)
+    kps = synth.uniform_sampling(scene, 0.03)
+    lib = b200.Library(ctx)
+    for joint, v in (("y", 3), ("y", 20), ("diagonal", 7)):
+        cloud = synth.make_partial_view(joint, v, 5000)
+        lib.add_view(cloud, synth.uniform_sampling(cloud, 0.02), p)
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, 3] = [0.1, -0.2, 0.3]
+    lib.set_view_pose(1, pose)
+    path = str(tmp_path / "joints.b200lib")
+    lib.save(path)
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"B200LIB1" and np.frombuffer(raw[8:16], "<u4").tolist() == [3, 352]
+    assert len(raw) == 16 + sum(4 + 64 + lib.view_size(v) * (3 + 352) * 4 for v in range(3)) + 8
+    ctx2 = b200.Context(0)
+    lib2 = b200.Library.load(ctx2, path)
+    assert lib2.views == 3
+    for v in range(3):
+        d1, k1 = lib.download_view(v)
+        d2, k2 = lib2.download_view(v)
+        assert np.array_equal(d1, d2, equal_nan=True) and np.array_equal(k1, k2)
+        assert np.array_equal(lib2.view_pose(v), pose if v == 1 else np.eye(4))
+    r1 = lib.register_scene(scene, kps, p)
+    r2 = lib2.register_scene(scene, kps, p)
+    assert r1["n_instances"] == r2["n_instances"] > 0 and np.array_equal(r1["transforms"], r2["transforms"])
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(r1["instances"], r2["instances"]))
+    # the reference's text dump: one float per line, 6 significant digits
+    d0, k0 = lib.download_view(0)
+    txt = str(tmp_path / "Partial_View0.txt")
+    ok = ~np.isnan(d0[:, 0])
+    b200.write_partial_view_text(txt, d0[ok])
+    dt = b200.read_partial_view_text(txt)
+    assert dt.shape == d0[ok].shape and np.abs(dt - d0[ok]).max() < 1e-5
+    lib3 = b200.Library(ctx2)
+    assert lib3.add_view_descriptors(dt, k0[ok]) == 0
+    r3 = lib3.register_scene(scene, kps, p)
+    n0 = int((r1["view"] == 0).sum())
+    assert abs(r3["n_instances"] - n0) <= max(1, n0 // 10)
+    # damaged files
+    for name, data in (("trunc", raw[:len(raw) // 2]), ("magic", b"X" + raw[1:]),
+                       ("flip", raw[:4000] + bytes([raw[4000] ^ 1]) + raw[4001:])):
+        bad = str(tmp_path / (name + ".b200lib"))
+        open(bad, "wb").write(data)
+        with pytest.raises(b200.B200Error):
+            b200.Library.load(ctx2, bad)
+    with pytest.raises(b200.B200Error):
+        b200.Library.load(ctx2, str(tmp_path / "missing.b200lib"))
+    lib3.close()
+    lib2.close()
+    ctx2.close()
+    lib.close()
