@@ -10,6 +10,52 @@
 
 #include "common.cuh"
 
+WideGate *wide_gate(int device) {
+  static WideGate gates[64];
+  static const bool on = [] {
+    const char *e = getenv("B200_WIDE_GATE");
+    return e && e[0] == '1';
+  }();
+  if (!on || device < 0 || device >= 64) return nullptr;
+  return &gates[device];
+}
+
+namespace {
+__global__ void mailbox_publish_kernel(const unsigned *__restrict__ src, unsigned *__restrict__ dst, int words) {
+  if ((int)threadIdx.x < words) dst[threadIdx.x] = src[threadIdx.x];
+}
+struct SmallWords {
+  unsigned w[16];
+};
+__global__ void write_small_kernel(unsigned *__restrict__ dst, SmallWords v, int words) {
+  if ((int)threadIdx.x < words) dst[threadIdx.x] = v.w[threadIdx.x];
+}
+}  // namespace
+
+int readback_small(b200_ctx *ctx, const void *d_src, void *h_dst, size_t bytes) {
+  if (bytes == 0) return B200_OK;
+  if (bytes > B200_MAILBOX_BYTES || (bytes & 3)) return ctx->fail(B200_ERR_INVALID, "readback_small: bad size");
+  if (!ctx->mailbox_host) {
+    B200_CUDA(ctx, cudaHostAlloc(&ctx->mailbox_host, B200_MAILBOX_BYTES, cudaHostAllocMapped));
+    B200_CUDA(ctx, cudaHostGetDevicePointer(&ctx->mailbox_dev, ctx->mailbox_host, 0));
+  }
+  mailbox_publish_kernel<<<1, 64, 0, ctx->stream>>>((const unsigned *)d_src, (unsigned *)ctx->mailbox_dev, (int)(bytes / 4));
+  B200_LAUNCHED(ctx);
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(h_dst, ctx->mailbox_host, bytes);
+  return B200_OK;
+}
+
+int write_small(b200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+  if (bytes == 0) return B200_OK;
+  if (bytes > sizeof(SmallWords) || (bytes & 3)) return ctx->fail(B200_ERR_INVALID, "write_small: bad size");
+  SmallWords v;
+  memcpy(v.w, h_src, bytes);
+  write_small_kernel<<<1, 32, 0, ctx->stream>>>((unsigned *)d_dst, v, (int)(bytes / 4));
+  B200_LAUNCHED(ctx);
+  return B200_OK;
+}
+
 namespace {
 
 std::string g_error = "";
@@ -35,9 +81,14 @@ int upload(b200_ctx *ctx, DevBuf<T> &buf, const T *host, size_t count) {
   return B200_OK;
 }
 
+// Result downloads are enqueued only once the stream has drained: a D2H copy waiting in the (shared, in-order)
+// copy-engine queue for its own stream's kernels would hold up the copies and memsets of every other context.
 template <class T>
 int download(b200_ctx *ctx, T *host, const T *dev, size_t count) {
-  if (count) B200_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  if (count) {
+    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   return B200_OK;
 }
 
@@ -74,6 +125,8 @@ int scene_pipeline(b200_ctx *ctx, const b200_model *model, b200_cloud *scene, co
                    float *d_desc_out) {
   DevBuf<float> normals, desc_tmp;
   B200_TRY(normals.alloc(ctx, (size_t)std::max(scene->n, 1) * 4));
+  WideSection wide;  // this scene's turn for the GPU-wide stages; dev_gc ends it before the grouping kernel
+  B200_TRY(wide.enter(ctx));
   B200_TRY(dev_normals(ctx, scene, scene->raw.p, scene->n, true, p->normal_k, p->normal_radius, nullptr, normals.p));
   float *d_desc = d_desc_out;
   if (!d_desc) {
@@ -198,6 +251,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   ctx->arena_destroy();
   if (ctx->mt_state) cudaFree(ctx->mt_state);
+  if (ctx->mailbox_host) cudaFreeHost(ctx->mailbox_host);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200_OK;
@@ -766,8 +820,10 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
   B200_TRY(check_params(ctx, p));
   *n_inst = 0;
   if (n_corrs) *n_corrs = 0;
+  HostTrace tr;
   b200_cloud *scene = nullptr;
   B200_TRY(cloud_upload(ctx, scene_xyz, n, stride, false, &scene));
+  tr.tick("e2e cloud_upload");
   int rc = B200_OK;
   do {
     DevBuf<float4> dkp;
@@ -786,6 +842,7 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
     if ((rc = scene_pipeline(ctx, model, scene, dkp.p, Ks, p, dT.p, doffs.p, dcnts.p, dic.p, cap, dn.p, dcorrs.p,
                              dnc.p, nullptr)) != B200_OK)
       break;
+    tr.tick("e2e pipeline issue");
     int nc = 0;
     if ((rc = download(ctx, &nc, dnc.p, 1)) != B200_OK) break;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -793,12 +850,14 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
       rc = ctx->fail_cuda(e, "register_scene sync", __FILE__, __LINE__);
       break;
     }
+    tr.tick("e2e wait");
     if (n_corrs) *n_corrs = nc;
     if (corrs_out && nc > 0) {
       if ((rc = download(ctx, corrs_out, dcorrs.p, (size_t)nc)) != B200_OK) break;
     }
     rc = download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, p->max_instances, cap, transforms, inst_offsets,
                             inst_corrs, corr_cap, n_inst);
+    tr.tick("e2e download");
   } while (0);
   delete scene;
   return rc;

@@ -9,7 +9,11 @@
 
 #include <string>
 #include <array>
+#include <mutex>
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
+#include <chrono>
 
 #include "../../include/b200reg.h"
 
@@ -43,7 +47,10 @@ struct ArenaBlock {
   bool used;
 };
 
+struct WideSection;
+
 struct b200_ctx {
+  WideSection *wide = nullptr;  // set while this context is inside the wide-stage gate (see WideGate)
   std::vector<ArenaBlock> arena;
   size_t arena_bytes = 0;
   void *arena_alloc(size_t bytes, cudaError_t *err) {
@@ -87,6 +94,10 @@ struct b200_ctx {
   int sm_count = 148;
   size_t smem_optin = 0;
   int64_t launches = 0;
+  // small device->host readbacks go through mapped pinned memory written by a kernel, not through the copy engine
+  // (see readback_small in api.cu)
+  void *mailbox_host = nullptr;
+  void *mailbox_dev = nullptr;
   uint32_t rand_state[31] = {0};  // glibc rand() stream for BOARD's random axis (board.cu)
   bool rand_seeded = false;
   double last_mean_nbrs = 0.0;
@@ -283,6 +294,84 @@ struct b200_library {
   std::vector<b200_model *> views;
   std::vector<std::array<float, 16>> poses;  // per view: row-major 4x4 (view -> CAD pose table), identity by default
 };
+
+// B200_TRACE=1: host-side wall time between ticks (debugging aid)
+struct HostTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  HostTrace() : on(getenv("B200_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void tick(const char *what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    double ms = std::chrono::duration<double, std::milli>(n - t).count();
+    if (ms > 0.3) fprintf(stderr, "[b200 trace] %s: %.3f ms host\n", what, ms);
+    t = n;
+  }
+};
+
+// Wide-stage gate.  A scene registration is a run of GPU-wide stages (normals, descriptors, matching, the
+// consistency bitmap: every SM busy) followed by the grouping kernel, a latency-bound chain on one 8-CTA cluster.
+// With several scenes in flight on one device (one context + stream + host thread each) the step rate is best when
+// the wide runs of different scenes do not overlap each other but do overlap the grouping of the previous scenes —
+// and worst when the lanes fall into lockstep (all in their wide run, then all in grouping with 140 SMs idle).  The
+// gate makes the good schedule deterministic: contexts take turns for the wide run, in arrival order; a turn ends
+// when the grouping kernel is about to be enqueued, by recording an event the next turn's stream waits on.
+// Measured (target workload): gated 9.4 ms/scene with any number of lanes >= 2; free-running lanes 9.9 (2 lanes),
+// 8.0 (4 lanes) once nothing small goes through the copy engines (readback_small).  Free running is therefore the
+// default and the gate is opt-in (B200_WIDE_GATE=1) for deployments that can afford only two lanes of memory.
+struct WideGate {
+  std::mutex mu;
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+};
+WideGate *wide_gate(int device);  // api.cu; nullptr unless B200_WIDE_GATE=1
+
+struct WideSection {
+  b200_ctx *ctx = nullptr;
+  WideGate *g = nullptr;
+  bool held = false;
+  int enter(b200_ctx *c) {
+    ctx = c;
+    g = wide_gate(c->device);
+    if (!g) return B200_OK;
+    g->mu.lock();
+    held = true;
+    c->wide = this;
+    if (!g->ev) {
+      cudaError_t e = cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming);
+      if (e != cudaSuccess) {
+        g->ev = nullptr;
+        leave();
+        return c->fail_cuda(e, "cudaEventCreate (wide gate)", __FILE__, __LINE__);
+      }
+    }
+    if (g->recorded) {
+      cudaError_t e = cudaStreamWaitEvent(c->stream, g->ev, 0);
+      if (e != cudaSuccess) {
+        leave();
+        return c->fail_cuda(e, "cudaStreamWaitEvent (wide gate)", __FILE__, __LINE__);
+      }
+    }
+    return B200_OK;
+  }
+  void leave() {
+    if (!held) return;
+    if (g->ev && cudaEventRecord(g->ev, ctx->stream) == cudaSuccess) g->recorded = true;
+    ctx->wide = nullptr;
+    held = false;
+    g->mu.unlock();
+  }
+  ~WideSection() { leave(); }
+};
+
+// api.cu — small transfers that stay off the copy engines.  The copy-engine queues are shared by all streams and run
+// in order: a tiny D2H readback enqueued behind another context's pending result download (which waits for that
+// context's whole scene) stalls this context's host for the length of the other scene.  readback_small: up to 256
+// bytes device -> host through a kernel writing mapped pinned memory, then a stream synchronise.  write_small: up
+// to 64 bytes host -> device as kernel arguments.
+constexpr size_t B200_MAILBOX_BYTES = 256;
+int readback_small(b200_ctx *ctx, const void *d_src, void *h_dst, size_t bytes);
+int write_small(b200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 
 // scan.cu
 int exclusive_scan_i32(b200_ctx *ctx, const int *d_in, int *d_out, int n, int *d_total /*nullable*/);

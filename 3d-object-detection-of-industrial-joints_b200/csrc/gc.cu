@@ -1363,8 +1363,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   int C_eff = C_cap;
   if (C_cap > GC_ASYNC_CAP) {
     int C_now = 0;
-    B200_CUDA(ctx, cudaMemcpyAsync(&C_now, d_C, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_TRY(readback_small(ctx, d_C, &C_now, sizeof(int)));
     C_eff = std::max(1, std::min(C_now, C_cap));
     if (C_eff > GC_MAX_C) return ctx->fail(B200_ERR_CAPACITY, "gc: more than 524288 correspondences");
   }
@@ -1408,6 +1407,9 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
     B200_TRY(dbg.zero());
     ga.dbg = dbg.p;
   }
+  // everything up to here keeps the whole GPU busy; the grouping kernel is one cluster: the next scene's wide
+  // stages may start beside it
+  if (ctx->wide) ctx->wide->leave();
   {
     StageScope st_(ctx, ST_GC_GROUP);
     const size_t row_bytes = (size_t)row_words_cap * sizeof(unsigned);

@@ -112,20 +112,6 @@ __global__ void cell_scatter_kernel(const float4 *__restrict__ pts, int n, const
   sorted[slot] = p;
 }
 
-// B200_TRACE=1: host-side wall time of each step of a grid build (debugging aid)
-struct HostTrace {
-  bool on;
-  std::chrono::steady_clock::time_point t;
-  HostTrace() : on(getenv("B200_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
-  void tick(const char *what) {
-    if (!on) return;
-    auto n = std::chrono::steady_clock::now();
-    double ms = std::chrono::duration<double, std::milli>(n - t).count();
-    if (ms > 1.0) fprintf(stderr, "[b200 trace] %s: %.3f ms host\n", what, ms);
-    t = n;
-  }
-};
-
 int build_grid(b200_cloud *c, float cell, DeviceGrid &g) {
   HostTrace tr;
   b200_ctx *ctx = c->ctx;
@@ -236,18 +222,16 @@ int cloud_upload(b200_ctx *ctx, const float *xyz, int n, int stride, bool on_dev
   DevBuf<unsigned> box;
   if ((rc = box.alloc(ctx, 8)) != B200_OK) return bail(rc);
   unsigned init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
-  cudaError_t e = cudaMemcpyAsync(box.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
-  if (e != cudaSuccess) return bail(ctx->fail_cuda(e, "H2D box init", __FILE__, __LINE__));
+  if ((rc = write_small(ctx, box.p, init, sizeof(init))) != B200_OK) return bail(rc);
   if (n > 0) {
     int blocks = std::min(ceil_div(n, 256), ctx->sm_count * 8);
     bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(c->raw.p, n, box.p, reinterpret_cast<int *>(box.p + 6));
     ctx->launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) return bail(ctx->fail_cuda(e, "bbox_kernel", __FILE__, __LINE__));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(ctx->fail_cuda(e, "bbox_kernel", __FILE__, __LINE__));
   }
   unsigned hbox[8];
-  e = cudaMemcpyAsync(hbox, box.p, sizeof(hbox), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) return bail(ctx->fail_cuda(e, "bbox readback", __FILE__, __LINE__));
+  if ((rc = readback_small(ctx, box.p, hbox, sizeof(hbox))) != B200_OK) return bail(rc);
   c->n_valid = (int)hbox[6];
   if (c->n_valid > 0) {
     for (int a = 0; a < 3; ++a) {

@@ -775,8 +775,7 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
   B200_TRY(stats.alloc(ctx, 2));
   B200_TRY(dev_radius_count(ctx, *g, d_kp, K, radius, counts.p, stats.p));
   unsigned long long hstats[2];
-  B200_CUDA(ctx, cudaMemcpyAsync(hstats, stats.p, sizeof(hstats), cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_TRY(readback_small(ctx, stats.p, hstats, sizeof(hstats)));
   const int max_count = (int)hstats[0];
   ctx->last_max_nbrs = max_count;
   ctx->last_mean_nbrs = (double)hstats[1] / K;

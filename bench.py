@@ -349,7 +349,7 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e2e_steps = max(2 * L, min(args.steps, 12))
+    e2e_steps = max(6 * L, args.steps)   # enough steps per lane for the lanes to fall out of lockstep
     gate.reset()
     t0 = time.perf_counter()
     sharding.run_lanes(L, e2e_steps, e2e_step)
@@ -458,7 +458,7 @@ def main():
     ap.add_argument("--model-points", type=int, default=50_000)
     ap.add_argument("--cpu-sample", type=int, default=1500, help="scene keypoints in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=4, help="scenes in flight per GPU (context + stream + host thread each)")
+    ap.add_argument("--lanes", type=int, default=6, help="scenes in flight per GPU (context + stream + host thread each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner)
