@@ -33,34 +33,46 @@
 namespace {
 
 // ---- sort by (distance, original position): rank by counting -----------------------------------
+// A CTA ranks RANK_ITEMS correspondences: lane = item, warp = one eighth of every 256-key tile, partial counts
+// merged in shared memory (32 items per CTA give ~800 CTAs for the 25 k correspondences of the target scene; one
+// item per thread and 256 per CTA left two thirds of the SMs idle).
+constexpr int RANK_ITEMS = 32;
+constexpr int RANK_TILE = 2048;  // keys staged per barrier pair
 __global__ void __launch_bounds__(256)
     gc_rank_kernel(const b200_corr *__restrict__ corrs, const int *__restrict__ d_C, int C_cap,
                    const float4 *__restrict__ model_kp, const float4 *__restrict__ scene_kp,
                    b200_corr *__restrict__ sorted, float4 *__restrict__ mp, float4 *__restrict__ sp) {
-  __shared__ unsigned long long tile[256];
+  __shared__ unsigned long long tile[RANK_TILE];
+  __shared__ int s_rank[RANK_ITEMS];
   const int C = min(*d_C, C_cap);
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (blockIdx.x * 256 >= C) return;
+  if (blockIdx.x * RANK_ITEMS >= C) return;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * RANK_ITEMS + lane;
   unsigned long long mykey = 0;
-  b200_corr mine;
-  if (i < C) {
-    mine = corrs[i];
-    mykey = ((unsigned long long)__float_as_uint(mine.distance) << 32) | (unsigned)i;
-  }
+  if (i < C) mykey = ((unsigned long long)__float_as_uint(corrs[i].distance) << 32) | (unsigned)i;
+  if (threadIdx.x < RANK_ITEMS) s_rank[threadIdx.x] = 0;
   int rank = 0;
-  for (int base = 0; base < C; base += 256) {
-    const int j = base + threadIdx.x;
+  for (int base = 0; base < C; base += RANK_TILE) {
     __syncthreads();
-    tile[threadIdx.x] = (j < C) ? (((unsigned long long)__float_as_uint(corrs[j].distance) << 32) | (unsigned)j)
-                                : ~0ull;
+#pragma unroll
+    for (int u = 0; u < RANK_TILE / 256; ++u) {
+      const int j = base + u * 256 + threadIdx.x;
+      tile[u * 256 + threadIdx.x] =
+          (j < C) ? (((unsigned long long)__float_as_uint(corrs[j].distance) << 32) | (unsigned)j) : ~0ull;
+    }
     __syncthreads();
-#pragma unroll 8
-    for (int t = 0; t < 256; ++t) rank += (tile[t] < mykey) ? 1 : 0;
+    const unsigned long long *mine = tile + slice * (RANK_TILE / 8);
+#pragma unroll 16
+    for (int t = 0; t < RANK_TILE / 8; ++t) rank += (mine[t] < mykey) ? 1 : 0;
   }
-  if (i < C) {
-    sorted[rank] = mine;
-    mp[rank] = model_kp[mine.index_query];
-    sp[rank] = scene_kp[mine.index_match];
+  atomicAdd(&s_rank[lane], rank);
+  __syncthreads();
+  if (slice == 0 && i < C) {
+    const b200_corr mine = corrs[i];
+    const int r = s_rank[lane];
+    sorted[r] = mine;
+    mp[r] = model_kp[mine.index_query];
+    sp[r] = scene_kp[mine.index_match];
   }
 }
 
@@ -114,6 +126,10 @@ __global__ void __launch_bounds__(ADJ_THREADS)
   const int w0 = blockIdx.x * ADJ_WORDS;
   const int i0 = blockIdx.y * ADJ_ROWS;
   if (w0 >= row_words || i0 >= C) return;
+  // The relation is symmetric (gc_fits is bit-for-bit symmetric in its two correspondences): a CTA evaluates only
+  // the 128-column groups on or right of its 128-row block and writes the groups strictly right of it a second time
+  // transposed (32 x 32 bit blocks turned by ballots), which fills the skipped groups of the rows below.
+  if ((w0 + ADJ_WORDS) * 32 <= i0) return;
   const int tid = threadIdx.x;
   for (int t = tid; t < ADJ_WORDS * 32; t += ADJ_THREADS) {
     const int j = w0 * 32 + t;
@@ -122,13 +138,21 @@ __global__ void __launch_bounds__(ADJ_THREADS)
     s_s[t] = in ? sp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
+  const int lane = tid & 31;
   const int i = i0 + (tid & (ADJ_ROWS - 1));
-  const int wbase = (tid / ADJ_ROWS) * (ADJ_WORDS / 2);  // 16 words per thread
-  if (i >= C) return;
-  const float4 mi = mp[i], si = sp[i];
-  unsigned *row = adj + (size_t)i * row_words + w0 + wbase;
+  const int ib_word = (i0 >> 5) + ((tid & (ADJ_ROWS - 1)) >> 5);  // word index of this warp's 32 rows
+  const int wbase = (tid / ADJ_ROWS) * (ADJ_WORDS / 2);           // 16 words per thread
+  const bool valid = i < C;
+  const float4 mi = valid ? mp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 si = valid ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned *row = adj + (size_t)(valid ? i : 0) * row_words + w0 + wbase;
 #pragma unroll 1
   for (int wq = 0; wq < ADJ_WORDS / 2; wq += 4) {
+    const int gw0 = w0 + wbase + wq;  // first of four words = 128 aligned columns
+    if (gw0 >= row_words) break;
+    const int jg = gw0 * 32;
+    if (jg + 128 <= i0) continue;  // left of the row block: written by the transposed stores of the rows above
+    const bool mirror = jg >= i0 + ADJ_ROWS;
     unsigned out[4];
 #pragma unroll
     for (int w4 = 0; w4 < 4; ++w4) {
@@ -140,13 +164,23 @@ __global__ void __launch_bounds__(ADJ_THREADS)
         const bool ok = gc_fits(mi, si, s_m[t0 + b], s_s[t0 + b], g_lo, g_hi, gc_size);
         bits |= (ok ? 1u : 0u) << b;
       }
-      const int gw = w0 + wbase + w;  // global word index
+      const int gw = gw0 + w4;  // global word index
       const int j0 = gw * 32;
       if (j0 + 32 > C) bits &= (j0 >= C) ? 0u : ((1u << (C - j0)) - 1u);
       if ((i >> 5) == gw) bits &= ~(1u << (i & 31));
+      if (!valid) bits = 0u;
       out[w4] = bits;
+      if (mirror && j0 < C) {  // warp-uniform
+        unsigned tw = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const unsigned v = __ballot_sync(0xffffffffu, (bits >> b) & 1u);
+          if (lane == b) tw = v;
+        }
+        if (j0 + lane < C) adj[(size_t)(j0 + lane) * row_words + ib_word] = tw;
+      }
     }
-    if (w0 + wbase + wq < row_words) *reinterpret_cast<uint4 *>(row + wq) = make_uint4(out[0], out[1], out[2], out[3]);
+    if (valid) *reinterpret_cast<uint4 *>(row + wq) = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
 
@@ -1379,7 +1413,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   B200_TRY(adj.alloc(ctx, (size_t)C_eff * row_words_cap));
   {
     StageScope st_(ctx, ST_GC_SORT);
-    gc_rank_kernel<<<ceil_div(C_eff, 256), 256, 0, ctx->stream>>>(d_corrs, d_C, C_eff, d_model_kp, d_scene_kp,
+    gc_rank_kernel<<<ceil_div(C_eff, RANK_ITEMS), 256, 0, ctx->stream>>>(d_corrs, d_C, C_eff, d_model_kp, d_scene_kp,
                                                                  sorted.p, mp.p, sp.p);
     B200_LAUNCHED(ctx);
   }
