@@ -53,14 +53,22 @@ def unpack_gathered(counts, words):
 
 def register_scene_batch(ctx, model, scenes, keypoints, params, rank=0, world=1, group=None, device=None):
     """BASELINE.json config 5: a batch of scenes sharded round-robin over the ranks (scene s -> rank s mod world),
-    every rank registering its scenes against the replicated model library through the host-buffer C-ABI call,
+    every rank registering its scenes (ctx: one context, or a list of contexts = lanes working through the rank's
+    scenes concurrently) against the replicated model library through the host-buffer C-ABI call,
     then ONE gather of the per-scene correspondence lists.  Returns (local, gathered): `local` maps scene id ->
     result dict of this rank's scenes (poses and instances stay on the rank that found them); `gathered` maps
     every scene id of the batch -> its correspondence list (structured numpy array), on every rank.
     world == 1 needs no process group."""
     import torch
     mine = scenes_for_rank(len(scenes), rank, world)
-    local = {s: ctx.register_scene_shot(model, scenes[s], keypoints[s], params) for s in mine}
+    lanes = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx]   # several contexts = several scenes in flight
+    local = {}
+
+    def one(lane, k):
+        s = mine[k]
+        local[s] = lanes[lane].register_scene_shot(model, scenes[s], keypoints[s], params)
+
+    run_lanes(len(lanes), len(mine), one)
     if world == 1:
         return local, {s: local[s]["corrs"] for s in mine}
     import torch.distributed as dist

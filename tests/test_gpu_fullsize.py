@@ -165,3 +165,81 @@ def test_fullsize_keypoint_filters(full, orc):
     vg = ctx.voxel_grid(wl["scene"], 0.01)
     assert len(vg) == len(us)                                    # same lattice, same occupied leaves, same order
     assert np.abs(vg - us).max() <= 0.01 * np.sqrt(3) + 1e-6     # a centroid and the kept point share a leaf
+
+
+def test_config4_view_library_fullsize(b200, synth, tmp_path):
+    """BASELINE.json config 4 at its size: 64 rendered partial views x 3 CAD joints = 192 views in one resident
+    library, one scene matched against all of them.  Properties: per-view results equal the single-model pipeline
+    (sampled views), instances reference keypoints of their own view, poses are rigid, and the library file
+    round-trips bit for bit."""
+    p = b200.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=3,
+                         max_instances=512)
+    ctx = b200.Context(0)
+    lib = b200.Library(ctx)
+    views = []
+    for joint in ("y", "diagonal", "horizontal"):
+        for v in range(64):
+            cloud = synth.make_partial_view(joint, v, 4000)
+            kp = synth.uniform_sampling(cloud, 0.02)
+            lib.add_view(cloud, kp, p)
+            views.append((cloud, kp))
+    assert lib.views == 192
+    scene = synth.make_scene(("y", "diagonal", "horizontal"), 150000, scene_id=7)
+    kps = synth.uniform_sampling(scene, 0.03)
+    res = lib.register_scene(scene, kps, p, max_inst=98304)
+    n = res["n_instances"]
+    assert n > 0 and np.all(np.diff(res["view"]) >= 0) and len(res["view_n_corrs"]) == 192
+    for i in range(n):
+        v = int(res["view"][i])
+        ic = res["instances"][i]
+        assert len(ic) >= 3 and ic["index_query"].max() < len(views[v][1]) and ic["index_match"].max() < len(kps)
+    R = res["transforms"][:, :3, :3].astype(np.float64)
+    assert np.abs(np.einsum("nij,nkj->nik", R, R) - np.eye(3)).max() < 1e-4
+    assert np.abs(np.linalg.det(R) - 1.0).max() < 1e-4
+    for v in (5, 77, 150):
+        m = ctx.model_create_shot(views[v][0], views[v][1], p)
+        single = ctx.register_scene_shot(m, scene, kps, p)
+        mine = [i for i in range(n) if res["view"][i] == v]
+        assert len(mine) == single["n_instances"] and res["view_n_corrs"][v] == len(single["corrs"])
+        for i, ins in zip(mine, single["instances"]):
+            assert res["instances"][i].tobytes() == ins.tobytes()
+        m.close()
+    path = str(tmp_path / "views192.b200lib")
+    lib.save(path)
+    lib2 = b200.Library.load(ctx, path)
+    res2 = lib2.register_scene(scene, kps, p, max_inst=98304)
+    assert res2["n_instances"] == n and np.array_equal(res2["transforms"], res["transforms"])
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(res["instances"], res2["instances"]))
+    lib2.close()
+    lib.close()
+    ctx.close()
+
+
+def test_config5_scene_batch_lanes_are_deterministic(b200, synth, pkg):
+    """BASELINE.json config 5 (500 k-point scenes, a batch of 12 on one GPU): the scenes of a rank go through four
+    lanes (contexts driven by their own host threads, kernels of different scenes interleaving on the GPU).  The
+    results must be bit-identical to the same scenes registered one after the other on a single context."""
+    sharding = importlib.import_module(pkg.__name__ + ".sharding")
+    p = b200.shot_params(normal_k=20, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=4096)
+    model = synth.make_model("y", 20000)
+    kpm = synth.uniform_sampling(model, 0.005)
+    scenes = [synth.make_kinect_scene(("y", "diagonal", "horizontal"), target_points=500_000, scene_id=20 + (s % 3))
+              for s in range(3)]
+    scenes = [scenes[s % 3] for s in range(12)]
+    kps = [synth.uniform_sampling(sc, 0.012) for sc in scenes[:3]]
+    kps = [kps[s % 3] for s in range(12)]
+    ctxs = [b200.Context(0) for _ in range(4)]
+    m = ctxs[0].model_create_shot(model, kpm, p)
+    seq, _ = sharding.register_scene_batch(ctxs[0], m, scenes[:3], kps[:3], p)
+    par, gathered = sharding.register_scene_batch(ctxs, m, scenes, kps, p)
+    assert sorted(par) == list(range(12)) and sorted(gathered) == list(range(12))
+    for s in range(12):
+        a, b = par[s], seq[s % 3]
+        assert a["n_instances"] == b["n_instances"] > 0
+        assert a["corrs"].tobytes() == b["corrs"].tobytes() == gathered[s].tobytes()
+        assert np.array_equal(a["transforms"], b["transforms"])
+        assert all(x.tobytes() == y.tobytes() for x, y in zip(a["instances"], b["instances"]))
+    m.close()
+    for c in ctxs:
+        c.close()
