@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
     "b200_library_add_view_descriptors", "b200_library_set_view_pose", "b200_library_get_view_pose",
-    "b200_library_save", "b200_library_load",
+    "b200_library_save", "b200_library_load", "b200_register_scene_batch_shot",
     "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
     "b200_hough3d_recognize",
     "b200_icp_align",
@@ -143,6 +143,9 @@ def lib():
             "b200_library_get_view_pose": [vp, i, fp],
             "b200_library_save": [vp, vp, C.c_char_p],
             "b200_library_load": [vp, C.c_char_p, C.POINTER(vp)],
+            "b200_register_scene_batch_shot": [i, vp, i, C.POINTER(fp), ip, i, C.POINTER(fp), ip, i, C.POINTER(ShotParams), i,
+                                               C.POINTER(fp), C.POINTER(ip), C.POINTER(C.POINTER(Corr)), ip, ip,
+                                               C.POINTER(C.POINTER(Corr)), ip, ip],
             "b200_library_views": [vp],
             "b200_library_view_size": [vp, i],
             "b200_library_download_view": [vp, vp, i, fp, fp],
@@ -674,6 +677,43 @@ class Context:
     def dev_match(self, d_model, Km, d_scene, Ks, D, mode, thr, d_out, d_count):
         self._chk(lib().b200_dev_match(self.h, _dptr(d_model), int(Km), _dptr(d_scene), int(Ks), int(D), int(mode),
                                        float(thr), _dptr(d_out), _dptr(d_count)))
+
+
+def register_scene_batch(model, scenes, keypoints, params, lanes=4, device=0):
+    """b200_register_scene_batch_shot: a batch of scenes against one resident model, `lanes` scenes in flight on
+    `device` (contexts and host threads live inside the library).  Returns one result dict per scene, like
+    Context.register_scene_shot."""
+    n = len(scenes)
+    scenes = [_pts(x) for x in scenes]
+    keypoints = [_pts(k) for k in keypoints]
+    stride = scenes[0].shape[1] if n else 3
+    kstride = keypoints[0].shape[1] if n else 3
+    assert all(x.shape[1] == stride for x in scenes) and all(k.shape[1] == kstride for k in keypoints)
+    mi = params.max_instances
+    fp, ip, cp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(Corr)
+    T = [np.empty((mi, 16), dtype=np.float32) for _ in range(n)]
+    off = [np.empty(mi + 1, dtype=np.int32) for _ in range(n)]
+    ic = [np.empty(max(len(k), 1), dtype=CORR_DTYPE) for k in keypoints]
+    co = [np.empty(max(len(k), 1), dtype=CORR_DTYPE) for k in keypoints]
+    npts = np.array([len(x) for x in scenes], dtype=np.int32)
+    nkp = np.array([len(k) for k in keypoints], dtype=np.int32)
+    cap = np.array([len(a) for a in ic], dtype=np.int32)
+    n_inst = np.zeros(max(n, 1), dtype=np.int32)
+    n_corr = np.zeros(max(n, 1), dtype=np.int32)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    rc = lib().b200_register_scene_batch_shot(
+        int(device), model.h, n, (fp * n)(*[_f(x) for x in scenes]), _i(npts), stride,
+        (fp * n)(*[_f(k) for k in keypoints]), _i(nkp), kstride, C.byref(params), int(lanes),
+        (fp * n)(*[_f(t) for t in T]), (ip * n)(*[_i(o) for o in off]), (cp * n)(*[_c(a) for a in ic]), _i(cap),
+        _i(n_inst), (cp * n)(*[_c(a) for a in co]), _i(n_corr), _i(status))
+    if rc != OK:
+        raise B200Error(rc, lib().b200_last_error(None).decode())
+    out = []
+    for s in range(n):
+        m = min(int(n_inst[s]), mi)
+        out.append({"transforms": T[s][:m].reshape(m, 4, 4), "instances": InstanceList(ic[s], off[s], m),
+                    "n_instances": int(n_inst[s]), "corrs": co[s][:int(n_corr[s])], "status": int(status[s])})
+    return out
 
 
 # ---- the reference's text dump of a view's descriptors (CAD_desc.cpp:354-370) ----------------------------------

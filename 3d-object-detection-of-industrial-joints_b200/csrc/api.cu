@@ -1,6 +1,8 @@
 // api.cu — the C ABI of libb200reg.so (include/b200reg.h): argument checking, host<->device staging
 // and the resident SHOT registration pipeline.  No torch types, no exceptions across the boundary.
 #include <algorithm>
+#include <mutex>
+#include <thread>
 #include <array>
 #include <string>
 #include <cstdio>
@@ -861,6 +863,63 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
   } while (0);
   delete scene;
   return rc;
+}
+
+/* ------------------------------------------------------------------ lanes */
+namespace {
+// contexts kept per device for b200_register_scene_batch_shot (their arenas stay warm between batches)
+struct LanePool {
+  std::mutex mu;
+  std::vector<b200_ctx *> ctxs;
+};
+LanePool &lane_pool(int device) {
+  static LanePool pools[64];
+  return pools[(device >= 0 && device < 64) ? device : 0];
+}
+}  // namespace
+
+int b200_register_scene_batch_shot(int device, const b200_model *model, int n_scenes, const float *const *scene_xyz,
+                                   const int *n_points, int stride, const float *const *scene_kp, const int *n_kp,
+                                   int kstride, const b200_shot_params *p, int lanes, float *const *transforms,
+                                   int *const *inst_offsets, b200_corr *const *inst_corrs, const int *corr_cap,
+                                   int *n_inst, b200_corr *const *corrs_out, int *n_corrs, int *status) {
+  if (!model || n_scenes < 0 || lanes < 1 || lanes > 16 || !p ||
+      (n_scenes > 0 && (!scene_xyz || !n_points || !scene_kp || !n_kp || !n_inst || !status))) {
+    g_error = "register_scene_batch: bad arguments";
+    return B200_ERR_INVALID;
+  }
+  if (n_scenes == 0) return B200_OK;
+  lanes = std::min(lanes, n_scenes);
+  LanePool &pool = lane_pool(device);
+  std::lock_guard<std::mutex> hold(pool.mu);  // one batch at a time per device
+  while ((int)pool.ctxs.size() < lanes) {
+    b200_ctx *c = nullptr;
+    const int rc = b200_ctx_create(&c, device, nullptr);
+    if (rc != B200_OK) return rc;
+    pool.ctxs.push_back(c);
+  }
+  auto work = [&](int lane) {
+    b200_ctx *c = pool.ctxs[(size_t)lane];
+    for (int s = lane; s < n_scenes; s += lanes) {
+      int nc = 0;
+      status[s] = b200_register_scene_shot(c, model, scene_xyz[s], n_points[s], stride, scene_kp[s], n_kp[s], kstride, p,
+                                           transforms ? transforms[s] : nullptr, inst_offsets ? inst_offsets[s] : nullptr,
+                                           inst_corrs ? inst_corrs[s] : nullptr, corr_cap ? corr_cap[s] : 0, &n_inst[s],
+                                           corrs_out ? corrs_out[s] : nullptr, &nc);
+      if (n_corrs) n_corrs[s] = nc;
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int l = 1; l < lanes; ++l) threads.emplace_back(work, l);
+  work(0);
+  for (std::thread &t : threads) t.join();
+  for (int s = 0; s < n_scenes; ++s)
+    if (status[s] != B200_OK && status[s] != B200_ERR_CAPACITY) {
+      g_error = std::string("register_scene_batch: scene ") + std::to_string(s) + ": " +
+                b200_last_error(pool.ctxs[(size_t)(s % lanes)]);
+      return status[s];
+    }
+  return B200_OK;
 }
 
 /* ------------------------------------------------------------------ multi-view library */

@@ -268,6 +268,23 @@ B200_API int b200_dev_register_scene_shot(b200_ctx *ctx, const b200_model *model
                                  int *d_inst_counts, b200_corr *d_inst_corrs, int corr_cap, int *d_n_inst,
                                  b200_corr *d_corrs_out, int *d_n_corrs, float *d_desc_out);
 
+/* A batch of scenes against one model with several scenes in flight (BASELINE config 5 on one GPU; the per-rank part
+ * of the sharded batch).  The reference's programs register one frame per callback; for throughput the scenes are
+ * independent, and `lanes` contexts (each with its own stream, arena and host thread, created and kept by the library
+ * for `device`) work through the batch concurrently so that the latency-bound grouping kernel of one scene (8 SMs)
+ * runs beside the GPU-wide stages of the others.  Scene s is handled by lane s mod lanes.  Per scene s: inputs
+ * scene_xyz[s] (n_points[s] x stride), scene_kp[s] (n_kp[s] x kstride); outputs as b200_register_scene_shot into
+ * transforms[s] (p->max_instances x 16), inst_offsets[s] (p->max_instances + 1), inst_corrs[s] (capacity corr_cap[s]),
+ * n_inst[s], corrs_out[s] (capacity n_kp[s]; the array or any entry may be NULL), n_corrs[s], status[s] (the scene's
+ * own return code).  Results are bit-identical to calling b200_register_scene_shot scene by scene.  Returns the
+ * first non-OK status other than B200_ERR_CAPACITY, else B200_OK.  lanes: 1..16 (4 to 6 saturate a B200). */
+B200_API int b200_register_scene_batch_shot(int device, const b200_model *model, int n_scenes,
+                                            const float *const *scene_xyz, const int *n_points, int stride,
+                                            const float *const *scene_kp, const int *n_kp, int kstride,
+                                            const b200_shot_params *p, int lanes, float *const *transforms,
+                                            int *const *inst_offsets, b200_corr *const *inst_corrs, const int *corr_cap,
+                                            int *n_inst, b200_corr *const *corrs_out, int *n_corrs, int *status);
+
 /* ---------------------------------------------------------------- multi-view library ----- */
 /* The reference recognises against a set of rendered partial views of the CAD models: CAD_desc.cpp:231-370
  * builds one SHOT descriptor set per view, and SHOT.cpp:243-483 / 6Dpose.cpp / SHOT_demo.cpp:430-663 loop over

@@ -25,7 +25,7 @@ def _write(path, a):
 
 def test_apps_build_and_need_a_gpu(apps, synth, tmp_path):
     import torch
-    assert set(apps) >= {"shot_recognition", "fpfh_recognition"}
+    assert set(apps) >= {"shot_recognition", "fpfh_recognition", "batch_recognition"}
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     m = synth.make_model("y", 500)
@@ -215,3 +215,37 @@ def test_shot_recognition_app_hough_board_frames(apps, orc, synth, tmp_path):
         assert x.tobytes() == y.tobytes()
     if len(T):
         assert max(np.abs(A - B).max() for A, B in zip(T, oT)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_batch_recognition_app_lanes(apps, b200, synth, tmp_path):
+    """C++ host side of the lanes (b200_register_scene_batch_shot): six scenes, three lanes; every scene's
+    correspondences and poses equal the scene registered alone."""
+    model = synth.make_model("y", 20000)
+    kpm = synth.uniform_sampling(model, 0.005)
+    _write(tmp_path / "m.f32", model)
+    _write(tmp_path / "mk.f32", kpm)
+    args, scenes = [], []
+    for s in range(6):
+        sc = synth.make_scene(("y", "diagonal"), 60000, scene_id=30 + s % 2)
+        kp = synth.uniform_sampling(sc, 0.02)
+        _write(tmp_path / ("s%d.f32" % s), sc)
+        _write(tmp_path / ("k%d.f32" % s), kp)
+        args += [str(tmp_path / ("s%d.f32" % s)), str(tmp_path / ("k%d.f32" % s))]
+        scenes.append((sc, kp))
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([apps["batch_recognition"], str(tmp_path / "m.f32"), str(tmp_path / "mk.f32"), prefix, "3"] + args,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    p = b200.shot_params(normal_k=20, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=4096)
+    ctx = b200.Context(0)
+    m = ctx.model_create_shot(model, kpm, p)
+    for s, (sc, kp) in enumerate(scenes):
+        ref = ctx.register_scene_shot(m, sc, kp, p)
+        corr = np.fromfile("%s.%d.corr" % (prefix, s), dtype=CORR)
+        T = np.fromfile("%s.%d.T" % (prefix, s), dtype=np.float32).reshape(-1, 4, 4)
+        assert "scene %d: %d correspondences, %d instances" % (s, len(ref["corrs"]), ref["n_instances"]) in r.stdout
+        assert corr.tobytes() == ref["corrs"].tobytes() and np.array_equal(T, ref["transforms"])
+    m.close()
+    ctx.close()

@@ -240,6 +240,15 @@ def test_config5_scene_batch_lanes_are_deterministic(b200, synth, pkg):
         assert a["corrs"].tobytes() == b["corrs"].tobytes() == gathered[s].tobytes()
         assert np.array_equal(a["transforms"], b["transforms"])
         assert all(x.tobytes() == y.tobytes() for x, y in zip(a["instances"], b["instances"]))
+    # the same through the library's own lanes (b200_register_scene_batch_shot: contexts and host threads inside)
+    nat = b200.register_scene_batch(m, scenes, kps, p, lanes=4)
+    assert len(nat) == 12
+    for s in range(12):
+        a, b = nat[s], seq[s % 3]
+        assert a["status"] == 0 and a["n_instances"] == b["n_instances"]
+        assert a["corrs"].tobytes() == b["corrs"].tobytes() and np.array_equal(a["transforms"], b["transforms"])
+        assert all(x.tobytes() == y.tobytes() for x, y in zip(a["instances"], b["instances"]))
+    assert b200.register_scene_batch(m, [], [], p) == []
     m.close()
     for c in ctxs:
         c.close()
