@@ -213,6 +213,7 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // ------------------------------------------------------------------------------------------
 struct GridView {
   const float4 *pts;
+  const float4 *raw;  // the cloud in caller order (x, y, z, 1): neighbour coordinates by original index
   const int *cell_start;  // ncell + 1 entries
   float lox, loy, loz;
   float h, inv_h;

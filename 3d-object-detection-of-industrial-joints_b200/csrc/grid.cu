@@ -163,6 +163,7 @@ int build_grid(b200_cloud *c, float cell, DeviceGrid &g) {
   B200_TRY(cell_of.alloc(ctx, (size_t)std::max(c->n, 1)));
   tr.tick("memset + alloc cell_of");
   v.pts = g.pts.p;
+  v.raw = c->raw.p;
   v.cell_start = g.cell_start.p;
   if (c->n > 0) {
     cell_count_kernel<<<ceil_div(c->n, 256), 256, 0, ctx->stream>>>(c->raw.p, c->n, v, cell_of.p, counts.p);

@@ -26,22 +26,21 @@ namespace {
 
 constexpr int ICP_THREADS = 128;
 
-// nearest target point of every (finite) source point: target row, d2; valid = kept by the distance gate
+// nearest target point of every (finite) source point: original target row, d2; -1 = none within the distance gate
 __global__ void __launch_bounds__(ICP_THREADS)
     icp_nn_kernel(GridView g, const float4 *__restrict__ src, int n, float max_d2, int *__restrict__ tgt_idx,
                   float *__restrict__ d2_out) {
-  __shared__ float sd[ICP_THREADS];
-  __shared__ int sp[ICP_THREADS];
+  __shared__ unsigned long long sk[ICP_THREADS];
   const int i = blockIdx.x * ICP_THREADS + threadIdx.x;
   if (i >= n) return;
   const float4 p = src[i];
   int t = -1;
   float d2 = 0.f;
   if (finite3(p.x, p.y, p.z)) {
-    const int cnt = knn_query(g, p.x, p.y, p.z, 1, sd + threadIdx.x, sp + threadIdx.x, ICP_THREADS);
-    if (cnt == 1 && !(sd[threadIdx.x] > max_d2)) {
-      t = sp[threadIdx.x];  // position in g.pts
-      d2 = sd[threadIdx.x];
+    const int cnt = knn_query(g, p.x, p.y, p.z, 1, sk + threadIdx.x, ICP_THREADS);
+    if (cnt == 1 && !(knn_d2(sk[threadIdx.x]) > max_d2)) {
+      t = knn_orig(sk[threadIdx.x]);  // original row of the target cloud
+      d2 = knn_d2(sk[threadIdx.x]);
     }
   }
   tgt_idx[i] = t;
@@ -59,7 +58,7 @@ __global__ void __launch_bounds__(256)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int t = tgt_idx[i];
     if (t < 0) continue;
-    const float4 s = src[i], q = g.pts[t];
+    const float4 s = src[i], q = g.raw[t];
     const double sv[3] = {s.x, s.y, s.z}, dv[3] = {q.x, q.y, q.z};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {

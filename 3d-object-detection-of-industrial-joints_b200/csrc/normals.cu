@@ -95,8 +95,7 @@ __global__ void normals_knn_kernel(GridView g, const float4 *__restrict__ q, int
                                    float vpz, float4 *__restrict__ out) {
   extern __shared__ unsigned char smem_raw[];
   const int T = blockDim.x;
-  float *sd = reinterpret_cast<float *>(smem_raw) + threadIdx.x;
-  int *sp = reinterpret_cast<int *>(smem_raw + (size_t)k * T * sizeof(float)) + threadIdx.x;
+  unsigned long long *sk = reinterpret_cast<unsigned long long *>(smem_raw) + threadIdx.x;
   const int i = blockIdx.x * T + threadIdx.x;
   if (i >= nq) return;
   float4 p;
@@ -110,11 +109,11 @@ __global__ void normals_knn_kernel(GridView g, const float4 *__restrict__ q, int
   }
   float4 o = make_float4(nanf32(), nanf32(), nanf32(), nanf32());
   if (finite3(p.x, p.y, p.z)) {
-    const int cnt = knn_query(g, p.x, p.y, p.z, k, sd, sp, T);
+    const int cnt = knn_query(g, p.x, p.y, p.z, k, sk, T);
     if (cnt >= 3) {
       float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int j = 0; j < cnt; ++j) {
-        const float4 n = g.pts[sp[j * T]];
+        const float4 n = g.raw[knn_orig(sk[j * T])];
         accu[0] += n.x * n.x;
         accu[1] += n.x * n.y;
         accu[2] += n.x * n.z;

@@ -11,17 +11,17 @@ __global__ void knn_search_kernel(GridView g, const float4 *__restrict__ q, int 
                                   float *__restrict__ d2) {
   extern __shared__ unsigned char smem_raw[];
   const int T = blockDim.x;
-  float *sd = reinterpret_cast<float *>(smem_raw) + threadIdx.x;
-  int *sp = reinterpret_cast<int *>(smem_raw + (size_t)k * T * sizeof(float)) + threadIdx.x;
+  unsigned long long *sk = reinterpret_cast<unsigned long long *>(smem_raw) + threadIdx.x;
   const int i = blockIdx.x * T + threadIdx.x;
   if (i >= nq) return;
   const float4 p = q[i];
   int cnt = 0;
-  if (finite3(p.x, p.y, p.z)) cnt = knn_query(g, p.x, p.y, p.z, k, sd, sp, T);
+  if (finite3(p.x, p.y, p.z)) cnt = knn_query(g, p.x, p.y, p.z, k, sk, T);
   for (int j = 0; j < k; ++j) {
     const bool have = j < cnt;
-    idx[(size_t)i * k + j] = have ? orig_index(g.pts[sp[j * T]]) : -1;
-    d2[(size_t)i * k + j] = have ? sd[j * T] : __int_as_float(0x7f800000);
+    const unsigned long long key = have ? sk[j * T] : 0ull;
+    idx[(size_t)i * k + j] = have ? knn_orig(key) : -1;
+    d2[(size_t)i * k + j] = have ? knn_d2(key) : __int_as_float(0x7f800000);
   }
 }
 

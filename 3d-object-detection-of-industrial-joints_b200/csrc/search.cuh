@@ -17,10 +17,15 @@ __device__ __forceinline__ bool cand_before(float d, int o, float d2, int o2) {
   return (d < d2) || (d == d2 && o < o2);
 }
 
-// Exact k nearest neighbours of (qx,qy,qz).  sd/sp: this thread's column of two [k][T] shared
-// arrays (element j at [j*T]).  Returns the number found (min(k, g.n)); entries are sorted by
-// (d2, original index); sp holds positions in g.pts.
-__device__ inline int knn_query(const GridView &g, float qx, float qy, float qz, int k, float *sd, int *sp, int T) {
+// Exact k nearest neighbours of (qx,qy,qz).  sk: this thread's column of a [k][T] shared array of 64-bit keys
+// (element j at [j*T]); key = float bits of d2 (non-negative, so the unsigned order is the float order) in the high
+// word, ORIGINAL row index in the low word: one unsigned compare is FLANN's (distance, index) order, and a shift
+// of the sorted list moves one 8-byte word per step.  Returns the number found (min(k, g.n)), sorted ascending.
+// Coordinates of a neighbour: g.raw[knn_orig(key)].
+__device__ __forceinline__ float knn_d2(unsigned long long key) { return __uint_as_float((unsigned)(key >> 32)); }
+__device__ __forceinline__ int knn_orig(unsigned long long key) { return (int)(unsigned)(key & 0xffffffffull); }
+
+__device__ inline int knn_query(const GridView &g, float qx, float qy, float qz, int k, unsigned long long *sk, int T) {
   const float4 *__restrict__ pts = g.pts;
   const int *__restrict__ cs = g.cell_start;
   if (k > g.n) k = g.n;
@@ -31,30 +36,25 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
   int cnt = 0;
   const int maxR = max(g.dx, max(g.dy, g.dz));
   const float margin = 4e-6f * (g.coord_scale + fabsf(qx) + fabsf(qy) + fabsf(qz)) + 1e-5f * g.h;
+  unsigned long long worst = ~0ull;  // key of the current k-th neighbour once the list is full
 
   auto scan_run = [&](int c0, int c1) {
     const int s = cs[c0], e = cs[c1 + 1];
     for (int j = s; j < e; ++j) {
       const float4 p = pts[j];
       const float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
-      if (cnt == k) {
-        const float wd = sd[(k - 1) * T];
-        if (d > wd) continue;
-        if (d == wd && orig_index(p) >= orig_index(pts[sp[(k - 1) * T]])) continue;
-      }
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)orig_index(p);
+      if (key >= worst) continue;
       int pos = (cnt < k) ? cnt : k - 1;
-      const int o = orig_index(p);
       while (pos > 0) {
-        const float pd = sd[(pos - 1) * T];
-        const int pp = sp[(pos - 1) * T];
-        if (pd < d || (pd == d && orig_index(pts[pp]) < o)) break;
-        sd[pos * T] = pd;
-        sp[pos * T] = pp;
+        const unsigned long long pk = sk[(pos - 1) * T];
+        if (pk < key) break;
+        sk[pos * T] = pk;
         --pos;
       }
-      sd[pos * T] = d;
-      sp[pos * T] = j;
+      sk[pos * T] = key;
       if (cnt < k) ++cnt;
+      if (cnt == k) worst = sk[(k - 1) * T];
     }
   };
 
@@ -104,7 +104,7 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
       if (cz - R > 0) cert = fminf(cert, qz - (g.loz + (float)(cz - R) * g.h));
       if (cz + R < g.dz - 1) cert = fminf(cert, (g.loz + (float)(cz + R + 1) * g.h) - qz);
       cert -= margin;
-      if (cert > 0.f && sd[(k - 1) * T] < cert * cert * 0.99999f) break;
+      if (cert > 0.f && knn_d2(worst) < cert * cert * 0.99999f) break;
     }
   }
   return cnt;
