@@ -49,7 +49,7 @@ __global__ void gather_normals_kernel(const float4 *__restrict__ sorted_pts, int
 // Histogram accumulators.  FloatBins: float32 atomics (CTA kernel, several warps share the bins).
 // FixedBins: fixed point in 32 bits — shared-memory integer adds are native while float (and 64-bit)
 // adds are compare-and-swap loops.  Every contribution is >= 0 and <= 4, so with n neighbours a bin sum
-// is at most 4 n: the scale is 2^20 for n <= 1024 and 2^19 up to SW_CAP = 2048 (the unsigned sum cannot
+// is at most 4 n: the scale is 2^20 for n <= 1024 and 2^19 up to SW_CAP = 2016 (the unsigned sum cannot
 // wrap).  The quantisation (<= 4.8e-7 per contribution of order 1, same size as float32 rounding of the
 // bin sums) is ~1e-7 of the histogram norm, far inside the 1e-4 parity bound.
 struct FloatBins {
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(SHOT_THREADS)
 // ------------------------------------------------------------------------------------------
 constexpr int SW_WARPS = 8;
 constexpr int SW_THREADS = SW_WARPS * 32;
-constexpr int SW_CAP = 2048;  // neighbours per keypoint held in shared memory
+constexpr int SW_CAP = 2016;  // neighbours per keypoint held in shared memory (three CTAs of 8 warps fit one SM)
 
 struct ShotWarpSmem {
   int pos[SW_CAP];     // position of the neighbour in the cell-ordered point array; its float32 squared
@@ -387,7 +387,7 @@ struct ShotWarpSmem {
   int sel[8];          // rows picked by the tie rule
 };
 
-__global__ void __launch_bounds__(SW_THREADS, 2)
+__global__ void __launch_bounds__(SW_THREADS, 3)
     shot_warp_kernel(GridView g, const float4 *__restrict__ nrm, const float4 *__restrict__ kp,
                      const int *__restrict__ counts, int K, float radius_f, double radius, float r2,
                      int *__restrict__ work_counter, float *__restrict__ desc, float *__restrict__ rf_out,
@@ -798,7 +798,7 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
     B200_TRY(work.zero());
     const size_t smem_w = sizeof(ShotWarpSmem) * SW_WARPS;
     B200_CUDA(ctx, cudaFuncSetAttribute(shot_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-    const int grid_w = std::min(ceil_div(K, SW_WARPS), ctx->sm_count * 2);
+    const int grid_w = std::min(ceil_div(K, SW_WARPS), ctx->sm_count * 3);
     shot_warp_kernel<<<grid_w, SW_THREADS, smem_w, ctx->stream>>>(*g, nrm_sorted.p, d_kp, counts.p, K, (float)radius,
                                                                  radius, r2, work.p, d_desc, d_rf, lrf_only ? 1 : 0);
     B200_LAUNCHED(ctx);
