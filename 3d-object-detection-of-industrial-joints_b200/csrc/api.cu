@@ -302,7 +302,8 @@ int b200_ctx_stage_count(void) { return ST_COUNT; }
 
 const char *b200_ctx_stage_name(int stage) {
   static const char *names[ST_COUNT] = {"grid_build", "normals", "neighbor_count", "shot", "fpfh",
-                                        "match",      "gc_sort", "gc_adjacency",   "gc_group", "gc_ransac"};
+                                        "match",      "gc_sort", "gc_adjacency",   "gc_group", "gc_ransac",
+                                        "match_filter"};
   return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
 }
 

@@ -29,6 +29,7 @@ enum b200_stage {
   ST_GC_ADJ,
   ST_GC_GROUP,
   ST_GC_RANSAC,
+  ST_MATCH_FILTER,  // nested inside ST_MATCH: the tcgen05 pre-filter kernel alone
   ST_COUNT
 };
 

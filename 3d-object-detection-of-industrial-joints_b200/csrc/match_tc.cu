@@ -641,8 +641,11 @@ int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned 
   p.cand_j = cand_j.p;
   B200_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int grid = std::min(ctx->sm_count, m_tiles * n_split);
-  tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(mapA, mapB, p);
-  B200_LAUNCHED(ctx);
+  {
+    StageScope st_(ctx, ST_MATCH_FILTER);
+    tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(mapA, mapB, p);
+    B200_LAUNCHED(ctx);
+  }
   // error bound of the approximate inner product relative to |a||b|: fp16 operand rounding (2^-11 per
   // operand for one term, ~2^-21 for the three-term split) plus fp32 tensor-core accumulation
   const float eta = (terms == 3) ? 1.0e-4f : 1.2e-3f;
