@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(ADJ_THREADS)
                         int C_cap, double gc_size, float g_lo, float g_hi, unsigned *__restrict__ adj) {
   __shared__ float4 s_m[ADJ_WORDS * 32];
   __shared__ float4 s_s[ADJ_WORDS * 32];
+  __shared__ unsigned s_t[2][4][ADJ_ROWS];  // mirror staging: [half][32-row block][column]
   const int C = min(*d_C, C_cap);
   const int row_words = gc_row_words(C);
   const int w0 = blockIdx.x * ADJ_WORDS;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(ADJ_THREADS)
   __syncthreads();
   const int lane = tid & 31;
   const int i = i0 + (tid & (ADJ_ROWS - 1));
-  const int ib_word = (i0 >> 5) + ((tid & (ADJ_ROWS - 1)) >> 5);  // word index of this warp's 32 rows
+  const int half = tid / ADJ_ROWS, wr = (tid & (ADJ_ROWS - 1)) >> 5;  // column half of the tile, 32-row block
   const int wbase = (tid / ADJ_ROWS) * (ADJ_WORDS / 2);           // 16 words per thread
   const bool valid = i < C;
   const float4 mi = valid ? mp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -170,15 +171,25 @@ __global__ void __launch_bounds__(ADJ_THREADS)
       if ((i >> 5) == gw) bits &= ~(1u << (i & 31));
       if (!valid) bits = 0u;
       out[w4] = bits;
-      if (mirror && j0 < C) {  // warp-uniform
+      if (mirror) {  // uniform over the half CTA
         unsigned tw = 0;
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
           const unsigned v = __ballot_sync(0xffffffffu, (bits >> b) & 1u);
           if (lane == b) tw = v;
         }
-        if (j0 + lane < C) adj[(size_t)(j0 + lane) * row_words + ib_word] = tw;
+        s_t[half][wr][w4 * 32 + lane] = tw;  // column j0 + lane, rows of this warp
       }
+    }
+    if (mirror) {
+      // the four warps of the half hold the same 128 columns for four consecutive 32-row blocks: one 16-byte
+      // store per column instead of four scattered words
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(ADJ_ROWS) : "memory");
+      const int col = tid & (ADJ_ROWS - 1);
+      if (jg + col < C)
+        *reinterpret_cast<uint4 *>(adj + (size_t)(jg + col) * row_words + (i0 >> 5)) =
+            make_uint4(s_t[half][0][col], s_t[half][1][col], s_t[half][2][col], s_t[half][3][col]);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(ADJ_ROWS) : "memory");
     }
     if (valid) *reinterpret_cast<uint4 *>(row + wq) = make_uint4(out[0], out[1], out[2], out[3]);
   }
