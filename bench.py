@@ -231,6 +231,14 @@ def run_b200(args, rank, world, local_rank):
     # host thread (sharding.run_lanes).  The grouping stage of one scene is a latency-bound chain on 8 SMs; the
     # other lanes' wide stages (normals, SHOT, matching) fill the rest of the GPU meanwhile.
     L = max(1, args.lanes)
+    # every lane is a host thread that spins in stream synchronisations: keep lanes x ranks within the host cores
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    if world * L > cores:
+        L = max(2, min(L, cores // world - 1))
+    args.lanes = L
     streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
     ctxs = [binding.Context(local_rank, stream=st.cuda_stream) for st in streams]
     ctx = ctxs[0]
