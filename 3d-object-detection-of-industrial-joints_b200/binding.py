@@ -35,6 +35,8 @@ EXPORTS = [
     "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
     "b200_hough3d_recognize",
     "b200_icp_align",
+    "b200_remove_nan",
+    "b200_transform_points",
     "b200_board_params_default",
     "b200_ctx_srand",
     "b200_board_lrf",
@@ -134,6 +136,8 @@ def lib():
             "b200_board_params_default": [C.POINTER(BoardParams)],
             "b200_ctx_srand": [vp, C.c_uint],
             "b200_board_lrf": [vp, vp, fp, fp, i, i, d, C.POINTER(BoardParams), fp],
+            "b200_remove_nan": [vp, fp, i, i, fp, ip, ip],
+            "b200_transform_points": [vp, fp, i, i, fp, fp],
             "b200_icp_align": [vp, fp, i, i, vp, i, d, d, d, fp, fp, fp, C.POINTER(d), ip, ip],
             "b200_library_create": [vp, C.POINTER(vp)],
             "b200_library_destroy": [vp],
@@ -601,6 +605,23 @@ class Context:
             self._chk(rc)
         m = min(n.value, max_inst)
         return T[:m].reshape(m, 4, 4).copy(), [oc[off[i]:off[i + 1]].copy() for i in range(m)], n.value
+
+    def remove_nan(self, xyz):
+        """pcl::removeNaNFromPointCloud (b200_remove_nan).  Returns (kept rows n x 3, their original indices)."""
+        xyz = _pts(xyz)
+        out = np.zeros((max(len(xyz), 1), 3), dtype=np.float32)
+        idx = np.zeros(max(len(xyz), 1), dtype=np.int32)
+        n = C.c_int()
+        self._chk(lib().b200_remove_nan(self.h, _f(xyz), len(xyz), xyz.shape[1], _f(out), _i(idx), C.byref(n)))
+        return out[:n.value], idx[:n.value]
+
+    def transform_points(self, xyz, transform):
+        """pcl::transformPointCloud with a 4x4 matrix (b200_transform_points)."""
+        xyz = _pts(xyz)
+        T = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+        out = np.zeros((max(len(xyz), 1), 3), dtype=np.float32)
+        self._chk(lib().b200_transform_points(self.h, _f(xyz), len(xyz), xyz.shape[1], _f(T), _f(out)))
+        return out[:len(xyz)]
 
     def srand(self, seed):
         """Reseeds the context's rand() stream (BOARD's random axis), like srand(seed) for PCL."""

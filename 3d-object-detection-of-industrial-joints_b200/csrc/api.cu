@@ -578,6 +578,40 @@ int b200_uniform_sampling(b200_ctx *ctx, const float *xyz, int n, int stride, do
   return B200_OK;
 }
 
+int b200_remove_nan(b200_ctx *ctx, const float *xyz, int n, int stride, float *out_xyz, int *out_index, int *count) {
+  API_ENTER(ctx);
+  if (n < 0 || stride < 3 || !count || (n > 0 && (!xyz || !out_xyz)))
+    return ctx->fail(B200_ERR_INVALID, "remove_nan: bad arguments");
+  *count = 0;
+  if (n == 0) return B200_OK;
+  DevBuf<float> din, dout;
+  DevBuf<int> didx, dcount;
+  B200_TRY(upload(ctx, din, xyz, (size_t)n * stride));
+  B200_TRY(dout.alloc(ctx, (size_t)n * 3));
+  B200_TRY(didx.alloc(ctx, (size_t)n));
+  B200_TRY(dcount.alloc(ctx, 1));
+  B200_TRY(dev_remove_nan(ctx, din.p, n, stride, dout.p, didx.p, dcount.p));
+  B200_TRY(readback_small(ctx, dcount.p, count, sizeof(int)));
+  B200_TRY(download(ctx, out_xyz, dout.p, (size_t)*count * 3));
+  if (out_index) B200_TRY(download(ctx, out_index, didx.p, (size_t)*count));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_transform_points(b200_ctx *ctx, const float *xyz, int n, int stride, const float *transform, float *out_xyz) {
+  API_ENTER(ctx);
+  if (n < 0 || stride < 3 || !transform || (n > 0 && (!xyz || !out_xyz)))
+    return ctx->fail(B200_ERR_INVALID, "transform_points: bad arguments");
+  if (n == 0) return B200_OK;
+  DevBuf<float> din, dout;
+  B200_TRY(upload(ctx, din, xyz, (size_t)n * stride));
+  B200_TRY(dout.alloc(ctx, (size_t)n * 3));
+  B200_TRY(dev_transform_points(ctx, din.p, n, stride, transform, dout.p));
+  B200_TRY(download(ctx, out_xyz, dout.p, (size_t)n * 3));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 int b200_dev_voxel_grid(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx, float ly, float lz,
                         float *d_out_xyz, int *d_count) {
   API_ENTER(ctx);

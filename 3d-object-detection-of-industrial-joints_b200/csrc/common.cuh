@@ -421,6 +421,8 @@ int dev_icp_align(b200_ctx *ctx, const float4 *d_src, int ns, b200_cloud *target
                   double transformation_epsilon, double euclidean_fitness_epsilon, const float *guess, float *final_T,
                   float4 *d_aligned, double *fitness, int *converged, int *iterations);
 // keypoints.cu
+int dev_remove_nan(b200_ctx *ctx, const float *d_xyz, int n, int stride, float *d_out_xyz, int *d_out_index, int *d_count);
+int dev_transform_points(b200_ctx *ctx, const float *d_xyz, int n, int stride, const float *T16, float *d_out_xyz);
 int dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, float leaf, float *d_out_xyz,
                          int *d_out_index, int *d_count);
 int dev_voxel_grid(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx, float ly, float lz,

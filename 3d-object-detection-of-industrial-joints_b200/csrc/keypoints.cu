@@ -17,6 +17,8 @@
 // leaves — PCL refuses lattices whose index overflows an int in the same way ("leaf size is too small").
 #include <algorithm>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -170,6 +172,76 @@ int make_lattice(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx,
 }  // namespace
 
 // d_count: device int (number of keypoints written)
+// ---- cloud utilities around the hot path: removeNaNFromPointCloud (SHOT.cpp:298-299) and transformPointCloud
+// (SHOT.cpp / SHOT_demo.cpp: the model placed by a pose before ICP) ------------------------------------------
+namespace {
+__global__ void finite_flags_kernel(const float *__restrict__ xyz, int n, int stride, int *__restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *p = xyz + (size_t)i * stride;
+  flags[i] = finite3(p[0], p[1], p[2]) ? 1 : 0;
+}
+__global__ void compact_rows_kernel(const float *__restrict__ xyz, int n, int stride, const int *__restrict__ flags,
+                                    const int *__restrict__ slots, float *__restrict__ out_xyz, int *__restrict__ out_index) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flags[i]) return;
+  const float *p = xyz + (size_t)i * stride;
+  const int s = slots[i];
+  out_xyz[3 * (size_t)s + 0] = p[0];
+  out_xyz[3 * (size_t)s + 1] = p[1];
+  out_xyz[3 * (size_t)s + 2] = p[2];
+  if (out_index) out_index[s] = i;
+}
+struct Mat34 {
+  float m[12];
+};
+// pcl::transformPointCloud (common/impl/transforms.hpp): x' = ((t00 x + t01 y) + t02 z) + t03, row by row; rows with
+// a non-finite coordinate are copied unchanged (the non-dense branch)
+__global__ void transform_rows_kernel(const float *__restrict__ xyz, int n, int stride, Mat34 T, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *p = xyz + (size_t)i * stride;
+  const float x = p[0], y = p[1], z = p[2];
+  float o[3] = {x, y, z};
+  if (finite3(x, y, z)) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float v = T.m[r * 4 + 0] * x;
+      v += T.m[r * 4 + 1] * y;
+      v += T.m[r * 4 + 2] * z;
+      v += T.m[r * 4 + 3];
+      o[r] = v;
+    }
+  }
+  out[3 * (size_t)i + 0] = o[0];
+  out[3 * (size_t)i + 1] = o[1];
+  out[3 * (size_t)i + 2] = o[2];
+}
+}  // namespace
+
+int dev_remove_nan(b200_ctx *ctx, const float *d_xyz, int n, int stride, float *d_out_xyz, int *d_out_index, int *d_count) {
+  B200_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+  if (n <= 0) return B200_OK;
+  DevBuf<int> flags, slots;
+  B200_TRY(flags.alloc(ctx, (size_t)n));
+  B200_TRY(slots.alloc(ctx, (size_t)n));
+  finite_flags_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, stride, flags.p);
+  B200_LAUNCHED(ctx);
+  B200_TRY(exclusive_scan_i32(ctx, flags.p, slots.p, n, d_count));
+  compact_rows_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, stride, flags.p, slots.p, d_out_xyz, d_out_index);
+  B200_LAUNCHED(ctx);
+  return B200_OK;
+}
+
+int dev_transform_points(b200_ctx *ctx, const float *d_xyz, int n, int stride, const float *T16, float *d_out_xyz) {
+  if (n <= 0) return B200_OK;
+  Mat34 T;
+  memcpy(T.m, T16, sizeof(T.m));
+  transform_rows_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, stride, T, d_out_xyz);
+  B200_LAUNCHED(ctx);
+  return B200_OK;
+}
+
 int dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, float leaf, float *d_out_xyz,
                          int *d_out_index, int *d_count) {
   B200_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));

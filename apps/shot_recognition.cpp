@@ -72,6 +72,10 @@ int main(int argc, char **argv) {
   pcl::PointCloud<DescriptorType>::Ptr model_descriptors(new pcl::PointCloud<DescriptorType>()),
       scene_descriptors(new pcl::PointCloud<DescriptorType>());
   if (!load_cloud(argv[1], *model) || !load_cloud(argv[3], *scene)) return 1;
+  {
+    std::vector<int> indices;  // SHOT.cpp:298-299
+    pcl::removeNaNFromPointCloud(*scene, *scene, indices);
+  }
   // keypoints: a file, or "us:<leaf>" to extract them like the reference does (SHOT.cpp:314-323)
   for (int side = 0; side < 2; ++side) {
     const std::string spec = argv[side ? 4 : 2];
@@ -222,12 +226,15 @@ int main(int argc, char **argv) {
   if (icp_iters > 0) {
     f = fopen((prefix + ".icp").c_str(), "wb");
     for (size_t i = 0; i < rototranslations.size() && i < 8; ++i) {
+      // SHOT.cpp: transformPointCloud(*model, *rotated_model, rototranslations[i]); icp_align(scene, rotated_model)
+      pcl::PointCloud<PointType>::Ptr rotated_model(new pcl::PointCloud<PointType>());
+      pcl::transformPointCloud(*model, *rotated_model, rototranslations[i]);
       pcl::IterativeClosestPoint<PointType, PointType> icp;
       icp.setMaximumIterations(icp_iters);
-      icp.setInputSource(model);
+      icp.setInputSource(rotated_model);
       icp.setInputTarget(scene);
       pcl::PointCloud<PointType> cloud_icp;
-      icp.align(cloud_icp, rototranslations[i]);  // the reference transforms the model first; the guess does the same
+      icp.align(cloud_icp);
       const double score = icp.getFitnessScore();
       if (i < 3) printf("\nICP has converged, score is %+.0e\n", score);
       float rec[18];

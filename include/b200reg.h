@@ -118,6 +118,16 @@ B200_API int b200_voxel_grid(b200_ctx *ctx, const float *xyz, int n, int stride,
 B200_API int b200_dev_voxel_grid(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx, float ly, float lz,
                                  float *d_out_xyz, int *d_count);
 
+/* pcl::removeNaNFromPointCloud (SHOT.cpp:298-299, first statement of the callback): rows with finite x, y, z, in
+ * order; out_xyz n x 3, out_index (nullable) n: the kept rows' original positions. */
+B200_API int b200_remove_nan(b200_ctx *ctx, const float *xyz, int n, int stride, float *out_xyz, int *out_index,
+                             int *count);
+/* pcl::transformPointCloud(cloud_in, cloud_out, Eigen::Matrix4f) (the model placed by a grouped pose before ICP and for
+ * display: SHOT.cpp, SHOT_demo.cpp:590-663): transform = row-major 4x4; out_xyz n x 3; rows with a non-finite
+ * coordinate are copied unchanged, like PCL's non-dense branch. */
+B200_API int b200_transform_points(b200_ctx *ctx, const float *xyz, int n, int stride, const float *transform,
+                                   float *out_xyz);
+
 /* ---------------------------------------------------------------- normals ---------------- */
 /* pcl::NormalEstimationOMP::compute — setKSearch(k) (SHOT.cpp:302-308, 6Dpose.cpp:275-278,
  * SHOT_demo.cpp:405-411, CAD_desc.cpp:283-289) or setRadiusSearch(r) (FPFH_demo.cpp:416-420,

@@ -446,6 +446,51 @@ class FeatureBase {
   detail::Surface surf_;
 };
 
+/* ---------------------------------------------------------------- cloud utilities */
+/* pcl::removeNaNFromPointCloud (SHOT.cpp:298-299): keeps the rows with finite x, y, z (all fields of the kept
+ * points are copied), index = their positions in the input; cloud_out becomes dense and unorganised. */
+template <class PointT>
+inline void removeNaNFromPointCloud(const PointCloud<PointT> &cloud_in, PointCloud<PointT> &cloud_out,
+                                    std::vector<int> &index) {
+  const size_t n = cloud_in.size();
+  std::vector<int> idx(n ? n : 1);
+  std::vector<float> xyz((n ? n : 1) * 3);
+  int kept = 0;
+  if (n && (!detail::ctx() ||
+            !detail::ok(b200_remove_nan(detail::ctx(), detail::xyz(cloud_in.points), (int)n, detail::stride<PointT>(),
+                                        xyz.data(), idx.data(), &kept),
+                        "removeNaNFromPointCloud")))
+    kept = 0;
+  PointCloud<PointT> out;
+  out.points.resize((size_t)kept);
+  for (int i = 0; i < kept; ++i) out.points[(size_t)i] = cloud_in.points[(size_t)idx[(size_t)i]];
+  out.width = (uint32_t)kept;
+  out.height = 1;
+  out.is_dense = true;
+  index.assign(idx.begin(), idx.begin() + kept);
+  cloud_out = out; /* in-place use (cloud_in == cloud_out) is what the reference does */
+}
+
+/* pcl::transformPointCloud(cloud_in, cloud_out, transform) with a 4x4 matrix (the model placed by a pose before
+ * ICP and for display, SHOT_demo.cpp:590-663). */
+template <class PointT>
+inline void transformPointCloud(const PointCloud<PointT> &cloud_in, PointCloud<PointT> &cloud_out, const Matrix4f &transform) {
+  const size_t n = cloud_in.size();
+  std::vector<float> xyz((n ? n : 1) * 3);
+  if (n && (!detail::ctx() ||
+            !detail::ok(b200_transform_points(detail::ctx(), detail::xyz(cloud_in.points), (int)n, detail::stride<PointT>(),
+                                              transform.m, xyz.data()),
+                        "transformPointCloud")))
+    return;
+  PointCloud<PointT> out = cloud_in;
+  for (size_t i = 0; i < n; ++i) {
+    out.points[i].x = xyz[3 * i + 0];
+    out.points[i].y = xyz[3 * i + 1];
+    out.points[i].z = xyz[3 * i + 2];
+  }
+  cloud_out = out;
+}
+
 /* ---------------------------------------------------------------- normals (a10) */
 /* pcl::NormalEstimationOMP (SHOT.cpp:302-308, SHOT_demo.cpp:405-411, FPFH_demo.cpp:416-420) */
 template <class PointInT, class PointOutT = Normal>

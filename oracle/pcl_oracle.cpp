@@ -2071,6 +2071,39 @@ int orc_glibc_rand_nth(unsigned seed, int nth) {
   return v;
 }
 
+/* pcl::removeNaNFromPointCloud (common/impl/filter.hpp; SHOT.cpp:298-299): rows with finite x, y, z, in order. */
+int orc_remove_nan(const float *xyz, int n, int stride, float *out_xyz, int *out_index) {
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    const float *p = xyz + (size_t)i * stride;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    for (int a = 0; a < 3; ++a) out_xyz[3 * (size_t)k + a] = p[a];
+    if (out_index) out_index[k] = i;
+    ++k;
+  }
+  return k;
+}
+
+/* pcl::transformPointCloud(in, out, Matrix4f) (common/impl/transforms.hpp): x' = ((t00 x + t01 y) + t02 z) + t03 in
+ * float32, row by row; in a non-dense cloud rows with a non-finite coordinate are left as they are. */
+void orc_transform_points(const float *xyz, int n, int stride, const float *T, float *out_xyz) {
+  for (int i = 0; i < n; ++i) {
+    const float *p = xyz + (size_t)i * stride;
+    float *o = out_xyz + 3 * (size_t)i;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) {
+      o[0] = p[0], o[1] = p[1], o[2] = p[2];
+      continue;
+    }
+    for (int r = 0; r < 3; ++r) {
+      float v = T[r * 4 + 0] * p[0];
+      v += T[r * 4 + 1] * p[1];
+      v += T[r * 4 + 2] * p[2];
+      v += T[r * 4 + 3];
+      o[r] = v;
+    }
+  }
+}
+
 void orc_umeyama3(const double *src, const double *dst, int n, double T16[16]) { umeyama3(src, dst, n, T16); }
 uint32_t orc_mt19937_nth(uint32_t seed, int nth) {
   std::mt19937 rng(seed);

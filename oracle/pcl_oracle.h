@@ -121,6 +121,10 @@ int orc_board_lrf(const float *surf, const float *normals, int n, int sstride, c
                   double radius, const orc_board_params *bp, unsigned rand_seed, int rand_skip, float *out);
 int orc_glibc_rand_nth(unsigned seed, int nth); /* nth value of rand() after srand(seed), nth >= 1 */
 
+/* pcl::removeNaNFromPointCloud / pcl::transformPointCloud (SHOT.cpp:298-299; the model placed by a pose before ICP). */
+int orc_remove_nan(const float *xyz, int n, int stride, float *out_xyz, int *out_index);
+void orc_transform_points(const float *xyz, int n, int stride, const float *T16, float *out_xyz);
+
 /* pcl::IterativeClosestPoint::align + getFitnessScore (SHOT.cpp:177-192, SHOT_demo.cpp:604-663).  PCL defaults:
  * max_corr_dist <= 0 = unlimited, transformation_epsilon 0, euclidean_fitness_epsilon -DBL_MAX.  final_T: row-major
  * 4x4; aligned (nullable): ns x 3. */

@@ -67,6 +67,10 @@ def lib():
                                     C.c_uint, C.c_int, fp]
         L.orc_glibc_rand_nth.restype = C.c_int
         L.orc_glibc_rand_nth.argtypes = [C.c_uint, C.c_int]
+        L.orc_remove_nan.restype = C.c_int
+        L.orc_remove_nan.argtypes = [fp, C.c_int, C.c_int, fp, ip]
+        L.orc_transform_points.restype = None
+        L.orc_transform_points.argtypes = [fp, C.c_int, C.c_int, fp, fp]
         L.orc_icp_align.restype = C.c_int
         L.orc_icp_align.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_double, fp, fp, fp, C.POINTER(C.c_double), ip, ip]
@@ -236,6 +240,22 @@ def board_lrf(surf, normals, kp, radius, params=None, rand_seed=1, rand_skip=0):
 
 def glibc_rand_nth(seed, nth):
     return lib().orc_glibc_rand_nth(int(seed), int(nth))
+
+
+def remove_nan(xyz):
+    xyz = _pts(xyz)
+    out = np.zeros((max(len(xyz), 1), 3), dtype=np.float32)
+    idx = np.zeros(max(len(xyz), 1), dtype=np.int32)
+    n = lib().orc_remove_nan(_f(xyz), len(xyz), xyz.shape[1], _f(out), _i(idx))
+    return out[:n].copy(), idx[:n].copy()
+
+
+def transform_points(xyz, transform):
+    xyz = _pts(xyz)
+    T = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+    out = np.zeros((max(len(xyz), 1), 3), dtype=np.float32)
+    lib().orc_transform_points(_f(xyz), len(xyz), xyz.shape[1], _f(T), _f(out))
+    return out[:len(xyz)]
 
 
 def icp_align(source, target, max_iterations=10, max_corr_dist=0.0, transformation_epsilon=0.0,

@@ -173,7 +173,7 @@ def test_shot_recognition_app_icp_refinement(apps, orc, synth, tmp_path):
     assert len(rec) == min(len(T), 8) and len(rec) >= 1
     assert "ICP has converged, score is" in r.stdout
     for i in range(min(len(rec), 3)):
-        o = orc.icp_align(model, scene, max_iterations=4, guess=T[i])
+        o = orc.icp_align(orc.transform_points(model, T[i]), scene, max_iterations=4)
         assert np.abs(rec[i, :16].reshape(4, 4) - o["final_transform"]).max() < 1e-4
         assert abs(rec[i, 16] - o["fitness"]) <= 1e-3 * o["fitness"] and rec[i, 17] == float(o["converged"])
 

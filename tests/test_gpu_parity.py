@@ -737,3 +737,27 @@ def test_library_file_roundtrip(ctx, orc, synth, b200, tmp_path):
     lib2.close()
     ctx2.close()
     lib.close()
+
+
+# ------------------------------------------------------------------------------------------ cloud utilities
+def test_remove_nan_and_transform_bit_exact(ctx, orc, synth):
+    """removeNaNFromPointCloud (SHOT.cpp:298-299) and transformPointCloud with a 4x4 (model placed by a pose before
+    ICP): bit-exact against the restatement, including non-finite rows, strided input and empty clouds."""
+    from scipy.spatial.transform import Rotation
+    rng = _rng(21)
+    c = synth.make_scene(("y",), 20000, scene_id=2)
+    c = np.concatenate([c, rng.uniform(0, 1, (len(c), 5)).astype(np.float32)], axis=1)   # stride 8, like PointXYZRGBA
+    bad = rng.choice(len(c), 300, replace=False)
+    c[bad[:100], 0] = np.nan
+    c[bad[100:200], 1] = np.inf
+    c[bad[200:], 2] = -np.inf
+    kept, idx = ctx.remove_nan(c)
+    okept, oidx = orc.remove_nan(c)
+    assert np.array_equal(idx, oidx) and kept.tobytes() == okept.tobytes() and len(kept) == len(c) - 300
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = Rotation.from_rotvec([0.7, -0.4, 1.1]).as_matrix()
+    T[:3, 3] = [0.31, -1.2, 0.77]
+    a, b = ctx.transform_points(c, T), orc.transform_points(c, T)
+    assert a.tobytes() == b.tobytes()
+    assert len(ctx.remove_nan(np.zeros((0, 3), np.float32))[0]) == 0
+    assert len(ctx.transform_points(np.zeros((0, 3), np.float32), T)) == 0

@@ -406,3 +406,24 @@ def test_board_lrf_properties(orc):
         d = surf[j] - kp2[0]
         d[2] = 0
         assert np.dot(f[0], d / np.linalg.norm(d)) > 0.99
+
+
+def test_cloud_utilities(orc):
+    """removeNaNFromPointCloud keeps the finite rows in order; transformPointCloud applies the 4x4 in float32 and
+    leaves non-finite rows alone."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.Generator(np.random.PCG64(11))
+    c = rng.uniform(-1, 1, (50, 3)).astype(np.float32)
+    c[3] = np.nan
+    c[17, 1] = np.inf
+    kept, idx = orc.remove_nan(c)
+    assert idx.tolist() == [i for i in range(50) if i not in (3, 17)] and np.array_equal(kept, c[idx])
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = Rotation.from_rotvec([0.3, -0.2, 0.5]).as_matrix()
+    T[:3, 3] = [0.1, 0.2, -0.3]
+    out = orc.transform_points(c, T)
+    ok = np.isfinite(c).all(1)
+    ref = c[ok].astype(np.float64) @ T[:3, :3].astype(np.float64).T + T[:3, 3]
+    assert np.abs(out[ok] - ref).max() < 1e-6
+    assert np.array_equal(out[~ok], c[~ok], equal_nan=True)
+    assert len(orc.remove_nan(np.zeros((0, 3), np.float32))[0]) == 0
