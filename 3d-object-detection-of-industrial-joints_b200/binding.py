@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
     "b200_library_add_view_descriptors", "b200_library_set_view_pose", "b200_library_get_view_pose",
-    "b200_library_save", "b200_library_load", "b200_register_scene_batch_shot",
+    "b200_library_save", "b200_library_load", "b200_register_scene_batch_shot", "b200_lanes_release",
     "b200_library_view_size", "b200_library_download_view", "b200_register_scene_library",
     "b200_hough3d_recognize",
     "b200_icp_align",
@@ -150,6 +150,7 @@ def lib():
             "b200_register_scene_batch_shot": [i, vp, i, C.POINTER(fp), ip, i, C.POINTER(fp), ip, i, C.POINTER(ShotParams), i,
                                                C.POINTER(fp), C.POINTER(ip), C.POINTER(C.POINTER(Corr)), ip, ip,
                                                C.POINTER(C.POINTER(Corr)), ip, ip],
+            "b200_lanes_release": [i],
             "b200_library_views": [vp],
             "b200_library_view_size": [vp, i],
             "b200_library_download_view": [vp, vp, i, fp, fp],
@@ -735,6 +736,11 @@ def register_scene_batch(model, scenes, keypoints, params, lanes=4, device=0):
         out.append({"transforms": T[s][:m].reshape(m, 4, 4), "instances": InstanceList(ic[s], off[s], m),
                     "n_instances": int(n_inst[s]), "corrs": co[s][:int(n_corr[s])], "status": int(status[s])})
     return out
+
+
+def lanes_release(device=0):
+    """Frees the contexts b200_register_scene_batch_shot keeps for `device`."""
+    lib().b200_lanes_release(int(device))
 
 
 # ---- the reference's text dump of a view's descriptors (CAD_desc.cpp:354-370) ----------------------------------

@@ -957,6 +957,14 @@ int b200_register_scene_batch_shot(int device, const b200_model *model, int n_sc
   return B200_OK;
 }
 
+int b200_lanes_release(int device) {
+  LanePool &pool = lane_pool(device);
+  std::lock_guard<std::mutex> hold(pool.mu);
+  for (b200_ctx *c : pool.ctxs) b200_ctx_destroy(c);
+  pool.ctxs.clear();
+  return B200_OK;
+}
+
 /* ------------------------------------------------------------------ multi-view library */
 static const std::array<float, 16> kIdentityPose = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
 int b200_library_create(b200_ctx *ctx, b200_library **out) {

@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(FPFH_THREADS)
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_count;
   __shared__ double s_sum[3];
+  __shared__ double s_part[FPFH_THREADS / 32][3];
+  __shared__ float s_tile[32 * 33];
   unsigned long long *key;
   int *pos;
   if (glob_key) {
@@ -204,28 +206,46 @@ __global__ void __launch_bounds__(FPFH_THREADS)
     int n = gather_radius(g, c.x, c.y, c.z, radius, r2, key, pos, cap, &s_count);
     if (n > cap) n = cap;
     bitonic_sort(key, pos, n);
+    // Products spfh[neighbour][bin] * (1 / d2) are staged 32 neighbours at a time by the whole CTA (independent
+    // loads in flight together), then
+    //  - one lane per bin adds them in float32, sequentially in PCL's (d2, index) order (the weighted histogram);
+    //  - every thread adds the products it staged into float64 partial sums of the three 11-bin blocks (PCL adds
+    //    the same float products into a double neighbour by neighbour; the double sum is exact to ~1e-16 either
+    //    way and only its float32 cast is used).
+    double part[3] = {0.0, 0.0, 0.0};
     float acc = 0.0f;
-    if (tid < 33) {
-      for (int j = 0; j < n; ++j) {
-        const float d2 = key_d2(key[j]);
-        if (d2 == 0.0f) continue;
-        const float weight = 1.0f / d2;
-        const float val = spfh[(size_t)key_orig(key[j]) * 33 + tid] * weight;
-        acc += val;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+      const int m = min(32, n - c0);
+      for (int idx = tid; idx < m * 33; idx += FPFH_THREADS) {
+        const int jj = idx / 33, b = idx - jj * 33;
+        const unsigned long long kj = key[c0 + jj];
+        const float d2 = key_d2(kj);
+        float val = 0.0f;  // d2 == 0: PCL skips the neighbour (adding +0 leaves the non-negative sums unchanged)
+        if (d2 != 0.0f) {
+          const float weight = 1.0f / d2;
+          val = spfh[(size_t)key_orig(kj) * 33 + b] * weight;
+          part[b / 11] += (double)val;
+        }
+        s_tile[idx] = val;
       }
-    } else if (tid >= 64 && tid < 67) {
-      // float64 running sum of one 11-bin block in PCL's order (neighbour-major, bin-minor)
-      const int f = tid - 64;
+      __syncthreads();
+      if (tid < 33)
+        for (int jj = 0; jj < m; ++jj) acc += s_tile[jj * 33 + tid];
+      __syncthreads();
+    }
+#pragma unroll
+    for (int f = 0; f < 3; ++f) part[f] = warp_sum(part[f]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int f = 0; f < 3; ++f) s_part[tid >> 5][f] = part[f];
+    }
+    __syncthreads();
+    if (tid < 3) {
       double sum = 0.0;
-      for (int j = 0; j < n; ++j) {
-        const float d2 = key_d2(key[j]);
-        if (d2 == 0.0f) continue;
-        const float weight = 1.0f / d2;
-        const float *row = spfh + (size_t)key_orig(key[j]) * 33 + f * 11;
-        for (int b = 0; b < 11; ++b) sum += (double)(row[b] * weight);
-      }
+#pragma unroll
+      for (int w = 0; w < FPFH_THREADS / 32; ++w) sum += s_part[w][tid];
       if (sum != 0) sum = 100.0 / sum;
-      s_sum[f] = sum;
+      s_sum[tid] = sum;
     }
     __syncthreads();
     if (tid < 33) {

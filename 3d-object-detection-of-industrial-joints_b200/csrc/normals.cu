@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(128) normals_radius_kernel(GridView g, const f
                                                              float vpy, float vpz, float4 *__restrict__ out) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_count;
+  __shared__ float4 s_pts[128];
   unsigned long long *key;
   int *pos;
   if (glob_key) {
@@ -156,12 +157,17 @@ __global__ void __launch_bounds__(128) normals_radius_kernel(GridView g, const f
     int n = gather_radius(g, p.x, p.y, p.z, radius, r2, key, pos, cap, &s_count);
     if (n > cap) n = cap;
     bitonic_sort(key, pos, n);
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      float acc = 0.0f;
-      if (n >= 3 && lane < 9) {
-        for (int j = 0; j < n; ++j) {
-          const float4 v = g.pts[pos[j]];
+    // the nine float32 sums run sequentially in PCL's (d2, index) order, one lane each; the points are staged 128
+    // at a time by the whole CTA so that their loads are in flight together instead of one per loop step
+    float acc = 0.0f;
+    for (int c0 = 0; c0 < n && n >= 3; c0 += 128) {
+      const int m = min(128, n - c0);
+      if ((int)threadIdx.x < m) s_pts[threadIdx.x] = g.pts[pos[c0 + threadIdx.x]];
+      __syncthreads();
+      if (threadIdx.x < 9) {
+        const int lane = threadIdx.x;
+        for (int j = 0; j < m; ++j) {
+          const float4 v = s_pts[j];
           float a, b;
           switch (lane) {
             case 0: a = v.x, b = v.x; break;
@@ -176,8 +182,12 @@ __global__ void __launch_bounds__(128) normals_radius_kernel(GridView g, const f
           }
           acc += (lane < 6) ? a * b : a;
         }
-        acc = acc / (float)n;
       }
+      __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      if (n >= 3 && lane < 9) acc = acc / (float)n;
       float accu[9];
 #pragma unroll
       for (int a = 0; a < 9; ++a) accu[a] = __shfl_sync(0xffffffffu, acc, a);

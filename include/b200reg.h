@@ -295,6 +295,10 @@ B200_API int b200_register_scene_batch_shot(int device, const b200_model *model,
                                             int *const *inst_offsets, b200_corr *const *inst_corrs, const int *corr_cap,
                                             int *n_inst, b200_corr *const *corrs_out, int *n_corrs, int *status);
 
+/* The lane contexts of b200_register_scene_batch_shot (streams, arenas: about 1.3 GB each for a 1 M-point scene) stay
+ * alive between batches; this frees the ones of `device`. */
+B200_API int b200_lanes_release(int device);
+
 /* ---------------------------------------------------------------- multi-view library ----- */
 /* The reference recognises against a set of rendered partial views of the CAD models: CAD_desc.cpp:231-370
  * builds one SHOT descriptor set per view, and SHOT.cpp:243-483 / 6Dpose.cpp / SHOT_demo.cpp:430-663 loop over

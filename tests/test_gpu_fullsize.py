@@ -249,6 +249,9 @@ def test_config5_scene_batch_lanes_are_deterministic(b200, synth, pkg):
         assert a["corrs"].tobytes() == b["corrs"].tobytes() and np.array_equal(a["transforms"], b["transforms"])
         assert all(x.tobytes() == y.tobytes() for x, y in zip(a["instances"], b["instances"]))
     assert b200.register_scene_batch(m, [], [], p) == []
+    b200.lanes_release(0)
+    assert b200.register_scene_batch(m, scenes[:2], kps[:2], p, lanes=2)[1]['n_instances'] == seq[1]['n_instances']
+    b200.lanes_release(0)
     m.close()
     for c in ctxs:
         c.close()
