@@ -475,16 +475,31 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
     j = cand_j[(size_t)i * nc + c];
     s = cand_s[(size_t)i * nc + c];
   }
-  const bool pair_ok = row_ok && j >= 0 && j < Km;
+  bool pair_ok = row_ok && j >= 0 && j < Km;
   // s_cut: every model row that is not a candidate has approximate s >= the worst kept value of its split
   float s_cut = __int_as_float(0x7f800000);
   if (row_ok && (c % TC_CAND) == TC_CAND - 1) s_cut = s;
   for (int o = nc >> 1; o > 0; o >>= 1) s_cut = fminf(s_cut, __shfl_xor_sync(0xffffffffu, s_cut, o));
 
+  // Prune: a candidate whose approximate value exceeds the row's smallest one by more than twice the error bound
+  // cannot have the smallest float32 distance (nor tie with it), so its exact distance is never needed.  Typically
+  // a handful of the nc candidates survive; their rows are the only ones staged below.
+  {
+    float s_min = pair_ok ? s : __int_as_float(0x7f800000);
+    for (int o = nc >> 1; o > 0; o >>= 1) s_min = fminf(s_min, __shfl_xor_sync(0xffffffffu, s_min, o));
+    if (pair_ok) {
+      const float nai = na[i], nbm = normmaxB[0];
+      const float d_lo = fmaxf(nai + s_min, 0.0f);
+      const float e = 2.0f * eta * sqrtf(nai * nbm) + 4e-5f * (nai + nbm + d_lo + 4.0f * eta * sqrtf(nai * nbm)) +
+                      4e-6f * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+      pair_ok = s <= s_min + 2.0f * e;
+    }
+  }
+
   float acc = 0.0f;
   for (int d0 = 0; d0 < D; d0 += RS_CHUNK) {
     const int w = min(RS_CHUNK, D - d0);
-    // stage: scene rows, then the 32 candidate rows (two coalesced 128-byte loads per row)
+    // stage: scene rows, then the surviving candidate rows (two coalesced 128-byte loads per row)
     for (int rr = 0; rr < rpw; ++rr) {
       const int ii = gw * rpw + rr;
       for (int dd = lane; dd < w; dd += 32) sm.a[rr][dd] = (ii < Ks) ? scene[(size_t)ii * D + d0 + dd] : 0.0f;
