@@ -129,17 +129,22 @@ class Turnstile:
                 self._cv.notify_all()
 
 
-def run_lanes(n_lanes, n_steps, step_fn, first_step=0):
+def run_lanes(n_lanes, n_steps, step_fn, first_step=0, stagger_s=0.0):
     """Scenes within one rank are independent too: lane l (one host thread driving its own b200 context and
     CUDA stream) runs steps l, l + n_lanes, ... of `n_steps`, so that the latency-bound grouping stage of one
     scene (8 SMs) overlaps the wide stages of the next ones on the rest of the GPU.  step_fn(lane, step) is
     called on the lane's thread; exceptions are re-raised on the caller's thread.  Returns after every lane has
-    issued (not necessarily completed) its steps."""
+    issued (not necessarily completed) its steps.  stagger_s: lane l starts l * stagger_s late, so that lanes
+    released together do not walk through the same stages in lockstep (all in the wide stages, then all in
+    grouping with most of the GPU idle) until they drift apart by themselves."""
     import threading
     errors = []
 
     def work(lane):
         try:
+            if stagger_s > 0.0 and lane > 0:
+                import time
+                time.sleep(lane * stagger_s)
             for s in range(first_step + lane, first_step + n_steps, n_lanes):
                 if errors:
                     break

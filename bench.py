@@ -317,7 +317,8 @@ def run_b200(args, rank, world, local_rank):
     ev_start = torch.cuda.Event(enable_timing=True)
     ev_ends = [torch.cuda.Event(enable_timing=True) for _ in range(L)]
     ev_start.record(streams[0])
-    sharding.run_lanes(L, args.steps, lambda lane, s: step(lane, s, flush=True))
+    stagger = single_ms / 1e3 / L   # inside the timed region: lane l starts l/L of a scene latency late
+    sharding.run_lanes(L, args.steps, lambda lane, s: step(lane, s, flush=True), stagger_s=stagger)
     for l in range(L):
         ev_ends[l].record(streams[l])
     torch.cuda.synchronize()
@@ -360,7 +361,7 @@ def run_b200(args, rank, world, local_rank):
     e2e_steps = max(6 * L, args.steps)   # enough steps per lane for the lanes to fall out of lockstep
     gate.reset()
     t0 = time.perf_counter()
-    sharding.run_lanes(L, e2e_steps, e2e_step)
+    sharding.run_lanes(L, e2e_steps, e2e_step, stagger_s=stagger)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     res = results[0]
