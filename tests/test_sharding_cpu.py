@@ -162,3 +162,25 @@ def test_lanes_keep_collective_order_gloo_world2(tmp_path):
     mp.spawn(_lanes_worker, args=(world, _free_port(), ROOT, PKG_NAME, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert int(np.load(tmp_path / ("lok%d.npy" % r))[0]) == 1
+
+
+def test_bench_reference_arm_json_contract():
+    """bench.py --impl reference (the CPU arm) prints exactly one JSON line with the contract's keys; run on a reduced
+    workload so that the CPU suite stays short."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--scene-points", "150000", "--model-points", "8000", "--cpu-sample", "200"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "descriptors/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
