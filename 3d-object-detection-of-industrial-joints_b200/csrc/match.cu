@@ -51,28 +51,17 @@ __global__ void init_best_kernel(unsigned long long *best, int *zero_cnt, int n)
   }
 }
 
-__global__ void __launch_bounds__(MTHREADS)
-    match_tile_kernel(const float *__restrict__ model, int Km, const unsigned char *__restrict__ model_valid,
-                      const float *__restrict__ scene, int Ks, int D, const int *__restrict__ row_map,
-                      const int *__restrict__ n_rows_dev, unsigned long long *__restrict__ best,
-                      int *__restrict__ zero_cnt) {
-  __shared__ float As[MT][MKC + 1];
-  __shared__ float Bs[MT][MKC + 1];
-  __shared__ int s_row[MT];
+// Exact float32 distances of one 64-row scene block against the model tiles t0, t0 + tstep, ...; the running
+// minimum per scene row goes to best[] / zero_cnt[] with atomics.  s_row: the block's scene rows (-1 = none).
+__device__ __forceinline__ void match_block_tiles(const float *__restrict__ model, int Km,
+                                                  const unsigned char *__restrict__ model_valid,
+                                                  const float *__restrict__ scene, int D, float (*As)[MKC + 1],
+                                                  float (*Bs)[MKC + 1], const int *s_row, int t0, int tstep, int tend,
+                                                  unsigned long long *__restrict__ best, int *__restrict__ zero_cnt) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int s0 = blockIdx.x * MT;
-  // optional indirection: only the rows listed in row_map (the tensor-core filter's uncertified rows)
-  const int n_rows = row_map ? *n_rows_dev : Ks;
-  if (s0 >= n_rows) return;
-  if (threadIdx.x < MT) {
-    const int r = s0 + threadIdx.x;
-    s_row[threadIdx.x] = (r < n_rows) ? (row_map ? row_map[r] : r) : -1;
-  }
-  __syncthreads();
   unsigned long long rbest[4] = {~0ull, ~0ull, ~0ull, ~0ull};
   int rzero[4] = {0, 0, 0, 0};
-  const int ntiles = (Km + MT - 1) / MT;
-  for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+  for (int tile = t0; tile < tend; tile += tstep) {
     const int m0 = tile * MT;
     float acc[4][4];
 #pragma unroll
@@ -133,6 +122,50 @@ __global__ void __launch_bounds__(MTHREADS)
       if (k != ~0ull) atomicMin(&best[sr], k);
       if (z) atomicAdd(&zero_cnt[sr], z);
     }
+  }
+}
+
+// all scene rows: grid (scene blocks, model-tile slices)
+__global__ void __launch_bounds__(MTHREADS)
+    match_tile_kernel(const float *__restrict__ model, int Km, const unsigned char *__restrict__ model_valid,
+                      const float *__restrict__ scene, int Ks, int D, unsigned long long *__restrict__ best,
+                      int *__restrict__ zero_cnt) {
+  __shared__ float As[MT][MKC + 1];
+  __shared__ float Bs[MT][MKC + 1];
+  __shared__ int s_row[MT];
+  const int s0 = blockIdx.x * MT;
+  if (s0 >= Ks) return;
+  if (threadIdx.x < MT) {
+    const int r = s0 + threadIdx.x;
+    s_row[threadIdx.x] = (r < Ks) ? r : -1;
+  }
+  __syncthreads();
+  match_block_tiles(model, Km, model_valid, scene, D, As, Bs, s_row, blockIdx.y, gridDim.y, (Km + MT - 1) / MT, best,
+                    zero_cnt);
+}
+
+// the rows listed in row_map (the tensor-core filter's uncertified rows; their number is only known on the device):
+// persistent CTAs take (row block, model tile) items in turn, so that a handful of rows still spreads over the GPU
+__global__ void __launch_bounds__(MTHREADS)
+    match_rows_kernel(const float *__restrict__ model, int Km, const unsigned char *__restrict__ model_valid,
+                      const float *__restrict__ scene, int D, const int *__restrict__ row_map,
+                      const int *__restrict__ n_rows_dev, unsigned long long *__restrict__ best,
+                      int *__restrict__ zero_cnt) {
+  __shared__ float As[MT][MKC + 1];
+  __shared__ float Bs[MT][MKC + 1];
+  __shared__ int s_row[MT];
+  const int n_rows = *n_rows_dev;
+  const int ntiles = (Km + MT - 1) / MT;
+  const long long items = (long long)((n_rows + MT - 1) / MT) * ntiles;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int s0 = (int)(item / ntiles) * MT, tile = (int)(item % ntiles);
+    __syncthreads();  // the previous item's readers of s_row are done
+    if (threadIdx.x < MT) {
+      const int r = s0 + threadIdx.x;
+      s_row[threadIdx.x] = (r < n_rows) ? row_map[r] : -1;
+    }
+    __syncthreads();
+    match_block_tiles(model, Km, model_valid, scene, D, As, Bs, s_row, tile, ntiles, tile + 1, best, zero_cnt);
   }
 }
 
@@ -233,15 +266,12 @@ int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene,
         B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_fallback, fb_count.p, sizeof(int), cudaMemcpyDeviceToHost,
                                        ctx->stream));
       }
-      // uncertified rows: exact evaluation.  They are few, so the model side is split finely to keep
-      // every SM busy (grid sized for the worst case; CTAs past fb_count exit at once)
-      dim3 grid_fb(sx, std::max(1, std::min(mtiles, 32)));
-      match_tile_kernel<<<grid_fb, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, fb_rows.p,
-                                                               fb_count.p, best.p, zero_cnt.p);
+      // uncertified rows: exact evaluation by persistent CTAs over (row block, model tile) items
+      match_rows_kernel<<<ctx->sm_count * 4, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, D, fb_rows.p,
+                                                                        fb_count.p, best.p, zero_cnt.p);
       B200_LAUNCHED(ctx);
     } else {
-      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, nullptr, nullptr,
-                                                            best.p, zero_cnt.p);
+      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, best.p, zero_cnt.p);
       B200_LAUNCHED(ctx);
     }
   }

@@ -39,7 +39,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
 constexpr int TC_BK = 64;  // fp16 elements per k-block = 128 bytes = one swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_CAND = 8;
+constexpr int TC_CAND = 4;
 constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_EPI_WARPS = 16;  // TC_PARTS warps per TMEM lane quarter, each handles 1/TC_PARTS of the tile's columns
 constexpr int TC_PARTS = TC_EPI_WARPS / 4;
@@ -448,7 +448,7 @@ constexpr int RS_CHUNK = 64;
 constexpr int RS_WARPS_PER_CTA = 8;
 
 struct RescoreSmem {
-  float a[4][RS_CHUNK];        // scene rows of the warp (at most 4)
+  float a[32 / TC_CAND][RS_CHUNK];  // scene rows of the warp (32 / nc of them, nc >= TC_CAND)
   float b[32][RS_CHUNK + 1];   // candidate rows, padded: lane l reads b[l][d], conflict free
 };
 
