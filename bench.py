@@ -38,8 +38,8 @@ _REAL_STDOUT = None
 
 # DRAM read + write bytes per launch of each stage's main kernel, from the committed `ncu --set full` capture of the
 # default workload (profiles/summary_r01.md)
-TRAFFIC_NCU = {"match_filter": 296.0e6, "gc_group": 26.0e6, "gc_ransac": 1.4e6, "match": 296.0e6 + 156.5e6, "normals": 23.0e6,
-               "shot": 123.2e6, "gc_adjacency": 73.6e6, "gc_sort": 1.0e6}
+TRAFFIC_NCU = {"match_filter": 332.2e6, "gc_group": 25.7e6, "gc_ransac": 1.4e6, "match": 332.2e6 + 142.8e6,
+               "normals": 35.3e6, "shot": 145.9e6, "gc_adjacency": 50.4e6, "gc_sort": 1.0e6}
 
 
 def _emit(line):
@@ -417,7 +417,7 @@ def run_b200(args, rank, world, local_rank):
                 # exact float32 results from fp16 tensor cores: each operand is split into hi + lo halves and three
                 # of the four products are issued (the stage also holds the exact rescoring of 8 candidates per row)
                 r["note"] = ("algorithmic flop = 2*K_s*K_m*352; the tcgen05 filter issues 3x that (fp16 hi/lo split, "
-                             "error ~2^-22) and runs at 73 % tensor-pipe activity (ncu, profiles/summary_r01.md); "
+                             "error ~2^-22) and runs at 88 % tensor-pipe activity (ncu, profiles/summary_r01.md); "
                              "exact FP32 rescoring + certificate make the result bit-identical to the FP32 search")
                 if k == "match_filter":
                     r["kernel"] = "tc_filter_kernel"
