@@ -10,20 +10,24 @@
 //   TMEM).  Each fp32 value is split into fp16 terms x = x1 + x2 (x1 = rn16(x), x2 = rn16(x - x1)) and
 //   the contraction runs over the concatenated K' = [a1|a1|a2] . [b1|b2|b1] (3 terms, ~2^-22 relative
 //   operand error) or just a1.b1 (1 term, 2^-11), after an exact power-of-two rescale into fp16 range.
-//   The epilogue (4 warps, one TMEM lane = one scene row per thread) keeps the 8 smallest s_ij of the
-//   row in registers across all model tiles.
+//   The epilogue (16 warps: one TMEM lane = one scene row per thread, four column parts per row) keeps the
+//   TC_CAND smallest s_ij of the row in registers across all model tiles; the parts' lists are merged per row.
 //   A second kernel rescoring those candidates with the exact sequential float32 distance then
-//   CERTIFIES the arg-min: every non-candidate has approximate s >= the 8th smallest, so if the best
-//   exact distance is below |a_i|^2 + s_8 - eps (eps = proven error bound of the approximation) no
+//   CERTIFIES the arg-min: every non-candidate has approximate s >= the TC_CAND-th smallest s_c, so if the best
+//   exact distance is below |a_i|^2 + s_c - eps (eps = proven error bound of the approximation) no
 //   other row can win or tie.  Rows that cannot be certified are re-evaluated exactly by
-//   match_tile_kernel.  The result is therefore bit-identical to the exact path.
+//   match_rows_kernel.  The result is therefore bit-identical to the exact path.
+//   TC_CAND = 4: with 32 independent rows per warp some lane inserts at almost every 32-column chunk, and
+//   the insertion cost made the epilogue co-limiting at 8 (1.78 ms, tensor pipe 73 % active; 1.45 ms and
+//   88 % at 4; a handful of rows per 100 k then miss the certificate and take the exact path).
 //
 // Kernel structure (one CTA per SM, persistent over (scene tile, model split) work items):
 //   warp 0   TMA producer: 4-stage ring of {A 128x64, B 256x64} fp16 tiles, SWIZZLE_128B
 //   warp 1   TMEM allocator (512 columns = two 128x256 fp32 accumulators) + single-thread MMA issuer:
 //            tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, smem descriptors, commit → mbarrier
-//   warps 2-9 epilogue (two per TMEM lane quarter, half of the columns each): tcgen05.ld 32x32b.x32 → s = nb_j - 2*acc → top-8 insert; overlaps the next
-//            tile's MMAs through the second accumulator
+//   warps 2-17 epilogue (four per TMEM lane quarter, a quarter of the columns each): tcgen05.ld 32x32b.x32 →
+//            s = nb_j - 2*acc → sorted insert into the row's candidate list; overlaps the next tile's MMAs
+//            through the second accumulator
 // Roofline: tensor pipe; 2*Ks*Km*K' flop per call.
 #include <cuda.h>
 #include <cuda_fp16.h>
