@@ -25,7 +25,7 @@ EXPORTS = [
     "b200_dev_shot352", "b200_fpfh33", "b200_dev_fpfh33", "b200_match", "b200_dev_match", "b200_gc_recognize",
     "b200_model_create_shot", "b200_model_destroy", "b200_model_size", "b200_model_download",
     "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
-    "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
+    "b200_ctx_set_blocking_sync", "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
     "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio",
     "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
@@ -117,6 +117,7 @@ def lib():
             "b200_dev_register_scene_shot": [vp, vp, vp, i, i, vp, i, i, C.POINTER(ShotParams), vp, vp, vp, vp, i, vp,
                                              vp, vp, vp],
             "b200_last_neighbor_stats": [vp, C.POINTER(d), ip],
+            "b200_ctx_set_blocking_sync": [vp, i],
             "b200_ctx_set_profiling": [vp, i],
             "b200_ctx_reset_profiling": [vp],
             "b200_ctx_stage_count": [],
@@ -417,6 +418,10 @@ class Context:
                 ch.close()
             lib().b200_ctx_destroy(self.h)
             self.h = None
+
+    def set_blocking_sync(self, on=True):
+        """Host waits sleep on a blocking event instead of spinning (more lanes than host cores)."""
+        self._chk(lib().b200_ctx_set_blocking_sync(self.h, 1 if on else 0))
 
     def sync(self):
         self._chk(lib().b200_ctx_sync(self.h))

@@ -43,7 +43,7 @@ int readback_small(b200_ctx *ctx, const void *d_src, void *h_dst, size_t bytes) 
   }
   mailbox_publish_kernel<<<1, 64, 0, ctx->stream>>>((const unsigned *)d_src, (unsigned *)ctx->mailbox_dev, (int)(bytes / 4));
   B200_LAUNCHED(ctx);
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   memcpy(h_dst, ctx->mailbox_host, bytes);
   return B200_OK;
 }
@@ -88,7 +88,7 @@ int upload(b200_ctx *ctx, DevBuf<T> &buf, const T *host, size_t count) {
 template <class T>
 int download(b200_ctx *ctx, T *host, const T *dev, size_t count) {
   if (count) {
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     B200_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
   }
   return B200_OK;
@@ -157,7 +157,7 @@ int download_instances(b200_ctx *ctx, const float *d_T, const int *d_offsets, co
                               float *transforms, int *inst_offsets, b200_corr *inst_corrs, int corr_cap, int *n_inst) {
   int found = 0;
   B200_TRY(download(ctx, &found, d_n_inst, 1));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   *n_inst = found;
   const int m = std::min(found, max_inst);
   if (inst_offsets) inst_offsets[0] = 0;
@@ -166,11 +166,11 @@ int download_instances(b200_ctx *ctx, const float *d_T, const int *d_offsets, co
     B200_TRY(download(ctx, offs.data(), d_offsets, (size_t)m + 1));
     B200_TRY(download(ctx, cnts.data(), d_counts, (size_t)m));
     if (transforms) B200_TRY(download(ctx, transforms, d_T, (size_t)m * 16));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     const int used = std::min(offs[m], C_cap);
     std::vector<b200_corr> all((size_t)std::max(used, 1));
     B200_TRY(download(ctx, all.data(), d_inst_corrs, (size_t)used));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     int w = 0;
     bool overflow = false;
     for (int i = 0; i < m; ++i) {
@@ -245,7 +245,7 @@ int b200_ctx_create(b200_ctx **out, int device, void *stream) {
 int b200_ctx_destroy(b200_ctx *ctx) {
   if (!ctx) return B200_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  ctx->sync();
   for (auto &ev : ctx->stage_events) {
     cudaEventDestroy(ev.a);
     cudaEventDestroy(ev.b);
@@ -254,21 +254,28 @@ int b200_ctx_destroy(b200_ctx *ctx) {
   ctx->arena_destroy();
   if (ctx->mt_state) cudaFree(ctx->mt_state);
   if (ctx->mailbox_host) cudaFreeHost(ctx->mailbox_host);
+  if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200_OK;
 }
 
+int b200_ctx_set_blocking_sync(b200_ctx *ctx, int enable) {
+  API_ENTER(ctx);
+  ctx->blocking_sync = enable != 0;
+  return B200_OK;
+}
+
 int b200_ctx_sync(b200_ctx *ctx) {
   API_ENTER(ctx);
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
 int64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 static int resolve_stage_events(b200_ctx *ctx) {
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   for (auto &ev : ctx->stage_events) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {
@@ -318,14 +325,14 @@ int b200_ctx_stage_time(b200_ctx *ctx, int stage, double *total_ms, int *calls) 
 
 int b200_last_match_fallback(b200_ctx *ctx, int *rows) {
   API_ENTER(ctx);
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   if (rows) *rows = ctx->last_match_fallback;
   return B200_OK;
 }
 
 int b200_last_match_error_ratio(b200_ctx *ctx, float *ratio) {
   API_ENTER(ctx);
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   if (ratio) *ratio = ctx->last_match_err_ratio;
   return B200_OK;
 }
@@ -381,7 +388,7 @@ int b200_radius_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, 
   unsigned long long hstats[2];
   B200_TRY(download(ctx, hstats, stats.p, 2));
   B200_TRY(download(ctx, reinterpret_cast<long long *>(offsets), offs.p, (size_t)nq + 1));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   *total = offsets[nq];
   if (cap < *total || !idx || !d2) {
     if (cap == 0) return B200_OK; /* sizing call */
@@ -395,7 +402,7 @@ int b200_radius_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, 
   B200_TRY(dev_radius_fill_sized(ctx, *g, dq.p, nq, radius, (int)hstats[0], offs.p, didx.p, dd2.p));
   B200_TRY(download(ctx, idx, didx.p, (size_t)*total));
   B200_TRY(download(ctx, d2, dd2.p, (size_t)*total));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -412,7 +419,7 @@ int b200_knn_search(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int
   B200_TRY(dev_knn_search(ctx, surf, dq.p, nq, k, didx.p, dd2.p, k_found));
   B200_TRY(download(ctx, idx, didx.p, (size_t)nq * k));
   B200_TRY(download(ctx, d2, dd2.p, (size_t)nq * k));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -443,7 +450,7 @@ int b200_normals(b200_ctx *ctx, b200_cloud *surf, const float *q, int nq, int qs
     B200_TRY(dev_normals(ctx, surf, dq.p, nq, false, k, radius, viewpoint, dout.p));
   }
   B200_TRY(download(ctx, out, dout.p, (size_t)nq * 4));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -457,7 +464,7 @@ int b200_shot_lrf(b200_ctx *ctx, b200_cloud *surf, const float *kp, int K, int k
   B200_TRY(drf.alloc(ctx, (size_t)std::max(K, 1) * 9));
   B200_TRY(dev_shot(ctx, surf, nullptr, dkp.p, K, radius, nullptr, drf.p, true));
   B200_TRY(download(ctx, out, drf.p, (size_t)K * 9));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -483,7 +490,7 @@ int b200_shot352(b200_ctx *ctx, b200_cloud *surf, const float *normals, const fl
   B200_TRY(dev_shot(ctx, surf, dn.p, dkp.p, K, radius, ddesc.p, drf.p, false));
   B200_TRY(download(ctx, desc, ddesc.p, (size_t)K * 352));
   if (rf) B200_TRY(download(ctx, rf, drf.p, (size_t)K * 9));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -515,7 +522,7 @@ int b200_fpfh33(b200_ctx *ctx, b200_cloud *surf, const float *normals, const flo
     B200_TRY(dev_fpfh(ctx, surf, dn.p, dq.p, nq, false, radius, dout.p));
   }
   B200_TRY(download(ctx, out, dout.p, (size_t)nq * 33));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -541,9 +548,9 @@ int b200_match(b200_ctx *ctx, const float *model, int Km, const float *scene, in
   B200_TRY(dcount.alloc(ctx, 1));
   B200_TRY(dev_match(ctx, dm.p, Km, ds.p, Ks, D, mode, thr, dout.p, dcount.p));
   B200_TRY(download(ctx, count, dcount.p, 1));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   B200_TRY(download(ctx, out, dout.p, (size_t)*count));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -571,10 +578,10 @@ int b200_uniform_sampling(b200_ctx *ctx, const float *xyz, int n, int stride, do
   B200_TRY(dcount.alloc(ctx, 1));
   B200_TRY(dev_uniform_sampling(ctx, din.p, n, stride, (float)leaf, dout.p, didx.p, dcount.p));
   B200_TRY(download(ctx, count, dcount.p, 1));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   B200_TRY(download(ctx, out_xyz, dout.p, (size_t)*count * 3));
   if (out_index) B200_TRY(download(ctx, out_index, didx.p, (size_t)*count));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -594,7 +601,7 @@ int b200_remove_nan(b200_ctx *ctx, const float *xyz, int n, int stride, float *o
   B200_TRY(readback_small(ctx, dcount.p, count, sizeof(int)));
   B200_TRY(download(ctx, out_xyz, dout.p, (size_t)*count * 3));
   if (out_index) B200_TRY(download(ctx, out_index, didx.p, (size_t)*count));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -608,7 +615,7 @@ int b200_transform_points(b200_ctx *ctx, const float *xyz, int n, int stride, co
   B200_TRY(dout.alloc(ctx, (size_t)n * 3));
   B200_TRY(dev_transform_points(ctx, din.p, n, stride, transform, dout.p));
   B200_TRY(download(ctx, out_xyz, dout.p, (size_t)n * 3));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -634,9 +641,9 @@ int b200_voxel_grid(b200_ctx *ctx, const float *xyz, int n, int stride, float lx
   B200_TRY(dcount.alloc(ctx, 1));
   B200_TRY(dev_voxel_grid(ctx, din.p, n, stride, lx, ly, lz, dout.p, dcount.p));
   B200_TRY(download(ctx, count, dcount.p, 1));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   B200_TRY(download(ctx, out_xyz, dout.p, (size_t)*count * 3));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -738,7 +745,7 @@ int b200_board_lrf(b200_ctx *ctx, b200_cloud *surface, const float *normals, con
   B200_TRY(drf.alloc(ctx, (size_t)std::max(K, 1) * 9));
   B200_TRY(dev_board_lrf(ctx, surface, dn.p, dkp.p, K, radius, p, drf.p));
   B200_TRY(download(ctx, rf, drf.p, (size_t)K * 9));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -759,7 +766,7 @@ int b200_icp_align(b200_ctx *ctx, const float *source, int ns, int sstride, b200
   if (aligned && ns > 0) {
     std::vector<float4> h((size_t)ns);
     B200_TRY(download(ctx, h.data(), dal.p, (size_t)ns));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     for (int i = 0; i < ns; ++i) {
       aligned[3 * i + 0] = h[i].x;
       aligned[3 * i + 1] = h[i].y;
@@ -791,7 +798,7 @@ int b200_model_create_shot(b200_ctx *ctx, const float *xyz, int n, int stride, c
     if ((rc = m->desc.alloc(ctx, (size_t)std::max(K, 1) * 352)) != B200_OK) break;
     if ((rc = dev_shot(ctx, cloud, normals.p, m->kp.p, K, p->descr_radius, m->desc.p, nullptr, false)) != B200_OK)
       break;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = ctx->sync();
     if (e != cudaSuccess) rc = ctx->fail_cuda(e, "model_create sync", __FILE__, __LINE__);
   } while (0);
   delete cloud;
@@ -823,7 +830,7 @@ int b200_model_download(b200_ctx *ctx, const b200_model *m, float *desc, float *
     B200_LAUNCHED(ctx);
     B200_TRY(download(ctx, kp, tmp.p, (size_t)m->K * 3));
   }
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 
@@ -882,7 +889,7 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
     tr.tick("e2e pipeline issue");
     int nc = 0;
     if ((rc = download(ctx, &nc, dnc.p, 1)) != B200_OK) break;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = ctx->sync();
     if (e != cudaSuccess) {
       rc = ctx->fail_cuda(e, "register_scene sync", __FILE__, __LINE__);
       break;
@@ -1004,7 +1011,7 @@ int b200_library_add_view_descriptors(b200_ctx *ctx, b200_library *lib, const fl
   m->K = K;
   int rc = upload(ctx, m->desc, desc, (size_t)K * 352);
   if (rc == B200_OK) rc = upload_points(ctx, kp, K, kstride, m->kp);
-  if (rc == B200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = B200_ERR_CUDA;
+  if (rc == B200_OK && ctx->sync() != cudaSuccess) rc = B200_ERR_CUDA;
   if (rc != B200_OK) {
     delete m;
     return rc;

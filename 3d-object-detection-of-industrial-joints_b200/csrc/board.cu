@@ -466,14 +466,14 @@ int dev_board_lrf(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const fl
   int n_full = 0;
   B200_CUDA(ctx, cudaMemcpyAsync(hstats, stats.p, sizeof(hstats), cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(ctx, cudaMemcpyAsync(&n_full, total.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   int max_count = (int)hstats[0];
   if (second) {  // the x-axis support may be larger than the plane-fit support
     DevBuf<int> counts2;
     B200_TRY(counts2.alloc(ctx, (size_t)K));
     B200_TRY(dev_radius_count(ctx, *g, d_kp, K, (double)p->tangent_radius, counts2.p, stats.p));
     B200_CUDA(ctx, cudaMemcpyAsync(hstats, stats.p, sizeof(hstats), cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     max_count = std::max(max_count, (int)hstats[0]);
   }
   // two rand() values per keypoint with a full support, in keypoint order (PCL's serial loop)
@@ -517,6 +517,6 @@ int dev_board_lrf(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const fl
     B200_LAUNCHED(ctx);
     rc = B200_OK;
   }
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // hr is a host vector
+  B200_CUDA(ctx, ctx->sync());  // hr is a host vector
   return rc;
 }

@@ -95,6 +95,18 @@ struct b200_ctx {
   int sm_count = 148;
   size_t smem_optin = 0;
   int64_t launches = 0;
+  // Host waits.  Spinning (cudaStreamSynchronize) has the lowest latency; with more lanes than host cores the
+  // contexts are switched to a blocking event wait instead (b200_ctx_set_blocking_sync), which sleeps the thread.
+  bool blocking_sync = false;
+  cudaEvent_t sync_ev = nullptr;
+  cudaError_t sync() {
+    if (!blocking_sync) return cudaStreamSynchronize(stream);
+    cudaError_t e = cudaSuccess;
+    if (!sync_ev) e = cudaEventCreateWithFlags(&sync_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(sync_ev, stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(sync_ev);
+    return e;
+  }
   // small device->host readbacks go through mapped pinned memory written by a kernel, not through the copy engine
   // (see readback_small in api.cu)
   void *mailbox_host = nullptr;

@@ -134,7 +134,7 @@ int b200_desc_index_create(b200_ctx *ctx, const float *desc, int K, int D, b200_
       ctx->launches++;
     }
     e = cudaMemcpyAsync(&ix->n_valid, nv.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = ctx->sync();
     if (e != cudaSuccess) rc = ctx->fail_cuda(e, "desc_index_create sync", __FILE__, __LINE__);
   } while (0);
   if (rc != B200_OK) {
@@ -178,7 +178,7 @@ int b200_desc_index_knn(b200_ctx *ctx, const b200_desc_index *ix, const float *q
   B200_LAUNCHED(ctx);
   B200_CUDA(ctx, cudaMemcpyAsync(idx, didx.p, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(ctx, cudaMemcpyAsync(d2, dd2.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   return B200_OK;
 }
 

@@ -295,14 +295,14 @@ int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
   unsigned long long hs[2], hq[2];
   B200_TRY(dev_radius_count(ctx, *g, g->pts, nv, radius, counts.p, stats.p));
   B200_CUDA(ctx, cudaMemcpyAsync(hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   if (q_is_surface) {
     hq[0] = hs[0];
     hq[1] = hs[1];
   } else {
     B200_TRY(dev_radius_count(ctx, *g, d_q, nq, radius, counts.p, stats.p));
     B200_CUDA(ctx, cudaMemcpyAsync(hq, stats.p, sizeof(hq), cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
   }
   ctx->last_max_nbrs = (int)hq[0];
   ctx->last_mean_nbrs = (double)hq[1] / nq;

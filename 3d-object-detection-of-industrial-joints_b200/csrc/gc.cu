@@ -1481,7 +1481,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   if (debug) {
     long long h[GW * 8];
     B200_CUDA(ctx, cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     for (int w = 0; w < GCL; ++w)
       fprintf(stderr, "gc_group cta %d: window %lld init %lld and %lld list %lld list+greedy %lld cluster-sync %lld commit %lld rounds %lld\n",
               w, h[w * 8], h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6], h[w * 8 + 7]);
@@ -1504,7 +1504,7 @@ int dev_ransac_instances(b200_ctx *ctx, const b200_corr *d_corrs, const float4 *
     mt19937_twisted_state(12345u, host_state);
     B200_CUDA(ctx, cudaMalloc(&ctx->mt_state, sizeof(host_state)));
     B200_CUDA(ctx, cudaMemcpyAsync(ctx->mt_state, host_state, sizeof(host_state), cudaMemcpyHostToDevice, ctx->stream));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
   }
   B200_TRY(shuffled.alloc(ctx, (size_t)C_cap));
   B200_TRY(last_pos.alloc(ctx, (size_t)C_cap));

@@ -207,7 +207,7 @@ int dev_hough3d(b200_ctx *ctx, const float4 *d_model_kp, const float *d_model_rf
   B200_LAUNCHED(ctx);
   unsigned hb[6];
   B200_CUDA(ctx, cudaMemcpyAsync(hb, box.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   if (hb[0] > hb[3]) return B200_OK;  // no finite vote
   HoughSpace H;
   H.bin = bin_size;

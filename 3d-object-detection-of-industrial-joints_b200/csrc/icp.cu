@@ -164,7 +164,7 @@ int dev_icp_align(b200_ctx *ctx, const float4 *d_src, int ns, b200_cloud *target
     int cnt = 0;
     B200_CUDA(ctx, cudaMemcpyAsync(h, sums.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(ctx, cudaMemcpyAsync(&cnt, count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     if (cnt < 3) {  // "Not enough correspondences found. Relax your threshold parameters."
       conv = false;
       break;
@@ -182,7 +182,7 @@ int dev_icp_align(b200_ctx *ctx, const float4 *d_src, int ns, b200_cloud *target
     B200_CUDA(ctx, cudaMemcpyAsync(dT.p, T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     icp_transform_kernel<<<ceil_div(ns, 256), 256, 0, ctx->stream>>>(cur.p, ns, dT.p);
     B200_LAUNCHED(ctx);
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // T is a stack buffer
+    B200_CUDA(ctx, ctx->sync());  // T is a stack buffer
     mat4_mul(T, fin, fin);
     ++it;
     // hasConverged()
@@ -228,10 +228,10 @@ int dev_icp_align(b200_ctx *ctx, const float4 *d_src, int ns, b200_cloud *target
     int cnt = 0;
     B200_CUDA(ctx, cudaMemcpyAsync(h, sums.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(ctx, cudaMemcpyAsync(&cnt, count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
     *fitness = cnt > 0 ? h[15] / cnt : DBL_MAX;
   } else {
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
   }
   return B200_OK;
 }

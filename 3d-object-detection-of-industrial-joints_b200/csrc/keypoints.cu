@@ -155,7 +155,7 @@ int make_lattice(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx,
   B200_LAUNCHED(ctx);
   int h[6];
   B200_CUDA(ctx, cudaMemcpyAsync(h, box.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(ctx, ctx->sync());
   if (h[0] > h[3]) {  // no finite point
     *nleaf = 0;
     return B200_OK;

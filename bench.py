@@ -69,6 +69,7 @@ def config_dict(args, wl, world):
                        "library replicated, NCCL gather of the correspondence lists; %d scenes in flight per GPU "
                        "(lanes)" % (world, args.lanes),
         "lanes_per_gpu": args.lanes,
+        "host_waits": "blocking events" if getattr(args, "blocking", False) else "spinning",
         "l2": "256 MiB buffer written on the step's stream before every step, inside the timed region (lanes pass); "
               "between steps, outside the timed intervals, in the single-lane pass",
     }
@@ -236,11 +237,15 @@ def run_b200(args, rank, world, local_rank):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    if world * L > cores:
-        L = max(2, min(L, cores // world - 1))
+    # more lane threads than cores: the contexts wait on blocking events (the threads sleep) instead of spinning
+    blocking = world * L > cores or args.blocking_sync
     args.lanes = L
+    args.blocking = blocking
     streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
     ctxs = [binding.Context(local_rank, stream=st.cuda_stream) for st in streams]
+    if blocking:
+        for c in ctxs:
+            c.set_blocking_sync(True)
     ctx = ctxs[0]
     with torch.cuda.stream(streams[0]):
         model = ctx.model_create_shot(wl["model"], wl["model_kp"], p)   # resident, replicated library (setup)
@@ -482,6 +487,7 @@ def main():
     ap.add_argument("--model-points", type=int, default=50_000)
     ap.add_argument("--cpu-sample", type=int, default=1500, help="scene keypoints in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocking-sync", action="store_true", help="contexts sleep in host waits instead of spinning")
     ap.add_argument("--lanes", type=int, default=6, help="scenes in flight per GPU (context + stream + host thread each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

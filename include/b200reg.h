@@ -65,6 +65,9 @@ typedef struct {
 /* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
 B200_API int b200_ctx_create(b200_ctx **out, int device, void *stream);
 B200_API int b200_ctx_destroy(b200_ctx *ctx);
+/* Host waits of this context: 0 (default) spin on the stream (lowest latency), 1 sleep on a blocking event — for
+ * deployments with more contexts (lanes) than host cores. */
+B200_API int b200_ctx_set_blocking_sync(b200_ctx *ctx, int enable);
 B200_API int b200_ctx_sync(b200_ctx *ctx);
 B200_API const char *b200_last_error(const b200_ctx *ctx); /* never NULL; ctx may be NULL (global error) */
 B200_API int b200_abi_version(void);
