@@ -940,6 +940,9 @@ int b200_register_scene_batch_shot(int device, const b200_model *model, int n_sc
     if (rc != B200_OK) return rc;
     pool.ctxs.push_back(c);
   }
+  // more lanes than host cores: sleep in the host waits instead of spinning
+  const unsigned hw = std::thread::hardware_concurrency();
+  for (int l = 0; l < lanes; ++l) pool.ctxs[(size_t)l]->blocking_sync = hw != 0 && (unsigned)lanes > hw;
   auto work = [&](int lane) {
     b200_ctx *c = pool.ctxs[(size_t)lane];
     for (int s = lane; s < n_scenes; s += lanes) {
