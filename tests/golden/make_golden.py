@@ -46,6 +46,33 @@ def main():
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_small.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes;", len(c1), "k=1 corrs,", len(c2), "k=2 corrs,", len(T), "instances")
+    make_next(model, scene, kpm, kps, nm, ns, c2, T)
+
+
+def make_next(model, scene, kpm, kps, nm, ns, corrs, gc_T):
+    """Second fixture, same inputs: the SURVEY 8(f) rows (keypoint filters, BOARD frames, Hough grouping, ICP, cloud
+    utilities).  Kept in its own file so that golden_small.npz stays byte-identical."""
+    out = {}
+    us, us_idx = orc.uniform_sampling(scene, 0.03, return_index=True)
+    out.update(us_xyz=us, us_index=us_idx, vg_xyz=orc.voxel_grid(scene, 0.03))
+    bm, used = orc.board_lrf(model, nm, kpm, 0.03)
+    bs, used2 = orc.board_lrf(scene, ns, kps, 0.03, rand_skip=used)
+    out.update(board_model=bm, board_scene=bs, board_rand_used=np.array([used, used2], np.int32))
+    hT, hinst = orc.hough3d_recognize(kpm, bm, kps, bs, corrs, 0.08, 3.0, max_inst=256)
+    out.update(hough_T=hT, hough_sizes=np.array([len(i) for i in hinst], np.int32),
+               hough_corrs=np.concatenate(hinst) if hinst else np.zeros(0, orc.CORR_DTYPE))
+    if len(gc_T):
+        placed = orc.transform_points(model, gc_T[0])
+        r = orc.icp_align(placed[::2], scene, max_iterations=5)
+        out.update(icp_source=placed[::2], icp_T=r["final_transform"], icp_fitness=np.array([r["fitness"]]),
+                   icp_iterations=np.array([r["iterations"], int(r["converged"])], np.int32))
+    c = scene[:500].copy()
+    c[::50] = np.nan
+    kept, idx = orc.remove_nan(c)
+    out.update(nan_cloud=c, nan_kept=kept, nan_index=idx)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_next.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes;", len(hT), "Hough instances,", used + used2, "rand() draws")
 
 
 if __name__ == "__main__":
