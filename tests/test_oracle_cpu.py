@@ -427,3 +427,30 @@ def test_cloud_utilities(orc):
     assert np.abs(out[ok] - ref).max() < 1e-6
     assert np.array_equal(out[~ok], c[~ok], equal_nan=True)
     assert len(orc.remove_nan(np.zeros((0, 3), np.float32))[0]) == 0
+
+
+def test_fpfh_plane_known_answer(orc):
+    """Analytic known answer: on a plane with identical normals every pair has f1 = atan2(0, 1) = 0, f2 = v.n = 0,
+    f3 = n.dp/|dp| = 0, i.e. the middle bin (5 of 0..10) of each of the three 11-bin blocks: every SPFH is
+    [0,0,0,0,0,100,0,0,0,0,0] x 3, and so is every weighted, renormalised FPFH."""
+    gx, gy = np.meshgrid(np.arange(0, 0.4, 0.01), np.arange(0, 0.4, 0.01))
+    cloud = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], 1).astype(np.float32)
+    normals = np.zeros((len(cloud), 4), np.float32)
+    normals[:, 2] = 1.0
+    f = orc.fpfh33(cloud, normals, 0.035)
+    expected = np.zeros(33, np.float32)
+    expected[[5, 16, 27]] = 100.0
+    assert np.abs(f - expected).max() < 1e-3
+
+
+def test_icp_translation_known_answer(orc):
+    """A cloud shifted by less than half the point spacing is registered back exactly in one iteration: every nearest
+    neighbour is the point's own original, so Umeyama returns the pure translation."""
+    rng = np.random.Generator(np.random.PCG64(8))
+    tgt = rng.uniform(-1, 1, (400, 3)).astype(np.float32)
+    from scipy.spatial import cKDTree
+    dmin = cKDTree(tgt).query(tgt, k=2)[0][:, 1].min()
+    shift = np.array([0.2, -0.1, 0.15], np.float32) * np.float32(dmin)
+    r = orc.icp_align(tgt + shift, tgt, max_iterations=3)
+    assert np.abs(r["final_transform"][:3, :3] - np.eye(3)).max() < 1e-5
+    assert np.abs(r["final_transform"][:3, 3] + shift).max() < 1e-6 and r["fitness"] < 1e-10
