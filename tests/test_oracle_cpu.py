@@ -454,3 +454,54 @@ def test_icp_translation_known_answer(orc):
     r = orc.icp_align(tgt + shift, tgt, max_iterations=3)
     assert np.abs(r["final_transform"][:3, :3] - np.eye(3)).max() < 1e-5
     assert np.abs(r["final_transform"][:3, 3] + shift).max() < 1e-6 and r["fitness"] < 1e-10
+
+
+def test_icp_against_numpy_restatement(orc, synth):
+    """Independent cross-check of the ICP loop: scipy cKDTree nearest neighbours + numpy SVD Umeyama (float64),
+    same convergence rules; transforms agree to float32 rounding, iteration counts are equal."""
+    from scipy.spatial import cKDTree
+    from scipy.spatial.transform import Rotation
+    model = synth.make_model("y", 2500, seed=4)
+    R0 = Rotation.from_rotvec([0.015, 0.02, -0.01]).as_matrix()
+    src = (model.astype(np.float64) @ R0.T + [0.002, -0.003, 0.001]).astype(np.float32)[::2]
+    tree = cKDTree(model.astype(np.float64))
+
+    def umeyama(a, b):
+        ma, mb = a.mean(0), b.mean(0)
+        S = (b - mb).T @ (a - ma) / len(a)
+        U, _, Vt = np.linalg.svd(S)
+        D = np.eye(3)
+        if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+            D[2, 2] = -1
+        Rm = U @ D @ Vt
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = Rm, mb - Rm @ ma
+        return T
+
+    for iters in (1, 4, 50):
+        cur = src.copy()
+        fin = np.eye(4, dtype=np.float32)
+        prev, it, conv = np.finfo(np.float64).max, 0, False
+        while True:
+            # float32 L2_Simple distances like FLANN; the tree only proposes the neighbour
+            nn = tree.query(cur.astype(np.float64))[1]
+            d2 = ((cur - model[nn]) ** 2).astype(np.float32)
+            d2 = (d2[:, 0] + d2[:, 1]) + d2[:, 2]
+            T = umeyama(cur.astype(np.float64), model[nn].astype(np.float64)).astype(np.float32)
+            cur = (cur @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+            fin = (T @ fin).astype(np.float32)
+            it += 1
+            if it >= iters:
+                conv = True
+                break
+            if 0.5 * (np.trace(T[:3, :3].astype(np.float64)) - 1.0) >= 1.0 and float((T[:3, 3].astype(np.float64) ** 2).sum()) <= 0.0:
+                conv = True
+                break
+            mse = float(d2.astype(np.float64).mean())
+            if abs(mse - prev) < 1e-12:
+                conv = True
+                break
+            prev = mse
+        r = orc.icp_align(src, model, max_iterations=iters)
+        assert r["iterations"] == it and r["converged"] == conv
+        assert np.abs(r["final_transform"] - fin).max() < 2e-5
