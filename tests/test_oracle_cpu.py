@@ -505,3 +505,48 @@ def test_icp_against_numpy_restatement(orc, synth):
         r = orc.icp_align(src, model, max_iterations=iters)
         assert r["iterations"] == it and r["converged"] == conv
         assert np.abs(r["final_transform"] - fin).max() < 2e-5
+
+
+def test_board_against_numpy_restatement(orc, synth):
+    """Independent cross-check of BOARD without the hole search (no random axis involved): z = eigenvector of the
+    smallest eigenvalue of the support's scatter matrix (numpy eigh), signed by the mean support normal; x = unit
+    projection on the tangent plane of the direction to the support point whose normal deviates most from z (first
+    one in (distance, index) order on ties); y = z x x."""
+    from scipy.spatial import cKDTree
+    cloud = synth.make_model("y", 6000, seed=9)
+    normals = orc.normals(cloud, k=12)
+    kp = cloud[::150]
+    r = 0.025
+    rf, used = orc.board_lrf(cloud, normals, kp, r, orc.board_params(find_holes=False))
+    assert used == 0
+    tree = cKDTree(cloud.astype(np.float64))
+    ok_rows = 0
+    for i, c in enumerate(kp):
+        idx = np.array(tree.query_ball_point(c.astype(np.float64), r * 1.0001))
+        d2 = ((cloud[idx] - c) ** 2).astype(np.float32)
+        d2 = (d2[:, 0] + d2[:, 1]) + d2[:, 2]
+        keep = d2 < np.float32(r * r)
+        idx, d2 = idx[keep], d2[keep]
+        order = np.lexsort((idx, d2))
+        idx, d2 = idx[order], d2[order]
+        if len(idx) < 6:
+            assert np.isnan(rf[i]).all()
+            continue
+        P = cloud[idx].astype(np.float64)
+        w, V = np.linalg.eigh(np.cov((P - P.mean(0)).T, bias=True))
+        z = V[:, 0]
+        nm = normals[idx, :3].astype(np.float64)
+        nm = nm[np.isfinite(nm).all(1)].sum(0)
+        if z @ nm < 0:
+            z = -z
+        cosines = normals[idx, :3].astype(np.float64) @ z
+        ring = d2 > 0                       # tangent_radius 0: every support point with d2 > 0 is a margin point
+        cand = np.where(ring)[0] if ring.any() else np.arange(len(idx))
+        j = cand[np.argmin(cosines[cand])]  # argmin returns the first minimum: (distance, index) order
+        v = cloud[idx[j]].astype(np.float64) - c
+        x = v - (v @ z) * z
+        x /= np.linalg.norm(x)
+        ref = np.concatenate([x, np.cross(z, x), z])
+        if np.abs(rf[i] - ref).max() < 2e-5:
+            ok_rows += 1
+    assert ok_rows >= 0.97 * len(kp)       # the rest: float32 cosine ties / near-degenerate scatter matrices
