@@ -36,6 +36,9 @@ def test_apps_build_and_need_a_gpu(apps, synth, tmp_path):
                        capture_output=True, text=True, timeout=120)
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr
+    r = subprocess.run([apps["batch_recognition"], str(tmp_path / "m.f32"), str(tmp_path / "mk.f32"), str(tmp_path / "b"),
+                        "2", str(tmp_path / "s.f32"), str(tmp_path / "sk.f32")], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
 def _read_instances(prefix):
