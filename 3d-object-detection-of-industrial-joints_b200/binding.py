@@ -26,7 +26,7 @@ EXPORTS = [
     "b200_model_create_shot", "b200_model_destroy", "b200_model_size", "b200_model_download",
     "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
     "b200_ctx_set_blocking_sync", "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
-    "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio",
+    "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio", "b200_last_match_pass1_rows",
     "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
@@ -123,6 +123,7 @@ def lib():
             "b200_ctx_stage_count": [],
             "b200_ctx_stage_time": [vp, i, C.POINTER(d), ip],
             "b200_last_match_fallback": [vp, ip],
+            "b200_last_match_pass1_rows": [vp, ip],
             "b200_last_match_error_ratio": [vp, fp],
             "b200_desc_index_create": [vp, fp, i, i, C.POINTER(vp)],
             "b200_desc_index_destroy": [vp],
@@ -448,6 +449,11 @@ class Context:
     def match_fallback_rows(self):
         n = C.c_int()
         self._chk(lib().b200_last_match_fallback(self.h, C.byref(n)))
+        return n.value
+
+    def match_pass1_rows(self):
+        n = C.c_int()
+        self._chk(lib().b200_last_match_pass1_rows(self.h, C.byref(n)))
         return n.value
 
     def match_error_ratio(self):

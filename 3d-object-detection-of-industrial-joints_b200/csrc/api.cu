@@ -136,7 +136,8 @@ int scene_pipeline(b200_ctx *ctx, const b200_model *model, b200_cloud *scene, co
     d_desc = desc_tmp.p;
   }
   B200_TRY(dev_shot(ctx, scene, normals.p, d_kp, Ks, p->descr_radius, d_desc, nullptr, false));
-  B200_TRY(dev_match(ctx, model->desc.p, model->K, d_desc, Ks, 352, p->match_mode, p->match_thr, d_corrs, d_n_corrs));
+  B200_TRY(dev_match(ctx, model->desc.p, model->K, d_desc, Ks, 352, p->match_mode, p->match_thr, d_corrs, d_n_corrs,
+                     &model->tc));
   B200_TRY(dev_gc(ctx, model->kp.p, d_kp, d_corrs, d_n_corrs, Ks, p->gc_size, p->gc_threshold, d_T, p->max_instances,
                   d_inst_offsets, d_inst_counts, d_inst_corrs, corr_cap, d_n_inst));
   return B200_OK;
@@ -327,6 +328,13 @@ int b200_last_match_fallback(b200_ctx *ctx, int *rows) {
   API_ENTER(ctx);
   B200_CUDA(ctx, ctx->sync());
   if (rows) *rows = ctx->last_match_fallback;
+  return B200_OK;
+}
+
+int b200_last_match_pass1_rows(b200_ctx *ctx, int *rows) {
+  API_ENTER(ctx);
+  B200_CUDA(ctx, ctx->sync());
+  if (rows) *rows = ctx->last_match_pass1_fail;
   return B200_OK;
 }
 
@@ -798,6 +806,7 @@ int b200_model_create_shot(b200_ctx *ctx, const float *xyz, int n, int stride, c
     if ((rc = m->desc.alloc(ctx, (size_t)std::max(K, 1) * 352)) != B200_OK) break;
     if ((rc = dev_shot(ctx, cloud, normals.p, m->kp.p, K, p->descr_radius, m->desc.p, nullptr, false)) != B200_OK)
       break;
+    if ((rc = match_prepare_model(ctx, m)) != B200_OK) break;
     cudaError_t e = ctx->sync();
     if (e != cudaSuccess) rc = ctx->fail_cuda(e, "model_create sync", __FILE__, __LINE__);
   } while (0);
@@ -1014,6 +1023,7 @@ int b200_library_add_view_descriptors(b200_ctx *ctx, b200_library *lib, const fl
   m->K = K;
   int rc = upload(ctx, m->desc, desc, (size_t)K * 352);
   if (rc == B200_OK) rc = upload_points(ctx, kp, K, kstride, m->kp);
+  if (rc == B200_OK) rc = match_prepare_model(ctx, m);
   if (rc == B200_OK && ctx->sync() != cudaSuccess) rc = B200_ERR_CUDA;
   if (rc != B200_OK) {
     delete m;
@@ -1182,7 +1192,9 @@ int b200_register_scene_library(b200_ctx *ctx, const b200_library *lib, const fl
     bool overflow = false;
     for (int v = 0; v < (int)lib->views.size() && rc == B200_OK; ++v) {
       const b200_model *m = lib->views[v];
-      if ((rc = dev_match(ctx, m->desc.p, m->K, desc.p, Ks, 352, p->match_mode, p->match_thr, dcorrs.p, dnc.p)) != B200_OK) break;
+      if ((rc = dev_match(ctx, m->desc.p, m->K, desc.p, Ks, 352, p->match_mode, p->match_thr, dcorrs.p, dnc.p, &m->tc)) !=
+          B200_OK)
+        break;
       if ((rc = dev_gc(ctx, m->kp.p, dkp.p, dcorrs.p, dnc.p, Ks, p->gc_size, p->gc_threshold, dT.p, mi, doffs.p, dcnts.p,
                        dic.p, cap, dn.p)) != B200_OK)
         break;

@@ -117,6 +117,7 @@ struct b200_ctx {
   int last_max_nbrs = 0;
   float last_match_err_ratio = 0.f;  // max observed approximation error / assumed bound (profiling only)
   int last_match_fallback = -1;  // rows the tensor-core filter could not certify (valid after a sync)
+  int last_match_pass1_fail = -1;  // rows the one-term pass left to the three-term pass (profiling only)
   std::string err;
   void *pinned = nullptr;  // small pinned staging block for tiny readbacks
   unsigned *mt_state = nullptr;  // mt19937 state after seeding with 12345 and the first twist (gc.cu)
@@ -295,12 +296,26 @@ struct b200_cloud {
   DeviceGrid radius_grid;  // cell sized for fixed-radius queries
 };
 
+// Model side of the tensor-core correspondence filter (match_tc.cu), prepared once per resident model: the fp16
+// split operands, |b|^2, the power-of-two scale and the row-validity flags do not change between scenes.
+struct TcModelPrep {
+  bool ready = false;
+  int Km = 0, D = 0, rowsB = 0;
+  DevBuf<unsigned short> B1, B3;  // fp16 bits: one-term [b1] and three-term [b1|b2|b1] rows, zero padded
+  DevBuf<float> nb;               // |b_j|^2 (+inf for padding / invalid rows)
+  DevBuf<float> scaleB;           // [0] = 2^s, [1] = max |b|
+  DevBuf<unsigned> bits;          // [0] = bits of max |b|, [1] = bits of max |b|^2
+  DevBuf<unsigned char> mvalid;   // row has only finite values
+  DevBuf<int> nmv;                // number of valid rows
+};
+
 struct b200_model {
   b200_ctx *ctx = nullptr;
   int K = 0;
   int D = 352;
   DevBuf<float> desc;  // K x D
   DevBuf<float4> kp;   // K keypoints
+  TcModelPrep tc;      // filled by match_prepare_model for libraries large enough for the tensor-core path
 };
 
 struct b200_library {
@@ -414,7 +429,8 @@ int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
              double radius, float *d_out);
 // match.cu
 int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
-              b200_corr *d_out, int *d_count);
+              b200_corr *d_out, int *d_count, const TcModelPrep *prep = nullptr);
+int match_prepare_model(b200_ctx *ctx, b200_model *m);  // no-op for small libraries
 int dev_ransac_instances(b200_ctx *ctx, const b200_corr *d_corrs, const float4 *d_mp, const float4 *d_sp,
                          const int *d_members, const int *d_inst_offsets, const int *d_n_inst, int C_cap,
                          double threshold, float *d_T, int max_inst, int *d_inst_counts, b200_corr *d_inst_corrs,

@@ -202,28 +202,49 @@ __global__ void match_emit_kernel(const unsigned long long *__restrict__ best, c
 
 }  // namespace
 
-int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid, const float *d_scene,
-                    int Ks, const unsigned char *svalid, int D, int terms, unsigned long long *best, int *zero_cnt,
-                    int *fb_rows, int *fb_count);
+int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid, const TcModelPrep *prep,
+                    const float *d_scene, int Ks, const unsigned char *svalid, int D, int plan,
+                    unsigned long long *best, int *zero_cnt, int *fb_rows, int *fb_count);
+int match_tc_prepare_model(b200_ctx *ctx, const float *d_model, int Km, int D, const unsigned char *mvalid,
+                           TcModelPrep *out);
 
-// 0: exact float32 kernel only; 1 / 3: tcgen05 pre-filter with 1 / 3 fp16 terms + exact rescoring.
-// B200_MATCH=exact|tc1|tc3 overrides the size heuristic (testing aid).
+// Smallest library / all-pairs volume for which the tensor-core filter pays off.
+static bool tc_worthwhile(int Km, double Ks, int D) {
+  return D >= 16 && D <= 1024 && Km >= 1024 && (double)Km * Ks * D >= 2.0e10;
+}
+
+// 0: exact float32 kernel only; 1 / 3: tcgen05 pre-filter with 1 / 3 fp16 terms + exact rescoring; 13: one term for
+// every row, three terms for the rows the first pass cannot certify (a few per cent), then the exact kernel for
+// what is left (a few rows).  B200_MATCH=exact|tc1|tc3|tc13 overrides the size heuristic (testing aid).
 static int match_mode_for(int Km, int Ks, int D) {
   const char *e = getenv("B200_MATCH");
   if (e) {
     if (!strcmp(e, "exact")) return 0;
-    if (!strcmp(e, "tc1")) return 1;
-    if (!strcmp(e, "tc3")) return 3;
+    if (D >= 16 && D <= 1024) {
+      if (!strcmp(e, "tc1")) return 1;
+      if (!strcmp(e, "tc3")) return 3;
+      if (!strcmp(e, "tc13")) return 13;
+    }
   }
-  if (D > 2048 || D < 16) return 0;
-  // the filter pays off once the all-pairs work is large.  The three-term split certifies every row of
-  // real SHOT data; one term leaves ~0.3 % to the exact kernel and the filter's run time is set by its
-  // epilogue, not by the contraction length (measured: 2.6 ms either way), so three terms it is.
-  return ((double)Km * (double)Ks * D >= 2.0e10 && Km >= 1024) ? 3 : 0;
+  return tc_worthwhile(Km, (double)Ks, D) ? 13 : 0;
+}
+
+// Keeps the model side of the filter resident with the model (b200_model_create_shot, b200_library_*): validity
+// flags, fp16 split operands, norms and scale are computed once instead of once per scene.
+int match_prepare_model(b200_ctx *ctx, b200_model *m) {
+  if (!m || m->K < 1024 || getenv("B200_MATCH_NOCACHE")) return B200_OK;
+  TcModelPrep &t = m->tc;
+  B200_TRY(t.mvalid.alloc(ctx, (size_t)m->K));
+  B200_TRY(t.nmv.alloc(ctx, 1));
+  B200_TRY(t.nmv.zero());
+  row_valid_kernel<<<ceil_div((long long)m->K * 32, 256), 256, 0, ctx->stream>>>(m->desc.p, m->K, m->D, 1, t.mvalid.p,
+                                                                                t.nmv.p);
+  B200_LAUNCHED(ctx);
+  return match_tc_prepare_model(ctx, m->desc.p, m->K, m->D, t.mvalid.p, &t);
 }
 
 int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
-              b200_corr *d_out, int *d_count) {
+              b200_corr *d_out, int *d_count, const TcModelPrep *prep) {
   if (mode != 1 && mode != 2) return ctx->fail(B200_ERR_INVALID, "match: mode must be 1 or 2");
   if (D <= 0 || Km < 0 || Ks < 0) return ctx->fail(B200_ERR_INVALID, "match: bad sizes");
   B200_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
@@ -240,7 +261,10 @@ int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene,
   B200_TRY(flags.alloc(ctx, (size_t)Ks));
   B200_TRY(slots.alloc(ctx, (size_t)Ks));
   B200_TRY(best.alloc(ctx, (size_t)Ks));
-  if (Km > 0) {
+  if (prep && (!prep->ready || prep->Km != Km || prep->D != D)) prep = nullptr;
+  const unsigned char *mvalid_p = prep ? prep->mvalid.p : mvalid.p;
+  const int *nmv_p = prep ? prep->nmv.p : nmv.p;
+  if (Km > 0 && !prep) {
     row_valid_kernel<<<ceil_div((long long)Km * 32, 256), 256, 0, ctx->stream>>>(d_model, Km, D, 1, mvalid.p, nmv.p);
     B200_LAUNCHED(ctx);
   }
@@ -260,22 +284,22 @@ int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene,
       DevBuf<int> fb_rows, fb_count;
       B200_TRY(fb_rows.alloc(ctx, (size_t)Ks));
       B200_TRY(fb_count.alloc(ctx, 1));
-      B200_TRY(match_tc_filter(ctx, d_model, Km, mvalid.p, d_scene, Ks, svalid.p, D, tc_terms, best.p, zero_cnt.p,
-                               fb_rows.p, fb_count.p));
+      B200_TRY(match_tc_filter(ctx, d_model, Km, mvalid_p, prep, d_scene, Ks, svalid.p, D, tc_terms, best.p,
+                               zero_cnt.p, fb_rows.p, fb_count.p));
       if (ctx->profiling) {  // bench statistic: how many rows needed the exact kernel
         B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_fallback, fb_count.p, sizeof(int), cudaMemcpyDeviceToHost,
                                        ctx->stream));
       }
       // uncertified rows: exact evaluation by persistent CTAs over (row block, model tile) items
-      match_rows_kernel<<<ctx->sm_count * 4, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, D, fb_rows.p,
+      match_rows_kernel<<<ctx->sm_count * 4, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid_p, d_scene, D, fb_rows.p,
                                                                         fb_count.p, best.p, zero_cnt.p);
       B200_LAUNCHED(ctx);
     } else {
-      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid.p, d_scene, Ks, D, best.p, zero_cnt.p);
+      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid_p, d_scene, Ks, D, best.p, zero_cnt.p);
       B200_LAUNCHED(ctx);
     }
   }
-  match_flags_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, svalid.p, nmv.p, Ks, mode, thr,
+  match_flags_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, svalid.p, nmv_p, Ks, mode, thr,
                                                                  flags.p);
   B200_LAUNCHED(ctx);
   B200_TRY(exclusive_scan_i32(ctx, flags.p, slots.p, Ks, d_count));

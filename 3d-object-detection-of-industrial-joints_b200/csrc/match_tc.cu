@@ -146,26 +146,38 @@ __global__ void absmax_kernel(const float *__restrict__ x, size_t n, unsigned *_
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
 }
 
-// scale[0] = 2^-e such that absmax * scale <= 1; scale[1] = absmax
+// scale[0] = 2^(TC_SCALE_EXP - e): absmax * scale lies in [2^(TC_SCALE_EXP-1), 2^TC_SCALE_EXP); scale[1] = absmax.
+// The operands sit high in the fp16 range so that the second split term x2 = rn16(x - x1) (about 2^-11 |x|) is a
+// normal fp16 number for every element within 2^-13 of the largest one; products and the K'-term fp32 sums stay
+// far below the fp32 range (2^22 * K').
+constexpr int TC_SCALE_EXP = 11;
 __global__ void make_scale_kernel(const unsigned *__restrict__ absmax_bits, float *__restrict__ scale) {
   const float m = __uint_as_float(*absmax_bits);
   int e = 0;
   if (m > 0.f) frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
-  scale[0] = ldexpf(1.0f, -e);
+  scale[0] = ldexpf(1.0f, TC_SCALE_EXP - e);
   scale[1] = m;
 }
 
 // One warp per row.  is_b = 0: row = [x1 | x1 | x2], is_b = 1: row = [x1 | x2 | x1] (terms == 3);
 // terms == 1: row = [x1].  Rows are zero padded to Kp halves.  norm2[row] = float32 sum of squares of
 // the ORIGINAL values (+inf for rows that are not valid).
+// row_map / n_rows_dev (both or neither): output row w is input row row_map[w], for w < *n_rows_dev only (the rows a
+// first pass could not certify; their number is known on the device only — rows beyond it are left untouched).
 __global__ void tc_prep_kernel(const float *__restrict__ X, int rows, int rows_padded, int D, int Kp, int terms,
                                int is_b, const float *__restrict__ scale, const unsigned char *__restrict__ valid,
-                               __half *__restrict__ out, float *__restrict__ norm2, unsigned *__restrict__ normmax_bits) {
+                               __half *__restrict__ out, float *__restrict__ norm2, unsigned *__restrict__ normmax_bits,
+                               const int *__restrict__ row_map, const int *__restrict__ n_rows_dev) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= rows_padded) return;
+  int src = w;
+  if (row_map) {
+    if (w >= *n_rows_dev) return;
+    src = row_map[w];
+  }
   __half *o = out + (size_t)w * Kp;
-  const bool ok = (w < rows) && (valid == nullptr || valid[w]);
+  const bool ok = (w < rows) && (valid == nullptr || valid[src]);
   if (!ok) {
     for (int d = lane; d < Kp; d += 32) o[d] = __float2half_rn(0.f);
     if (lane == 0) norm2[w] = __int_as_float(0x7f800000);
@@ -174,7 +186,7 @@ __global__ void tc_prep_kernel(const float *__restrict__ X, int rows, int rows_p
   const float sc = scale[0];
   float n2 = 0.f;
   for (int d = lane; d < D; d += 32) {
-    const float x = X[(size_t)w * D + d];
+    const float x = X[(size_t)src * D + d];
     n2 += x * x;
     const float xs = x * sc;
     const __half h1 = __float2half_rn(xs);
@@ -206,6 +218,7 @@ struct TcParams {
   const float *scaleB;
   float *cand_s;       // [Ks][n_split * TC_CAND]
   int *cand_j;
+  const int *rows_dev;  // nullable: the number of scene rows lives on the device (second pass), Ks is the capacity
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -251,7 +264,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_items = p.m_tiles * p.n_split;
+  const int Ks_eff = p.rows_dev ? min(*p.rows_dev, p.Ks) : p.Ks;
+  const int n_items = ((Ks_eff + TC_BM - 1) / TC_BM) * p.n_split;
   const int tiles_per_split = (p.n_tiles + p.n_split - 1) / p.n_split;
 
   if (warp == 0) {
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory");  // the hand-over buffer is free again
       const int row = mt * TC_BM + row_in_tile;
-      if (half == 0 && row < p.Ks) {
+      if (half == 0 && row < Ks_eff) {
         float *os = p.cand_s + ((size_t)row * p.n_split + sp) * TC_CAND;
         int *oj = p.cand_j + ((size_t)row * p.n_split + sp) * TC_CAND;
 #pragma unroll
@@ -463,21 +477,31 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
                       const float *__restrict__ normmaxB, const float *__restrict__ scaleA,
                       const float *__restrict__ scaleB, float eta, unsigned long long *__restrict__ best,
                       int *__restrict__ zero_cnt, int *__restrict__ fb_rows, int *__restrict__ fb_count,
-                      unsigned *__restrict__ err_ratio_bits) {
+                      unsigned *__restrict__ err_ratio_bits, const int *__restrict__ row_map,
+                      const int *__restrict__ n_rows_dev) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RescoreSmem &sm = reinterpret_cast<RescoreSmem *>(rs_raw)[warp];
-  const int nc = n_split * TC_CAND;  // 8, 16 or 32
+  const int nc = n_split * TC_CAND;  // 4, 8 or 16
   const int rpw = 32 / nc;           // rows per warp
   const int gw = blockIdx.x * RS_WARPS_PER_CTA + warp;
   const int r = lane / nc, c = lane % nc;  // this lane's (row, candidate)
-  const int i = gw * rpw + r;
-  const bool row_ok = i < Ks && svalid[i];  // rows skipped by the caller's flags (pcl_isfinite(descriptor[0]))
+  // ci: row of the filter's operand / candidate arrays; i: the scene row it stands for
+  const int n_rows = row_map ? min(*n_rows_dev, Ks) : Ks;
+  if (gw * rpw >= n_rows) return;
+  const int ci = gw * rpw + r;
+  const int i = (ci < n_rows) ? (row_map ? row_map[ci] : ci) : -1;
+  const bool row_ok = i >= 0 && svalid[i];  // rows skipped by the caller's flags (pcl_isfinite(descriptor[0]))
+  // float32 error of a D-term sequential sum / a warp-tree norm, relative to the sum of magnitudes
+  const float c_sum = (float)(D + 8) * 1.1920929e-7f;
+  // fp16 flush of tiny elements: absolute 2^-25 per element of the scaled operand (2^-(25+10) of the largest
+  // element), against a vector of at most sqrt(D) |b| in the 1-norm; both operands, times two for -2 a.b
+  const float c_sub = 1.2e-10f * sqrtf((float)D);
   int j = -1;
   float s = __int_as_float(0x7f800000);
   if (row_ok) {
-    j = cand_j[(size_t)i * nc + c];
-    s = cand_s[(size_t)i * nc + c];
+    j = cand_j[(size_t)ci * nc + c];
+    s = cand_s[(size_t)ci * nc + c];
   }
   bool pair_ok = row_ok && j >= 0 && j < Km;
   // s_cut: every model row that is not a candidate has approximate s >= the worst kept value of its split
@@ -492,10 +516,10 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
     float s_min = pair_ok ? s : __int_as_float(0x7f800000);
     for (int o = nc >> 1; o > 0; o >>= 1) s_min = fminf(s_min, __shfl_xor_sync(0xffffffffu, s_min, o));
     if (pair_ok) {
-      const float nai = na[i], nbm = normmaxB[0];
+      const float nai = na[ci], nbm = normmaxB[0];
       const float d_lo = fmaxf(nai + s_min, 0.0f);
-      const float e = 2.0f * eta * sqrtf(nai * nbm) + 4e-5f * (nai + nbm + d_lo + 4.0f * eta * sqrtf(nai * nbm)) +
-                      4e-6f * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+      const float e = 2.0f * eta * sqrtf(nai * nbm) + c_sum * (nai + nbm + d_lo + 4.0f * eta * sqrtf(nai * nbm)) +
+                      c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
       pair_ok = s <= s_min + 2.0f * e;
     }
   }
@@ -505,8 +529,8 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
     const int w = min(RS_CHUNK, D - d0);
     // stage: scene rows, then the surviving candidate rows (two coalesced 128-byte loads per row)
     for (int rr = 0; rr < rpw; ++rr) {
-      const int ii = gw * rpw + rr;
-      for (int dd = lane; dd < w; dd += 32) sm.a[rr][dd] = (ii < Ks) ? scene[(size_t)ii * D + d0 + dd] : 0.0f;
+      const int ii = __shfl_sync(0xffffffffu, i, rr * nc);
+      for (int dd = lane; dd < w; dd += 32) sm.a[rr][dd] = (ii >= 0) ? scene[(size_t)ii * D + d0 + dd] : 0.0f;
     }
     for (int l = 0; l < 32; ++l) {
       const int jl = __shfl_sync(0xffffffffu, pair_ok ? j : -1, l);
@@ -531,9 +555,9 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
     if (err_ratio_bits) {
       // observed |approximate - exact| distance of this candidate, relative to the bound the certificate
       // assumes (statistic for the tests: must stay well below 1)
-      const float nai = na[i], nbm = normmaxB[0];
-      const float eps = 2.0f * eta * sqrtf(nai * nbm) + 4e-5f * (nai + nbm + acc) +
-                        4e-6f * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+      const float nai = na[ci], nbm = normmaxB[0];
+      const float eps = 2.0f * eta * sqrtf(nai * nbm) + c_sum * (nai + nbm + acc) +
+                        c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
       const float ratio = fabsf((nai + s) - acc) / eps;
       if (ratio == ratio) atomicMax(err_ratio_bits, __float_as_uint(ratio));
     }
@@ -550,12 +574,12 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
       if (!(s_cut < __int_as_float(0x7f800000))) {
         certified = true;  // every valid model row was a candidate
       } else {
-        const float nai = na[i];
+        const float nai = na[ci];
         const float nbm = normmaxB[0];
-        // |s_approx - s_real| <= 2*eta*|a||b| ; float32 sequential sums and norms: 4e-5 relative
-        // fp16 subnormal flush of the split terms: absolute 2^-24 per element in scaled units
-        const float eps = 2.0f * eta * sqrtf(nai * nbm) + 4e-5f * (nai + nbm + best_d2) +
-                          4e-6f * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+        // |s_approx - s_real| <= 2*eta*|a||b| (tc_eta); float32 sequential sums and norms: (D + 8) 2^-23 relative;
+        // fp16 flush of tiny elements: c_sub
+        const float eps = 2.0f * eta * sqrtf(nai * nbm) + c_sum * (nai + nbm + best_d2) +
+                          c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
         certified = best_d2 < (nai + s_cut) - eps;
       }
     }
@@ -600,52 +624,82 @@ int make_map(b200_ctx *ctx, CUtensorMap *map, const __half *base, int rows, int 
 
 }  // namespace
 
-// terms: 1 or 3.  On return best[] / zero_cnt[] hold the certified rows; fb_rows[0..*fb_count) lists the
-// rows that need the exact kernel.
-int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid, const float *d_scene,
-                    int Ks, const unsigned char *svalid, int D, int terms, unsigned long long *best, int *zero_cnt,
-                    int *fb_rows, int *fb_count) {
-  const int Kp = ((terms * D + TC_BK - 1) / TC_BK) * TC_BK;
-  const int m_tiles = ceil_div(Ks, TC_BM), n_tiles = ceil_div(Km, TC_BN);
-  const int rowsA = m_tiles * TC_BM, rowsB = n_tiles * TC_BN;
+// Error bound of the approximate inner product, relative to |a||b| (derivation):
+//   operands: fp16 round-to-nearest keeps 11 significant bits, |x^ - x| <= 2^-11 |x| for elements that stay normal
+//   (tiny ones are covered by c_sub in the rescoring kernel).  One term: |a^.b^ - a.b| <= (2^-10 + 2^-22) sum|a_k b_k|.
+//   Three terms: x = x1 + x2 + r with |x2| <= 2^-11 |x|, |r| <= 2^-22 |x|; the contraction a1.b1 + a1.b2 + a2.b1
+//   drops a2.b2 and the r terms: <= (3 * 2^-22 + 2^-32) sum|a_k b_k|.  Cauchy-Schwarz: sum|a_k b_k| <= |a||b|.
+//   accumulation: the products of two fp16 numbers are exact in fp32; the tensor core adds the K' products of a
+//   row in fp32 with an unspecified order and possibly truncation.  Model: every one of the K' additions loses at
+//   most 2^-23 of the running magnitude, itself <= sum|a^_k b^_k| <= 1.001 |a||b|; a factor 2 of safety on top:
+//   K' * 2^-22.  (Observed errors are about sqrt(K') * 2^-24: tests/test_gpu_match_tc.py checks the observed /
+//   assumed ratio and cross-checks every row against the exact kernel.)
+static float tc_eta(int terms, int Kp) {
+  const float operand = (terms == 3) ? (3.0f * 2.3841858e-7f + 2.4e-10f) : (9.765625e-4f + 2.3841858e-7f);
+  return 1.001f * (operand + (float)Kp * 2.3841858e-7f);
+}
+
+static int tc_kp(int terms, int D) { return ((terms * D + TC_BK - 1) / TC_BK) * TC_BK; }
+
+// Model-side operands, both splits.  mvalid: per-row validity flags (device).
+int match_tc_prepare_model(b200_ctx *ctx, const float *d_model, int Km, int D, const unsigned char *mvalid,
+                           TcModelPrep *out) {
+  const int n_tiles = ceil_div(Km, TC_BN), rowsB = n_tiles * TC_BN;
+  out->ready = false;
+  out->Km = Km;
+  out->D = D;
+  out->rowsB = rowsB;
+  B200_TRY(out->B1.alloc(ctx, (size_t)rowsB * tc_kp(1, D)));
+  B200_TRY(out->B3.alloc(ctx, (size_t)rowsB * tc_kp(3, D)));
+  B200_TRY(out->nb.alloc(ctx, (size_t)rowsB));
+  B200_TRY(out->scaleB.alloc(ctx, 2));
+  B200_TRY(out->bits.alloc(ctx, 2));
+  B200_TRY(out->bits.zero());
+  const int rb = std::min(ctx->sm_count * 8, 4096);
+  absmax_kernel<<<rb, 256, 0, ctx->stream>>>(d_model, (size_t)Km * D, out->bits.p + 0);
+  B200_LAUNCHED(ctx);
+  make_scale_kernel<<<1, 1, 0, ctx->stream>>>(out->bits.p + 0, out->scaleB.p);
+  B200_LAUNCHED(ctx);
+  for (int terms = 1; terms <= 3; terms += 2) {
+    tc_prep_kernel<<<ceil_div((long long)rowsB * 32, 256), 256, 0, ctx->stream>>>(
+        d_model, Km, rowsB, D, tc_kp(terms, D), terms, 1, out->scaleB.p, mvalid,
+        reinterpret_cast<__half *>(terms == 1 ? out->B1.p : out->B3.p), out->nb.p, out->bits.p + 1, nullptr, nullptr);
+    B200_LAUNCHED(ctx);
+  }
+  out->ready = true;
+  return B200_OK;
+}
+
+namespace {
+
+// One filter + rescoring pass.  row_map / rows_dev: nullable (first pass: all Ks rows in order).  Rows it cannot
+// certify are appended to fb_rows / fb_count.
+int tc_pass(b200_ctx *ctx, const float *d_model, int Km, const TcModelPrep &B, const float *d_scene, int Ks,
+            const unsigned char *svalid, int D, int terms, const float *scA, const int *row_map, const int *rows_dev,
+            unsigned long long *best, int *zero_cnt, int *fb_rows, int *fb_count, unsigned *err_bits) {
+  const int Kp = tc_kp(terms, D);
+  const int m_tiles = ceil_div(Ks, TC_BM), n_tiles = B.rowsB / TC_BN;
+  const int rowsA = m_tiles * TC_BM;
   int n_split = 1;
-  while (n_split < TC_MAX_SPLIT && m_tiles * n_split < ctx->sm_count && n_split * 2 <= n_tiles) n_split *= 2;
-  DevBuf<__half> A16, B16;
-  DevBuf<float> na, nb, scA, scB, cand_s, nbmax;
-  DevBuf<unsigned> bits;
+  if (rows_dev) {
+    n_split = std::min(TC_MAX_SPLIT, n_tiles);  // few rows expected: spread them over the model tiles
+    while (n_split & (n_split - 1)) --n_split;
+  } else {
+    while (n_split < TC_MAX_SPLIT && m_tiles * n_split < ctx->sm_count && n_split * 2 <= n_tiles) n_split *= 2;
+  }
+  DevBuf<__half> A16;
+  DevBuf<float> na, cand_s;
   DevBuf<int> cand_j;
   B200_TRY(A16.alloc(ctx, (size_t)rowsA * Kp));
-  B200_TRY(B16.alloc(ctx, (size_t)rowsB * Kp));
   B200_TRY(na.alloc(ctx, (size_t)rowsA));
-  B200_TRY(nb.alloc(ctx, (size_t)rowsB));
-  B200_TRY(scA.alloc(ctx, 2));
-  B200_TRY(scB.alloc(ctx, 2));
-  B200_TRY(nbmax.alloc(ctx, 1));
-  B200_TRY(bits.alloc(ctx, 4));
-  B200_TRY(bits.zero());
   B200_TRY(cand_s.alloc(ctx, (size_t)Ks * n_split * TC_CAND));
   B200_TRY(cand_j.alloc(ctx, (size_t)Ks * n_split * TC_CAND));
-  B200_CUDA(ctx, cudaMemsetAsync(fb_count, 0, sizeof(int), ctx->stream));
-
-  const int rb = std::min(ctx->sm_count * 8, 4096);
-  absmax_kernel<<<rb, 256, 0, ctx->stream>>>(d_scene, (size_t)Ks * D, bits.p + 0);
+  tc_prep_kernel<<<ceil_div((long long)(rows_dev ? Ks : rowsA) * 32, 256), 256, 0, ctx->stream>>>(
+      d_scene, Ks, rows_dev ? Ks : rowsA, D, Kp, terms, 0, scA, nullptr, A16.p, na.p, nullptr, row_map, rows_dev);
   B200_LAUNCHED(ctx);
-  absmax_kernel<<<rb, 256, 0, ctx->stream>>>(d_model, (size_t)Km * D, bits.p + 1);
-  B200_LAUNCHED(ctx);
-  make_scale_kernel<<<1, 1, 0, ctx->stream>>>(bits.p + 0, scA.p);
-  B200_LAUNCHED(ctx);
-  make_scale_kernel<<<1, 1, 0, ctx->stream>>>(bits.p + 1, scB.p);
-  B200_LAUNCHED(ctx);
-  tc_prep_kernel<<<ceil_div((long long)rowsA * 32, 256), 256, 0, ctx->stream>>>(d_scene, Ks, rowsA, D, Kp, terms, 0,
-                                                                                scA.p, nullptr, A16.p, na.p, nullptr);
-  B200_LAUNCHED(ctx);
-  tc_prep_kernel<<<ceil_div((long long)rowsB * 32, 256), 256, 0, ctx->stream>>>(d_model, Km, rowsB, D, Kp, terms, 1,
-                                                                                scB.p, mvalid, B16.p, nb.p, bits.p + 2);
-  B200_LAUNCHED(ctx);
-
   CUtensorMap mapA, mapB;
   B200_TRY(make_map(ctx, &mapA, A16.p, rowsA, Kp, TC_BM));
-  B200_TRY(make_map(ctx, &mapB, B16.p, rowsB, Kp, TC_BN));
+  B200_TRY(make_map(ctx, &mapB, reinterpret_cast<const __half *>(terms == 1 ? B.B1.p : B.B3.p), B.rowsB, Kp, TC_BN));
   TcParams p;
   p.Ks = Ks;
   p.Km = Km;
@@ -653,11 +707,12 @@ int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned 
   p.n_tiles = n_tiles;
   p.n_split = n_split;
   p.k_blocks = Kp / TC_BK;
-  p.nb = nb.p;
-  p.scaleA = scA.p;
-  p.scaleB = scB.p;
+  p.nb = B.nb.p;
+  p.scaleA = scA;
+  p.scaleB = B.scaleB.p;
   p.cand_s = cand_s.p;
   p.cand_j = cand_j.p;
+  p.rows_dev = rows_dev;
   B200_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int grid = std::min(ctx->sm_count, m_tiles * n_split);
   {
@@ -665,19 +720,65 @@ int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned 
     tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(mapA, mapB, p);
     B200_LAUNCHED(ctx);
   }
-  // error bound of the approximate inner product relative to |a||b|: fp16 operand rounding (2^-11 per
-  // operand for one term, ~2^-21 for the three-term split) plus fp32 tensor-core accumulation
-  const float eta = (terms == 3) ? 1.0e-4f : 1.2e-3f;
+  const float eta = tc_eta(terms, Kp);
   const int rows_per_cta = RS_WARPS_PER_CTA * (32 / (n_split * TC_CAND));
   const size_t rs_smem = sizeof(RescoreSmem) * RS_WARPS_PER_CTA;
   B200_CUDA(ctx, cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
   tc_rescore_kernel<<<ceil_div(Ks, rows_per_cta), RS_WARPS_PER_CTA * 32, rs_smem, ctx->stream>>>(
       d_model, Km, d_scene, Ks, D, svalid, n_split, cand_s.p, cand_j.p, na.p,
-      reinterpret_cast<const float *>(bits.p + 2), scA.p, scB.p, eta, best, zero_cnt, fb_rows, fb_count,
-      ctx->profiling ? bits.p + 3 : nullptr);
+      reinterpret_cast<const float *>(B.bits.p + 1), scA, B.scaleB.p, eta, best, zero_cnt, fb_rows, fb_count,
+      err_bits, row_map, rows_dev);
   B200_LAUNCHED(ctx);
+  return B200_OK;
+}
+
+}  // namespace
+
+// plan: 1 = one-term pass only, 3 = three-term pass only, 13 = one-term pass over every row, three-term pass over
+// the rows it could not certify.  On return best[] / zero_cnt[] hold the certified rows; fb_rows[0..*fb_count)
+// lists the rows that need the exact kernel.  prep: the model side if it is resident (nullable).
+int match_tc_filter(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid, const TcModelPrep *prep,
+                    const float *d_scene, int Ks, const unsigned char *svalid, int D, int plan,
+                    unsigned long long *best, int *zero_cnt, int *fb_rows, int *fb_count) {
+  if (tc_kp(3, D) > 4096) return ctx->fail(B200_ERR_INVALID, "match: descriptor too long for the tensor-core filter");
+  TcModelPrep local;
+  if (!prep || !prep->ready || prep->Km != Km || prep->D != D) {
+    B200_TRY(match_tc_prepare_model(ctx, d_model, Km, D, mvalid, &local));
+    prep = &local;
+  }
+  DevBuf<float> scA;
+  DevBuf<unsigned> bitsA;
+  DevBuf<int> fb1_rows, fb1_count;
+  B200_TRY(scA.alloc(ctx, 2));
+  B200_TRY(bitsA.alloc(ctx, 2));
+  B200_TRY(bitsA.zero());
+  B200_CUDA(ctx, cudaMemsetAsync(fb_count, 0, sizeof(int), ctx->stream));
+  const int rb = std::min(ctx->sm_count * 8, 4096);
+  absmax_kernel<<<rb, 256, 0, ctx->stream>>>(d_scene, (size_t)Ks * D, bitsA.p + 0);
+  B200_LAUNCHED(ctx);
+  make_scale_kernel<<<1, 1, 0, ctx->stream>>>(bitsA.p + 0, scA.p);
+  B200_LAUNCHED(ctx);
+  DevBuf<unsigned> errb;
+  B200_TRY(errb.alloc(ctx, 1));
+  B200_TRY(errb.zero());
+  unsigned *err_bits = ctx->profiling ? errb.p : nullptr;
+  if (plan == 13) {
+    B200_TRY(fb1_rows.alloc(ctx, (size_t)Ks));
+    B200_TRY(fb1_count.alloc(ctx, 1));
+    B200_TRY(fb1_count.zero());
+    B200_TRY(tc_pass(ctx, d_model, Km, *prep, d_scene, Ks, svalid, D, 1, scA.p, nullptr, nullptr, best, zero_cnt,
+                     fb1_rows.p, fb1_count.p, err_bits));
+    if (ctx->profiling)
+      B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_pass1_fail, fb1_count.p, sizeof(int), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    B200_TRY(tc_pass(ctx, d_model, Km, *prep, d_scene, Ks, svalid, D, 3, scA.p, fb1_rows.p, fb1_count.p, best,
+                     zero_cnt, fb_rows, fb_count, nullptr));
+  } else {
+    B200_TRY(tc_pass(ctx, d_model, Km, *prep, d_scene, Ks, svalid, D, plan, scA.p, nullptr, nullptr, best, zero_cnt,
+                     fb_rows, fb_count, err_bits));
+  }
   if (ctx->profiling)
-    B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_err_ratio, bits.p + 3, sizeof(float), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+    B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_err_ratio, errb.p, sizeof(float),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
   return B200_OK;
 }

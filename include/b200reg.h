@@ -347,6 +347,8 @@ B200_API int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, in
  * that were re-evaluated by the exact float32 kernel (-1: the filter was not used).  Recorded only while
  * profiling is enabled; synchronises the stream. */
 B200_API int b200_last_match_fallback(b200_ctx *ctx, int *rows);
+/* Rows the one-term first pass of the filter left to the three-term second pass (-1: no such pass ran). */
+B200_API int b200_last_match_pass1_rows(b200_ctx *ctx, int *rows);
 /* Largest observed |approximate - exact| candidate distance of the last filtered match, divided by the
  * error bound the certificate assumes (must stay well below 1).  Profiling only; synchronises. */
 B200_API int b200_last_match_error_ratio(b200_ctx *ctx, float *ratio);

@@ -41,7 +41,7 @@ def _shot_like(rng, n, D=352, clusters=None):
     return x.astype(np.float32)
 
 
-@pytest.mark.parametrize("terms", ["tc3", "tc1"])
+@pytest.mark.parametrize("terms", ["tc13", "tc3", "tc1"])
 def test_tc_filter_matches_exact(ctx, orc, terms):
     rng = _rng(31)
     centres = _shot_like(rng, 300)
@@ -75,11 +75,11 @@ def test_tc_filter_certifies_most_rows(ctx, orc, synth):
     dm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, 0.02)
     ds, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, 0.02)
     ref = _with_mode("exact", lambda: ctx.match(dm, ds, 1, 0.25))
-    for terms, max_frac in (("tc3", 0.05), ("tc1", 0.6)):
+    for terms, max_frac in (("tc13", 0.05), ("tc3", 0.05), ("tc1", 0.6)):
         got = _with_mode(terms, lambda: ctx.match(dm, ds, 1, 0.25))
         fb = ctx.match_fallback_rows()
-        print("%s: %d of %d rows fell back to the exact kernel (Km=%d); error/bound = %.3f" %
-              (terms, fb, len(ds), len(dm), ctx.match_error_ratio()))
+        print("%s: %d of %d rows fell back to the exact kernel (Km=%d); error/bound = %.3f; first pass left %d" %
+              (terms, fb, len(ds), len(dm), ctx.match_error_ratio(), ctx.match_pass1_rows()))
         assert ctx.match_error_ratio() < 0.5
         assert got.tobytes() == ref.tobytes()
         assert fb <= max_frac * len(ds)
@@ -91,9 +91,39 @@ def test_tc_approximation_error_within_bound(ctx):
     model = (rng.gamma(0.2, 1.0, (2000, 352)) * rng.uniform(0.01, 100.0, (2000, 1))).astype(np.float32)
     scene = (model[rng.integers(0, 2000, 1500)] * rng.uniform(0.98, 1.02, (1500, 352))).astype(np.float32)
     ref = _with_mode("exact", lambda: ctx.match(model, scene, 1, 1e9))
-    for terms in ("tc3", "tc1"):
+    for terms in ("tc13", "tc3", "tc1"):
         got = _with_mode(terms, lambda: ctx.match(model, scene, 1, 1e9))
         assert got.tobytes() == ref.tobytes()
         print("%s adversarial: fallback %d, error/bound %.3f" % (terms, ctx.match_fallback_rows(),
                                                                  ctx.match_error_ratio()))
         assert ctx.match_error_ratio() < 0.5
+
+
+@pytest.mark.parametrize("D", [640, 1024])
+def test_tc_filter_long_descriptors(ctx, D):
+    """The certificate's error terms scale with the descriptor length (float32 sum error ~ D 2^-23, tensor-core
+    accumulation ~ K' 2^-22): long rows of near-duplicates must still give the exact kernel's answer."""
+    rng = _rng(D)
+    centres = rng.gamma(0.3, 1.0, (200, D)).astype(np.float32)
+    model = (centres[rng.integers(0, 200, 2048)] + 0.02 * rng.gamma(0.3, 1.0, (2048, D))).astype(np.float32)
+    scene = (model[rng.integers(0, 2048, 1500)] * rng.uniform(0.999, 1.001, (1500, D))).astype(np.float32)
+    ref = _with_mode("exact", lambda: ctx.match(model, scene, 1, 1e9))
+    for terms in ("tc13", "tc3", "tc1"):
+        got = _with_mode(terms, lambda: ctx.match(model, scene, 1, 1e9))
+        assert got.tobytes() == ref.tobytes(), (terms, D)
+        print("D=%d %s: fallback %d, error/bound %.3f" % (D, terms, ctx.match_fallback_rows(), ctx.match_error_ratio()))
+        assert ctx.match_error_ratio() < 0.5
+
+
+def test_tc_filter_full_cross_check_at_bench_size(ctx):
+    """Every row of a bench-sized problem (91 k x 13 k x 352) against the exact float32 kernel — not a sample."""
+    rng = _rng(77)
+    centres = _shot_like(rng, 2000)
+    model = _shot_like(rng, 13049, 352, centres)
+    scene = _shot_like(rng, 91076, 352, centres)
+    ref = _with_mode("exact", lambda: ctx.match(model, scene, 1, 0.25))
+    got = _with_mode("tc13", lambda: ctx.match(model, scene, 1, 0.25))
+    print("bench size: %d correspondences, first pass left %d rows, exact kernel %d rows, error/bound %.3f" %
+          (len(ref), ctx.match_pass1_rows(), ctx.match_fallback_rows(), ctx.match_error_ratio()))
+    assert got.tobytes() == ref.tobytes()
+    assert ctx.match_error_ratio() < 0.5
