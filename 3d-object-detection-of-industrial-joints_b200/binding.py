@@ -382,8 +382,12 @@ class Library:
         if rc not in (OK, ERR_CAPACITY):
             self.ctx._chk(rc)
         m = n.value
+        if rc == ERR_CAPACITY:
+            import warnings
+            warnings.warn("b200_register_scene_library: output capacity exceeded, results truncated", RuntimeWarning,
+                          stacklevel=2)
         return {"transforms": T[:m].reshape(m, 4, 4), "view": view[:m], "instances": InstanceList(ic, off, m),
-                "n_instances": m, "view_n_corrs": ncorr[:nv]}
+                "n_instances": m, "view_n_corrs": ncorr[:nv], "truncated": rc == ERR_CAPACITY}
 
     def close(self):
         if self.h and self.ctx.h:
@@ -689,8 +693,12 @@ class Context:
         if rc not in (OK, ERR_CAPACITY):
             self._chk(rc)
         m = min(n_inst.value, mi)
+        if rc == ERR_CAPACITY:
+            import warnings
+            warnings.warn("b200_register_scene_shot: output capacity exceeded (%d instances found, %d kept): %s"
+                          % (n_inst.value, m, lib().b200_last_error(self.h).decode()), RuntimeWarning, stacklevel=2)
         return {"transforms": T[:m].reshape(m, 4, 4), "instances": InstanceList(ic, off, m),
-                "n_instances": n_inst.value, "corrs": corrs[:n_corr.value]}
+                "n_instances": n_inst.value, "corrs": corrs[:n_corr.value], "truncated": rc == ERR_CAPACITY}
 
     def dev_register_scene_shot(self, model, d_xyz, n, stride, d_kp, Ks, kstride, params, out):
         """All buffers resident (torch CUDA tensors in `out`), asynchronous (b200_dev_register_scene_shot)."""

@@ -56,22 +56,25 @@ def workload(scene_id, scene_points, model_points):
                 scene_kp=synth.uniform_sampling(scene, SCENE_SS))
 
 
-def config_dict(args, wl, world):
+def config_dict(args, wl, world, scenes_per_step=None):
     synth = importlib.import_module(PKG).synth
     return {
         "workload": "SHOT_scenes pipeline, north-star target: %d-pt Kinect-like scene (Y+diagonal+horizontal joints) "
-                    "vs %d-pt Y-joint model; one scene per GPU per step" % (len(wl["scene"]), len(wl["model"])),
+                    "vs %d-pt Y-joint model; a step = one batch of scene registrations (distinct scenes, round-robin)"
+                    % (len(wl["scene"]), len(wl["model"])),
         "params": {"normals_k": 20, "uniform_sampling": {"model": MODEL_SS, "scene": SCENE_SS}, "shot_radius": 0.02,
                    "match": "k=1, d2<0.25", "gc": {"size": 0.02, "threshold": 2}},
         "N_scene": int(len(wl["scene"])), "N_model": int(len(wl["model"])), "K_scene": int(len(wl["scene_kp"])),
-        "K_model": int(len(wl["model_kp"])), "shapes": synth.SHAPE_INFO, "scenes_per_step": world,
-        "parallelism": "scene-sharded x%d (one scene per rank per step, same synthetic scene on every rank), model "
-                       "library replicated, NCCL gather of the correspondence lists; %d scenes in flight per GPU "
-                       "(lanes)" % (world, args.lanes),
+        "K_model": int(len(wl["model_kp"])), "shapes": synth.SHAPE_INFO,
+        "scenes_per_step": scenes_per_step if scenes_per_step is not None else world,
+        "scene_pool_per_rank": getattr(args, "pool", 1),
+        "parallelism": "scene-sharded x%d (every rank registers its own distinct scenes), model library replicated, "
+                       "NCCL gather of each scene's correspondence list; %d scenes in flight per GPU (lanes)"
+                       % (world, args.lanes),
         "lanes_per_gpu": args.lanes,
         "host_waits": "blocking events" if getattr(args, "blocking", False) else "spinning",
-        "l2": "256 MiB buffer written on the step's stream before every step, inside the timed region (lanes pass); "
-              "between steps, outside the timed intervals, in the single-lane pass",
+        "l2": "256 MiB buffer written on the scene's stream before every scene registration, inside the timed region "
+              "(lanes pass); between scenes, outside the timed intervals, in the single-lane pass",
     }
 
 
@@ -126,83 +129,101 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_pipeline_sample(wl, n_sample, threads=None):
-    """The reference path (CPU restatement, oracle/) on a bounded sample: normals for the full scene,
-    then SHOT / matching / grouping for an evenly strided subset of the scene keypoints against the
-    full model library.  Returns (estimated full-workload seconds, detail dict)."""
+def cpu_full_pass(wl, threads=None, serial_sample=1500):
+    """The reference path (CPU restatement, oracle/) on ONE COMPLETE scene, nothing sampled: normals of every
+    point (OpenMP, as NormalEstimationOMP), SHOT352 at every scene keypoint (OpenMP, as SHOTEstimationOMP), the
+    correspondence loop over every scene descriptor against the full model library, geometric-consistency grouping +
+    RANSAC.  The reference's matching loop is serial (SHOT.cpp:409-423); run serially it alone takes minutes on this
+    workload, so the measured pass parallelises it with OpenMP (faster than the reference, i.e. a stronger baseline)
+    and the serial loop is timed on `serial_sample` scene descriptors and extrapolated, labelled as an estimate.
+    Returns (measured seconds, detail)."""
     from oracle import pcl_oracle as orc
-    if threads:
-        orc.set_num_threads(threads)
+    orc.set_num_threads(threads or os.cpu_count() or 1)
     scene, kp = wl["scene"], wl["scene_kp"]
-    stride = max(1, len(kp) // max(n_sample, 1))
-    sub = np.ascontiguousarray(kp[::stride])
-    f = len(sub) / len(kp)
     t0 = time.perf_counter()
     nrm = orc.normals(scene, k=PARAMS["normal_k"])
     t1 = time.perf_counter()
-    desc, _ = orc.shot352(scene, nrm, sub, PARAMS["descr_radius"])
+    desc, _ = orc.shot352(scene, nrm, kp, PARAMS["descr_radius"])
     t2 = time.perf_counter()
-    corr = orc.match(wl["model_desc"], desc, PARAMS["match_mode"], PARAMS["match_thr"])  # serial, as SHOT.cpp:409-423
+    corr = orc.match(wl["model_desc"], desc, PARAMS["match_mode"], PARAMS["match_thr"], omp=True)
     t3 = time.perf_counter()
-    orc.gc_recognize(wl["model_kp"], sub, corr, PARAMS["gc_size"], PARAMS["gc_threshold"], max_inst=4096)
+    T, _inst = orc.gc_recognize(wl["model_kp"], kp, corr, PARAMS["gc_size"], PARAMS["gc_threshold"],
+                                max_inst=PARAMS["max_instances"])
     t4 = time.perf_counter()
-    corr_omp = orc.match(wl["model_desc"], desc, PARAMS["match_mode"], PARAMS["match_thr"], omp=True)
+    stride = max(1, len(kp) // max(serial_sample, 1))
+    sub = np.ascontiguousarray(desc[::stride])
     t5 = time.perf_counter()
-    assert corr_omp.tobytes() == corr.tobytes()
-    t_norm, t_shot, t_match, t_gc, t_match_omp = t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4
-    # keypoint-proportional stages are scaled by 1/f (grouping is O(C^2): linear scaling favours the CPU)
-    full = t_norm + (t_shot + t_match + t_gc) / f
-    full_omp = t_norm + (t_shot + t_match_omp + t_gc) / f
-    detail = {"sample_keypoints": int(len(sub)), "fraction": f, "t_normals_s": t_norm, "t_shot_s": t_shot,
-              "t_match_serial_s": t_match, "t_match_omp_s": t_match_omp, "t_gc_s": t_gc, "sample_corrs": int(len(corr)),
-              "est_full_s": full, "est_full_s_with_omp_match": full_omp}
-    return full, detail
+    orc.match(wl["model_desc"], sub, PARAMS["match_mode"], PARAMS["match_thr"])  # serial, as SHOT.cpp:409-423
+    t6 = time.perf_counter()
+    t_serial_est = (t6 - t5) * len(desc) / len(sub)
+    measured = t4 - t0
+    detail = {"t_normals_s": t1 - t0, "t_shot_s": t2 - t1, "t_match_omp_s": t3 - t2, "t_gc_s": t4 - t3,
+              "measured_full_pass_s": measured, "correspondences": int(len(corr)), "instances": int(len(T)),
+              "serial_match_sample_rows": int(len(sub)), "t_match_serial_sample_s": t6 - t5,
+              "t_match_serial_est_s": t_serial_est,
+              "est_full_pass_s_with_serial_matching": measured - (t3 - t2) + t_serial_est}
+    return measured, detail
 
 
 def model_descriptors_cpu(wl):
     from oracle import pcl_oracle as orc
+    orc.set_num_threads(os.cpu_count() or 1)
     nrm = orc.normals(wl["model"], k=PARAMS["normal_k"])
     desc, _ = orc.shot352(wl["model"], nrm, wl["model_kp"], PARAMS["descr_radius"])
     return desc
 
 
+def cpu_baseline_record(wl, measured, detail, cores):
+    K = len(wl["scene_kp"])
+    return {
+        "value": K / measured, "unit": "descriptors/s", "cores": cores, "kind": "port",
+        "sample": "ONE complete pass over scene 0 (%d points, %d keypoints vs %d model descriptors), nothing sampled or "
+                  "extrapolated: normals + SHOT352 (OpenMP over points / keypoints as PCL's *OMP classes), matching loop "
+                  "parallelised with OpenMP (the reference's loop is serial: that variant is estimated below from %d "
+                  "rows), GC grouping + RANSAC serial; PCL-semantics restatement (oracle/), not libpcl" %
+                  (len(wl["scene"]), K, len(wl["model_kp"]), detail["serial_match_sample_rows"]),
+        "measured": True, "detail": detail,
+        "value_with_serial_matching_estimate": K / detail["est_full_pass_s_with_serial_matching"],
+    }
+
+
 def run_reference(args, rank, world):
+    """CPU arm: rank 0 alone, every host core, one measured un-sampled pass per invocation (a pass takes tens of
+    seconds; repeating the identical pass K times would only burn the lease)."""
     if rank != 0:
         return
     from oracle import pcl_oracle as orc
+    cores = os.cpu_count() or 1
+    orc.set_num_threads(cores)   # explicitly: torchrun exports OMP_NUM_THREADS=1
     wl = workload(0, args.scene_points, args.model_points)
     wl["model_desc"] = model_descriptors_cpu(wl)  # resident library: untimed setup, like the GPU arm
-    cores = orc.num_threads()
-    K = len(wl["scene_kp"])
-    times, detail = [], None
-    for s in range(args.warmup + args.steps):
-        full, detail = cpu_pipeline_sample(wl, args.cpu_sample)
-        if s >= args.warmup:
-            times.append(full)
-    est = float(np.mean(times))
-    value = K / est
-    sample = ("normals on the full %d-pt scene + SHOT/match/GC on %d of %d scene keypoints (every %d-th) vs the full "
-              "%d-descriptor model library; keypoint-proportional stage times scaled by 1/fraction; serial matching "
-              "loop as in the reference (SHOT.cpp:409-423)" %
-              (len(wl["scene"]), detail["sample_keypoints"], K, max(1, K // max(args.cpu_sample, 1)),
-               len(wl["model_kp"])))
+    measured, detail = cpu_full_pass(wl, cores, args.cpu_sample)
+    rec = cpu_baseline_record(wl, measured, detail, orc.num_threads())
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": "descriptors/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": measured * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": config_dict(args, wl, 1),
-        "registrations_per_s": 1.0 / est,
-        "cpu_baseline": {"value": value, "unit": "descriptors/s", "cores": cores, "kind": "port", "sample": sample,
-                         "detail": detail,
-                         "value_with_omp_matching": K / detail["est_full_s_with_omp_match"]},
-        "e2e": {"value": value, "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": config_dict(args, wl, 1, scenes_per_step=1),
+        "registrations_per_s": 1.0 / measured,
+        "cpu_passes_timed": 1,
+        "cpu_baseline": rec,
+        "e2e": {"value": rec["value"], "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "PCL-semantics restatement (oracle/), not libpcl: PCL is neither vendored in the reference nor "
-                "installed here",
+                "installed here or on the GPU box (profiles/pcl_probe_r02.txt).  ms_per_step is one complete scene "
+                "registration on the CPU (the GPU arm's step holds several scenes: compare `value`, not ms_per_step); "
+                "value uses an OpenMP matching loop, value_with_serial_matching_estimate the reference's serial loop",
     }
     _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
+# algorithmic bytes / flop per stage (SURVEY.md 8(d)); the kernel that carries the stage
+STAGE_KERNEL = {"normals": "normals_knn_kernel", "shot": "shot_warp_kernel", "match_filter": "tc_filter_kernel",
+                "gc_adjacency": "gc_adjacency_kernel", "gc_group": "gc_group_cluster_kernel",
+                "gc_ransac": "gc_ransac_kernel", "gc_sort": "gc_rank_kernel", "neighbor_count": "radius_count_kernel",
+                "grid_build": "cell_count/scan/scatter kernels", "match": "tc_filter + tc_rescore + prep kernels"}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -217,10 +238,12 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # weak scaling: every rank registers one scene per step; all ranks use the same synthetic scene so that
-    # the per-GPU work is identical (distinct scenes differ by up to 25 % in correspondences / instances and the
-    # step time is the max over ranks)
-    wl = workload(0, args.scene_points, args.model_points)
+    # Workload: every rank owns a pool of DISTINCT synthetic scenes (scene ids rank*P .. rank*P+P-1: different joint
+    # poses, clutter and noise, so K_s, the correspondence count and the number of instances differ from scene to
+    # scene and from rank to rank) and registers them round-robin against the replicated model library.
+    P = max(1, args.pool)
+    pool = [workload(rank * P + i, args.scene_points, args.model_points) for i in range(P)]
+    wl = pool[0]
     p = binding.shot_params(**PARAMS)
     peaks = {}
     try:
@@ -232,7 +255,6 @@ def run_b200(args, rank, world, local_rank):
     # host thread (sharding.run_lanes).  The grouping stage of one scene is a latency-bound chain on 8 SMs; the
     # other lanes' wide stages (normals, SHOT, matching) fill the rest of the GPU meanwhile.
     L = max(1, args.lanes)
-    # every lane is a host thread that spins in stream synchronisations: keep lanes x ranks within the host cores
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -241,6 +263,7 @@ def run_b200(args, rank, world, local_rank):
     blocking = world * L > cores or args.blocking_sync
     args.lanes = L
     args.blocking = blocking
+    B = L * max(1, args.scenes_per_lane)   # scene registrations per step and rank
     streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
     ctxs = [binding.Context(local_rank, stream=st.cuda_stream) for st in streams]
     if blocking:
@@ -250,18 +273,21 @@ def run_b200(args, rank, world, local_rank):
     with torch.cuda.stream(streams[0]):
         model = ctx.model_create_shot(wl["model"], wl["model_kp"], p)   # resident, replicated library (setup)
     ctx.sync()
-    N, Ks, Km = len(wl["scene"]), len(wl["scene_kp"]), model.size
-    d_scene = torch.from_numpy(wl["scene"]).to(dev)
-    d_kp = torch.from_numpy(wl["scene_kp"]).to(dev)
+    Km = model.size
+    d_scenes = [torch.from_numpy(w["scene"]).to(dev) for w in pool]
+    d_kps = [torch.from_numpy(w["scene_kp"]).to(dev) for w in pool]
+    Ns = [len(w["scene"]) for w in pool]
+    Kss = [len(w["scene_kp"]) for w in pool]
+    Ks_max = max(Kss)
     mi = PARAMS["max_instances"]
     # the gather needs equally sized correspondence buffers on every rank (scenes differ in K_s)
-    corr_cap_all = sharding.common_capacity(Ks, device=dev) if world > 1 else Ks
+    corr_cap_all = sharding.common_capacity(Ks_max, device=dev) if world > 1 else Ks_max
 
     def make_out():
         return {"transforms": torch.zeros(mi * 16, dtype=torch.float32, device=dev),
                 "inst_offsets": torch.zeros(mi + 1, dtype=torch.int32, device=dev),
                 "inst_counts": torch.zeros(mi, dtype=torch.int32, device=dev),
-                "inst_corrs": torch.zeros((Ks, 3), dtype=torch.int32, device=dev), "corr_cap": Ks,
+                "inst_corrs": torch.zeros((Ks_max, 3), dtype=torch.int32, device=dev), "corr_cap": Ks_max,
                 "n_inst": torch.zeros(1, dtype=torch.int32, device=dev),
                 "corrs": torch.zeros((corr_cap_all, 3), dtype=torch.int32, device=dev),
                 "n_corrs": torch.zeros(1, dtype=torch.int32, device=dev)}
@@ -273,18 +299,19 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     def step(lane, s, flush=False):
+        i = s % P
         with torch.cuda.stream(streams[lane]):
             if flush:
                 flushes[lane].zero_()
-            ctxs[lane].dev_register_scene_shot(model, d_scene, N, 3, d_kp, Ks, 3, p, outs[lane])
+            ctxs[lane].dev_register_scene_shot(model, d_scenes[i], Ns[i], 3, d_kps[i], Kss[i], 3, p, outs[lane])
             if world > 1:   # the path's one exchange: gather the correspondence lists (NCCL over NVLink)
                 gate.run(s, lambda: sharding.gather_correspondences(outs[lane]["corrs"], outs[lane]["n_corrs"]))
 
     gate.reset()
-    sharding.run_lanes(L, args.warmup * L, step)
+    sharding.run_lanes(L, max(args.warmup, 3) * L, step)
     torch.cuda.synchronize()
 
-    # ---- pass A, one lane: per-step latency and the per-stage device times (roofline attribution) ----
+    # ---- pass A, one lane: per-scene latency and the per-stage device times (roofline attribution) ----
     stream = streams[0]
     ctx.set_profiling(True)
     ctx.reset_profiling()
@@ -294,26 +321,32 @@ def run_b200(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize()
     t_begin = time.time()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    n_single = max(2 * P, 8)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(n_single)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_single)]
+    per_scene = {}
     gate.reset()
-    for s in range(args.steps):
+    for s in range(n_single):
         with torch.cuda.stream(stream):
             flushes[0].zero_()
             starts[s].record(stream)
         step(0, s)
         ends[s].record(stream)
+        if s < P:
+            torch.cuda.synchronize()
+            per_scene[s] = {"N": Ns[s], "K_scene": Kss[s], "correspondences": int(out["n_corrs"].item()),
+                            "instances": int(out["n_inst"].item())}
     torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
     stages = ctx.stage_times()
+    fb_rows, p1_rows = ctx.match_fallback_rows(), ctx.match_pass1_rows()
     ctx.set_profiling(False)
     mean_nbrs, max_nbrs = ctx.neighbor_stats()
-    n_inst = int(out["n_inst"].item())
-    n_corrs = int(out["n_corrs"].item())
     single_ms = float(np.mean(step_ms))
 
     # ---- pass B, L lanes: the throughput the metric is quoted on.  One start event when the device is idle,
-    # one end event per lane stream; the L2 flush (256 MiB write) runs before every step INSIDE the timed region
+    # one end event per lane stream; the L2 flush (256 MiB write) runs before every scene INSIDE the timed region
+    n_scene_steps = args.steps * B
     gate.reset()
     if world > 1:
         dist.barrier()
@@ -323,7 +356,7 @@ def run_b200(args, rank, world, local_rank):
     ev_ends = [torch.cuda.Event(enable_timing=True) for _ in range(L)]
     ev_start.record(streams[0])
     stagger = single_ms / 1e3 / L   # inside the timed region: lane l starts l/L of a scene latency late
-    sharding.run_lanes(L, args.steps, lambda lane, s: step(lane, s, flush=True), stagger_s=stagger)
+    sharding.run_lanes(L, n_scene_steps, lambda lane, s: step(lane, s, flush=True), stagger_s=stagger)
     for l in range(L):
         ev_ends[l].record(streams[l])
     torch.cuda.synchronize()
@@ -333,10 +366,10 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop(t_begin, t_end)
     total_ms = max(ev_start.elapsed_time(e) for e in ev_ends)
     launches = sum(c.launches for c in ctxs) - launches0
-    assert all(int(o["n_inst"].item()) == n_inst for o in outs[:min(L, args.steps)])
+    desc_done = float(sum(Kss[s % P] for s in range(n_scene_steps)))
 
     ms = total_ms / args.steps
-    t = torch.tensor([ms, float(Ks), single_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, desc_done, single_ms], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -344,16 +377,21 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_max, total_desc, single_ms_max = float(tmax[0]), float(tsum[1]), float(tmax[2])
     else:
-        ms_max, total_desc, single_ms_max = ms, float(Ks), single_ms
+        ms_max, total_desc, single_ms_max = ms, desc_done, single_ms
+    total_s = ms_max * args.steps / 1e3
 
     # ---- end to end through the host-buffer C-ABI call: pinned host buffers, copies timed, same lanes ----
-    h_scene = torch.from_numpy(wl["scene"]).pin_memory()
-    h_kp = torch.from_numpy(wl["scene_kp"]).pin_memory()
-    hs, hk = h_scene.numpy(), h_kp.numpy()
+    h_scenes = [torch.from_numpy(w["scene"]).pin_memory() for w in pool]
+    h_kps = [torch.from_numpy(w["scene_kp"]).pin_memory() for w in pool]
+    hs, hk = [x.numpy() for x in h_scenes], [x.numpy() for x in h_kps]
     results = [None] * L
+    truncated = [0]
 
     def e2e_step(lane, s):
-        results[lane] = ctxs[lane].register_scene_shot(model, hs, hk, p)
+        i = s % P
+        results[lane] = ctxs[lane].register_scene_shot(model, hs[i], hk[i], p)
+        if results[lane].get("truncated"):
+            truncated[0] += 1
         if world > 1:
             with torch.cuda.stream(streams[lane]):
                 gate.run(s, lambda: sharding.gather_correspondences(outs[lane]["corrs"], outs[lane]["n_corrs"]))
@@ -363,50 +401,40 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e2e_steps = max(6 * L, args.steps)   # enough steps per lane for the lanes to fall out of lockstep
     gate.reset()
     t0 = time.perf_counter()
-    sharding.run_lanes(L, e2e_steps, e2e_step, stagger_s=stagger)
+    sharding.run_lanes(L, n_scene_steps, e2e_step, stagger_s=stagger)
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_total_s = time.perf_counter() - t0
+    h2d = float(sum(hs[s % P].nbytes + hk[s % P].nbytes for s in range(n_scene_steps))) / args.steps
     res = results[0]
-    h2d = hs.nbytes + hk.nbytes
-    d2h = int(res["transforms"].nbytes + 4 * (len(res["instances"]) + 2) + 12 * len(res["corrs"]) +
-              12 * sum(len(i) for i in res["instances"]))
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    d2h_scene = int(res["transforms"].nbytes + 4 * (len(res["instances"]) + 2) + 12 * len(res["corrs"]) +
+                    12 * sum(len(i) for i in res["instances"]))
+    te = torch.tensor([e2e_total_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(te[0])
+    e2e_total_s = float(te[0])
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (stage with the largest device time) ----
+        N, Ks = Ns[0], Kss[0]
+        n_corrs, n_inst = per_scene[0]["correspondences"], per_scene[0]["instances"]
+        Nm = float(np.mean(Ns))
+        Ksm = float(np.mean(Kss))
+        Cm = float(np.mean([v["correspondences"] for v in per_scene.values()]))
         work = {
-            "normals": ("hbm", 32.0 * N, "GB/s"),
-            "shot": ("hbm", 1444.0 * Ks + 32.0 * N, "GB/s"),
-            "neighbor_count": ("hbm", 16.0 * N + 4.0 * Ks, "GB/s"),
-            "grid_build": ("hbm", 40.0 * N, "GB/s"),
-            "match": ("tensor", 2.0 * Ks * Km * 352, "TFLOP/s"),
-            "match_filter": ("tensor", 2.0 * Ks * Km * 352, "TFLOP/s"),   # nested in "match": the tcgen05 kernel alone
-            "gc_adjacency": ("hbm", 32.0 * n_corrs + n_corrs * (n_corrs / 8.0), "GB/s"),
-            "gc_group": ("hbm", 12.0 * n_corrs + 16.0 * (Ks + Km), "GB/s"),
-            "gc_sort": ("hbm", 12.0 * n_corrs * 2, "GB/s"),
-            "gc_ransac": ("hbm", 12.0 * n_corrs, "GB/s"),
+            "normals": ("hbm", 32.0 * Nm, "GB/s"),
+            "shot": ("hbm", 1444.0 * Ksm + 32.0 * Nm, "GB/s"),
+            "neighbor_count": ("hbm", 16.0 * Nm + 4.0 * Ksm, "GB/s"),
+            "grid_build": ("hbm", 40.0 * Nm, "GB/s"),
+            "match": ("tensor", 2.0 * Ksm * Km * 352, "TFLOP/s"),
+            "match_filter": ("tensor", 2.0 * Ksm * Km * 352, "TFLOP/s"),   # nested in "match": the tcgen05 kernel alone
+            "gc_adjacency": ("hbm", 32.0 * Cm + Cm * (Cm / 8.0), "GB/s"),
+            "gc_group": ("hbm", 12.0 * Cm + 16.0 * (Ksm + Km), "GB/s"),
+            "gc_sort": ("hbm", 12.0 * Cm * 2, "GB/s"),
+            "gc_ransac": ("hbm", 12.0 * Cm, "GB/s"),
         }
-        stage_ms = {k: (v[0] / max(args.steps, 1), v[1] // max(args.steps, 1)) for k, v in stages.items() if v[1] > 0}
-        # The dominant kernel is the stage with the largest SM-time: with several scenes in flight the step rate is
-        # set by the GPU-wide stages (their sum is the lanes-pass step time); the grouping stage is one 8-CTA
-        # cluster (8 of the SMs) and runs beside the other lanes' kernels, so its wall time counts 8/SMs.
-        sm_total = torch.cuda.get_device_properties(dev).multi_processor_count
-        sm_share = {"gc_group": 8.0 / sm_total}
-        sm_ms = {k: stage_ms[k][0] * sm_share.get(k, 1.0) for k in stage_ms if k in work}
-        # dominant STAGE among the top-level ones; when it is matching, the roofline line is its dominant KERNEL
-        # (the tcgen05 filter, timed by its own nested event pair)
-        dom = max((k for k in sm_ms if k != "match_filter"), key=lambda k: sm_ms[k])
-        if dom == "match" and "match_filter" in sm_ms:
-            dom = "match_filter"
-        # DRAM read + write per launch of the stage's main kernel, from the committed `ncu --set full`
-        # capture of this workload (profiles/summary_r01.md); None for stages not captured
-        traffic_ncu = TRAFFIC_NCU
+        stage_ms = {k: (v[0] / n_single, v[1] / n_single) for k, v in stages.items() if v[1] > 0}
+        kernel_total = sum(v[0] for k, v in stage_ms.items() if k != "match_filter")
 
         def roof(k):
             bound, units, unit = work[k]
@@ -414,67 +442,179 @@ def run_b200(args, rank, world, local_rank):
             if bound == "hbm":
                 achieved, peak = units / dur_s / 1e9, peaks.get("hbm_gbs", 6650.0)
             else:
-                achieved, peak = units / dur_s / 1e12, peaks.get("bf16_tflops_sustained", 1400.0)
-            r = {"kernel": k, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                 "frac": achieved / peak, "traffic": traffic_ncu.get(k), "algorithmic_units": units,
-                 "avg_stage_ms": stage_ms[k][0], "sm_ms": sm_ms[k]}
+                achieved, peak = units / dur_s / 1e12, peaks.get("bf16_tflops", 1650.0)
+            r = {"kernel": STAGE_KERNEL.get(k, k), "stage": k, "bound": bound, "achieved": achieved, "peak": peak,
+                 "unit": unit, "frac": achieved / peak, "traffic": TRAFFIC_NCU.get(k), "algorithmic_units": units,
+                 "avg_ms": stage_ms[k][0], "share_of_scene_kernel_time": stage_ms[k][0] / kernel_total}
             if k in ("match", "match_filter"):
-                # exact float32 results from fp16 tensor cores: each operand is split into hi + lo halves and three
-                # of the four products are issued (the stage also holds the exact rescoring of 8 candidates per row)
-                r["note"] = ("algorithmic flop = 2*K_s*K_m*352; the tcgen05 filter issues 3x that (fp16 hi/lo split, "
-                             "error ~2^-22) and runs at 88 % tensor-pipe activity (ncu, profiles/summary_r01.md); "
+                r["note"] = ("algorithmic flop = 2*K_s*K_m*352 per scene; the tcgen05 filter issues one fp16 term for "
+                             "every row plus three terms (hi/lo split) for the rows the first pass cannot certify; "
                              "exact FP32 rescoring + certificate make the result bit-identical to the FP32 search")
-                if k == "match_filter":
-                    r["kernel"] = "tc_filter_kernel"
-                    r["issued_tflops"] = 3.0 * achieved
             return r
 
-        roofline = roof(dom)
-        roofline.update({"traffic_source": "ncu --set full, profiles/summary_r01.md (default workload only)",
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
-                         "selection": "largest SM-time (stage time x share of the SMs it occupies); stage times are "
-                                      "CUDA-event pairs around the stage in the single-lane pass"})
-        roofline_all = [roof(k) for k in sorted(sm_ms, key=lambda k: -sm_ms[k])]
+        # the roofline line is the kernel with the LARGEST DURATION per scene, whatever it is; the three largest follow
+        order = sorted((k for k in stage_ms if k in work and k != "match"), key=lambda k: -stage_ms[k][0])
+        roofline = roof(order[0])
+        roofline.update({"traffic_source": "ncu --set full (profiles/), per launch, default workload",
+                         "peak_source": ("MEASURED_PEAKS.json (burst figures: kernel timed alone, single-lane pass)"
+                                         if peaks else "fallback (B200_PROFILING.md)"),
+                         "selection": "largest average duration per scene among all kernels of the step (CUDA-event "
+                                      "pair around the stage on the launching stream, single-lane pass)"})
+        roofline_top3 = [roof(k) for k in order[:3]]
+        roofline_all = [roof(k) for k in sorted((k for k in stage_ms if k in work), key=lambda k: -stage_ms[k][0])]
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             wl["model_desc"], _ = model.download()
             from oracle import pcl_oracle as orc
-            full, detail = cpu_pipeline_sample(wl, args.cpu_sample)
-            K = len(wl["scene_kp"])
-            cpu_baseline = {
-                "value": K / full, "unit": "descriptors/s", "cores": orc.num_threads(), "kind": "port",
-                "sample": "normals on the full scene + SHOT/match/GC on %d of %d scene keypoints vs the full model "
-                          "library, keypoint-proportional stages scaled by 1/fraction; serial matching loop as in the "
-                          "reference; PCL-semantics restatement, not libpcl" % (detail["sample_keypoints"], K),
-                "detail": detail, "value_with_omp_matching": K / detail["est_full_s_with_omp_match"]}
+            measured, detail = cpu_full_pass(wl, os.cpu_count(), args.cpu_sample)
+            cpu_baseline = cpu_baseline_record(wl, measured, detail, orc.num_threads())
+            # the same scene on both arms: the CPU pass must find what the device found
+            cpu_baseline["agrees_with_gpu"] = {"correspondences": detail["correspondences"] == n_corrs,
+                                               "instances": detail["instances"] == n_inst}
         line = {
-            "metric": METRIC, "value": total_desc / (ms_max / 1e3), "unit": "descriptors/s", "n_gpus": world,
+            "metric": METRIC, "value": total_desc / total_s, "unit": "descriptors/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 for the SHOT frame/bin decisions)",
-            "data": "synthetic", "config": config_dict(args, wl, world),
-            "registrations_per_s": world / (ms_max / 1e3),
+            "data": "synthetic", "config": config_dict(args, wl, world, scenes_per_step=B * world),
+            "registrations_per_s": world * n_scene_steps / total_s,
+            "timed_region_s": total_s,
             "lanes": L,
-            "single_lane": {"ms_per_step": single_ms_max, "value": total_desc / (single_ms_max / 1e3),
+            "single_lane": {"ms_per_scene": single_ms_max, "value": Ksm / (single_ms_max / 1e3),
                             "note": "one scene in flight per GPU (per-scene latency); stage times and the roofline "
-                                    "entry are measured in this pass"},
-            "e2e": {"value": total_desc / (e2e_ms_max / 1e3), "unit": "descriptors/s", "ms_per_step": e2e_ms_max,
-                    "registrations_per_s": world / (e2e_ms_max / 1e3), "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": d2h, "api": "b200_register_scene_shot (host buffers, pinned)"},
+                                    "entries are measured in this pass"},
+            "e2e": {"value": total_desc / e2e_total_s, "unit": "descriptors/s",
+                    "ms_per_step": e2e_total_s * 1e3 / args.steps, "timed_region_s": e2e_total_s,
+                    "registrations_per_s": world * n_scene_steps / e2e_total_s, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h_scene * B), "truncated_results": truncated[0],
+                    "api": "b200_register_scene_shot (host buffers, pinned), %d scenes per step" % B},
             "gpu_launches": int(launches),
+            "gpu_launches_per_scene": launches / max(n_scene_steps, 1),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_top3": roofline_top3,
             "roofline_all_stages": roofline_all,
             "cpu_baseline": cpu_baseline,
-            "stages_ms_per_step": {k: round(v[0], 4) for k, v in stage_ms.items()},
+            "stages_ms_per_scene": {k: round(v[0], 4) for k, v in stage_ms.items()},
+            "match_filter_rows": {"left_by_one_term_pass": p1_rows, "left_to_exact_kernel": fb_rows},
             "measured": {"N": N, "K_scene": Ks, "K_model": Km, "mean_neighbors": mean_nbrs, "max_neighbors": max_nbrs,
-                         "correspondences": n_corrs, "instances": n_inst, "step_ms": [round(x, 3) for x in step_ms]},
+                         "correspondences": n_corrs, "instances": n_inst, "scene_ms": [round(x, 3) for x in step_ms],
+                         "pool": per_scene},
         }
+        if args.other_configs and world == 1:
+            try:
+                line["other_configs"] = run_other_configs(ctx, binding, pkg, args)
+            except Exception as e:  # the headline line must survive a failure of the side measurements
+                line["other_configs"] = {"error": repr(e)}
         _emit(line)
     model.close()
     for c in ctxs:
         c.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timeit(fn, sync, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = fn()
+    sync()
+    return (time.perf_counter() - t0) / reps, r
+
+
+def run_other_configs(ctx, binding, pkg, args):
+    """BASELINE.json configs 1, 2 and 4 through the host-buffer C ABI (host arrays in, host results out, copies inside
+    the timed region), one scene in flight, with the CPU restatement of the same calls timed beside each on every host
+    core.  Small cases: each takes a second or two."""
+    from oracle import pcl_oracle as orc
+    synth = pkg.synth
+    orc.set_num_threads(os.cpu_count() or 1)
+    out = {}
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 100000, scene_id=1)
+    # ---- config 1: SHOT_demo pipeline (SHOT_demo.cpp:405-424, 497-531 + GC grouping), normals k=10, SHOT r=0.02
+    kpm, kps = synth.voxel_grid(model, 0.02), synth.voxel_grid(scene, 0.03)
+    p1 = binding.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                             max_instances=1024)
+    m1 = ctx.model_create_shot(model, kpm, p1)
+    t_gpu, res = _timeit(lambda: ctx.register_scene_shot(m1, scene, kps, p1), ctx.sync, 10)
+    dm, _ = m1.download()
+    m1.close()
+
+    def cpu1():
+        nrm = orc.normals(scene, k=10)
+        ds, _ = orc.shot352(scene, nrm, kps, 0.02)
+        c = orc.match(dm, ds, 1, 0.25)          # serial loop, as the reference
+        T, inst = orc.gc_recognize(kpm, kps, c, 0.02, 2, max_inst=1024)
+        return c, T
+    t_cpu, (c_cpu, T_cpu) = _timeit(cpu1, lambda: None, 2, warm=0)
+    out["config1_shot_demo"] = {
+        "workload": "5000-pt Y-joint model (%d keypoints) vs 100000-pt scene (%d keypoints), normals k=10, SHOT r=0.02, "
+                    "k=1 d2<0.25, GC 0.02/2" % (len(kpm), len(kps)),
+        "descriptors_per_s": len(kps) / t_gpu, "registrations_per_s": 1.0 / t_gpu, "ms_per_scene_e2e": t_gpu * 1e3,
+        "cpu": {"descriptors_per_s": len(kps) / t_cpu, "ms_per_scene": t_cpu * 1e3, "cores": orc.num_threads(),
+                "kind": "port", "measured": True, "matching": "serial loop (as the reference)"},
+        "same_result_as_cpu": bool(res["corrs"].tobytes() == c_cpu.tobytes() and res["n_instances"] == len(T_cpu)),
+        "correspondences": int(len(res["corrs"])), "instances": int(res["n_instances"])}
+    # ---- config 2: FPFH_demo (FPFH_demo.cpp:416-428, 505-538): radius normals + FPFH33 on the keypoint cloud,
+    # k = 2 ratio matching, GC grouping; radius 0.05 as BASELINE.json states
+    kq_m, kq_s = synth.voxel_grid(model, 0.01), synth.voxel_grid(scene, 0.01)
+    r = 0.05
+
+    def gpu2():
+        cm, cs = ctx.cloud(kq_m), ctx.cloud(kq_s)
+        fm = ctx.fpfh33(cm, ctx.normals(cm, radius=r), r)
+        fs = ctx.fpfh33(cs, ctx.normals(cs, radius=r), r)
+        c = ctx.match(fm, fs, 2, 0.0)
+        g = ctx.gc_recognize(kq_m, kq_s, c, 0.02, 3, max_inst=1024)
+        cm.close()
+        cs.close()
+        return fs, c, g
+    t_gpu2, (fs_gpu, c_gpu, g_gpu) = _timeit(gpu2, ctx.sync, 5)
+
+    def cpu2():
+        fm = orc.fpfh33(kq_m, orc.normals(kq_m, radius=r), r)
+        fs = orc.fpfh33(kq_s, orc.normals(kq_s, radius=r), r)
+        c = orc.match(fm, fs, 2, 0.0)
+        return fs, c
+    t_cpu2, (fs_cpu, c_cpu2) = _timeit(cpu2, lambda: None, 1, warm=0)
+    ok = np.isfinite(fs_cpu[:, 0]) & np.isfinite(fs_gpu[:, 0])
+    out["config2_fpfh_demo"] = {
+        "workload": "FPFH33 r=%.2f on the voxel-filtered (0.01) clouds: %d model / %d scene points, radius normals, "
+                    "k=2 ratio matching, GC 0.02/3" % (r, len(kq_m), len(kq_s)),
+        "descriptors_per_s": (len(kq_s) + len(kq_m)) / t_gpu2, "ms_per_scene_e2e": t_gpu2 * 1e3,
+        "cpu": {"descriptors_per_s": (len(kq_s) + len(kq_m)) / t_cpu2, "ms_per_scene": t_cpu2 * 1e3,
+                "cores": orc.num_threads(), "kind": "port", "measured": True,
+                "note": "normals + FPFH + matching (no grouping); FPFH via the OpenMP variant"},
+        "max_descriptor_l2_vs_cpu": float(np.linalg.norm(fs_gpu[ok] - fs_cpu[ok], axis=1).max()),
+        "correspondences": int(len(c_gpu)), "instances": int(len(g_gpu[0]))}
+    # ---- config 4: CAD_desc + partial views: 64 views x 3 joints in one resident library, one scene against all
+    p4 = binding.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=3,
+                             max_instances=512)
+    lib = binding.Library(ctx)
+    t0 = time.perf_counter()
+    n_desc = 0
+    for joint in ("y", "diagonal", "horizontal"):
+        for v in range(64):
+            cloud = synth.make_partial_view(joint, v, 4000)
+            kp = synth.uniform_sampling(cloud, 0.02)
+            lib.add_view(cloud, kp, p4)
+            n_desc += len(kp)
+    ctx.sync()
+    t_build = time.perf_counter() - t0
+    scene4 = synth.make_scene(("y", "diagonal", "horizontal"), 150000, scene_id=7)
+    kps4 = synth.uniform_sampling(scene4, 0.03)
+    t_gpu4, res4 = _timeit(lambda: lib.register_scene(scene4, kps4, p4, max_inst=98304), ctx.sync, 3, warm=1)
+    lib.close()
+    out["config4_view_library"] = {
+        "workload": "192 partial views (64 x Y/diagonal/horizontal, %d library descriptors) vs a 150000-pt scene "
+                    "(%d keypoints); scene normals + SHOT once, then per view: matching + GC grouping + poses"
+                    % (n_desc, len(kps4)),
+        "library_build_s_incl_host_synthesis": t_build, "registrations_per_s": 1.0 / t_gpu4,
+        "ms_per_scene_e2e": t_gpu4 * 1e3, "view_matches_per_s": 192.0 / t_gpu4, "instances": int(res4["n_instances"])}
+    return out
 
 
 def main():
@@ -489,6 +629,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blocking-sync", action="store_true", help="contexts sleep in host waits instead of spinning")
     ap.add_argument("--lanes", type=int, default=6, help="scenes in flight per GPU (context + stream + host thread each)")
+    ap.add_argument("--scenes-per-lane", type=int, default=8, help="a step = lanes x this many scene registrations per GPU")
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic scenes per rank, registered round-robin")
+    ap.add_argument("--other-configs", type=int, default=1,
+                    help="also measure BASELINE configs 1, 2 and 4 (small) and report them under other_configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner)
