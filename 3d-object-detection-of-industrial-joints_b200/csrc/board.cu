@@ -498,7 +498,7 @@ int dev_board_lrf(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const fl
   const size_t smem = (size_t)cap * 20;
   int rc = B200_OK;
   if (smem <= 160 * 1024) {
-    B200_CUDA(ctx, cudaFuncSetAttribute(board_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(ctx, ensure_dyn_smem(board_kernel, smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 4096)));
     const int grid = std::min(K, ctx->sm_count * per_sm);
     board_kernel<<<grid, BOARD_THREADS, smem, ctx->stream>>>(*g, d_normals, d_kp, K, (float)radius, r2, cap, nullptr, nullptr,

@@ -10,6 +10,8 @@
 #include <string>
 #include <array>
 #include <mutex>
+#include <map>
+#include <utility>
 #include <vector>
 #include <cstdio>
 #include <cstdlib>
@@ -65,8 +67,20 @@ struct b200_ctx {
       *err = cudaSuccess;
       return arena[best].p;
     }
+    // high-water cap: before growing past it, give the idle blocks back to the driver (a long-running service that
+    // sees scenes of very different sizes would otherwise keep every size class it ever needed)
+    static const size_t cap = []() {
+      const char *e = getenv("B200_ARENA_CAP_MB");
+      return (size_t)(e ? atoll(e) : 4096) << 20;
+    }();
+    if (arena_bytes + bytes > cap) arena_trim();
     void *p = nullptr;
     *err = cudaMalloc(&p, bytes);
+    if (*err == cudaErrorMemoryAllocation) {  // out of memory: release what is idle and retry once
+      cudaGetLastError();
+      arena_trim();
+      *err = cudaMalloc(&p, bytes);
+    }
     if (*err != cudaSuccess) return nullptr;
     arena.push_back({p, bytes, true});
     arena_bytes += bytes;
@@ -78,6 +92,18 @@ struct b200_ctx {
         b.used = false;
         return;
       }
+  }
+  void arena_trim() {  // frees every idle block (cudaFree synchronises the device: only on the growth path)
+    size_t w = 0;
+    for (size_t i = 0; i < arena.size(); ++i) {
+      if (arena[i].used) {
+        arena[w++] = arena[i];
+      } else {
+        cudaFree(arena[i].p);
+        arena_bytes -= arena[i].size;
+      }
+    }
+    arena.resize(w);
   }
   void arena_destroy() {
     for (auto &b : arena) cudaFree(b.p);
@@ -220,6 +246,23 @@ struct StageScope {
 };
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Opt-in dynamic shared memory of a kernel.  The attribute is per function and device, shared by every context
+// (lane) of the process: it only ever grows here, so a launch on another thread that asked for less stays valid
+// (setting it to each call's own size let one lane shrink it under another lane's launch).
+template <class F>
+static inline cudaError_t ensure_dyn_smem(F *func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> cur;  // (device, kernel) -> bytes granted so far
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  size_t &c = cur[std::make_pair(dev, reinterpret_cast<const void *>(func))];
+  if (bytes <= c) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) c = bytes;
+  return e;
+}
 
 // ------------------------------------------------------------------------------------------
 // Uniform grid over a search surface (grid.cu builds it).

@@ -172,7 +172,7 @@ int b200_desc_index_knn(b200_ctx *ctx, const b200_desc_index *ix, const float *q
   B200_CUDA(ctx, cudaMemcpyAsync(dq.p, queries, (size_t)nq * D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   const size_t smem = (size_t)D * sizeof(float);
   if (smem > 48 * 1024)
-    B200_CUDA(ctx, cudaFuncSetAttribute(desc_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(ctx, ensure_dyn_smem(desc_knn_kernel, smem));
   desc_knn_kernel<<<std::min(nq, ctx->sm_count * 8), DK_THREADS, smem, ctx->stream>>>(ix->desc.p, ix->valid.p, ix->K, D,
                                                                                      dq.p, nq, k, didx.p, dd2.p);
   B200_LAUNCHED(ctx);

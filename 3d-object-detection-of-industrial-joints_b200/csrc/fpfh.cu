@@ -314,8 +314,8 @@ int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
   DevBuf<int> gp;
   int grid1, grid2;
   if (in_smem) {
-    B200_CUDA(ctx, cudaFuncSetAttribute(spfh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA(ctx, cudaFuncSetAttribute(fpfh_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(ctx, ensure_dyn_smem(spfh_kernel, smem));
+    B200_CUDA(ctx, ensure_dyn_smem(fpfh_weight_kernel, smem));
     grid1 = std::min(std::max(nv, 1), ctx->sm_count * 8);
     grid2 = std::min(nq, ctx->sm_count * 8);
   } else {

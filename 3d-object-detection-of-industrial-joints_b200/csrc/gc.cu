@@ -1402,8 +1402,10 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   B200_CUDA(ctx, cudaMemsetAsync(d_inst_counts, 0, sizeof(int) * (size_t)max_inst, ctx->stream));
   if (C_cap <= 0) return B200_OK;
   // The consistency bitmap is C x C bits.  Up to GC_ASYNC_CAP correspondences it is sized for the
-  // capacity and the whole stage stays asynchronous; above that the actual count is read back first.
-  constexpr int GC_ASYNC_CAP = 131072;          // 2 GiB bitmap
+  // capacity and the whole stage stays asynchronous; above that the actual count is read back first, so that the
+  // bitmap follows the real number of correspondences (typically a quarter of the scene keypoints: 88 MB instead
+  // of 1.07 GB for the 91 k-keypoint scenes of the benchmark) at the price of one small readback per scene.
+  constexpr int GC_ASYNC_CAP = 32768;           // 128 MiB bitmap
   constexpr long long GC_MAX_C = 524288;        // 32 GiB bitmap
   int C_eff = C_cap;
   if (C_cap > GC_ASYNC_CAP) {
@@ -1463,7 +1465,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
     if (use_cluster) {
       // one 8-CTA cluster: a seed per CTA; shared memory = taken bitmap + candidate bitmap
       const size_t smem = 2 * row_bytes;
-      B200_CUDA(ctx, cudaFuncSetAttribute(gc_group_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B200_CUDA(ctx, ensure_dyn_smem(gc_group_cluster_kernel, smem));
       gc_group_cluster_kernel<<<GCL, GCL_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, gc_size, g_lo, g_hi, gc_threshold,
                                                                       max_inst);
       B200_LAUNCHED(ctx);
@@ -1472,7 +1474,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
       const size_t budget = 160 * 1024;
       if (2 * row_bytes > budget) return ctx->fail(B200_ERR_CAPACITY, "gc: too many correspondences for the grouping kernel");
       const size_t smem = std::min(budget, row_bytes * (size_t)(1 + GW));
-      B200_CUDA(ctx, cudaFuncSetAttribute(gc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B200_CUDA(ctx, ensure_dyn_smem(gc_group_kernel, smem));
       gc_group_kernel<<<1, GG_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, (int)smem, gc_size, g_lo, g_hi, gc_threshold,
                                                             max_inst);
       B200_LAUNCHED(ctx);

@@ -713,7 +713,7 @@ int tc_pass(b200_ctx *ctx, const float *d_model, int Km, const TcModelPrep &B, c
   p.cand_s = cand_s.p;
   p.cand_j = cand_j.p;
   p.rows_dev = rows_dev;
-  B200_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  B200_CUDA(ctx, ensure_dyn_smem(tc_filter_kernel, TC_SMEM));
   const int grid = std::min(ctx->sm_count, m_tiles * n_split);
   {
     StageScope st_(ctx, ST_MATCH_FILTER);
@@ -723,7 +723,7 @@ int tc_pass(b200_ctx *ctx, const float *d_model, int Km, const TcModelPrep &B, c
   const float eta = tc_eta(terms, Kp);
   const int rows_per_cta = RS_WARPS_PER_CTA * (32 / (n_split * TC_CAND));
   const size_t rs_smem = sizeof(RescoreSmem) * RS_WARPS_PER_CTA;
-  B200_CUDA(ctx, cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+  B200_CUDA(ctx, ensure_dyn_smem(tc_rescore_kernel, rs_smem));
   tc_rescore_kernel<<<ceil_div(Ks, rows_per_cta), RS_WARPS_PER_CTA * 32, rs_smem, ctx->stream>>>(
       d_model, Km, d_scene, Ks, D, svalid, n_split, cand_s.p, cand_j.p, na.p,
       reinterpret_cast<const float *>(B.bits.p + 1), scA, B.scaleB.p, eta, best, zero_cnt, fb_rows, fb_count,

@@ -576,7 +576,7 @@ int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_
     size_t smem;
     const int T = knn_threads_for(k, &smem);
     if (smem > ctx->smem_optin) return ctx->fail(B200_ERR_INVALID, "normals: k too large for shared memory");
-    B200_CUDA(ctx, cudaFuncSetAttribute(normals_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(ctx, ensure_dyn_smem(normals_knn_kernel, smem));
     StageScope st_(ctx, ST_NORMALS);
     if (q_is_surface) {
       // rows with non-finite coordinates are not in the grid: they keep NaN normals (PCL: is_dense=false)
@@ -600,13 +600,11 @@ int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_
           B200_TRY(stats.zero());
         }
         if (L == 1) {
-          B200_CUDA(ctx, cudaFuncSetAttribute(normals_knn_cell_kernel<1, 12>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          B200_CUDA(ctx, ensure_dyn_smem(normals_knn_cell_kernel<1, 12>, sm));
           normals_knn_cell_kernel<1, 12><<<blocks, NKC_WARPS * 32, sm, ctx->stream>>>(
               *g, c->n_valid, k, cap, vpx, vpy, vpz, out, want_stats ? stats.p : nullptr);
         } else {
-          B200_CUDA(ctx, cudaFuncSetAttribute(normals_knn_cell_kernel<2, 24>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          B200_CUDA(ctx, ensure_dyn_smem(normals_knn_cell_kernel<2, 24>, sm));
           normals_knn_cell_kernel<2, 24><<<blocks, NKC_WARPS * 32, sm, ctx->stream>>>(
               *g, c->n_valid, k, cap, vpx, vpy, vpz, out, want_stats ? stats.p : nullptr);
         }
@@ -650,7 +648,7 @@ int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_
   StageScope st_(ctx, ST_NORMALS);
   if (smem <= 96 * 1024) {
     B200_CUDA(ctx,
-              cudaFuncSetAttribute(normals_radius_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              ensure_dyn_smem(normals_radius_kernel, smem));
     const int grid = std::min(nq, ctx->sm_count * 8);
     normals_radius_kernel<<<grid, 128, smem, ctx->stream>>>(*g, d_q, nq, (float)radius, r2, cap, nullptr, nullptr, vpx,
                                                             vpy, vpz, out);

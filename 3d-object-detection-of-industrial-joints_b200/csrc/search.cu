@@ -100,7 +100,7 @@ int dev_knn_search(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, int 
   size_t smem;
   const int T = knn_threads_for(k, &smem);
   if (smem > ctx->smem_optin) return ctx->fail(B200_ERR_INVALID, "knn_search: k too large for shared memory");
-  B200_CUDA(ctx, cudaFuncSetAttribute(knn_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200_CUDA(ctx, ensure_dyn_smem(knn_search_kernel, smem));
   knn_search_kernel<<<ceil_div(nq, T), T, smem, ctx->stream>>>(*g, d_q, nq, k, d_idx, d_d2);
   B200_LAUNCHED(ctx);
   return B200_OK;
@@ -127,7 +127,7 @@ int dev_radius_fill_sized(b200_ctx *ctx, const GridView &g, const float4 *d_q, i
   const size_t smem = (size_t)cap * 12;
   const int grid = std::min(nq, ctx->sm_count * 8);
   if (smem <= 96 * 1024) {
-    B200_CUDA(ctx, cudaFuncSetAttribute(radius_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(ctx, ensure_dyn_smem(radius_fill_kernel, smem));
     radius_fill_kernel<<<grid, 128, smem, ctx->stream>>>(g, d_q, nq, (float)radius, r2, cap, nullptr, nullptr,
                                                          d_offsets, d_idx, d_d2);
     B200_LAUNCHED(ctx);

@@ -797,7 +797,7 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
     B200_TRY(work.alloc(ctx, 1));
     B200_TRY(work.zero());
     const size_t smem_w = sizeof(ShotWarpSmem) * SW_WARPS;
-    B200_CUDA(ctx, cudaFuncSetAttribute(shot_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    B200_CUDA(ctx, ensure_dyn_smem(shot_warp_kernel, smem_w));
     const int grid_w = std::min(ceil_div(K, SW_WARPS), ctx->sm_count * 3);
     shot_warp_kernel<<<grid_w, SW_THREADS, smem_w, ctx->stream>>>(*g, nrm_sorted.p, d_kp, counts.p, K, (float)radius,
                                                                  radius, r2, work.p, d_desc, d_rf, lrf_only ? 1 : 0);
@@ -809,7 +809,7 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
   const int cap = next_pow2_host(std::max(max_count, 32));
   const size_t smem = (size_t)cap * 12;
   if (smem <= 96 * 1024) {
-    B200_CUDA(ctx, cudaFuncSetAttribute(shot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(ctx, ensure_dyn_smem(shot_kernel, smem));
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 4096)));
     const int grid = std::min(K, ctx->sm_count * per_sm);
     shot_kernel<<<grid, SHOT_THREADS, smem, ctx->stream>>>(*g, nrm_sorted.p, d_kp, K, (float)radius, radius, r2, cap,

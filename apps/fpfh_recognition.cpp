@@ -96,6 +96,14 @@ int main(int argc, char **argv) {
   FILE *f = fopen((prefix + ".desc").c_str(), "wb");
   for (size_t i = 0; i < scene_descriptors->size(); ++i) fwrite(scene_descriptors->at(i).histogram, sizeof(float), 33, f);
   fclose(f);
+  // the normals the descriptors were computed from (stage-by-stage parity checks start from identical inputs)
+  f = fopen((prefix + ".normals").c_str(), "wb");
+  for (size_t i = 0; i < scene_normals->size(); ++i) {
+    const float n4[4] = {scene_normals->at(i).normal_x, scene_normals->at(i).normal_y, scene_normals->at(i).normal_z,
+                         scene_normals->at(i).curvature};
+    fwrite(n4, sizeof(float), 4, f);
+  }
+  fclose(f);
   f = fopen((prefix + ".corr").c_str(), "wb");
   if (!model_scene_corrs->empty()) fwrite(model_scene_corrs->data(), sizeof(pcl::Correspondence), model_scene_corrs->size(), f);
   fclose(f);

@@ -307,9 +307,15 @@ def run_b200(args, rank, world, local_rank):
             if world > 1:   # the path's one exchange: gather the correspondence lists (NCCL over NVLink)
                 gate.run(s, lambda: sharding.gather_correspondences(outs[lane]["corrs"], outs[lane]["n_corrs"]))
 
+    # warm-up: every lane meets each of the scenes it will see in the timed passes at least twice (its arena grows to
+    # the largest of them), then lane 0 walks the whole pool once for the single-lane pass
     gate.reset()
-    sharding.run_lanes(L, max(args.warmup, 3) * L, step)
+    sharding.run_lanes(L, max(args.warmup, 3, 2 * P) * L, step)
     torch.cuda.synchronize()
+    if world == 1:
+        for s in range(P):
+            step(0, s)
+        torch.cuda.synchronize()
 
     # ---- pass A, one lane: per-scene latency and the per-stage device times (roofline attribution) ----
     stream = streams[0]
@@ -556,7 +562,10 @@ def run_other_configs(ctx, binding, pkg, args):
         "descriptors_per_s": len(kps) / t_gpu, "registrations_per_s": 1.0 / t_gpu, "ms_per_scene_e2e": t_gpu * 1e3,
         "cpu": {"descriptors_per_s": len(kps) / t_cpu, "ms_per_scene": t_cpu * 1e3, "cores": orc.num_threads(),
                 "kind": "port", "measured": True, "matching": "serial loop (as the reference)"},
-        "same_result_as_cpu": bool(res["corrs"].tobytes() == c_cpu.tobytes() and res["n_instances"] == len(T_cpu)),
+        "same_correspondence_pairs_as_cpu": bool(
+            np.array_equal(res["corrs"]["index_query"], c_cpu["index_query"]) and
+            np.array_equal(res["corrs"]["index_match"], c_cpu["index_match"])),
+        "same_instance_count_as_cpu": bool(res["n_instances"] == len(T_cpu)),
         "correspondences": int(len(res["corrs"])), "instances": int(res["n_instances"])}
     # ---- config 2: FPFH_demo (FPFH_demo.cpp:416-428, 505-538): radius normals + FPFH33 on the keypoint cloud,
     # k = 2 ratio matching, GC grouping; radius 0.05 as BASELINE.json states

@@ -35,6 +35,37 @@ namespace {
 
 const float kNaNf = std::numeric_limits<float>::quiet_NaN();
 
+/* Sensitivity variants (oracle/sensitivity.py, tests): alternatives for the details of upstream PCL that this
+ * restatement could not pin (SURVEY.md Appendix A "[?]" items), plus +-epsilon perturbations of the discrete
+ * decisions, used to tell which outputs are stable.  0 = the restatement as documented. */
+unsigned g_variant = 0;
+enum {
+  V_DOT4 = 1,         /* Eigen 4-lane dot products: (x x' + z z') + (y y' + w w') instead of the sequential sum */
+  V_UMEYAMA_F32 = 2,  /* rigid fit from float32 moments (PCL's Matrix4f path) instead of float64 */
+  V_FPFH_SKIP = 4,    /* degenerate FPFH pairs do not vote (Appendix A) instead of voting with f = 0 */
+  V_FPFH_BIN_UP = 8,  /* FPFH f1 (atan2f) bin coordinate + 1e-6 / - 1e-6 before the floor */
+  V_FPFH_BIN_DOWN = 16,
+  V_ROOT_UP = 32,     /* eigen33: theta of the closed-form roots * (1 +- 2^-21) (libm atan2f / cosf / sinf ulps) */
+  V_ROOT_DOWN = 64,
+  V_SHOT_BIN_UP = 128,  /* SHOT: cosine-bin coordinate + 1e-6 / - 1e-6 before floor(x + 0.5) */
+  V_SHOT_BIN_DOWN = 256,
+  V_BOARD_ANGLE_UP = 512, /* BOARD: direction angle of a support point * (1 +- 2^-21) before the sector index (acosf ulps) */
+  V_BOARD_ANGLE_DOWN = 1024
+};
+
+/* float dot product of two 3-vectors the way the call site evaluates it */
+inline float vdot3f(const float *a, const float *b) {
+  if (g_variant & V_DOT4) return (a[0] * b[0] + a[2] * b[2]) + (a[1] * b[1] + 0.0f);
+  float s = a[0] * b[0];
+  s += a[1] * b[1];
+  s += a[2] * b[2];
+  return s;
+}
+inline double dot3d(const double *a, const double *b) {
+  if (g_variant & V_DOT4) return (a[0] * b[0] + a[2] * b[2]) + (a[1] * b[1] + 0.0);
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+
 inline bool finite3(const float *p) {
   return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]);
 }
@@ -284,6 +315,8 @@ inline void compute_roots(const float m[9], float roots[3]) {
     if (q > 0.0f) q = 0.0f;
     float rho = std::sqrt(-a_over_3);
     float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+    if (g_variant & V_ROOT_UP) theta *= 1.0f + 4.76837158e-7f;
+    if (g_variant & V_ROOT_DOWN) theta *= 1.0f - 4.76837158e-7f;
     float cos_theta = std::cos(theta);
     float sin_theta = std::sin(theta);
     roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
@@ -439,20 +472,43 @@ void eigh3_f64(const double A_in[9], double w[3], double V[9]) {
  * cross-covariance via the eigen-decomposition of S^T S; rotation R = U diag(1,1,det(U)det(V)) V^T. */
 void umeyama3(const double *src, const double *dst, int n, double T[16]) {
   double ms[3] = {0, 0, 0}, md[3] = {0, 0, 0};
-  for (int i = 0; i < n; ++i)
-    for (int a = 0; a < 3; ++a) {
-      ms[a] += src[i * 3 + a];
-      md[a] += dst[i * 3 + a];
-    }
-  for (int a = 0; a < 3; ++a) {
-    ms[a] /= n;
-    md[a] /= n;
-  }
   double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; /* sigma = dst_demean * src_demean^T / n */
-  for (int i = 0; i < n; ++i)
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) S[r * 3 + c] += (dst[i * 3 + r] - md[r]) * (src[i * 3 + c] - ms[c]);
-  for (int i = 0; i < 9; ++i) S[i] /= n;
+  if (g_variant & V_UMEYAMA_F32) {
+    /* float32 means and cross-covariance (what a Matrix<float, 3, Dynamic> umeyama accumulates); the
+     * decomposition below stays float64, standing in for a backward-stable float SVD */
+    float fs[3] = {0, 0, 0}, fd[3] = {0, 0, 0}, FS[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < 3; ++a) {
+        fs[a] += (float)src[i * 3 + a];
+        fd[a] += (float)dst[i * 3 + a];
+      }
+    for (int a = 0; a < 3; ++a) {
+      fs[a] /= (float)n;
+      fd[a] /= (float)n;
+    }
+    for (int i = 0; i < n; ++i)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) FS[r * 3 + c] += ((float)dst[i * 3 + r] - fd[r]) * ((float)src[i * 3 + c] - fs[c]);
+    for (int i = 0; i < 9; ++i) S[i] = FS[i] / (float)n;
+    for (int a = 0; a < 3; ++a) {
+      ms[a] = fs[a];
+      md[a] = fd[a];
+    }
+  } else {
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < 3; ++a) {
+        ms[a] += src[i * 3 + a];
+        md[a] += dst[i * 3 + a];
+      }
+    for (int a = 0; a < 3; ++a) {
+      ms[a] /= n;
+      md[a] /= n;
+    }
+    for (int i = 0; i < n; ++i)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) S[r * 3 + c] += (dst[i * 3 + r] - md[r]) * (src[i * 3 + c] - ms[c]);
+    for (int i = 0; i < 9; ++i) S[i] /= n;
+  }
   double StS[9];
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) {
@@ -518,6 +574,11 @@ void umeyama3(const double *src, const double *dst, int n, double T[16]) {
     for (int c = 0; c < 3; ++c) T[r * 4 + c] = R[r * 3 + c];
     T[r * 4 + 3] = md[r] - (R[r * 3 + 0] * ms[0] + R[r * 3 + 1] * ms[1] + R[r * 3 + 2] * ms[2]);
   }
+  if (g_variant & V_UMEYAMA_F32)
+    for (int r = 0; r < 3; ++r) {
+      const float fR[3] = {(float)R[r * 3 + 0], (float)R[r * 3 + 1], (float)R[r * 3 + 2]};
+      T[r * 4 + 3] = (float)md[r] - ((fR[0] * (float)ms[0] + fR[1] * (float)ms[1]) + fR[2] * (float)ms[2]);
+    }
   T[15] = 1;
 }
 
@@ -561,9 +622,9 @@ bool shot_local_rf(const float *surf, int sstride, const float *central, const s
   int plusNormal = 0, plusTangent = 0;
   for (int ne = 0; ne < valid; ++ne) {
     const double *v = &vij[(size_t)ne * 3];
-    double dp = v[0] * v1[0] + v[1] * v1[1] + v[2] * v1[2];
+    double dp = dot3d(v, v1);
     if (dp >= 0) plusTangent++;
-    dp = v[0] * v3[0] + v[1] * v3[1] + v[2] * v3[2];
+    dp = dot3d(v, v3);
     if (dp >= 0) plusNormal++;
   }
   auto disambiguate = [&](int plus, double *axis) {
@@ -573,7 +634,7 @@ bool shot_local_rf(const float *surf, int sstride, const float *central, const s
       int medianIndex = valid / 2;
       for (int i = -points / 2; i <= points / 2; i++) {
         const double *v = &vij[(size_t)(medianIndex - i) * 3];
-        if (v[0] * axis[0] + v[1] * axis[1] + v[2] * axis[2] > 0) plus++;
+        if (dot3d(v, axis) > 0) plus++;
       }
       if (plus < points / 2 + 1)
         for (int k = 0; k < 3; ++k) axis[k] *= -1;
@@ -619,9 +680,7 @@ void point_shot352(const float *surf, const float *normals, int sstride, const f
     const float *nrm = normals + (size_t)nb[i].idx * 4;
     if (!std::isfinite(nrm[0]) || !std::isfinite(nrm[1]) || !std::isfinite(nrm[2])) continue;
     /* createBinDistanceShape: float dot, widened */
-    float dotf = nrm[0] * fz[0];
-    dotf += nrm[1] * fz[1];
-    dotf += nrm[2] * fz[2];
+    float dotf = vdot3f(nrm, fz);
     double cosineDesc = dotf;
     if (cosineDesc > 1.0) cosineDesc = 1.0;
     if (cosineDesc < -1.0) cosineDesc = -1.0;
@@ -631,12 +690,7 @@ void point_shot352(const float *surf, const float *normals, int sstride, const f
     float delta[3] = {pt[0] - central[0], pt[1] - central[1], pt[2] - central[2]};
     double distance = std::sqrt((double)nb[i].d2);
     if (std::fabs(distance - 0.0) < 1E-15) continue;
-    auto dotd = [&](const float *f) {
-      float s = delta[0] * f[0];
-      s += delta[1] * f[1];
-      s += delta[2] * f[2];
-      return (double)s;
-    };
+    auto dotd = [&](const float *f) { return (double)vdot3f(delta, f); };
     double xInFeatRef = dotd(fx), yInFeatRef = dotd(fy), zInFeatRef = dotd(fz);
     if (std::fabs(yInFeatRef) < 1E-30) yInFeatRef = 0;
     if (std::fabs(xInFeatRef) < 1E-30) xInFeatRef = 0;
@@ -654,6 +708,8 @@ void point_shot352(const float *surf, const float *normals, int sstride, const f
     desc_index += zInFeatRef > 0 ? 1 : 0;
     desc_index += (distance > radius1_2) ? 2 : 0;
 
+    if (g_variant & V_SHOT_BIN_UP) binDistance += 1e-6;
+    if (g_variant & V_SHOT_BIN_DOWN) binDistance -= 1e-6;
     int step_index = (int)std::floor(binDistance + 0.5);
     int volume_index = desc_index * stride_b;
 
@@ -815,8 +871,13 @@ void point_spfh(const float *surf, const float *normals, int sstride, int p_idx,
   for (size_t i = 0; i < nb.size(); ++i) {
     if (nb[i].idx == p_idx) continue;
     float f1, f2, f3, f4;
-    pair_features(p, np, surf + (size_t)nb[i].idx * sstride, normals + (size_t)nb[i].idx * 4, f1, f2, f3, f4);
-    int h = clamp_bin(nb1 * ((f1 + M_PI) * d_pi), nb1);
+    const bool okp =
+        pair_features(p, np, surf + (size_t)nb[i].idx * sstride, normals + (size_t)nb[i].idx * 4, f1, f2, f3, f4);
+    if (!okp && (g_variant & V_FPFH_SKIP)) continue;
+    /* f1 comes out of atan2f (libm implementations differ by an ulp or two: 1e-6 in bin units covers 2 ulp at
+     * |f1| = pi); f2, f3 are plain float products and sums, identical everywhere */
+    const double be = (g_variant & V_FPFH_BIN_UP) ? 1e-6 : (g_variant & V_FPFH_BIN_DOWN) ? -1e-6 : 0.0;
+    int h = clamp_bin(nb1 * ((f1 + M_PI) * d_pi) + be, nb1);
     hist[h] += hist_incr;
     h = clamp_bin(nb1 * ((f2 + 1.0) * 0.5), nb1);
     hist[11 + h] += hist_incr;
@@ -1084,6 +1145,9 @@ void emit_instance(const float *model_kp, int mstride, const float *scene_kp, in
  * C API
  * ============================================================================================== */
 extern "C" {
+
+void orc_set_variant(unsigned v) { g_variant = v; }
+unsigned orc_get_variant(void) { return g_variant; }
 
 int orc_num_threads(void) {
 #ifdef _OPENMP
@@ -1889,7 +1953,9 @@ bool board_point_lrf(const float *surf, int sstride, const float *normals, const
     if (bp.find_holes) {
       float ind[3];
       directed_orthogonal_axis(z, c, surf + (size_t)e.idx * sstride, ind);
-      const float angle = angle_between_unit(x_axis, ind, z);
+      float angle = angle_between_unit(x_axis, ind, z);
+      if (g_variant & V_BOARD_ANGLE_UP) angle *= 1.0f + 4.76837158e-7f;
+      if (g_variant & V_BOARD_ANGLE_DOWN) angle *= 1.0f - 4.76837158e-7f;
       const int b = std::min((int)std::floor(angle / max_boundary_angle), S - 1);
       if (b >= 0) { /* a NaN angle (neighbour on the axis) indexes out of range in PCL; skipped here */
         check[b] = true;

@@ -112,6 +112,33 @@ def set_num_threads(n):
     lib().orc_set_num_threads(int(n))
 
 
+VARIANTS = {"dot4": 1, "umeyama_f32": 2, "fpfh_skip": 4, "fpfh_bin_up": 8, "fpfh_bin_down": 16, "root_up": 32,
+            "root_down": 64, "shot_bin_up": 128, "shot_bin_down": 256, "board_angle_up": 512, "board_angle_down": 1024}
+
+
+def set_variant(*names):
+    """Selects sensitivity variants of the restatement (see pcl_oracle.h); no argument = the documented one."""
+    mask = 0
+    for n in names:
+        mask |= VARIANTS[n]
+    lib().orc_set_variant.argtypes = [C.c_uint]
+    lib().orc_set_variant(mask)
+
+
+class variant:
+    """with orc.variant("dot4"): ...  — restores the documented restatement afterwards."""
+
+    def __init__(self, *names):
+        self.names = names
+
+    def __enter__(self):
+        set_variant(*self.names)
+
+    def __exit__(self, *exc):
+        set_variant()
+        return False
+
+
 def radius_search(surf, q, radius):
     surf, q = _pts(surf), _pts(q)
     off = np.zeros(len(q) + 1, dtype=np.int64)

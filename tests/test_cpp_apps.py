@@ -6,6 +6,8 @@ import os
 import subprocess
 
 import numpy as np
+
+import eps
 import pytest
 
 from conftest import PKG_NAME
@@ -72,9 +74,9 @@ def test_shot_recognition_app_matches_oracle(apps, orc, synth, tmp_path, mode):
     dm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, rad)
     ds, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, rad)
     oc = orc.match(dm, ds, 1, 0.25)
-    a = set(map(tuple, corr[["index_query", "index_match"]].tolist()))
-    b = set(map(tuple, oc[["index_query", "index_match"]].tolist()))
-    assert len(b) > 20 and len(a ^ b) <= max(2, 0.002 * len(b))
+    assert len(oc) > 20
+    # every entry that differs sits within the descriptor tolerance of the threshold or of a runner-up tie
+    print("app correspondences:", eps.corr_check(dm, ds, corr, oc, 0.25, label="app correspondences"))
     # grouping on the app's own correspondences is bit-exact against the oracle
     oT, oinst = orc.gc_recognize(kpm, kps, corr, float(np.float32(0.02)), 2, max_inst=len(corr))
     assert len(oT) == len(T) == len(inst)
@@ -96,11 +98,10 @@ def test_fpfh_recognition_app_matches_oracle(apps, orc, synth, tmp_path):
                         "0.02", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     desc = np.fromfile(prefix + ".desc", dtype=np.float32).reshape(-1, 33)
-    ref = orc.fpfh33(kps, orc.normals(kps, radius=0.05), 0.05)
-    assert np.array_equal(np.isnan(desc[:, 0]), np.isnan(ref[:, 0]))
-    ok = ~np.isnan(ref[:, 0])
-    rel = np.linalg.norm(desc[ok].astype(np.float64) - ref[ok], axis=1) / np.linalg.norm(ref[ok], axis=1)
-    assert rel.max() < 1e-4
+    # stage by stage, each from identical inputs, each with an absolute bar and its boundary cases shown (tests/eps.py)
+    nrm = np.fromfile(prefix + ".normals", dtype=np.float32).reshape(-1, 4)
+    print("app normals:", eps.normals_check(orc, nrm, kps, radius=0.05, label="app normals"))
+    print("app fpfh:", eps.fpfh_check(orc, desc, kps, nrm, 0.05, label="app fpfh"))
     corr = np.fromfile(prefix + ".corr", dtype=CORR)
     dm = orc.fpfh33(kpm, orc.normals(kpm, radius=0.05), 0.05)
     oc = orc.match(dm, desc, 2, 0.0)            # k = 2 ratio test on the app's own scene descriptors

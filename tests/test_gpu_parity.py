@@ -3,6 +3,8 @@ seeded inputs.  Bars (BASELINE.json north_star): neighbour index sets and corres
 bit-exact; descriptors within 1e-4 L2 per descriptor; poses within 1e-4 m and 0.01 degrees.
 """
 import numpy as np
+
+import eps
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -108,11 +110,12 @@ def test_normals_knn_parity(ctx, orc, small, k):
         ref = orc.normals(cloud_np, k=k)
         assert np.array_equal(np.isnan(got), np.isnan(ref))
         err = np.abs(got - ref)
-        # float32 covariance sums are bit-identical; only the libm calls in eigen33 differ by an ulp
-        assert np.nanmax(err[:, :3]) < 2e-4, np.nanmax(err[:, :3])
         assert np.nanmedian(err[:, :3]) < 1e-6
-        assert np.nanmax(err[:, 3]) < 2e-4
-        assert np.mean(np.all(err[:, :3] < 1e-5, axis=1)) > 0.995
+        # float32 covariance sums are bit-identical; only the libm calls in eigen33 differ by an ulp: every row
+        # whose eigenvector is stable under a 2-ulp perturbation of theta agrees to 1e-5, the ill-conditioned
+        # rest differs by no more than that perturbation explains (tests/eps.py)
+        st = eps.normals_check(orc, got, cloud_np, k=k, label="normals k=%d" % k)
+        print("normals k=%d: %s" % (k, st))
 
 
 def test_normals_radius_and_nan(ctx, orc, synth):
@@ -120,21 +123,17 @@ def test_normals_radius_and_nan(ctx, orc, synth):
     kp = synth.voxel_grid(scene, 0.03)
     cl = ctx.cloud(kp)
     got = ctx.normals(cl, radius=0.15)          # FPFH_demo.cpp:416-420: normals on the keypoints
-    ref = orc.normals(kp, radius=0.15)
-    assert np.array_equal(np.isnan(got), np.isnan(ref))
-    assert np.nanmax(np.abs(got - ref)) < 2e-4
+    eps.normals_check(orc, got, kp, radius=0.15, label="normals r=0.15")
     s = scene[:5000].copy()
     s[7] = np.nan
     cl2 = ctx.cloud(s)
     got = ctx.normals(cl2, k=10)
-    ref = orc.normals(s, k=10)
-    assert np.all(np.isnan(got[7])) and np.array_equal(np.isnan(got), np.isnan(ref))
-    assert np.nanmax(np.abs(got - ref)) < 2e-4
+    assert np.all(np.isnan(got[7]))
+    eps.normals_check(orc, got, s, k=10, label="normals with a NaN row")
     # explicit query cloud (input != surface) and a non-default viewpoint
     q = s[100:400]
     got = ctx.normals(cl2, q=q, k=15, viewpoint=(0.5, 0.5, 3.0))
-    ref = orc.normals(s, q=q, k=15, viewpoint=(0.5, 0.5, 3.0))
-    assert np.nanmax(np.abs(got - ref)) < 2e-4
+    eps.normals_check(orc, got, s, k=15, q=q, viewpoint=(0.5, 0.5, 3.0), label="normals, explicit queries")
     # Feature::initCompute: k and radius are exclusive
     with pytest.raises(Exception):
         ctx.normals(cl2, k=10, radius=0.1)
@@ -210,17 +209,15 @@ def test_fpfh_parity(ctx, orc, synth, small):
         ref = orc.fpfh33(kp, nrm, r)
         assert np.array_equal(np.isnan(got), np.isnan(ref))
         ok = ~np.isnan(ref[:, 0])
-        nrm_ref = np.linalg.norm(ref[ok], axis=1)
-        rel = np.linalg.norm(got[ok].astype(np.float64) - ref[ok], axis=1) / nrm_ref
-        # 1e-4 L2 relative to the descriptor norm (FPFH blocks sum to 100, |d| ~ 60..170)
-        assert rel.max() < 1e-4, rel.max()
+        # ABSOLUTE 1e-4 L2 per descriptor (north star) on every row no atan2f bin-border case can reach; the
+        # border rows differ by at most what their border cases move (tests/eps.py)
+        st = eps.fpfh_check(orc, got, kp, nrm, r, label="fpfh r=%g" % r)
+        print("fpfh r=%g: %s" % (r, st))
         np.testing.assert_allclose(got[ok].reshape(-1, 3, 11).sum(2), 100.0, atol=2e-3)
         # explicit query set (input != surface)
         got_q = ctx.fpfh33(cl, nrm, r, q=kp[::9])
         ref_q = orc.fpfh33(kp, nrm, r, q=kp[::9])
-        okq = ~np.isnan(ref_q[:, 0])
-        relq = np.linalg.norm(got_q[okq] - ref_q[okq], axis=1) / np.linalg.norm(ref_q[okq], axis=1)
-        assert relq.max() < 1e-4
+        eps.fpfh_check(orc, got_q, kp, nrm, r, q=kp[::9], label="fpfh queries r=%g" % r)
 
 
 # ------------------------------------------------------------------------------------------ matching
@@ -408,9 +405,9 @@ def test_register_scene_pipeline(ctx, orc, synth, b200):
     # descriptor distance sits within 1e-5 of the threshold / of the runner-up
     oc = orc.match(odm, ods, 1, 0.25)
     gc_ = res["corrs"]
-    same = set(map(tuple, gc_[["index_query", "index_match"]].tolist()))
-    osame = set(map(tuple, oc[["index_query", "index_match"]].tolist()))
-    assert len(same ^ osame) <= max(2, 0.002 * len(osame))
+    # every differing entry must sit within the descriptor tolerance of the threshold or of a runner-up tie
+    st = eps.corr_check(odm, ods, gc_, oc, 0.25, label="pipeline correspondences")
+    print("pipeline correspondences: %s" % st)
     # grouping parity on identical correspondences
     T, inst, n = ctx.gc_recognize(kpm, kps, gc_, 0.02, 2, max_inst=2048)
     assert n == res["n_instances"]
@@ -632,21 +629,37 @@ def test_icp_parity(ctx, orc, synth, small):
 # ------------------------------------------------------------------------------------------ BOARD
 def test_board_lrf_parity(ctx, orc, synth, small, b200):
     """BOARDLocalReferenceFrameEstimation (SHOT.cpp:441-453: find_holes, keypoints on the full cloud).  Same NaN rows;
-    frames within 1e-5 of the restatement except where a support direction sits within an ulp of a sector border
-    (acosf differs in the last bit between the device and glibc) — at most 0.5 % of the keypoints.  The rand()
-    stream continues across calls (model, then scene) like PCL's two compute() calls."""
+    frames within 1e-5 of the restatement on every keypoint whose frame does not change when the support directions'
+    angles are perturbed by 2 ulp (acosf differs in the last bit between the device and glibc, and an angle within
+    an ulp of a sector border then lands in the other sector) — the border cases are identified, not counted.  The
+    rand() stream continues across calls (model, then scene) like PCL's two compute() calls."""
     model, scene = small
     kpm, kps = synth.uniform_sampling(model, 0.02), synth.uniform_sampling(scene, 0.03)
     nm, ns = orc.normals(model, k=10), orc.normals(scene, k=10)
     cm, cs = ctx.cloud(model), ctx.cloud(scene)
 
-    def compare(a, b, allowed):
+    def compare(a, b, variants):
+        """variants: the restatement's frames under the +2 ulp / -2 ulp angle perturbation."""
         assert np.array_equal(np.isnan(a), np.isnan(b))
         ok = ~np.isnan(b[:, 0])
-        bad = np.abs(a[ok] - b[ok]).max(axis=1) > 1e-5
-        assert bad.mean() <= allowed, bad.mean()
+        stable = ok.copy()
+        for v in variants:
+            stable &= np.nan_to_num(np.abs(v - b)).max(axis=1) <= 1e-7
+        assert stable.sum() >= 0.98 * ok.sum(), (int(stable.sum()), int(ok.sum()))
+        err = np.abs(a - b).max(axis=1)
+        assert err[stable].max() <= 1e-5, float(err[stable].max())
+        print("BOARD: %d frames, %d stable under the 2-ulp angle perturbation (max err %.2e), %d border cases of which "
+              "%d differ" % (ok.sum(), stable.sum(), err[stable].max(), (ok & ~stable).sum(),
+                             (err[ok & ~stable] > 1e-5).sum()))
         f = a[ok].reshape(-1, 3, 3)
         assert np.abs(np.einsum("nij,nkj->nik", f, f) - np.eye(3)).max() < 1e-4
+
+    def oracle_variants(cloud, nrm, kp, r, **kw):
+        out = []
+        for name in ("board_angle_up", "board_angle_down"):
+            with orc.variant(name):
+                out.append(orc.board_lrf(cloud, nrm, kp, r, **kw)[0])
+        return out
 
     ctx.srand(1)
     a_m = ctx.board_lrf(cm, nm, kpm, 0.015)
@@ -654,8 +667,8 @@ def test_board_lrf_parity(ctx, orc, synth, small, b200):
     o_m, used = orc.board_lrf(model, nm, kpm, 0.015)
     o_s, used2 = orc.board_lrf(scene, ns, kps, 0.015, rand_skip=used)
     assert used > 0 and used2 > 0
-    compare(a_m, o_m, 0.005)
-    compare(a_s, o_s, 0.005)
+    compare(a_m, o_m, oracle_variants(model, nm, kpm, 0.015))
+    compare(a_s, o_s, oracle_variants(scene, ns, kps, 0.015, rand_skip=used))
     # reseeding reproduces the first call
     ctx.srand(1)
     assert np.array_equal(ctx.board_lrf(cm, nm, kpm, 0.015), a_m, equal_nan=True)
@@ -665,7 +678,7 @@ def test_board_lrf_parity(ctx, orc, synth, small, b200):
         ctx.srand(7)
         a = ctx.board_lrf(cs, ns, kps, r, b200.board_params(**kw))
         o, _ = orc.board_lrf(scene, ns, kps, r, orc.board_params(**kw), rand_seed=7)
-        compare(a, o, 0.005)
+        compare(a, o, oracle_variants(scene, ns, kps, r, params=orc.board_params(**kw), rand_seed=7))
     # NaN normals and a far keypoint
     ns2 = ns.copy()
     ns2[::7] = np.nan
