@@ -644,7 +644,7 @@ def test_board_lrf_parity(ctx, orc, synth, small, b200):
         ok = ~np.isnan(b[:, 0])
         stable = ok.copy()
         for v in variants:
-            stable &= np.nan_to_num(np.abs(v - b)).max(axis=1) <= 1e-7
+            stable &= np.nan_to_num(np.abs(v - b)).max(axis=1) <= 5e-6   # continuous effect of 2 ulp on the angles: ~3e-6
         assert stable.sum() >= 0.98 * ok.sum(), (int(stable.sum()), int(ok.sum()))
         err = np.abs(a - b).max(axis=1)
         assert err[stable].max() <= 1e-5, float(err[stable].max())
@@ -687,7 +687,7 @@ def test_board_lrf_parity(ctx, orc, synth, small, b200):
     a = ctx.board_lrf(cs, ns2, kp2, 0.02)
     o, _ = orc.board_lrf(scene, ns2, kp2, 0.02, rand_seed=3)
     assert np.isnan(a[-1]).all()
-    compare(a, o, 0.01)
+    compare(a, o, oracle_variants(scene, ns2, kp2, 0.02, rand_seed=3))
     cm.close()
     cs.close()
 
