@@ -26,7 +26,8 @@ EXPORTS = [
     "b200_model_create_shot", "b200_model_destroy", "b200_model_size", "b200_model_download",
     "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
     "b200_ctx_set_blocking_sync", "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
-    "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio", "b200_last_match_pass1_rows",
+    "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio", "b200_last_match_pass1_rows", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
+    "b200_comm_rank", "b200_comm_size", "b200_gather_correspondences", "b200_register_scene_shot_sharded",
     "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
@@ -124,6 +125,14 @@ def lib():
             "b200_ctx_stage_time": [vp, i, C.POINTER(d), ip],
             "b200_last_match_fallback": [vp, ip],
             "b200_last_match_pass1_rows": [vp, ip],
+            "b200_comm_unique_id": [vp, C.c_size_t],
+            "b200_comm_init": [vp, vp, i, i],
+            "b200_comm_destroy": [vp],
+            "b200_comm_rank": [vp],
+            "b200_comm_size": [vp],
+            "b200_gather_correspondences": [vp, vp, vp, i, vp, vp],
+            "b200_register_scene_shot_sharded": [vp, vp, i, fp, i, i, fp, i, i, C.POINTER(ShotParams), fp, ip,
+                                                 C.POINTER(Corr), i, ip, C.POINTER(Corr), ip],
             "b200_last_match_error_ratio": [vp, fp],
             "b200_desc_index_create": [vp, fp, i, i, C.POINTER(vp)],
             "b200_desc_index_destroy": [vp],
@@ -700,6 +709,48 @@ class Context:
         return {"transforms": T[:m].reshape(m, 4, 4), "instances": InstanceList(ic, off, m),
                 "n_instances": n_inst.value, "corrs": corrs[:n_corr.value], "truncated": rc == ERR_CAPACITY}
 
+    # ---- multi-GPU (the library's own NCCL communicator) -----------------------------------------
+    def comm_init(self, unique_id, rank, world):
+        """Collective over the `world` contexts sharing `unique_id` (bytes from comm_unique_id() on one rank)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(lib().b200_comm_init(self.h, buf, int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._chk(lib().b200_comm_destroy(self.h))
+
+    @property
+    def comm_rank(self):
+        return lib().b200_comm_rank(self.h)
+
+    @property
+    def comm_size(self):
+        return lib().b200_comm_size(self.h)
+
+    def register_scene_shot_sharded(self, model, params, scene_xyz=None, scene_kp=None, root=0):
+        """One scene over all ranks (b200_register_scene_shot_sharded).  Collective; the root passes the scene and
+        gets the result dict, the other ranks pass nothing and get None."""
+        is_root = self.comm_rank == root
+        if not is_root:
+            self._chk(lib().b200_register_scene_shot_sharded(self.h, model.h, int(root), None, 0, 3, None, 0, 3,
+                                                             C.byref(params), None, None, None, 0, None, None, None))
+            return None
+        scene_xyz, scene_kp = _pts(scene_xyz), _pts(scene_kp)
+        mi, Ks = params.max_instances, len(scene_kp)
+        T = np.empty((mi, 16), dtype=np.float32)
+        off = np.empty(mi + 1, dtype=np.int32)
+        ic = np.empty(max(Ks, 1), dtype=CORR_DTYPE)
+        corrs = np.empty(max(Ks, 1), dtype=CORR_DTYPE)
+        n_inst, n_corr = C.c_int(), C.c_int()
+        rc = lib().b200_register_scene_shot_sharded(
+            self.h, model.h, int(root), _f(scene_xyz), len(scene_xyz), scene_xyz.shape[1], _f(scene_kp), Ks,
+            scene_kp.shape[1], C.byref(params), _f(T), _i(off), _c(ic), max(Ks, 1), C.byref(n_inst), _c(corrs),
+            C.byref(n_corr))
+        if rc not in (OK, ERR_CAPACITY):
+            self._chk(rc)
+        m = min(n_inst.value, mi)
+        return {"transforms": T[:m].reshape(m, 4, 4), "instances": InstanceList(ic, off, m),
+                "n_instances": n_inst.value, "corrs": corrs[:n_corr.value], "truncated": rc == ERR_CAPACITY}
+
     def dev_register_scene_shot(self, model, d_xyz, n, stride, d_kp, Ks, kstride, params, out):
         """All buffers resident (torch CUDA tensors in `out`), asynchronous (b200_dev_register_scene_shot)."""
         self._chk(lib().b200_dev_register_scene_shot(
@@ -718,6 +769,15 @@ class Context:
     def dev_match(self, d_model, Km, d_scene, Ks, D, mode, thr, d_out, d_count):
         self._chk(lib().b200_dev_match(self.h, _dptr(d_model), int(Km), _dptr(d_scene), int(Ks), int(D), int(mode),
                                        float(thr), _dptr(d_out), _dptr(d_count)))
+
+
+def comm_unique_id():
+    """128-byte NCCL rendezvous token (b200_comm_unique_id): create on one rank, send to the others."""
+    buf = (C.c_char * 128)()
+    rc = lib().b200_comm_unique_id(buf, 128)
+    if rc != OK:
+        raise B200Error(rc, lib().b200_last_error(None).decode())
+    return bytes(buf)
 
 
 def register_scene_batch(model, scenes, keypoints, params, lanes=4, device=0):

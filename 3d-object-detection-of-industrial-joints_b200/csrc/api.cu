@@ -60,7 +60,7 @@ int write_small(b200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
 
 namespace {
 
-std::string g_error = "";
+thread_local std::string g_error = "";  // per thread: the batch API's lane threads write it too
 
 int set_device(b200_ctx *ctx) {
   cudaError_t e = cudaSetDevice(ctx->device);
@@ -252,6 +252,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     cudaEventDestroy(ev.b);
   }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  comm_destroy(ctx);
   ctx->arena_destroy();
   if (ctx->mt_state) cudaFree(ctx->mt_state);
   if (ctx->mailbox_host) cudaFreeHost(ctx->mailbox_host);
@@ -911,6 +912,135 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
     rc = download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, p->max_instances, cap, transforms, inst_offsets,
                             inst_corrs, corr_cap, n_inst);
     tr.tick("e2e download");
+  } while (0);
+  delete scene;
+  return rc;
+}
+
+/* ------------------------------------------------------------------ multi-GPU (comm.cu) */
+int b200_comm_unique_id(void *id128, size_t bytes) {
+  std::string err;
+  const int rc = comm_unique_id(id128, bytes, &err);
+  if (rc != B200_OK) g_error = err;
+  return rc;
+}
+
+int b200_comm_init(b200_ctx *ctx, const void *id128, int rank, int world) {
+  API_ENTER(ctx);
+  return comm_init(ctx, id128, rank, world);
+}
+
+int b200_comm_destroy(b200_ctx *ctx) {
+  API_ENTER(ctx);
+  return comm_destroy(ctx);
+}
+
+int b200_comm_rank(const b200_ctx *ctx) { return ctx ? ctx->comm_rank : 0; }
+int b200_comm_size(const b200_ctx *ctx) { return ctx ? ctx->comm_world : 1; }
+
+int b200_gather_correspondences(b200_ctx *ctx, const b200_corr *d_corrs, const int *d_count, int cap,
+                                b200_corr *d_gathered, int *d_counts) {
+  API_ENTER(ctx);
+  if (!d_corrs || !d_count || !d_gathered || !d_counts)
+    return ctx->fail(B200_ERR_INVALID, "gather_correspondences: null buffer");
+  return dev_gather_correspondences(ctx, d_corrs, d_count, cap, d_gathered, d_counts);
+}
+
+// One scene over all ranks of the communicator (north star: "scene keypoints are sharded across the GPUs, the model
+// library replicated, correspondences gathered with NCCL"; SURVEY.md 8(e) single-large-scene mode).  Collective:
+// every rank calls it; the scene and the outputs are the root's (other ranks may pass null buffers).
+//   root: upload -> broadcast xyz + keypoints (NCCL) -> every rank: grid + normals of the whole scene (replicated:
+//   1 M points cost about a millisecond) -> SHOT352 + correspondence search for the rank's contiguous keypoint slab
+//   [Ks r / G, Ks (r + 1) / G) -> all-gather of the slab lists -> root: concatenation in rank order (= ascending scene
+//   index, exactly the single-GPU list) -> grouping + RANSAC -> download.
+// Every per-keypoint / per-row computation is independent of the partition, so the result is the single-GPU one
+// bit for bit.
+int b200_register_scene_shot_sharded(b200_ctx *ctx, const b200_model *model, int root, const float *scene_xyz, int n,
+                                     int stride, const float *scene_kp, int Ks, int kstride, const b200_shot_params *p,
+                                     float *transforms, int *inst_offsets, b200_corr *inst_corrs, int corr_cap,
+                                     int *n_inst, b200_corr *corrs_out, int *n_corrs) {
+  API_ENTER(ctx);
+  const int G = ctx->comm_world, r = ctx->comm_rank;
+  if (!model || root < 0 || root >= G) return ctx->fail(B200_ERR_INVALID, "register_scene_sharded: bad arguments");
+  B200_TRY(check_params(ctx, p));
+  const bool is_root = r == root;
+  if (is_root && (!n_inst || Ks < 0 || n < 0)) return ctx->fail(B200_ERR_INVALID, "register_scene_sharded: bad arguments");
+  if (n_inst) *n_inst = 0;
+  if (n_corrs) *n_corrs = 0;
+  // sizes from the root
+  DevBuf<int> dh;
+  B200_TRY(dh.alloc(ctx, 4));
+  int hdr[4] = {n, Ks, 0, 0};
+  if (is_root) B200_TRY(write_small(ctx, dh.p, hdr, sizeof(hdr)));
+  B200_TRY(comm_broadcast(ctx, dh.p, sizeof(hdr), root));
+  if (!is_root) B200_TRY(readback_small(ctx, dh.p, hdr, sizeof(hdr)));
+  n = hdr[0];
+  Ks = hdr[1];
+  DevBuf<float4> raw, dkp;
+  if (is_root) {
+    B200_TRY(upload_points(ctx, scene_xyz, n, stride, raw));
+    B200_TRY(upload_points(ctx, scene_kp, Ks, kstride, dkp));
+  } else {
+    B200_TRY(raw.alloc(ctx, (size_t)std::max(n, 1)));
+    B200_TRY(dkp.alloc(ctx, (size_t)std::max(Ks, 1)));
+  }
+  B200_TRY(comm_broadcast(ctx, raw.p, (size_t)n * sizeof(float4), root));
+  B200_TRY(comm_broadcast(ctx, dkp.p, (size_t)Ks * sizeof(float4), root));
+  b200_cloud *scene = nullptr;
+  B200_TRY(cloud_upload(ctx, reinterpret_cast<const float *>(raw.p), n, 4, true, &scene));
+  int rc = B200_OK;
+  do {
+    const int k0 = (int)((long long)Ks * r / G), k1 = (int)((long long)Ks * (r + 1) / G);
+    const int slab = k1 - k0, cap = (Ks + G - 1) / G + 1;
+    DevBuf<float> normals, desc;
+    DevBuf<b200_corr> dslab, dall, dcorrs, dic;
+    DevBuf<int> dcnt, dcounts, doffs, dinstc, dn, dnc;
+    DevBuf<float> dT;
+    if ((rc = normals.alloc(ctx, (size_t)std::max(n, 1) * 4)) != B200_OK) break;
+    if ((rc = desc.alloc(ctx, (size_t)std::max(slab, 1) * 352)) != B200_OK) break;
+    if ((rc = dslab.alloc(ctx, (size_t)cap)) != B200_OK) break;
+    if ((rc = dall.alloc(ctx, (size_t)cap * G)) != B200_OK) break;
+    if ((rc = dcnt.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dcounts.alloc(ctx, (size_t)G)) != B200_OK) break;
+    if ((rc = dev_normals(ctx, scene, scene->raw.p, scene->n, true, p->normal_k, p->normal_radius, nullptr, normals.p)) !=
+        B200_OK)
+      break;
+    if ((rc = dev_shot(ctx, scene, normals.p, dkp.p + k0, slab, p->descr_radius, desc.p, nullptr, false)) != B200_OK) break;
+    if ((rc = dev_match(ctx, model->desc.p, model->K, desc.p, slab, 352, p->match_mode, p->match_thr, dslab.p, dcnt.p,
+                        &model->tc)) != B200_OK)
+      break;
+    if ((rc = dev_offset_scene_index(ctx, dslab.p, dcnt.p, cap, k0)) != B200_OK) break;
+    if ((rc = dev_gather_correspondences(ctx, dslab.p, dcnt.p, cap, dall.p, dcounts.p)) != B200_OK) break;
+    if (!is_root) {
+      cudaError_t e = ctx->sync();
+      if (e != cudaSuccess) rc = ctx->fail_cuda(e, "register_scene_sharded sync", __FILE__, __LINE__);
+      break;
+    }
+    const int ccap = std::max(Ks, 1), mi = p->max_instances;
+    if ((rc = dcorrs.alloc(ctx, (size_t)ccap)) != B200_OK) break;
+    if ((rc = dic.alloc(ctx, (size_t)ccap)) != B200_OK) break;
+    if ((rc = doffs.alloc(ctx, (size_t)mi + 1)) != B200_OK) break;
+    if ((rc = dinstc.alloc(ctx, (size_t)mi)) != B200_OK) break;
+    if ((rc = dn.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dnc.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dT.alloc(ctx, (size_t)mi * 16)) != B200_OK) break;
+    if ((rc = dev_concat_lists(ctx, dall.p, dcounts.p, G, cap, dcorrs.p, ccap, dnc.p)) != B200_OK) break;
+    if ((rc = dev_gc(ctx, model->kp.p, dkp.p, dcorrs.p, dnc.p, Ks, p->gc_size, p->gc_threshold, dT.p, mi, doffs.p,
+                     dinstc.p, dic.p, ccap, dn.p)) != B200_OK)
+      break;
+    int nc = 0;
+    if ((rc = download(ctx, &nc, dnc.p, 1)) != B200_OK) break;
+    cudaError_t e = ctx->sync();
+    if (e != cudaSuccess) {
+      rc = ctx->fail_cuda(e, "register_scene_sharded sync", __FILE__, __LINE__);
+      break;
+    }
+    if (n_corrs) *n_corrs = nc;
+    if (corrs_out && nc > 0) {
+      if ((rc = download(ctx, corrs_out, dcorrs.p, (size_t)nc)) != B200_OK) break;
+    }
+    rc = download_instances(ctx, dT.p, doffs.p, dinstc.p, dic.p, dn.p, mi, ccap, transforms, inst_offsets, inst_corrs,
+                            corr_cap, n_inst);
   } while (0);
   delete scene;
   return rc;

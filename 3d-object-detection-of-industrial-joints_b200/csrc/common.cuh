@@ -145,6 +145,8 @@ struct b200_ctx {
   int last_match_fallback = -1;  // rows the tensor-core filter could not certify (valid after a sync)
   int last_match_pass1_fail = -1;  // rows the one-term pass left to the three-term pass (profiling only)
   std::string err;
+  void *nccl_comm = nullptr;  // ncclComm_t once b200_comm_init has run (comm.cu)
+  int comm_rank = 0, comm_world = 1;
   void *pinned = nullptr;  // small pinned staging block for tiny readbacks
   unsigned *mt_state = nullptr;  // mt19937 state after seeding with 12345 and the first twist (gc.cu)
   int fail(int code, const char *msg) {
@@ -498,6 +500,17 @@ int dev_uniform_sampling(b200_ctx *ctx, const float *d_xyz, int n, int stride, f
                          int *d_out_index, int *d_count);
 int dev_voxel_grid(b200_ctx *ctx, const float *d_xyz, int n, int stride, float lx, float ly, float lz,
                    float *d_out_xyz, int *d_count);
+// comm.cu
+int comm_unique_id(void *id128, size_t bytes, std::string *err);
+int comm_init(b200_ctx *ctx, const void *id128, int rank, int world);
+int comm_destroy(b200_ctx *ctx);
+int comm_broadcast(b200_ctx *ctx, void *d_buf, size_t bytes, int root);
+int comm_allgather(b200_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank);
+int dev_gather_correspondences(b200_ctx *ctx, const b200_corr *d_corrs, const int *d_count, int cap,
+                               b200_corr *d_gathered, int *d_counts);
+int dev_concat_lists(b200_ctx *ctx, const b200_corr *d_gathered, const int *d_counts, int world, int cap,
+                     b200_corr *d_out, int out_cap, int *d_n_out);
+int dev_offset_scene_index(b200_ctx *ctx, b200_corr *d_corrs, const int *d_n, int cap, int offset);
 // gc.cu
 int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, const b200_corr *d_corrs,
            const int *d_C, int C_cap, double gc_size, int gc_threshold, float *d_T, int max_inst,

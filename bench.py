@@ -519,6 +519,82 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_sharded(args, rank, world, local_rank):
+    """Strong scaling of ONE scene stream (north star: "scene keypoints are sharded across the GPUs"): every step is
+    one b200_register_scene_shot_sharded call — the root holds the scene in pinned host memory, the library broadcasts
+    it over NCCL, every rank computes the normals and its keypoint slab's descriptors + correspondences, the lists are
+    gathered on the root, which groups them.  Total work is fixed as N grows.  Wall clock per call on the root
+    (host buffers in, host results out), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    binding = importlib.import_module(PKG + ".binding")
+    binding.lib()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = workload(0, args.scene_points, args.model_points)
+    p = binding.shot_params(**PARAMS)
+    ctx = binding.Context(local_rank)
+    if world > 1:   # the library's own communicator; torch.distributed only carries the 128-byte token
+        tok = [binding.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(tok, src=0)
+        ctx.comm_init(tok[0], rank, world)
+    model = ctx.model_create_shot(wl["model"], wl["model_kp"], p)
+    hs = torch.from_numpy(wl["scene"]).pin_memory().numpy()
+    hk = torch.from_numpy(wl["scene_kp"]).pin_memory().numpy()
+
+    def call():
+        if rank == 0:
+            return ctx.register_scene_shot_sharded(model, p, hs, hk, root=0)
+        return ctx.register_scene_shot_sharded(model, p, root=0)
+
+    for _ in range(max(args.warmup, 3)):
+        res = call()
+    single = ctx.register_scene_shot(model, hs, hk, p) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_begin = time.time()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = call()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    clocks = sampler.stop(t_begin, time.time())
+    if rank == 0:
+        same = (res["corrs"].tobytes() == single["corrs"].tobytes() and res["n_instances"] == single["n_instances"] and
+                np.array_equal(res["transforms"], single["transforms"]) and
+                all(a.tobytes() == b.tobytes() for a, b in zip(res["instances"], single["instances"])))
+        Ks = len(wl["scene_kp"])
+        _emit({"metric": METRIC, "mode": "sharded", "value": Ks * args.steps / dt, "unit": "descriptors/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32 (f64 for the SHOT frame/bin decisions)", "data": "synthetic",
+               "registrations_per_s": args.steps / dt,
+               "config": {"workload": "ONE %d-pt scene (%d keypoints) per step vs the %d-descriptor model, keypoint "
+                                      "slabs over %d GPU(s): b200_register_scene_shot_sharded, host buffers, one call in "
+                                      "flight" % (len(wl["scene"]), Ks, model.size, world),
+                          "l2": "inputs larger than L2 are re-uploaded and re-broadcast every step"},
+               "identical_to_single_gpu_result": bool(same), "correspondences": int(len(res["corrs"])),
+               "instances": int(res["n_instances"]), "clocks": clocks,
+               "e2e": {"value": Ks * args.steps / dt, "unit": "descriptors/s",
+                       "h2d_bytes_per_step": int(hs.nbytes + hk.nbytes),
+                       "d2h_bytes_per_step": int(12 * len(res["corrs"]) + 64 * res["n_instances"])}})
+    model.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _timeit(fn, sync, reps, warm=2):
     for _ in range(warm):
         fn()
@@ -632,6 +708,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
+                    help="batch: independent scenes per rank (weak scaling, the headline); sharded: one scene stream "
+                         "split over the ranks (strong scaling)")
     ap.add_argument("--scene-points", type=int, default=1_000_000)
     ap.add_argument("--model-points", type=int, default=50_000)
     ap.add_argument("--cpu-sample", type=int, default=1500, help="scene keypoints in the bounded CPU sample")
@@ -655,6 +734,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.mode == "sharded":
+        run_sharded(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 

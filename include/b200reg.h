@@ -339,6 +339,34 @@ B200_API int b200_register_scene_library(b200_ctx *ctx, const b200_library *lib,
                                          float *transforms, int *inst_view, int *inst_offsets, b200_corr *inst_corrs,
                                          int corr_cap, int max_inst, int *n_inst, int *view_n_corrs);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: one context per GPU, each driven by its own host thread or process; the context owns
+ * an NCCL communicator (NCCL is bound at run time: libnccl.so.2).  The reference's callbacks process one scene at a
+ * time (SHOT.cpp:204, per-keypoint SHOT at :360-371, the matching loop :409-423): the sharded call splits exactly
+ * those two loops over the GPUs.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* 128-byte rendezvous token (ncclUniqueId).  Call on one rank, hand the bytes to the others (pipe, file, MPI ...). */
+B200_API int b200_comm_unique_id(void *id128, size_t bytes);
+/* Collective over the `world` contexts that share the token. */
+B200_API int b200_comm_init(b200_ctx *ctx, const void *id128, int rank, int world);
+B200_API int b200_comm_destroy(b200_ctx *ctx);
+B200_API int b200_comm_rank(const b200_ctx *ctx);
+B200_API int b200_comm_size(const b200_ctx *ctx);
+/* Device buffers, asynchronous on the context's stream.  Every rank contributes *d_count (<= cap) correspondences;
+ * afterwards d_gathered holds rank r's list at [r * cap, r * cap + d_counts[r]) on every rank (multi-scene batches:
+ * gather of the lists of the scenes registered in this step). */
+B200_API int b200_gather_correspondences(b200_ctx *ctx, const b200_corr *d_corrs, const int *d_count, int cap,
+                                         b200_corr *d_gathered, int *d_counts);
+/* One scene over all ranks: keypoint slabs per rank, model library replicated, correspondence lists gathered on
+ * `root`, grouping + poses there.  Collective (every rank calls it with its own resident copy of the model);
+ * host buffers; the scene and the outputs are the root's, other ranks may pass NULL.  Same outputs as
+ * b200_register_scene_shot, bit for bit. */
+B200_API int b200_register_scene_shot_sharded(b200_ctx *ctx, const b200_model *model, int root, const float *scene_xyz,
+                                              int n, int stride, const float *scene_kp, int Ks, int kstride,
+                                              const b200_shot_params *p, float *transforms, int *inst_offsets,
+                                              b200_corr *inst_corrs, int corr_cap, int *n_inst, b200_corr *corrs_out,
+                                              int *n_corrs);
+
 /* Statistics of the last descriptor call on this context (for bench records): mean / max number of
  * radius neighbours per keypoint. */
 B200_API int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs);
