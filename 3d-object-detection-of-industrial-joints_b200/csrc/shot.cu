@@ -380,6 +380,97 @@ constexpr int SW_WARPS = 8;
 constexpr int SW_THREADS = SW_WARPS * 32;
 constexpr int SW_CAP = 2016;  // neighbours per keypoint held in shared memory (three CTAs of 8 warps fit one SM)
 
+// ---- local reference frame, pass 1: neighbour count + weighted covariance sums (shot_lrf.hpp getLocalRF) -----------
+// One keypoint per warp, straight over the candidate cells (no list): n = #{d2 < r2}, the number of neighbours
+// coinciding with the keypoint (PCL skips them), and the seven float64 sums  sum w v v^T (upper triangle), sum w  with
+// w = r - |v|.  This pass doubles as the neighbour count every descriptor call needs (list sizing, n-bar statistics).
+// The eigen-solve then runs one keypoint per THREAD (shot_eigen_kernel) instead of on one lane of a warp whose other
+// 31 lanes idle, and the descriptor kernel's instruction footprint shrinks by the float64 Jacobi code (the fused
+// kernel stalled on instruction fetch more than on anything else: 24 warps per SM in different phases of 64 KB of code).
+__global__ void __launch_bounds__(256)
+    shot_count_cov_kernel(GridView g, const float4 *__restrict__ kp, int K, float radius_f, double radius, float r2,
+                          int *__restrict__ counts, double *__restrict__ acc, unsigned long long *__restrict__ stats) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= K) return;
+  const float4 c = kp[i];
+  double part[7] = {0, 0, 0, 0, 0, 0, 0};
+  int n = 0, skipped = 0;
+  int x0, x1, y0, y1, z0, z1;
+  if (finite3(c.x, c.y, c.z) && g.n > 0 && ball_cell_range(g, c.x, c.y, c.z, radius_f, x0, x1, y0, y1, z0, z1)) {
+    const float4 *__restrict__ pts = g.pts;
+    const int *__restrict__ cs = g.cell_start;
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const int base = g.dx * (y + g.dy * z);
+        const int e = cs[base + x1 + 1];
+        for (int j = cs[base + x0] + lane; j < e; j += 32) {
+          const float4 p = pts[j];
+          const float d2 = sqdist3(c.x, c.y, c.z, p.x, p.y, p.z);
+          if (d2 < r2) {
+            ++n;
+            if (p.x == c.x && p.y == c.y && p.z == c.z) {
+              ++skipped;
+            } else {
+              const double vx = (double)(p.x - c.x), vy = (double)(p.y - c.y), vz = (double)(p.z - c.z);
+              const double w = radius - sqrt((double)d2);
+              part[0] += w * (vx * vx);
+              part[1] += w * (vx * vy);
+              part[2] += w * (vx * vz);
+              part[3] += w * (vy * vy);
+              part[4] += w * (vy * vz);
+              part[5] += w * (vz * vz);
+              part[6] += w;
+            }
+          }
+        }
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 7; ++a) part[a] = warp_sum(part[a]);
+  n = warp_sum(n);
+  skipped = warp_sum(skipped);
+  if (lane < 7) {
+    double v = part[0];
+#pragma unroll
+    for (int a = 1; a < 7; ++a)
+      if (lane == a) v = part[a];
+    acc[(size_t)i * 8 + lane] = v;
+  }
+  if (lane == 7) acc[(size_t)i * 8 + 7] = (double)skipped;
+  if (lane == 0) {
+    counts[i] = n;
+    if (stats) {
+      atomicMax(&stats[0], (unsigned long long)n);
+      atomicAdd(&stats[1], (unsigned long long)n);
+    }
+  }
+}
+
+// ---- pass 2: 3x3 eigen-solve, one keypoint per thread.  axes: x axis (largest eigenvalue) and z axis (smallest)
+// before the sign disambiguation, float64; flags: 1 = frame defined (>= 5 valid neighbours, finite eigenvalues) ----
+__global__ void shot_eigen_kernel(const int *__restrict__ counts, const double *__restrict__ acc, int K,
+                                  double *__restrict__ axes, int *__restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const double *s = acc + (size_t)i * 8;
+  const int valid = counts[i] - (int)s[7];
+  int ok = valid >= 5 ? 1 : 0;
+  double ax[6] = {0, 0, 0, 0, 0, 0};
+  if (ok) {
+    const double cov[9] = {s[0] / s[6], s[1] / s[6], s[2] / s[6], s[1] / s[6], s[3] / s[6],
+                           s[4] / s[6], s[2] / s[6], s[4] / s[6], s[5] / s[6]};
+    double w[3], V[9];
+    eigh3_f64(cov, w, V);
+    if (!isfinite(w[0]) || !isfinite(w[1]) || !isfinite(w[2])) ok = 0;
+    ax[0] = V[0 * 3 + 2], ax[1] = V[1 * 3 + 2], ax[2] = V[2 * 3 + 2];
+    ax[3] = V[0 * 3 + 0], ax[4] = V[1 * 3 + 0], ax[5] = V[2 * 3 + 0];
+  }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) axes[(size_t)i * 6 + a] = ax[a];
+  flags[i] = ok;
+}
+
 struct ShotWarpSmem {
   int pos[SW_CAP];     // position of the neighbour in the cell-ordered point array; its float32 squared
                        // distance (FLANN's L2_Simple value) is recomputed from the point when needed
@@ -389,7 +480,8 @@ struct ShotWarpSmem {
 
 __global__ void __launch_bounds__(SW_THREADS, 3)
     shot_warp_kernel(GridView g, const float4 *__restrict__ nrm, const float4 *__restrict__ kp,
-                     const int *__restrict__ counts, int K, float radius_f, double radius, float r2,
+                     const int *__restrict__ counts, const double *__restrict__ acc, const double *__restrict__ axes,
+                     const int *__restrict__ flags, int K, float radius_f, double radius, float r2,
                      int *__restrict__ work_counter, float *__restrict__ desc, float *__restrict__ rf_out,
                      int lrf_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -447,46 +539,13 @@ __global__ void __launch_bounds__(SW_THREADS, 3)
     for (int b = lane; b < SHOT_LEN; b += 32) sm.hist[b] = 0;
     __syncwarp();
 
-    // ---- local reference frame: weighted covariance (shot_lrf.hpp getLocalRF), float64 ----
-    double part[7] = {0, 0, 0, 0, 0, 0, 0};
-    int skipped = 0;
-    for (int j = lane; j < n; j += 32) {
-      const float4 p = pts[sm.pos[j]];
-      if (p.x == c.x && p.y == c.y && p.z == c.z) {
-        ++skipped;
-        continue;
-      }
-      const double vx = (double)(p.x - c.x), vy = (double)(p.y - c.y), vz = (double)(p.z - c.z);
-      const double w = radius - sqrt((double)sqdist3(c.x, c.y, c.z, p.x, p.y, p.z));
-      part[0] += w * (vx * vx);
-      part[1] += w * (vx * vy);
-      part[2] += w * (vx * vz);
-      part[3] += w * (vy * vy);
-      part[4] += w * (vy * vz);
-      part[5] += w * (vz * vz);
-      part[6] += w;
-    }
-#pragma unroll
-    for (int a = 0; a < 7; ++a) part[a] = warp_sum(part[a]);
-    const int n_skip = warp_sum(skipped);
+    // ---- local reference frame: covariance sums and eigenvectors come from the two passes above ----
+    const int n_skip = (int)acc[(size_t)i * 8 + 7];
     const int valid = n - n_skip;
-    int ok = (valid >= 5) ? 1 : 0;
-    double ax[6] = {0, 0, 0, 0, 0, 0};  // x axis (largest eigenvalue), z axis (smallest), before disambiguation
-    if (ok) {
-      if (lane == 0) {
-        const double *sacc = part;
-        double cov[9] = {sacc[0] / sacc[6], sacc[1] / sacc[6], sacc[2] / sacc[6], sacc[1] / sacc[6], sacc[3] / sacc[6],
-                         sacc[4] / sacc[6], sacc[2] / sacc[6], sacc[4] / sacc[6], sacc[5] / sacc[6]};
-        double w[3], V[9];
-        eigh3_f64(cov, w, V);
-        if (!isfinite(w[0]) || !isfinite(w[1]) || !isfinite(w[2])) ok = 0;
-        ax[0] = V[0 * 3 + 2], ax[1] = V[1 * 3 + 2], ax[2] = V[2 * 3 + 2];
-        ax[3] = V[0 * 3 + 0], ax[4] = V[1 * 3 + 0], ax[5] = V[2 * 3 + 0];
-      }
-      ok = __shfl_sync(0xffffffffu, ok, 0);
+    const int ok = flags[i];
+    double ax[6];  // x axis (largest eigenvalue), z axis (smallest), before disambiguation
 #pragma unroll
-      for (int a = 0; a < 6; ++a) ax[a] = __shfl_sync(0xffffffffu, ax[a], 0);
-    }
+    for (int a = 0; a < 6; ++a) ax[a] = axes[(size_t)i * 6 + a];
     float fr[9];
     if (ok) {
       // sign votes: v . axis >= 0 in float64; a float32 estimate settles the clear cases
@@ -768,12 +827,25 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
   if (K <= 0) return B200_OK;
   const GridView *g;
   B200_TRY(cloud_grid_for_radius(c, radius, &g));
-  // neighbour counts size the per-CTA list (and give the bench its n-bar)
-  DevBuf<int> counts;
+  // pass 1: neighbour counts (list sizing, the bench's n-bar) + the frames' covariance sums; pass 2: eigen-solves
+  DevBuf<int> counts, flags;
+  DevBuf<double> acc, axes;
   DevBuf<unsigned long long> stats;
   B200_TRY(counts.alloc(ctx, (size_t)K));
+  B200_TRY(flags.alloc(ctx, (size_t)K));
+  B200_TRY(acc.alloc(ctx, (size_t)K * 8));
+  B200_TRY(axes.alloc(ctx, (size_t)K * 6));
   B200_TRY(stats.alloc(ctx, 2));
-  B200_TRY(dev_radius_count(ctx, *g, d_kp, K, radius, counts.p, stats.p));
+  const float r2 = (float)(radius * radius);
+  {
+    StageScope stc_(ctx, ST_NBR_COUNT);
+    B200_CUDA(ctx, cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    shot_count_cov_kernel<<<ceil_div((long long)K * 32, 256), 256, 0, ctx->stream>>>(*g, d_kp, K, (float)radius, radius,
+                                                                                    r2, counts.p, acc.p, stats.p);
+    B200_LAUNCHED(ctx);
+    shot_eigen_kernel<<<ceil_div(K, 128), 128, 0, ctx->stream>>>(counts.p, acc.p, K, axes.p, flags.p);
+    B200_LAUNCHED(ctx);
+  }
   unsigned long long hstats[2];
   B200_TRY(readback_small(ctx, stats.p, hstats, sizeof(hstats)));
   const int max_count = (int)hstats[0];
@@ -790,7 +862,6 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
       B200_LAUNCHED(ctx);
     }
   }
-  const float r2 = (float)(radius * radius);
   // neighbourhoods up to SW_CAP points: one keypoint per warp, dynamic work distribution
   {
     DevBuf<int> work;
@@ -799,8 +870,9 @@ int dev_shot(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
     const size_t smem_w = sizeof(ShotWarpSmem) * SW_WARPS;
     B200_CUDA(ctx, ensure_dyn_smem(shot_warp_kernel, smem_w));
     const int grid_w = std::min(ceil_div(K, SW_WARPS), ctx->sm_count * 3);
-    shot_warp_kernel<<<grid_w, SW_THREADS, smem_w, ctx->stream>>>(*g, nrm_sorted.p, d_kp, counts.p, K, (float)radius,
-                                                                 radius, r2, work.p, d_desc, d_rf, lrf_only ? 1 : 0);
+    shot_warp_kernel<<<grid_w, SW_THREADS, smem_w, ctx->stream>>>(*g, nrm_sorted.p, d_kp, counts.p, acc.p, axes.p, flags.p,
+                                                                 K, (float)radius, radius, r2, work.p, d_desc, d_rf,
+                                                                 lrf_only ? 1 : 0);
     B200_LAUNCHED(ctx);
   }
   if (max_count <= SW_CAP) return B200_OK;
