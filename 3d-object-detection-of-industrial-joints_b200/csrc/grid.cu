@@ -255,9 +255,7 @@ int cloud_grid_for_knn(b200_cloud *c, int k, const GridView **out) {
     double area = std::max((double)ext[2] * (double)ext[1], 1e-12);
     // about k points per (flat-surface) cell: measured on the 1 M-point scene, k = 20: 0.5 k -> 1.95 ms, 0.7 k -> 1.42,
     // 1.0 k -> 1.35, 1.5 k -> 1.58, 3 k -> 1.89 (smaller cells need the second ring too often, larger ones scan more)
-    static const char *env_f = getenv("B200_KNN_CELL_FACTOR");
-    const double factor = env_f ? atof(env_f) : 1.0;
-    double target = std::max(2.0, factor * k);
+    double target = std::max(2.0, 1.0 * k);
     float cell = (float)sqrt(area * target / std::max(c->n_valid, 1));
     B200_TRY(build_grid(c, cell, c->knn_grid));
     c->knn_grid_k = k;
