@@ -53,7 +53,8 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;
 constexpr uint32_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ +
                              2 * TC_BN * 4 /*|b|^2 of the two accumulators' model tiles*/ +
-                             (TC_PARTS - 1) * TC_BM * TC_CAND * 8 /*candidate hand-over between the column parts*/;
+                             (TC_PARTS - 1) * TC_BM * TC_CAND * 8 /*candidate hand-over between the column parts*/ +
+                             (TC_PARTS - 1) * TC_BM * 4 /*... and their non-candidate bounds*/;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,7 +168,7 @@ __global__ void make_scale_kernel(const unsigned *__restrict__ absmax_bits, floa
 __global__ void tc_prep_kernel(const float *__restrict__ X, int rows, int rows_padded, int D, int Kp, int terms,
                                int is_b, const float *__restrict__ scale, const unsigned char *__restrict__ valid,
                                __half *__restrict__ out, float *__restrict__ norm2, unsigned *__restrict__ normmax_bits,
-                               const int *__restrict__ row_map, const int *__restrict__ n_rows_dev) {
+                               const int *__restrict__ row_map, const int *__restrict__ n_rows_dev, int perm_tiles) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= rows_padded) return;
@@ -176,8 +177,13 @@ __global__ void tc_prep_kernel(const float *__restrict__ X, int rows, int rows_p
     if (w >= *n_rows_dev) return;
     src = row_map[w];
   }
+  // model side: operand row w holds model row tc_unpermute(w) — consecutive operand rows (the 32-column chunks of the
+  // filter's epilogue) are 256 model rows apart.  Keypoints that are neighbours in space are neighbours in index and
+  // have similar descriptors: without this a row's best and runner-up often share a chunk, where only one of them
+  // can become a candidate.
+  if (perm_tiles) src = (w % perm_tiles) * TC_BN + w / perm_tiles;
   __half *o = out + (size_t)w * Kp;
-  const bool ok = (w < rows) && (valid == nullptr || valid[src]);
+  const bool ok = (src < rows) && (valid == nullptr || valid[src]);
   if (!ok) {
     for (int d = lane; d < Kp; d += 32) o[d] = __float2half_rn(0.f);
     if (lane == 0) norm2[w] = __int_as_float(0x7f800000);
@@ -218,6 +224,7 @@ struct TcParams {
   const float *scaleB;
   float *cand_s;       // [Ks][n_split * TC_CAND]
   int *cand_j;
+  float *cand_b;       // [Ks][n_split]: lower bound of every approximate value that is not a chunk minimum
   const int *rows_dev;  // nullable: the number of scene rows lives on the device (second pass), Ks is the capacity
 };
 
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   float *s_nb = reinterpret_cast<float *>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256);  // [2][TC_BN]
   float *s_hs = s_nb + 2 * TC_BN;  // [TC_PARTS - 1][TC_BM][TC_CAND] candidates of the column parts 1..
   int *s_hj = reinterpret_cast<int *>(s_hs + (TC_PARTS - 1) * TC_BM * TC_CAND);
+  float *s_hb = reinterpret_cast<float *>(s_hj + (TC_PARTS - 1) * TC_BM * TC_CAND);  // [TC_PARTS - 1][TC_BM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int nt0 = sp * tiles_per_split, nt1 = min(p.n_tiles, nt0 + tiles_per_split);
       float cs[TC_CAND];
       int cj[TC_CAND];
+      float bnd = __int_as_float(0x7f800000);  // smallest second-in-chunk value seen
 #pragma unroll
       for (int t = 0; t < TC_CAND; ++t) {
         cs[t] = __int_as_float(0x7f800000);
@@ -366,36 +375,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int c0 = col_lo; c0 < col_lo + TC_BN / TC_PARTS; c0 += 32) {
           float v[32];
           tmem_ld32(t_addr + (uint32_t)c0, v);
-          // s = |b|^2 - 2 a.b for 32 model rows; a row rarely has anything below its current cut
-          float gmin = __int_as_float(0x7f800000);
+          // s = |b|^2 - 2 a.b for the chunk's 32 model rows.  Only the chunk's MINIMUM competes for the row's
+          // candidate list (one insertion attempt per chunk instead of one per element: with 32 independent rows per
+          // warp some lane inserted at almost every element and the whole warp walked the insertion code); the chunk's
+          // SECOND smallest value bounds everything else in the chunk from below and goes into the row's
+          // non-candidate bound.  The column (5 bits) rides in the low mantissa bits of the value, so minimum and
+          // arg-min are one FMNMX chain; the perturbation (<= 31 ulp) is part of the certificate's error budget.
+          float m1 = __int_as_float(0x7f800000), m2 = m1;
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const float4 nb4 = *reinterpret_cast<const float4 *>(snb + c0 + e);
-            v[e] = fmaf(m2inv, v[e], nb4.x);
-            v[e + 1] = fmaf(m2inv, v[e + 1], nb4.y);
-            v[e + 2] = fmaf(m2inv, v[e + 2], nb4.z);
-            v[e + 3] = fmaf(m2inv, v[e + 3], nb4.w);
-            gmin = fminf(gmin, fminf(fminf(v[e], v[e + 1]), fminf(v[e + 2], v[e + 3])));
-          }
-          if (gmin < cs[TC_CAND - 1]) {
+            const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float s = v[e];
-              if (s < cs[TC_CAND - 1]) {
-                cs[TC_CAND - 1] = s;
-                cj[TC_CAND - 1] = n0 + c0 + e;
-#pragma unroll
-                for (int t = TC_CAND - 1; t > 0; --t)
-                  if (cs[t] < cs[t - 1]) {
-                    const float ts = cs[t];
-                    cs[t] = cs[t - 1];
-                    cs[t - 1] = ts;
-                    const int tj = cj[t];
-                    cj[t] = cj[t - 1];
-                    cj[t - 1] = tj;
-                  }
-              }
+            for (int q = 0; q < 4; ++q) {
+              const float x = fminf(fmaf(m2inv, v[e + q], nbv[q]), 3.0e38f);  // +inf (padding) would turn into NaN below
+              const float xb = __uint_as_float((__float_as_uint(x) & ~31u) | (unsigned)(e + q));
+              m2 = fminf(m2, fmaxf(m1, xb));
+              m1 = fminf(m1, xb);
             }
+          }
+          bnd = fminf(bnd, m2);
+          if (m1 < cs[TC_CAND - 1]) {
+            cs[TC_CAND - 1] = m1;
+            cj[TC_CAND - 1] = n0 + c0 + (int)(__float_as_uint(m1) & 31u);
+#pragma unroll
+            for (int t = TC_CAND - 1; t > 0; --t)
+              if (cs[t] < cs[t - 1]) {
+                const float ts = cs[t];
+                cs[t] = cs[t - 1];
+                cs[t - 1] = ts;
+                const int tj = cj[t];
+                cj[t] = cj[t - 1];
+                cj[t - 1] = tj;
+              }
           }
         }
         tc_fence_before();
@@ -412,9 +424,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           s_hs[((half - 1) * TC_BM + row_in_tile) * TC_CAND + t] = cs[t];
           s_hj[((half - 1) * TC_BM + row_in_tile) * TC_CAND + t] = cj[t];
         }
+        s_hb[(half - 1) * TC_BM + row_in_tile] = bnd;
       }
       asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory");
       if (half == 0) {
+#pragma unroll
+        for (int u = 0; u < TC_PARTS - 1; ++u) bnd = fminf(bnd, s_hb[u * TC_BM + row_in_tile]);
 #pragma unroll 1
         for (int u = 0; u < (TC_PARTS - 1) * TC_CAND; ++u) {
           const int o = ((u / TC_CAND) * TC_BM + row_in_tile) * TC_CAND + (u % TC_CAND);
@@ -445,6 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           os[t] = cs[t];
           oj[t] = cj[t];
         }
+        p.cand_b[(size_t)row * p.n_split + sp] = bnd;
       }
     }
   }
@@ -473,12 +489,12 @@ struct RescoreSmem {
 __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
     tc_rescore_kernel(const float *__restrict__ model, int Km, const float *__restrict__ scene, int Ks, int D,
                       const unsigned char *__restrict__ svalid, int n_split, const float *__restrict__ cand_s,
-                      const int *__restrict__ cand_j, const float *__restrict__ na,
+                      const int *__restrict__ cand_j, const float *__restrict__ cand_b, const float *__restrict__ na,
                       const float *__restrict__ normmaxB, const float *__restrict__ scaleA,
                       const float *__restrict__ scaleB, float eta, unsigned long long *__restrict__ best,
                       int *__restrict__ zero_cnt, int *__restrict__ fb_rows, int *__restrict__ fb_count,
                       unsigned *__restrict__ err_ratio_bits, const int *__restrict__ row_map,
-                      const int *__restrict__ n_rows_dev) {
+                      const int *__restrict__ n_rows_dev, int n_tiles) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RescoreSmem &sm = reinterpret_cast<RescoreSmem *>(rs_raw)[warp];
@@ -497,16 +513,21 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
   // fp16 flush of tiny elements: absolute 2^-25 per element of the scaled operand (2^-(25+10) of the largest
   // element), against a vector of at most sqrt(D) |b| in the 1-norm; both operands, times two for -2 a.b
   const float c_sub = 1.2e-10f * sqrtf((float)D);
+  // the filter keeps the column index in the 5 low mantissa bits of s: <= 31 ulp of |s| <= |b|^2 + 2 |a||b|
+  const float c_pay = 4e-6f;
   int j = -1;
   float s = __int_as_float(0x7f800000);
   if (row_ok) {
     j = cand_j[(size_t)ci * nc + c];
+    if (j >= 0) j = (j % n_tiles) * TC_BN + j / n_tiles;  // operand row -> model row (see tc_prep_kernel)
     s = cand_s[(size_t)ci * nc + c];
   }
   bool pair_ok = row_ok && j >= 0 && j < Km;
   // s_cut: every model row that is not a candidate has approximate s >= the worst kept value of its split
   float s_cut = __int_as_float(0x7f800000);
-  if (row_ok && (c % TC_CAND) == TC_CAND - 1) s_cut = s;
+  // ... a value that was its 32-column chunk's minimum but not kept is >= the split's worst kept one; any other value
+  // is >= its chunk's second smallest, whose minimum over the split the filter recorded (cand_b)
+  if (row_ok && (c % TC_CAND) == TC_CAND - 1) s_cut = fminf(s, cand_b[(size_t)ci * n_split + c / TC_CAND]);
   for (int o = nc >> 1; o > 0; o >>= 1) s_cut = fminf(s_cut, __shfl_xor_sync(0xffffffffu, s_cut, o));
 
   // Prune: a candidate whose approximate value exceeds the row's smallest one by more than twice the error bound
@@ -519,7 +540,8 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
       const float nai = na[ci], nbm = normmaxB[0];
       const float d_lo = fmaxf(nai + s_min, 0.0f);
       const float e = 2.0f * eta * sqrtf(nai * nbm) + c_sum * (nai + nbm + d_lo + 4.0f * eta * sqrtf(nai * nbm)) +
-                      c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+                      c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) +
+                      c_pay * (nbm + 2.0f * sqrtf(nai * nbm)) + 1e-30f;
       pair_ok = s <= s_min + 2.0f * e;
     }
   }
@@ -557,7 +579,8 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
       // assumes (statistic for the tests: must stay well below 1)
       const float nai = na[ci], nbm = normmaxB[0];
       const float eps = 2.0f * eta * sqrtf(nai * nbm) + c_sum * (nai + nbm + acc) +
-                        c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+                        c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) +
+                        c_pay * (nbm + 2.0f * sqrtf(nai * nbm)) + 1e-30f;
       const float ratio = fabsf((nai + s) - acc) / eps;
       if (ratio == ratio) atomicMax(err_ratio_bits, __float_as_uint(ratio));
     }
@@ -579,7 +602,8 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
         // |s_approx - s_real| <= 2*eta*|a||b| (tc_eta); float32 sequential sums and norms: (D + 8) 2^-23 relative;
         // fp16 flush of tiny elements: c_sub
         const float eps = 2.0f * eta * sqrtf(nai * nbm) + c_sum * (nai + nbm + best_d2) +
-                          c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) + 1e-30f;
+                          c_sub * (scaleA[1] * sqrtf(nbm) + scaleB[1] * sqrtf(nai)) +
+                          c_pay * (nbm + 2.0f * sqrtf(nai * nbm)) + 1e-30f;
         certified = best_d2 < (nai + s_cut) - eps;
       }
     }
@@ -663,7 +687,8 @@ int match_tc_prepare_model(b200_ctx *ctx, const float *d_model, int Km, int D, c
   for (int terms = 1; terms <= 3; terms += 2) {
     tc_prep_kernel<<<ceil_div((long long)rowsB * 32, 256), 256, 0, ctx->stream>>>(
         d_model, Km, rowsB, D, tc_kp(terms, D), terms, 1, out->scaleB.p, mvalid,
-        reinterpret_cast<__half *>(terms == 1 ? out->B1.p : out->B3.p), out->nb.p, out->bits.p + 1, nullptr, nullptr);
+        reinterpret_cast<__half *>(terms == 1 ? out->B1.p : out->B3.p), out->nb.p, out->bits.p + 1, nullptr, nullptr,
+        n_tiles);
     B200_LAUNCHED(ctx);
   }
   out->ready = true;
@@ -688,14 +713,15 @@ int tc_pass(b200_ctx *ctx, const float *d_model, int Km, const TcModelPrep &B, c
     while (n_split < TC_MAX_SPLIT && m_tiles * n_split < ctx->sm_count && n_split * 2 <= n_tiles) n_split *= 2;
   }
   DevBuf<__half> A16;
-  DevBuf<float> na, cand_s;
+  DevBuf<float> na, cand_s, cand_b;
   DevBuf<int> cand_j;
   B200_TRY(A16.alloc(ctx, (size_t)rowsA * Kp));
   B200_TRY(na.alloc(ctx, (size_t)rowsA));
   B200_TRY(cand_s.alloc(ctx, (size_t)Ks * n_split * TC_CAND));
   B200_TRY(cand_j.alloc(ctx, (size_t)Ks * n_split * TC_CAND));
+  B200_TRY(cand_b.alloc(ctx, (size_t)Ks * n_split));
   tc_prep_kernel<<<ceil_div((long long)(rows_dev ? Ks : rowsA) * 32, 256), 256, 0, ctx->stream>>>(
-      d_scene, Ks, rows_dev ? Ks : rowsA, D, Kp, terms, 0, scA, nullptr, A16.p, na.p, nullptr, row_map, rows_dev);
+      d_scene, Ks, rows_dev ? Ks : rowsA, D, Kp, terms, 0, scA, nullptr, A16.p, na.p, nullptr, row_map, rows_dev, 0);
   B200_LAUNCHED(ctx);
   CUtensorMap mapA, mapB;
   B200_TRY(make_map(ctx, &mapA, A16.p, rowsA, Kp, TC_BM));
@@ -712,6 +738,7 @@ int tc_pass(b200_ctx *ctx, const float *d_model, int Km, const TcModelPrep &B, c
   p.scaleB = B.scaleB.p;
   p.cand_s = cand_s.p;
   p.cand_j = cand_j.p;
+  p.cand_b = cand_b.p;
   p.rows_dev = rows_dev;
   B200_CUDA(ctx, ensure_dyn_smem(tc_filter_kernel, TC_SMEM));
   const int grid = std::min(ctx->sm_count, m_tiles * n_split);
@@ -725,9 +752,9 @@ int tc_pass(b200_ctx *ctx, const float *d_model, int Km, const TcModelPrep &B, c
   const size_t rs_smem = sizeof(RescoreSmem) * RS_WARPS_PER_CTA;
   B200_CUDA(ctx, ensure_dyn_smem(tc_rescore_kernel, rs_smem));
   tc_rescore_kernel<<<ceil_div(Ks, rows_per_cta), RS_WARPS_PER_CTA * 32, rs_smem, ctx->stream>>>(
-      d_model, Km, d_scene, Ks, D, svalid, n_split, cand_s.p, cand_j.p, na.p,
+      d_model, Km, d_scene, Ks, D, svalid, n_split, cand_s.p, cand_j.p, cand_b.p, na.p,
       reinterpret_cast<const float *>(B.bits.p + 1), scA, B.scaleB.p, eta, best, zero_cnt, fb_rows, fb_count,
-      err_bits, row_map, rows_dev);
+      err_bits, row_map, rows_dev, n_tiles);
   B200_LAUNCHED(ctx);
   return B200_OK;
 }
