@@ -27,7 +27,8 @@ EXPORTS = [
     "b200_register_scene_shot", "b200_dev_register_scene_shot", "b200_last_neighbor_stats",
     "b200_ctx_set_blocking_sync", "b200_ctx_set_profiling", "b200_ctx_reset_profiling", "b200_ctx_stage_count", "b200_ctx_stage_name",
     "b200_ctx_stage_time", "b200_last_match_fallback", "b200_last_match_error_ratio", "b200_last_match_pass1_rows", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
-    "b200_comm_rank", "b200_comm_size", "b200_gather_correspondences", "b200_register_scene_shot_sharded",
+    "b200_comm_rank", "b200_comm_size", "b200_model_create_fpfh", "b200_model_descriptor_length",
+    "b200_register_scene_fpfh", "b200_gather_correspondences", "b200_register_scene_shot_sharded",
     "b200_desc_index_create", "b200_desc_index_destroy", "b200_desc_index_size", "b200_desc_index_knn",
     "b200_uniform_sampling", "b200_dev_uniform_sampling", "b200_voxel_grid", "b200_dev_voxel_grid",
     "b200_library_create", "b200_library_destroy", "b200_library_add_view", "b200_library_views",
@@ -125,6 +126,10 @@ def lib():
             "b200_ctx_stage_time": [vp, i, C.POINTER(d), ip],
             "b200_last_match_fallback": [vp, ip],
             "b200_last_match_pass1_rows": [vp, ip],
+            "b200_model_create_fpfh": [vp, fp, i, i, C.POINTER(ShotParams), C.POINTER(vp)],
+            "b200_model_descriptor_length": [vp],
+            "b200_register_scene_fpfh": [vp, vp, fp, i, i, C.POINTER(ShotParams), fp, ip, C.POINTER(Corr), i, ip,
+                                         C.POINTER(Corr), ip, fp],
             "b200_comm_unique_id": [vp, C.c_size_t],
             "b200_comm_init": [vp, vp, i, i],
             "b200_comm_destroy": [vp],
@@ -264,7 +269,7 @@ class Model:
 
     def download(self):
         K = self.size
-        desc = np.zeros((K, 352), dtype=np.float32)
+        desc = np.zeros((K, lib().b200_model_descriptor_length(self.h)), dtype=np.float32)
         kp = np.zeros((K, 3), dtype=np.float32)
         self.ctx._chk(lib().b200_model_download(self.ctx.h, self.h, _f(desc), _f(kp)))
         return desc, kp
@@ -708,6 +713,34 @@ class Context:
                           % (n_inst.value, m, lib().b200_last_error(self.h).decode()), RuntimeWarning, stacklevel=2)
         return {"transforms": T[:m].reshape(m, 4, 4), "instances": InstanceList(ic, off, m),
                 "n_instances": n_inst.value, "corrs": corrs[:n_corr.value], "truncated": rc == ERR_CAPACITY}
+
+    # ---- resident FPFH pipeline (FPFH_demo.cpp:405-538) -------------------------------------------
+    def model_create_fpfh(self, kp, params):
+        kp = _pts(kp)
+        h = C.c_void_p()
+        self._chk(lib().b200_model_create_fpfh(self.h, _f(kp), len(kp), kp.shape[1], C.byref(params), C.byref(h)))
+        return Model(self, h)
+
+    def register_scene_fpfh(self, model, scene_kp, params, want_desc=False):
+        scene_kp = _pts(scene_kp)
+        mi, Ks = params.max_instances, len(scene_kp)
+        T = np.empty((mi, 16), dtype=np.float32)
+        off = np.empty(mi + 1, dtype=np.int32)
+        ic = np.empty(max(Ks, 1), dtype=CORR_DTYPE)
+        corrs = np.empty(max(Ks, 1), dtype=CORR_DTYPE)
+        desc = np.empty((max(Ks, 1), 33), dtype=np.float32) if want_desc else None
+        n_inst, n_corr = C.c_int(), C.c_int()
+        rc = lib().b200_register_scene_fpfh(self.h, model.h, _f(scene_kp), Ks, scene_kp.shape[1], C.byref(params), _f(T),
+                                            _i(off), _c(ic), max(Ks, 1), C.byref(n_inst), _c(corrs), C.byref(n_corr),
+                                            _f(desc) if want_desc else None)
+        if rc not in (OK, ERR_CAPACITY):
+            self._chk(rc)
+        m = min(n_inst.value, mi)
+        out = {"transforms": T[:m].reshape(m, 4, 4), "instances": InstanceList(ic, off, m),
+               "n_instances": n_inst.value, "corrs": corrs[:n_corr.value], "truncated": rc == ERR_CAPACITY}
+        if want_desc:
+            out["desc"] = desc[:Ks]
+        return out
 
     # ---- multi-GPU (the library's own NCCL communicator) -----------------------------------------
     def comm_init(self, unique_id, rank, world):

@@ -7,6 +7,7 @@
 #include <string>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <vector>
 
@@ -832,7 +833,7 @@ int b200_model_size(const b200_model *m) { return m ? m->K : 0; }
 int b200_model_download(b200_ctx *ctx, const b200_model *m, float *desc, float *kp) {
   API_ENTER(ctx);
   if (!m) return ctx->fail(B200_ERR_INVALID, "model_download: null model");
-  if (desc) B200_TRY(download(ctx, desc, m->desc.p, (size_t)m->K * 352));
+  if (desc) B200_TRY(download(ctx, desc, m->desc.p, (size_t)m->K * m->D));
   DevBuf<float> tmp;
   if (kp && m->K > 0) {
     B200_TRY(tmp.alloc(ctx, (size_t)m->K * 3));
@@ -912,6 +913,109 @@ int b200_register_scene_shot(b200_ctx *ctx, const b200_model *model, const float
     rc = download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, p->max_instances, cap, transforms, inst_offsets,
                             inst_corrs, corr_cap, n_inst);
     tr.tick("e2e download");
+  } while (0);
+  delete scene;
+  return rc;
+}
+
+/* ------------------------------------------------------------------ resident FPFH pipeline */
+// FPFH_demo.cpp:405-538 with the model side resident: the reference estimates normals ON the keypoint clouds by radius
+// (:416-420, :486-492) and runs FPFHEstimation with input = surface = the keypoint cloud (:422-428, :505-510).
+namespace {
+int fpfh_side(b200_ctx *ctx, b200_cloud *cloud, const b200_shot_params *p, DevBuf<float> &desc) {
+  DevBuf<float> normals;
+  B200_TRY(normals.alloc(ctx, (size_t)std::max(cloud->n, 1) * 4));
+  B200_TRY(desc.alloc(ctx, (size_t)std::max(cloud->n, 1) * 33));
+  B200_TRY(dev_normals(ctx, cloud, cloud->raw.p, cloud->n, true, p->normal_k, p->normal_radius, nullptr, normals.p));
+  return dev_fpfh(ctx, cloud, normals.p, cloud->raw.p, cloud->n, true, p->descr_radius, desc.p);
+}
+}  // namespace
+
+int b200_model_create_fpfh(b200_ctx *ctx, const float *kp, int K, int kstride, const b200_shot_params *p,
+                           b200_model **out) {
+  API_ENTER(ctx);
+  if (!out) return ctx->fail(B200_ERR_INVALID, "model_create_fpfh: null output");
+  B200_TRY(check_params(ctx, p));
+  b200_cloud *cloud = nullptr;
+  B200_TRY(cloud_upload(ctx, kp, K, kstride, false, &cloud));
+  b200_model *m = new (std::nothrow) b200_model();
+  if (!m) {
+    delete cloud;
+    return ctx->fail(B200_ERR_NOMEM, "model_create_fpfh: out of host memory");
+  }
+  m->ctx = ctx;
+  m->K = K;
+  m->D = 33;
+  int rc = B200_OK;
+  do {
+    if ((rc = fpfh_side(ctx, cloud, p, m->desc)) != B200_OK) break;
+    if ((rc = m->kp.alloc(ctx, (size_t)std::max(K, 1))) != B200_OK) break;
+    if (K > 0) {
+      cudaError_t e = cudaMemcpyAsync(m->kp.p, cloud->raw.p, (size_t)K * sizeof(float4), cudaMemcpyDeviceToDevice,
+                                      ctx->stream);
+      if (e != cudaSuccess) {
+        rc = ctx->fail_cuda(e, "model_create_fpfh copy", __FILE__, __LINE__);
+        break;
+      }
+    }
+    if ((rc = match_prepare_model(ctx, m)) != B200_OK) break;
+    cudaError_t e = ctx->sync();
+    if (e != cudaSuccess) rc = ctx->fail_cuda(e, "model_create_fpfh sync", __FILE__, __LINE__);
+  } while (0);
+  delete cloud;
+  if (rc != B200_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return B200_OK;
+}
+
+int b200_model_descriptor_length(const b200_model *m) { return m ? m->D : 0; }
+
+int b200_register_scene_fpfh(b200_ctx *ctx, const b200_model *model, const float *scene_kp, int Ks, int kstride,
+                             const b200_shot_params *p, float *transforms, int *inst_offsets, b200_corr *inst_corrs,
+                             int corr_cap, int *n_inst, b200_corr *corrs_out, int *n_corrs, float *desc_out) {
+  API_ENTER(ctx);
+  if (!model || model->D != 33 || !n_inst || Ks < 0)
+    return ctx->fail(B200_ERR_INVALID, "register_scene_fpfh: bad arguments (the model must come from b200_model_create_fpfh)");
+  B200_TRY(check_params(ctx, p));
+  *n_inst = 0;
+  if (n_corrs) *n_corrs = 0;
+  b200_cloud *scene = nullptr;
+  B200_TRY(cloud_upload(ctx, scene_kp, Ks, kstride, false, &scene));
+  int rc = B200_OK;
+  do {
+    const int cap = std::max(Ks, 1), mi = p->max_instances;
+    DevBuf<float> desc, dT;
+    DevBuf<b200_corr> dcorrs, dic;
+    DevBuf<int> doffs, dcnts, dn, dnc;
+    if ((rc = fpfh_side(ctx, scene, p, desc)) != B200_OK) break;
+    if ((rc = dcorrs.alloc(ctx, (size_t)cap)) != B200_OK) break;
+    if ((rc = dic.alloc(ctx, (size_t)cap)) != B200_OK) break;
+    if ((rc = doffs.alloc(ctx, (size_t)mi + 1)) != B200_OK) break;
+    if ((rc = dcnts.alloc(ctx, (size_t)mi)) != B200_OK) break;
+    if ((rc = dn.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dnc.alloc(ctx, 1)) != B200_OK) break;
+    if ((rc = dT.alloc(ctx, (size_t)mi * 16)) != B200_OK) break;
+    if ((rc = dev_match(ctx, model->desc.p, model->K, desc.p, Ks, 33, p->match_mode, p->match_thr, dcorrs.p, dnc.p,
+                        &model->tc)) != B200_OK)
+      break;
+    if ((rc = dev_gc(ctx, model->kp.p, scene->raw.p, dcorrs.p, dnc.p, Ks, p->gc_size, p->gc_threshold, dT.p, mi, doffs.p,
+                     dcnts.p, dic.p, cap, dn.p)) != B200_OK)
+      break;
+    int nc = 0;
+    if ((rc = download(ctx, &nc, dnc.p, 1)) != B200_OK) break;
+    cudaError_t e = ctx->sync();
+    if (e != cudaSuccess) {
+      rc = ctx->fail_cuda(e, "register_scene_fpfh sync", __FILE__, __LINE__);
+      break;
+    }
+    if (n_corrs) *n_corrs = nc;
+    if (corrs_out && nc > 0 && (rc = download(ctx, corrs_out, dcorrs.p, (size_t)nc)) != B200_OK) break;
+    if (desc_out && Ks > 0 && (rc = download(ctx, desc_out, desc.p, (size_t)Ks * 33)) != B200_OK) break;
+    rc = download_instances(ctx, dT.p, doffs.p, dcnts.p, dic.p, dn.p, mi, cap, transforms, inst_offsets, inst_corrs,
+                            corr_cap, n_inst);
   } while (0);
   delete scene;
   return rc;
@@ -1236,10 +1340,21 @@ int b200_library_load(b200_ctx *ctx, const char *path, b200_library **out) {
   Fnv h;
   char magic[8];
   uint32_t nv = 0, D = 0;
-  b200_library *lib = new b200_library();
+  // what is left of the file bounds every allocation below (a corrupt count must not turn into a 94 GB vector)
+  long long file_left = 0;
+  if (fseek(f, 0, SEEK_END) == 0) {
+    file_left = ftell(f);
+    rewind(f);
+  }
+  b200_library *lib = new (std::nothrow) b200_library();
+  if (!lib) {
+    fclose(f);
+    return ctx->fail(B200_ERR_NOMEM, "library_load: out of host memory");
+  }
   lib->ctx = ctx;
   int rc = B200_OK;
   const char *why = nullptr;
+  try {
   if (!get(f, h, magic, 8) || memcmp(magic, kLibMagic, 8) != 0) why = "not a B200LIB1 file";
   if (!why && (!get(f, h, &nv, 4) || !get(f, h, &D, 4) || D != 352 || nv > (1u << 20))) why = "bad header";
   for (uint32_t v = 0; !why && rc == B200_OK && v < nv; ++v) {
@@ -1247,6 +1362,10 @@ int b200_library_load(b200_ctx *ctx, const char *path, b200_library **out) {
     std::array<float, 16> pose;
     if (!get(f, h, &K, 4) || K > (1u << 26) || !get(f, h, pose.data(), 64)) {
       why = "truncated view header";
+      break;
+    }
+    if ((long long)K * (3 + D) * 4 > file_left - ftell(f)) {
+      why = "view larger than the file";
       break;
     }
     std::vector<float> kp((size_t)K * 3), desc((size_t)K * D);
@@ -1260,6 +1379,10 @@ int b200_library_load(b200_ctx *ctx, const char *path, b200_library **out) {
   }
   uint64_t sum = 0;
   if (!why && rc == B200_OK && (fread(&sum, 8, 1, f) != 1 || sum != h.h)) why = "checksum mismatch";
+  } catch (const std::exception &) {  // std::bad_alloc from the staging vectors: no exception crosses the C ABI
+    rc = B200_ERR_NOMEM;
+    ctx->fail(rc, "library_load: out of host memory");
+  }
   fclose(f);
   if (why || rc != B200_OK) {
     b200_library_destroy(lib);

@@ -476,6 +476,9 @@ int dev_fpfh(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const float4 
 int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
               b200_corr *d_out, int *d_count, const TcModelPrep *prep = nullptr);
 int match_prepare_model(b200_ctx *ctx, b200_model *m);  // no-op for small libraries
+int match_prepare_rows(b200_ctx *ctx, const float *d_desc, int K, int D, TcModelPrep *t);
+int dev_nearest1(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid_p, const TcModelPrep *prep,
+                 const float *d_q, int nq, int D, int *d_idx, float *d_d2);
 int dev_ransac_instances(b200_ctx *ctx, const b200_corr *d_corrs, const float4 *d_mp, const float4 *d_sp,
                          const int *d_members, const int *d_inst_offsets, const int *d_n_inst, int C_cap,
                          double threshold, float *d_T, int max_inst, int *d_inst_counts, b200_corr *d_inst_corrs,

@@ -17,6 +17,7 @@ struct b200_desc_index {
   int K = 0, D = 0, n_valid = 0;
   DevBuf<float> desc;
   DevBuf<unsigned char> valid;
+  TcModelPrep tc;  // tensor-core filter operands (large indices): batched k = 1 queries take the matching path
 };
 
 namespace {
@@ -132,6 +133,7 @@ int b200_desc_index_create(b200_ctx *ctx, const float *desc, int K, int D, b200_
       }
       desc_valid_kernel<<<ceil_div((long long)K * 32, 256), 256, 0, ctx->stream>>>(ix->desc.p, K, D, ix->valid.p, nv.p);
       ctx->launches++;
+      if ((rc = match_prepare_rows(ctx, ix->desc.p, K, D, &ix->tc)) != B200_OK) break;
     }
     e = cudaMemcpyAsync(&ix->n_valid, nv.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = ctx->sync();
@@ -170,6 +172,15 @@ int b200_desc_index_knn(b200_ctx *ctx, const b200_desc_index *ix, const float *q
   B200_TRY(dd2.alloc(ctx, (size_t)nq * k));
   B200_TRY(didx.alloc(ctx, (size_t)nq * k));
   B200_CUDA(ctx, cudaMemcpyAsync(dq.p, queries, (size_t)nq * D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (k == 1 && nq >= 32) {
+    // a batch of k = 1 queries (the look-ahead of the PCL-style adapter, or a caller's own batch) is the correspondence
+    // search itself: tensor-core filter + exact rescoring, same answers as the per-query kernel below
+    B200_TRY(dev_nearest1(ctx, ix->desc.p, ix->K, ix->valid.p, &ix->tc, dq.p, nq, D, didx.p, dd2.p));
+    B200_CUDA(ctx, cudaMemcpyAsync(idx, didx.p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(ctx, cudaMemcpyAsync(d2, dd2.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
+    return B200_OK;
+  }
   const size_t smem = (size_t)D * sizeof(float);
   if (smem > 48 * 1024)
     B200_CUDA(ctx, ensure_dyn_smem(desc_knn_kernel, smem));

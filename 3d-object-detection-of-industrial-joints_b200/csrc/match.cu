@@ -231,16 +231,87 @@ static int match_mode_for(int Km, int Ks, int D) {
 
 // Keeps the model side of the filter resident with the model (b200_model_create_shot, b200_library_*): validity
 // flags, fp16 split operands, norms and scale are computed once instead of once per scene.
-int match_prepare_model(b200_ctx *ctx, b200_model *m) {
-  if (!m || m->K < 1024 || getenv("B200_MATCH_NOCACHE")) return B200_OK;
-  TcModelPrep &t = m->tc;
-  B200_TRY(t.mvalid.alloc(ctx, (size_t)m->K));
-  B200_TRY(t.nmv.alloc(ctx, 1));
-  B200_TRY(t.nmv.zero());
-  row_valid_kernel<<<ceil_div((long long)m->K * 32, 256), 256, 0, ctx->stream>>>(m->desc.p, m->K, m->D, 1, t.mvalid.p,
-                                                                                t.nmv.p);
+int match_prepare_rows(b200_ctx *ctx, const float *d_desc, int K, int D, TcModelPrep *t) {
+  if (K < 1024 || D < 16 || D > 1024 || getenv("B200_MATCH_NOCACHE")) return B200_OK;
+  B200_TRY(t->mvalid.alloc(ctx, (size_t)K));
+  B200_TRY(t->nmv.alloc(ctx, 1));
+  B200_TRY(t->nmv.zero());
+  row_valid_kernel<<<ceil_div((long long)K * 32, 256), 256, 0, ctx->stream>>>(d_desc, K, D, 1, t->mvalid.p, t->nmv.p);
   B200_LAUNCHED(ctx);
-  return match_tc_prepare_model(ctx, m->desc.p, m->K, m->D, t.mvalid.p, &t);
+  return match_tc_prepare_model(ctx, d_desc, K, D, t->mvalid.p, t);
+}
+
+int match_prepare_model(b200_ctx *ctx, b200_model *m) {
+  if (!m) return B200_OK;
+  return match_prepare_rows(ctx, m->desc.p, m->K, m->D, &m->tc);
+}
+
+// best[i] = (d2 bits << 32 | model row) of scene row i's exact float32 nearest valid model row, zero_cnt[i] = number
+// of model rows at distance exactly 0; both must be initialised (init_best_kernel).  The tensor-core filter takes
+// the bulk of the work for large libraries; the result is the exact kernel's, bit for bit.
+static int match_best_rows(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid_p,
+                           const TcModelPrep *prep, const float *d_scene, int Ks, const unsigned char *svalid_p, int D,
+                           unsigned long long *best_p, int *zero_cnt_p) {
+  if (Km > 0) {
+    const int sx = ceil_div(Ks, MT);
+    const int mtiles = ceil_div(Km, MT);
+    // enough CTAs for >= 4 waves when the scene is small
+    int sy = std::max(1, std::min(mtiles, (ctx->sm_count * 8) / std::max(sx, 1)));
+    dim3 grid(sx, sy);
+    const int tc_terms = match_mode_for(Km, Ks, D);
+    ctx->last_match_fallback = -1;
+    if (tc_terms) {
+      DevBuf<int> fb_rows, fb_count;
+      B200_TRY(fb_rows.alloc(ctx, (size_t)Ks));
+      B200_TRY(fb_count.alloc(ctx, 1));
+      B200_TRY(match_tc_filter(ctx, d_model, Km, mvalid_p, prep, d_scene, Ks, svalid_p, D, tc_terms, best_p,
+                               zero_cnt_p, fb_rows.p, fb_count.p));
+      if (ctx->profiling) {  // bench statistic: how many rows needed the exact kernel
+        B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_fallback, fb_count.p, sizeof(int), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+      }
+      // uncertified rows: exact evaluation by persistent CTAs over (row block, model tile) items
+      match_rows_kernel<<<ctx->sm_count * 4, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid_p, d_scene, D, fb_rows.p,
+                                                                        fb_count.p, best_p, zero_cnt_p);
+      B200_LAUNCHED(ctx);
+    } else {
+      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid_p, d_scene, Ks, D, best_p, zero_cnt_p);
+      B200_LAUNCHED(ctx);
+    }
+  }
+  return B200_OK;
+}
+
+__global__ void nearest1_emit_kernel(const unsigned long long *__restrict__ best, const unsigned char *__restrict__ qvalid,
+                                     int nq, int *__restrict__ idx, float *__restrict__ d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const unsigned long long k = best[i];
+  const bool have = qvalid[i] && k != ~0ull;
+  idx[i] = have ? (int)(unsigned)(k & 0xffffffffull) : -1;
+  d2[i] = have ? __uint_as_float((unsigned)(k >> 32)) : __int_as_float(0x7f800000);
+}
+
+// Nearest valid model row of every query row (k = 1 of KdTreeFLANN::nearestKSearch for a batch of queries): the
+// correspondence search without the acceptance test.  Queries with a non-finite value get -1 / +inf.
+int dev_nearest1(b200_ctx *ctx, const float *d_model, int Km, const unsigned char *mvalid_p, const TcModelPrep *prep,
+                 const float *d_q, int nq, int D, int *d_idx, float *d_d2) {
+  if (nq <= 0) return B200_OK;
+  if (prep && (!prep->ready || prep->Km != Km || prep->D != D)) prep = nullptr;
+  DevBuf<unsigned char> qvalid;
+  DevBuf<int> zero_cnt;
+  DevBuf<unsigned long long> best;
+  B200_TRY(qvalid.alloc(ctx, (size_t)nq));
+  B200_TRY(zero_cnt.alloc(ctx, (size_t)nq));
+  B200_TRY(best.alloc(ctx, (size_t)nq));
+  row_valid_kernel<<<ceil_div((long long)nq * 32, 256), 256, 0, ctx->stream>>>(d_q, nq, D, 1, qvalid.p, nullptr);
+  B200_LAUNCHED(ctx);
+  init_best_kernel<<<ceil_div(nq, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, nq);
+  B200_LAUNCHED(ctx);
+  B200_TRY(match_best_rows(ctx, d_model, Km, mvalid_p, prep, d_q, nq, qvalid.p, D, best.p, zero_cnt.p));
+  nearest1_emit_kernel<<<ceil_div(nq, 256), 256, 0, ctx->stream>>>(best.p, qvalid.p, nq, d_idx, d_d2);
+  B200_LAUNCHED(ctx);
+  return B200_OK;
 }
 
 int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene, int Ks, int D, int mode, float thr,
@@ -272,33 +343,7 @@ int dev_match(b200_ctx *ctx, const float *d_model, int Km, const float *d_scene,
   B200_LAUNCHED(ctx);
   init_best_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, Ks);
   B200_LAUNCHED(ctx);
-  if (Km > 0) {
-    const int sx = ceil_div(Ks, MT);
-    const int mtiles = ceil_div(Km, MT);
-    // enough CTAs for >= 4 waves when the scene is small
-    int sy = std::max(1, std::min(mtiles, (ctx->sm_count * 8) / std::max(sx, 1)));
-    dim3 grid(sx, sy);
-    const int tc_terms = match_mode_for(Km, Ks, D);
-    ctx->last_match_fallback = -1;
-    if (tc_terms) {
-      DevBuf<int> fb_rows, fb_count;
-      B200_TRY(fb_rows.alloc(ctx, (size_t)Ks));
-      B200_TRY(fb_count.alloc(ctx, 1));
-      B200_TRY(match_tc_filter(ctx, d_model, Km, mvalid_p, prep, d_scene, Ks, svalid.p, D, tc_terms, best.p,
-                               zero_cnt.p, fb_rows.p, fb_count.p));
-      if (ctx->profiling) {  // bench statistic: how many rows needed the exact kernel
-        B200_CUDA(ctx, cudaMemcpyAsync(&ctx->last_match_fallback, fb_count.p, sizeof(int), cudaMemcpyDeviceToHost,
-                                       ctx->stream));
-      }
-      // uncertified rows: exact evaluation by persistent CTAs over (row block, model tile) items
-      match_rows_kernel<<<ctx->sm_count * 4, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid_p, d_scene, D, fb_rows.p,
-                                                                        fb_count.p, best.p, zero_cnt.p);
-      B200_LAUNCHED(ctx);
-    } else {
-      match_tile_kernel<<<grid, MTHREADS, 0, ctx->stream>>>(d_model, Km, mvalid_p, d_scene, Ks, D, best.p, zero_cnt.p);
-      B200_LAUNCHED(ctx);
-    }
-  }
+  B200_TRY(match_best_rows(ctx, d_model, Km, mvalid_p, prep, d_scene, Ks, svalid.p, D, best.p, zero_cnt.p));
   match_flags_kernel<<<ceil_div(Ks, 256), 256, 0, ctx->stream>>>(best.p, zero_cnt.p, svalid.p, nmv_p, Ks, mode, thr,
                                                                  flags.p);
   B200_LAUNCHED(ctx);

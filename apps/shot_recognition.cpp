@@ -19,6 +19,7 @@
 //        reference's icp_align (SHOT.cpp:177-192) on the model placed by the grouped pose
 #include <pcl_b200/pcl_b200.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
@@ -58,6 +59,7 @@ int main(int argc, char **argv) {
   const float cg_size_ = argc > 9 ? (float)atof(argv[9]) : 0.02f;
   const float cg_thresh_ = argc > 10 ? (float)atof(argv[10]) : 2.0f;
   const bool batch = argc > 11 && std::string(argv[11]) == "batch";
+  const bool loop_single = argc > 11 && std::string(argv[11]) == "loop-single";  // the loop, one device call per query
   const std::string algo = argc > 12 ? argv[12] : "gc";  // the reference's --algorithm Hough|GC
   const bool use_hough = algo == "hough" || algo == "hough-shot";
   const bool board_frames = algo == "hough";
@@ -118,12 +120,14 @@ int main(int argc, char **argv) {
 
   //  Find Model-Scene Correspondences
   pcl::CorrespondencesPtr model_scene_corrs(new pcl::Correspondences());
+  const auto t_corr0 = std::chrono::steady_clock::now();
   if (batch) {
     // one call for the whole scene (b200_match): same list as the loop below
     pcl::determineCorrespondences(*model_descriptors, *scene_descriptors, 1, match_thr, *model_scene_corrs);
   } else {
     pcl::KdTreeFLANN<DescriptorType> match_search;
     match_search.setInputCloud(model_descriptors);
+    if (loop_single) match_search.setLookAhead(0);
     for (size_t i = 0; i < scene_descriptors->size(); ++i) {
       std::vector<int> neigh_indices(1);
       std::vector<float> neigh_sqr_dists(1);
@@ -133,7 +137,12 @@ int main(int argc, char **argv) {
         model_scene_corrs->push_back(pcl::Correspondence(neigh_indices[0], static_cast<int>(i), neigh_sqr_dists[0]));
     }
   }
+  const double corr_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_corr0).count();
   std::cout << "Correspondences found: " << model_scene_corrs->size() << std::endl;
+  std::cout << "Correspondence search: " << corr_ms << " ms for " << scene_descriptors->size() << " scene descriptors ("
+            << (batch ? "one batched call" : loop_single ? "reference loop, one device call per query"
+                                                         : "reference loop, look-ahead batches")
+            << "), " << corr_ms * 1e3 / std::max<size_t>(scene_descriptors->size(), 1) << " us per query" << std::endl;
 
   //  Actual Clustering (GeometricConsistency branch)
   std::vector<pcl::Matrix4f> rototranslations;

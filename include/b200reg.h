@@ -262,8 +262,22 @@ B200_API int b200_model_create_shot(b200_ctx *ctx, const float *xyz, int n, int 
                            int kstride, const b200_shot_params *p, b200_model **out);
 B200_API int b200_model_destroy(b200_model *m);
 B200_API int b200_model_size(const b200_model *m);
-/* copy the library out (host): desc K x 352, kp K x 3 (either may be NULL) */
+/* copy the library out (host): desc K x 352 (K x 33 for an FPFH model), kp K x 3 (either may be NULL) */
 B200_API int b200_model_download(b200_ctx *ctx, const b200_model *m, float *desc, float *kp);
+
+/* FPFH_demo.cpp:405-538 with the model side resident.  The reference estimates the normals ON the keypoint clouds by
+ * radius (FPFH_demo.cpp:416-420, 486-492) and runs FPFHEstimation with input = surface = keypoints (:422-428,
+ * :505-510); params: normal_radius (or normal_k), descr_radius = the FPFH radius, match_mode = 2 (the k = 2 ratio test
+ * of :516-538), gc_size / gc_threshold.  The model's descriptors are K x 33 (b200_model_descriptor_length). */
+B200_API int b200_model_create_fpfh(b200_ctx *ctx, const float *kp, int K, int kstride, const b200_shot_params *p,
+                                    b200_model **out);
+B200_API int b200_model_descriptor_length(const b200_model *m);
+/* Scene side in one call (host buffers): normals + FPFH33 of the scene keypoint cloud, correspondence search against
+ * the resident model, GC grouping + poses.  desc_out (Ks x 33) may be NULL; other outputs as b200_register_scene_shot. */
+B200_API int b200_register_scene_fpfh(b200_ctx *ctx, const b200_model *model, const float *scene_kp, int Ks, int kstride,
+                                      const b200_shot_params *p, float *transforms, int *inst_offsets,
+                                      b200_corr *inst_corrs, int corr_cap, int *n_inst, b200_corr *corrs_out,
+                                      int *n_corrs, float *desc_out);
 
 /* Scene side of SHOT.cpp:305-483 in one call (host buffers in, host results out): normals →
  * SHOT352 at the keypoints → correspondence search against the resident model → GC grouping.

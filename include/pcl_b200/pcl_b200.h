@@ -26,7 +26,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../b200reg.h"
@@ -85,6 +87,50 @@ struct Matrix4f {
   float operator()(int r, int c) const { return m[r * 4 + c]; }
 };
 
+namespace detail {
+/* Live clouds of one point type.  The reference's correspondence loop hands KdTreeFLANN::nearestKSearch one element
+ * of a descriptor cloud at a time (SHOT.cpp:409-423); the adapter looks the element's address up here to learn that
+ * it is row i of a cloud and may answer rows i .. i + B in one device call (see KdTreeFLANN<PointT, true>). */
+template <class PointT>
+struct CloudRegistry {
+  static std::mutex &mu() {
+    static std::mutex m;
+    return m;
+  }
+  static std::vector<const std::vector<PointT> *> &live() {
+    static std::vector<const std::vector<PointT> *> v;
+    return v;
+  }
+  static void add(const std::vector<PointT> *p) {
+    std::lock_guard<std::mutex> lk(mu());
+    live().push_back(p);
+  }
+  static void remove(const std::vector<PointT> *p) {
+    std::lock_guard<std::mutex> lk(mu());
+    auto &v = live();
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i] == p) {
+        v[i] = v.back();
+        v.pop_back();
+        return;
+      }
+  }
+  /* the live cloud whose storage holds *q (nullptr if none); *index = its row */
+  static const std::vector<PointT> *find(const PointT *q, size_t *index) {
+    std::lock_guard<std::mutex> lk(mu());
+    for (const std::vector<PointT> *v : live()) {
+      if (v->empty()) continue;
+      const PointT *b = v->data();
+      if (q >= b && q < b + v->size()) {
+        *index = (size_t)(q - b);
+        return v;
+      }
+    }
+    return nullptr;
+  }
+};
+}  // namespace detail
+
 template <class PointT>
 struct PointCloud {
   typedef std::shared_ptr<PointCloud<PointT>> Ptr;
@@ -92,7 +138,18 @@ struct PointCloud {
   std::vector<PointT> points;
   uint32_t width, height;
   bool is_dense;
-  PointCloud() : width(0), height(0), is_dense(true) {}
+  PointCloud() : width(0), height(0), is_dense(true) { detail::CloudRegistry<PointT>::add(&points); }
+  PointCloud(const PointCloud &o) : points(o.points), width(o.width), height(o.height), is_dense(o.is_dense) {
+    detail::CloudRegistry<PointT>::add(&points);
+  }
+  PointCloud &operator=(const PointCloud &o) {
+    points = o.points;
+    width = o.width;
+    height = o.height;
+    is_dense = o.is_dense;
+    return *this;
+  }
+  ~PointCloud() { detail::CloudRegistry<PointT>::remove(&points); }
   size_t size() const { return points.size(); }
   bool empty() const { return points.empty(); }
   void resize(size_t n) {
@@ -279,27 +336,76 @@ class KdTreeFLANN<PointT, true> {
       detail::ok(b200_desc_index_create(detail::ctx(), flat.data(), (int)cloud->size(), D, &index_),
                  "KdTreeFLANN::setInputCloud");
   }
+  /* The reference calls this once per scene descriptor from a plain loop (SHOT.cpp:409-423, SHOT_demo.cpp:513-530).
+   * One device round trip per call would make that loop ~1000 times slower than the batched search, so when the query
+   * is row i of a live descriptor cloud the rows i .. i + lookAhead() are answered in one call and the following calls
+   * are served from that answer — after checking, byte for byte, that the row still holds what was sent.  The
+   * results are those of the single-query call.  setLookAhead(0) turns it off. */
   int nearestKSearch(const PointT &p, int k, std::vector<int> &k_indices, std::vector<float> &k_sqr_distances) const {
     if (!index_ || k < 1) return 0;
+    const int D = detail::DescTraits<PointT>::dim;
+    const float *row = detail::DescTraits<PointT>::data(p);
+    if (look_ahead_ > 0) {
+      size_t i = 0;
+      const std::vector<PointT> *cloud = detail::CloudRegistry<PointT>::find(&p, &i);
+      if (cloud) {
+        const bool hit = cloud == batch_cloud_ && k == batch_k_ && i >= batch_first_ && i < batch_first_ + batch_n_ &&
+                         memcmp(row, &batch_q_[(i - batch_first_) * (size_t)D], sizeof(float) * D) == 0;
+        if (!hit) {
+          const size_t n = std::min(cloud->size() - i, (size_t)look_ahead_);
+          batch_q_.resize(n * (size_t)D);
+          for (size_t r = 0; r < n; ++r)
+            memcpy(&batch_q_[r * D], detail::DescTraits<PointT>::data((*cloud)[i + r]), sizeof(float) * D);
+          batch_idx_.assign(n * (size_t)k, -1);
+          batch_d2_.assign(n * (size_t)k, 0.f);
+          batch_found_ = 0;
+          batch_n_ = 0;
+          if (!detail::ok(b200_desc_index_knn(detail::ctx(), index_, batch_q_.data(), (int)n, k, batch_idx_.data(),
+                                              batch_d2_.data(), &batch_found_),
+                          "KdTreeFLANN::nearestKSearch"))
+            return 0;
+          batch_cloud_ = cloud;
+          batch_first_ = i;
+          batch_n_ = n;
+          batch_k_ = k;
+        }
+        const size_t o = (i - batch_first_) * (size_t)k;
+        int found = 0;
+        while (found < batch_found_ && batch_idx_[o + found] >= 0) ++found;
+        k_indices.assign(batch_idx_.begin() + o, batch_idx_.begin() + o + found);
+        k_sqr_distances.assign(batch_d2_.begin() + o, batch_d2_.begin() + o + found);
+        return found;
+      }
+    }
     k_indices.assign((size_t)k, -1);
     k_sqr_distances.assign((size_t)k, 0.f);
     int found = 0;
-    if (!detail::ok(b200_desc_index_knn(detail::ctx(), index_, detail::DescTraits<PointT>::data(p), 1, k,
-                                        k_indices.data(), k_sqr_distances.data(), &found),
+    if (!detail::ok(b200_desc_index_knn(detail::ctx(), index_, row, 1, k, k_indices.data(), k_sqr_distances.data(),
+                                        &found),
                     "KdTreeFLANN::nearestKSearch"))
       return 0;
     k_indices.resize((size_t)found);
     k_sqr_distances.resize((size_t)found);
     return found;
   }
+  void setLookAhead(int rows) { look_ahead_ = rows < 0 ? 0 : rows; }
+  int lookAhead() const { return look_ahead_; }
 
  private:
   void reset() {
     if (index_) b200_desc_index_destroy(index_);
     index_ = nullptr;
+    batch_cloud_ = nullptr;
+    batch_n_ = 0;
   }
   PointCloudConstPtr input_;
   b200_desc_index *index_ = nullptr;
+  int look_ahead_ = 8192;
+  mutable const std::vector<PointT> *batch_cloud_ = nullptr;
+  mutable size_t batch_first_ = 0, batch_n_ = 0;
+  mutable int batch_k_ = 0, batch_found_ = 0;
+  mutable std::vector<float> batch_q_, batch_d2_;
+  mutable std::vector<int> batch_idx_;
 };
 
 namespace search {

@@ -41,10 +41,10 @@ def test_no_cpu_fallback():
 
 
 def test_product_does_not_reference_oracle():
-    """Nothing in the package or include/ may import, link or name the oracle."""
-    for base in (os.path.join(ROOT, PKG_NAME), os.path.join(ROOT, "include")):
+    """Nothing in the package, include/ or apps/ may import, link or name the oracle."""
+    for base in (os.path.join(ROOT, PKG_NAME), os.path.join(ROOT, "include"), os.path.join(ROOT, "apps")):
         for dp, _, files in os.walk(base):
-            if "build" in dp.split(os.sep):
+            if "build" in dp.split(os.sep) or "bin" in dp.split(os.sep):
                 continue
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):

@@ -55,7 +55,7 @@ def _read_instances(prefix):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["loop", "batch"])
+@pytest.mark.parametrize("mode", ["loop", "loop-single", "batch"])
 def test_shot_recognition_app_matches_oracle(apps, orc, synth, tmp_path, mode):
     model = synth.make_model("y", 5000)
     scene = synth.make_scene(("y",), 30000, scene_id=3)
@@ -67,6 +67,7 @@ def test_shot_recognition_app_matches_oracle(apps, orc, synth, tmp_path, mode):
                        [prefix, "10", "0.02", "0.25", "0.02", "2", mode], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     assert "Model instances found" in r.stdout
+    print([l for l in r.stdout.splitlines() if l.startswith("Correspondence search")])
     corr = np.fromfile(prefix + ".corr", dtype=CORR)
     T, inst = _read_instances(prefix)
     # oracle chain with the same parameters (descr_rad is a float in the reference: 0.02f)

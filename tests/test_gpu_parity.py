@@ -774,3 +774,35 @@ def test_remove_nan_and_transform_bit_exact(ctx, orc, synth):
     assert a.tobytes() == b.tobytes()
     assert len(ctx.remove_nan(np.zeros((0, 3), np.float32))[0]) == 0
     assert len(ctx.transform_points(np.zeros((0, 3), np.float32), T)) == 0
+
+
+def test_resident_fpfh_pipeline(ctx, orc, synth, b200):
+    """b200_model_create_fpfh + b200_register_scene_fpfh (FPFH_demo.cpp:405-538 with the model resident): equals the
+    per-call API bit for bit; normals and descriptors hold the stage bars against the restatement (tests/eps.py)."""
+    model = synth.make_model("y", 5000)
+    scene = synth.make_scene(("y",), 30000, scene_id=4)
+    kpm, kps = synth.voxel_grid(model, 0.01), synth.voxel_grid(scene, 0.02)
+    r = 0.05
+    p = b200.shot_params(normal_k=0, normal_radius=r, descr_radius=r, match_mode=2, match_thr=0.0, gc_size=0.02,
+                         gc_threshold=3, max_instances=2048)
+    m = ctx.model_create_fpfh(kpm, p)
+    dm, kk = m.download()
+    assert dm.shape == (len(kpm), 33) and np.array_equal(kk, kpm)
+    res = ctx.register_scene_fpfh(m, kps, p, want_desc=True)
+    # per-call API, same stages
+    cm, cs = ctx.cloud(kpm), ctx.cloud(kps)
+    nm, ns = ctx.normals(cm, radius=r), ctx.normals(cs, radius=r)
+    fm, fs = ctx.fpfh33(cm, nm, r), ctx.fpfh33(cs, ns, r)
+    assert np.array_equal(dm, fm, equal_nan=True) and np.array_equal(res["desc"], fs, equal_nan=True)
+    c = ctx.match(fm, fs, 2, 0.0)
+    assert c.tobytes() == res["corrs"].tobytes() and len(c) > 100
+    T, inst, n = ctx.gc_recognize(kpm, kps, c, 0.02, 3, max_inst=2048)
+    assert n == res["n_instances"] and all(a.tobytes() == b.tobytes() for a, b in zip(inst, res["instances"]))
+    # against the restatement, stage by stage from identical inputs
+    eps.normals_check(orc, ns, kps, radius=r, label="resident fpfh: normals")
+    eps.fpfh_check(orc, fs, kps, ns, r, label="resident fpfh: descriptors")
+    oc = orc.match(fm, fs, 2, 0.0)
+    assert oc.tobytes() == c.tobytes()
+    cm.close()
+    cs.close()
+    m.close()
