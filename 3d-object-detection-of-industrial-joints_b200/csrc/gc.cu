@@ -1037,7 +1037,7 @@ __device__ __forceinline__ unsigned fastmod_u32(unsigned r, unsigned long long m
 // positions 0..2 of the shuffle array live in registers.  Models (double-precision Umeyama) are
 // fitted and scored one sample per thread, in batches of 1, 4, 32, 128, 128, ...; thread 0 then
 // replays the adaptive termination rule in order and discards the samples past the stopping point.
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 5)
     gc_ransac_kernel(RansacBuffers rb, int max_inst, int corr_cap, double threshold, int max_iterations) {
   __shared__ unsigned s_mt[624];
   __shared__ unsigned short s_jx[624];  // swap partner of draw t (valid when n <= 65536)

@@ -478,13 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 // 64-column chunks with coalesced loads (the candidate rows are scattered over the library); each lane
 // then adds its 64 squared differences in column order, so the distance is the exact sequential
 // float32 L2_Simple value.
-constexpr int RS_CHUNK = 64;
 constexpr int RS_WARPS_PER_CTA = 8;
-
-struct RescoreSmem {
-  float a[32 / TC_CAND][RS_CHUNK];  // scene rows of the warp (32 / nc of them, nc >= TC_CAND)
-  float b[32][RS_CHUNK + 1];   // candidate rows, padded: lane l reads b[l][d], conflict free
-};
 
 __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
     tc_rescore_kernel(const float *__restrict__ model, int Km, const float *__restrict__ scene, int Ks, int D,
@@ -495,9 +489,7 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
                       int *__restrict__ zero_cnt, int *__restrict__ fb_rows, int *__restrict__ fb_count,
                       unsigned *__restrict__ err_ratio_bits, const int *__restrict__ row_map,
                       const int *__restrict__ n_rows_dev, int n_tiles) {
-  extern __shared__ __align__(16) unsigned char rs_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  RescoreSmem &sm = reinterpret_cast<RescoreSmem *>(rs_raw)[warp];
   const int nc = n_split * TC_CAND;  // 4, 8 or 16
   const int rpw = 32 / nc;           // rows per warp
   const int gw = blockIdx.x * RS_WARPS_PER_CTA + warp;
@@ -546,28 +538,52 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32)
     }
   }
 
+  // Exact distance of this lane's surviving (row, candidate) pair: the two descriptor rows are read straight from
+  // global memory with independent 16-byte loads (several in flight per lane; the lanes of a warp touch a handful of
+  // rows, which stay in L1) and summed in column order — FLANN's sequential float32 L2_Simple value.
   float acc = 0.0f;
-  for (int d0 = 0; d0 < D; d0 += RS_CHUNK) {
-    const int w = min(RS_CHUNK, D - d0);
-    // stage: scene rows, then the surviving candidate rows (two coalesced 128-byte loads per row)
-    for (int rr = 0; rr < rpw; ++rr) {
-      const int ii = __shfl_sync(0xffffffffu, i, rr * nc);
-      for (int dd = lane; dd < w; dd += 32) sm.a[rr][dd] = (ii >= 0) ? scene[(size_t)ii * D + d0 + dd] : 0.0f;
-    }
-    for (int l = 0; l < 32; ++l) {
-      const int jl = __shfl_sync(0xffffffffu, pair_ok ? j : -1, l);
-      if (jl >= 0)
-        for (int dd = lane; dd < w; dd += 32) sm.b[l][dd] = model[(size_t)jl * D + d0 + dd];
-    }
-    __syncwarp();
-    if (pair_ok) {
-#pragma unroll 8
-      for (int dd = 0; dd < w; ++dd) {
-        const float diff = sm.a[r][dd] - sm.b[lane][dd];
+  if (pair_ok) {
+    const float *a = scene + (size_t)i * D, *b = model + (size_t)j * D;
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0) {
+      const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b);
+      const int n4 = D >> 2;
+      int d = 0;
+      for (; d + 4 <= n4; d += 4) {
+        float4 x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          x[u] = __ldg(a4 + d + u);
+          y[u] = __ldg(b4 + d + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float diff = x[u].x - y[u].x;
+          acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+          diff = x[u].y - y[u].y;
+          acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+          diff = x[u].z - y[u].z;
+          acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+          diff = x[u].w - y[u].w;
+          acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+        }
+      }
+      for (; d < n4; ++d) {
+        const float4 x = __ldg(a4 + d), y = __ldg(b4 + d);
+        float diff = x.x - y.x;
+        acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+        diff = x.y - y.y;
+        acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+        diff = x.z - y.z;
+        acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+        diff = x.w - y.w;
+        acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        const float diff = __ldg(a + d) - __ldg(b + d);
         acc = __fadd_rn(acc, __fmul_rn(diff, diff));
       }
     }
-    __syncwarp();
   }
   unsigned long long key = ~0ull;
   int zeros = 0;
@@ -749,9 +765,7 @@ int tc_pass(b200_ctx *ctx, const float *d_model, int Km, const TcModelPrep &B, c
   }
   const float eta = tc_eta(terms, Kp);
   const int rows_per_cta = RS_WARPS_PER_CTA * (32 / (n_split * TC_CAND));
-  const size_t rs_smem = sizeof(RescoreSmem) * RS_WARPS_PER_CTA;
-  B200_CUDA(ctx, ensure_dyn_smem(tc_rescore_kernel, rs_smem));
-  tc_rescore_kernel<<<ceil_div(Ks, rows_per_cta), RS_WARPS_PER_CTA * 32, rs_smem, ctx->stream>>>(
+  tc_rescore_kernel<<<ceil_div(Ks, rows_per_cta), RS_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
       d_model, Km, d_scene, Ks, D, svalid, n_split, cand_s.p, cand_j.p, cand_b.p, na.p,
       reinterpret_cast<const float *>(B.bits.p + 1), scA, B.scaleB.p, eta, best, zero_cnt, fb_rows, fb_count,
       err_bits, row_map, rows_dev, n_tiles);
