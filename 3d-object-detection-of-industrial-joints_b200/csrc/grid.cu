@@ -273,6 +273,8 @@ int cloud_grid_for_radius(b200_cloud *c, double radius, const GridView **out) {
   double area = std::max((double)ext[2] * (double)ext[1], 1e-12);
   // edge at which a surface cell would hold ~8 points
   float dens_cell = (float)sqrt(area * 8.0 / std::max(c->n_valid, 1));
+  // cell edge = radius (3 x 3 x 3 stencil).  Measured on the 1 M-point scene, r = 0.02: edge r / 1.5, r / 2, r / 3 scan
+  // fewer candidates but more and shorter rows: SHOT 0.95 -> 0.98, 1.02, 1.16 ms.
   float cell = (float)radius;
   if (!(cell > 0.f)) cell = dens_cell;
   cell = std::max(cell, 0.5f * dens_cell);
