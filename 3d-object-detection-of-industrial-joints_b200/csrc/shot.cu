@@ -404,9 +404,14 @@ __global__ void __launch_bounds__(256)
       for (int y = y0; y <= y1; ++y) {
         const int base = g.dx * (y + g.dy * z);
         const int e = cs[base + x1 + 1];
-        for (int j = cs[base + x0] + lane; j < e; j += 32) {
-          const float4 p = pts[j];
-          const float d2 = sqdist3(c.x, c.y, c.z, p.x, p.y, p.z);
+        for (int j0 = cs[base + x0] + lane; j0 < e; j0 += 128) {
+         float4 pp[4];
+#pragma unroll
+         for (int u = 0; u < 4; ++u) pp[u] = (j0 + 32 * u < e) ? pts[j0 + 32 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+         for (int u = 0; u < 4; ++u) {
+          const float4 p = pp[u];
+          const float d2 = (j0 + 32 * u < e) ? sqdist3(c.x, c.y, c.z, p.x, p.y, p.z) : 3.0e38f;
           if (d2 < r2) {
             ++n;
             if (p.x == c.x && p.y == c.y && p.z == c.z) {
@@ -423,6 +428,7 @@ __global__ void __launch_bounds__(256)
               part[6] += w;
             }
           }
+         }
         }
       }
   }
@@ -516,21 +522,26 @@ __global__ void __launch_bounds__(SW_THREADS, 3)
           for (int y = y0; y <= y1; ++y) {
             const int base = g.dx * (y + g.dy * z);
             const int s0 = cs[base + x0], e = cs[base + x1 + 1];
-            for (int j0 = s0; j0 < e; j0 += 32) {
-              const int j = j0 + lane;
-              bool hit = false;
-              float d2 = 0.f;
-              if (j < e) {
-                const float4 p = pts[j];
-                d2 = sqdist3(c.x, c.y, c.z, p.x, p.y, p.z);
-                hit = d2 < r2;
+            // four 32-point chunks per trip, their loads issued before the first ballot (a trip per chunk made every
+            // chunk wait for its own L2 round trip: the kernel's largest stall)
+            for (int j0 = s0; j0 < e; j0 += 128) {
+              float4 p[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                p[u] = (j < e) ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
               }
-              const unsigned m = __ballot_sync(0xffffffffu, hit);
-              if (hit) {
-                const int slot = n + __popc(m & ((1u << lane) - 1u));
-                if (slot < SW_CAP) sm.pos[slot] = j;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                const bool hit = j < e && sqdist3(c.x, c.y, c.z, p[u].x, p[u].y, p[u].z) < r2;
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                  const int slot = n + __popc(m & ((1u << lane) - 1u));
+                  if (slot < SW_CAP) sm.pos[slot] = j;
+                }
+                n += __popc(m);
               }
-              n += __popc(m);
             }
           }
       }
