@@ -87,7 +87,7 @@ def build_apps(force=False):
         src, out = os.path.join(APPS, f), os.path.join(APP_BIN, f[:-4])
         deps = [src, hdr, os.path.join(ROOT, "include", "b200reg.h"), so]
         if force or not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-            cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-o", out,
+            cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-o", out,
                    "-L" + HERE, "-lb200reg", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE)]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:

@@ -27,7 +27,7 @@ def _write(path, a):
 
 def test_apps_build_and_need_a_gpu(apps, synth, tmp_path):
     import torch
-    assert set(apps) >= {"shot_recognition", "fpfh_recognition", "batch_recognition"}
+    assert set(apps) >= {"shot_recognition", "fpfh_recognition", "batch_recognition", "sharded_recognition"}
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     m = synth.make_model("y", 500)
@@ -254,3 +254,33 @@ def test_batch_recognition_app_lanes(apps, b200, synth, tmp_path):
         assert corr.tobytes() == ref["corrs"].tobytes() and np.array_equal(T, ref["transforms"])
     m.close()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_sharded_recognition_app(apps, b200, synth, tmp_path):
+    """C++ host side of the multi-GPU path (b200_comm_* + b200_register_scene_shot_sharded, one host thread per GPU):
+    the files it writes equal the single-GPU registration, with one rank and — on a box with two GPUs — with two."""
+    import torch
+    model = synth.make_model("y", 20000)
+    kpm = synth.uniform_sampling(model, 0.005)
+    scene = synth.make_scene(("y", "diagonal"), 120000, scene_id=31)
+    kps = synth.uniform_sampling(scene, 0.015)
+    for name, a in (("m", model), ("mk", kpm), ("s", scene), ("sk", kps)):
+        _write(tmp_path / (name + ".f32"), a)
+    p = b200.shot_params(normal_k=20, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=4096)
+    ctx = b200.Context(0)
+    m = ctx.model_create_shot(model, kpm, p)
+    ref = ctx.register_scene_shot(m, scene, kps, p)
+    m.close()
+    ctx.close()
+    assert ref["n_instances"] > 0
+    for ranks in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
+        prefix = str(tmp_path / ("out%d" % ranks))
+        r = subprocess.run([apps["sharded_recognition"]] + [str(tmp_path / (n + ".f32")) for n in ("m", "mk", "s", "sk")] +
+                           [prefix, str(ranks), "3"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        print(r.stdout.strip())
+        corr = np.fromfile(prefix + ".corr", dtype=CORR)
+        T = np.fromfile(prefix + ".T", dtype=np.float32).reshape(-1, 4, 4)
+        assert corr.tobytes() == ref["corrs"].tobytes() and np.array_equal(T, ref["transforms"])
