@@ -37,9 +37,10 @@ MODEL_SS, SCENE_SS = 0.005, 0.01
 _REAL_STDOUT = None
 
 # DRAM read + write bytes per launch of each stage's main kernel, from the committed `ncu --set full` capture of the
-# default workload (profiles/summary_r01.md)
-TRAFFIC_NCU = {"match_filter": 332.2e6, "gc_group": 25.7e6, "gc_ransac": 1.4e6, "match": 332.2e6 + 142.8e6,
-               "normals": 35.3e6, "shot": 145.9e6, "gc_adjacency": 50.4e6, "gc_sort": 1.0e6}
+# default workload (profiles/summary_r02.md)
+TRAFFIC_NCU = {"match_filter": 83.2e6 + 33.0e6, "gc_group": 25.7e6, "gc_ransac": 2.0e6,
+               "match": 83.2e6 + 33.0e6 + 147.8e6 + 6.4e6, "normals": 36.5e6, "shot": 128.1e6, "gc_adjacency": 52.4e6,
+               "gc_sort": 1.0e6, "neighbor_count": 17.8e6}
 
 
 def _emit(line):
@@ -220,7 +221,8 @@ def run_reference(args, rank, world):
 # algorithmic bytes / flop per stage; the kernel that carries the stage
 STAGE_KERNEL = {"normals": "normals_knn_kernel", "shot": "shot_warp_kernel", "match_filter": "tc_filter_kernel",
                 "gc_adjacency": "gc_adjacency_kernel", "gc_group": "gc_group_cluster_kernel",
-                "gc_ransac": "gc_ransac_kernel", "gc_sort": "gc_rank_kernel", "neighbor_count": "radius_count_kernel",
+                "gc_ransac": "gc_ransac_kernel", "gc_sort": "gc_rank_kernel",
+                "neighbor_count": "shot_count_cov_kernel (+ shot_eigen_kernel)",
                 "grid_build": "cell_count/scan/scatter kernels", "match": "tc_filter + tc_rescore + prep kernels"}
 
 
@@ -461,7 +463,7 @@ def run_b200(args, rank, world, local_rank):
         # the roofline line is the kernel with the LARGEST DURATION per scene, whatever it is; the three largest follow
         order = sorted((k for k in stage_ms if k in work and k != "match"), key=lambda k: -stage_ms[k][0])
         roofline = roof(order[0])
-        roofline.update({"traffic_source": "ncu --set full (profiles/), per launch, default workload",
+        roofline.update({"traffic_source": "ncu --set full, profiles/summary_r02.md, per launch, default workload",
                          "peak_source": ("MEASURED_PEAKS.json (burst figures: kernel timed alone, single-lane pass)"
                                          if peaks else "fallback (B200_PROFILING.md)"),
                          "selection": "largest average duration per scene among all kernels of the step (CUDA-event "
