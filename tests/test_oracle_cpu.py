@@ -550,3 +550,41 @@ def test_board_against_numpy_restatement(orc, synth):
         if np.abs(rf[i] - ref).max() < 2e-5:
             ok_rows += 1
     assert ok_rows >= 0.97 * len(kp)       # the rest: float32 cosine ties / near-degenerate scatter matrices
+
+
+def test_sensitivity_variants(orc, synth):
+    """The oracle's variant switch (oracle/pcl_oracle.h): every variant is off by default and after a `with` block; the
+    Appendix-A alternatives (Eigen 4-lane dot order, float32 Umeyama moments) stay far inside the north-star bars on a
+    small case; the +-epsilon perturbations leave most rows bit-identical (they only move boundary cases)."""
+    model = synth.make_model("y", 3000)
+    kp = synth.voxel_grid(model, 0.02)
+    nrm = orc.normals(model, k=10)
+    base, rf = orc.shot352(model, nrm, kp, 0.03)
+    with orc.variant("dot4"):
+        alt, _ = orc.shot352(model, nrm, kp, 0.03)
+    again, _ = orc.shot352(model, nrm, kp, 0.03)
+    assert np.array_equal(base, again, equal_nan=True)            # the switch was restored
+    ok = ~np.isnan(base[:, 0])
+    assert np.linalg.norm(alt[ok] - base[ok], axis=1).max() < 1e-4
+    with orc.variant("root_up"):
+        nup = orc.normals(model, k=10)
+    assert np.nanmax(np.abs(nup - nrm)) < 1e-3 and np.mean(np.abs(nup - nrm).max(1) <= 1e-6) > 0.95
+    cloud = synth.voxel_grid(model, 0.01)
+    nc = orc.normals(cloud, radius=0.05)
+    f0 = orc.fpfh33(cloud, nc, 0.05)
+    with orc.variant("fpfh_bin_up"):
+        f1 = orc.fpfh33(cloud, nc, 0.05)
+    with orc.variant("fpfh_skip"):
+        f2 = orc.fpfh33(cloud, nc, 0.05)
+    same = np.all((f0 == f1) | (np.isnan(f0) & np.isnan(f1)), axis=1)
+    assert same.mean() > 0.9 and np.array_equal(f0, f2, equal_nan=True)
+    # float32 Umeyama moments: a rigid fit moves by far less than the pose bars
+    rng = np.random.default_rng(3)
+    src = rng.normal(size=(20, 3))
+    R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    R *= np.sign(np.linalg.det(R))
+    dst = src @ R.T + np.array([0.3, -0.2, 1.0])
+    T0 = orc.umeyama3(src, dst)
+    with orc.variant("umeyama_f32"):
+        T1 = orc.umeyama3(src, dst)
+    assert np.abs(T0 - T1).max() < 1e-5 and np.abs(T0[:3, :3] - R).max() < 1e-9
