@@ -244,7 +244,16 @@ def run_b200(args, rank, world, local_rank):
     # poses, clutter and noise, so K_s, the correspondence count and the number of instances differ from scene to
     # scene and from rank to rank) and registers them round-robin against the replicated model library.
     P = max(1, args.pool)
-    pool = [workload(rank * P + i, args.scene_points, args.model_points) for i in range(P)]
+    fixed_total = max(0, args.total_scenes)
+    if fixed_total:
+        # BASELINE config 5 as written: a fixed batch of scenes sharded over the ranks (scene g -> rank g mod world); the
+        # batch cycles through P distinct scenes (generating hundreds of distinct scenes on the host would take minutes);
+        # rank r's j-th scene is batch scene r + j * world
+        base = [workload(i, args.scene_points, args.model_points) for i in range(P)]
+        mine = [(rank + j * world) % P for j in range(P)]
+        pool = [base[i] for i in mine]
+    else:
+        pool = [workload(rank * P + i, args.scene_points, args.model_points) for i in range(P)]
     wl = pool[0]
     p = binding.shot_params(**PARAMS)
     peaks = {}
@@ -266,6 +275,9 @@ def run_b200(args, rank, world, local_rank):
     args.lanes = L
     args.blocking = blocking
     B = L * max(1, args.scenes_per_lane)   # scene registrations per step and rank
+    if fixed_total:
+        B = max(1, fixed_total // world)   # this rank's share of the batch (every rank the same: one gather per scene)
+        args.steps = 1
     streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
     ctxs = [binding.Context(local_rank, stream=st.cuda_stream) for st in streams]
     if blocking:
@@ -482,8 +494,10 @@ def run_b200(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": total_desc / total_s, "unit": "descriptors/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 for the SHOT frame/bin decisions)",
-            "data": "synthetic", "config": config_dict(args, wl, world, scenes_per_step=B * world),
+            "scaling": "strong" if fixed_total else "weak", "vs_baseline": None,
+            "dtype": "f32 (f64 for the SHOT frame/bin decisions)",
+            "data": "synthetic",
+            "config": config_dict(args, wl, world, scenes_per_step=fixed_total if fixed_total else B * world),
             "registrations_per_s": world * n_scene_steps / total_s,
             "timed_region_s": total_s,
             "lanes": L,
@@ -725,6 +739,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=6, help="scenes in flight per GPU (context + stream + host thread each)")
     ap.add_argument("--scenes-per-lane", type=int, default=8, help="a step = lanes x this many scene registrations per GPU")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic scenes per rank, registered round-robin")
+    ap.add_argument("--total-scenes", type=int, default=0,
+                    help="BASELINE config 5: a fixed batch of this many scenes sharded over the ranks in one step (strong "
+                         "scaling), e.g. --total-scenes 256 --scene-points 500000 --pool 8")
     ap.add_argument("--other-configs", type=int, default=1,
                     help="also measure BASELINE configs 1, 2 and 4 (small) and report them under other_configs")
     args = ap.parse_args()
