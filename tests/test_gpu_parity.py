@@ -806,3 +806,31 @@ def test_resident_fpfh_pipeline(ctx, orc, synth, b200):
     cm.close()
     cs.close()
     m.close()
+
+
+def test_desc_index_batched_k1_equals_single_queries(ctx, orc):
+    """b200_desc_index_knn with a batch of k = 1 queries goes through the correspondence-search machinery (tensor-core
+    filter + exact rescoring for large indices); the per-query call goes through the per-query kernel.  Same answers,
+    bit for bit, including rows with non-finite values on either side."""
+    rng = np.random.Generator(np.random.PCG64(9))
+    for K, D in ((3000, 352), (500, 352), (2000, 33)):
+        centres = rng.gamma(0.3, 1.0, (100, D)).astype(np.float32)
+        model = (centres[rng.integers(0, 100, K)] + 0.05 * rng.gamma(0.3, 1.0, (K, D))).astype(np.float32)
+        model /= np.linalg.norm(model, axis=1, keepdims=True)
+        q = (model[rng.integers(0, K, 300)] * rng.uniform(0.99, 1.01, (300, D))).astype(np.float32)
+        model[7, 3] = np.nan
+        q[11, 0] = np.inf
+        ix = ctx.desc_index(model)
+        bi, bd, kf = ix.knn(q, 1)
+        assert kf == 1
+        for r in (0, 5, 11, 42, 123, 299):
+            si, sd, _ = ix.knn(q[r:r + 1], 1)
+            if r == 11:
+                assert bi[r, 0] == -1
+                continue
+            assert si[0, 0] == bi[r, 0] and sd[0, 0].tobytes() == bd[r, 0].tobytes(), (K, D, r)
+        # and against the restatement's search on the valid rows
+        oc = orc.match(model, q, 1, 1e30, omp=True)
+        ok = oc["index_match"]
+        assert np.array_equal(bi[ok, 0], oc["index_query"]) and np.array_equal(bd[ok, 0], oc["distance"])
+        ix.close()
