@@ -834,3 +834,45 @@ def test_desc_index_batched_k1_equals_single_queries(ctx, orc):
         ok = oc["index_match"]
         assert np.array_equal(bi[ok, 0], oc["index_query"]) and np.array_equal(bd[ok, 0], oc["distance"])
         ix.close()
+
+
+def test_new_entry_points_edge_cases(ctx, b200, synth):
+    """Empty and degenerate inputs through the round-2 entry points: nothing crashes, nothing is invented."""
+    p = b200.shot_params(normal_k=10, descr_radius=0.02, match_mode=1, match_thr=0.25, gc_size=0.02, gc_threshold=2,
+                         max_instances=64)
+    model = synth.make_model("y", 3000)
+    kpm = synth.voxel_grid(model, 0.02)
+    m = ctx.model_create_shot(model, kpm, p)
+    scene = synth.make_scene(("y",), 8000, scene_id=3)
+    # sharded call without a communicator (world 1): no keypoints, then keypoints far away from the scene
+    r = ctx.register_scene_shot_sharded(m, p, scene, np.zeros((0, 3), np.float32))
+    assert r["n_instances"] == 0 and len(r["corrs"]) == 0
+    far = np.full((5, 3), 50.0, np.float32)
+    r = ctx.register_scene_shot_sharded(m, p, scene, far)
+    assert r["n_instances"] == 0 and len(r["corrs"]) == 0
+    m.close()
+    # FPFH pipeline: a model of three isolated points (no neighbour within the radius: PCL's histograms stay all zero)
+    pf = b200.shot_params(normal_k=0, normal_radius=0.05, descr_radius=0.05, match_mode=2, match_thr=0.0, gc_size=0.02,
+                          gc_threshold=3, max_instances=64)
+    tiny = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    mf = ctx.model_create_fpfh(tiny, pf)
+    dm, _ = mf.download()
+    assert dm.shape == (3, 33)
+    from oracle import pcl_oracle as orc_
+    assert np.array_equal(dm, orc_.fpfh33(tiny, orc_.normals(tiny, radius=0.05), 0.05), equal_nan=True)
+    kq = synth.voxel_grid(scene, 0.03)
+    r = ctx.register_scene_fpfh(mf, kq, pf, want_desc=True)
+    assert r["corrs"].tobytes() == orc_.match(dm, r["desc"], 2, 0.0).tobytes()
+    r = ctx.register_scene_fpfh(mf, np.zeros((0, 3), np.float32), pf)
+    assert r["n_instances"] == 0 and len(r["corrs"]) == 0
+    mf.close()
+    # a SHOT model cannot be used with the FPFH scene call
+    m = ctx.model_create_shot(model, kpm, p)
+    with pytest.raises(Exception):
+        ctx.register_scene_fpfh(m, kq, pf)
+    m.close()
+    # batched k = 1 index queries on an index without a single valid row
+    ix = ctx.desc_index(np.full((40, 352), np.nan, np.float32))
+    bi, bd, kf = ix.knn(np.ones((64, 352), np.float32), 1)
+    assert kf == 0 and np.all(bi == -1)
+    ix.close()
