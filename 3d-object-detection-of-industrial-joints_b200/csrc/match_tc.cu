@@ -162,7 +162,7 @@ __global__ void make_scale_kernel(const unsigned *__restrict__ absmax_bits, floa
 
 // One warp per row.  is_b = 0: row = [x1 | x1 | x2], is_b = 1: row = [x1 | x2 | x1] (terms == 3);
 // terms == 1: row = [x1].  Rows are zero padded to Kp halves.  norm2[row] = float32 sum of squares of
-// the ORIGINAL values (+inf for rows that are not valid).
+// the ORIGINAL values (3e38 for rows that are not valid).
 // row_map / n_rows_dev (both or neither): output row w is input row row_map[w], for w < *n_rows_dev only (the rows a
 // first pass could not certify; their number is known on the device only — rows beyond it are left untouched).
 __global__ void tc_prep_kernel(const float *__restrict__ X, int rows, int rows_padded, int D, int Kp, int terms,
@@ -186,7 +186,8 @@ __global__ void tc_prep_kernel(const float *__restrict__ X, int rows, int rows_p
   const bool ok = (src < rows) && (valid == nullptr || valid[src]);
   if (!ok) {
     for (int d = lane; d < Kp; d += 32) o[d] = __float2half_rn(0.f);
-    if (lane == 0) norm2[w] = __int_as_float(0x7f800000);
+    if (lane == 0) norm2[w] = 3.0e38f;  // "never the minimum", and finite: the filter's epilogue packs the column index
+                                        // into the value's low mantissa bits, which would turn +inf into a NaN
     return;
   }
   const float sc = scale[0];
@@ -219,7 +220,7 @@ struct TcParams {
   int Ks, Km;
   int m_tiles, n_tiles, n_split;
   int k_blocks;
-  const float *nb;     // |b_j|^2, padded to n_tiles * TC_BN (+inf padding)
+  const float *nb;     // |b_j|^2, padded to n_tiles * TC_BN (3e38 for padding and invalid rows)
   const float *scaleA;
   const float *scaleB;
   float *cand_s;       // [Ks][n_split * TC_CAND]
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float x = fminf(fmaf(m2inv, v[e + q], nbv[q]), 3.0e38f);  // +inf (padding) would turn into NaN below
+              const float x = fmaf(m2inv, v[e + q], nbv[q]);  // padding / invalid model rows carry |b|^2 = 3e38
               const float xb = __uint_as_float((__float_as_uint(x) & ~31u) | (unsigned)(e + q));
               m2 = fminf(m2, fmaxf(m1, xb));
               m1 = fminf(m1, xb);
