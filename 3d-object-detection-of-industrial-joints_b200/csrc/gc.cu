@@ -99,6 +99,12 @@ __device__ __forceinline__ float dist2f(const float4 &a, const float4 &b) {
   return s;
 }
 
+// PCL's float expression itself (taken by the pairs inside the estimate's error band: out of line, the IEEE square
+// roots are most of the test's code and it is inlined at every test site)
+__device__ __noinline__ bool gc_fits_exact(float a, float c, double gc_size) {
+  return !((double)fabsf(sqrtf(a) - sqrtf(c)) > gc_size);
+}
+
 // The grouping test with a fast path: `fits` <=> !gc_rejects.  sqrt.approx has a relative error of at
 // most 2^-22, so |estimate - float expression| < 1e-6 (sa + sc); pairs outside that band around the
 // threshold are decided by the estimate, the others evaluate the exact expression.
@@ -111,7 +117,7 @@ __device__ __forceinline__ bool gc_fits(const float4 &mk, const float4 &sk, cons
   const float tol = 1e-6f * (sa + sc) + 1e-15f;
   if (diff > g_hi + tol) return false;
   if (diff < g_lo - tol) return true;
-  return !((double)fabsf(sqrtf(a) - sqrtf(c)) > gc_size);
+  return gc_fits_exact(a, c, gc_size);
 }
 
 __device__ __forceinline__ int gc_row_words(int C) { return (((C + 31) >> 5) + 127) & ~127; }
@@ -240,8 +246,9 @@ __device__ __forceinline__ int first_bit128(const uint4 &w, int base) {
 // admission is a warp-wide integer min.  Rows are padded to a multiple of 128 words (32 groups).
 __global__ void __launch_bounds__(GG_THREADS, 1)
     gc_group_kernel(GroupArgs ga, const int *__restrict__ d_C, int C_cap, int dyn_smem_bytes, double gc_size, float g_lo,
-                    float g_hi, int gc_threshold, int max_inst) {
+                    float g_hi, int gc_threshold, int max_inst, const int *__restrict__ gate) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  if (gate && *gate == 0) return;  // the stream kernel has done the scene
   __shared__ int s_seed[GW], s_size[GW], s_conf[GW];
   __shared__ int s_nwin, s_big;
   __shared__ int s_hkey[G_HS], s_hval[G_HS];
@@ -619,8 +626,9 @@ __device__ __forceinline__ void dsmem_store(unsigned addr, int v) {
 
 __global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
     gc_group_cluster_kernel(GroupArgs ga, const int *__restrict__ d_C, int C_cap, double gc_size, float g_lo, float g_hi,
-                            int gc_threshold, int max_inst) {
+                            int gc_threshold, int max_inst, const int *__restrict__ gate) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  if (gate && *gate == 0) return;  // the stream kernel has done the scene (uniform over the cluster)
   __shared__ int s_res[2][GCL][1 + G_MC];  // published results by round parity: [0] size, then members
   __shared__ int s_seed[GCL];
   __shared__ int s_nwin;
@@ -925,6 +933,635 @@ __global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
     for (int i = 0; i < 8; ++i) ga.dbg[rank * 8 + i] = tc_[i];
 #endif
   if (rank == 0 && tid == 0) *ga.n_inst_out = n_inst;
+}
+
+// ---- greedy grouping as a stream on one SM ---------------------------------------------------------
+// The round-based kernels above pay, per round of eight seeds, two or three dependent trips to the bitmap rows in
+// L2 plus a cluster barrier: 7.8 us per round, 678 rounds on the target scene.  Here nothing that touches global
+// memory is on the sequential chain.  One CTA, three kinds of warps:
+//   * the dispatcher (warp 0) walks the `taken` flags and hands the next position that is not taken yet to the
+//     next production ticket, at most GS_NSLOT tickets ahead of the last commit;
+//   * producer warps stage a seed each: the seed's bitmap row is read once (lane l owns a contiguous 1/32 of the
+//     row, so the candidates a lane finds are consecutive in the ascending list and one warp scan places them),
+//     what is taken already is dropped, the lowest candidate's row is read too and every candidate is marked with
+//     whether it fits that first candidate (bit 31 of its index — the first admission's tests, three quarters of all
+//     pair tests of a seed, come out of the bitmap instead of being recomputed); the list and the candidates' model /
+//     scene points go into a ring buffer in shared memory (32-candidate blocks: index + 6 coordinates, one
+//     128-byte line per field).  Ring space is handed out in ticket order, so the chunk of the seed the consumers
+//     wait for is always allocated before any later one and the ring cannot deadlock;
+//   * consumer warps take the staged seeds in order.  A consumer filters the list against the live `taken` flags
+//     and grows the consensus set in the points domain entirely out of shared memory (lowest live candidate by
+//     redux.min, its points broadcast, every lane tests the candidates it owns: PCL's loop over j, in j order),
+//     then waits for its turn to commit.  At its turn every earlier seed has committed: if the seed was taken in the
+//     meantime it is dropped; if one of the set's members was taken the growth is repeated (from shared memory, no
+//     load); otherwise the set is exactly what the sequential algorithm computes (a set grown against older flags
+//     stays exact as long as none of its members has been taken since).  Inside the turn only the flags and the
+//     running totals are updated; the member list goes to global memory after the turn has been passed on.
+// All hand-overs are mbarriers (count 1, one phase per use of a slot) waited on with a suspend-time hint: the
+// hardware parks the waiting warp.  (Polling — volatile loads with __nanosleep, or try_wait with the default time
+// limit — left the working warps a third of the SM's issue slots: 58 % of the executed instructions were the wait
+// loops, and their S2R saturated the XU pipe.)
+// Target scene: 4 276 seeds, 183 candidates per seed on average (1 285 at most), 5.9 members per set; with eight
+// consumers 8 % of the sets are grown twice.  A seed with more than GS_LCAP live candidates, or more than 32 768
+// correspondences, sends the scene to the round-based kernel instead (flag on the device, no host round trip).
+constexpr int GS_PROD = 15;
+constexpr int GS_CONS = 8;
+constexpr int GS_THREADS = (1 + GS_PROD + GS_CONS) * 32;
+constexpr int GS_NSLOT = 32;            // seeds staged or being staged (> GS_PROD)
+constexpr int GS_LCAP = 2048;           // candidates per seed: 64 per lane, one 64-bit mask
+constexpr int GS_MAXQ = 8;              // 16-byte row pieces per lane: rows of up to 32 768 positions
+constexpr int GS_BLK = 7 * 128;         // bytes of a 32-candidate block
+constexpr int GS_NBLK = 224;            // ring blocks (196 KB)
+constexpr int GS_MAX_ROW_WORDS = GS_MAXQ * 128;
+
+struct StreamState {
+  unsigned long long bar_disp[GS_NSLOT];    // ticket t has its position
+  unsigned long long bar_alloc[GS_NSLOT];   // ticket t may take ring space
+  unsigned long long bar_ready[GS_NSLOT];   // slot staged
+  unsigned long long bar_commit[GS_NSLOT];  // ticket u may commit
+  unsigned long long bar_free[GS_NSLOT];    // slot's previous ticket committed
+  int seed[GS_NSLOT], n[GS_NSLOT], blk[GS_NSLOT], vend[GS_NSLOT];
+  int issue;             // next production ticket
+  int alloc_done;        // tickets that have their ring space
+  int commit_done;       // tickets committed
+  int ring_head;         // virtual block counters: [ring_tail, ring_head) is in use
+  int ring_tail;
+  int take;              // next consumer ticket
+  int end_ticket;        // first ticket past the last position
+  int abort;
+  int total, n_inst;
+};
+
+__device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// true once the phase with this parity has completed; the hardware parks the warp for a short, system-defined time
+// (about 0.1 us on B200) before it answers "not yet"
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// A hand-over that takes longer than about two seconds cannot be a healthy pipeline: the kernel then raises
+// `abort`, records where it was (fallback[1..]) and the round-based kernel does the scene.
+__device__ __noinline__ void gs_give_up(StreamState &S, int *fallback, int code, int ticket) {
+  if (atomicCAS(&S.abort, 0, 1) == 0) {
+    fallback[1] = code;
+    fallback[2] = ticket;
+    fallback[3] = ld_vol(&S.issue), fallback[4] = ld_vol(&S.commit_done);
+    fallback[5] = ld_vol(&S.ring_head), fallback[6] = ld_vol(&S.ring_tail);
+    fallback[7] = ld_vol(&S.end_ticket);
+    __threadfence();
+    fallback[0] = 1;
+  }
+}
+// The wait loop is two instructions (try_wait, branch); abort flag and watchdog are looked at every 1024 tries.
+// sleep_ns > 0: for waits nobody downstream is waiting on (the pipeline is several tickets deep there) the warp
+// sleeps between two looks, so that the shared-memory pipe is left to the warps that work.
+// (A suspend-time hint of 20 us parks the warp properly but wakes it about 2 us after the arrival.  A loop that
+// also read the clock and the abort flag each time took 58 % of the SM's issue slots and saturated the XU pipe with
+// its S2R.  The kernel's code must stay small: 24 warps in different phases share a 32 KB instruction cache.)
+__device__ __noinline__ void gs_wait(StreamState &S, int *fallback, unsigned bar, unsigned parity, unsigned sleep_ns, int code,
+                                     int ticket) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = 0;
+  unsigned tries = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+    if ((++tries & 1023u) == 0) {
+      if (ld_vol(&S.abort)) return;
+      if (t0 == 0)
+        t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) {
+        gs_give_up(S, fallback, code, ticket);
+        return;
+      }
+    }
+  }
+}
+#define GS_GIVE_UP(code, ticket) gs_give_up(S, fallback, (code), (ticket))
+#define GS_WAIT(bar, parity, code, ticket) gs_wait(S, fallback, (bar), (parity), 0u, (code), (ticket))
+#define GS_WAIT_COARSE(bar, parity, ns, code, ticket) gs_wait(S, fallback, (bar), (parity), (ns), (code), (ticket))
+
+// A consumer's result: the admitted candidates as a mask over the chunk's blocks (bit k of lane l = list position
+// 32 k + l; 64 blocks = two words), the set size (seed included), and whether the seed was found taken.
+struct StreamEval {
+  unsigned mlo, mhi;
+  int size;
+  bool skip;
+};
+
+__device__ __forceinline__ bool gs_taken(const unsigned *s_taken, int j) {
+  return ((ld_vol(reinterpret_cast<const int *>(s_taken) + (j >> 5)) >> (j & 31)) & 1) != 0;
+}
+
+// Growth of one seed's set by one warp from its staged chunk.  Candidate at list position q lives in block q >> 5,
+// lane q & 31; lane l owns the positions congruent to l.
+__device__ __forceinline__ StreamEval stream_grow(const unsigned *s_taken, const unsigned char *chunk, int seed, int n, int lane,
+                                               float g_lo, float g_hi, double gc_size) {
+  StreamEval r;
+  r.mlo = r.mhi = 0u;
+  r.size = 1;
+  // one answer for the warp: the flag may flip (another consumer's commit) between two lanes' reads
+  r.skip = __any_sync(0xffffffffu, gs_taken(s_taken, seed));
+  if (r.skip) return r;
+  unsigned alo = 0u, ahi = 0u, flo = 0u, fhi = 0u;
+  const int nb = (n + 31) >> 5;
+  for (int k = 0; k < nb; ++k) {
+    if (k * 32 + lane < n) {
+      const unsigned w = *reinterpret_cast<const unsigned *>(chunk + k * GS_BLK + lane * 4);
+      const unsigned bit = 1u << (k & 31);
+      const bool live = !gs_taken(s_taken, (int)(w & 0x7fffffffu));
+      if (k < 32) {
+        if (live) alo |= bit;
+        if (w >> 31) flo |= bit;
+      } else {
+        if (live) ahi |= bit;
+        if (w >> 31) fhi |= bit;
+      }
+    }
+  }
+  bool first = true;
+  while (true) {
+    const int mine = alo ? (((__ffs((int)alo) - 1) << 5) | lane) : (ahi ? (((__ffs((int)ahi) + 31) << 5) | lane) : 0x7fffffff);
+    const int c = __reduce_min_sync(0xffffffffu, mine);
+    if (c == 0x7fffffff) break;
+    const int ck = c >> 5, cl = c & 31;
+    if (lane == cl) {
+      if (ck < 32) {
+        r.mlo |= 1u << ck;
+        alo &= ~(1u << ck);
+      } else {
+        r.mhi |= 1u << (ck - 32);
+        ahi &= ~(1u << (ck - 32));
+      }
+    }
+    ++r.size;
+    if (first && c == 0) {  // the list's first candidate: its tests were read off the bitmap by the producer
+      alo &= flo;
+      ahi &= fhi;
+      first = false;
+      continue;
+    }
+    first = false;
+    const float *cb = reinterpret_cast<const float *>(chunk + ck * GS_BLK) + cl;
+    const float4 mk = make_float4(cb[32], cb[64], cb[96], 0.f);
+    const float4 sk = make_float4(cb[128], cb[160], cb[192], 0.f);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      unsigned a = h ? ahi : alo, keep = a;
+      const unsigned char *hb = chunk + h * 32 * GS_BLK;
+      while (a) {
+        const int kk = __ffs((int)a) - 1;
+        a &= a - 1;
+        const float *pb = reinterpret_cast<const float *>(hb + kk * GS_BLK) + lane;
+        const float4 mj = make_float4(pb[32], pb[64], pb[96], 0.f);
+        const float4 sj = make_float4(pb[128], pb[160], pb[192], 0.f);
+        if (!gc_fits(mk, sk, mj, sj, g_lo, g_hi, gc_size)) keep &= ~(1u << kk);
+      }
+      if (h)
+        ahi = keep;
+      else
+        alo = keep;
+      if (nb <= 32) break;
+    }
+  }
+  return r;
+}
+
+// Writes the positions of the set bits of one 64-bit piece of a candidate row (first position `base`) into the
+// chunk's index list from list position o on; returns the next list position.
+__device__ __forceinline__ int stream_list_piece(unsigned long long v, int base, unsigned char *chunk, int o) {
+  while (v) {
+    const int b = __ffsll((long long)v) - 1;
+    v &= v - 1;
+    *reinterpret_cast<unsigned *>(chunk + (o >> 5) * GS_BLK + (o & 31) * 4) = (unsigned)(base + b);
+    ++o;
+  }
+  return o;
+}
+
+struct StreamCommit {
+  unsigned *s_taken;
+  StreamState *S;
+  int *members;
+  int *inst_offsets;
+  int gc_threshold, max_inst;
+  float g_lo, g_hi;
+  double gc_size;
+  long long *tq;  // timing builds
+};
+
+// The in-order part of a consumer's work (it holds the commit turn) and the write-out behind it.
+// Returns after the turn has been passed on and the slot released.
+__device__ __forceinline__ void stream_commit(const StreamCommit &cc, StreamEval ev, const unsigned char *chunk, int seed, int n,
+                                           int lane, unsigned bar_next_commit, int ticket, unsigned bar_free, int vend) {
+  StreamState &S = *cc.S;
+#ifdef B200_GC_TIMING
+  long long c_a = clock64();
+#endif
+  // members into registers (two per lane; a lane with more makes the set a `wide` one)
+  int j0 = -1, j1 = -1, k0 = 0, k1 = 0;
+  bool wide = false;
+  if (!ev.skip) {
+    bool bad = gs_taken(cc.s_taken, seed);
+    for (int pass = 0; pass < 2; ++pass) {
+      j0 = j1 = -1;
+      wide = false;
+      int cnt = 0;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        unsigned a = h ? ev.mhi : ev.mlo;
+        while (a) {
+          const int kk = __ffs((int)a) - 1 + h * 32;
+          a &= a - 1;
+          const int j = (int)(*reinterpret_cast<const unsigned *>(chunk + kk * GS_BLK + lane * 4) & 0x7fffffffu);
+          bad = bad || gs_taken(cc.s_taken, j);
+          if (cnt == 0)
+            j0 = j, k0 = kk;
+          else if (cnt == 1)
+            j1 = j, k1 = kk;
+          else
+            wide = true;
+          ++cnt;
+        }
+      }
+      if (pass == 1 || !__any_sync(0xffffffffu, bad)) break;
+      if (__any_sync(0xffffffffu, gs_taken(cc.s_taken, seed))) {  // the seed itself went
+        ev.skip = true;
+        break;
+      }
+      ev = stream_grow(cc.s_taken, chunk, seed, n, lane, cc.g_lo, cc.g_hi, cc.gc_size);  // exact now: nothing is in flight before us
+#ifdef B200_GC_TIMING
+      cc.tq[6] += 1;
+#endif
+      bad = false;
+    }
+  }
+#ifdef B200_GC_TIMING
+  {
+    const long long c_b = clock64();
+    cc.tq[4] += c_b - c_a;
+    c_a = c_b;
+  }
+#endif
+  const bool emit = !ev.skip && ev.size > cc.gc_threshold;
+  wide = __any_sync(0xffffffffu, wide);
+  int total = 0, ninst = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  if (emit) {
+    if (lane == 0) {
+      total = ld_vol(&S.total), ninst = ld_vol(&S.n_inst);
+      st_vol(&S.total, total + ev.size);
+      st_vol(&S.n_inst, ninst + 1);
+      atomicOr(&cc.s_taken[seed >> 5], 1u << (seed & 31));
+    }
+    if (!wide) {
+      if (j0 >= 0) atomicOr(&cc.s_taken[j0 >> 5], 1u << (j0 & 31));
+      if (j1 >= 0) atomicOr(&cc.s_taken[j1 >> 5], 1u << (j1 & 31));
+    } else {
+      // a set with more than two members in some lane: flags and member list straight from the chunk, inside the turn
+      total = __shfl_sync(0xffffffffu, total, 0);
+      int run = 1;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const unsigned mine = h ? ev.mhi : ev.mlo;
+        unsigned any = __reduce_or_sync(0xffffffffu, mine);
+        while (any) {
+          const int kb = __ffs((int)any) - 1;
+          any &= any - 1;
+          const bool in = (mine >> kb) & 1u;
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          if (in) {
+            const int j = (int)(*reinterpret_cast<const unsigned *>(chunk + (kb + h * 32) * GS_BLK + lane * 4) & 0x7fffffffu);
+            cc.members[total + run + __popc(bal & lt_mask)] = j;
+            atomicOr(&cc.s_taken[j >> 5], 1u << (j & 31));
+          }
+          run += __popc(bal);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    st_vol(&S.ring_tail, vend);
+    st_vol(&S.commit_done, ticket + 1);
+    mbar_arrive(bar_next_commit);  // the next ticket's turn
+    mbar_arrive(bar_free);         // the slot may be staged again
+  }
+#ifdef B200_GC_TIMING
+  {
+    const long long c_b = clock64();
+    cc.tq[5] += c_b - c_a;
+    c_a = c_b;
+  }
+#endif
+  // ---- behind the turn: the member list ----
+  if (emit) {
+    total = __shfl_sync(0xffffffffu, total, 0);
+    ninst = __shfl_sync(0xffffffffu, ninst, 0);
+    if (lane == 0) {
+      cc.members[total] = seed;
+      if (ninst < cc.max_inst) cc.inst_offsets[ninst + 1] = total + ev.size;
+    }
+    if (!wide) {
+      int run = 1;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const unsigned mine = h ? ev.mhi : ev.mlo;
+        unsigned any = __reduce_or_sync(0xffffffffu, mine);
+        while (any) {
+          const int kb = __ffs((int)any) - 1;
+          any &= any - 1;
+          const bool in = (mine >> kb) & 1u;
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          if (in) cc.members[total + run + __popc(bal & lt_mask)] = (j0 >= 0 && k0 == kb + h * 32) ? j0 : j1;
+          run += __popc(bal);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+    gc_group_stream_kernel(GroupArgs ga, const int *__restrict__ d_C, int C_cap, double gc_size, float g_lo, float g_hi,
+                           int gc_threshold, int max_inst, int *__restrict__ fallback) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ __align__(8) StreamState S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = min(*d_C, C_cap);
+  const int row_words = gc_row_words(C);
+  if (row_words > GS_MAX_ROW_WORDS) {  // uniform
+    if (tid == 0) *fallback = 1;
+    return;
+  }
+  const int nq = row_words >> 7;
+  unsigned *s_taken = reinterpret_cast<unsigned *>(s_raw);
+  const uint4 *s_taken4 = reinterpret_cast<const uint4 *>(s_raw);
+  unsigned char *ring = s_raw + GS_MAX_ROW_WORDS * 4;
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&S.bar_disp[0]);
+  const unsigned BAR_DISP = bar0, BAR_ALLOC = bar0 + 8 * GS_NSLOT, BAR_READY = bar0 + 16 * GS_NSLOT,
+                 BAR_COMMIT = bar0 + 24 * GS_NSLOT, BAR_FREE = bar0 + 32 * GS_NSLOT;
+
+  for (int w = tid; w < row_words; w += GS_THREADS) {
+    const int j0 = w * 32;
+    s_taken[w] = (j0 + 32 <= C) ? 0u : ((j0 >= C) ? ~0u : ~((1u << (C - j0)) - 1u));  // padding counts as taken
+  }
+  if (tid < 5 * GS_NSLOT) mbar_init(bar0 + 8 * tid, 1);
+  if (tid == 0) {
+    S.issue = S.alloc_done = S.commit_done = S.ring_head = S.ring_tail = 0;
+    S.take = 0;
+    S.end_ticket = 0x7fffffff;
+    S.abort = 0;
+    S.total = S.n_inst = 0;
+    ga.inst_offsets[0] = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {  // ticket 0 has no predecessor
+    mbar_arrive(BAR_ALLOC);
+    mbar_arrive(BAR_COMMIT);
+  }
+#ifdef B200_GC_TIMING
+  long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tl = clock64();
+#define ST(i)                      \
+  do {                             \
+    const long long n__ = clock64(); \
+    tq[i] += n__ - tl;             \
+    tl = n__;                      \
+  } while (0)
+#else
+#define ST(i)
+#endif
+
+  if (warp == 0) {
+    // ------------------------------------------------ dispatcher ----------------------------------------------
+    if (lane == 0) {
+      int pos = 0, ends = 0;
+      for (int t = 0;; ++t) {
+        const int s = t & (GS_NSLOT - 1);
+        if (t >= GS_NSLOT) GS_WAIT_COARSE(BAR_FREE + 8 * s, ((t / GS_NSLOT) - 1) & 1, 100, 1, t);
+        ST(0);
+        if (ld_vol(&S.abort)) break;
+        int p = -1;
+        int w = pos >> 5;
+        unsigned bits = 0u;
+        if (w < row_words) {
+          bits = ~s_taken[w] & ~((1u << (pos & 31)) - 1u);
+          while (!bits && ++w < row_words) bits = ~s_taken[w];
+        }
+        if (bits) {
+          p = w * 32 + __ffs(bits) - 1;
+          pos = p + 1;
+        } else {
+          pos = row_words * 32;
+          if (ends == 0) st_vol(&S.end_ticket, t);
+          ++ends;
+        }
+        st_vol(&S.seed[s], p);
+        mbar_arrive(BAR_DISP + 8 * s);
+        ST(1);
+#ifdef B200_GC_TIMING
+        tq[7] += 1;
+#endif
+        if (ends == GS_PROD) break;  // every producer gets one end marker (and passes it on to a consumer)
+      }
+    }
+  } else if (warp <= GS_PROD) {
+    // ------------------------------------------------ producer ------------------------------------------------
+    while (true) {
+      int t = 0, p = -1;
+      if (lane == 0) {
+        t = atomicAdd(&S.issue, 1);
+        GS_WAIT_COARSE(BAR_DISP + 8 * (t & (GS_NSLOT - 1)), (t / GS_NSLOT) & 1, 100, 2, t);
+        p = ld_vol(&S.seed[t & (GS_NSLOT - 1)]);
+      }
+      t = __shfl_sync(0xffffffffu, t, 0);
+      p = __shfl_sync(0xffffffffu, p, 0);
+      ST(0);
+      if (ld_vol(&S.abort)) break;
+      const int s = t & (GS_NSLOT - 1), sn = (t + 1) & (GS_NSLOT - 1);
+      const unsigned par = (t / GS_NSLOT) & 1;
+      if (p < 0) {  // past the last position: an end marker for the consumer that draws this ticket
+        if (lane == 0) mbar_arrive(BAR_READY + 8 * s);
+        break;
+      }
+      // the seed's row without what is taken already; lane l owns pieces [l nq, (l + 1) nq): its candidates are
+      // consecutive in the ascending list.  Pieces that are taken completely are not read.
+      const uint4 *row4 = reinterpret_cast<const uint4 *>(ga.adj + (size_t)p * row_words) + lane * nq;
+      const uint4 *tk4 = s_taken4 + lane * nq;
+      uint4 x[GS_MAXQ];
+#pragma unroll
+      for (int i = 0; i < GS_MAXQ; ++i) {
+        x[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < nq) {
+          const uint4 tk = tk4[i];
+          if ((tk.x & tk.y & tk.z & tk.w) != ~0u) x[i] = __ldg(row4 + i);
+        }
+      }
+      int cnt = 0;
+#pragma unroll
+      for (int i = GS_MAXQ - 1; i >= 0; --i) {
+        if (i < nq) {
+          const uint4 tk = tk4[i];
+          x[i].x &= ~tk.x, x[i].y &= ~tk.y, x[i].z &= ~tk.z, x[i].w &= ~tk.w;
+          cnt += __popc(x[i].x) + __popc(x[i].y) + __popc(x[i].z) + __popc(x[i].w);
+        }
+      }
+      const int incl = warp_incl_scan(cnt, lane);
+      int o = incl - cnt;
+      const int n0 = __shfl_sync(0xffffffffu, incl, 31);
+      ST(1);
+      // ring space, in ticket order
+      const int nb = (n0 + 31) >> 5;
+      int start = 0;
+      if (lane == 0) {
+        while (t - ld_vol(&S.alloc_done) > 2 && !ld_vol(&S.abort)) __nanosleep(150);  // only the next two look at the barrier
+        GS_WAIT(BAR_ALLOC + 8 * s, par, 3, t);
+        if (n0 > GS_LCAP) {
+          *fallback = 1;
+          st_vol(&S.abort, 1);
+        }
+        int H = ld_vol(&S.ring_head);
+        start = H % GS_NBLK;
+        if (nb > 0 && start + nb > GS_NBLK) {
+          H += GS_NBLK - start;
+          start = 0;
+        }
+        if (H + nb - ld_vol(&S.ring_tail) > GS_NBLK) {
+          const long long t0 = clock64();
+          while (H + nb - ld_vol(&S.ring_tail) > GS_NBLK && !ld_vol(&S.abort)) {
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000000ll) {
+              GS_GIVE_UP(4, t);
+              break;
+            }
+          }
+        }
+        st_vol(&S.blk[s], start);
+        st_vol(&S.vend[s], H + nb);
+        st_vol(&S.ring_head, H + nb);
+        st_vol(&S.alloc_done, t + 1);
+        mbar_arrive(BAR_ALLOC + 8 * sn);
+      }
+      start = __shfl_sync(0xffffffffu, start, 0);
+      ST(2);
+      if (ld_vol(&S.abort)) break;
+      unsigned char *chunk = ring + (size_t)start * GS_BLK;
+      // candidate indices in ascending order
+#pragma unroll
+      for (int i = 0; i < GS_MAXQ; ++i) {
+        if (i < nq) {
+          const int base = (lane * nq + i) * 128;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const unsigned long long v = h ? (((unsigned long long)x[i].w << 32) | x[i].z) : (((unsigned long long)x[i].y << 32) | x[i].x);
+            if (v) o = stream_list_piece(v, base + h * 64, chunk, o);
+          }
+        }
+      }
+      __syncwarp();
+      ST(3);
+      // their points, and whether they fit the first candidate (its bitmap row: bit 31 of the index)
+      const unsigned *rowc = ga.adj + (size_t)(nb ? *reinterpret_cast<const unsigned *>(chunk) : 0u) * row_words;  // list[0]
+      for (int k0 = 0; k0 < nb; k0 += 4) {
+        int j[4];
+        float4 m[4], sc[4];
+        unsigned fw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u;
+          j[u] = (k < nb && k * 32 + lane < n0) ? *reinterpret_cast<const int *>(chunk + k * GS_BLK + lane * 4) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j[u] >= 0) {
+            m[u] = __ldg(ga.mp + j[u]);
+            sc[u] = __ldg(ga.sp + j[u]);
+            fw[u] = __ldg(rowc + (j[u] >> 5));
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j[u] >= 0) {
+            unsigned char *blk = chunk + (k0 + u) * GS_BLK;
+            float *pb = reinterpret_cast<float *>(blk) + lane;
+            if ((fw[u] >> (j[u] & 31)) & 1u) *reinterpret_cast<unsigned *>(blk + lane * 4) = (unsigned)j[u] | 0x80000000u;
+            pb[32] = m[u].x, pb[64] = m[u].y, pb[96] = m[u].z;
+            pb[128] = sc[u].x, pb[160] = sc[u].y, pb[192] = sc[u].z;
+          }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        st_vol(&S.n[s], n0);
+        mbar_arrive(BAR_READY + 8 * s);
+      }
+      ST(4);
+#ifdef B200_GC_TIMING
+      tq[7] += 1;
+#endif
+    }
+  } else {
+    // ------------------------------------------------ consumer ------------------------------------------------
+    StreamCommit cc;
+    cc.s_taken = s_taken;
+    cc.S = &S;
+    cc.members = ga.members;
+    cc.inst_offsets = ga.inst_offsets;
+    cc.gc_threshold = gc_threshold;
+    cc.max_inst = max_inst;
+    cc.g_lo = g_lo, cc.g_hi = g_hi, cc.gc_size = gc_size;
+    cc.tq = nullptr;
+#ifdef B200_GC_TIMING
+    cc.tq = tq;
+#endif
+    // Tickets are dealt round-robin (consumer c takes c, c + GS_CONS, ...).  Only the consumers whose turn is at most
+    // two commits away look at their barrier; the others sleep on the commit counter.
+    const int cw = warp - 1 - GS_PROD;
+    for (int u = cw;; u += GS_CONS) {
+      if (lane == 0) GS_WAIT_COARSE(BAR_READY + 8 * (u & (GS_NSLOT - 1)), (u / GS_NSLOT) & 1, 40, 5, u);
+      __syncwarp();
+      ST(0);
+      const int s = u & (GS_NSLOT - 1);
+      const int seed = ld_vol(&S.seed[s]);
+      const bool aborted = ld_vol(&S.abort) != 0;
+      if (aborted || seed < 0) {  // past the last position (or giving up)
+        if (!aborted && u == ld_vol(&S.end_ticket) && lane == 0) {  // every seed before the end has committed: result count
+          GS_WAIT(BAR_COMMIT + 8 * s, (u / GS_NSLOT) & 1, 6, u);
+          if (!ld_vol(&S.abort)) *ga.n_inst_out = ld_vol(&S.n_inst);
+        }
+        break;
+      }
+      const int n = ld_vol(&S.n[s]), vend = ld_vol(&S.vend[s]);
+      const unsigned char *chunk = ring + (size_t)ld_vol(&S.blk[s]) * GS_BLK;
+      const StreamEval ev = stream_grow(s_taken, chunk, seed, n, lane, g_lo, g_hi, gc_size);
+      ST(1);
+      if (lane == 0) {
+        while (u - ld_vol(&S.commit_done) > 2 && !ld_vol(&S.abort)) __nanosleep(100);  // only the next two look at the barrier
+        GS_WAIT(BAR_COMMIT + 8 * s, (u / GS_NSLOT) & 1, 7, u);
+      }
+      __syncwarp();
+      ST(2);
+      stream_commit(cc, ev, chunk, seed, n, lane, BAR_COMMIT + 8 * ((u + 1) & (GS_NSLOT - 1)), u, BAR_FREE + 8 * s, vend);
+      ST(3);
+#ifdef B200_GC_TIMING
+      tq[7] += 1;
+#endif
+    }
+  }
+#ifdef B200_GC_TIMING
+  if (ga.dbg && lane == 0)
+    for (int i = 0; i < 8; ++i) ga.dbg[warp * 8 + i] = tq[i];
+#endif
 }
 
 // ---- RANSAC pose per instance -------------------------------------------------------------------
@@ -1419,7 +2056,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   DevBuf<b200_corr> sorted;
   DevBuf<float4> mp, sp;
   DevBuf<unsigned> adj;
-  DevBuf<int> overflow, members;
+  DevBuf<int> overflow, members, fb;
   B200_TRY(sorted.alloc(ctx, (size_t)C_eff));
   B200_TRY(mp.alloc(ctx, (size_t)C_eff));
   B200_TRY(sp.alloc(ctx, (size_t)C_eff));
@@ -1438,6 +2075,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   }
   B200_TRY(overflow.alloc(ctx, (size_t)std::max(GW, GCL) * C_eff));
   B200_TRY(members.alloc(ctx, (size_t)C_eff));
+  B200_TRY(fb.alloc(ctx, 16));
   GroupArgs ga;
   ga.adj = adj.p;
   ga.mp = mp.p;
@@ -1450,7 +2088,7 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   const bool debug = getenv("B200_GC_DEBUG") != nullptr;
   ga.dbg = nullptr;
   if (debug) {
-    B200_TRY(dbg.alloc(ctx, GW * 8));
+    B200_TRY(dbg.alloc(ctx, 256));
     B200_TRY(dbg.zero());
     ga.dbg = dbg.p;
   }
@@ -1460,14 +2098,28 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   {
     StageScope st_(ctx, ST_GC_GROUP);
     const size_t row_bytes = (size_t)row_words_cap * sizeof(unsigned);
-    const char *sel = getenv("B200_GC_GROUP");
+    const char *sel = getenv("B200_GC_GROUP");  // "cluster" (default) | "cta" | "stream" (experimental, see its header)
+    const bool use_stream = sel && !strcmp(sel, "stream") && row_words_cap <= GS_MAX_ROW_WORDS;
+    const int *gate = nullptr;
+    if (use_stream) {
+      // one CTA: producer warps stage the seeds' candidates in shared memory, consumer warps grow and commit in order.
+      // A scene it cannot take (a seed with more than GS_LCAP live candidates) raises the flag and the round-based
+      // kernel launched behind it does the scene instead; otherwise that launch returns at once.
+      B200_CUDA(ctx, cudaMemsetAsync(fb.p, 0, 16 * sizeof(int), ctx->stream));
+      const size_t smem = (size_t)GS_MAX_ROW_WORDS * 4 + (size_t)GS_NBLK * GS_BLK;
+      B200_CUDA(ctx, ensure_dyn_smem(gc_group_stream_kernel, smem));
+      gc_group_stream_kernel<<<1, GS_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, gc_size, g_lo, g_hi, gc_threshold, max_inst,
+                                                                  fb.p);
+      B200_LAUNCHED(ctx);
+      gate = fb.p;
+    }
     const bool use_cluster = !(sel && !strcmp(sel, "cta")) && 2 * row_bytes <= 200 * 1024;
     if (use_cluster) {
       // one 8-CTA cluster: a seed per CTA; shared memory = taken bitmap + candidate bitmap
       const size_t smem = 2 * row_bytes;
       B200_CUDA(ctx, ensure_dyn_smem(gc_group_cluster_kernel, smem));
       gc_group_cluster_kernel<<<GCL, GCL_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, gc_size, g_lo, g_hi, gc_threshold,
-                                                                      max_inst);
+                                                                      max_inst, gate);
       B200_LAUNCHED(ctx);
     } else {
       // single CTA: the taken bitmap plus one candidate bitmap per concurrently evaluated seed
@@ -1476,11 +2128,28 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
       const size_t smem = std::min(budget, row_bytes * (size_t)(1 + GW));
       B200_CUDA(ctx, ensure_dyn_smem(gc_group_kernel, smem));
       gc_group_kernel<<<1, GG_THREADS, smem, ctx->stream>>>(ga, d_C, C_eff, (int)smem, gc_size, g_lo, g_hi, gc_threshold,
-                                                            max_inst);
+                                                            max_inst, gate);
       B200_LAUNCHED(ctx);
     }
   }
   if (debug) {
+    int f[16];
+    B200_CUDA(ctx, cudaMemcpyAsync(f, fb.p, sizeof(f), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
+    fprintf(stderr, "gc_group stream: handed over %d, wait %d ticket %d | issue %d take %d head %d tail %d end %d\n", f[0], f[1], f[2],
+            f[3], f[4], f[5], f[6], f[7]);
+  }
+  if (debug && getenv("B200_GC_STREAM_TIMING")) {
+    long long h[256];
+    B200_CUDA(ctx, cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(ctx, ctx->sync());
+    for (int w = 0; w < 1 + GS_PROD + GS_CONS; ++w)
+      fprintf(stderr,
+              w == 0 ? "dispatcher %2d: wait-free %lld pick %lld (%lld %lld %lld %lld %lld) tickets %lld\n"
+                     : (w <= GS_PROD ? "producer %2d: wait-turn %lld row %lld wait-ring %lld list %lld gather %lld (%lld %lld) slots %lld\n"
+                                     : "consumer %2d: wait-ready %lld grow %lld wait-commit %lld commit %lld [validate %lld in-turn %lld] regrown %lld slots %lld\n"),
+              w, h[w * 8], h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6], h[w * 8 + 7]);
+  } else if (debug) {
     long long h[GW * 8];
     B200_CUDA(ctx, cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(ctx, ctx->sync());

@@ -352,6 +352,63 @@ def test_gc_large_instances(ctx, orc, b200):
         assert _rot_angle_deg(A[:3, :3].astype(np.float64), B[:3, :3].astype(np.float64)) < 0.01
 
 
+def _rigid_instances_case(b200, sizes, n_model, n_clutter, seed):
+    from scipy.spatial.transform import Rotation
+    rng = _rng(seed)
+    model = rng.uniform(-0.3, 0.3, (n_model, 3)).astype(np.float32)
+    parts, corr_parts = [], []
+    base = 0
+    for k, n_in in enumerate(sizes):
+        R = Rotation.random(random_state=seed + k).as_matrix()
+        t = rng.uniform(-1, 1, 3) + 3 * (k + 1)
+        sel = rng.permutation(n_model)[:n_in]
+        pts = (model[sel].astype(np.float64) @ R.T + t + rng.normal(0, 0.0005, (n_in, 3))).astype(np.float32)
+        parts.append(pts)
+        c = np.zeros(n_in, dtype=b200.CORR_DTYPE)
+        c["index_query"], c["index_match"] = sel, base + np.arange(n_in)
+        corr_parts.append(c)
+        base += n_in
+    parts.append(rng.uniform(-2, 3 * len(sizes) + 2, (n_clutter, 3)).astype(np.float32))
+    c = np.zeros(n_clutter, dtype=b200.CORR_DTYPE)
+    c["index_query"], c["index_match"] = rng.integers(0, n_model, n_clutter), base + np.arange(n_clutter)
+    corr_parts.append(c)
+    corrs = np.concatenate(corr_parts)
+    corrs["distance"] = rng.uniform(0, 0.25, len(corrs)).astype(np.float32)
+    return model, np.concatenate(parts), corrs[rng.permutation(len(corrs))]
+
+
+def test_gc_group_kernel_variants(ctx, orc, synth, small, b200, monkeypatch):
+    """The grouping kernels — the round-based cluster kernel (default), the single-CTA one, and the experimental stream
+    kernel (B200_GC_GROUP=stream) including its device-side hand-over to the cluster kernel when a seed has more live
+    candidates than the staging ring takes (> 2048) — all return the sequential algorithm's instance lists byte for
+    byte."""
+    cases = []
+    # (a) one instance above the stream kernel's per-seed capacity, one below, clutter: the hand-over
+    cases.append(_rigid_instances_case(b200, (2600, 900), 4000, 800, 5) + (0.01, 3, 256))
+    # (b) everything inside the stream kernel's capacity, sets far beyond 64 members
+    cases.append(_rigid_instances_case(b200, (1900, 40, 300), 2500, 1500, 6) + (0.01, 3, 512))
+    # (c) hundreds of 3-4 element instances on noisy descriptor matches (threshold 2), failed seeds in between
+    model, scene = small
+    kpm, kps = synth.voxel_grid(model, 0.02), synth.voxel_grid(scene, 0.03)
+    dm, _ = orc.shot352(model, orc.normals(model, k=10), kpm, 0.02)
+    ds, _ = orc.shot352(scene, orc.normals(scene, k=10), kps, 0.02)
+    cases.append((kpm, kps, orc.match(dm, ds, 1, 0.25), 0.02, 2, 2048))
+    for m, sc, corrs, size, thr, max_inst in cases:
+        oT, oinst = orc.gc_recognize(m, sc, corrs, size, thr, max_inst=max_inst)
+        assert len(oT) > 0
+        for sel in (None, "stream", "cta"):
+            if sel is None:
+                monkeypatch.delenv("B200_GC_GROUP", raising=False)
+            else:
+                monkeypatch.setenv("B200_GC_GROUP", sel)
+            T, inst, n = ctx.gc_recognize(m, sc, corrs, size, thr, max_inst=max_inst)
+            assert n == len(oT), (sel, n, len(oT))
+            assert [len(i) for i in inst] == [len(i) for i in oinst], sel
+            for a, b in zip(inst, oinst):
+                assert a.tobytes() == b.tobytes(), sel
+    monkeypatch.delenv("B200_GC_GROUP", raising=False)
+
+
 def test_gc_ransac_rare_good_samples(ctx, orc, b200):
     """Instances in which almost every 3-sample is rejected by isSampleGood (many scene points matched to one model
     point): RANSAC redraws hundreds of times, past the first 624 outputs of the mt19937 stream.  One instance
