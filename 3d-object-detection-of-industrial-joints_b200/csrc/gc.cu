@@ -935,21 +935,21 @@ __global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
   if (rank == 0 && tid == 0) *ga.n_inst_out = n_inst;
 }
 
-// ---- greedy grouping as a stream on one SM ---------------------------------------------------------
-// The round-based kernels above pay, per round of eight seeds, two or three dependent trips to the bitmap rows in
-// L2 plus a cluster barrier: 7.8 us per round, 678 rounds on the target scene.  Here nothing that touches global
+// ---- greedy grouping as a stream on one SM (experimental: B200_GC_GROUP=stream) --------------------
+// The round-based kernels above pay, per round of eight seeds, two or three dependent trips to the bitmap rows
+// plus a cluster barrier: 7.8 us per round, 678 rounds on the target scene.  Here nothing that touches global
 // memory is on the sequential chain.  One CTA, three kinds of warps:
 //   * the dispatcher (warp 0) walks the `taken` flags and hands the next position that is not taken yet to the
 //     next production ticket, at most GS_NSLOT tickets ahead of the last commit;
 //   * producer warps stage a seed each: the seed's bitmap row is read once (lane l owns a contiguous 1/32 of the
 //     row, so the candidates a lane finds are consecutive in the ascending list and one warp scan places them),
-//     what is taken already is dropped, the lowest candidate's row is read too and every candidate is marked with
-//     whether it fits that first candidate (bit 31 of its index — the first admission's tests, three quarters of all
-//     pair tests of a seed, come out of the bitmap instead of being recomputed); the list and the candidates' model /
-//     scene points go into a ring buffer in shared memory (32-candidate blocks: index + 6 coordinates, one
-//     128-byte line per field).  Ring space is handed out in ticket order, so the chunk of the seed the consumers
-//     wait for is always allocated before any later one and the ring cannot deadlock;
-//   * consumer warps take the staged seeds in order.  A consumer filters the list against the live `taken` flags
+//     what is taken already is dropped, the list and the candidates' model / scene points go into a ring buffer in
+//     shared memory (32-candidate blocks: index + 6 coordinates, one 128-byte line per field); with the points the
+//     producer reads each candidate's bit of the FIRST candidate's bitmap row (bit 31 of its index): the first
+//     admission's tests — three quarters of all pair tests of a seed — come off the bitmap instead of being
+//     recomputed.  Ring space is handed out in ticket order, so the chunk of the seed the consumers wait for is
+//     always allocated before any later one and the ring cannot deadlock;
+//   * consumer warps take the staged seeds round-robin.  A consumer filters the list against the live `taken` flags
 //     and grows the consensus set in the points domain entirely out of shared memory (lowest live candidate by
 //     redux.min, its points broadcast, every lane tests the candidates it owns: PCL's loop over j, in j order),
 //     then waits for its turn to commit.  At its turn every earlier seed has committed: if the seed was taken in the
@@ -957,13 +957,15 @@ __global__ void __cluster_dims__(GCL, 1, 1) __launch_bounds__(GCL_THREADS, 1)
 //     load); otherwise the set is exactly what the sequential algorithm computes (a set grown against older flags
 //     stays exact as long as none of its members has been taken since).  Inside the turn only the flags and the
 //     running totals are updated; the member list goes to global memory after the turn has been passed on.
-// All hand-overs are mbarriers (count 1, one phase per use of a slot) waited on with a suspend-time hint: the
-// hardware parks the waiting warp.  (Polling — volatile loads with __nanosleep, or try_wait with the default time
-// limit — left the working warps a third of the SM's issue slots: 58 % of the executed instructions were the wait
-// loops, and their S2R saturated the XU pipe.)
-// Target scene: 4 276 seeds, 183 candidates per seed on average (1 285 at most), 5.9 members per set; with eight
-// consumers 8 % of the sets are grown twice.  A seed with more than GS_LCAP live candidates, or more than 32 768
-// correspondences, sends the scene to the round-based kernel instead (flag on the device, no host round trip).
+// Hand-overs are mbarriers (count 1, one phase per use of a slot).  A seed with more than GS_LCAP live candidates,
+// or a scene with more than 32 768 correspondences, or a hand-over that a watchdog finds stuck, sends the scene to
+// the round-based kernel instead (flag on the device, no host round trip).
+// MEASURED (target scene: 5 578 tickets for 4 276 seeds, 183 candidates per seed on average, 1 285 at most, 5.9
+// members per set, 4 % of the sets grown twice): byte-identical, but 8.3 ms against the cluster kernel's 5.5 ms, so
+// the cluster kernel stays the default.  Why, with numbers: profiles/summary_r02.md (polling warps took 58 % of the
+// issue slots and saturated the XU pipe with S2R; a suspend-time hint wakes 2 us late; after both were fixed the
+// commit turn — 1 900 cycles of dependent shared-memory operations in one warp — and the 47 KB of code shared by 24
+// warps in different phases bound the kernel).
 constexpr int GS_PROD = 15;
 constexpr int GS_CONS = 8;
 constexpr int GS_THREADS = (1 + GS_PROD + GS_CONS) * 32;
