@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(256)
 constexpr int ADJ_ROWS = 128;
 constexpr int ADJ_WORDS = 32;  // words per CTA tile (1024 columns)
 constexpr int ADJ_THREADS = 256;
+#ifndef ADJ_UNROLL
+#define ADJ_UNROLL 8  // pair tests inlined per word (measured: 4 -> 0.545 ms, 8 -> 0.521 ms once the ballot transposes were gone)
+#endif
+constexpr int ADJ_UNROLL_N = ADJ_UNROLL;
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
@@ -121,6 +125,24 @@ __device__ __forceinline__ bool gc_fits(const float4 &mk, const float4 &sk, cons
 }
 
 __device__ __forceinline__ int gc_row_words(int C) { return (((C + 31) >> 5) + 127) & ~127; }
+
+// 32 x 32 bit transpose across a warp: lane r holds row r (bit c = element (r, c)); returns, in lane c, column c
+// (bit r = element (r, c)).  Five block-swap steps (blocks of 16, 8, 4, 2, 1) with one shuffle each — 32 ballots,
+// each wrapped in the compiler's convergence guards, were 40 % of the kernel's code and a third of a mirrored word's
+// instructions.
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int j = 16 >> s;
+    const unsigned m = (s == 0) ? 0x0000ffffu : (s == 1) ? 0x00ff00ffu : (s == 2) ? 0x0f0f0f0fu : (s == 3) ? 0x33333333u : 0x55555555u;
+    const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+    const bool upper = (lane & j) == 0;             // this lane holds the upper row of the pair
+    const unsigned a = upper ? x : y, b = upper ? y : x;
+    const unsigned t = ((a >> j) ^ b) & m;          // upper-right block of a against lower-left block of b
+    x ^= upper ? (t << j) : t;
+  }
+  return x;
+}
 
 __global__ void __launch_bounds__(ADJ_THREADS)
     gc_adjacency_kernel(const float4 *__restrict__ mp, const float4 *__restrict__ sp, const int *__restrict__ d_C,
@@ -166,7 +188,7 @@ __global__ void __launch_bounds__(ADJ_THREADS)
       const int w = wq + w4;
       unsigned bits = 0;
       const int t0 = (wbase + w) * 32;
-#pragma unroll 8
+#pragma unroll ADJ_UNROLL_N
       for (int b = 0; b < 32; ++b) {
         const bool ok = gc_fits(mi, si, s_m[t0 + b], s_s[t0 + b], g_lo, g_hi, gc_size);
         bits |= (ok ? 1u : 0u) << b;
@@ -177,15 +199,8 @@ __global__ void __launch_bounds__(ADJ_THREADS)
       if ((i >> 5) == gw) bits &= ~(1u << (i & 31));
       if (!valid) bits = 0u;
       out[w4] = bits;
-      if (mirror) {  // uniform over the half CTA
-        unsigned tw = 0;
-#pragma unroll
-        for (int b = 0; b < 32; ++b) {
-          const unsigned v = __ballot_sync(0xffffffffu, (bits >> b) & 1u);
-          if (lane == b) tw = v;
-        }
-        s_t[half][wr][w4 * 32 + lane] = tw;  // column j0 + lane, rows of this warp
-      }
+      if (mirror)  // uniform over the half CTA
+        s_t[half][wr][w4 * 32 + lane] = transpose32(bits, lane);  // column j0 + lane, rows of this warp
     }
     if (mirror) {
       // the four warps of the half hold the same 128 columns for four consecutive 32-row blocks: one 16-byte
@@ -1643,6 +1658,15 @@ constexpr int RS_EXHAUST_MAX_N = 18;    // ... for instances of at most this siz
 constexpr int RS_SMALL = 128;          // instances up to this size keep shuffle array / pair matrix in shared memory
 
 // squared residual of correspondence (s → g) under the row-major 4x4 float transform T
+// The float64 fit of a 3-point sample (Jacobi eigen-solve with double divisions and square roots: ~20 KB of SASS
+// per inlined copy).  Out of line: the kernel was 139 KB of code against a 32 KB instruction cache.
+__device__ __noinline__ void umeyama3_sample(const double *src, const double *dst, float *T) {
+  double Td[16];
+  umeyama3(src, dst, 3, Td);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) T[i] = (float)Td[i];
+}
+
 __device__ __forceinline__ float residual2(const float *T, const float4 &s, const float4 &g) {
   float e[3];
 #pragma unroll
@@ -1892,10 +1916,7 @@ __global__ void __launch_bounds__(RS_THREADS, 5)
         dst[i * 3 + 1] = g.y;
         dst[i * 3 + 2] = g.z;
       }
-      double Td[16];
-      umeyama3(src, dst, 3, Td);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) s_Tb[tid][i] = (float)Td[i];
+      umeyama3_sample(src, dst, s_Tb[tid]);
     }
     __syncthreads();
     if (nb >= 32 && n <= 256) {
@@ -1980,11 +2001,8 @@ __global__ void __launch_bounds__(RS_THREADS, 5)
           src[i * 3 + 0] = sv.x, src[i * 3 + 1] = sv.y, src[i * 3 + 2] = sv.z;
           dst[i * 3 + 0] = gv.x, dst[i * 3 + 1] = gv.y, dst[i * 3 + 2] = gv.z;
         }
-        double Td[16];
-        umeyama3(src, dst, 3, Td);
         float Tf[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) Tf[i] = (float)Td[i];
+        umeyama3_sample(src, dst, Tf);
         int cnt = 0;
         for (int t = 0; t < n; ++t) cnt += ((double)residual2(Tf, rb.mp[mem[t]], rb.sp[mem[t]]) < thresh2) ? 1 : 0;
         atomicMax(&s_ctrl[6], cnt);
