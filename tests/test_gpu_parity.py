@@ -118,6 +118,33 @@ def test_normals_knn_parity(ctx, orc, small, k):
         print("normals k=%d: %s" % (k, st))
 
 
+def test_normals_knn_two_pass_equals_insertion(ctx, orc, synth, small, monkeypatch):
+    """B200_NORMALS_KNN=2pass switches k = 10 / 20 to the two-pass search (register min/max chain for the k-th distance,
+    then collect + order) instead of the sorted-insertion search.  Same neighbour lists, so the same bits — on surface
+    scans, on an exact lattice (many ties at the k-th distance: the list overflows into the fall-back), on fewer
+    points than k, and with NaN rows and explicit queries."""
+    model, scene = small
+    g = np.arange(40, dtype=np.float32) * 0.01
+    lattice = np.stack(np.meshgrid(g, g, np.zeros(1, np.float32), indexing="ij"), -1).reshape(-1, 3)
+    tiny = scene[:7].copy()
+    holes = scene[:4000].copy()
+    holes[11] = np.nan
+    clouds = [("model", model, None), ("scene", scene, None), ("lattice", lattice, None), ("tiny", tiny, None),
+              ("holes", holes, None), ("queries", scene, model[::7])]
+    for k in (10, 20):
+        for name, cloud_np, q in clouds:
+            cl = ctx.cloud(cloud_np)
+            monkeypatch.delenv("B200_NORMALS_KNN", raising=False)
+            a = ctx.normals(cl, q=q, k=k)
+            monkeypatch.setenv("B200_NORMALS_KNN", "2pass")
+            b = ctx.normals(cl, q=q, k=k)
+            monkeypatch.delenv("B200_NORMALS_KNN", raising=False)
+            assert a.tobytes() == b.tobytes(), (name, k)
+    ref = orc.normals(lattice, k=20)
+    got = ctx.normals(ctx.cloud(lattice), k=20)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+
+
 def test_normals_radius_and_nan(ctx, orc, synth):
     scene = synth.make_scene(("horizontal",), 20000, scene_id=2)
     kp = synth.voxel_grid(scene, 0.03)
