@@ -118,11 +118,14 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
 // exact k-th smallest distance d_K of the certified block.  The second pass walks the same cells again (they are in
 // L1) and appends every candidate with d2 <= d_K to the shared-memory list (K of them plus ties at d_K), which is
 // then ordered once by (d2, index), all lanes together.  The result is knn_query's, bit for bit.
-// MEASURED: 1.45 ms against knn_query's 1.32 ms (1 M points, k = 20) — opt-in only (normals.cu); kept as the record of
-// the experiment and because the tests pin it bit for bit against the insertion form.
+// MEASURED (1 M points, k = 20): 1.45 - 1.8 ms against knn_query's 1.32 - 1.36 ms although it executes 20 % fewer warp
+// instructions (710 M against 881 M) with more lanes active (16.7 against 10.8 of 32): the candidate loop now has so
+// little work per load that it waits on the loads (long_scoreboard 4.0 per issue against 2.3; issue-active 51 %
+// against 65 %); four loads in flight per step did not change that (1.76 ms).  Opt-in only (normals.cu); kept as the
+// record of the experiment and because the tests pin it bit for bit against the insertion form.
 // sk: this thread's column of a [cap][T] array, cap >= K + KNN2_SLACK.  Returns the count (<= K), or -1 when more
 // than cap candidates tie into the list (the caller falls back to knn_query).
-constexpr int KNN2_SLACK = 12;
+constexpr int KNN2_SLACK = 4;   // 12 cost a third of the resident warps (shared memory); more ties than this fall back
 
 template <class F>
 __device__ __forceinline__ void knn_for_shell(const GridView &g, int cx, int cy, int cz, int R, F &&run) {
