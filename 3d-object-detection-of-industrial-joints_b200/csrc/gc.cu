@@ -41,9 +41,11 @@ constexpr int RANK_TILE = 2048;  // keys staged per barrier pair
 __global__ void __launch_bounds__(256)
     gc_rank_kernel(const b200_corr *__restrict__ corrs, const int *__restrict__ d_C, int C_cap,
                    const float4 *__restrict__ model_kp, const float4 *__restrict__ scene_kp,
-                   b200_corr *__restrict__ sorted, float4 *__restrict__ mp, float4 *__restrict__ sp) {
+                   b200_corr *__restrict__ sorted, float4 *__restrict__ mp, float4 *__restrict__ sp,
+                   const int *__restrict__ gate) {
   __shared__ unsigned long long tile[RANK_TILE];
   __shared__ int s_rank[RANK_ITEMS];
+  if (gate && *gate == 0) return;  // the bucket sort below has done it
   const int C = min(*d_C, C_cap);
   if (blockIdx.x * RANK_ITEMS >= C) return;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -74,6 +76,108 @@ __global__ void __launch_bounds__(256)
     mp[r] = model_kp[mine.index_query];
     sp[r] = scene_kp[mine.index_match];
   }
+}
+
+// ---- the same order by buckets ------------------------------------------------------------------------
+// Ranking by counting is O(C^2) (0.14 ms for the 25 k correspondences of the target scene).  The key's top 13 bits
+// (sign, exponent, 4 mantissa bits of the distance) are a monotone bucket index: histogram -> one-CTA scan ->
+// scatter -> rank inside the bucket (a hundred or two keys).  Four small launches; if a bucket holds more than
+// SORT_BIG_BUCKET keys (many equal or nearly equal distances) a flag hands the scene to gc_rank_kernel instead —
+// on the device, no host round trip.  Same keys, same total order: the output is gc_rank_kernel's bit for bit.
+constexpr int SORT_BUCKETS = 8192;
+constexpr int SORT_SHIFT = 19;       // bucket = sign, exponent, 4 mantissa bits of the distance
+constexpr int SORT_BIG_BUCKET = 4096;
+
+__device__ __forceinline__ unsigned long long corr_key(const b200_corr &c, int i) {
+  return ((unsigned long long)__float_as_uint(c.distance) << 32) | (unsigned)i;
+}
+
+__global__ void __launch_bounds__(256)
+    gc_sort_hist_kernel(const b200_corr *__restrict__ corrs, const int *__restrict__ d_C, int C_cap, int *__restrict__ hist) {
+  const int C = min(*d_C, C_cap);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < C) atomicAdd(&hist[__float_as_uint(corrs[i].distance) >> SORT_SHIFT], 1);
+}
+
+// one CTA: start[b] = number of keys in buckets before b; hist is cleared (it becomes the scatter cursor);
+// *fallback = 1 when a bucket is too large for the per-key scan of gc_sort_rank_kernel
+__global__ void __launch_bounds__(1024) gc_sort_scan_kernel(int *__restrict__ hist, int *__restrict__ start, int *__restrict__ fallback) {
+  __shared__ int s_warp[32];
+  __shared__ int s_big;
+  constexpr int PER = SORT_BUCKETS / 1024;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_big = 0;
+  __syncthreads();
+  int sum = 0, mx = 0;
+#pragma unroll 8
+  for (int u = 0; u < PER; ++u) {
+    const int v = hist[tid * PER + u];
+    sum += v;
+    mx = max(mx, v);
+  }
+  if (mx > SORT_BIG_BUCKET) s_big = 1;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+#pragma unroll 8
+  for (int u = 0; u < PER; ++u) {
+    const int v = hist[tid * PER + u];
+    start[tid * PER + u] = run;
+    run += v;
+    hist[tid * PER + u] = 0;
+  }
+  if (tid == 1023) start[SORT_BUCKETS] = run;
+  if (tid == 0) *fallback = s_big;
+}
+
+__global__ void __launch_bounds__(256)
+    gc_sort_scatter_kernel(const b200_corr *__restrict__ corrs, const int *__restrict__ d_C, int C_cap,
+                           const int *__restrict__ start, int *__restrict__ cursor, unsigned long long *__restrict__ keys,
+                           const int *__restrict__ fallback) {
+  if (*fallback) return;
+  const int C = min(*d_C, C_cap);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= C) return;
+  const b200_corr c = corrs[i];
+  const int b = (int)(__float_as_uint(c.distance) >> SORT_SHIFT);
+  keys[start[b] + atomicAdd(&cursor[b], 1)] = corr_key(c, i);
+}
+
+__global__ void __launch_bounds__(256)
+    gc_sort_rank_kernel(const b200_corr *__restrict__ corrs, const int *__restrict__ d_C, int C_cap,
+                        const float4 *__restrict__ model_kp, const float4 *__restrict__ scene_kp,
+                        const int *__restrict__ start, const unsigned long long *__restrict__ keys,
+                        b200_corr *__restrict__ sorted, float4 *__restrict__ mp, float4 *__restrict__ sp,
+                        const int *__restrict__ fallback) {
+  if (*fallback) return;
+  const int C = min(*d_C, C_cap);
+  const int p = blockIdx.x * 256 + threadIdx.x;  // a position of the bucket-ordered key array: the threads of a
+  if (p >= C) return;                            // warp mostly share a bucket, so they read the same keys
+  const unsigned long long key = keys[p];
+  const b200_corr mine = corrs[(int)(unsigned)(key & 0xffffffffull)];
+  const int b = (int)((unsigned)(key >> 32) >> SORT_SHIFT);
+  const int s = start[b], e = start[b + 1];
+  int r = s;
+  for (int j = s; j < e; ++j) r += (keys[j] < key) ? 1 : 0;
+  sorted[r] = mine;
+  mp[r] = model_kp[mine.index_query];
+  sp[r] = scene_kp[mine.index_match];
 }
 
 // ---- pairwise consistency bitmap ------------------------------------------------------------------
@@ -2076,15 +2180,37 @@ int dev_gc(b200_ctx *ctx, const float4 *d_model_kp, const float4 *d_scene_kp, co
   DevBuf<b200_corr> sorted;
   DevBuf<float4> mp, sp;
   DevBuf<unsigned> adj;
-  DevBuf<int> overflow, members, fb;
+  DevBuf<int> overflow, members, fb, sort_fb;
   B200_TRY(sorted.alloc(ctx, (size_t)C_eff));
+  B200_TRY(sort_fb.alloc(ctx, 1));
   B200_TRY(mp.alloc(ctx, (size_t)C_eff));
   B200_TRY(sp.alloc(ctx, (size_t)C_eff));
   B200_TRY(adj.alloc(ctx, (size_t)C_eff * row_words_cap));
   {
     StageScope st_(ctx, ST_GC_SORT);
+    const char *sel = getenv("B200_GC_SORT");  // "count": the O(C^2) counting kernel alone
+    const int *gate = nullptr;
+    if (!(sel && !strcmp(sel, "count"))) {
+      DevBuf<int> hist, start;
+      DevBuf<unsigned long long> keys;
+      B200_TRY(hist.alloc(ctx, SORT_BUCKETS));
+      B200_TRY(start.alloc(ctx, SORT_BUCKETS + 1));
+      B200_TRY(keys.alloc(ctx, (size_t)C_eff));
+      B200_TRY(hist.zero());
+      const int nblk = ceil_div(C_eff, 256);
+      gc_sort_hist_kernel<<<nblk, 256, 0, ctx->stream>>>(d_corrs, d_C, C_eff, hist.p);
+      B200_LAUNCHED(ctx);
+      gc_sort_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist.p, start.p, sort_fb.p);
+      B200_LAUNCHED(ctx);
+      gc_sort_scatter_kernel<<<nblk, 256, 0, ctx->stream>>>(d_corrs, d_C, C_eff, start.p, hist.p, keys.p, sort_fb.p);
+      B200_LAUNCHED(ctx);
+      gc_sort_rank_kernel<<<nblk, 256, 0, ctx->stream>>>(d_corrs, d_C, C_eff, d_model_kp, d_scene_kp, start.p, keys.p,
+                                                        sorted.p, mp.p, sp.p, sort_fb.p);
+      B200_LAUNCHED(ctx);
+      gate = sort_fb.p;
+    }
     gc_rank_kernel<<<ceil_div(C_eff, RANK_ITEMS), 256, 0, ctx->stream>>>(d_corrs, d_C, C_eff, d_model_kp, d_scene_kp,
-                                                                 sorted.p, mp.p, sp.p);
+                                                                 sorted.p, mp.p, sp.p, gate);
     B200_LAUNCHED(ctx);
   }
   {

@@ -736,7 +736,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1500, help="scene keypoints in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blocking-sync", action="store_true", help="contexts sleep in host waits instead of spinning")
-    ap.add_argument("--lanes", type=int, default=6, help="scenes in flight per GPU (context + stream + host thread each)")
+    ap.add_argument("--lanes", type=int, default=8, help="scenes in flight per GPU (context + stream + host thread each)")
     ap.add_argument("--scenes-per-lane", type=int, default=8, help="a step = lanes x this many scene registrations per GPU")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic scenes per rank, registered round-robin")
     ap.add_argument("--total-scenes", type=int, default=0,

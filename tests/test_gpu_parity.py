@@ -434,6 +434,23 @@ def test_gc_group_kernel_variants(ctx, orc, synth, small, b200, monkeypatch):
             for a, b in zip(inst, oinst):
                 assert a.tobytes() == b.tobytes(), sel
     monkeypatch.delenv("B200_GC_GROUP", raising=False)
+    # the (distance, position) order: bucket sort (default), its hand-over to the counting kernel when a bucket is too
+    # large (here: 3 000 equal distances), and the counting kernel alone
+    m, sc, corrs, size, thr, max_inst = cases[1]
+    tied = corrs.copy()
+    tied["distance"][:3000] = np.float32(0.125)
+    for c in (corrs, tied):
+        oT, oinst = orc.gc_recognize(m, sc, c, size, thr, max_inst=max_inst)
+        for sel in (None, "count"):
+            if sel is None:
+                monkeypatch.delenv("B200_GC_SORT", raising=False)
+            else:
+                monkeypatch.setenv("B200_GC_SORT", sel)
+            T, inst, n = ctx.gc_recognize(m, sc, c, size, thr, max_inst=max_inst)
+            assert n == len(oT), (sel, n, len(oT))
+            for a, b in zip(inst, oinst):
+                assert a.tobytes() == b.tobytes(), sel
+    monkeypatch.delenv("B200_GC_SORT", raising=False)
 
 
 def test_gc_ransac_rare_good_samples(ctx, orc, b200):
