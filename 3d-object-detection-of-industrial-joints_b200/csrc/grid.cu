@@ -72,14 +72,30 @@ __global__ void bbox_kernel(const float4 *__restrict__ pts, int n, unsigned *__r
     }
     c += __shfl_xor_sync(0xffffffffu, c, o);
   }
+  // one set of global atomics per CTA (one per warp — 66 000 atomics on seven addresses for a 1 M-point cloud — made
+  // this kernel 49 us)
+  __shared__ unsigned s_mn[3], s_mx[3];
+  __shared__ int s_c;
+  if (threadIdx.x == 0) {
+    s_mn[0] = s_mn[1] = s_mn[2] = 0xffffffffu;
+    s_mx[0] = s_mx[1] = s_mx[2] = 0u;
+    s_c = 0;
+  }
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      atomicMin(&box[a], mn[a]);
-      atomicMax(&box[3 + a], mx[a]);
+      atomicMin(&s_mn[a], mn[a]);
+      atomicMax(&s_mx[a], mx[a]);
     }
-    if (c) atomicAdd(cnt, c);
+    if (c) atomicAdd(&s_c, c);
   }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    atomicMin(&box[threadIdx.x], s_mn[threadIdx.x]);
+    atomicMax(&box[3 + threadIdx.x], s_mx[threadIdx.x]);
+  }
+  if (threadIdx.x == 3 && s_c) atomicAdd(cnt, s_c);
 }
 
 __global__ void cell_count_kernel(const float4 *__restrict__ pts, int n, GridView g, int *__restrict__ cell_of,
@@ -225,7 +241,7 @@ int cloud_upload(b200_ctx *ctx, const float *xyz, int n, int stride, bool on_dev
   unsigned init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
   if ((rc = write_small(ctx, box.p, init, sizeof(init))) != B200_OK) return bail(rc);
   if (n > 0) {
-    int blocks = std::min(ceil_div(n, 256), ctx->sm_count * 8);
+    int blocks = std::min(ceil_div(n, 256), ctx->sm_count * 4);
     bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(c->raw.p, n, box.p, reinterpret_cast<int *>(box.p + 6));
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
