@@ -11,6 +11,8 @@
 // 4 B cell id write/read + 16 B reordered write per point (~40 B/point) plus the cell array.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -271,7 +273,8 @@ int cloud_grid_for_knn(b200_cloud *c, int k, const GridView **out) {
     double area = std::max((double)ext[2] * (double)ext[1], 1e-12);
     // about k points per (flat-surface) cell: measured on the 1 M-point scene, k = 20: 0.5 k -> 1.95 ms, 0.7 k -> 1.42,
     // 1.0 k -> 1.35, 1.5 k -> 1.58, 3 k -> 1.89 (smaller cells need the second ring too often, larger ones scan more)
-    double target = std::max(2.0, 1.0 * k);
+    const char *cf = getenv("B200_KNN_CELL");  // points per surface cell as a multiple of k (tuning knob)
+    double target = std::max(2.0, (cf ? atof(cf) : 1.0) * k);
     float cell = (float)sqrt(area * target / std::max(c->n_valid, 1));
     B200_TRY(build_grid(c, cell, c->knn_grid));
     c->knn_grid_k = k;

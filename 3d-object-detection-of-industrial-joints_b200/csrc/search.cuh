@@ -38,6 +38,28 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
   const float margin = 4e-6f * (g.coord_scale + fabsf(qx) + fabsf(qy) + fabsf(qz)) + 1e-5f * g.h;
   unsigned long long worst = ~0ull;  // key of the current k-th neighbour once the list is full
 
+  // The k best keys are kept as a MAX-HEAP in the shared-memory column (root = current k-th): a candidate that beats
+  // the root replaces it and sinks at most log2(k) levels.  A sorted list (round 1) shifted k / 2 entries on average —
+  // and, one query per thread, a warp executes the LONGEST shift of its inserting lanes: with the heap the longest
+  // path is 4 levels for k = 20.  The list is put in (distance, index) order once at the end.
+  auto sift_down = [&](int i, int n, unsigned long long key) {  // key sinks from slot i of a heap of n slots
+    while (true) {
+      int c = 2 * i + 1;
+      if (c >= n) break;
+      unsigned long long ck = sk[c * T];
+      if (c + 1 < n) {
+        const unsigned long long ck2 = sk[(c + 1) * T];
+        if (ck2 > ck) {
+          ck = ck2;
+          ++c;
+        }
+      }
+      if (ck <= key) break;
+      sk[i * T] = ck;
+      i = c;
+    }
+    sk[i * T] = key;
+  };
   auto scan_run = [&](int c0, int c1) {
     const int s = cs[c0], e = cs[c1 + 1];
     for (int j = s; j < e; ++j) {
@@ -45,16 +67,16 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
       const float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
       const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)orig_index(p);
       if (key >= worst) continue;
-      int pos = (cnt < k) ? cnt : k - 1;
-      while (pos > 0) {
-        const unsigned long long pk = sk[(pos - 1) * T];
-        if (pk < key) break;
-        sk[pos * T] = pk;
-        --pos;
+      if (cnt < k) {
+        sk[cnt * T] = key;
+        if (++cnt == k) {
+          for (int i = k / 2 - 1; i >= 0; --i) sift_down(i, k, sk[i * T]);
+          worst = sk[0];
+        }
+      } else {
+        sift_down(0, k, key);
+        worst = sk[0];
       }
-      sk[pos * T] = key;
-      if (cnt < k) ++cnt;
-      if (cnt == k) worst = sk[(k - 1) * T];
     }
   };
 
@@ -105,6 +127,26 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
       if (cz + R < g.dz - 1) cert = fminf(cert, (g.loz + (float)(cz + R + 1) * g.h) - qz);
       cert -= margin;
       if (cert > 0.f && knn_d2(worst) < cert * cert * 0.99999f) break;
+    }
+  }
+  // ascending (distance, index) order: FLANN's result order
+  if (cnt == k) {
+    for (int n = k - 1; n > 0; --n) {  // heap sort: the maximum goes to the end, the former last key sinks from the root
+      const unsigned long long last = sk[n * T];
+      sk[n * T] = sk[0];
+      sift_down(0, n, last);
+    }
+  } else {
+    for (int i = 1; i < cnt; ++i) {  // fewer points than k in the whole grid: the list was only appended to
+      const unsigned long long key = sk[i * T];
+      int pos = i;
+      while (pos > 0) {
+        const unsigned long long pk = sk[(pos - 1) * T];
+        if (pk < key) break;
+        sk[pos * T] = pk;
+        --pos;
+      }
+      sk[pos * T] = key;
     }
   }
   return cnt;
