@@ -41,7 +41,8 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
   // The k best keys are kept as a MAX-HEAP in the shared-memory column (root = current k-th): a candidate that beats
   // the root replaces it and sinks at most log2(k) levels.  A sorted list (round 1) shifted k / 2 entries on average —
   // and, one query per thread, a warp executes the LONGEST shift of its inserting lanes: with the heap the longest
-  // path is 4 levels for k = 20.  The list is put in (distance, index) order once at the end.
+  // path is 4 levels for k = 20.  The list is put in (distance, index) order once at the end.  (A 4-ary heap — two
+// levels, independent child loads — measured the same: 1.173 against 1.168 ms.)
   auto sift_down = [&](int i, int n, unsigned long long key) {  // key sinks from slot i of a heap of n slots
     while (true) {
       int c = 2 * i + 1;
