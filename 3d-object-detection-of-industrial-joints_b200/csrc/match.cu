@@ -57,8 +57,12 @@ __device__ __forceinline__ void match_block_tiles(const float *__restrict__ mode
                                                   const unsigned char *__restrict__ model_valid,
                                                   const float *__restrict__ scene, int D, float (*As)[MKC + 1],
                                                   float (*Bs)[MKC + 1], const int *s_row, int t0, int tstep, int tend,
-                                                  unsigned long long *__restrict__ best, int *__restrict__ zero_cnt) {
+                                                  unsigned long long *__restrict__ best, int *__restrict__ zero_cnt,
+                                                  int n_block_rows = MT) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // a thread's scene rows are ty + 16 i: with fewer than 64 rows in the block (the handful of rows the tensor-core
+  // filter leaves over) the upper i do no arithmetic
+  const int imax = (n_block_rows + 15) >> 4;
   unsigned long long rbest[4] = {~0ull, ~0ull, ~0ull, ~0ull};
   int rzero[4] = {0, 0, 0, 0};
   for (int tile = t0; tile < tend; tile += tstep) {
@@ -82,15 +86,18 @@ __device__ __forceinline__ void match_block_tiles(const float *__restrict__ mode
       for (int c = 0; c < MKC; ++c) {
         float a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[ty + 16 * i][c];
+        for (int i = 0; i < 4; ++i)
+          if (i < imax) a[i] = As[ty + 16 * i][c];
 #pragma unroll
         for (int j = 0; j < 4; ++j) b[j] = Bs[tx + 16 * j][c];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
+          if (i < imax) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float diff = a[i] - b[j];
-            acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(diff, diff));
+            for (int j = 0; j < 4; ++j) {
+              const float diff = a[i] - b[j];
+              acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(diff, diff));
+            }
           }
       }
     }
@@ -165,7 +172,8 @@ __global__ void __launch_bounds__(MTHREADS)
       s_row[threadIdx.x] = (r < n_rows) ? row_map[r] : -1;
     }
     __syncthreads();
-    match_block_tiles(model, Km, model_valid, scene, D, As, Bs, s_row, tile, ntiles, tile + 1, best, zero_cnt);
+    match_block_tiles(model, Km, model_valid, scene, D, As, Bs, s_row, tile, ntiles, tile + 1, best, zero_cnt,
+                      min(MT, n_rows - s0));
   }
 }
 
