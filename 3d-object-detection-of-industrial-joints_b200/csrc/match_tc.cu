@@ -29,6 +29,7 @@
 //            s = nb_j - 2*acc → sorted insert into the row's candidate list; overlaps the next tile's MMAs
 //            through the second accumulator
 // Roofline: tensor pipe; 2*Ks*Km*K' flop per call.
+#include <stdint.h>
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -138,9 +139,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 // ---------------------------------------------------------------- operand preparation
 __global__ void absmax_kernel(const float *__restrict__ x, size_t n, unsigned *__restrict__ out_bits) {
   float m = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = fabsf(x[i]);
+  auto take = [&](float v) {
+    v = fabsf(v);
     if (isfinite(v)) m = fmaxf(m, v);
+  };
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // 16-byte loads, four in flight per thread (scalar loads reached 2.2 TB/s: 57 us for the 128 MB of a scene)
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const size_t n4 = n >> 2;
+    for (size_t i = tid; i < n4; i += 4 * nthr) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * nthr < n4) v[u] = __ldg(x4 + i + u * nthr);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * nthr < n4) take(v[u].x), take(v[u].y), take(v[u].z), take(v[u].w);
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += nthr) take(x[i]);
+  } else {
+    for (size_t i = tid; i < n; i += nthr) take(x[i]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
