@@ -42,6 +42,8 @@ EXPORTS = [
     "b200_board_params_default",
     "b200_ctx_srand",
     "b200_board_lrf",
+    "b200_hv_params_default", "b200_hv_create", "b200_hv_destroy", "b200_hv_set_params", "b200_hv_set_scene",
+    "b200_hv_add_models", "b200_hv_verify", "b200_hv_last_size", "b200_hv_last_copy", "b200_hv_optimize",
 ]
 
 
@@ -77,6 +79,33 @@ def board_params(find_holes=True, tangent_radius=0.0, margin_thresh=0.85, check_
     """PCL's constructor defaults, with find_holes as the reference sets it (SHOT.cpp:442)."""
     return BoardParams(int(find_holes), float(tangent_radius), float(margin_thresh), int(check_margin_array_size),
                        float(hole_size_prob_thresh), float(steep_thresh))
+
+
+class HvParams(C.Structure):
+    """b200_hv_params (pcl::GlobalHypothesesVerification's members; SHOT_hypothesis.cpp:58-64, 642-648)."""
+    _fields_ = [("resolution", C.c_float), ("inlier_threshold", C.c_float), ("occlusion_threshold", C.c_float),
+                ("regularizer", C.c_float), ("radius_normals", C.c_float), ("res_occupancy_grid", C.c_float),
+                ("w_occupied_multiple_cm", C.c_float), ("initial_temp", C.c_float), ("max_iterations", C.c_int),
+                ("occlusion_reasoning", C.c_int), ("zbuffer_scene_resolution", C.c_int),
+                ("zbuffer_self_resolution", C.c_int), ("self_occlusion_threshold", C.c_float),
+                ("detect_clutter", C.c_int), ("radius_clutter", C.c_float), ("clutter_regularizer", C.c_float),
+                ("rand_seed", C.c_uint), ("mt_seed", C.c_uint), ("sa_uniform_mode", C.c_int)]
+
+
+HV_INFO_DTYPE = np.dtype([("valid", "<i4"), ("n_visible", "<i4"), ("n_points", "<i4"), ("n_outliers", "<i4"),
+                          ("n_explained", "<i4"), ("n_occupancy", "<i4"), ("outliers_weight", "<f4"),
+                          ("explained_sum", "<f4")])
+
+
+def hv_params(**kw):
+    """PCL's constructor defaults, overridden by keyword."""
+    p = HvParams()
+    lib().b200_hv_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown hypothesis-verification parameter %r" % k)
+        setattr(p, k, v)
+    return p
 
 
 def lib():
@@ -172,12 +201,24 @@ def lib():
             "b200_library_download_view": [vp, vp, i, fp, fp],
             "b200_register_scene_library": [vp, vp, fp, i, i, fp, i, i, C.POINTER(ShotParams), fp, ip, ip,
                                             C.POINTER(Corr), i, i, ip, ip],
+            "b200_hv_create": [vp, C.POINTER(HvParams), C.POINTER(vp)],
+            "b200_hv_destroy": [vp],
+            "b200_hv_set_params": [vp, C.POINTER(HvParams)],
+            "b200_hv_set_scene": [vp, vp, fp, i, i],
+            "b200_hv_add_models": [vp, vp, fp, ip, i, i, i],
+            "b200_hv_verify": [vp, vp, C.POINTER(C.c_ubyte), vp, C.POINTER(d), ip],
+            "b200_hv_last_size": [vp, i],
+            "b200_hv_last_copy": [vp, vp, i, vp],
+            "b200_hv_optimize": [vp, i, i, ip, ip, fp, ip, ip, i, fp, ip, C.POINTER(HvParams), C.POINTER(C.c_ubyte),
+                                 C.POINTER(d), ip],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = C.c_int
         L.b200_board_params_default.restype = None
+        L.b200_hv_params_default.restype = None
+        L.b200_hv_params_default.argtypes = [C.POINTER(HvParams)]
         L.b200_last_error.argtypes = [vp]
         L.b200_last_error.restype = C.c_char_p
         L.b200_ctx_stage_name.argtypes = [i]
@@ -415,6 +456,70 @@ class Library:
             pass
 
 
+class HypothesisVerification:
+    """b200_hv: pcl::GlobalHypothesesVerification in the reference's call order (SHOT_hypothesis.cpp:631-653)."""
+
+    def __init__(self, ctx, params=None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._chk(lib().b200_hv_create(ctx.h, C.byref(params) if params is not None else None, C.byref(h)))
+        self.h = h
+        self.H = 0
+        ctx._children.add(self)
+
+    def set_params(self, params):
+        self.ctx._chk(lib().b200_hv_set_params(self.h, C.byref(params)))
+
+    def set_scene(self, scene_xyz):
+        xyz = _pts(scene_xyz)
+        self.ctx._chk(lib().b200_hv_set_scene(self.ctx.h, self.h, _f(xyz), len(xyz), xyz.shape[1]))
+
+    def add_models(self, models, occlusion_reasoning=False):
+        models = [_pts(m) for m in models]
+        offs = np.zeros(len(models) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(m) for m in models])
+        flat = np.ascontiguousarray(np.concatenate([m[:, :3] for m in models]) if models and offs[-1] > 0
+                                    else np.zeros((1, 3), np.float32), dtype=np.float32)
+        self.H = len(models)
+        self.ctx._chk(lib().b200_hv_add_models(self.ctx.h, self.h, _f(flat), _i(offs), self.H, 3,
+                                               1 if occlusion_reasoning else 0))
+
+    def verify(self):
+        """verify + getMask.  Returns a dict: mask, info, best_cost, accepted_moves, n_scene_points, n_cells and the cue lists (CSR over the valid hypotheses)."""
+        H = self.H
+        mask = np.zeros(max(H, 1), dtype=np.uint8)
+        info = np.zeros(max(H, 1), dtype=HV_INFO_DTYPE)
+        cost, acc = C.c_double(0.0), C.c_int(0)
+        self.ctx._chk(lib().b200_hv_verify(self.ctx.h, self.h, mask.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                           info.ctypes.data, C.byref(cost), C.byref(acc)))
+        out = {"mask": mask[:H].astype(bool), "info": info[:H], "best_cost": cost.value, "accepted_moves": acc.value,
+               "n_scene_points": lib().b200_hv_last_size(self.h, 0), "n_cells": lib().b200_hv_last_size(self.h, 1)}
+        arrs = {}
+        for which, (name, dt) in {2: ("expl_idx", np.int32), 3: ("expl_w", np.float32), 4: ("occ_idx", np.int32),
+                                  5: ("sizes", np.int32)}.items():
+            n = lib().b200_hv_last_size(self.h, which)
+            a = np.zeros(max(n, 1), dtype=dt)
+            if n > 0:
+                self.ctx._chk(lib().b200_hv_last_copy(self.ctx.h, self.h, which, a.ctypes.data))
+            arrs[name] = a[:n]
+        sizes = arrs.pop("sizes").reshape(-1, 2)
+        out.update(arrs)
+        out["expl_off"] = np.concatenate([[0], np.cumsum(sizes[:, 0])]).astype(np.int32)
+        out["occ_off"] = np.concatenate([[0], np.cumsum(sizes[:, 1])]).astype(np.int32)
+        return out
+
+    def close(self):
+        if self.h and self.ctx.h:
+            lib().b200_hv_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """b200_ctx: one per host thread.  stream: a raw cudaStream_t (int), e.g.
     torch.cuda.current_stream().cuda_stream, or None for a private stream."""
@@ -563,6 +668,28 @@ class Context:
             self._chk(lib().b200_fpfh33(self.h, cloud.h, _f(normals), _f(q), len(q), q.shape[1], float(radius),
                                         _f(out)))
         return out
+
+    # ---- hypothesis verification (GlobalHypothesesVerification, SHOT_hypothesis.cpp:631-653) -------
+    def hypothesis_verification(self, params=None):
+        return HypothesisVerification(self, params)
+
+    def hv_optimize(self, ns, expl_off, expl_idx, expl_w, occ_off, occ_idx, n_cells, outliers_weight,
+                    bad_information, params):
+        """SAOptimize alone on given cue lists.  Returns (mask, best_cost, accepted_moves)."""
+        H = len(expl_off) - 1
+        eo = np.ascontiguousarray(expl_off, dtype=np.int32)
+        ei = np.ascontiguousarray(np.append(expl_idx, 0), dtype=np.int32)
+        ew = np.ascontiguousarray(np.append(expl_w, 0), dtype=np.float32)
+        oo = np.ascontiguousarray(occ_off, dtype=np.int32)
+        oi = np.ascontiguousarray(np.append(occ_idx, 0), dtype=np.int32)
+        ow = np.ascontiguousarray(outliers_weight, dtype=np.float32)
+        bi = np.ascontiguousarray(bad_information, dtype=np.int32)
+        mask = np.zeros(max(H, 1), dtype=np.uint8)
+        cost, acc = C.c_double(0.0), C.c_int(0)
+        self._chk(lib().b200_hv_optimize(self.h, H, int(ns), _i(eo), _i(ei), _f(ew), _i(oo), _i(oi), int(n_cells),
+                                         _f(ow), _i(bi), C.byref(params), mask.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                         C.byref(cost), C.byref(acc)))
+        return mask[:H].astype(bool), cost.value, acc.value
 
     # ---- per-query descriptor index (KdTreeFLANN<Descriptor> drop-in) -------------------------------
     def desc_index(self, desc):

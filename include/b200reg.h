@@ -381,6 +381,79 @@ B200_API int b200_register_scene_shot_sharded(b200_ctx *ctx, const b200_model *m
                                               b200_corr *inst_corrs, int corr_cap, int *n_inst, b200_corr *corrs_out,
                                               int *n_corrs);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Hypothesis verification: pcl::GlobalHypothesesVerification<PointT, PointT> as SHOT_hypothesis.cpp:631-653 drives
+ * it after ICP — setSceneCloud (:639), addModels(registered_instances, true) (:640), setInlierThreshold /
+ * setOcclusionThreshold / setRegularizer / setRadiusClutter / setClutterRegularizer / setDetectClutter /
+ * setRadiusNormals (:642-648), verify (:650), getMask (:651).  The object mirrors that call order, because PCL's
+ * results depend on it: the scene is voxelised with the resolution in force at setSceneCloud, the models are
+ * occlusion-filtered with the occlusion threshold in force at addModels (the reference sets its own value only
+ * afterwards, so the constructor default 0.005 applies), everything else is read at verify.
+ *
+ * On the device: the scene voxel grid, the scene and per-hypothesis z-buffers (focal length from the cloud's
+ * extent, depth maps by atomic minimum), the visibility filter, the hypotheses' voxel grids and radius normals, the
+ * radius search of every hypothesis point in the scene (explained points, their weights, the outliers), the
+ * occupancy grid of the complete models, and the simulated-annealing search over the hypothesis mask (one CTA; the
+ * shuffle and acceptance streams — glibc rand() and mt19937, both never seeded by PCL — are generated on the host
+ * and consumed in order).  Only detect_clutter = 0 (the reference's setting) is implemented; B200_ERR_INVALID
+ * otherwise.  Input points must be finite (the reference removes NaNs first, SHOT.cpp:298-299): non-finite rows are
+ * skipped.  See DESIGN.md for the recalled PCL details this rests on.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct b200_hv b200_hv;
+typedef struct {
+  float resolution;               /* HypothesisVerification::resolution_, 0.005: voxel size of scene and hypotheses */
+  float inlier_threshold;         /* setInlierThreshold (hv_inlier_th_, SHOT_hypothesis.cpp:59) */
+  float occlusion_threshold;      /* setOcclusionThreshold; read when the models are added */
+  float regularizer;              /* setRegularizer (hv_regularizer_) */
+  float radius_normals;           /* setRadiusNormals (hv_rad_normals_) */
+  float res_occupancy_grid;       /* 0.01 */
+  float w_occupied_multiple_cm;   /* 4 */
+  float initial_temp;             /* 1000 */
+  int max_iterations;             /* 5000: annealing stops after this many iterations without improvement */
+  int occlusion_reasoning;        /* unused by the object API (addModels' argument); kept for layout parity with tests */
+  int zbuffer_scene_resolution;   /* 100 */
+  int zbuffer_self_resolution;    /* 75 */
+  float self_occlusion_threshold; /* 0.005 */
+  int detect_clutter;             /* setDetectClutter; must be 0 at verify */
+  float radius_clutter;           /* setRadiusClutter: accepted, unused without the clutter cue */
+  float clutter_regularizer;      /* setClutterRegularizer: accepted, unused without the clutter cue */
+  unsigned rand_seed;             /* srand() state std::random_shuffle draws from (1: never seeded) */
+  unsigned mt_seed;               /* 5489: default-constructed mt19937 */
+  int sa_uniform_mode;            /* 0: x / 2^32; 1: the raw 32-bit value (uphill moves never accepted) */
+} b200_hv_params;
+typedef struct {
+  int valid;           /* addModel succeeded (the visible cloud has points) */
+  int n_visible;       /* points left by the self- and scene-occlusion filters */
+  int n_points;        /* after VoxelGrid and the NaN-normal compaction */
+  int n_outliers;      /* points with no scene point within the inlier threshold (bad_information_) */
+  int n_explained;     /* scene points explained by the hypothesis */
+  int n_occupancy;     /* occupancy-grid cells of the complete model */
+  float outliers_weight;
+  float explained_sum; /* float32 sum of the explained weights, in scene order */
+} b200_hv_info;
+B200_API void b200_hv_params_default(b200_hv_params *p); /* PCL's constructor defaults */
+B200_API int b200_hv_create(b200_ctx *ctx, const b200_hv_params *p /* nullable: defaults */, b200_hv **out);
+B200_API int b200_hv_destroy(b200_hv *hv);
+B200_API int b200_hv_set_params(b200_hv *hv, const b200_hv_params *p);                       /* the set* calls */
+B200_API int b200_hv_set_scene(b200_ctx *ctx, b200_hv *hv, const float *scene_xyz, int n, int stride); /* setSceneCloud */
+/* addModels: H clouds concatenated (host rows), model_offsets[H + 1] in points.  Replaces earlier models. */
+B200_API int b200_hv_add_models(b200_ctx *ctx, b200_hv *hv, const float *models_xyz, const int *model_offsets, int H,
+                                int stride, int occlusion_reasoning);
+/* verify + getMask.  mask: H bytes (1 = the hypothesis survives).  info (nullable): H entries.  best_cost /
+ * accepted_moves (nullable): the annealing's best cost and its number of accepted moves. */
+B200_API int b200_hv_verify(b200_ctx *ctx, b200_hv *hv, unsigned char *mask, b200_hv_info *info, double *best_cost,
+                            int *accepted_moves);
+/* Sizes / contents of the last verify: which = 0 scene points after the NaN-normal compaction (size only), 1
+ * occupancy cells (size only), 2 explained scene indices, 3 explained weights (float), 4 occupancy cell indices
+ * (order within a hypothesis unspecified), 5 per valid hypothesis: list lengths (explained, occupancy) pairs. */
+B200_API int b200_hv_last_size(const b200_hv *hv, int which);
+B200_API int b200_hv_last_copy(b200_ctx *ctx, const b200_hv *hv, int which, void *dst);
+/* The annealing alone on given cue lists (CSR over H hypotheses, host arrays): SAOptimize. */
+B200_API int b200_hv_optimize(b200_ctx *ctx, int H, int ns, const int *expl_off, const int *expl_idx, const float *expl_w,
+                              const int *occ_off, const int *occ_idx, int n_cells, const float *outliers_weight,
+                              const int *bad_information, const b200_hv_params *p, unsigned char *mask,
+                              double *best_cost, int *accepted_moves);
+
 /* Statistics of the last descriptor call on this context (for bench records): mean / max number of
  * radius neighbours per keypoint. */
 B200_API int b200_last_neighbor_stats(const b200_ctx *ctx, double *mean_nbrs, int *max_nbrs);

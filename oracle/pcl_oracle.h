@@ -143,6 +143,55 @@ int orc_icp_align(const float *source, int ns, int sstride, const float *target,
 int orc_uniform_sampling(const float *xyz, int n, int stride, double leaf, float *out_xyz, int *out_index);
 int orc_voxel_grid(const float *xyz, int n, int stride, float lx, float ly, float lz, float *out_xyz);
 
+/* pcl::GlobalHypothesesVerification as SHOT_hypothesis.cpp:631-653 drives it (setSceneCloud, addModels(.., true), the
+ * set* calls, verify, getMask); restated in hv_oracle.cpp — see its header for what could not be checked.
+ * occlusion_threshold is the value in force when addModels ran (the reference calls setOcclusionThreshold AFTER
+ * addModels, so its models are filtered with the constructor default 0.005).  detect_clutter must be 0. */
+typedef struct {
+  float resolution;              /* HypothesisVerification::resolution_ 0.005 (voxel size of scene and hypotheses) */
+  float inlier_threshold;        /* setInlierThreshold (hv_inlier_th_ 0.005, SHOT_hypothesis.cpp:59) */
+  float occlusion_threshold;     /* occlusion_thres_ at addModels time */
+  float regularizer;             /* setRegularizer (hv_regularizer_) */
+  float radius_normals;          /* setRadiusNormals (hv_rad_normals_) */
+  float res_occupancy_grid;      /* 0.01 */
+  float w_occupied_multiple_cm;  /* 4 */
+  float initial_temp;            /* 1000 */
+  int max_iterations;            /* 5000 (noimprove_termination_criteria) */
+  int occlusion_reasoning;       /* addModels' second argument */
+  int zbuffer_scene_resolution;  /* 100 */
+  int zbuffer_self_resolution;   /* 75 */
+  float self_occlusion_threshold; /* 0.005 */
+  int detect_clutter;            /* setDetectClutter; only 0 is restated */
+  float radius_clutter;          /* unused without the clutter cue */
+  float clutter_regularizer;     /* unused without the clutter cue */
+  unsigned rand_seed;            /* srand() state std::random_shuffle draws from (1 = never seeded) */
+  unsigned mt_seed;              /* mt19937 default seed 5489 */
+  int sa_uniform_mode;           /* 0: x / 2^32 (boost::uniform_real), 1: the raw 32-bit value (tr1 on a bare engine) */
+} orc_hv_params;
+typedef struct {
+  int valid;        /* addModel returned true */
+  int n_visible;    /* points left by the occlusion filters */
+  int n_points;     /* after VoxelGrid and the NaN-normal compaction */
+  int n_outliers;   /* bad_information_ */
+  int n_explained;  /* explained_.size() */
+  int n_occupancy;  /* complete_cloud_occupancy_indices_.size() */
+  float outliers_weight;
+  float explained_sum; /* sequential float32 sum of explained_distances_ */
+} orc_hv_info;
+void orc_hv_params_default(orc_hv_params *p);
+/* models: H clouds concatenated, model_offsets[H+1] in points.  mask: H bytes.  info: H entries (nullable).
+ * Returns 0, -1 detect_clutter set, -2 voxel lattice too fine, -3 occupancy grid too large. */
+int orc_hv_verify(const float *scene, int n, int sstride, const float *models, const int *model_offsets, int H, int mstride,
+                  const orc_hv_params *P, unsigned char *mask, orc_hv_info *info, double *best_cost, int *accepted_moves,
+                  int *n_scene_points, int *n_cells);
+/* SAOptimize alone on given cue lists (CSR over the H hypotheses). */
+int orc_hv_optimize(int H, int ns, const int *expl_off, const int *expl_idx, const float *expl_w, const int *occ_off,
+                    const int *occ_idx, int n_cells, const float *outliers_weight, const int *bad_information,
+                    const orc_hv_params *P, unsigned char *mask, double *best_cost, int *accepted_moves);
+/* cue lists of the last orc_hv_verify on this thread: 0 expl_off, 1 expl_idx, 2 expl_w (float), 3 occ_off, 4 occ_idx */
+int orc_hv_last_size(int which);
+int orc_hv_last_copy(int which, void *dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,27 @@ class Corr(C.Structure):
     _fields_ = [("index_query", C.c_int), ("index_match", C.c_int), ("distance", C.c_float)]
 
 
+class HvParams(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("inlier_threshold", C.c_float), ("occlusion_threshold", C.c_float),
+                ("regularizer", C.c_float), ("radius_normals", C.c_float), ("res_occupancy_grid", C.c_float),
+                ("w_occupied_multiple_cm", C.c_float), ("initial_temp", C.c_float), ("max_iterations", C.c_int),
+                ("occlusion_reasoning", C.c_int), ("zbuffer_scene_resolution", C.c_int),
+                ("zbuffer_self_resolution", C.c_int), ("self_occlusion_threshold", C.c_float),
+                ("detect_clutter", C.c_int), ("radius_clutter", C.c_float), ("clutter_regularizer", C.c_float),
+                ("rand_seed", C.c_uint), ("mt_seed", C.c_uint), ("sa_uniform_mode", C.c_int)]
+
+
+class HvInfo(C.Structure):
+    _fields_ = [("valid", C.c_int), ("n_visible", C.c_int), ("n_points", C.c_int), ("n_outliers", C.c_int),
+                ("n_explained", C.c_int), ("n_occupancy", C.c_int), ("outliers_weight", C.c_float),
+                ("explained_sum", C.c_float)]
+
+
+HV_INFO_DTYPE = np.dtype([("valid", "<i4"), ("n_visible", "<i4"), ("n_points", "<i4"), ("n_outliers", "<i4"),
+                          ("n_explained", "<i4"), ("n_occupancy", "<i4"), ("outliers_weight", "<f4"),
+                          ("explained_sum", "<f4")])
+
+
 class BoardParams(C.Structure):
     _fields_ = [("find_holes", C.c_int), ("tangent_radius", C.c_float), ("margin_thresh", C.c_float),
                 ("check_margin_array_size", C.c_int), ("hole_size_prob_thresh", C.c_float), ("steep_thresh", C.c_float)]
@@ -28,7 +49,7 @@ CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distanc
 
 def build(force=False):
     so = os.path.join(_HERE, "libpcl_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("pcl_oracle.cpp", "pcl_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("pcl_oracle.cpp", "hv_oracle.cpp", "pcl_oracle.h", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -86,6 +107,18 @@ def lib():
         L.orc_umeyama3.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
         L.orc_mt19937_nth.restype = C.c_uint32
         L.orc_mt19937_nth.argtypes = [C.c_uint32, C.c_int]
+        L.orc_hv_params_default.restype = None
+        L.orc_hv_params_default.argtypes = [C.POINTER(HvParams)]
+        L.orc_hv_verify.restype = C.c_int
+        L.orc_hv_verify.argtypes = [fp, C.c_int, C.c_int, fp, ip, C.c_int, C.c_int, C.POINTER(HvParams),
+                                    C.POINTER(C.c_ubyte), C.c_void_p, C.POINTER(C.c_double), ip, ip, ip]
+        L.orc_hv_optimize.restype = C.c_int
+        L.orc_hv_optimize.argtypes = [C.c_int, C.c_int, ip, ip, fp, ip, ip, C.c_int, fp, ip, C.POINTER(HvParams),
+                                      C.POINTER(C.c_ubyte), C.POINTER(C.c_double), ip]
+        L.orc_hv_last_size.restype = C.c_int
+        L.orc_hv_last_size.argtypes = [C.c_int]
+        L.orc_hv_last_copy.restype = C.c_int
+        L.orc_hv_last_copy.argtypes = [C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -348,3 +381,70 @@ def umeyama3(src, dst):
 
 def mt19937_nth(seed, nth):
     return int(lib().orc_mt19937_nth(seed, nth))
+
+
+def hv_params(**kw):
+    """GlobalHypothesesVerification parameters: PCL's constructor defaults, overridden by keyword."""
+    p = HvParams()
+    lib().orc_hv_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown hypothesis-verification parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+def _hv_models(models):
+    models = [_pts(m) for m in models]
+    offs = np.zeros(len(models) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(m) for m in models])
+    flat = np.ascontiguousarray(np.concatenate([m[:, :3] for m in models]) if models else np.zeros((0, 3), np.float32),
+                                dtype=np.float32)
+    if len(flat) == 0:
+        flat = np.zeros((1, 3), np.float32)
+    return flat, offs
+
+
+def hv_verify(scene, models, params):
+    """GlobalHypothesesVerification (SHOT_hypothesis.cpp:631-653).  Returns a dict: mask, info, best_cost,
+    accepted_moves, n_scene_points, n_cells and the cue lists (expl_off / expl_idx / expl_w / occ_off / occ_idx,
+    CSR over the valid hypotheses)."""
+    scene = _pts(scene)
+    flat, offs = _hv_models(models)
+    H = len(models)
+    mask = np.zeros(max(H, 1), dtype=np.uint8)
+    info = np.zeros(max(H, 1), dtype=HV_INFO_DTYPE)
+    cost = C.c_double(0.0)
+    acc, ns, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().orc_hv_verify(_f(scene), len(scene), scene.shape[1], _f(flat), _i(offs), H, 3, C.byref(params),
+                             mask.ctypes.data_as(C.POINTER(C.c_ubyte)), info.ctypes.data, C.byref(cost), C.byref(acc),
+                             C.byref(ns), C.byref(nc))
+    if rc != 0:
+        raise ValueError("orc_hv_verify failed: %d" % rc)
+    out = {"mask": mask[:H].astype(bool), "info": info[:H], "best_cost": cost.value, "accepted_moves": acc.value,
+           "n_scene_points": ns.value, "n_cells": nc.value}
+    for which, (name, dt) in enumerate((("expl_off", np.int32), ("expl_idx", np.int32), ("expl_w", np.float32),
+                                        ("occ_off", np.int32), ("occ_idx", np.int32))):
+        a = np.zeros(max(lib().orc_hv_last_size(which), 1), dtype=dt)
+        n = lib().orc_hv_last_size(which)
+        lib().orc_hv_last_copy(which, a.ctypes.data)
+        out[name] = a[:n]
+    return out
+
+
+def hv_optimize(ns, expl_off, expl_idx, expl_w, occ_off, occ_idx, n_cells, outliers_weight, bad_information, params):
+    """SAOptimize on given cue lists.  Returns (mask, best_cost, accepted_moves)."""
+    H = len(expl_off) - 1
+    eo = np.ascontiguousarray(expl_off, dtype=np.int32)
+    ei = np.ascontiguousarray(np.append(expl_idx, 0), dtype=np.int32)
+    ew = np.ascontiguousarray(np.append(expl_w, 0), dtype=np.float32)
+    oo = np.ascontiguousarray(occ_off, dtype=np.int32)
+    oi = np.ascontiguousarray(np.append(occ_idx, 0), dtype=np.int32)
+    ow = np.ascontiguousarray(outliers_weight, dtype=np.float32)
+    bi = np.ascontiguousarray(bad_information, dtype=np.int32)
+    mask = np.zeros(max(H, 1), dtype=np.uint8)
+    cost = C.c_double(0.0)
+    acc = C.c_int(0)
+    lib().orc_hv_optimize(H, int(ns), _i(eo), _i(ei), _f(ew), _i(oo), _i(oi), int(n_cells), _f(ow), _i(bi),
+                          C.byref(params), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.byref(cost), C.byref(acc))
+    return mask[:H].astype(bool), cost.value, acc.value
