@@ -338,7 +338,7 @@ struct AnnealArgs {
   int *out_accepted;
 };
 
-constexpr int HV_SA_THREADS = 512;
+constexpr int HV_SA_THREADS = 1024;
 
 // sequential float32 sum of v[0..n) (optionally only where gate[i] > 0) by one warp: coalesced loads, the additions in
 // index order on lane 0's accumulator
@@ -392,10 +392,19 @@ __device__ void hv_block_sum2(int a, int b, int *red, int *oa, int *ob) {
   __syncthreads();
 }
 
+// A move is evaluated without touching the arrays: the duplicity changes are integer functions of the current
+// counts, the float32 running values live on thread 0, and PCL's explained_by_RM_distance_weighted is never read
+// again after the initial total.  The counts only change when a move is accepted, and an accepted move ends the
+// iteration — so all H moves are evaluated at once, and only after an accepted move (phase A); thread 0 replays
+// PCL's sequence over the shuffled order on the running values: apply, test, unapply (the float32 round trip
+// (v + a) - a is kept as PCL computes it; the unapply's duplicity changes are the exact negatives of the apply's) up
+// to the first accepted move (phase B), and the block writes that move's counts (phase C).  An iteration that
+// accepts nothing costs two barriers and H scalar evaluations.
 __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) {
   __shared__ int red[2 * (HV_SA_THREADS / 32)];
-  __shared__ int s_a, s_b, s_ctl;
-  const int tid = threadIdx.x;
+  __shared__ int s_d0[HV_MAX_HYPOTHESES], s_d1[HV_MAX_HYPOTHESES];
+  __shared__ int s_a, s_b, s_ctl, s_stop;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int H = A.H;
   // ---- initial state: every hypothesis active
   for (int h = tid; h < H; h += HV_SA_THREADS) A.active[h] = 1, A.best[h] = 1;
@@ -446,41 +455,21 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
                     -1.f);
     best_cost = cost;
   }
-  // one move evaluation (evaluateSolution after the flip); cost updated on thread 0
-  auto flip = [&](int m) {
-    const int sgn = A.active[m] ? -1 : 1;  // the state before the flip
+  // evaluateSolution's value from the running values (thread 0)
+  auto scalar_flip = [&](int m, int sgn, int d0, int d1) {
     const float sign = (float)sgn;
-    int d0 = 0, d1 = 0;
-    const HvExpl e = A.expl[m];
-    for (int k = tid; k < e.n; k += HV_SA_THREADS) {
-      const int j = e.idx[k];
-      const int prev = A.explained[j], cur = prev + sgn;
-      A.explained[j] = cur;
-      A.weighted[j] += e.w[k] * sign;
-      d0 += hv_dup_rule(prev, cur, sgn);
-    }
-    const HvOcc o = A.occ[m];
-    for (int k = tid; k < o.n; k += HV_SA_THREADS) {
-      const int c = o.idx[k];
-      const int prev = A.occupancy[c], cur = prev + sgn;
-      A.occupancy[c] = cur;
-      d1 += hv_dup_rule(prev, cur, sgn);
-    }
-    hv_block_sum2(d0, d1, red, &s_a, &s_b);
-    if (tid == 0) {
-      A.active[m] = sgn > 0 ? 1 : 0;
-      n_active += sgn;
-      previous_explained += A.seq_sum[m] * sign;
-      previous_dup += s_a;
-      previous_cm += s_b;
-      const float bad_info = previous_bad + (A.outliers_weight[m] * (float)A.bad_information[m]) * sign;
-      previous_bad = bad_info;
-      const float duplicity_cm = (float)previous_cm * A.w_cm;
-      cost = (double)((previous_explained - bad_info - (float)previous_dup - previous_unexplained - duplicity_cm -
-                       (float)n_active) *
-                      -1.f);
-    }
+    n_active += sgn;
+    previous_explained += A.seq_sum[m] * sign;
+    previous_dup += d0;
+    previous_cm += d1;
+    const float bad_info = previous_bad + (A.outliers_weight[m] * (float)A.bad_information[m]) * sign;
+    previous_bad = bad_info;
+    const float duplicity_cm = (float)previous_cm * A.w_cm;
+    cost = (double)((previous_explained - bad_info - (float)previous_dup - previous_unexplained - duplicity_cm -
+                     (float)n_active) *
+                    -1.f);
   };
+  bool dirty = true;  // the counts changed since the moves were last evaluated (uniform over the block)
   for (int it = 0; it < A.n_iter; ++it) {
     if (tid == 0) {  // noimprove_termination_criteria, then the temperature test
       int stop = 0;
@@ -491,15 +480,45 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
       if (iterations_left <= 0) stop = 1;
       --iterations_left;
       if (!(temp > 1e-7)) stop = 1;
-      s_ctl = stop;
+      s_stop = stop;
     }
-    __syncthreads();
-    if (s_ctl) break;
-    const double actual_cost = cost;  // meaningful on thread 0
-    for (int mi = 0; mi < H; ++mi) {
-      const int m = A.perms[(size_t)it * H + mi];
-      flip(m);
-      if (tid == 0) {
+    __syncthreads();  // also orders the previous iteration's count writes before the reads below
+    if (s_stop) break;
+    // ---- phase A (only after the counts changed): duplicity changes of every move against the current counts; the
+    // block strides over one list after the other, per-move sums by shared-memory atomics, no barrier in between
+    if (dirty) {
+      for (int h = tid; h < H; h += HV_SA_THREADS) s_d0[h] = 0, s_d1[h] = 0;
+      __syncthreads();
+      for (int m = 0; m < H; ++m) {
+        const int sgn = A.active[m] ? -1 : 1;
+        int d0 = 0, d1 = 0;
+        const HvExpl e = A.expl[m];
+        for (int k = tid; k < e.n; k += HV_SA_THREADS) {
+          const int prev = A.explained[e.idx[k]];
+          d0 += hv_dup_rule(prev, prev + sgn, sgn);
+        }
+        const HvOcc o = A.occ[m];
+        for (int k = tid; k < o.n; k += HV_SA_THREADS) {
+          const int prev = A.occupancy[o.idx[k]];
+          d1 += hv_dup_rule(prev, prev + sgn, sgn);
+        }
+        d0 = warp_sum(d0);
+        d1 = warp_sum(d1);
+        if (lane == 0) {
+          if (d0) atomicAdd(&s_d0[m], d0);
+          if (d1) atomicAdd(&s_d1[m], d1);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase B: PCL's sequence over the shuffled moves, up to the first accepted one
+    if (tid == 0) {
+      const double actual_cost = cost;
+      int taken = -1;
+      for (int mi = 0; mi < H; ++mi) {
+        const int m = A.perms[(size_t)it * H + mi];
+        const int sgn = A.active[m] ? -1 : 1;
+        scalar_flip(m, sgn, s_d0[m], s_d1[m]);  // apply_and_evaluate
         const double delta = cost - actual_cost;
         bool take = delta < 0;
         if (!take) {
@@ -507,26 +526,35 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
           const double u = A.uniform_mode == 1 ? (double)x : (double)x / 4294967296.0;
           take = u < exp(2.0 * -delta / temp);
         }
-        int ctl = 0;
         if (take) {
-          ctl = 1;
           accepted++;
+          A.active[m] = sgn > 0 ? 1 : 0;
+          taken = m;
           if (cost < best_cost) {
             best_cost = cost;
-            ctl = 2;
+            taken |= 0x40000000;  // also a new best
           }
+          break;
         }
-        s_ctl = ctl;
+        scalar_flip(m, -sgn, -s_d0[m], -s_d1[m]);  // unapply
       }
-      __syncthreads();
-      const int ctl = s_ctl;
-      if (ctl == 2)
-        for (int h = tid; h < H; h += HV_SA_THREADS) A.best[h] = A.active[h];
-      __syncthreads();
-      if (ctl) break;
-      flip(m);  // unapply
+      s_ctl = taken;
+      temp *= 0.95;
     }
-    if (tid == 0) temp *= 0.95;
+    __syncthreads();
+    // ---- phase C: the accepted move's counts
+    const int ctl = s_ctl;
+    if (ctl >= 0) {
+      const int m = ctl & 0x3fffffff;
+      const int sgn = A.active[m] ? 1 : -1;  // the state after the flip
+      const HvExpl e = A.expl[m];
+      for (int k = tid; k < e.n; k += HV_SA_THREADS) A.explained[e.idx[k]] += sgn;
+      const HvOcc o = A.occ[m];
+      for (int k = tid; k < o.n; k += HV_SA_THREADS) A.occupancy[o.idx[k]] += sgn;
+      if (ctl & 0x40000000)
+        for (int h = tid; h < H; h += HV_SA_THREADS) A.best[h] = A.active[h];
+    }
+    dirty = ctl >= 0;
   }
   if (tid == 0) {
     *A.out_cost = best_cost;

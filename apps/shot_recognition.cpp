@@ -11,12 +11,15 @@
 //
 // usage: shot_recognition <model.f32> <model_kp.f32 | us:leaf> <scene.f32> <scene_kp.f32 | us:leaf> <out_prefix>
 //                         [normal_k=10] [descr_rad=0.02] [match_thr=0.25] [cg_size=0.02] [cg_thresh=2] [loop|batch] [gc|hough|hough-shot]
-//                         [icp:N]
+//                         [icp:N] [hv:<normal radius>]
 // writes <out_prefix>.corr (b200_corr records), <out_prefix>.T (instances x 16 float),
 //        <out_prefix>.inst (int32 count per instance followed by the records)
 //        with hough, <out_prefix>.rf (model then scene BOARD frames, 9 float each)
 //        with icp:N, <out_prefix>.icp (per instance, first 8: 16 float refined pose, fitness, converged) — the
 //        reference's icp_align (SHOT.cpp:177-192) on the model placed by the grouped pose
+//        with hv:r (needs icp:N), <out_prefix>.hv (one byte per registered instance) — the reference's hypothesis
+//        verification block (SHOT_hypothesis.cpp:631-653) on the ICP-registered instances, with its parameters
+//        (:58-64) except the normal radius r (the reference's 5 mm suits its 1 mm scans, not the synthetic clouds)
 #include <pcl_b200/pcl_b200.h>
 
 #include <chrono>
@@ -65,6 +68,11 @@ int main(int argc, char **argv) {
   const bool board_frames = algo == "hough";
   const float rf_rad_ = 0.02f;  // SHOT.cpp:51
   const int icp_iters = (argc > 13 && std::string(argv[13]).compare(0, 4, "icp:") == 0) ? atoi(argv[13] + 4) : 0;
+  const float hv_rad_normals_ = (argc > 14 && std::string(argv[14]).compare(0, 3, "hv:") == 0) ? (float)atof(argv[14] + 3) : 0.f;
+  // SHOT_hypothesis.cpp:58-64
+  const float hv_clutter_reg_ = 0.001f, hv_inlier_th_ = 0.005f, hv_occlusion_th_ = 0.001f, hv_rad_clutter_ = 0.003f,
+              hv_regularizer_ = 0.001f;
+  const bool hv_detect_clutter_ = false;
 
   pcl::PointCloud<PointType>::Ptr model(new pcl::PointCloud<PointType>()), scene(new pcl::PointCloud<PointType>());
   pcl::PointCloud<PointType>::Ptr model_keypoints(new pcl::PointCloud<PointType>()),
@@ -232,6 +240,7 @@ int main(int argc, char **argv) {
     if (n) fwrite(clustered_corrs[i].data(), sizeof(pcl::Correspondence), (size_t)n, f);
   }
   fclose(f);
+  std::vector<pcl::PointCloud<PointType>::ConstPtr> registered_instances;
   if (icp_iters > 0) {
     f = fopen((prefix + ".icp").c_str(), "wb");
     for (size_t i = 0; i < rototranslations.size() && i < 8; ++i) {
@@ -251,6 +260,31 @@ int main(int argc, char **argv) {
       rec[16] = (float)score;
       rec[17] = icp.hasConverged() ? 1.f : 0.f;
       fwrite(rec, sizeof(float), 18, f);
+      registered_instances.push_back(pcl::PointCloud<PointType>::ConstPtr(new pcl::PointCloud<PointType>(cloud_icp)));
+    }
+    fclose(f);
+  }
+  if (hv_rad_normals_ > 0.f && registered_instances.size() > 0) {
+    // SHOT_hypothesis.cpp:631-653, statement for statement
+    std::cout << "--- Hypotheses Verification ---" << std::endl;
+    std::vector<bool> hypotheses_mask;  // Mask Vector to identify positive hypotheses
+    pcl::GlobalHypothesesVerification<PointType, PointType> GoHv;
+    GoHv.setSceneCloud(scene);                      // Scene Cloud
+    GoHv.addModels(registered_instances, true);     // Models to verify
+    GoHv.setInlierThreshold(hv_inlier_th_);
+    GoHv.setOcclusionThreshold(hv_occlusion_th_);
+    GoHv.setRegularizer(hv_regularizer_);
+    GoHv.setRadiusClutter(hv_rad_clutter_);
+    GoHv.setClutterRegularizer(hv_clutter_reg_);
+    GoHv.setDetectClutter(hv_detect_clutter_);
+    GoHv.setRadiusNormals(hv_rad_normals_);
+    GoHv.verify();
+    GoHv.getMask(hypotheses_mask);  // i-element TRUE if hvModels[i] verifies hypotheses
+    f = fopen((prefix + ".hv").c_str(), "wb");
+    for (size_t i = 0; i < hypotheses_mask.size(); i++) {
+      if (hypotheses_mask[i]) std::cout << "Instance " << i << " is GOOD! <---" << std::endl;
+      const unsigned char b = hypotheses_mask[i] ? 1 : 0;
+      fwrite(&b, 1, 1, f);
     }
     fclose(f);
   }

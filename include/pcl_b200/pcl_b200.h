@@ -994,6 +994,92 @@ class IterativeClosestPoint {
   Matrix4f final_transformation_;
 };
 
+/* ---- pcl::GlobalHypothesesVerification<ModelT, SceneT> (SHOT_hypothesis.cpp:631-653) --------------------------
+ * Same call order, same order dependence as PCL: setSceneCloud voxelises the scene at once, addModels filters the
+ * hypotheses with the occlusion threshold in force at that moment, the other setters are read by verify(). */
+template <class ModelT, class SceneT>
+class GlobalHypothesesVerification {
+ public:
+  GlobalHypothesesVerification() { b200_hv_params_default(&p_); }
+  ~GlobalHypothesesVerification() {
+    if (hv_) b200_hv_destroy(hv_);
+  }
+  GlobalHypothesesVerification(const GlobalHypothesesVerification &) = delete;
+  GlobalHypothesesVerification &operator=(const GlobalHypothesesVerification &) = delete;
+  void setResolution(float r) { p_.resolution = r, push(); }
+  void setInlierThreshold(float r) { p_.inlier_threshold = r, push(); }
+  void setOcclusionThreshold(float t) { p_.occlusion_threshold = t, push(); }
+  void setRegularizer(float r) { p_.regularizer = r, push(); }
+  void setRadiusClutter(float r) { p_.radius_clutter = r, push(); }
+  void setClutterRegularizer(float r) { p_.clutter_regularizer = r, push(); }
+  void setDetectClutter(bool d) { p_.detect_clutter = d ? 1 : 0, push(); }
+  void setRadiusNormals(float r) { p_.radius_normals = r, push(); }
+  void setMaxIterations(int i) { p_.max_iterations = i, push(); }
+  void setInitialTemp(float t) { p_.initial_temp = t, push(); }
+  void setSceneCloud(const typename PointCloud<SceneT>::Ptr &scene) { setSceneCloud(typename PointCloud<SceneT>::ConstPtr(scene)); }
+  void setSceneCloud(const typename PointCloud<SceneT>::ConstPtr &scene) {
+    n_models_ = 0;
+    mask_.clear();
+    if (!handle() || !scene) return;
+    scene_ok_ = detail::ok(b200_hv_set_scene(detail::ctx(), hv_, detail::xyz(scene->points), (int)scene->size(),
+                                             detail::stride<SceneT>()),
+                           "GlobalHypothesesVerification::setSceneCloud");
+  }
+  void addModels(std::vector<typename PointCloud<ModelT>::ConstPtr> &models, bool occlusion_reasoning = false) {
+    mask_.clear();
+    n_models_ = 0;
+    if (!handle()) return;
+    std::vector<int> off(1, 0);
+    std::vector<float> flat;
+    for (const auto &m : models) {
+      const size_t n = m ? m->size() : 0;
+      for (size_t i = 0; i < n; ++i) {
+        flat.push_back(m->points[i].x);
+        flat.push_back(m->points[i].y);
+        flat.push_back(m->points[i].z);
+      }
+      off.push_back((int)(flat.size() / 3));
+    }
+    if (flat.empty()) flat.resize(3, 0.f);
+    if (detail::ok(b200_hv_add_models(detail::ctx(), hv_, flat.data(), off.data(), (int)models.size(), 3,
+                                      occlusion_reasoning ? 1 : 0),
+                   "GlobalHypothesesVerification::addModels"))
+      n_models_ = (int)models.size();
+  }
+  void addModels(std::vector<typename PointCloud<ModelT>::Ptr> &models, bool occlusion_reasoning = false) {
+    std::vector<typename PointCloud<ModelT>::ConstPtr> c(models.begin(), models.end());
+    addModels(c, occlusion_reasoning);
+  }
+  void verify() {
+    mask_.assign((size_t)n_models_, false);
+    if (!handle() || n_models_ == 0) return;
+    std::vector<unsigned char> m((size_t)n_models_, 0);
+    if (!detail::ok(b200_hv_verify(detail::ctx(), hv_, m.data(), nullptr, &best_cost_, &accepted_moves_),
+                    "GlobalHypothesesVerification::verify"))
+      return;
+    for (int i = 0; i < n_models_; ++i) mask_[(size_t)i] = m[(size_t)i] != 0;
+  }
+  void getMask(std::vector<bool> &mask) const { mask = mask_; }
+  double getBestCost() const { return best_cost_; } /* not in PCL: the annealing's best cost */
+
+ private:
+  bool handle() {
+    if (hv_) return true;
+    if (!detail::ctx()) return false;
+    return detail::ok(b200_hv_create(detail::ctx(), &p_, &hv_), "GlobalHypothesesVerification");
+  }
+  void push() {
+    if (hv_) b200_hv_set_params(hv_, &p_);
+  }
+  b200_hv *hv_ = nullptr;
+  b200_hv_params p_;
+  int n_models_ = 0;
+  bool scene_ok_ = false;
+  std::vector<bool> mask_;
+  double best_cost_ = 0.0;
+  int accepted_moves_ = 0;
+};
+
 }  // namespace pcl_b200
 
 #ifdef PCL_B200_AS_PCL

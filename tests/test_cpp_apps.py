@@ -184,6 +184,42 @@ def test_shot_recognition_app_icp_refinement(apps, orc, synth, tmp_path):
 
 
 @pytest.mark.gpu
+def test_shot_recognition_app_hypothesis_verification(apps, orc, synth, tmp_path):
+    """`hv:r`: the reference's hypothesis-verification block (SHOT_hypothesis.cpp:631-653) through the
+    GlobalHypothesesVerification adapter on the ICP-registered instances; the mask equals the restatement run on the
+    same instances (the app's refined poses applied to the model) with the reference's parameters in its call order
+    (the occlusion threshold arrives after addModels: the constructor's 0.005 filters the models)."""
+    model = synth.make_model("y", 8000)
+    scene = synth.make_kinect_scene(("y", "diagonal", "horizontal"), 150000, scene_id=5)
+    kpm, kps = synth.uniform_sampling(model, 0.015), synth.uniform_sampling(scene, 0.015)
+    for name, a in (("m", model), ("mk", kpm), ("s", scene), ("sk", kps)):
+        _write(tmp_path / (name + ".f32"), a)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([apps["shot_recognition"]] + [str(tmp_path / (n + ".f32")) for n in ("m", "mk", "s", "sk")] +
+                       [prefix, "10", "0.03", "0.25", "0.02", "3", "batch", "gc", "icp:5", "hv:0.02"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rec = np.fromfile(prefix + ".icp", dtype=np.float32).reshape(-1, 18)
+    T, _ = _read_instances(prefix)
+    if len(rec) == 0:
+        assert not os.path.exists(prefix + ".hv")
+        pytest.skip("the grouping found no instance in this scene")
+    assert "--- Hypotheses Verification ---" in r.stdout
+    mask = np.fromfile(prefix + ".hv", dtype=np.uint8).astype(bool)
+    assert len(mask) == len(rec)
+    # the registered instance = the model placed by the grouped pose, then by ICP's final transformation
+    inst = [orc.transform_points(orc.transform_points(model, T[i]), rec[i, :16].reshape(4, 4)) for i in range(len(rec))]
+    p = orc.hv_params(detect_clutter=0, occlusion_reasoning=1, inlier_threshold=0.005, regularizer=0.001,
+                      radius_clutter=0.003, clutter_regularizer=0.001, radius_normals=0.02)
+    o = orc.hv_verify(scene, inst, p)
+    print("hv app: %d instances, mask %s, restatement %s, visible %s" % (len(rec), mask.astype(int), o["mask"].astype(int),
+                                                                         o["info"]["n_visible"]))
+    assert mask.tolist() == o["mask"].tolist()
+    for i, m in enumerate(mask):
+        assert (("Instance %d is GOOD!" % i) in r.stdout) == bool(m)
+
+
+@pytest.mark.gpu
 def test_shot_recognition_app_hough_board_frames(apps, orc, synth, tmp_path):
     """The reference's Hough branch as written (SHOT.cpp:433-470): BOARD frames (find_holes, rf_rad 0.02) for model
     and scene keypoints through the BOARDLocalReferenceFrameEstimation adapter, then Hough3DGrouping.  Frames equal
