@@ -81,6 +81,46 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
     }
   };
 
+  // Slab pruning.  Every point of a cell row (y, z fixed) is at least the row's slab distance away from the query;
+  // once the list is full, a row (or a single cell of it) that is STRICTLY farther than the current k-th neighbour
+  // cannot change the result — (distance, index) ties included — and is skipped.  -DB200_KNN_NO_PRUNE restores the
+  // unpruned scan (the result is the same by construction; the parity tests hold either way).
+#ifndef B200_KNN_NO_PRUNE
+  auto gap = [&](int c, int qc, float q, float lo) -> float {  // lower bound of |coordinate - q| inside cell index c
+    float d = 0.f;
+    if (c > qc) d = (lo + (float)c * g.h) - q;
+    else if (c < qc) d = q - (lo + (float)(c + 1) * g.h);
+    return fmaxf(d - margin, 0.f);
+  };
+  auto row_far = [&](int y, int z, float gx) -> bool {
+    if (cnt < k) return false;
+    const float gy = gap(y, cy, qy, g.loy), gz = gap(z, cz, qz, g.loz);
+    return (gx * gx + gy * gy + gz * gz) * 0.99999f > knn_d2(worst);
+  };
+  // a row's run of cells xa..xb (it spans the query's column): the end cells are dropped while they are too far
+  auto scan_row = [&](int y, int z, int row, int xa, int xb) {
+    if (cnt == k) {
+      const float gy = gap(y, cy, qy, g.loy), gz = gap(z, cz, qz, g.loz);
+      const float yz = gy * gy + gz * gz, w = knn_d2(worst);
+      if (yz * 0.99999f > w) return;
+      while (xa < cx) {
+        const float gx = gap(xa, cx, qx, g.lox);
+        if (!((gx * gx + yz) * 0.99999f > w)) break;
+        ++xa;
+      }
+      while (xb > cx) {
+        const float gx = gap(xb, cx, qx, g.lox);
+        if (!((gx * gx + yz) * 0.99999f > w)) break;
+        --xb;
+      }
+    }
+    scan_run(row + xa, row + xb);
+  };
+#else
+  auto gap = [&](int, int, float, float) -> float { return 0.f; };
+  auto row_far = [&](int, int, float) -> bool { return false; };
+  auto scan_row = [&](int, int, int row, int xa, int xb) { scan_run(row + xa, row + xb); };
+#endif
   for (int R = 0; R <= maxR; ++R) {
     const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
     const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
@@ -97,10 +137,10 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
         if (z < 0 || z >= g.dz || y < 0 || y >= g.dy) continue;
         const int row = g.dx * (y + g.dy * z);
         if (t == 0) {
-          if (cx - 1 >= 0) scan_run(row + cx - 1, row + cx - 1);
-          if (cx + 1 <= g.dx - 1) scan_run(row + cx + 1, row + cx + 1);
+          if (cx - 1 >= 0 && !row_far(y, z, gap(cx - 1, cx, qx, g.lox))) scan_run(row + cx - 1, row + cx - 1);
+          if (cx + 1 <= g.dx - 1 && !row_far(y, z, gap(cx + 1, cx, qx, g.lox))) scan_run(row + cx + 1, row + cx + 1);
         } else {
-          scan_run(row + x0, row + x1);
+          scan_row(y, z, row, x0, x1);
         }
       }
     } else
@@ -109,10 +149,11 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
         const bool face = (abs(z - cz) == R) || (abs(y - cy) == R);
         const int row = g.dx * (y + g.dy * z);
         if (face) {
-          scan_run(row + x0, row + x1);
+          scan_row(y, z, row, x0, x1);
         } else {
-          if (cx - R >= 0) scan_run(row + cx - R, row + cx - R);
-          if (cx + R <= g.dx - 1) scan_run(row + cx + R, row + cx + R);  // R > 0 here (R == 0 is a face row)
+          if (cx - R >= 0 && !row_far(y, z, gap(cx - R, cx, qx, g.lox))) scan_run(row + cx - R, row + cx - R);
+          // R > 0 here (R == 0 is a face row)
+          if (cx + R <= g.dx - 1 && !row_far(y, z, gap(cx + R, cx, qx, g.lox))) scan_run(row + cx + R, row + cx + R);
         }
       }
     const bool whole = (z0 == 0 && z1 == g.dz - 1 && y0 == 0 && y1 == g.dy - 1 && x0 == 0 && x1 == g.dx - 1);
