@@ -128,7 +128,9 @@ __device__ inline int knn_query(const GridView &g, float qx, float qy, float qz,
     if (R == 1) {
       // the first shell, nearest rows first (|dz| + |dy| = 0, 1, 2): the list fills with close points
       // early, so that most later candidates fail the cheap "farther than the current k-th" test
-      // instead of being inserted and displaced again (the result does not depend on the order)
+      // instead of being inserted and displaced again (the result does not depend on the order).  Measured and dropped:
+      // visiting, of each pair of opposite neighbours, the one on the query's side of its cell first — the lanes of a
+      // warp then read different rows at the same step: 1.06 against 1.02 ms
 #pragma unroll 1
       for (int t = 0; t < 9; ++t) {
         const int dz = (t == 3) ? -1 : (t == 4) ? 1 : (t >= 5) ? ((t & 1) ? -1 : 1) : 0;
