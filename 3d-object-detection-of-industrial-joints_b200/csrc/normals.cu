@@ -163,7 +163,8 @@ __global__ void normals_knn_kernel(GridView g, const float4 *__restrict__ q, int
 __global__ void __launch_bounds__(128) normals_radius_kernel(GridView g, const float4 *__restrict__ q, int nq,
                                                              float radius, float r2, int cap,
                                                              unsigned long long *glob_key, int *glob_pos, float vpx,
-                                                             float vpy, float vpz, float4 *__restrict__ out) {
+                                                             float vpy, float vpz, float4 *__restrict__ out,
+                                                             const int *__restrict__ counts, int min_count) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_count;
   __shared__ float4 s_pts[128];
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(128) normals_radius_kernel(GridView g, const f
     pos = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(unsigned long long));
   }
   for (int i = blockIdx.x; i < nq; i += gridDim.x) {
+    if (counts[i] < min_count) continue;  // done by normals_radius_warp_kernel
     const float4 p = q[i];
     int n = gather_radius(g, p.x, p.y, p.z, radius, r2, key, pos, cap, &s_count);
     if (n > cap) n = cap;
@@ -226,6 +228,141 @@ __global__ void __launch_bounds__(128) normals_radius_kernel(GridView g, const f
     }
     __syncthreads();
   }
+}
+
+
+// radius mode, one query per WARP (neighbourhoods of up to CAP points; larger ones are left to the CTA kernel above).
+// The CTA form spends most of a query's time with 119 of its 128 threads waiting: block-wide barriers between the
+// 28-36 stages of the sort, and the nine sequential float32 sums at the end.  Here a warp gathers its query's
+// neighbours into its own slice of shared memory (four 32-point chunks per trip, ballot compaction), orders the
+// (d2, index) keys with a bitonic network synchronised by __syncwarp only, stages the points in that order and lets
+// nine lanes run PCL's nine sums — each still strictly in (d2, index) order, so the covariance is the same bit for
+// bit — while the SM's other warps work on their own queries.  Measured times: DESIGN.md section 4.
+constexpr int NRW_WARPS = 8;
+template <int CAP>
+struct NrwSmem {
+  unsigned long long key[CAP];
+  float4 pts[CAP];
+  int pos[CAP];
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(NRW_WARPS * 32)
+    normals_radius_warp_kernel(GridView g, const float4 *__restrict__ q, int nq, float radius, float r2,
+                               const int *__restrict__ counts, float vpx, float vpy, float vpz, float4 *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NrwSmem<CAP> &sm = reinterpret_cast<NrwSmem<CAP> *>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * NRW_WARPS;
+  const float4 *__restrict__ pts = g.pts;
+  const int *__restrict__ cs = g.cell_start;
+  // which components of a staged point (x, y, z, 1) this lane multiplies: xx xy xz yy yz zz x y z
+  const int ia = (lane < 3) ? 0 : (lane < 5) ? 1 : (lane == 5) ? 2 : (lane < 9 ? lane - 6 : 0);
+  const int ib = (lane < 3) ? lane : (lane < 5) ? lane - 2 : (lane == 5) ? 2 : 3;
+  for (int i = blockIdx.x * NRW_WARPS + (threadIdx.x >> 5); i < nq; i += nwarps) {
+    const int cnt = counts[i];
+    if (cnt > CAP) continue;  // the CTA kernel's
+    const float4 c = q[i];
+    if (cnt < 3) {  // search failure or computePointNormal: fewer than three neighbours
+      if (lane == 0) out[i] = make_float4(nanf32(), nanf32(), nanf32(), nanf32());
+      continue;
+    }
+    // ---- gather (the count pass found cnt <= CAP neighbours: the same test on the same points)
+    int n = 0;
+    int x0, x1, y0, y1, z0, z1;
+    if (ball_cell_range(g, c.x, c.y, c.z, radius, x0, x1, y0, y1, z0, z1)) {
+      for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+          const int base = g.dx * (y + g.dy * z);
+          const int s0 = cs[base + x0], e = cs[base + x1 + 1];
+          for (int j0 = s0; j0 < e; j0 += 128) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j0 + 32 * u + lane;
+              p[u] = (j < e) ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j0 + 32 * u + lane;
+              const float d2 = sqdist3(c.x, c.y, c.z, p[u].x, p[u].y, p[u].z);
+              const bool hit = j < e && d2 < r2;
+              const unsigned m = __ballot_sync(0xffffffffu, hit);
+              if (hit) {
+                const int slot = n + __popc(m & ((1u << lane) - 1u));
+                if (slot < CAP) {
+                  sm.key[slot] = nbr_key(d2, orig_index(p[u]));
+                  sm.pos[slot] = j;
+                }
+              }
+              n += __popc(m);
+            }
+          }
+        }
+    }
+    if (n > CAP) n = CAP;  // cannot happen: cnt is the same count
+    // ---- order by (d2, index): FLANN's result order
+    int np = 32;
+    while (np < n) np <<= 1;
+    for (int t = n + lane; t < np; t += 32) {
+      sm.key[t] = ~0ull;
+      sm.pos[t] = -1;
+    }
+    __syncwarp();
+    for (int k = 2; k <= np; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (np >> 1); t += 32) {
+          const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int b = a | j;
+          const bool up = ((a & k) == 0);
+          const unsigned long long ka = sm.key[a], kb = sm.key[b];
+          if ((ka > kb) == up) {
+            sm.key[a] = kb;
+            sm.key[b] = ka;
+            const int pa = sm.pos[a];
+            sm.pos[a] = sm.pos[b];
+            sm.pos[b] = pa;
+          }
+        }
+        __syncwarp();
+      }
+    // ---- the points in that order (w = 1: the plain sums read it as their second factor)
+    for (int t = lane; t < n; t += 32) {
+      const float4 v = pts[sm.pos[t]];
+      sm.pts[t] = make_float4(v.x, v.y, v.z, 1.0f);
+    }
+    __syncwarp();
+    // ---- nine sequential float32 sums, one lane each
+    float acc = 0.0f;
+    if (lane < 9) {
+      const float *sp = reinterpret_cast<const float *>(sm.pts);
+      for (int j = 0; j < n; ++j) {
+        const float a = sp[4 * j + ia], b = sp[4 * j + ib];
+        acc += (lane < 6) ? a * b : a;
+      }
+      acc = acc / (float)n;
+    }
+    float accu[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) accu[a] = __shfl_sync(0xffffffffu, acc, a);
+    if (lane == 0) {
+      const Normal4 r = normal_from_accu(accu, c.x, c.y, c.z, vpx, vpy, vpz);
+      out[i] = make_float4(r.nx, r.ny, r.nz, r.curv);
+    }
+    __syncwarp();
+  }
+}
+
+template <int CAP>
+int launch_normals_radius_warp(b200_ctx *ctx, const GridView &g, const float4 *d_q, int nq, float radius, float r2,
+                               const int *d_counts, float vpx, float vpy, float vpz, float4 *out) {
+  const size_t smem = sizeof(NrwSmem<CAP>) * NRW_WARPS;
+  B200_CUDA(ctx, ensure_dyn_smem(normals_radius_warp_kernel<CAP>, smem));
+  const int grid = std::min(ceil_div(nq, NRW_WARPS), ctx->sm_count * 16);
+  normals_radius_warp_kernel<CAP><<<grid, NRW_WARPS * 32, smem, ctx->stream>>>(g, d_q, nq, radius, r2, d_counts, vpx, vpy, vpz,
+                                                                              out);
+  B200_LAUNCHED(ctx);
+  return B200_OK;
 }
 
 }  // namespace
@@ -283,15 +420,29 @@ int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_
   ctx->last_max_nbrs = max_count;
   ctx->last_mean_nbrs = (double)hstats[1] / nq;
   const float r2 = (float)(radius * radius);
+  StageScope st_(ctx, ST_NORMALS);
+  // neighbourhoods of up to 256 points: one query per warp (B200_NORMALS_RADIUS=cta: everything by the CTA kernel)
+  constexpr int WCAP = 256;
+  const char *sel = getenv("B200_NORMALS_RADIUS");
+  const bool warp_path = !(sel && !strcmp(sel, "cta"));
+  if (warp_path) {
+    if (max_count <= 64)
+      B200_TRY(launch_normals_radius_warp<64>(ctx, *g, d_q, nq, (float)radius, r2, counts.p, vpx, vpy, vpz, out));
+    else if (max_count <= 128)
+      B200_TRY(launch_normals_radius_warp<128>(ctx, *g, d_q, nq, (float)radius, r2, counts.p, vpx, vpy, vpz, out));
+    else
+      B200_TRY(launch_normals_radius_warp<WCAP>(ctx, *g, d_q, nq, (float)radius, r2, counts.p, vpx, vpy, vpz, out));
+    if (max_count <= WCAP) return B200_OK;
+  }
+  const int min_count = warp_path ? WCAP + 1 : 0;
   const int cap = next_pow2_host(std::max(max_count, 32));
   const size_t smem = (size_t)cap * 12;
-  StageScope st_(ctx, ST_NORMALS);
   if (smem <= 96 * 1024) {
     B200_CUDA(ctx,
               ensure_dyn_smem(normals_radius_kernel, smem));
     const int grid = std::min(nq, ctx->sm_count * 8);
     normals_radius_kernel<<<grid, 128, smem, ctx->stream>>>(*g, d_q, nq, (float)radius, r2, cap, nullptr, nullptr, vpx,
-                                                            vpy, vpz, out);
+                                                            vpy, vpz, out, counts.p, min_count);
     B200_LAUNCHED(ctx);
   } else {
     const int grid = std::min(nq, ctx->sm_count * 2);
@@ -300,7 +451,7 @@ int dev_normals(b200_ctx *ctx, b200_cloud *c, const float4 *d_q, int nq, bool q_
     B200_TRY(gk.alloc(ctx, (size_t)grid * cap));
     B200_TRY(gp.alloc(ctx, (size_t)grid * cap));
     normals_radius_kernel<<<grid, 128, 0, ctx->stream>>>(*g, d_q, nq, (float)radius, r2, cap, gk.p, gp.p, vpx, vpy,
-                                                         vpz, out);
+                                                         vpz, out, counts.p, min_count);
     B200_LAUNCHED(ctx);
   }
   return B200_OK;

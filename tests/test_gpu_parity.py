@@ -168,6 +168,37 @@ def test_normals_radius_and_nan(ctx, orc, synth):
         ctx.normals(cl2, k=0, radius=0.0)
 
 
+def test_normals_radius_warp_kernel_equals_cta_kernel(ctx, orc, synth):
+    """Radius normals: the one-query-per-warp kernel (neighbourhoods of up to 256 points; the three shared-memory
+    sizes 64 / 128 / 256 and the hand-over of larger neighbourhoods to the CTA kernel) gives the CTA kernel's
+    result bit for bit — both run PCL's nine sums in (d2, index) order — and both stand against the restatement."""
+    import os
+    scene = synth.make_scene(("y",), 60000, scene_id=4)
+    s = scene[:30000].copy()
+    s[11] = np.nan
+    kp = synth.voxel_grid(scene, 0.01)
+    cases = [(kp, 0.02, None), (kp, 0.05, None), (kp, 0.08, None), (s, 0.03, None), (s, 0.12, None), (s, 0.05, s[200:900])]
+    seen_max = []
+    for cloud_np, r, q in cases:
+        cl = ctx.cloud(cloud_np)
+        os.environ.pop("B200_NORMALS_RADIUS", None)
+        got = ctx.normals(cl, q=q, radius=r)
+        seen_max.append(ctx.neighbor_stats()[1])
+        os.environ["B200_NORMALS_RADIUS"] = "cta"
+        try:
+            ref = ctx.normals(cl, q=q, radius=r)
+        finally:
+            os.environ.pop("B200_NORMALS_RADIUS", None)
+        assert got.tobytes() == ref.tobytes(), (len(cloud_np), r)
+        cl.close()
+    print("largest neighbourhoods of the cases:", seen_max)
+    # the cases cross the size classes of the warp kernel and the hand-over to the CTA kernel
+    assert min(seen_max) <= 128 and any(128 < m <= 256 for m in seen_max) and max(seen_max) > 256, seen_max
+    cl = ctx.cloud(kp)
+    eps.normals_check(orc, ctx.normals(cl, radius=0.05), kp, radius=0.05, label="normals r=0.05 (warp kernel)")
+    cl.close()
+
+
 # ------------------------------------------------------------------------------------------ SHOT
 def _desc_check(got, ref, tol=1e-4):
     assert np.array_equal(np.isnan(got[:, 0]), np.isnan(ref[:, 0]))
