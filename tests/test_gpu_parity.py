@@ -278,6 +278,35 @@ def test_fpfh_parity(ctx, orc, synth, small):
         eps.fpfh_check(orc, got_q, kp, nrm, r, q=kp[::9], label="fpfh queries r=%g" % r)
 
 
+def test_fpfh_warp_kernels_equal_cta_kernels(ctx, orc, synth):
+    """FPFH: the one-point-per-warp kernels (neighbourhoods of up to 256 points, larger ones handed to the CTA kernels)
+    give the CTA kernels' descriptors bit for bit, with input == surface (rows written at the original index, a NaN row
+    for a point that is not in the grid) and with an explicit query set."""
+    import os
+    scene = synth.make_scene(("diagonal",), 50000, scene_id=6)
+    seen = []
+    for leaf, r in ((0.01, 0.03), (0.01, 0.06), (0.008, 0.13)):
+        kp = synth.voxel_grid(scene, leaf)[:20000].copy()
+        kp[5] = np.nan
+        nrm = orc.normals(kp, radius=r)
+        cl = ctx.cloud(kp)
+        res = {}
+        for mode in ("warp", "cta"):
+            if mode == "cta":
+                os.environ["B200_FPFH"] = "cta"
+            try:
+                res[mode] = (ctx.fpfh33(cl, nrm, r), ctx.fpfh33(cl, nrm, r, q=kp[3::7]))
+            finally:
+                os.environ.pop("B200_FPFH", None)
+        seen.append(ctx.neighbor_stats()[1])
+        assert np.all(np.isnan(res["warp"][0][5]))
+        assert res["warp"][0].tobytes() == res["cta"][0].tobytes(), (leaf, r)
+        assert res["warp"][1].tobytes() == res["cta"][1].tobytes(), (leaf, r)
+        cl.close()
+    print("largest neighbourhoods:", seen)
+    assert min(seen) <= 256 < max(seen), seen
+
+
 # ------------------------------------------------------------------------------------------ matching
 def test_match_bit_exact(ctx, orc):
     rng = _rng(11)
