@@ -326,6 +326,7 @@ struct AnnealArgs {
   float *weighted;    // ns, zero
   int *occupancy;     // n_cells, zero
   float *seq_sum;     // H scratch: add_to_explained of every hypothesis
+  float *compact;     // ns scratch: the weights of the explained points, in order
   const int *perms;   // n_iter x H: the move order of every iteration (std::random_shuffle, cumulative)
   const unsigned *mt; // n_iter x H raw mt19937 outputs
   int n_iter;         // iterations until the temperature falls to 1e-7
@@ -429,6 +430,31 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
     for (int k = tid; k < o.n; k += HV_SA_THREADS) cm += A.occupancy[o.idx[k]] > 1 ? 1 : 0;
   }
   hv_block_sum2(dup, cm, red, &s_a, &s_b);
+  // getTotalExplainedInformation adds weighted[i] over the explained points in ascending i: the few explained points
+  // (a few per cent of the scene) are first compacted in order by the whole block — every thread a contiguous chunk,
+  // counts scanned across the block — so that the sequential float32 sum only walks those
+  int n_compact = 0;
+  {
+    const int chunk = (A.ns + HV_SA_THREADS - 1) / HV_SA_THREADS;
+    const int lo = min(tid * chunk, A.ns), hi = min(lo + chunk, A.ns);
+    int c = 0;
+    for (int i = lo; i < hi; ++i) c += A.explained[i] > 0 ? 1 : 0;
+    int incl = c;  // inclusive scan over the block: warp scan, then the warp totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) red[tid >> 5] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += red[w];
+    for (int w = 0; w < HV_SA_THREADS / 32; ++w) n_compact += red[w];
+    int o = base + incl - c;
+    for (int i = lo; i < hi; ++i)
+      if (A.explained[i] > 0) A.compact[o++] = A.weighted[i];
+    __syncthreads();
+  }
   // sequential sums (warp 0)
   float good_information = 0.f;
   if (tid < 32) {
@@ -436,7 +462,7 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
       const float s = hv_seq_sum_warp(A.expl[h].w, nullptr, A.expl[h].n, 0.f);
       if (tid == 0) A.seq_sum[h] = s;
     }
-    good_information = hv_seq_sum_warp(A.weighted, A.explained, A.ns, 0.f);
+    good_information = hv_seq_sum_warp(A.compact, nullptr, n_compact, 0.f);
   }
   __syncthreads();
   // thread 0 carries PCL's running values
@@ -629,7 +655,7 @@ int run_anneal(b200_ctx *ctx, int H, int ns, const std::vector<HvExpl> &expl, co
   for (auto &x : mt) x = (unsigned)rng();
   DevBuf<HvExpl> d_expl;
   DevBuf<HvOcc> d_occ;
-  DevBuf<float> d_ow, d_weighted, d_seq;
+  DevBuf<float> d_ow, d_weighted, d_seq, d_compact;
   DevBuf<int> d_bad, d_explained, d_occupancy, d_perms, d_acc;
   DevBuf<unsigned> d_mt;
   DevBuf<unsigned char> d_active, d_best;
@@ -644,6 +670,7 @@ int run_anneal(b200_ctx *ctx, int H, int ns, const std::vector<HvExpl> &expl, co
   B200_TRY(d_explained.alloc(ctx, (size_t)std::max(ns, 1)));
   B200_TRY(d_occupancy.alloc(ctx, (size_t)std::max(n_cells, 1)));
   B200_TRY(d_seq.alloc(ctx, (size_t)H));
+  B200_TRY(d_compact.alloc(ctx, (size_t)std::max(ns, 1)));
   B200_TRY(d_active.alloc(ctx, (size_t)H));
   B200_TRY(d_best.alloc(ctx, (size_t)H));
   B200_TRY(d_cost.alloc(ctx, 1));
@@ -654,7 +681,7 @@ int run_anneal(b200_ctx *ctx, int H, int ns, const std::vector<HvExpl> &expl, co
   AnnealArgs A;
   A.H = H, A.ns = ns, A.expl = d_expl.p, A.occ = d_occ.p, A.outliers_weight = d_ow.p, A.bad_information = d_bad.p;
   A.w_cm = P.w_occupied_multiple_cm, A.explained = d_explained.p, A.weighted = d_weighted.p, A.occupancy = d_occupancy.p;
-  A.seq_sum = d_seq.p, A.perms = d_perms.p, A.mt = d_mt.p, A.n_iter = n_iter, A.max_iterations = P.max_iterations;
+  A.seq_sum = d_seq.p, A.compact = d_compact.p, A.perms = d_perms.p, A.mt = d_mt.p, A.n_iter = n_iter, A.max_iterations = P.max_iterations;
   A.initial_temp = (double)P.initial_temp, A.uniform_mode = P.sa_uniform_mode, A.active = d_active.p, A.best = d_best.p;
   A.out_cost = d_cost.p, A.out_accepted = d_acc.p;
   hv_anneal_kernel<<<1, HV_SA_THREADS, 0, ctx->stream>>>(A);
