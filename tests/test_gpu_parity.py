@@ -853,6 +853,39 @@ def test_board_lrf_parity(ctx, orc, synth, small, b200):
     cs.close()
 
 
+def test_board_warp_kernel_equals_cta_kernel(ctx, orc, synth, b200):
+    """BOARD frames: the one-keypoint-per-warp kernel (supports of up to 512 points, larger ones handed to the CTA
+    kernel) against the CTA kernel on the same rand() stream.  Both run the same float32 sequence after the z axis; the
+    float64 plane-fit sums are grouped differently (32 partials instead of 128), so a frame may differ in the last
+    bits: 1e-6 is the bar, and nearly every frame is identical."""
+    import os
+    scene = synth.make_scene(("y",), 120000, scene_id=9)
+    kp = synth.uniform_sampling(scene, 0.03)
+    nrm = orc.normals(scene, k=10)
+    cl = ctx.cloud(scene)
+    seen = []
+    for r, kw in ((0.01, {}), (0.02, {}), (0.07, {}), (0.02, dict(find_holes=False)), (0.02, dict(check_margin_array_size=40))):
+        res = {}
+        for mode in ("warp", "cta"):
+            ctx.srand(5)
+            if mode == "cta":
+                os.environ["B200_BOARD"] = "cta"
+            try:
+                res[mode] = ctx.board_lrf(cl, nrm, kp, r, b200.board_params(**kw))
+            finally:
+                os.environ.pop("B200_BOARD", None)
+        off = ctx.radius_search(cl, kp, r)[0]
+        seen.append(int(np.diff(off).max()))
+        a, b = res["warp"], res["cta"]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        ok = ~np.isnan(b[:, 0])
+        same = (a[ok] == b[ok]).all(axis=1).mean()
+        assert np.abs(a[ok] - b[ok]).max() < 1e-6 and same > 0.999, (r, kw, float(np.abs(a[ok] - b[ok]).max()), same)
+    print("largest supports:", seen)
+    assert min(seen) <= 512 < max(seen), seen
+    cl.close()
+
+
 # ------------------------------------------------------------------------------------------ library file
 def test_library_file_roundtrip(ctx, orc, synth, b200, tmp_path):
     """The binary descriptor library (replaces the reference's Partial_View<l>.txt dumps, CAD_desc.cpp:354-370): save →
