@@ -1,5 +1,8 @@
 // search.cu — batched neighbour-search kernels behind b200_knn_search / b200_radius_search
 // (KdTreeFLANN::nearestKSearch SHOT.cpp:163, Edge_detection.cpp:120; ::radiusSearch SHOT_VAR.cpp:356).
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 #include "search.cuh"
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(128) radius_fill_kernel(GridView g, const floa
                                                           float radius, float r2, int cap,
                                                           unsigned long long *glob_key, int *glob_pos,
                                                           const long long *__restrict__ offsets,
-                                                          int *__restrict__ idx, float *__restrict__ d2) {
+                                                          int *__restrict__ idx, float *__restrict__ d2, int min_count) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_count;
   unsigned long long *key;
@@ -60,6 +63,7 @@ __global__ void __launch_bounds__(128) radius_fill_kernel(GridView g, const floa
     pos = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(unsigned long long));
   }
   for (int i = blockIdx.x; i < nq; i += gridDim.x) {
+    if (offsets[i + 1] - offsets[i] < (long long)min_count) continue;  // shorter lists: radius_fill_warp_kernel
     const float4 p = q[i];
     int n = gather_radius(g, p.x, p.y, p.z, radius, r2, key, pos, cap, &s_count);
     if (n > cap) n = cap;  // cannot happen: cap >= max count (host sized it)
@@ -70,6 +74,80 @@ __global__ void __launch_bounds__(128) radius_fill_kernel(GridView g, const floa
       d2[o + j] = key_d2(key[j]);
     }
     __syncthreads();
+  }
+}
+
+// one query per warp for lists of up to RFW_CAP neighbours: ballot-compacted gather of the (d2, index) keys into the
+// warp's slice of shared memory, bitonic sort synchronised by __syncwarp only, coalesced write of the CSR segment
+constexpr int RFW_CAP = 512;
+constexpr int RFW_WARPS = 8;
+__global__ void __launch_bounds__(RFW_WARPS * 32)
+    radius_fill_warp_kernel(GridView g, const float4 *__restrict__ q, int nq, float radius, float r2,
+                            const long long *__restrict__ offsets, int *__restrict__ idx, float *__restrict__ d2) {
+  __shared__ unsigned long long s_key[RFW_WARPS][RFW_CAP];
+  unsigned long long *key = s_key[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * RFW_WARPS;
+  const float4 *__restrict__ pts = g.pts;
+  const int *__restrict__ cs = g.cell_start;
+  for (int i = blockIdx.x * RFW_WARPS + (threadIdx.x >> 5); i < nq; i += nwarps) {
+    const long long o = offsets[i];
+    const long long cnt = offsets[i + 1] - o;
+    if (cnt == 0 || cnt > RFW_CAP) continue;
+    const float4 c = q[i];
+    int n = 0;
+    int x0, x1, y0, y1, z0, z1;
+    if (ball_cell_range(g, c.x, c.y, c.z, radius, x0, x1, y0, y1, z0, z1)) {
+      for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+          const int base = g.dx * (y + g.dy * z);
+          const int s0 = cs[base + x0], e = cs[base + x1 + 1];
+          for (int j0 = s0; j0 < e; j0 += 128) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j0 + 32 * u + lane;
+              p[u] = (j < e) ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j0 + 32 * u + lane;
+              const float dd = sqdist3(c.x, c.y, c.z, p[u].x, p[u].y, p[u].z);
+              const bool hit = j < e && dd < r2;
+              const unsigned m = __ballot_sync(0xffffffffu, hit);
+              if (hit) {
+                const int slot = n + __popc(m & ((1u << lane) - 1u));
+                if (slot < RFW_CAP) key[slot] = nbr_key(dd, orig_index(p[u]));
+              }
+              n += __popc(m);
+            }
+          }
+        }
+    }
+    if (n > RFW_CAP) n = RFW_CAP;  // cannot happen: the count pass ran the same test
+    int np = 32;
+    while (np < n) np <<= 1;
+    for (int t = n + lane; t < np; t += 32) key[t] = ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= np; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (np >> 1); t += 32) {
+          const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int b = a | j;
+          const bool up = ((a & k) == 0);
+          const unsigned long long ka = key[a], kb = key[b];
+          if ((ka > kb) == up) {
+            key[a] = kb;
+            key[b] = ka;
+          }
+        }
+        __syncwarp();
+      }
+    for (int j = lane; j < n; j += 32) {
+      idx[o + j] = key_orig(key[j]);
+      d2[o + j] = key_d2(key[j]);
+    }
+    __syncwarp();
   }
 }
 
@@ -123,13 +201,23 @@ int dev_radius_fill_sized(b200_ctx *ctx, const GridView &g, const float4 *d_q, i
                           const long long *d_offsets, int *d_idx, float *d_d2) {
   if (nq <= 0 || max_count <= 0) return B200_OK;
   const float r2 = (float)(radius * radius);
+  // lists of up to RFW_CAP neighbours: one query per warp (B200_RADIUS_FILL=cta: everything by the CTA kernel)
+  const char *sel = getenv("B200_RADIUS_FILL");
+  const bool warp_path = !(sel && !strcmp(sel, "cta"));
+  if (warp_path) {
+    radius_fill_warp_kernel<<<std::min(ceil_div(nq, RFW_WARPS), ctx->sm_count * 16), RFW_WARPS * 32, 0, ctx->stream>>>(
+        g, d_q, nq, (float)radius, r2, d_offsets, d_idx, d_d2);
+    B200_LAUNCHED(ctx);
+    if (max_count <= RFW_CAP) return B200_OK;
+  }
+  const int min_count = warp_path ? RFW_CAP + 1 : 0;
   const int cap = next_pow2_host(std::max(max_count, 32));
   const size_t smem = (size_t)cap * 12;
   const int grid = std::min(nq, ctx->sm_count * 8);
   if (smem <= 96 * 1024) {
     B200_CUDA(ctx, ensure_dyn_smem(radius_fill_kernel, smem));
     radius_fill_kernel<<<grid, 128, smem, ctx->stream>>>(g, d_q, nq, (float)radius, r2, cap, nullptr, nullptr,
-                                                         d_offsets, d_idx, d_d2);
+                                                         d_offsets, d_idx, d_d2, min_count);
     B200_LAUNCHED(ctx);
   } else {
     const int g2 = std::min(nq, ctx->sm_count * 2);
@@ -138,7 +226,7 @@ int dev_radius_fill_sized(b200_ctx *ctx, const GridView &g, const float4 *d_q, i
     B200_TRY(gk.alloc(ctx, (size_t)g2 * cap));
     B200_TRY(gp.alloc(ctx, (size_t)g2 * cap));
     radius_fill_kernel<<<g2, 128, 0, ctx->stream>>>(g, d_q, nq, (float)radius, r2, cap, gk.p, gp.p, d_offsets, d_idx,
-                                                    d_d2);
+                                                    d_d2, min_count);
     B200_LAUNCHED(ctx);
   }
   return B200_OK;

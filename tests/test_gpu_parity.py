@@ -100,6 +100,29 @@ def test_knn_clamps(ctx, orc):
     assert np.array_equal(idx, oidx) and np.array_equal(d2, od2)
 
 
+def test_radius_search_warp_kernel_equals_cta_kernel(ctx, synth):
+    """radiusSearch lists: the one-query-per-warp fill kernel (up to 512 neighbours, longer lists handed to the CTA
+    kernel) writes the same CSR — indices and squared distances — as the CTA kernel."""
+    import os
+    scene = synth.make_scene(("y",), 80000, scene_id=12)
+    q = scene[::13].copy()
+    q[3] = np.nan
+    cl = ctx.cloud(scene)
+    sizes = []
+    for r in (0.01, 0.03, 0.08):
+        a = ctx.radius_search(cl, q, r)
+        os.environ["B200_RADIUS_FILL"] = "cta"
+        try:
+            b = ctx.radius_search(cl, q, r)
+        finally:
+            os.environ.pop("B200_RADIUS_FILL", None)
+        for x, y in zip(a, b):
+            assert x.tobytes() == y.tobytes(), r
+        sizes.append(int(np.diff(a[0]).max()))
+    assert min(sizes) <= 512 < max(sizes), sizes
+    cl.close()
+
+
 # ------------------------------------------------------------------------------------------ normals
 @pytest.mark.parametrize("k", [10, 20, 50])
 def test_normals_knn_parity(ctx, orc, small, k):
