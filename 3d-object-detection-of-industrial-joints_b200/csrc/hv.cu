@@ -405,10 +405,20 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
   __shared__ int red[2 * (HV_SA_THREADS / 32)];
   __shared__ int s_d0[HV_MAX_HYPOTHESES], s_d1[HV_MAX_HYPOTHESES];
   __shared__ int s_a, s_b, s_ctl, s_stop;
+  // per-hypothesis scalars, the current iteration's move order and the mask live in shared memory: thread 0's replay
+  // of an iteration is a chain of dependent reads, which through global memory cost more than its arithmetic
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int H = A.H;
+  float *s_seq = reinterpret_cast<float *>(s_dyn);  // add_to_explained of every hypothesis
+  float *s_obad = s_seq + H;                         // outliers_weight_ * bad_information_
+  int *s_perm = reinterpret_cast<int *>(s_obad + H);
+  unsigned char *s_act = reinterpret_cast<unsigned char *>(s_perm + H);
   // ---- initial state: every hypothesis active
-  for (int h = tid; h < H; h += HV_SA_THREADS) A.active[h] = 1, A.best[h] = 1;
+  for (int h = tid; h < H; h += HV_SA_THREADS) {
+    s_act[h] = 1, A.best[h] = 1;
+    s_obad[h] = A.outliers_weight[h] * (float)A.bad_information[h];
+  }
   for (int h = 0; h < H; ++h) {
     const HvExpl e = A.expl[h];
     for (int k = tid; k < e.n; k += HV_SA_THREADS) {
@@ -460,7 +470,7 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
   if (tid < 32) {
     for (int h = 0; h < H; ++h) {
       const float s = hv_seq_sum_warp(A.expl[h].w, nullptr, A.expl[h].n, 0.f);
-      if (tid == 0) A.seq_sum[h] = s;
+      if (tid == 0) s_seq[h] = s;
     }
     good_information = hv_seq_sum_warp(A.compact, nullptr, n_compact, 0.f);
   }
@@ -475,7 +485,7 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
     previous_explained = good_information;
     previous_dup = s_a;
     previous_cm = s_b;
-    for (int h = 0; h < H; ++h) previous_bad += A.outliers_weight[h] * (float)A.bad_information[h];
+    for (int h = 0; h < H; ++h) previous_bad += s_obad[h];
     cost = (double)((previous_explained - previous_bad - (float)previous_dup - (float)previous_cm * A.w_cm - (float)H -
                      previous_unexplained) *
                     -1.f);
@@ -485,10 +495,10 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
   auto scalar_flip = [&](int m, int sgn, int d0, int d1) {
     const float sign = (float)sgn;
     n_active += sgn;
-    previous_explained += A.seq_sum[m] * sign;
+    previous_explained += s_seq[m] * sign;
     previous_dup += d0;
     previous_cm += d1;
-    const float bad_info = previous_bad + (A.outliers_weight[m] * (float)A.bad_information[m]) * sign;
+    const float bad_info = previous_bad + s_obad[m] * sign;
     previous_bad = bad_info;
     const float duplicity_cm = (float)previous_cm * A.w_cm;
     cost = (double)((previous_explained - bad_info - (float)previous_dup - previous_unexplained - duplicity_cm -
@@ -508,6 +518,7 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
       if (!(temp > 1e-7)) stop = 1;
       s_stop = stop;
     }
+    for (int h = tid; h < H; h += HV_SA_THREADS) s_perm[h] = A.perms[(size_t)it * H + h];
     __syncthreads();  // also orders the previous iteration's count writes before the reads below
     if (s_stop) break;
     // ---- phase A (only after the counts changed): duplicity changes of every move against the current counts; the
@@ -516,7 +527,7 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
       for (int h = tid; h < H; h += HV_SA_THREADS) s_d0[h] = 0, s_d1[h] = 0;
       __syncthreads();
       for (int m = 0; m < H; ++m) {
-        const int sgn = A.active[m] ? -1 : 1;
+        const int sgn = s_act[m] ? -1 : 1;
         int d0 = 0, d1 = 0;
         const HvExpl e = A.expl[m];
         for (int k = tid; k < e.n; k += HV_SA_THREADS) {
@@ -542,19 +553,24 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
       const double actual_cost = cost;
       int taken = -1;
       for (int mi = 0; mi < H; ++mi) {
-        const int m = A.perms[(size_t)it * H + mi];
-        const int sgn = A.active[m] ? -1 : 1;
+        const int m = s_perm[mi];
+        const int sgn = s_act[m] ? -1 : 1;
         scalar_flip(m, sgn, s_d0[m], s_d1[m]);  // apply_and_evaluate
         const double delta = cost - actual_cost;
         bool take = delta < 0;
         if (!take) {
           const unsigned x = A.mt[mt_pos++];
-          const double u = A.uniform_mode == 1 ? (double)x : (double)x / 4294967296.0;
-          take = u < exp(2.0 * -delta / temp);
+          // u < exp(-2 delta / T).  Every non-zero variate is at least 2^-32 = 2.3e-10 > exp(-22): when the exponent
+          // is below -25 (most evaluations once the temperature has fallen) the outcome is "rejected" without the
+          // float64 division and exponential, which were most of an iteration's serial time
+          if (x == 0u || !(2.0 * delta > 25.0 * temp)) {
+            const double u = A.uniform_mode == 1 ? (double)x : (double)x / 4294967296.0;
+            take = u < exp(2.0 * -delta / temp);
+          }
         }
         if (take) {
           accepted++;
-          A.active[m] = sgn > 0 ? 1 : 0;
+          s_act[m] = sgn > 0 ? 1 : 0;
           taken = m;
           if (cost < best_cost) {
             best_cost = cost;
@@ -572,13 +588,13 @@ __global__ void __launch_bounds__(HV_SA_THREADS) hv_anneal_kernel(AnnealArgs A) 
     const int ctl = s_ctl;
     if (ctl >= 0) {
       const int m = ctl & 0x3fffffff;
-      const int sgn = A.active[m] ? 1 : -1;  // the state after the flip
+      const int sgn = s_act[m] ? 1 : -1;  // the state after the flip
       const HvExpl e = A.expl[m];
       for (int k = tid; k < e.n; k += HV_SA_THREADS) A.explained[e.idx[k]] += sgn;
       const HvOcc o = A.occ[m];
       for (int k = tid; k < o.n; k += HV_SA_THREADS) A.occupancy[o.idx[k]] += sgn;
       if (ctl & 0x40000000)
-        for (int h = tid; h < H; h += HV_SA_THREADS) A.best[h] = A.active[h];
+        for (int h = tid; h < H; h += HV_SA_THREADS) A.best[h] = s_act[h];
     }
     dirty = ctl >= 0;
   }
@@ -684,7 +700,9 @@ int run_anneal(b200_ctx *ctx, int H, int ns, const std::vector<HvExpl> &expl, co
   A.seq_sum = d_seq.p, A.compact = d_compact.p, A.perms = d_perms.p, A.mt = d_mt.p, A.n_iter = n_iter, A.max_iterations = P.max_iterations;
   A.initial_temp = (double)P.initial_temp, A.uniform_mode = P.sa_uniform_mode, A.active = d_active.p, A.best = d_best.p;
   A.out_cost = d_cost.p, A.out_accepted = d_acc.p;
-  hv_anneal_kernel<<<1, HV_SA_THREADS, 0, ctx->stream>>>(A);
+  const size_t dyn = (size_t)H * 13 + 16;
+  B200_CUDA(ctx, ensure_dyn_smem(hv_anneal_kernel, dyn));
+  hv_anneal_kernel<<<1, HV_SA_THREADS, dyn, ctx->stream>>>(A);
   B200_LAUNCHED(ctx);
   B200_TRY(hv_download(ctx, mask, d_best.p, (size_t)H));
   double c;
