@@ -728,6 +728,12 @@ def run_other_configs(ctx, binding, pkg, args):
                     % (n_desc, len(kps4)),
         "library_build_s_incl_host_synthesis": t_build, "registrations_per_s": 1.0 / t_gpu4,
         "ms_per_scene_e2e": t_gpu4 * 1e3, "view_matches_per_s": 192.0 / t_gpu4, "instances": int(res4["n_instances"])}
+    # ---- the reference's DEFAULT grouping branch on config 1's clouds and correspondences (SHOT.cpp:433-470): BOARD
+    # frames (find_holes, rf_rad 0.02) for the model and the scene keypoints, then Hough3DGrouping
+    try:
+        out["config1_hough_branch"] = run_hough_config(ctx, binding, orc, model, scene, kpm, kps, res["corrs"])
+    except Exception as e:
+        out["config1_hough_branch"] = {"error": repr(e)}
     # ---- the last gate of the reference's callback: GlobalHypothesesVerification on the registered instances
     # (SHOT_hypothesis.cpp:631-653), host buffers in, mask out, in the reference's call order
     try:
@@ -735,6 +741,36 @@ def run_other_configs(ctx, binding, pkg, args):
     except Exception as e:  # an extra record must not cost the headline line
         out["hypothesis_verification"] = {"error": repr(e)}
     return out
+
+
+def run_hough_config(ctx, binding, orc, model, scene, kpm, kps, corrs):
+    cm, cs = ctx.cloud(model), ctx.cloud(scene)
+    nm, ns = ctx.normals(cm, k=10), ctx.normals(cs, k=10)
+
+    def gpu():
+        ctx.srand(1)
+        rf_m = ctx.board_lrf(cm, nm, kpm, 0.02)
+        rf_s = ctx.board_lrf(cs, ns, kps, 0.02)
+        T, inst, n = ctx.hough3d_recognize(kpm, rf_m, kps, rf_s, corrs, 0.03, 3.0, max_inst=1024)
+        return rf_m, rf_s, n
+    t_gpu, (rf_m, rf_s, n_gpu) = _timeit(gpu, ctx.sync, 5)
+    cm.close()
+    cs.close()
+
+    def cpu():
+        o_m, used = orc.board_lrf(model, nm, kpm, 0.02)
+        o_s, _ = orc.board_lrf(scene, ns, kps, 0.02, rand_skip=used)
+        T, inst = orc.hough3d_recognize(kpm, o_m, kps, o_s, corrs, 0.03, 3.0, max_inst=1024)
+        return o_m, o_s, len(T)
+    t_cpu, (o_m, o_s, n_cpu) = _timeit(cpu, lambda: None, 1, warm=0)
+    ok = ~np.isnan(o_s[:, 0]) & ~np.isnan(rf_s[:, 0])
+    return {"workload": "BOARD frames (find_holes, r = 0.02) of %d model + %d scene keypoints on config 1's clouds, "
+                        "Hough3DGrouping (bin 0.03, threshold 3) on its %d correspondences; normals given"
+                        % (len(kpm), len(kps), len(corrs)),
+            "api": "b200_board_lrf x 2 + b200_hough3d_recognize (host buffers)",
+            "ms_e2e": t_gpu * 1e3, "cpu": {"ms": t_cpu * 1e3, "cores": orc.num_threads(), "kind": "port", "measured": True},
+            "instances": int(n_gpu), "cpu_instances": int(n_cpu),
+            "scene_frames_within_1e-5_of_cpu": float((np.abs(rf_s[ok] - o_s[ok]).max(axis=1) < 1e-5).mean())}
 
 
 def run_hv_config(ctx, binding, synth, orc):
