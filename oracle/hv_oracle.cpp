@@ -437,6 +437,11 @@ int orc_hv_verify(const float *scene, int n, int sstride, const float *models, c
           min_d = kv.second[i].second;
           closest = i;
         }
+      if (orc_get_variant() & 2048u) { /* sensitivity variant: the model point that IS closest (what the comment in PCL says) */
+        closest = 0;
+        for (size_t i = 1; i < kv.second.size(); ++i)
+          if (kv.second[i].second < kv.second[closest].second) closest = i;
+      }
       const float d = kv.second[closest].second;
       const float d_weight = -(d * d / (P->inlier_threshold)) + 1;
       const float *sn = &SN[(size_t)kv.first * 3];

@@ -34,7 +34,9 @@ typedef struct {
 
 /* Sensitivity variants (bit mask, 0 = the documented restatement): 1 Eigen 4-lane dot order, 2 float32 Umeyama
  * moments, 4 degenerate FPFH pairs skipped, 8 / 16 FPFH f1 bin coordinate +- 1e-6, 32 / 64 eigen33 theta +- 2 ulp,
- * 128 / 256 SHOT cosine-bin coordinate +- 1e-6, 512 / 1024 BOARD direction angle +- 2 ulp.  See oracle/sensitivity.py. */
+ * 128 / 256 SHOT cosine-bin coordinate +- 1e-6, 512 / 1024 BOARD direction angle +- 2 ulp, 2048 hypothesis verification:
+ * the explaining model point of a scene point is the closest one (hv_oracle.cpp).  See oracle/sensitivity.py and
+ * oracle/sensitivity_hv.py. */
 void orc_set_variant(unsigned mask);
 unsigned orc_get_variant(void);
 int orc_num_threads(void);

@@ -146,7 +146,8 @@ def set_num_threads(n):
 
 
 VARIANTS = {"dot4": 1, "umeyama_f32": 2, "fpfh_skip": 4, "fpfh_bin_up": 8, "fpfh_bin_down": 16, "root_up": 32,
-            "root_down": 64, "shot_bin_up": 128, "shot_bin_down": 256, "board_angle_up": 512, "board_angle_down": 1024}
+            "root_down": 64, "shot_bin_up": 128, "shot_bin_down": 256, "board_angle_up": 512, "board_angle_down": 1024,
+            "hv_closest": 2048}
 
 
 def set_variant(*names):
