@@ -107,3 +107,71 @@ def test_verify_edge_cases(orc, synth):
     far = scene + np.float32(50.0)
     rf = orc.hv_verify(far, hyps[:2], p)
     assert (rf["info"]["n_explained"] == 0).all() and not rf["mask"].any()
+
+
+def test_cues_against_an_independent_numpy_restatement(orc, synth):
+    """The cue stage of the restatement (z-buffer visibility, voxel grids, explained points, outliers, occupancy cells)
+    recomputed with numpy / scipy from the same description of PCL's code, written separately: visibility counts and
+    occupancy counts exactly, explained / outlier counts up to the handful of pairs whose distance sits on the inlier
+    radius (cKDTree's ball query is <=, FLANN's is <) or whose voxel centroid differs in the last bit."""
+    from scipy.spatial import cKDTree
+    scene, hyps, _ = hv_cases.kinect(synth, 150000)
+    hyps = [h[::2] for h in hyps[:5]]
+    p = orc.hv_params(detect_clutter=0, occlusion_reasoning=1, regularizer=3.0, radius_normals=0.03)
+    r = orc.hv_verify(scene, hyps, p)
+    f32 = np.float32
+
+    def zbuffer(cloud, res):
+        c = f32(res) / f32(2) - f32(0.5)
+        bx, by = cloud[:, 0] / cloud[:, 2], cloud[:, 1] / cloud[:, 2]
+        maxc = max(abs(bx.max()), abs(by.max()), abs(bx.min()), abs(by.min()))
+        f = f32(c / maxc)
+
+        def pix(pts):
+            u = (f * pts[:, 0] / pts[:, 2] + c).astype(np.float32)
+            v = (f * pts[:, 1] / pts[:, 2] + c).astype(np.float32)
+            ui, vi = np.trunc(u).astype(np.int64), np.trunc(v).astype(np.int64)
+            ok = (ui >= 0) & (vi >= 0) & (ui < res) & (vi < res)
+            return ui, vi, ok
+        ui, vi, ok = pix(cloud)
+        depth = np.full((res, res), np.inf, np.float32)
+        np.minimum.at(depth, (vi[ok], ui[ok]), cloud[ok, 2])
+
+        def keeps(pts, thr):
+            ui, vi, ok = pix(pts)
+            d = np.full(len(pts), np.inf, np.float32)
+            d[ok] = depth[vi[ok], ui[ok]]
+            return ok & np.isfinite(d) & ~((pts[:, 2] - f32(thr)) > d)
+        return keeps
+
+    def voxel(cloud, leaf):
+        ijk = np.floor(cloud / f32(leaf)).astype(np.int64)
+        ijk -= ijk.min(0)
+        key = (ijk[:, 2] * (ijk[:, 1].max() + 1) + ijk[:, 1]) * (ijk[:, 0].max() + 1) + ijk[:, 0]
+        order = np.argsort(key, kind="stable")
+        uk, start = np.unique(key[order], return_index=True)
+        sums = np.add.reduceat(cloud[order].astype(np.float64), start)
+        cnt = np.diff(np.append(start, len(cloud)))[:, None]
+        return (sums / cnt).astype(np.float32)
+
+    def with_normals(cloud, radius):
+        t = cKDTree(cloud.astype(np.float64))
+        n = np.array([len(x) for x in t.query_ball_point(cloud.astype(np.float64), radius * (1 - 1e-7))])
+        return cloud[n >= 3]   # fewer than three neighbours: NaN normal, dropped
+
+    scene_keeps = zbuffer(scene, 100)
+    S = with_normals(voxel(scene, 0.005), 0.03)
+    assert abs(len(S) - r["n_scene_points"]) <= 2
+    tree = cKDTree(S.astype(np.float64))
+    lo = np.min([h.min(0) for h in hyps], axis=0)
+    for h, info in zip(hyps, r["info"]):
+        vis = h[zbuffer(h, 75)(h, 0.005) & scene_keeps(h, 0.005)]
+        assert len(vis) == info["n_visible"]
+        M = with_normals(voxel(vis, 0.005), 0.03) if len(vis) else vis
+        assert abs(len(M) - info["n_points"]) <= 2
+        nb = tree.query_ball_point(M.astype(np.float64), 0.005 * (1 - 1e-7)) if len(M) else []
+        outliers = sum(1 for x in nb if len(x) == 0)
+        explained = len(set(j for x in nb for j in x))
+        assert abs(outliers - info["n_outliers"]) <= 3 and abs(explained - info["n_explained"]) <= 3
+        cells = np.floor((h - lo.astype(np.float32)) / f32(0.01)).astype(np.int64)
+        assert len(np.unique(cells, axis=0)) == info["n_occupancy"]
