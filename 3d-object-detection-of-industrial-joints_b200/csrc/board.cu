@@ -23,7 +23,8 @@
 // analysis.  All float32 expressions keep PCL's operation order (--fmad=false).
 // Measured (91 076 keypoints on the 1 M-point scene, r = 0.02, 279 support points on average, up to 1 874; host
 // buffers in and out): 13.9 ms with one CTA per keypoint and one thread per sector walking the support; 8.0 ms with
-// the reductions; 6.5 ms with the warp kernel for the supports it takes.
+// the reductions; 6.5 ms with the warp kernel for the supports it takes; 5.2 ms once the warp kernel's reductions
+// break ties by the (d2, index) key themselves (BoardScan2) and its support is no longer sorted.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -459,19 +460,29 @@ __global__ void __launch_bounds__(BOARD_THREADS)
 
 // ---- one keypoint per WARP (supports of up to BW_CAP points, one search radius; the rest stays with board_kernel) ----
 // Same steps as board_kernel with the warp in the CTA's place: ballot-compacted gather into the warp's slice of shared
-// memory, bitonic sort synchronised by __syncwarp only, float64 sums by lane partials + shuffles, the sector table
-// replayed by one lane per sector (a second sector per lane above 32), the hole analysis by lane 0.  The CTA kernel
+// memory (left in gather order: no sort), float64 sums by lane partials + shuffles, the sector table and the most
+// different normal by two-stage reductions (BoardScan2), the hole analysis by lane 0.  The CTA kernel
 // keeps 128 threads on a keypoint through ~50 block-wide barriers and three single-thread phases; here the SM's other
 // warps work on their own keypoints meanwhile.  The float64 sums are grouped differently (32 partials instead of
 // 128), so they can differ from the CTA kernel's in the last bit; everything after the float32 cast of the z axis is
 // the same float32 sequence.
 constexpr int BW_CAP = 512;
 constexpr int BW_WARPS = 4;
+// Two-stage form of BoardScan for an UNSORTED support: the extreme value first (32-bit atomics), then — among the
+// points that reach it — the smallest (d2, index) key, which is the point PCL's scan over the sorted support meets
+// first.  The warp kernel therefore needs no sort at all (it was 45 of its stages for a 512-point support).
+struct BoardScan2 {
+  unsigned mnv[BOARD_MAX_SECTORS], mxv[BOARD_MAX_SECTORS];            // angle bits: smallest / largest per sector
+  unsigned long long mnk[BOARD_MAX_SECTORS], mxk[BOARD_MAX_SECTORS];  // first point (key) reaching them
+  unsigned cosv[2];                                                   // ordered cosine: margin points / the others
+  unsigned long long cosk[2];
+  int found;
+};
 struct BwSmem {
   unsigned long long key[BW_CAP];
   int pos[BW_CAP];
-  float f_cos[BW_CAP];
-  BoardScan scan;
+  float f_cos[BW_CAP], f_ang[BW_CAP];
+  BoardScan2 scan;
   int check[BOARD_MAX_SECTORS];
   float min_angle[BOARD_MAX_SECTORS], max_angle[BOARD_MAX_SECTORS], min_angle_normal[BOARD_MAX_SECTORS],
       max_angle_normal[BOARD_MAX_SECTORS];
@@ -484,8 +495,8 @@ __global__ void __launch_bounds__(BW_WARPS * 32)
     board_warp_kernel(GridView g, const float *__restrict__ normals, const float4 *__restrict__ kp, int K, float radius_f,
                       float r2, BoardArgs a, const int *__restrict__ counts, const int *__restrict__ rand_rank,
                       const int *__restrict__ rand_values, float *__restrict__ rf_out) {
-  __shared__ BwSmem s_all[BW_WARPS];
-  BwSmem &sm = s_all[threadIdx.x >> 5];
+  extern __shared__ __align__(16) unsigned char bw_raw[];
+  BwSmem &sm = reinterpret_cast<BwSmem *>(bw_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * BW_WARPS;
   const float4 *__restrict__ pts = g.pts;
@@ -540,31 +551,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32)
       }
     }
     if (n > BW_CAP) n = BW_CAP;  // cannot happen
-    // ---- (d2, index) order: the order PCL iterates the support in
-    int np = 32;
-    while (np < n) np <<= 1;
-    for (int t = n + lane; t < np; t += 32) {
-      sm.key[t] = ~0ull;
-      sm.pos[t] = -1;
-    }
-    __syncwarp();
-    for (int k = 2; k <= np; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = lane; t < (np >> 1); t += 32) {
-          const int ia = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-          const int ib = ia | j;
-          const bool up = ((ia & k) == 0);
-          const unsigned long long ka = sm.key[ia], kb = sm.key[ib];
-          if ((ka > kb) == up) {
-            sm.key[ia] = kb;
-            sm.key[ib] = ka;
-            const int pa = sm.pos[ia];
-            sm.pos[ia] = sm.pos[ib];
-            sm.pos[ib] = pa;
-          }
-        }
-        __syncwarp();
-      }
+    __syncwarp();  // the support stays in gather order: nothing below depends on the order (BoardScan2)
     // ---- planeFitting: float64 centroid and scatter
     double m[3] = {0.0, 0.0, 0.0}, nm[3] = {0.0, 0.0, 0.0};
     for (int t = lane; t < n; t += 32) {
@@ -604,31 +591,86 @@ __global__ void __launch_bounds__(BW_WARPS * 32)
     const float xr[3] = {sm.x[0], sm.x[1], sm.x[2]};
     // ---- per support point: cosine of its normal with z, direction angle from the random axis; sector table and
     // most different normal as order-independent reductions (BoardScan)
-    board_scan_init(sm.scan, lane, 32);
-    board_scan_init(sm.scan, lane + 32, BOARD_MAX_SECTORS);
+    for (int sct = lane; sct < BOARD_MAX_SECTORS; sct += 32) {
+      sm.scan.mnv[sct] = 0xffffffffu;
+      sm.scan.mxv[sct] = 0u;
+      sm.scan.mnk[sct] = ~0ull;
+      sm.scan.mxk[sct] = ~0ull;
+      sm.min_angle_normal[sct] = -1.0f;
+      sm.max_angle_normal[sct] = -1.0f;
+    }
+    if (lane < 2) {
+      sm.scan.cosv[lane] = 0xffffffffu;
+      sm.scan.cosk[lane] = ~0ull;
+    }
+    if (lane == 0) {
+      sm.scan.found = 0;
+      sm.min_t = -1;
+    }
     __syncwarp();
+    // stage 1: values
     for (int t = lane; t < n; t += 32) {
       const float *q = normals + (size_t)key_orig(sm.key[t]) * 4;
       const float nv[3] = {q[0], q[1], q[2]};
       const float nc = dot3f(z, nv);
       sm.f_cos[t] = nc;
-      const float d2t = key_d2(sm.key[t]);
+      const bool in_margin = key_d2(sm.key[t]) > margin_distance2;
       float ang = 0.f;
-      if (a.find_holes && d2t > margin_distance2) {
+      if (a.find_holes && in_margin) {
         const float4 p = pts[sm.pos[t]];
         const float pv[3] = {p.x, p.y, p.z};
         float ind[3];
         directed_orthogonal_axis(z, c, pv, ind);
         ang = angle_between_unit(xr, ind, z);
       }
-      board_scan_point(sm.scan, t, d2t, ang, nc, margin_distance2, max_boundary_angle, S, a.find_holes != 0);
+      sm.f_ang[t] = ang;
+      if (in_margin) sm.scan.found = 1;
+      if (nc == nc) atomicMin(&sm.scan.cosv[in_margin ? 0 : 1], board_ord(nc));
+      if (a.find_holes && in_margin && ang == ang) {  // PCL indexes out of range for a NaN direction
+        const int b = min((int)floorf(ang / max_boundary_angle), S - 1);
+        atomicMin(&sm.scan.mnv[b], __float_as_uint(ang));
+        atomicMax(&sm.scan.mxv[b], __float_as_uint(ang));
+      }
     }
     __syncwarp();
+    // stage 2: among the points reaching an extreme, the smallest (d2, index) key
+    for (int t = lane; t < n; t += 32) {
+      const float nc = sm.f_cos[t], ang = sm.f_ang[t];
+      const unsigned long long kt = sm.key[t];
+      const bool in_margin = key_d2(kt) > margin_distance2;
+      if (nc == nc && board_ord(nc) == sm.scan.cosv[in_margin ? 0 : 1]) atomicMin(&sm.scan.cosk[in_margin ? 0 : 1], kt);
+      if (a.find_holes && in_margin && ang == ang) {
+        const int b = min((int)floorf(ang / max_boundary_angle), S - 1);
+        if (__float_as_uint(ang) == sm.scan.mnv[b]) atomicMin(&sm.scan.mnk[b], kt);
+        if (__float_as_uint(ang) == sm.scan.mxv[b]) atomicMin(&sm.scan.mxk[b], kt);
+      }
+    }
+    __syncwarp();
+    // stage 3: the winners leave what the sequential scans would have kept
+    const int cos_set = sm.scan.found ? 0 : 1;
+    for (int t = lane; t < n; t += 32) {
+      const float nc = sm.f_cos[t], ang = sm.f_ang[t];
+      const unsigned long long kt = sm.key[t];
+      const bool in_margin = key_d2(kt) > margin_distance2;
+      if ((in_margin ? 0 : 1) == cos_set && kt == sm.scan.cosk[cos_set]) sm.min_t = t;
+      if (a.find_holes && in_margin && ang == ang) {
+        const int b = min((int)floorf(ang / max_boundary_angle), S - 1);
+        if (kt == sm.scan.mnk[b]) sm.min_angle_normal[b] = nc;
+        if (kt == sm.scan.mxk[b]) sm.max_angle_normal[b] = nc;
+      }
+    }
     if (a.find_holes)
-      for (int sct = lane; sct < S; sct += 32)
-        board_scan_sector(sm.scan, sct, sm.f_cos, sm.check, sm.min_angle, sm.max_angle, sm.min_angle_normal,
-                          sm.max_angle_normal);
-    if (lane == 31) board_scan_min_cos(sm.scan, &sm.min_cos, &sm.min_t, &sm.margin_found);
+      for (int sct = lane; sct < S; sct += 32) {
+        const bool chk = sm.scan.mnv[sct] != 0xffffffffu;
+        sm.check[sct] = chk ? 1 : 0;
+        sm.min_angle[sct] = chk ? __uint_as_float(sm.scan.mnv[sct]) : FLT_MAX;
+        sm.max_angle[sct] = chk ? __uint_as_float(sm.scan.mxv[sct]) : -FLT_MAX;
+      }
+    if (lane == 31) {
+      sm.margin_found = sm.scan.found;
+      const unsigned cv = sm.scan.cosv[cos_set];
+      sm.min_cos = (sm.scan.cosk[cos_set] == ~0ull) ? FLT_MAX : board_unord(cv);
+    }
     __syncwarp();
     if (lane == 0) {
       const BoardSectors sec = {sm.check, sm.min_angle, sm.max_angle, sm.min_angle_normal, sm.max_angle_normal};
@@ -730,7 +772,9 @@ int dev_board_lrf(b200_ctx *ctx, b200_cloud *c, const float *d_normals, const fl
   const bool warp_path = !second && !(sel && !strcmp(sel, "cta"));
   int rc = B200_OK;
   if (warp_path) {
-    board_warp_kernel<<<std::min(ceil_div(K, BW_WARPS), ctx->sm_count * 16), BW_WARPS * 32, 0, ctx->stream>>>(
+    const size_t smem_w = sizeof(BwSmem) * BW_WARPS;
+    B200_CUDA(ctx, ensure_dyn_smem(board_warp_kernel, smem_w));
+    board_warp_kernel<<<std::min(ceil_div(K, BW_WARPS), ctx->sm_count * 16), BW_WARPS * 32, smem_w, ctx->stream>>>(
         *g, d_normals, d_kp, K, (float)radius, r2, a, counts.p, rank.p, rnd.p, d_rf);
     B200_LAUNCHED(ctx);
   }
